@@ -1,0 +1,1014 @@
+// K1 — the HBM-bound "site pass": one read of the int8 genotype matrix produces per-population allele
+// counts per site and reduces them into per-window sums.
+//
+//   mode POPGEN : closed-form pi / dxy / Fst sums (exact when a window has no partially-missing site;
+//                 otherwise the window is flagged "ragged" and routed to K2)   -- genomics.py:956-995
+//   mode ABBA   : ABBA / BABA / D / fd / fdM sums                             -- genomics.py:1647-1695
+//   mode COUNTS : per-site per-population A,C,G,T counts                      -- genomics.py:1049-1052
+//
+// Data path: a persistent CTA per SM owns a contiguous range of tiles; a tile is T
+// consecutive sites = one contiguous T*pitch byte range, brought into shared memory by 1-D TMA bulk copies
+// (cp.async.bulk ... mbarrier::complete_tx) through a `stages`-deep ring.  One lane (or G lanes) owns one
+// site row and walks it with conflict-free LDS.128; alleles are counted with SWAR byte-lane accumulators
+// (8 integer ops per 4 genotypes).  Per-lane running sums are flushed per (warp, segment) into private
+// slots — no atomics, deterministic — and a finalize kernel folds slots -> segments -> windows -> statistics.
+#include <algorithm>
+#include <cmath>
+
+#include "pgwin_internal.h"
+
+namespace {
+
+constexpr int K1_THREADS = 256;
+constexpr int K1_WARPS = K1_THREADS / 32;
+
+enum { MODE_POPGEN = 0, MODE_ABBA = 1, MODE_COUNTS = 2 };
+
+struct K1Params {
+    const uint8_t* geno;
+    const int32_t* pos;
+    int64_t site_begin, site_end;     // sites processed by this launch
+    int64_t num_tiles;
+    int pitch, G, I, T, stages, tile_bytes;
+    // hap -> pop tables (shared-memory copies are made at kernel start)
+    const int32_t* ent_chunk;
+    const uint4* ent_mask;
+    int n_ent;
+    int ent_lo[PG_MAX_K1_POPS], ent_hi[PG_MAX_K1_POPS], full_lo[PG_MAX_K1_POPS], full_hi[PG_MAX_K1_POPS];
+    int popN[PG_MAX_K1_POPS];
+    // segments / slots
+    const int64_t* brk;
+    int nseg;
+    const int32_t* cta_seg_first;
+    const int64_t* cta_slot_off;
+    unsigned long long* part;
+    // ABBA: minimum non-missing count per population (exact integer form of n/N >= minData)
+    int thr[4];
+    // COUNTS
+    uint16_t* counts_out;
+    int64_t counts_stride;   // uint16 elements per site
+    int counts_pops;         // populations actually written (<= P)
+};
+
+// ---- PTX helpers: mbarrier + 1-D TMA bulk copy -------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+
+// ---- SWAR allele counting ----------------------------------------------------------------------
+// w: 4 genotype bytes (0..3, bit7 = missing); m: 0x01 in the byte lanes that belong to the population.
+// Byte-lane accumulators: av += valid, a0 += bit0, a1 += bit1, a01 += bit0&bit1   (all masked by valid).
+struct Lanes4 {
+    uint32_t v, e0, e1, e01;
+};
+__device__ __forceinline__ Lanes4 swar(uint32_t w, uint32_t m) {
+    Lanes4 r;
+    r.v = ~(w >> 7) & m;
+    r.e0 = w & r.v;
+    r.e1 = (w >> 1) & r.v;
+    r.e01 = r.e0 & r.e1;
+    return r;
+}
+#define K1_ACC_CHUNK(W, MX, MY, MZ, MW)                 \
+    {                                                   \
+        Lanes4 x = swar((W).x, (MX)), y = swar((W).y, (MY)); \
+        av += x.v + y.v;                                \
+        a0 += x.e0 + y.e0;                              \
+        a1 += x.e1 + y.e1;                              \
+        a01 += x.e01 + y.e01;                           \
+        Lanes4 z = swar((W).z, (MZ)), u = swar((W).w, (MW)); \
+        av += z.v + u.v;                                \
+        a0 += z.e0 + u.e0;                              \
+        a1 += z.e1 + u.e1;                              \
+        a01 += z.e01 + u.e01;                           \
+    }
+__device__ __forceinline__ uint32_t hsum4(uint32_t x, uint32_t acc) { return __dp4a(x, 0x01010101u, acc); }
+
+template <int QI, int QD>
+struct Acc {
+    long long i[QI > 0 ? QI : 1];
+    double d[QD > 0 ? QD : 1];
+};
+
+// Warp-cooperative flush of the per-lane running sums into this warp's private slots.
+template <int QI, int QD>
+__device__ __forceinline__ void warp_flush(Acc<QI, QD>& acc, int cur_seg, unsigned long long* part, int64_t slot_base,
+                                           int seg_first, int warp, int lane) {
+    constexpr int Q = QI + QD;
+    unsigned pending = __ballot_sync(0xffffffffu, cur_seg >= 0);
+    while (pending) {
+        const int leader = __ffs(pending) - 1;
+        const int g = __shfl_sync(0xffffffffu, cur_seg, leader);
+        const bool mine = (cur_seg == g);
+        unsigned long long* dst = part + slot_base + ((int64_t)(g - seg_first) * K1_WARPS + warp) * Q;
+#pragma unroll
+        for (int q = 0; q < QI; ++q) {
+            long long v = mine ? acc.i[q] : 0ll;
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+            if (lane == 0) dst[q] = (unsigned long long)((long long)dst[q] + v);
+            if (mine) acc.i[q] = 0;
+        }
+#pragma unroll
+        for (int q = 0; q < QD; ++q) {
+            double v = mine ? acc.d[q] : 0.0;
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);   // fixed butterfly order
+            if (lane == 0) dst[QI + q] = (unsigned long long)__double_as_longlong(__longlong_as_double((long long)dst[QI + q]) + v);
+            if (mine) acc.d[q] = 0.0;
+        }
+        pending &= ~__ballot_sync(0xffffffffu, mine);
+    }
+}
+
+__device__ __forceinline__ int find_seg(const int64_t* __restrict__ brk, int nseg, int from, int64_t site) {
+    int lo = from, hi = nseg - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (__ldg(brk + mid) <= site) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+template <int MODE, int P>
+struct ModeTraits;
+template <int P>
+struct ModeTraits<MODE_POPGEN, P> {
+    static constexpr int QI = 3 + P + P * (P - 1) / 2, QD = 0;
+};
+template <int P>
+struct ModeTraits<MODE_ABBA, P> {
+    static constexpr int QI = 3, QD = 6;
+};
+template <int P>
+struct ModeTraits<MODE_COUNTS, P> {
+    static constexpr int QI = 0, QD = 0;
+};
+
+template <int MODE, int P>
+__global__ void __launch_bounds__(K1_THREADS, 1) k1_site_pass(const __grid_constant__ K1Params prm) {
+    constexpr int QI = ModeTraits<MODE, P>::QI, QD = ModeTraits<MODE, P>::QD;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* tiles = smem;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)prm.stages * prm.tile_bytes);   // [stages]
+    uint4* s_ent_mask = reinterpret_cast<uint4*>(smem + (size_t)prm.stages * prm.tile_bytes + 256);
+    int32_t* s_ent_chunk = reinterpret_cast<int32_t*>(s_ent_mask + prm.n_ent);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.x, B = gridDim.x;
+    const int64_t t0 = (int64_t)b * prm.num_tiles / B, t1 = (int64_t)(b + 1) * prm.num_tiles / B;
+
+    for (int e = tid; e < prm.n_ent; e += K1_THREADS) {
+        s_ent_mask[e] = prm.ent_mask[e];
+        s_ent_chunk[e] = prm.ent_chunk[e];
+    }
+    if (tid == 0) {
+        for (int s = 0; s < prm.stages; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issue = [&](int64_t t, int stage) {
+        const int64_t s_lo = prm.site_begin + t * prm.T;
+        int64_t rows = prm.site_end - s_lo;
+        if (rows > prm.T) rows = prm.T;
+        const uint32_t bytes = (uint32_t)(rows * prm.pitch);
+        mbar_expect_tx(&full[stage], bytes);
+        const uint8_t* src = prm.geno + s_lo * prm.pitch;
+        uint8_t* dst = tiles + (size_t)stage * prm.tile_bytes;
+        for (uint32_t off = 0; off < bytes; off += 32768u) {
+            const uint32_t n = (bytes - off) < 32768u ? (bytes - off) : 32768u;
+            bulk_g2s(dst + off, src + off, n, &full[stage]);
+        }
+    };
+    if (tid == 0)
+        for (int s = 0; s < prm.stages; ++s)
+            if (t0 + s < t1) issue(t0 + s, s);
+
+    // lane -> (site slot, sub-lane) mapping: the 32/G sites of a warp are contiguous in `sl`, the G lanes of
+    // one site are spw apart so that the 8 lanes of an LDS.128 phase read 8 different rows (odd chunk pitch).
+    const int G = prm.G;
+    const int spw = 32 / G;
+    const int gsub = lane / spw;
+    const int sl = lane % spw;
+    const int sites_per_iter = K1_THREADS / G;
+
+    Acc<QI, QD> acc;
+#pragma unroll
+    for (int q = 0; q < QI; ++q) acc.i[q] = 0;
+#pragma unroll
+    for (int q = 0; q < QD; ++q) acc.d[q] = 0.0;
+    int cur_seg = -1;
+    int64_t seg_end = -1;
+    const int seg_first = (MODE == MODE_COUNTS) ? 0 : prm.cta_seg_first[b];
+    const int64_t slot_base = (MODE == MODE_COUNTS) ? 0 : prm.cta_slot_off[b];
+
+    for (int64_t t = t0; t < t1; ++t) {
+        const int it = (int)(t - t0);
+        const int stage = it % prm.stages;
+        const uint32_t parity = (uint32_t)((it / prm.stages) & 1);
+        mbar_wait(&full[stage], parity);
+        const uint8_t* tile = tiles + (size_t)stage * prm.tile_bytes;
+        const int64_t tile_site0 = prm.site_begin + t * prm.T;
+
+        for (int i = 0; i < prm.I; ++i) {
+            const int slot = i * sites_per_iter + warp * spw + sl;
+            const int64_t site = tile_site0 + slot;
+            const bool valid = site < prm.site_end;
+            const uint4* row = reinterpret_cast<const uint4*>(tile + (size_t)(valid ? slot : 0) * prm.pitch);
+
+            uint32_t n[P], c[P][4];
+#pragma unroll
+            for (int X = 0; X < P; ++X) {
+                uint32_t tn = 0, ts0 = 0, ts1 = 0, ts01 = 0;
+                // full 16-byte chunks of the population's main contiguous run (no mask loads)
+                {
+                    int ch = prm.full_lo[X] + gsub;
+                    const int hi = prm.full_hi[X];
+                    while (ch < hi) {
+                        uint32_t av = 0, a0 = 0, a1 = 0, a01 = 0;
+                        int end = ch + 60 * G;           // byte lanes hold <= 4 per chunk: flush before 255
+                        if (end > hi) end = hi;
+#pragma unroll 2
+                        for (; ch < end; ch += G) {
+                            const uint4 w = row[ch];
+                            K1_ACC_CHUNK(w, 0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u)
+                        }
+                        tn = hsum4(av, tn);
+                        ts0 = hsum4(a0, ts0);
+                        ts1 = hsum4(a1, ts1);
+                        ts01 = hsum4(a01, ts01);
+                    }
+                }
+                // chunks shared with other populations / unused haplotypes / row padding: masked
+                {
+                    int e = prm.ent_lo[X] + gsub;
+                    const int hi = prm.ent_hi[X];
+                    while (e < hi) {
+                        uint32_t av = 0, a0 = 0, a1 = 0, a01 = 0;
+                        int end = e + 60 * G;
+                        if (end > hi) end = hi;
+                        for (; e < end; e += G) {
+                            const uint4 m = s_ent_mask[e];
+                            const uint4 w = row[s_ent_chunk[e]];
+                            K1_ACC_CHUNK(w, m.x, m.y, m.z, m.w)
+                        }
+                        tn = hsum4(av, tn);
+                        ts0 = hsum4(a0, ts0);
+                        ts1 = hsum4(a1, ts1);
+                        ts01 = hsum4(a01, ts01);
+                    }
+                }
+                // combine the G lanes of this site (16-bit fields: counts < 65536)
+                uint32_t p0 = tn | (ts0 << 16), p1 = ts1 | (ts01 << 16);
+                for (int d = spw; d < 32; d <<= 1) {
+                    p0 += __shfl_xor_sync(0xffffffffu, p0, d);
+                    p1 += __shfl_xor_sync(0xffffffffu, p1, d);
+                }
+                tn = p0 & 0xffffu;
+                ts0 = p0 >> 16;
+                ts1 = p1 & 0xffffu;
+                ts01 = p1 >> 16;
+                n[X] = tn;
+                c[X][3] = ts01;
+                c[X][1] = ts0 - ts01;
+                c[X][2] = ts1 - ts01;
+                c[X][0] = tn - ts0 - ts1 + ts01;
+            }
+
+            const bool owner = valid && (gsub == 0);
+
+            if (MODE == MODE_COUNTS) {
+                if (owner) {
+                    uint16_t* o = prm.counts_out + (site - prm.site_begin) * prm.counts_stride;
+#pragma unroll
+                    for (int X = 0; X < P; ++X)
+                        if (X < prm.counts_pops) {
+                            ushort4 v = make_ushort4((unsigned short)c[X][0], (unsigned short)c[X][1],
+                                                     (unsigned short)c[X][2], (unsigned short)c[X][3]);
+                            *reinterpret_cast<ushort4*>(o + X * 4) = v;
+                        }
+                }
+                continue;
+            }
+
+            // ---- segment bookkeeping (warp-uniform control flow) ----
+            int sg = cur_seg;
+            if (owner && site >= seg_end) sg = find_seg(prm.brk, prm.nseg, cur_seg + 1, site);
+            if (__any_sync(0xffffffffu, sg != cur_seg)) {
+                warp_flush<QI, QD>(acc, cur_seg, prm.part, slot_base, seg_first, warp, lane);
+                if (sg != cur_seg) {
+                    cur_seg = sg;
+                    seg_end = __ldg(prm.brk + sg + 1);
+                }
+            }
+
+            if (MODE == MODE_POPGEN) {
+                bool allpres = true, allmiss = true;
+#pragma unroll
+                for (int X = 0; X < P; ++X) {
+                    allpres = allpres && (n[X] == (uint32_t)prm.popN[X]);
+                    allmiss = allmiss && (n[X] == 0u);
+                }
+                const bool pres = owner && allpres;
+                const bool ragged = owner && !allpres && !allmiss;
+                acc.i[0] += pres ? 1 : 0;
+                acc.i[1] += ragged ? 1 : 0;
+                acc.i[2] += owner ? (long long)__ldg(prm.pos + site) : 0ll;
+                const uint32_t f = pres ? 1u : 0u;
+#pragma unroll
+                for (int X = 0; X < P; ++X) {
+                    const uint32_t sq = c[X][0] * c[X][0] + c[X][1] * c[X][1] + c[X][2] * c[X][2] + c[X][3] * c[X][3];
+                    acc.i[3 + X] += (long long)(sq * f);
+                }
+                int k = 0;
+#pragma unroll
+                for (int X = 0; X < P; ++X)
+#pragma unroll
+                    for (int Y = X + 1; Y < P; ++Y) {
+                        const uint32_t cr = c[X][0] * c[Y][0] + c[X][1] * c[Y][1] + c[X][2] * c[Y][2] + c[X][3] * c[Y][3];
+                        acc.i[3 + P + k] += (long long)(cr * f);
+                        ++k;
+                    }
+            }
+
+            if (MODE == MODE_ABBA) {
+                // genomics.py:1655-1662: biallelic over P1+P2+P3+O and enough data in each population
+                uint32_t tot[4];
+                int nall = 0;
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    tot[a] = c[0][a] + c[1][a] + c[2][a] + c[3][a];
+                    nall += tot[a] > 0 ? 1 : 0;
+                }
+                bool good = owner && (nall == 2);
+#pragma unroll
+                for (int X = 0; X < 4; ++X) good = good && ((int)n[X] >= prm.thr[X]);
+                acc.i[1] += good ? 1 : 0;
+                acc.i[2] += owner ? (long long)__ldg(prm.pos + site) : 0ll;
+                if (good && n[3] > 0) {
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) {
+                        if (tot[a] > 0 && c[3][a] == 0) {   // derived: present overall, absent in the outgroup (1672)
+                            const double p1 = (double)c[0][a] / (double)n[0];
+                            const double p2 = (double)c[1][a] / (double)n[1];
+                            const double p3 = (double)c[2][a] / (double)n[2];
+                            const double p4 = (double)c[3][a] / (double)n[3];
+                            const double abba = (1 - p1) * p2 * p3 * (1 - p4);
+                            const double baba = p1 * (1 - p2) * p3 * (1 - p4);
+                            const double pd = p2 * (p2 > p3 ? 1.0 : 0.0) + p3 * (p3 >= p2 ? 1.0 : 0.0);
+                            const double fd_den = (1 - p1) * pd * pd * (1 - p4) - p1 * (1 - pd) * pd * (1 - p4);
+                            const bool A = p3 > p1, Bq = p3 > p2, Xq = p1 > p2, Yq = !Xq;
+                            const double xa = (Xq && A) ? 1.0 : 0.0, yb = (Yq && Bq) ? 1.0 : 0.0;
+                            const double xna = (Xq && !A) ? 1.0 : 0.0, ynb = (Yq && !Bq) ? 1.0 : 0.0;
+                            const double pdm1 = p3 * xa + p1 * (1.0 - xa);
+                            const double pdm2 = p3 * yb + p2 * (1.0 - yb);
+                            const double pdm3 = -p3 * xa + p3 * yb - p1 * xna + p2 * ynb;
+                            const double fdm_den =
+                                (1 - pdm1) * pdm2 * pdm3 * (1 - p4) - pdm1 * (1 - pdm2) * pdm3 * (1 - p4);
+                            acc.i[0] += 1;
+                            acc.d[0] += abba;
+                            acc.d[1] += baba;
+                            acc.d[2] += abba - baba;
+                            acc.d[3] += abba + baba;
+                            acc.d[4] += fd_den;
+                            acc.d[5] += fdm_den;
+                        }
+                    }
+                }
+            }
+        }
+
+        __syncthreads();   // every lane is done with this stage's bytes
+        if (tid == 0 && t + prm.stages < t1) issue(t + prm.stages, stage);
+    }
+    if (MODE != MODE_COUNTS) warp_flush<QI, QD>(acc, cur_seg, prm.part, slot_base, seg_first, warp, lane);
+}
+
+// ---- finalize: slots -> segments -> windows -> statistics ------------------------------------------
+struct FinParams {
+    const unsigned long long* part;
+    const int32_t* seg_cta_lo;     // [nseg] first CTA touching the segment
+    const int32_t* seg_cta_hi;     // [nseg] last CTA (inclusive)
+    const int32_t* cta_seg_first;  // [ctas]
+    const int64_t* cta_slot_off;   // [ctas]
+    const int32_t* win_seg_lo;     // [W]
+    const int32_t* win_seg_hi;     // [W]
+    const int64_t* win_lo;
+    const int64_t* win_hi;
+    int64_t W;
+    int Q, QI;
+    int P;                         // real population count
+    int Ppad;                      // template P used by the site pass
+    int popN[PG_MAX_K1_POPS];
+    int min_sites;
+    double min_data;
+    int force_path;
+    // outputs
+    double* pi;
+    double* dxy;
+    double* fst;
+    double* abba_out;              // [W x 5]
+    double* sites_used;
+    long long* n_sites;
+    long long* pos_sum;
+    int32_t* path;
+};
+
+__device__ __forceinline__ double nan_d() { return __longlong_as_double(0x7ff8000000000000ll); }
+
+// mean over the off-diagonal entries of an N x N block whose pairs all have n_ij = Lp
+__device__ __forceinline__ double cf_pi(long long N, long long Lp, long long sumsq, bool all_nan, double min_data) {
+    if (N <= 0) return nan_d();
+    const double size = (double)(N * N);
+    const double nan_cnt = all_nan ? size : (double)N;
+    if (1.0 - (1.0 * nan_cnt / size) < min_data) return nan_d();      // nanmean_min, genomics.py:88-90
+    if (all_nan) return nan_d();
+    const double num = (double)(N * N * Lp - sumsq);
+    const double den = (double)((N * N - N) * Lp);
+    return num / den;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(64) k1_finalize(const __grid_constant__ FinParams fp) {
+    __shared__ unsigned long long sums[64];
+    const int q = threadIdx.x;
+    for (int64_t w = blockIdx.x; w < fp.W; w += gridDim.x) {
+        __syncthreads();
+        if (q < fp.Q) {
+            long long si = 0;
+            double sd = 0.0;
+            for (int g = fp.win_seg_lo[w]; g < fp.win_seg_hi[w]; ++g) {
+                for (int b = fp.seg_cta_lo[g]; b <= fp.seg_cta_hi[g]; ++b) {
+                    const unsigned long long* src =
+                        fp.part + fp.cta_slot_off[b] + (int64_t)(g - fp.cta_seg_first[b]) * K1_WARPS * fp.Q;
+                    for (int wp = 0; wp < K1_WARPS; ++wp) {
+                        const unsigned long long v = src[wp * fp.Q + q];
+                        if (q < fp.QI) si += (long long)v; else sd += __longlong_as_double((long long)v);
+                    }
+                }
+            }
+            sums[q] = (q < fp.QI) ? (unsigned long long)si : (unsigned long long)__double_as_longlong(sd);
+        }
+        __syncthreads();
+        if (q != 0) continue;
+        const long long sites = fp.win_hi[w] - fp.win_lo[w];
+        fp.n_sites[w] = sites;
+        fp.pos_sum[w] = (long long)sums[2];
+        if (MODE == MODE_POPGEN) {
+            const int P = fp.P, Pp = fp.Ppad;
+            const int npairs = P * (P - 1) / 2;
+            const long long Lp = (long long)sums[0];
+            const bool ragged = (long long)sums[1] > 0;
+            int path = 1;
+            if (sites < fp.min_sites) path = 0;
+            else if (ragged || fp.force_path == 2) path = 2;
+            fp.path[w] = path;
+            if (path != 1) {
+                for (int x = 0; x < P; ++x) fp.pi[w * P + x] = nan_d();
+                for (int k = 0; k < npairs; ++k) fp.dxy[w * npairs + k] = fp.fst[w * npairs + k] = nan_d();
+                continue;
+            }
+            const bool all_nan = (Lp == 0) || (fp.min_sites > 0 && Lp < fp.min_sites);
+            double piv[PG_MAX_K1_POPS];
+            for (int x = 0; x < P; ++x) {
+                piv[x] = cf_pi(fp.popN[x], Lp, (long long)sums[3 + x], all_nan, fp.min_data);
+                fp.pi[w * P + x] = piv[x];
+            }
+            int k = 0;
+            for (int x = 0; x < P; ++x)
+                for (int y = x + 1; y < P; ++y) {
+                    // index of (x,y) in the padded pair enumeration of the site pass
+                    int kp = 0;
+                    for (int xx = 0; xx < x; ++xx) kp += Pp - 1 - xx;
+                    kp += y - x - 1;
+                    const long long cross = (long long)sums[3 + Pp + kp];
+                    const long long Nx = fp.popN[x], Ny = fp.popN[y];
+                    double dxy = nan_d();
+                    {
+                        const double size = (double)(Nx * Ny);
+                        const double nan_cnt = all_nan ? size : 0.0;
+                        const bool frac_bad = (1.0 - (1.0 * nan_cnt / size) < fp.min_data);
+                        if (!frac_bad && !all_nan) dxy = (double)(Nx * Ny * Lp - cross) / (double)(Nx * Ny * Lp);
+                    }
+                    const long long sq_t = (long long)sums[3 + x] + (long long)sums[3 + y] + 2 * cross;
+                    const double pi_t = cf_pi(Nx + Ny, Lp, sq_t, all_nan, fp.min_data);
+                    const double wgt = 1.0 * (double)Nx / (double)(Nx + Ny);
+                    const double pi_s = wgt * piv[x] + (1 - wgt) * piv[y];
+                    fp.dxy[w * npairs + k] = dxy;
+                    fp.fst[w * npairs + k] = 1 - pi_s / pi_t;
+                    ++k;
+                }
+        } else {   // MODE_ABBA
+            const long long used = (long long)sums[0], n_good = (long long)sums[1];
+            double* o = fp.abba_out + w * 5;
+            if (n_good < 1) {   // genomics.py:1694-1695: every value nan, sitesUsed included
+                for (int k = 0; k < 5; ++k) o[k] = nan_d();
+                fp.sites_used[w] = nan_d();
+                continue;
+            }
+            const double s_abba = __longlong_as_double((long long)sums[3]), s_baba = __longlong_as_double((long long)sums[4]);
+            const double s_f4 = __longlong_as_double((long long)sums[5]), s_ab = __longlong_as_double((long long)sums[6]);
+            const double s_fd = __longlong_as_double((long long)sums[7]), s_fdm = __longlong_as_double((long long)sums[8]);
+            o[0] = s_abba;
+            o[1] = s_baba;
+            o[2] = s_f4 * 1.0 / s_ab;
+            o[3] = s_f4 * 1.0 / s_fd;
+            o[4] = s_f4 * 1.0 / s_fdm;
+            fp.sites_used[w] = (double)used;
+        }
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+struct PopTables {
+    std::vector<int32_t> ent_chunk;
+    std::vector<uint32_t> ent_mask;   // 4 words per entry
+    int ent_lo[PG_MAX_K1_POPS], ent_hi[PG_MAX_K1_POPS], full_lo[PG_MAX_K1_POPS], full_hi[PG_MAX_K1_POPS];
+    int popN[PG_MAX_K1_POPS];
+};
+
+// hap_pop_local[h] in [0, Ppad) or -1
+void build_tables(const std::vector<int32_t>& hap_pop_local, int H, int chunks, int Ppad, PopTables& t) {
+    t.ent_chunk.clear();
+    t.ent_mask.clear();
+    for (int X = 0; X < PG_MAX_K1_POPS; ++X) t.ent_lo[X] = t.ent_hi[X] = t.full_lo[X] = t.full_hi[X] = t.popN[X] = 0;
+    for (int X = 0; X < Ppad; ++X) {
+        std::vector<uint16_t> cm(chunks, 0);
+        int N = 0;
+        for (int h = 0; h < H; ++h)
+            if (hap_pop_local[h] == X) {
+                cm[h / 16] |= (uint16_t)(1u << (h % 16));
+                ++N;
+            }
+        t.popN[X] = N;
+        // longest run of completely-owned chunks
+        int best_lo = 0, best_hi = 0, run_lo = -1;
+        for (int cidx = 0; cidx <= chunks; ++cidx) {
+            const bool fullc = cidx < chunks && cm[cidx] == 0xffff;
+            if (fullc && run_lo < 0) run_lo = cidx;
+            if (!fullc && run_lo >= 0) {
+                if (cidx - run_lo > best_hi - best_lo) {
+                    best_lo = run_lo;
+                    best_hi = cidx;
+                }
+                run_lo = -1;
+            }
+        }
+        t.full_lo[X] = best_lo;
+        t.full_hi[X] = best_hi;
+        t.ent_lo[X] = (int)t.ent_chunk.size();
+        for (int cidx = 0; cidx < chunks; ++cidx) {
+            if (cm[cidx] == 0) continue;
+            if (cidx >= best_lo && cidx < best_hi) continue;
+            t.ent_chunk.push_back(cidx);
+            for (int wd = 0; wd < 4; ++wd) {
+                uint32_t m = 0;
+                for (int by = 0; by < 4; ++by)
+                    if (cm[cidx] & (1u << (wd * 4 + by))) m |= 0x01u << (8 * by);
+                t.ent_mask.push_back(m);
+            }
+        }
+        t.ent_hi[X] = (int)t.ent_chunk.size();
+    }
+}
+
+struct K1Launch {
+    K1Plan plan;
+    K1Params prm;
+    std::vector<int32_t> cta_seg_first, seg_cta_lo, seg_cta_hi;
+    std::vector<int64_t> cta_slot_off;
+    int64_t total_slots = 0;   // 8-byte words
+};
+
+int seg_of(const std::vector<int64_t>& brk, int64_t site) {
+    // brk[g] <= site < brk[g+1]
+    return (int)(std::upper_bound(brk.begin(), brk.end(), site) - brk.begin()) - 1;
+}
+
+// device layout of the uploaded tables inside ctx->tables:
+//   [ent_mask (16B each)] [ent_chunk] [brk] [cta_seg_first] [cta_slot_off] [seg_cta_lo] [seg_cta_hi]
+//   [win_seg_lo] [win_seg_hi] [win_lo] [win_hi]
+struct DevTables {
+    uint4* ent_mask;
+    int32_t* ent_chunk;
+    int64_t* brk;
+    int32_t* cta_seg_first;
+    int64_t* cta_slot_off;
+    int32_t* seg_cta_lo;
+    int32_t* seg_cta_hi;
+    int32_t* win_seg_lo;
+    int32_t* win_seg_hi;
+    int64_t* win_lo;
+    int64_t* win_hi;
+};
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+template <typename T>
+int push(pg_ctx* ctx, uint8_t* base, size_t& off, const T* src, size_t n, T** out) {
+    off = align_up(off, 16);
+    *out = reinterpret_cast<T*>(base + off);
+    if (n) PG_CUDA(cudaMemcpyAsync(base + off, src, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    off += n * sizeof(T);
+    return PG_OK;
+}
+
+// Common preparation for the windowed modes: tables, segments, slot layout, zeroed slots.
+int prepare_windowed(pg_ctx* ctx, const std::vector<int32_t>& hap_pop_local, int Ppad, int Q, K1Launch& L,
+                     DevTables& dt, PopTables& pt) {
+    PG_TRY(pg_build_segments(ctx));
+    build_tables(hap_pop_local, ctx->H, ctx->pitch / 16, Ppad, pt);
+    const int n_ent = (int)pt.ent_chunk.size();
+    const int table_bytes = n_ent * 20 + 64;
+    PG_CHECK(table_bytes <= 48 * 1024, "population layout needs %d bytes of mask tables (limit 48 KiB)", table_bytes);
+    L.plan = pg_make_k1_plan(ctx->S, ctx->H, ctx->sm_count, table_bytes);
+    PG_CHECK(L.plan.stages >= 2, "rows of %d haplotypes are too long for the site-pass kernel (pitch %d bytes)", ctx->H,
+             L.plan.pitch);
+    const K1Plan& pl = L.plan;
+    const int B = pl.ctas;
+    const int nseg = (int)ctx->brk.size() - 1;
+    L.cta_seg_first.assign(B, 0);
+    L.cta_slot_off.assign(B, 0);
+    L.seg_cta_lo.assign(std::max(nseg, 1), 0);
+    L.seg_cta_hi.assign(std::max(nseg, 1), -1);
+    std::vector<int> cta_seg_last(B, -1);
+    int64_t off = 0;
+    for (int b = 0; b < B; ++b) {
+        const int64_t t0 = (int64_t)b * pl.num_tiles / B, t1 = (int64_t)(b + 1) * pl.num_tiles / B;
+        const int64_t s0 = t0 * pl.T, s1 = std::min<int64_t>(t1 * pl.T, ctx->S);
+        L.cta_slot_off[b] = off;
+        if (s1 <= s0) {
+            L.cta_seg_first[b] = 0;
+            cta_seg_last[b] = -1;
+            continue;
+        }
+        const int g0 = seg_of(ctx->brk, s0), g1 = seg_of(ctx->brk, s1 - 1);
+        L.cta_seg_first[b] = g0;
+        cta_seg_last[b] = g1;
+        off += (int64_t)(g1 - g0 + 1) * K1_WARPS * Q;
+    }
+    L.total_slots = off;
+    // per segment: contiguous CTA range touching it
+    {
+        for (int g = 0; g < nseg; ++g) {
+            L.seg_cta_lo[g] = B;
+            L.seg_cta_hi[g] = -1;
+        }
+        for (int b = 0; b < B; ++b) {
+            if (cta_seg_last[b] < 0) continue;
+            for (int g = L.cta_seg_first[b]; g <= cta_seg_last[b]; ++g) {
+                L.seg_cta_lo[g] = std::min(L.seg_cta_lo[g], b);
+                L.seg_cta_hi[g] = std::max(L.seg_cta_hi[g], b);
+            }
+        }
+    }
+    // upload tables
+    size_t bytes = 4096 + pt.ent_mask.size() * 4 + pt.ent_chunk.size() * 4 + ctx->brk.size() * 8 + (size_t)B * 12 +
+                   (size_t)std::max(nseg, 1) * 8 + (size_t)ctx->W * 24 + 16 * 16;
+    PG_TRY(ctx->tables.ensure(bytes));
+    uint8_t* base = (uint8_t*)ctx->tables.p;
+    size_t o = 0;
+    uint32_t* d_mask_words = nullptr;
+    PG_TRY(push(ctx, base, o, pt.ent_mask.data(), pt.ent_mask.size(), &d_mask_words));
+    dt.ent_mask = reinterpret_cast<uint4*>(d_mask_words);
+    PG_TRY(push(ctx, base, o, pt.ent_chunk.data(), pt.ent_chunk.size(), &dt.ent_chunk));
+    PG_TRY(push(ctx, base, o, ctx->brk.data(), ctx->brk.size(), &dt.brk));
+    PG_TRY(push(ctx, base, o, L.cta_seg_first.data(), L.cta_seg_first.size(), &dt.cta_seg_first));
+    PG_TRY(push(ctx, base, o, L.cta_slot_off.data(), L.cta_slot_off.size(), &dt.cta_slot_off));
+    PG_TRY(push(ctx, base, o, L.seg_cta_lo.data(), L.seg_cta_lo.size(), &dt.seg_cta_lo));
+    PG_TRY(push(ctx, base, o, L.seg_cta_hi.data(), L.seg_cta_hi.size(), &dt.seg_cta_hi));
+    PG_TRY(push(ctx, base, o, ctx->win_seg_lo.data(), ctx->win_seg_lo.size(), &dt.win_seg_lo));
+    PG_TRY(push(ctx, base, o, ctx->win_seg_hi.data(), ctx->win_seg_hi.size(), &dt.win_seg_hi));
+    PG_TRY(push(ctx, base, o, ctx->win_lo.data(), ctx->win_lo.size(), &dt.win_lo));
+    PG_TRY(push(ctx, base, o, ctx->win_hi.data(), ctx->win_hi.size(), &dt.win_hi));
+    PG_CHECK(o <= ctx->tables.cap, "internal: table buffer overflow");
+    // slots
+    PG_TRY(ctx->part.ensure((size_t)std::max<int64_t>(L.total_slots, 1) * 8));
+    PG_CUDA(cudaMemsetAsync(ctx->part.p, 0, (size_t)std::max<int64_t>(L.total_slots, 1) * 8, ctx->stream));
+
+    K1Params& p = L.prm;
+    memset(&p, 0, sizeof(p));
+    p.geno = (const uint8_t*)ctx->d_geno;
+    p.pos = ctx->d_pos;
+    p.site_begin = 0;
+    p.site_end = ctx->S;
+    p.num_tiles = pl.num_tiles;
+    p.pitch = pl.pitch;
+    p.G = pl.G;
+    p.I = pl.I;
+    p.T = pl.T;
+    p.stages = pl.stages;
+    p.tile_bytes = pl.tile_bytes;
+    p.ent_chunk = dt.ent_chunk;
+    p.ent_mask = dt.ent_mask;
+    p.n_ent = n_ent;
+    for (int X = 0; X < PG_MAX_K1_POPS; ++X) {
+        p.ent_lo[X] = pt.ent_lo[X];
+        p.ent_hi[X] = pt.ent_hi[X];
+        p.full_lo[X] = pt.full_lo[X];
+        p.full_hi[X] = pt.full_hi[X];
+        p.popN[X] = pt.popN[X];
+    }
+    p.brk = dt.brk;
+    p.nseg = nseg;
+    p.cta_seg_first = dt.cta_seg_first;
+    p.cta_slot_off = dt.cta_slot_off;
+    p.part = (unsigned long long*)ctx->part.p;
+    return PG_OK;
+}
+
+template <int MODE, int P>
+int launch_site_pass(pg_ctx* ctx, const K1Launch& L, const char* name) {
+    auto kern = k1_site_pass<MODE, P>;
+    PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.plan.smem_bytes));
+    const int ti = pg_time_begin(ctx, name);
+    kern<<<L.plan.ctas, K1_THREADS, L.plan.smem_bytes, ctx->stream>>>(L.prm);
+    pg_time_end(ctx, ti);
+    PG_CUDA(cudaGetLastError());
+    return PG_OK;
+}
+
+int pad_pops(int P) { return P <= 2 ? 2 : (P <= 4 ? 4 : 8); }
+
+}  // namespace
+
+// ================================================================================================
+// pg_popgen
+// ================================================================================================
+extern "C" int pg_popgen(pg_ctx* ctx, int32_t min_sites, double min_data, int32_t force_path, double* pi, double* dxy,
+                         double* fst, int64_t* n_sites, int64_t* pos_sum, int32_t* path) {
+    PG_CHECK(ctx && pi && dxy && fst && n_sites && pos_sum && path, "pg_popgen: null argument");
+    PG_CHECK(ctx->P >= 1, "pg_popgen: call pg_set_pops first");
+    PG_CHECK(force_path == 0 || force_path == 2, "pg_popgen: force_path must be 0 or 2");
+    PG_CUDA(cudaSetDevice(ctx->device));
+    pg_timings_reset(ctx);
+    const int P = ctx->P;
+    const int npairs = P * (P - 1) / 2;
+    const int64_t W = ctx->W;
+    if (W == 0) return PG_OK;
+    for (int x = 0; x < P; ++x) {
+        int N = 0;
+        for (int h = 0; h < ctx->H; ++h) N += ctx->hap_pop[h] == x;
+        PG_CHECK(N >= 1, "pg_popgen: population %d has no haplotypes", x);
+    }
+    std::vector<int64_t> k2_windows;
+    if (ctx->S == 0) {
+        for (int64_t w = 0; w < W; ++w) {
+            n_sites[w] = 0;
+            pos_sum[w] = 0;
+            path[w] = (0 < min_sites) ? 0 : 1;
+            for (int x = 0; x < P; ++x) pi[w * P + x] = NAN;
+            for (int k = 0; k < npairs; ++k) dxy[w * npairs + k] = fst[w * npairs + k] = NAN;
+        }
+        return PG_OK;
+    }
+    if (P <= PG_MAX_K1_POPS) {
+        const int Pp = pad_pops(P);
+        const int Q = 3 + Pp + Pp * (Pp - 1) / 2;
+        K1Launch L;
+        DevTables dt;
+        PopTables pt;
+        PG_TRY(prepare_windowed(ctx, ctx->hap_pop, Pp, Q, L, dt, pt));
+        if (Pp == 2) PG_TRY((launch_site_pass<MODE_POPGEN, 2>(ctx, L, "k1_popgen")));
+        else if (Pp == 4) PG_TRY((launch_site_pass<MODE_POPGEN, 4>(ctx, L, "k1_popgen")));
+        else PG_TRY((launch_site_pass<MODE_POPGEN, 8>(ctx, L, "k1_popgen")));
+
+        // outputs on device: pi | dxy | fst | n_sites | pos_sum | path
+        const size_t nd = (size_t)W * (P + 2 * npairs);
+        PG_TRY(ctx->out_d.ensure(nd * 8 + 64));
+        PG_TRY(ctx->out_i.ensure((size_t)W * (8 + 8 + 4) + 64));
+        FinParams fp;
+        memset(&fp, 0, sizeof(fp));
+        fp.part = (const unsigned long long*)ctx->part.p;
+        fp.seg_cta_lo = dt.seg_cta_lo;
+        fp.seg_cta_hi = dt.seg_cta_hi;
+        fp.cta_seg_first = dt.cta_seg_first;
+        fp.cta_slot_off = dt.cta_slot_off;
+        fp.win_seg_lo = dt.win_seg_lo;
+        fp.win_seg_hi = dt.win_seg_hi;
+        fp.win_lo = dt.win_lo;
+        fp.win_hi = dt.win_hi;
+        fp.W = W;
+        fp.Q = Q;
+        fp.QI = Q;
+        fp.P = P;
+        fp.Ppad = Pp;
+        for (int X = 0; X < PG_MAX_K1_POPS; ++X) fp.popN[X] = pt.popN[X];
+        fp.min_sites = min_sites;
+        fp.min_data = min_data;
+        fp.force_path = force_path;
+        double* d_out = (double*)ctx->out_d.p;
+        fp.pi = d_out;
+        fp.dxy = d_out + (size_t)W * P;
+        fp.fst = d_out + (size_t)W * (P + npairs);
+        long long* d_i = (long long*)ctx->out_i.p;
+        fp.n_sites = d_i;
+        fp.pos_sum = d_i + W;
+        fp.path = (int32_t*)(d_i + 2 * W);
+        const int ti = pg_time_begin(ctx, "k1_finalize");
+        k1_finalize<MODE_POPGEN><<<(unsigned)std::min<int64_t>(W, 65535), 64, 0, ctx->stream>>>(fp);
+        pg_time_end(ctx, ti);
+        PG_CUDA(cudaGetLastError());
+        PG_CUDA(cudaMemcpyAsync(pi, fp.pi, (size_t)W * P * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if (npairs) {
+            PG_CUDA(cudaMemcpyAsync(dxy, fp.dxy, (size_t)W * npairs * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            PG_CUDA(cudaMemcpyAsync(fst, fp.fst, (size_t)W * npairs * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        PG_CUDA(cudaMemcpyAsync(n_sites, fp.n_sites, (size_t)W * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        PG_CUDA(cudaMemcpyAsync(pos_sum, fp.pos_sum, (size_t)W * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        PG_CUDA(cudaMemcpyAsync(path, fp.path, (size_t)W * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        PG_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (int64_t w = 0; w < W; ++w)
+            if (path[w] == 2) k2_windows.push_back(w);
+    } else {
+        // more populations than K1 keeps in registers: bookkeeping on the host, statistics from K2
+        PG_CHECK(false, "pg_popgen: P=%d > %d populations is not supported yet", P, PG_MAX_K1_POPS);
+    }
+    if (!k2_windows.empty()) PG_TRY(pg_k2_popgen_windows(ctx, k2_windows, min_sites, min_data, pi, dxy, fst));
+    return PG_OK;
+}
+
+// ================================================================================================
+// pg_abbababa
+// ================================================================================================
+extern "C" int pg_abbababa(pg_ctx* ctx, int32_t p1, int32_t p2, int32_t p3, int32_t o, double min_data, double* out,
+                           double* sites_used, int64_t* n_sites, int64_t* pos_sum) {
+    PG_CHECK(ctx && out && sites_used && n_sites && pos_sum, "pg_abbababa: null argument");
+    PG_CHECK(ctx->P >= 1, "pg_abbababa: call pg_set_pops first");
+    const int sel[4] = {p1, p2, p3, o};
+    for (int k = 0; k < 4; ++k) {
+        PG_CHECK(sel[k] >= 0 && sel[k] < ctx->P, "pg_abbababa: population index %d out of range", sel[k]);
+        for (int j = 0; j < k; ++j) PG_CHECK(sel[j] != sel[k], "pg_abbababa: populations must be distinct");
+    }
+    PG_CUDA(cudaSetDevice(ctx->device));
+    pg_timings_reset(ctx);
+    const int64_t W = ctx->W;
+    if (W == 0) return PG_OK;
+    if (ctx->S == 0) {
+        for (int64_t w = 0; w < W; ++w) {
+            n_sites[w] = 0;
+            pos_sum[w] = 0;
+            sites_used[w] = NAN;
+            for (int k = 0; k < 5; ++k) out[w * 5 + k] = NAN;
+        }
+        return PG_OK;
+    }
+    std::vector<int32_t> local(ctx->H, -1);
+    for (int h = 0; h < ctx->H; ++h)
+        for (int k = 0; k < 4; ++k)
+            if (ctx->hap_pop[h] == sel[k]) local[h] = k;
+    const int Q = 9;
+    K1Launch L;
+    DevTables dt;
+    PopTables pt;
+    PG_TRY(prepare_windowed(ctx, local, 4, Q, L, dt, pt));
+    for (int k = 0; k < 4; ++k) {
+        PG_CHECK(pt.popN[k] >= 1, "pg_abbababa: population %d has no haplotypes", sel[k]);
+        // smallest n with (double)n / N >= minData  (genomics.py:1657-1660, exact in integers)
+        int thr = pt.popN[k] + 1;
+        for (int n = 0; n <= pt.popN[k]; ++n)
+            if ((double)n * 1.0 / (double)pt.popN[k] >= min_data) {
+                thr = n;
+                break;
+            }
+        L.prm.thr[k] = thr;
+    }
+    PG_TRY((launch_site_pass<MODE_ABBA, 4>(ctx, L, "k1_abba")));
+    PG_TRY(ctx->out_d.ensure((size_t)W * 6 * 8 + 64));
+    PG_TRY(ctx->out_i.ensure((size_t)W * 16 + 64));
+    FinParams fp;
+    memset(&fp, 0, sizeof(fp));
+    fp.part = (const unsigned long long*)ctx->part.p;
+    fp.seg_cta_lo = dt.seg_cta_lo;
+    fp.seg_cta_hi = dt.seg_cta_hi;
+    fp.cta_seg_first = dt.cta_seg_first;
+    fp.cta_slot_off = dt.cta_slot_off;
+    fp.win_seg_lo = dt.win_seg_lo;
+    fp.win_seg_hi = dt.win_seg_hi;
+    fp.win_lo = dt.win_lo;
+    fp.win_hi = dt.win_hi;
+    fp.W = W;
+    fp.Q = Q;
+    fp.QI = 3;
+    fp.P = 4;
+    fp.Ppad = 4;
+    double* d_out = (double*)ctx->out_d.p;
+    fp.abba_out = d_out;
+    fp.sites_used = d_out + (size_t)W * 5;
+    long long* d_i = (long long*)ctx->out_i.p;
+    fp.n_sites = d_i;
+    fp.pos_sum = d_i + W;
+    const int ti = pg_time_begin(ctx, "k1_finalize");
+    k1_finalize<MODE_ABBA><<<(unsigned)std::min<int64_t>(W, 65535), 64, 0, ctx->stream>>>(fp);
+    pg_time_end(ctx, ti);
+    PG_CUDA(cudaGetLastError());
+    PG_CUDA(cudaMemcpyAsync(out, fp.abba_out, (size_t)W * 5 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    PG_CUDA(cudaMemcpyAsync(sites_used, fp.sites_used, (size_t)W * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    PG_CUDA(cudaMemcpyAsync(n_sites, fp.n_sites, (size_t)W * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    PG_CUDA(cudaMemcpyAsync(pos_sum, fp.pos_sum, (size_t)W * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    PG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PG_OK;
+}
+
+// ================================================================================================
+// pg_site_counts
+// ================================================================================================
+extern "C" int pg_site_counts(pg_ctx* ctx, int64_t site0, int64_t n, uint16_t* counts) {
+    PG_CHECK(ctx && counts, "pg_site_counts: null argument");
+    PG_CHECK(ctx->P >= 1, "pg_site_counts: call pg_set_pops first");
+    PG_CHECK(site0 >= 0 && n >= 0 && site0 + n <= ctx->S, "pg_site_counts: range outside the uploaded sites");
+    PG_CUDA(cudaSetDevice(ctx->device));
+    pg_timings_reset(ctx);
+    if (n == 0) return PG_OK;
+    const int P = ctx->P;
+    const int64_t stride = (int64_t)P * 4;
+    // bounded device output buffer: process the range in slabs
+    const int64_t slab = std::max<int64_t>(1, std::min<int64_t>(n, (int64_t)(1ll << 30) / (stride * 2)));
+    PG_TRY(ctx->misc.ensure((size_t)slab * stride * 2 + 64));
+    for (int64_t s = 0; s < n; s += slab) {
+        const int64_t cnt = std::min(slab, n - s);
+        for (int p0 = 0; p0 < P; p0 += PG_MAX_K1_POPS) {
+            const int pc = std::min(PG_MAX_K1_POPS, P - p0);
+            const int Pp = pad_pops(pc);
+            std::vector<int32_t> local(ctx->H, -1);
+            for (int h = 0; h < ctx->H; ++h)
+                if (ctx->hap_pop[h] >= p0 && ctx->hap_pop[h] < p0 + pc) local[h] = ctx->hap_pop[h] - p0;
+            PopTables pt;
+            build_tables(local, ctx->H, ctx->pitch / 16, Pp, pt);
+            const int n_ent = (int)pt.ent_chunk.size();
+            const int table_bytes = n_ent * 20 + 64;
+            PG_CHECK(table_bytes <= 48 * 1024, "population layout needs too many mask entries");
+            K1Launch L;
+            L.plan = pg_make_k1_plan(cnt, ctx->H, ctx->sm_count, table_bytes);
+            PG_CHECK(L.plan.stages >= 2, "rows of %d haplotypes are too long for the site-pass kernel", ctx->H);
+            PG_TRY(ctx->tables.ensure((size_t)n_ent * 20 + 4096));
+            uint8_t* base = (uint8_t*)ctx->tables.p;
+            size_t o = 0;
+            uint32_t* d_mask_words = nullptr;
+            int32_t* d_chunk = nullptr;
+            PG_TRY(push(ctx, base, o, pt.ent_mask.data(), pt.ent_mask.size(), &d_mask_words));
+            PG_TRY(push(ctx, base, o, pt.ent_chunk.data(), pt.ent_chunk.size(), &d_chunk));
+            K1Params& p = L.prm;
+            memset(&p, 0, sizeof(p));
+            p.geno = (const uint8_t*)ctx->d_geno;
+            p.pos = ctx->d_pos;
+            p.site_begin = site0 + s;
+            p.site_end = site0 + s + cnt;
+            p.num_tiles = L.plan.num_tiles;
+            p.pitch = L.plan.pitch;
+            p.G = L.plan.G;
+            p.I = L.plan.I;
+            p.T = L.plan.T;
+            p.stages = L.plan.stages;
+            p.tile_bytes = L.plan.tile_bytes;
+            p.ent_chunk = d_chunk;
+            p.ent_mask = reinterpret_cast<uint4*>(d_mask_words);
+            p.n_ent = n_ent;
+            for (int X = 0; X < PG_MAX_K1_POPS; ++X) {
+                p.ent_lo[X] = pt.ent_lo[X];
+                p.ent_hi[X] = pt.ent_hi[X];
+                p.full_lo[X] = pt.full_lo[X];
+                p.full_hi[X] = pt.full_hi[X];
+                p.popN[X] = pt.popN[X];
+            }
+            p.counts_out = (uint16_t*)ctx->misc.p + (size_t)p0 * 4;
+            p.counts_stride = stride;
+            p.counts_pops = pc;
+            if (Pp == 2) PG_TRY((launch_site_pass<MODE_COUNTS, 2>(ctx, L, "k1_counts")));
+            else if (Pp == 4) PG_TRY((launch_site_pass<MODE_COUNTS, 4>(ctx, L, "k1_counts")));
+            else PG_TRY((launch_site_pass<MODE_COUNTS, 8>(ctx, L, "k1_counts")));
+            // the table buffer is reused by the next group: wait for this launch
+            if (p0 + PG_MAX_K1_POPS < P) PG_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
+        PG_CUDA(cudaMemcpyAsync(counts + (size_t)s * stride, ctx->misc.p, (size_t)cnt * stride * 2,
+                                cudaMemcpyDeviceToHost, ctx->stream));
+        PG_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return PG_OK;
+}

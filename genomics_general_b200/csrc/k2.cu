@@ -1,0 +1,664 @@
+// K2 — the pairwise path: per-window haplotype-pair matrices diff_ij / n_ij (integers) from bit-planes,
+// then the reference's mean-of-ratios epilogues.
+//
+//   k2_build_planes : int8 [S x pitch] -> 3 bit-planes per haplotype (allele bit0, allele bit1, valid),
+//                     haplotype-major, 32 sites per word           -- replaces Alignment.nanMask/numArray rows
+//   k2_pair         : diff_ij = popc(((b0_i^b0_j)|(b1_i^b1_j)) & m_i & m_j), n_ij = popc(m_i & m_j) summed over
+//                     the window's words; 64x64 haplotype tiles, 4x4 pairs per thread, cp.async ring
+//                     -- replaces distMatrix + pairNonNan (genomics.py:907-916, 1042-1047)
+//   k2_popgen_epi   : d_ij = diff/n, minSites mask, nanmean_min block means -> pi / dxy / Fst (genomics.py:956-995)
+//   k2_ind_epi      : individual x individual nanmean of ploidy blocks (genomics.py:934-954)
+//
+// This path is integer-issue bound (LOP3/POPC), not HBM bound.
+#include <stdlib.h>
+
+#include <algorithm>
+#include <cmath>
+
+#include "pgwin_internal.h"
+
+namespace {
+
+constexpr int TS = 64;          // haplotypes per tile side
+constexpr int TSP = TS + 1;     // padded (16-byte units) -> conflict-free STS/LDS
+constexpr int KW = 16;          // words (32 sites each) per pipeline stage
+constexpr int K4 = KW / 4;
+constexpr int NST = 3;          // cp.async ring depth
+constexpr int OPND_BYTES = 3 * K4 * TSP * 16;
+constexpr int STAGE_BYTES = 2 * OPND_BYTES;
+constexpr int PAIR_SMEM = NST * STAGE_BYTES;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid) {
+    const int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// bit-plane build
+// ------------------------------------------------------------------------------------------------
+constexpr int BP_SITES = 256, BP_COLS = 256, BP_ROWW = BP_COLS / 4 + 1;   // 65 words per site row
+constexpr int BP_SMEM = BP_SITES * BP_ROWW * 4 + 3 * BP_COLS * 8 * 4 + BP_COLS * 4;
+
+__global__ void __launch_bounds__(256) k2_build_planes(const uint8_t* __restrict__ geno, int pitch, int64_t S,
+                                                       int64_t site_base, const int32_t* __restrict__ col_to_row,
+                                                       uint32_t* __restrict__ planes, int Hk, int64_t NWp) {
+    extern __shared__ __align__(16) uint8_t bsm[];
+    uint32_t* tile = reinterpret_cast<uint32_t*>(bsm);                          // [256][65]
+    uint32_t* outp = tile + BP_SITES * BP_ROWW;                                  // [3][256][8]
+    int32_t* s_c2r = reinterpret_cast<int32_t*>(outp + 3 * BP_COLS * 8);        // [256]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int col0 = blockIdx.x * BP_COLS;
+    const int64_t sblk = blockIdx.y;
+    const int64_t site0 = site_base + sblk * BP_SITES;
+
+    {
+        const int col = col0 + tid;
+        s_c2r[tid] = (col < pitch) ? col_to_row[col] : -1;
+    }
+    // load 256 sites x 256 columns (16-byte vectors, 2 rows per warp instruction)
+    for (int pass = 0; pass < 16; ++pass) {
+        const int r = pass * 16 + warp * 2 + (lane >> 4);
+        const int c16 = lane & 15;
+        const int64_t site = site0 + r;
+        const int col = col0 + c16 * 16;
+        uint4 v = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+        if (site < S && col < pitch) v = *reinterpret_cast<const uint4*>(geno + site * pitch + col);
+        uint32_t* d = tile + r * BP_ROWW + c16 * 4;
+        d[0] = v.x;
+        d[1] = v.y;
+        d[2] = v.z;
+        d[3] = v.w;
+    }
+    __syncthreads();
+    // warp w transposes sites 32w..32w+31 (lane = site) for every used column
+    const uint32_t* myrow = tile + (warp * 32 + lane) * BP_ROWW;
+    for (int cw = 0; cw < BP_COLS / 4; ++cw) {
+        const uint32_t word = myrow[cw];
+#pragma unroll
+        for (int by = 0; by < 4; ++by) {
+            const int cl = cw * 4 + by;
+            if (s_c2r[cl] < 0) continue;                 // warp-uniform
+            const uint32_t b = (word >> (8 * by)) & 0xffu;
+            const bool valid = (b & 0x80u) == 0;
+            const uint32_t m = __ballot_sync(0xffffffffu, valid);
+            const uint32_t b0 = __ballot_sync(0xffffffffu, valid && (b & 1u));
+            const uint32_t b1 = __ballot_sync(0xffffffffu, valid && (b & 2u));
+            if (lane < 3) outp[(lane * BP_COLS + cl) * 8 + warp] = (lane == 0) ? b0 : (lane == 1 ? b1 : m);
+        }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < 3 * BP_COLS * 2; idx += 256) {
+        const int p = idx / (BP_COLS * 2);
+        const int rem = idx % (BP_COLS * 2);
+        const int cl = rem >> 1, half = rem & 1;
+        const int r = s_c2r[cl];
+        if (r < 0) continue;
+        const uint4 v = *reinterpret_cast<const uint4*>(outp + (p * BP_COLS + cl) * 8 + half * 4);
+        *reinterpret_cast<uint4*>(planes + ((size_t)p * Hk + r) * NWp + sblk * 8 + half * 4) = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pair kernel
+// ------------------------------------------------------------------------------------------------
+struct PairParams {
+    const uint32_t* planes;
+    int Hk;
+    int64_t NWp;
+    int64_t site_base;
+    const int64_t* win_lo;    // [nb] absolute site indices (non-empty windows only)
+    const int64_t* win_hi;
+    int ntile;
+    int32_t* out_diff;        // [nb][Hk][Hk]
+    int32_t* out_n;
+};
+
+__global__ void __launch_bounds__(256, 2) k2_pair(const __grid_constant__ PairParams pp) {
+    extern __shared__ __align__(16) uint8_t psm[];
+    const int tid = threadIdx.x;
+    const int ty = tid >> 4, tx = tid & 15;
+    // decode the upper-triangular tile pair
+    int tp = blockIdx.x, ti = 0;
+    while (tp >= pp.ntile - ti) {
+        tp -= pp.ntile - ti;
+        ++ti;
+    }
+    const int tj = ti + tp;
+    const int wb = blockIdx.y;
+    const int64_t rel_lo = pp.win_lo[wb] - pp.site_base, rel_hi = pp.win_hi[wb] - pp.site_base;
+    const int64_t w_first = rel_lo >> 5, w_last = (rel_hi - 1) >> 5;
+    const uint32_t mask_first = 0xffffffffu << (rel_lo & 31);
+    const uint32_t mask_last = 0xffffffffu >> (31 - (int)((rel_hi - 1) & 31));
+    const int64_t k_begin = w_first & ~(int64_t)3;
+    const int nchunk = (int)((w_last - k_begin) / KW) + 1;
+
+    auto fill = [&](int chunk, int stage) {
+        const int64_t k0 = k_begin + (int64_t)chunk * KW;
+        uint8_t* sb = psm + stage * STAGE_BYTES;
+#pragma unroll
+        for (int it = 0; it < (2 * 3 * TS * K4) / 256; ++it) {
+            const int item = tid + it * 256;
+            const int k4 = item & (K4 - 1);
+            const int hap = (item / K4) & (TS - 1);
+            const int p = (item / (K4 * TS)) % 3;
+            const int opnd = item / (K4 * TS * 3);
+            const int gh = (opnd == 0 ? ti : tj) * TS + hap;
+            const bool valid = gh < pp.Hk;
+            const uint32_t* src = pp.planes + ((size_t)p * pp.Hk + (valid ? gh : 0)) * pp.NWp + k0 + 4 * k4;
+            cp_async16(sb + opnd * OPND_BYTES + ((p * K4 + k4) * TSP + hap) * 16, src, valid);
+        }
+    };
+
+    int accd[4][4], accn[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) accd[a][b] = accn[a][b] = 0;
+
+    for (int s = 0; s < NST - 1; ++s) {
+        if (s < nchunk) fill(s, s);
+        cp_async_commit();
+    }
+    for (int ch = 0; ch < nchunk; ++ch) {
+        cp_async_wait<NST - 2>();
+        __syncthreads();
+        // prefetch chunk ch+NST-1 into the stage consumed at iteration ch-1 (all threads are past it)
+        {
+            const int nxt = ch + NST - 1;
+            if (nxt < nchunk) fill(nxt, nxt % NST);
+            cp_async_commit();
+        }
+        const int stage = ch % NST;
+        uint8_t* sb = psm + stage * STAGE_BYTES;
+        const int64_t k0 = k_begin + (int64_t)ch * KW;
+        const bool need_fix = (k0 <= w_first) || (k0 + KW - 1 >= w_last);
+        if (need_fix) {   // block-uniform: clip the J operand's valid plane to the window
+            if (tid < TS) {
+                for (int kk = 0; kk < KW; ++kk) {
+                    const int64_t word = k0 + kk;
+                    uint32_t mk = 0xffffffffu;
+                    if (word < w_first || word > w_last) mk = 0;
+                    else {
+                        if (word == w_first) mk &= mask_first;
+                        if (word == w_last) mk &= mask_last;
+                    }
+                    if (mk != 0xffffffffu) {
+                        uint32_t* wp = reinterpret_cast<uint32_t*>(sb + OPND_BYTES + ((2 * K4 + (kk >> 2)) * TSP + tid) * 16) + (kk & 3);
+                        *wp &= mk;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        const uint4* I4 = reinterpret_cast<const uint4*>(sb);
+        const uint4* J4 = reinterpret_cast<const uint4*>(sb + OPND_BYTES);
+#pragma unroll
+        for (int k4 = 0; k4 < K4; ++k4) {
+            uint4 B0[4], B1[4], BM[4];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                B0[b] = J4[(0 * K4 + k4) * TSP + tx + 16 * b];
+                B1[b] = J4[(1 * K4 + k4) * TSP + tx + 16 * b];
+                BM[b] = J4[(2 * K4 + k4) * TSP + tx + 16 * b];
+            }
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const uint4 A0 = I4[(0 * K4 + k4) * TSP + ty + 16 * a];
+                const uint4 A1 = I4[(1 * K4 + k4) * TSP + ty + 16 * a];
+                const uint4 AM = I4[(2 * K4 + k4) * TSP + ty + 16 * a];
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+#define K2_PAIR_WORD(C)                                                   \
+    {                                                                     \
+        const uint32_t mm = AM.C & BM[b].C;                               \
+        const uint32_t df = ((A0.C ^ B0[b].C) | (A1.C ^ B1[b].C)) & mm;   \
+        accd[a][b] += __popc(df);                                         \
+        accn[a][b] += __popc(mm);                                         \
+    }
+                    K2_PAIR_WORD(x)
+                    K2_PAIR_WORD(y)
+                    K2_PAIR_WORD(z)
+                    K2_PAIR_WORD(w)
+#undef K2_PAIR_WORD
+                }
+            }
+        }
+    }
+    cp_async_wait<0>();
+    const size_t HH = (size_t)pp.Hk * pp.Hk;
+    int32_t* od = pp.out_diff + (size_t)wb * HH;
+    int32_t* on = pp.out_n + (size_t)wb * HH;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int i = ti * TS + ty + 16 * a;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int j = tj * TS + tx + 16 * b;
+            if (i < pp.Hk && j < pp.Hk) {
+                od[(size_t)i * pp.Hk + j] = accd[a][b];
+                on[(size_t)i * pp.Hk + j] = accn[a][b];
+                od[(size_t)j * pp.Hk + i] = accd[a][b];
+                on[(size_t)j * pp.Hk + i] = accn[a][b];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// epilogues
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double nan_d() { return __longlong_as_double(0x7ff8000000000000ll); }
+
+// deterministic block-wide sum: butterfly inside warps, then warp 0 adds the 8 partials in order
+__device__ __forceinline__ void block_sum(double& s, long long& c, double* sh_s, long long* sh_c) {
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, d);
+        c += __shfl_xor_sync(0xffffffffu, c, d);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) {
+        sh_s[warp] = s;
+        sh_c[warp] = c;
+    }
+    __syncthreads();
+    double ts = 0.0;
+    long long tc = 0;
+    for (int w = 0; w < 8; ++w) {
+        ts += sh_s[w];
+        tc += sh_c[w];
+    }
+    s = ts;
+    c = tc;
+}
+
+struct PopEpiParams {
+    const int32_t* diff;
+    const int32_t* n;
+    int Hk, P;
+    const int32_t* pop_start;   // [P+1] plane-row offsets (rows sorted by population)
+    int min_sites;
+    double min_data;
+    double* pi;                 // [nb x P]
+    double* dxy;                // [nb x npairs]
+    double* fst;
+};
+
+__device__ __forceinline__ double nanmean_min_dev(double sum, double nonnan, double size, double min_data) {
+    // genomics.py:88-90 on a block with `nonnan` finite entries out of `size`
+    if (size <= 0) return nan_d();
+    const double nan_cnt = size - nonnan;
+    if (1.0 - (1.0 * nan_cnt / size) < min_data) return nan_d();
+    if (nonnan <= 0) return nan_d();
+    return sum / nonnan;
+}
+
+__global__ void __launch_bounds__(256) k2_popgen_epi(const __grid_constant__ PopEpiParams ep) {
+    extern __shared__ __align__(16) uint8_t esm[];
+    const int P = ep.P;
+    const int nblk = P * (P + 1) / 2;
+    double* blk_s = reinterpret_cast<double*>(esm);                 // [nblk] upper-triangle sums
+    long long* blk_c = reinterpret_cast<long long*>(blk_s + nblk);  // [nblk] upper-triangle counts
+    __shared__ double sh_s[8];
+    __shared__ long long sh_c[8];
+    const int wb = blockIdx.x;
+    const size_t HH = (size_t)ep.Hk * ep.Hk;
+    const int32_t* D = ep.diff + (size_t)wb * HH;
+    const int32_t* N = ep.n + (size_t)wb * HH;
+    int bi = 0;
+    for (int X = 0; X < P; ++X)
+        for (int Y = X; Y < P; ++Y, ++bi) {
+            const int r0 = ep.pop_start[X], r1 = ep.pop_start[X + 1];
+            const int c0 = ep.pop_start[Y], c1 = ep.pop_start[Y + 1];
+            const int nr = r1 - r0, nc = c1 - c0;
+            double s = 0.0;
+            long long c = 0;
+            const int total = nr * nc;
+            for (int idx = threadIdx.x; idx < total; idx += 256) {
+                const int i = r0 + idx / nc, j = c0 + idx % nc;
+                if (X == Y && j <= i) continue;
+                const int nij = N[(size_t)i * ep.Hk + j];
+                if (nij == 0 || (ep.min_sites > 0 && nij < ep.min_sites)) continue;   // nan entries
+                s += (double)D[(size_t)i * ep.Hk + j] / (double)nij;
+                c += 1;
+            }
+            block_sum(s, c, sh_s, sh_c);
+            if (threadIdx.x == 0) {
+                blk_s[bi] = s;
+                blk_c[bi] = c;
+            }
+        }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    const int npairs = P * (P - 1) / 2;
+    auto bidx = [&](int X, int Y) { return X * P - X * (X - 1) / 2 + (Y - X); };
+    for (int X = 0; X < P; ++X) {
+        const double Nx = ep.pop_start[X + 1] - ep.pop_start[X];
+        const int b = bidx(X, X);
+        ep.pi[(size_t)wb * P + X] = nanmean_min_dev(2.0 * blk_s[b], 2.0 * (double)blk_c[b], Nx * Nx, ep.min_data);
+    }
+    int k = 0;
+    for (int X = 0; X < P; ++X)
+        for (int Y = X + 1; Y < P; ++Y, ++k) {
+            const double Nx = ep.pop_start[X + 1] - ep.pop_start[X], Ny = ep.pop_start[Y + 1] - ep.pop_start[Y];
+            const int bxx = bidx(X, X), byy = bidx(Y, Y), bxy = bidx(X, Y);
+            const double dxy = nanmean_min_dev(blk_s[bxy], (double)blk_c[bxy], Nx * Ny, ep.min_data);
+            const double st = blk_s[bxx] + blk_s[byy] + blk_s[bxy];
+            const double ct = (double)(blk_c[bxx] + blk_c[byy] + blk_c[bxy]);
+            const double pi_t = nanmean_min_dev(2.0 * st, 2.0 * ct, (Nx + Ny) * (Nx + Ny), ep.min_data);
+            const double w = 1.0 * Nx / (Nx + Ny);
+            const double pi_s = w * ep.pi[(size_t)wb * P + X] + (1 - w) * ep.pi[(size_t)wb * P + Y];
+            ep.dxy[(size_t)wb * npairs + k] = dxy;
+            ep.fst[(size_t)wb * npairs + k] = 1 - pi_s / pi_t;
+        }
+}
+
+struct IndEpiParams {
+    const int32_t* diff;
+    const int32_t* n;
+    int Hk, n_ind;
+    const int32_t* ind_start;   // [n_ind+1]
+    int include_same;
+    double* out;                // [nb x n_ind x n_ind]
+};
+
+__global__ void __launch_bounds__(256) k2_ind_epi(const __grid_constant__ IndEpiParams ep) {
+    const int wb = blockIdx.y;
+    const size_t HH = (size_t)ep.Hk * ep.Hk;
+    const int32_t* D = ep.diff + (size_t)wb * HH;
+    const int32_t* N = ep.n + (size_t)wb * HH;
+    const int64_t total = (int64_t)ep.n_ind * ep.n_ind;
+    for (int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * 256) {
+        const int a = (int)(idx / ep.n_ind), b = (int)(idx % ep.n_ind);
+        double s = 0.0;
+        int c = 0;
+        for (int i = ep.ind_start[a]; i < ep.ind_start[a + 1]; ++i)
+            for (int j = ep.ind_start[b]; j < ep.ind_start[b + 1]; ++j) {
+                double d;
+                if (i == j) {
+                    if (!ep.include_same) continue;          // diagonal = nan (genomics.py:940)
+                    d = 0.0;                                 // distMatrix leaves 0 on the diagonal (908)
+                } else {
+                    const int nij = N[(size_t)i * ep.Hk + j];
+                    if (nij == 0) continue;                  // np.mean of an empty array = nan
+                    d = (double)D[(size_t)i * ep.Hk + j] / (double)nij;
+                }
+                s += d;
+                c += 1;
+            }
+        ep.out[(size_t)wb * total + idx] = c ? s / (double)c : nan_d();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host orchestration
+// ------------------------------------------------------------------------------------------------
+struct PlaneSet {
+    int Hk = 0;
+    int64_t site_base = 0;
+    int64_t NWp = 0;
+    uint32_t* planes = nullptr;
+};
+
+// Build bit-planes for sites [lo, hi) of the haplotype columns listed in `order` (plane row r = column order[r]).
+int build_planes(pg_ctx* ctx, const std::vector<int32_t>& order, int64_t lo, int64_t hi, PlaneSet& ps) {
+    const int Hk = (int)order.size();
+    PG_CHECK(Hk >= 1, "pairwise path: no haplotypes selected");
+    const int64_t sb = lo & ~(int64_t)(BP_SITES - 1);
+    const int64_t nblk = (hi - sb + BP_SITES - 1) / BP_SITES;
+    const int64_t NWp = nblk * 8 + KW + 8;     // zero tail: chunk over-reads contribute nothing
+    const size_t bytes = (size_t)3 * Hk * NWp * 4;
+    PG_TRY(ctx->planes.ensure(bytes));
+    PG_CUDA(cudaMemsetAsync(ctx->planes.p, 0, bytes, ctx->stream));
+    std::vector<int32_t> c2r(ctx->pitch, -1);
+    for (int r = 0; r < Hk; ++r) c2r[order[r]] = r;
+    PG_TRY(ctx->misc2.ensure((size_t)ctx->pitch * 4 + 64));
+    PG_CUDA(cudaMemcpyAsync(ctx->misc2.p, c2r.data(), (size_t)ctx->pitch * 4, cudaMemcpyHostToDevice, ctx->stream));
+    PG_CUDA(cudaFuncSetAttribute(k2_build_planes, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM));
+    const int colblocks = (ctx->pitch + BP_COLS - 1) / BP_COLS;
+    for (int64_t y0 = 0; y0 < nblk; y0 += 65535) {
+        const int64_t ny = std::min<int64_t>(65535, nblk - y0);
+        dim3 grid((unsigned)colblocks, (unsigned)ny);
+        const int ti = pg_time_begin(ctx, "k2_planes");
+        k2_build_planes<<<grid, 256, BP_SMEM, ctx->stream>>>((const uint8_t*)ctx->d_geno, ctx->pitch, ctx->S,
+                                                             sb + y0 * BP_SITES, (const int32_t*)ctx->misc2.p,
+                                                             (uint32_t*)ctx->planes.p + y0 * 8, Hk, NWp);
+        pg_time_end(ctx, ti);
+        PG_CUDA(cudaGetLastError());
+    }
+    ps.Hk = Hk;
+    ps.site_base = sb;
+    ps.NWp = NWp;
+    ps.planes = (uint32_t*)ctx->planes.p;
+    return PG_OK;
+}
+
+size_t pair_budget_bytes() {
+    const char* e = getenv("PG_PAIR_SCRATCH_MB");
+    size_t mb = e ? (size_t)atoll(e) : 3072;
+    if (mb < 1) mb = 1;
+    return mb << 20;
+}
+
+// Pair matrices for a batch of non-empty windows (absolute site ranges) -> ctx->pairs (diff | n)
+int run_pair_batch(pg_ctx* ctx, const PlaneSet& ps, const std::vector<int64_t>& lo, const std::vector<int64_t>& hi,
+                   int32_t** d_diff, int32_t** d_n) {
+    const int nb = (int)lo.size();
+    const size_t HH = (size_t)ps.Hk * ps.Hk;
+    PG_TRY(ctx->pairs.ensure((size_t)nb * HH * 8 + 64));
+    PG_TRY(ctx->misc3.ensure((size_t)nb * 16 + 64));
+    int64_t* d_lo = (int64_t*)ctx->misc3.p;
+    int64_t* d_hi = d_lo + nb;
+    PG_CUDA(cudaMemcpyAsync(d_lo, lo.data(), (size_t)nb * 8, cudaMemcpyHostToDevice, ctx->stream));
+    PG_CUDA(cudaMemcpyAsync(d_hi, hi.data(), (size_t)nb * 8, cudaMemcpyHostToDevice, ctx->stream));
+    PairParams pp;
+    pp.planes = ps.planes;
+    pp.Hk = ps.Hk;
+    pp.NWp = ps.NWp;
+    pp.site_base = ps.site_base;
+    pp.win_lo = d_lo;
+    pp.win_hi = d_hi;
+    pp.ntile = (ps.Hk + TS - 1) / TS;
+    pp.out_diff = (int32_t*)ctx->pairs.p;
+    pp.out_n = pp.out_diff + (size_t)nb * HH;
+    PG_CUDA(cudaFuncSetAttribute(k2_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM));
+    dim3 grid((unsigned)(pp.ntile * (pp.ntile + 1) / 2), (unsigned)nb);
+    const int ti = pg_time_begin(ctx, "k2_pair");
+    k2_pair<<<grid, 256, PAIR_SMEM, ctx->stream>>>(pp);
+    pg_time_end(ctx, ti);
+    PG_CUDA(cudaGetLastError());
+    *d_diff = pp.out_diff;
+    *d_n = pp.out_n;
+    return PG_OK;
+}
+
+}  // namespace
+
+// pi / dxy / Fst for the listed windows through the pairwise path; results are scattered into the
+// caller's [W x ...] arrays at the windows' own indices.
+int pg_k2_popgen_windows(pg_ctx* ctx, const std::vector<int64_t>& wins, int32_t min_sites, double min_data, double* pi,
+                         double* dxy, double* fst) {
+    const int P = ctx->P;
+    const int npairs = P * (P - 1) / 2;
+    // plane rows: haplotypes that belong to a population, sorted by population (stable)
+    std::vector<int32_t> order;
+    std::vector<int32_t> pop_start(P + 1, 0);
+    for (int X = 0; X < P; ++X) {
+        pop_start[X] = (int32_t)order.size();
+        for (int h = 0; h < ctx->H; ++h)
+            if (ctx->hap_pop[h] == X) order.push_back(h);
+    }
+    pop_start[P] = (int32_t)order.size();
+    // empty windows cannot be "ragged"; every window here has at least one site
+    int64_t lo = ctx->S, hi = 0;
+    for (int64_t w : wins) {
+        lo = std::min(lo, ctx->win_lo[w]);
+        hi = std::max(hi, ctx->win_hi[w]);
+    }
+    PlaneSet ps;
+    PG_TRY(build_planes(ctx, order, lo, hi, ps));
+    const size_t HH = (size_t)ps.Hk * ps.Hk;
+    const size_t per_batch = std::max<size_t>(1, std::min<size_t>(pair_budget_bytes() / (HH * 8), 65535));
+    PG_TRY(ctx->misc.ensure((size_t)(P + 1) * 4 + 64));
+    PG_CUDA(cudaMemcpyAsync(ctx->misc.p, pop_start.data(), (size_t)(P + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    const size_t nd = (size_t)per_batch * (P + 2 * npairs);
+    PG_TRY(ctx->out_d.ensure(nd * 8 + 64));
+    void* hbuf = nullptr;
+    PG_TRY(pg_pinned(ctx, nd * 8 + 64, &hbuf));
+    double* hres = (double*)hbuf;
+    const int epi_smem = P * (P + 1) / 2 * 16 + 64;
+    for (size_t b0 = 0; b0 < wins.size(); b0 += per_batch) {
+        const size_t nb = std::min(per_batch, wins.size() - b0);
+        std::vector<int64_t> blo(nb), bhi(nb);
+        for (size_t k = 0; k < nb; ++k) {
+            blo[k] = ctx->win_lo[wins[b0 + k]];
+            bhi[k] = ctx->win_hi[wins[b0 + k]];
+        }
+        int32_t *d_diff = nullptr, *d_n = nullptr;
+        PG_TRY(run_pair_batch(ctx, ps, blo, bhi, &d_diff, &d_n));
+        PopEpiParams ep;
+        ep.diff = d_diff;
+        ep.n = d_n;
+        ep.Hk = ps.Hk;
+        ep.P = P;
+        ep.pop_start = (const int32_t*)ctx->misc.p;
+        ep.min_sites = min_sites;
+        ep.min_data = min_data;
+        ep.pi = (double*)ctx->out_d.p;
+        ep.dxy = ep.pi + nb * P;
+        ep.fst = ep.dxy + nb * npairs;
+        const int ti = pg_time_begin(ctx, "k2_popgen_epi");
+        k2_popgen_epi<<<(unsigned)nb, 256, epi_smem, ctx->stream>>>(ep);
+        pg_time_end(ctx, ti);
+        PG_CUDA(cudaGetLastError());
+        PG_CUDA(cudaMemcpyAsync(hres, ctx->out_d.p, nb * (P + 2 * npairs) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        PG_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (size_t k = 0; k < nb; ++k) {
+            const int64_t w = wins[b0 + k];
+            for (int x = 0; x < P; ++x) pi[w * P + x] = hres[k * P + x];
+            for (int q = 0; q < npairs; ++q) {
+                dxy[w * npairs + q] = hres[nb * P + k * npairs + q];
+                fst[w * npairs + q] = hres[nb * P + nb * npairs + k * npairs + q];
+            }
+        }
+    }
+    return PG_OK;
+}
+
+extern "C" int pg_pairdist(pg_ctx* ctx, int32_t n_ind, const int32_t* hap_ind, int32_t include_same_with_same,
+                           double* dist, int64_t* n_sites, int64_t* pos_sum) {
+    PG_CHECK(ctx && hap_ind && dist, "pg_pairdist: null argument");
+    PG_CHECK(n_ind >= 1, "pg_pairdist: n_ind must be >= 1");
+    PG_CHECK(ctx->H > 0, "pg_pairdist: upload genotypes first");
+    PG_CUDA(cudaSetDevice(ctx->device));
+    pg_timings_reset(ctx);
+    const int64_t W = ctx->W;
+    if (W == 0) return PG_OK;
+    std::vector<int32_t> order, ind_start(n_ind + 1, 0);
+    for (int h = 0; h < ctx->H; ++h)
+        PG_CHECK(hap_ind[h] >= -1 && hap_ind[h] < n_ind, "pg_pairdist: hap_ind[%d]=%d out of range", h, hap_ind[h]);
+    for (int a = 0; a < n_ind; ++a) {
+        ind_start[a] = (int32_t)order.size();
+        for (int h = 0; h < ctx->H; ++h)
+            if (hap_ind[h] == a) order.push_back(h);
+    }
+    ind_start[n_ind] = (int32_t)order.size();
+    const size_t nn = (size_t)n_ind * n_ind;
+    // sites / position sums on the host side of the library: prefix sums of the positions are cheap, but the
+    // positions live on the device — read them back once (4 bytes per site).
+    std::vector<int64_t> nonempty;
+    int64_t lo = ctx->S, hi = 0;
+    for (int64_t w = 0; w < W; ++w) {
+        if (n_sites) n_sites[w] = ctx->win_hi[w] - ctx->win_lo[w];
+        if (ctx->win_hi[w] > ctx->win_lo[w]) {
+            nonempty.push_back(w);
+            lo = std::min(lo, ctx->win_lo[w]);
+            hi = std::max(hi, ctx->win_hi[w]);
+        } else {
+            for (size_t k = 0; k < nn; ++k) dist[(size_t)w * nn + k] = NAN;
+        }
+    }
+    if (pos_sum) {
+        std::vector<int32_t> hp((size_t)std::max<int64_t>(ctx->S, 1));
+        if (ctx->S > 0)
+            PG_CUDA(cudaMemcpy(hp.data(), ctx->d_pos, (size_t)ctx->S * 4, cudaMemcpyDeviceToHost));
+        std::vector<int64_t> pre((size_t)ctx->S + 1, 0);
+        for (int64_t s = 0; s < ctx->S; ++s) pre[s + 1] = pre[s] + hp[s];
+        for (int64_t w = 0; w < W; ++w) pos_sum[w] = pre[ctx->win_hi[w]] - pre[ctx->win_lo[w]];
+    }
+    if (nonempty.empty()) return PG_OK;
+    PlaneSet ps;
+    PG_TRY(build_planes(ctx, order, lo, hi, ps));
+    const size_t HH = (size_t)ps.Hk * ps.Hk;
+    const size_t per_batch = std::max<size_t>(1, std::min<size_t>(pair_budget_bytes() / (HH * 8 + nn * 8), 65535));
+    PG_TRY(ctx->misc.ensure((size_t)(n_ind + 1) * 4 + 64));
+    PG_CUDA(cudaMemcpyAsync(ctx->misc.p, ind_start.data(), (size_t)(n_ind + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    PG_TRY(ctx->out_d.ensure(per_batch * nn * 8 + 64));
+    for (size_t b0 = 0; b0 < nonempty.size(); b0 += per_batch) {
+        const size_t nb = std::min(per_batch, nonempty.size() - b0);
+        std::vector<int64_t> blo(nb), bhi(nb);
+        for (size_t k = 0; k < nb; ++k) {
+            blo[k] = ctx->win_lo[nonempty[b0 + k]];
+            bhi[k] = ctx->win_hi[nonempty[b0 + k]];
+        }
+        int32_t *d_diff = nullptr, *d_n = nullptr;
+        PG_TRY(run_pair_batch(ctx, ps, blo, bhi, &d_diff, &d_n));
+        IndEpiParams ep;
+        ep.diff = d_diff;
+        ep.n = d_n;
+        ep.Hk = ps.Hk;
+        ep.n_ind = n_ind;
+        ep.ind_start = (const int32_t*)ctx->misc.p;
+        ep.include_same = include_same_with_same ? 1 : 0;
+        ep.out = (double*)ctx->out_d.p;
+        dim3 grid((unsigned)std::min<size_t>((nn + 255) / 256, 1024), (unsigned)nb);
+        const int ti = pg_time_begin(ctx, "k2_ind_epi");
+        k2_ind_epi<<<grid, 256, 0, ctx->stream>>>(ep);
+        pg_time_end(ctx, ti);
+        PG_CUDA(cudaGetLastError());
+        // consecutive non-empty windows are usually consecutive in `dist`: copy run by run
+        size_t k = 0;
+        while (k < nb) {
+            size_t e = k + 1;
+            while (e < nb && nonempty[b0 + e] == nonempty[b0 + e - 1] + 1) ++e;
+            PG_CUDA(cudaMemcpyAsync(dist + (size_t)nonempty[b0 + k] * nn, (double*)ctx->out_d.p + k * nn,
+                                    (e - k) * nn * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            k = e;
+        }
+        PG_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return PG_OK;
+}
+
+extern "C" int pg_pair_counts(pg_ctx* ctx, int64_t window, int32_t* diff, int32_t* n) {
+    PG_CHECK(ctx && diff && n, "pg_pair_counts: null argument");
+    PG_CHECK(window >= 0 && window < ctx->W, "pg_pair_counts: window %lld out of range", (long long)window);
+    PG_CUDA(cudaSetDevice(ctx->device));
+    pg_timings_reset(ctx);
+    const int H = ctx->H;
+    const size_t HH = (size_t)H * H;
+    const int64_t lo = ctx->win_lo[window], hi = ctx->win_hi[window];
+    if (hi <= lo) {
+        memset(diff, 0, HH * 4);
+        memset(n, 0, HH * 4);
+        return PG_OK;
+    }
+    std::vector<int32_t> order(H);
+    for (int h = 0; h < H; ++h) order[h] = h;
+    PlaneSet ps;
+    PG_TRY(build_planes(ctx, order, lo, hi, ps));
+    std::vector<int64_t> blo(1, lo), bhi(1, hi);
+    int32_t *d_diff = nullptr, *d_n = nullptr;
+    PG_TRY(run_pair_batch(ctx, ps, blo, bhi, &d_diff, &d_n));
+    PG_CUDA(cudaMemcpyAsync(diff, d_diff, HH * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PG_CUDA(cudaMemcpyAsync(n, d_n, HH * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PG_OK;
+}

@@ -1,0 +1,114 @@
+// Internal declarations shared by the translation units of libpgwin.so (not part of the C-ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/pgwin.h"
+
+#define PG_OK 0
+#define PG_ERR 1
+
+void pg_set_error(const char* fmt, ...);
+
+#define PG_CUDA(call)                                                                                  \
+    do {                                                                                               \
+        cudaError_t _e = (call);                                                                       \
+        if (_e != cudaSuccess) {                                                                       \
+            pg_set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e));  \
+            return PG_ERR;                                                                             \
+        }                                                                                              \
+    } while (0)
+
+#define PG_CHECK(cond, ...)                 \
+    do {                                    \
+        if (!(cond)) {                      \
+            pg_set_error(__VA_ARGS__);      \
+            return PG_ERR;                  \
+        }                                   \
+    } while (0)
+
+#define PG_TRY(expr)                 \
+    do {                             \
+        int _r = (expr);             \
+        if (_r != PG_OK) return _r;  \
+    } while (0)
+
+struct PgTiming {
+    char name[32];
+    cudaEvent_t start, stop;
+    int launches;
+};
+
+// grow-only device scratch buffer
+struct PgBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes);
+    void release();
+};
+
+static constexpr int PG_MAX_K1_POPS = 8;     // K1 keeps per-pop counts in registers: P <= 8
+static constexpr int PG_MAX_POPS = 64;       // K2 block epilogue
+
+// K1 launch geometry for one (S, H): see DESIGN.md "K1 tiling".
+struct K1Plan {
+    int pitch;        // bytes per site row on the device = 16 * chunks, chunks odd (bank-conflict-free LDS.128)
+    int chunks;       // 16-byte chunks per row
+    int G;            // lanes cooperating on one site (power of two, <= 32)
+    int I;            // sites per lane per tile
+    int T;            // sites per tile = (256 / G) * I
+    int stages;       // TMA ring depth
+    int tile_bytes;   // T * pitch
+    int smem_bytes;   // dynamic shared memory of the kernel
+    int64_t num_tiles;
+    int ctas;         // persistent CTAs, each owning a contiguous tile range
+};
+K1Plan pg_make_k1_plan(int64_t S, int H, int sm_count, int table_bytes);
+int pg_pitch_for(int H);
+
+struct pg_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    // genotype matrix
+    int8_t* d_geno = nullptr;
+    int32_t* d_pos = nullptr;
+    int64_t S = 0;
+    int32_t H = 0;
+    int32_t pitch = 0;
+    size_t geno_cap = 0, pos_cap = 0;
+    // populations
+    int32_t P = 0;
+    std::vector<int32_t> hap_pop;
+    // windows (host copies) + segments
+    int64_t W = 0;
+    std::vector<int64_t> win_lo, win_hi;
+    std::vector<int64_t> brk;                 // segment breakpoints, brk[0]=0 .. brk[nseg]=S
+    std::vector<int32_t> win_seg_lo, win_seg_hi;
+    // timings of the last statistics call
+    std::vector<PgTiming> timings;
+    std::vector<cudaEvent_t> event_pool;
+    size_t events_used = 0;
+    int64_t launches = 0;
+    // scratch
+    PgBuf tables, part, segmeta, winmeta, out_d, out_i, planes, pairs, misc, misc2, misc3;
+    void* h_pinned = nullptr;                 // small pinned staging for result read-back
+    size_t h_pinned_cap = 0;
+};
+
+// timing helpers: every kernel launch is bracketed by events on ctx->stream
+void pg_timings_reset(pg_ctx* ctx);
+int pg_time_begin(pg_ctx* ctx, const char* name);   // returns timing index
+void pg_time_end(pg_ctx* ctx, int idx);
+int pg_pinned(pg_ctx* ctx, size_t bytes, void** out);
+int pg_build_segments(pg_ctx* ctx);
+
+// implemented in k1.cu / k2.cu
+int pg_k2_popgen_windows(pg_ctx* ctx, const std::vector<int64_t>& wins, int32_t min_sites, double min_data,
+                         double* pi, double* dxy, double* fst);

@@ -1,0 +1,195 @@
+"""Thin object wrapper over the C-ABI: one ``Engine`` = one ``pg_ctx`` = one GPU.
+
+All numerics run in libpgwin.so (hand-written CUDA, sm_100a).  numpy is used only for host
+buffers.  Nothing here computes statistics on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import itertools
+
+import numpy as np
+
+from . import _lib
+from ._lib import PgError, check
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class PinnedArray:
+    """numpy view over cudaHostAlloc'd memory (freed on close/GC)."""
+
+    def __init__(self, shape, dtype):
+        self._lib = _lib.lib()
+        self.shape = tuple(int(s) for s in shape)
+        self.dtype = np.dtype(dtype)
+        nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        p = C.c_void_p()
+        check(self._lib.pg_host_alloc(C.byref(p), max(nbytes, 1)), "pg_host_alloc")
+        self._p = p
+        buf = (C.c_uint8 * max(nbytes, 1)).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
+
+    def close(self):
+        if self._p is not None:
+            self.array = None
+            self._lib.pg_host_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Engine:
+    def __init__(self, device: int = 0):
+        self._lib = _lib.lib()
+        ctx = C.c_void_p()
+        check(self._lib.pg_ctx_create(int(device), C.byref(ctx)), "pg_ctx_create")
+        self._ctx = ctx
+        self.device = int(device)
+        self.S = 0
+        self.H = 0
+        self.P = 0
+        self.W = 0
+
+    # ---- lifetime ----
+    def close(self):
+        if getattr(self, "_ctx", None) is not None:
+            self._lib.pg_ctx_destroy(self._ctx)
+            self._ctx = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- data ----
+    def upload(self, geno: np.ndarray, pos=None):
+        """geno: int8 [S, H] site-major (A0 C1 G2 T3, negative = missing); pos: int32 [S]."""
+        geno = np.ascontiguousarray(geno, dtype=np.int8)
+        assert geno.ndim == 2
+        S, H = geno.shape
+        if pos is not None:
+            pos = np.ascontiguousarray(pos, dtype=np.int32)
+            assert pos.shape == (S,)
+        check(self._lib.pg_upload(self._ctx, _ptr(geno), S, H, _ptr(pos)), "pg_upload")
+        self.S, self.H = S, H
+        self.W = 0
+
+    def synth_fill(self, spec, n_sites: int, spacing: int = 10):
+        tv, to, tt, tm = spec.thresholds()
+        check(self._lib.pg_synth_fill(self._ctx, int(n_sites), spec.n_pops, spec.samples_per_pop, spec.ploidy,
+                                      spec.seed, tv, to, tt, tm, int(spacing)), "pg_synth_fill")
+        self.S, self.H = int(n_sites), spec.n_haps
+        self.W = 0
+
+    def download(self, site0: int, n: int, into_geno=None, into_pos=None):
+        g = into_geno if into_geno is not None else np.empty((n, self.H), dtype=np.int8)
+        p = into_pos if into_pos is not None else np.empty(n, dtype=np.int32)
+        check(self._lib.pg_download(self._ctx, int(site0), int(n), _ptr(g), _ptr(p)), "pg_download")
+        return g, p
+
+    def set_pops(self, hap_pop, n_pops=None):
+        hap_pop = np.ascontiguousarray(hap_pop, dtype=np.int32)
+        assert hap_pop.shape == (self.H,), (hap_pop.shape, self.H)
+        P = int(n_pops) if n_pops is not None else int(hap_pop.max()) + 1
+        check(self._lib.pg_set_pops(self._ctx, P, _ptr(hap_pop)), "pg_set_pops")
+        self.P = P
+
+    def set_windows(self, lo, hi):
+        lo = np.ascontiguousarray(lo, dtype=np.int64)
+        hi = np.ascontiguousarray(hi, dtype=np.int64)
+        assert lo.shape == hi.shape and lo.ndim == 1
+        check(self._lib.pg_set_windows(self._ctx, len(lo), _ptr(lo), _ptr(hi)), "pg_set_windows")
+        self.W = len(lo)
+
+    # ---- statistics ----
+    def popgen(self, min_sites: int = 1, min_data: float = 0.01, force_pairwise: bool = False):
+        """-> dict(pi [W,P], dxy [W,npairs], fst [W,npairs], sites [W], pos_sum [W], path [W])."""
+        W, P = self.W, self.P
+        npairs = P * (P - 1) // 2
+        pi = np.empty((W, P), dtype=np.float64)
+        dxy = np.empty((W, npairs), dtype=np.float64)
+        fst = np.empty((W, npairs), dtype=np.float64)
+        sites = np.empty(W, dtype=np.int64)
+        pos_sum = np.empty(W, dtype=np.int64)
+        path = np.empty(W, dtype=np.int32)
+        check(self._lib.pg_popgen(self._ctx, int(min_sites) if min_sites else 0, float(min_data),
+                                  2 if force_pairwise else 0, _ptr(pi), _ptr(dxy), _ptr(fst), _ptr(sites),
+                                  _ptr(pos_sum), _ptr(path)), "pg_popgen")
+        return dict(pi=pi, dxy=dxy, fst=fst, sites=sites, pos_sum=pos_sum, path=path,
+                    pairs=list(itertools.combinations(range(P), 2)))
+
+    def abbababa(self, p1: int, p2: int, p3: int, o: int, min_data: float = 0.01):
+        """-> dict(ABBA,BABA,D,fd,fdM [W], sitesUsed [W] (nan = no good site), sites, pos_sum)."""
+        W = self.W
+        out = np.empty((W, 5), dtype=np.float64)
+        used = np.empty(W, dtype=np.float64)
+        sites = np.empty(W, dtype=np.int64)
+        pos_sum = np.empty(W, dtype=np.int64)
+        check(self._lib.pg_abbababa(self._ctx, p1, p2, p3, o, float(min_data), _ptr(out), _ptr(used), _ptr(sites),
+                                    _ptr(pos_sum)), "pg_abbababa")
+        return dict(ABBA=out[:, 0], BABA=out[:, 1], D=out[:, 2], fd=out[:, 3], fdM=out[:, 4], sitesUsed=used,
+                    sites=sites, pos_sum=pos_sum)
+
+    def site_counts(self, site0: int = 0, n: int = None):
+        """uint16 [n, P, 4] A,C,G,T counts per population."""
+        n = self.S - site0 if n is None else int(n)
+        out = np.empty((n, self.P, 4), dtype=np.uint16)
+        check(self._lib.pg_site_counts(self._ctx, int(site0), n, _ptr(out)), "pg_site_counts")
+        return out
+
+    def pairdist(self, hap_ind, n_ind: int, include_same_with_same: bool = False):
+        """-> dict(dist [W,n_ind,n_ind], sites [W], pos_sum [W])."""
+        hap_ind = np.ascontiguousarray(hap_ind, dtype=np.int32)
+        assert hap_ind.shape == (self.H,)
+        W = self.W
+        dist = np.empty((W, n_ind, n_ind), dtype=np.float64)
+        sites = np.empty(W, dtype=np.int64)
+        pos_sum = np.empty(W, dtype=np.int64)
+        check(self._lib.pg_pairdist(self._ctx, int(n_ind), _ptr(hap_ind), 1 if include_same_with_same else 0,
+                                    _ptr(dist), _ptr(sites), _ptr(pos_sum)), "pg_pairdist")
+        return dict(dist=dist, sites=sites, pos_sum=pos_sum)
+
+    def pair_counts(self, window: int):
+        """(diff, n) int32 [H,H] of one window (Alignment.distMatrix / pairNonNan numerators)."""
+        diff = np.empty((self.H, self.H), dtype=np.int32)
+        n = np.empty((self.H, self.H), dtype=np.int32)
+        check(self._lib.pg_pair_counts(self._ctx, int(window), _ptr(diff), _ptr(n)), "pg_pair_counts")
+        return diff, n
+
+    # ---- introspection ----
+    def last_timings(self):
+        cap = 32
+        names = (C.c_char * 32 * cap)()
+        ms = (C.c_float * cap)()
+        launches = (C.c_int32 * cap)()
+        cnt = C.c_int32(0)
+        check(self._lib.pg_last_timings(self._ctx, cap, names, ms, launches, C.byref(cnt)), "pg_last_timings")
+        return {names[k].value.decode(): dict(ms=float(ms[k]), launches=int(launches[k])) for k in range(cnt.value)}
+
+    def launch_count(self) -> int:
+        n = C.c_int64(0)
+        check(self._lib.pg_launch_count(self._ctx, C.byref(n)), "pg_launch_count")
+        return int(n.value)
+
+
+def k1_plan(S: int, H: int):
+    """Host-only: the site-pass launch geometry for a shape (works without a GPU)."""
+    L = _lib.lib()
+    v = [C.c_int32(0) for _ in range(5)]
+    check(L.pg_debug_k1_plan(int(S), int(H), *[C.byref(x) for x in v]), "pg_debug_k1_plan")
+    return dict(pitch=v[0].value, lanes_per_site=v[1].value, tile_sites=v[2].value, stages=v[3].value,
+                smem_bytes=v[4].value)

@@ -1,0 +1,108 @@
+/*
+ * pgwin.h — C-ABI of libpgwin.so: the B200 (sm_100a) engine for the per-window numerics of
+ * simonhmartin/genomics_general (popgenWindows.py / ABBABABAwindows.py / freq.py / distMat.py).
+ *
+ * The reference has no FFI: its seam is the Python API of genomics.py as used by the four scripts
+ * (SURVEY.md §8b).  Each entry point below names the reference code it replaces
+ * (/root/reference/<file>:<line>).  The binding a maintainer would add is a ctypes stub —
+ * see INTEGRATION.md and genomics_general_b200/_lib.py.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; pg_last_error() gives the message of the
+ *     last failure on the calling thread.
+ *   - the caller owns every host buffer; the library owns device memory behind the opaque pg_ctx.
+ *   - one ctx per device; calls on one ctx are not thread-safe; different ctxs are independent.
+ *   - genotype codes: A=0 C=1 G=2 T=3, missing = any value with bit 7 set (canonically -1).
+ *     This is Alignment.numArray (genomics.py:74-77, 834) narrowed to int8 and transposed to
+ *     site-major: geno[site * H + hap].
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef PGWIN_H
+#define PGWIN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pg_ctx pg_ctx;
+
+/* ---- library / context ------------------------------------------------------------------------ */
+int         pg_version(void);
+const char* pg_last_error(void);
+int         pg_device_count(int* n);
+int         pg_ctx_create(int device, pg_ctx** out);
+int         pg_ctx_destroy(pg_ctx* ctx);
+/* pinned host memory for the end-to-end path (H2D from pinned buffers) */
+int         pg_host_alloc(void** ptr, size_t bytes);
+int         pg_host_free(void* ptr);
+
+/* ---- data in ---------------------------------------------------------------------------------- */
+/* Replaces genoToAlignment + Alignment.__init__ (genomics.py:1101-1127, 813-869): the dense matrix of
+ * a whole file (or shard).  geno: int8 [S x H] site-major, pos: int32 [S] (may be NULL -> zeros).
+ * Copies host->device (pitched so that rows are 16-byte multiples). */
+int pg_upload(pg_ctx* ctx, const int8_t* geno, int64_t S, int32_t H, const int32_t* pos);
+/* Two-step variant: allocate, then fill site ranges (each call is an async H2D on the ctx stream). */
+int pg_alloc_sites(pg_ctx* ctx, int64_t S, int32_t H);
+int pg_upload_range(pg_ctx* ctx, int64_t site0, int64_t n, const int8_t* geno, const int32_t* pos);
+/* Device-side synthetic data (SURVEY.md §8d distribution; bit-identical to synth.py::synth_genotypes /
+ * synth_positions).  Thresholds are 32-bit integer probabilities (p * 2^32). */
+int pg_synth_fill(pg_ctx* ctx, int64_t S, int32_t n_pops, int32_t samples_per_pop, int32_t ploidy,
+                  uint64_t seed, uint64_t thr_var, uint64_t thr_out0, uint64_t thr_third, uint64_t thr_miss,
+                  int32_t spacing);
+/* Device -> host copy of a site range (tests / building host buffers for the e2e bench). */
+int pg_download(pg_ctx* ctx, int64_t site0, int64_t n, int8_t* geno, int32_t* pos);
+
+/* Replaces SampleData/Alignment.groups (genomics.py:1264-1290, 857-861): hap_pop[h] in [0,P) or -1. */
+int pg_set_pops(pg_ctx* ctx, int32_t P, const int32_t* hap_pop);
+/* Replaces the window generators' output (genomics.py:1971-2171): half-open site-index ranges
+ * [lo[w], hi[w]) computed on the host with the generators' exact semantics (windows.py). Ranges may
+ * overlap and may be empty. */
+int pg_set_windows(pg_ctx* ctx, int64_t W, const int64_t* lo, const int64_t* hi);
+
+/* ---- statistics ------------------------------------------------------------------------------- */
+/* Replaces Alignment.groupDistStats (genomics.py:956-995) + the sites/mid bookkeeping of
+ * popgenWindows.py:37-41 for every window.
+ *   pi  [W x P], dxy/fst [W x P(P-1)/2] (pairs in (0,1),(0,2),..,(1,2).. order), n_sites [W],
+ *   pos_sum [W] (sum of positions, for midPos genomics.py:1795), path [W]: 0 = failed (sites < minSites),
+ *   1 = closed-form allele-count path (K1), 2 = pairwise path (K2).
+ * force_path: 0 = route per window (K1 when exact, else K2), 2 = pairwise for every window.
+ * min_sites <= 0 disables the n_ij < minSites mask (genomics.py:958). */
+int pg_popgen(pg_ctx* ctx, int32_t min_sites, double min_data, int32_t force_path,
+              double* pi, double* dxy, double* fst, int64_t* n_sites, int64_t* pos_sum, int32_t* path);
+
+/* Replaces genomics.ABBABABA (genomics.py:1647-1695, polarize=True) per window.
+ * out [W x 5] = ABBA, BABA, D, fd, fdM; sites_used [W] (double: nan when the window has no good site,
+ * genomics.py:1694-1695); n_sites/pos_sum as above. p1,p2,p3,o are population indices of pg_set_pops. */
+int pg_abbababa(pg_ctx* ctx, int32_t p1, int32_t p2, int32_t p3, int32_t o, double min_data,
+                double* out, double* sites_used, int64_t* n_sites, int64_t* pos_sum);
+
+/* Replaces Alignment.siteFreqs(asCounts=True) per population (genomics.py:1049-1052; freq.py:52-58):
+ * counts uint16 [n x P x 4] (A,C,G,T) for sites site0 .. site0+n-1. */
+int pg_site_counts(pg_ctx* ctx, int64_t site0, int64_t n, uint16_t* counts);
+
+/* Replaces Alignment.indPairDists (genomics.py:934-954) as used by distMat.py:42-45.
+ * hap_ind[h] = individual index in [0,n_ind) or -1; dist [W x n_ind x n_ind]; n_sites/pos_sum [W]. */
+int pg_pairdist(pg_ctx* ctx, int32_t n_ind, const int32_t* hap_ind, int32_t include_same_with_same,
+                double* dist, int64_t* n_sites, int64_t* pos_sum);
+
+/* Replaces Alignment.distMatrix + pairNonNan (genomics.py:907-916, 1042-1047) for ONE window:
+ * diff, n int32 [H x H] (symmetric, diagonal: diff 0, n = non-missing sites of the haplotype). */
+int pg_pair_counts(pg_ctx* ctx, int64_t window, int32_t* diff, int32_t* n);
+
+/* ---- introspection ---------------------------------------------------------------------------- */
+/* Device time (ms, CUDA events on the ctx stream) of the kernels launched by the last statistics call:
+ * names[i] -> ms[i]; returns the number of entries through *count (at most cap). */
+int pg_last_timings(pg_ctx* ctx, int32_t cap, char (*names)[32], float* ms, int32_t* launches, int32_t* count);
+/* Total kernels launched by this ctx so far. */
+int pg_launch_count(pg_ctx* ctx, int64_t* n);
+/* Host-only planning self-test hook (no device needed): returns the K1 launch plan for a shape. */
+int pg_debug_k1_plan(int64_t S, int32_t H, int32_t* pitch, int32_t* lanes_per_site, int32_t* tile_sites,
+                     int32_t* stages, int32_t* smem_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PGWIN_H */

@@ -1,0 +1,129 @@
+"""CPU tests of the host window logic (genomics_general_b200/windows.py) against
+ (a) the reference generators' output (tests/golden/generator_cases.json) and
+ (b) the oracle's literal state-machine restatement on random inputs."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+from genomics_general_b200 import windows as W
+from oracle import dense_oracle as do
+from helpers import GOLDEN
+
+GEN = json.load(open(os.path.join(GOLDEN, "generator_cases.json")))
+
+
+def _ids(scaf):
+    names = []
+    ids = []
+    for s in scaf:
+        if not names or names[-1] != s:
+            if s in names:
+                names.append(s)         # a scaffold that re-appears later is a new run; same name
+            else:
+                names.append(s)
+        ids.append(len(names) - 1)
+    return np.array(ids, dtype=np.int32), names
+
+
+def _run(kind, p, scaf, pos):
+    ids, names = _ids(scaf)
+    if kind == "coordinate":
+        return W.sliding_coord_windows(ids, names, pos, p["windSize"], p["stepSize"], exclude=p.get("exclude"))
+    if kind == "sites":
+        return W.sliding_sites_windows(ids, names, pos, p["windSites"], p["overlap"], p["maxDist"], p["minSites"])
+    return W.predefined_coord_windows(ids, names, pos, [tuple(c) for c in p["windCoords"]])
+
+
+@pytest.mark.parametrize("idx", range(len(GEN["cases"])))
+def test_against_reference_generators(idx):
+    case = GEN["cases"][idx]
+    scaf, pos = GEN["scaffolds"], GEN["positions"]
+    ws = _run(case["kind"], case["params"], scaf, pos)
+    assert len(ws) == len(case["windows"])
+    for k, r in enumerate(case["windows"]):
+        assert ws.scaffold[k] == r["scaffold"]
+        assert [pos[i] for i in range(ws.lo[k], ws.hi[k])] == r["positions"], (k, ws.lo[k], ws.hi[k])
+        if case["kind"] != "sites":
+            assert [ws.start[k], ws.end[k]] == r["limits"]
+        if case["kind"] == "predefined":
+            assert ws.ID[k] == r["ID"]
+
+
+def _random_layout(rng):
+    scaf, pos = [], []
+    for k in range(int(rng.integers(1, 5))):
+        n = int(rng.integers(1, 120))
+        span = int(rng.integers(n, 40 * n + 2))
+        p = np.sort(rng.choice(np.arange(1, span + 1), size=n, replace=False))
+        scaf += ["sc%d" % k] * n
+        pos += [int(x) for x in p]
+    return scaf, pos
+
+
+@pytest.mark.parametrize("seed", range(25))
+def test_coordinate_against_oracle_state_machine(seed):
+    rng = np.random.default_rng(seed)
+    scaf, pos = _random_layout(rng)
+    wsz = int(rng.integers(5, 400))
+    step = [None, int(rng.integers(1, 500))][int(rng.integers(0, 2))]
+    ws = _run("coordinate", dict(windSize=wsz, stepSize=step), scaf, pos)
+    ref = do.sliding_coord_windows(scaf, pos, wsz, step)
+    assert len(ws) == len(ref)
+    for k, r in enumerate(ref):
+        assert (ws.scaffold[k], ws.start[k], ws.end[k]) == (r["scaffold"], r["start"], r["end"])
+        assert list(range(ws.lo[k], ws.hi[k])) == r["sites"]
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_sites_against_oracle_state_machine(seed):
+    rng = np.random.default_rng(100 + seed)
+    scaf, pos = _random_layout(rng)
+    wsz = int(rng.integers(2, 40))
+    ov = int(rng.integers(0, wsz))
+    ms = [None, int(rng.integers(1, wsz + 1))][int(rng.integers(0, 2))]
+    md = [None, int(rng.integers(5, 300))][int(rng.integers(0, 2))]
+    try:
+        ref = do.sliding_sites_windows(scaf, pos, wsz, ov, md if md else math.inf, ms)
+    except AssertionError:
+        with pytest.raises(RuntimeError):
+            _run("sites", dict(windSites=wsz, overlap=ov, maxDist=md, minSites=ms), scaf, pos)
+        return
+    ws = _run("sites", dict(windSites=wsz, overlap=ov, maxDist=md, minSites=ms), scaf, pos)
+    assert len(ws) == len(ref)
+    for k, r in enumerate(ref):
+        assert ws.scaffold[k] == r["scaffold"]
+        assert list(range(ws.lo[k], ws.hi[k])) == r["sites"]
+
+
+@pytest.mark.parametrize("seed", range(25))
+def test_predefined_against_oracle_state_machine(seed):
+    rng = np.random.default_rng(500 + seed)
+    scaf, pos = _random_layout(rng)
+    names = sorted(set(scaf), key=scaf.index)
+    coords = []
+    for sc in names:
+        if rng.random() < 0.25:
+            continue
+        mx = max(p for s, p in zip(scaf, pos) if s == sc)
+        start = 1
+        for _ in range(int(rng.integers(1, 6))):
+            start = start + int(rng.integers(0, max(2, mx // 3)))
+            end = start + int(rng.integers(0, max(2, mx // 2)))
+            coords.append((sc, start, end))
+    if not coords:
+        coords = [(names[0], 1, 10)]
+    ws = _run("predefined", dict(windCoords=coords), scaf, pos)
+    ref = do.predefined_coord_windows(scaf, pos, coords)
+    assert len(ws) == len(ref)
+    for k, r in enumerate(ref):
+        assert (ws.scaffold[k], ws.start[k], ws.end[k]) == (r["scaffold"], r["start"], r["end"])
+        assert list(range(ws.lo[k], ws.hi[k])) == r["sites"], (k, coords)
+
+
+def test_mid_pos_matches_python_round():
+    assert W.mid_pos(5, 2) == 2          # 2.5 -> 2 (banker's)
+    assert W.mid_pos(7, 2) == 4          # 3.5 -> 4
+    assert math.isnan(W.mid_pos(0, 0))
