@@ -1,6 +1,7 @@
 // libpgwin.so — context, data movement, synthetic data, windows/segments, timing.
 // C-ABI: include/pgwin.h.  No CPU fallback anywhere: every compute entry needs a CUDA device.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -184,28 +185,43 @@ int pg_pitch_for(int H) {
     return chunks * 16;
 }
 
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return (e && *e) ? atoi(e) : dflt;
+}
+
+// Tile geometry: 8 consumer warps per CTA are split into teams of `wpt` warps; one team owns one tile
+// (T consecutive sites) at a time, so up to 8/wpt tiles are being consumed while `stages` tiles sit in the
+// TMA ring.  G lanes share one site row when a row is too long for one lane's tile share.
 K1Plan pg_make_k1_plan(int64_t S, int H, int sm_count, int table_bytes) {
     K1Plan p;
     memset(&p, 0, sizeof(p));
     p.pitch = pg_pitch_for(H);
     p.chunks = p.pitch / 16;
-    const int threads = 256;
     const int smem_cap = 227 * 1024 - 2048 - table_bytes;   // per-CTA dynamic smem we allow ourselves
-    const int tile_target = 64 * 1024;
-    int G = 1;
-    while (G < 32 && (threads / G) * p.pitch > tile_target) G *= 2;
-    int I = 1;
-    if (G == 1) {
-        I = tile_target / (threads * p.pitch);
-        if (I < 1) I = 1;
-        if (I > 8) I = 8;
+    const int tile_target = env_int("PG_K1_TILE_KB", 32) * 1024;
+    int G = 1, wpt = 1, I = 1;
+    if (32 * p.pitch <= tile_target) {
+        while (wpt < 8 && 32 * (wpt * 2) * p.pitch <= tile_target) wpt *= 2;
+        if (wpt == 8) {
+            I = tile_target / (256 * p.pitch);
+            if (I < 1) I = 1;
+            if (I > 8) I = 8;
+        }
+    } else {
+        while (G < 32 && (32 / G) * p.pitch > tile_target) G *= 2;
     }
+    G = env_int("PG_K1_G", G);
+    wpt = env_int("PG_K1_WPT", wpt);
+    I = env_int("PG_K1_I", I);
     p.G = G;
     p.I = I;
-    p.T = (threads / G) * I;
+    p.wpt = wpt;
+    p.T = (32 * wpt / G) * I;
     p.tile_bytes = p.T * p.pitch;
     int stages = smem_cap / p.tile_bytes;
-    if (stages > 4) stages = 4;
+    if (stages > 8) stages = 8;
+    stages = std::min(stages, std::max(2, env_int("PG_K1_STAGES", stages)));
     p.stages = stages;                      // < 2 means the row is too long for this kernel
     p.smem_bytes = p.stages * p.tile_bytes + 256 + table_bytes;
     p.num_tiles = (S + p.T - 1) / p.T;
@@ -231,15 +247,42 @@ extern "C" int pg_debug_k1_plan(int64_t S, int32_t H, int32_t* pitch, int32_t* l
 // ------------------------------------------------------------------------------------------------
 // upload / download
 // ------------------------------------------------------------------------------------------------
-__global__ void k_fill_missing(int8_t* geno, int64_t S, int pitch, int H) {
-    // set the padding bytes [H, pitch) of every row to "missing" (0xFF)
-    const int pad = pitch - H;
-    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int64_t total = S * pad;
-    for (; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-        int64_t s = idx / pad;
-        int c = H + (int)(idx % pad);
-        geno[s * pitch + c] = (int8_t)-1;
+// Resident device code (DESIGN.md "HBM layout"): still ONE byte per genotype, but one-hot with 2-bit
+// spacing so that three bytes can be added before any field overflows:
+//     A = 0x01, C = 0x04, G = 0x10, T = 0x40, missing = 0x00
+// The C-ABI keeps the reference's codes (A0 C1 G2 T3, bit7 = missing); upload transcodes in place on the
+// device right behind the H2D copy, download decodes.
+__device__ __forceinline__ uint32_t encode4(uint32_t w) {
+    const uint32_t v = ~(w >> 7) & 0x01010101u;        // valid flag per byte
+    const uint32_t a0 = w & v, a1 = (w >> 1) & v;
+    const uint32_t A = v & ~a0 & ~a1, Cc = a0 & ~a1, Gg = a1 & ~a0, T = a0 & a1;
+    return A | (Cc << 2) | (Gg << 4) | (T << 6);
+}
+__device__ __forceinline__ uint32_t decode4(uint32_t c) {
+    const uint32_t lo = ((c >> 2) | (c >> 6)) & 0x01010101u;      // C or T
+    const uint32_t hi = ((c >> 4) | (c >> 6)) & 0x01010101u;      // G or T
+    const uint32_t any = (c | (c >> 2) | (c >> 4) | (c >> 6)) & 0x01010101u;
+    const uint32_t miss = (any ^ 0x01010101u) * 0xffu;            // 0xFF in missing bytes
+    return (lo | (hi << 1)) | miss;
+}
+
+// rows [row0, row0+n) of the pitched matrix; only the H data bytes of a row are touched
+__global__ void k_transcode(uint8_t* geno, int64_t row0, int64_t n, int pitch, int H, int decode) {
+    const int wpr = (H + 3) / 4;
+    const int64_t total = n * wpr;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = idx / wpr;
+        const int wi = (int)(idx % wpr);
+        uint32_t* p = reinterpret_cast<uint32_t*>(geno + (row0 + r) * pitch) + wi;
+        const uint32_t w = *p;
+        uint32_t x = decode ? decode4(w) : encode4(w);
+        const int rem = H - wi * 4;
+        if (rem < 4) {
+            const uint32_t keep = 0xffffffffu << (8 * rem);       // padding bytes stay as they are
+            x = (x & ~keep) | (w & keep);
+        }
+        *p = x;
     }
 }
 
@@ -269,10 +312,8 @@ extern "C" int pg_alloc_sites(pg_ctx* ctx, int64_t S, int32_t H) {
     ctx->H = H;
     ctx->pitch = pitch;
     PG_CUDA(cudaMemsetAsync(ctx->d_pos, 0, pneed, ctx->stream));
-    if (pitch != H && S > 0) {
-        k_fill_missing<<<1024, 256, 0, ctx->stream>>>(ctx->d_geno, S, pitch, H);
-        PG_CUDA(cudaGetLastError());
-    }
+    // every byte starts as "missing" (0x00): row padding and the slack rows never count
+    PG_CUDA(cudaMemsetAsync(ctx->d_geno, 0, need, ctx->stream));
     // data changed: windows/pops stay, segments depend on S
     ctx->brk.clear();
     return PG_OK;
@@ -286,6 +327,9 @@ extern "C" int pg_upload_range(pg_ctx* ctx, int64_t site0, int64_t n, const int8
     if (n == 0) return PG_OK;
     PG_CUDA(cudaMemcpy2DAsync(ctx->d_geno + site0 * ctx->pitch, ctx->pitch, geno, ctx->H, ctx->H, (size_t)n,
                               cudaMemcpyHostToDevice, ctx->stream));
+    k_transcode<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>((uint8_t*)ctx->d_geno, site0, n, ctx->pitch, ctx->H, 0);
+    PG_CUDA(cudaGetLastError());
+    ctx->launches += 1;
     if (pos)
         PG_CUDA(cudaMemcpyAsync(ctx->d_pos + site0, pos, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice,
                                 ctx->stream));
@@ -308,9 +352,16 @@ extern "C" int pg_download(pg_ctx* ctx, int64_t site0, int64_t n, int8_t* geno, 
     PG_CHECK(site0 >= 0 && n >= 0 && site0 + n <= ctx->S, "pg_download: range outside S");
     PG_CUDA(cudaSetDevice(ctx->device));
     if (n == 0) return PG_OK;
-    if (geno)
-        PG_CUDA(cudaMemcpy2DAsync(geno, ctx->H, ctx->d_geno + site0 * ctx->pitch, ctx->pitch, ctx->H, (size_t)n,
-                                  cudaMemcpyDeviceToHost, ctx->stream));
+    if (geno) {
+        // decode into a scratch copy so that the resident matrix is never modified
+        PG_TRY(ctx->misc.ensure((size_t)n * ctx->pitch + 64));
+        PG_CUDA(cudaMemcpyAsync(ctx->misc.p, ctx->d_geno + site0 * ctx->pitch, (size_t)n * ctx->pitch,
+                                cudaMemcpyDeviceToDevice, ctx->stream));
+        k_transcode<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>((uint8_t*)ctx->misc.p, 0, n, ctx->pitch, ctx->H, 1);
+        PG_CUDA(cudaGetLastError());
+        PG_CUDA(cudaMemcpy2DAsync(geno, ctx->H, ctx->misc.p, ctx->pitch, ctx->H, (size_t)n, cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+    }
     if (pos)
         PG_CUDA(cudaMemcpyAsync(pos, ctx->d_pos + site0, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost,
                                 ctx->stream));
@@ -371,7 +422,7 @@ __global__ void k_synth(int8_t* __restrict__ geno, int32_t* __restrict__ pos, Sy
                 const uint64_t mm = mix64(base + ((uint64_t)samp + 1ull) * K_SAMPLE);
                 if ((mm >> 32) < sp.thr_miss) g = -1;
             }
-            geno[site * sp.pitch + hap] = (int8_t)g;
+            geno[site * sp.pitch + hap] = (int8_t)(g < 0 ? 0 : (1 << (2 * g)));   // resident one-hot code
         }
     }
 }

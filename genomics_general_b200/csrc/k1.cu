@@ -19,8 +19,8 @@
 
 namespace {
 
-constexpr int K1_THREADS = 256;
-constexpr int K1_WARPS = K1_THREADS / 32;
+constexpr int K1_WARPS = 8;                       // consumer warps per CTA
+constexpr int K1_THREADS = (K1_WARPS + 1) * 32;   // + one TMA producer warp
 
 enum { MODE_POPGEN = 0, MODE_ABBA = 1, MODE_COUNTS = 2 };
 
@@ -29,7 +29,7 @@ struct K1Params {
     const int32_t* pos;
     int64_t site_begin, site_end;     // sites processed by this launch
     int64_t num_tiles;
-    int pitch, G, I, T, stages, tile_bytes;
+    int pitch, G, I, T, wpt, stages, tile_bytes;
     // hap -> pop tables (shared-memory copies are made at kernel start)
     const int32_t* ent_chunk;
     const uint4* ent_mask;
@@ -60,6 +60,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile(
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
@@ -79,34 +82,66 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     } while (!ok);
 }
 
-// ---- SWAR allele counting ----------------------------------------------------------------------
-// w: 4 genotype bytes (0..3, bit7 = missing); m: 0x01 in the byte lanes that belong to the population.
-// Byte-lane accumulators: av += valid, a0 += bit0, a1 += bit1, a01 += bit0&bit1   (all masked by valid).
-struct Lanes4 {
-    uint32_t v, e0, e1, e01;
+// ---- allele counting on the resident one-hot code (A 0x01, C 0x04, G 0x10, T 0x40, missing 0x00) ----------
+// level 1: three words are added -> 2-bit fields hold 0..3
+// level 2: split into 4-bit fields (lo = A | G<<4, hi = C | T<<4 per byte), up to 5 level-1 sums
+// level 3: split into byte lanes, up to 17 level-2 flushes, then __dp4a folds the 4 byte lanes
+struct Tally {
+    uint32_t nlo, nhi;            // nibble fields
+    uint32_t bA, bC, bG, bT;      // byte lanes
+    uint32_t tA, tC, tG, tT;      // totals
+    int load;                     // upper bound of what one byte lane holds
 };
-__device__ __forceinline__ Lanes4 swar(uint32_t w, uint32_t m) {
-    Lanes4 r;
-    r.v = ~(w >> 7) & m;
-    r.e0 = w & r.v;
-    r.e1 = (w >> 1) & r.v;
-    r.e01 = r.e0 & r.e1;
-    return r;
+__device__ __forceinline__ void tally_init(Tally& t) {
+    t.nlo = t.nhi = t.bA = t.bC = t.bG = t.bT = t.tA = t.tC = t.tG = t.tT = 0;
+    t.load = 0;
 }
-#define K1_ACC_CHUNK(W, MX, MY, MZ, MW)                 \
-    {                                                   \
-        Lanes4 x = swar((W).x, (MX)), y = swar((W).y, (MY)); \
-        av += x.v + y.v;                                \
-        a0 += x.e0 + y.e0;                              \
-        a1 += x.e1 + y.e1;                              \
-        a01 += x.e01 + y.e01;                           \
-        Lanes4 z = swar((W).z, (MZ)), u = swar((W).w, (MW)); \
-        av += z.v + u.v;                                \
-        a0 += z.e0 + u.e0;                              \
-        a1 += z.e1 + u.e1;                              \
-        a01 += z.e01 + u.e01;                           \
-    }
-__device__ __forceinline__ uint32_t hsum4(uint32_t x, uint32_t acc) { return __dp4a(x, 0x01010101u, acc); }
+__device__ __forceinline__ void add3(Tally& t, uint32_t a, uint32_t b, uint32_t c) {
+    const uint32_t s = a + b + c;
+    t.nlo += s & 0x33333333u;
+    t.nhi += (s >> 2) & 0x33333333u;
+}
+__device__ __forceinline__ void nib_flush(Tally& t) {
+    t.bA += t.nlo & 0x0f0f0f0fu;
+    t.bG += (t.nlo >> 4) & 0x0f0f0f0fu;
+    t.bC += t.nhi & 0x0f0f0f0fu;
+    t.bT += (t.nhi >> 4) & 0x0f0f0f0fu;
+    t.nlo = t.nhi = 0;
+}
+__device__ __forceinline__ void byte_flush(Tally& t) {
+    t.tA = __dp4a(t.bA, 0x01010101u, t.tA);
+    t.tC = __dp4a(t.bC, 0x01010101u, t.tC);
+    t.tG = __dp4a(t.bG, 0x01010101u, t.tG);
+    t.tT = __dp4a(t.bT, 0x01010101u, t.tT);
+    t.bA = t.bC = t.bG = t.bT = 0;
+    t.load = 0;
+}
+__device__ __forceinline__ uint4 and4(uint4 w, uint4 m) { return make_uint4(w.x & m.x, w.y & m.y, w.z & m.z, w.w & m.w); }
+// 3 chunks = 12 words -> 4 level-1 sums (<= 12 per nibble), one nibble flush
+__device__ __forceinline__ void add_chunks3(Tally& t, uint4 x, uint4 y, uint4 z) {
+    add3(t, x.x, y.x, z.x);
+    add3(t, x.y, y.y, z.y);
+    add3(t, x.z, y.z, z.z);
+    add3(t, x.w, y.w, z.w);
+    nib_flush(t);
+    t.load += 12;
+    if (t.load > 240) byte_flush(t);
+}
+__device__ __forceinline__ void add_chunks2(Tally& t, uint4 x, uint4 y) {
+    add3(t, x.x, x.y, x.z);
+    add3(t, x.w, y.x, y.y);
+    add3(t, y.z, y.w, 0u);
+    nib_flush(t);
+    t.load += 8;
+    if (t.load > 240) byte_flush(t);
+}
+__device__ __forceinline__ void add_chunks1(Tally& t, uint4 x) {
+    add3(t, x.x, x.y, x.z);
+    add3(t, x.w, 0u, 0u);
+    nib_flush(t);
+    t.load += 4;
+    if (t.load > 240) byte_flush(t);
+}
 
 template <int QI, int QD>
 struct Acc {
@@ -175,48 +210,59 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_site_pass(const __grid_const
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* tiles = smem;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)prm.stages * prm.tile_bytes);   // [stages]
+    uint64_t* empty = full + 8;                                                                  // [stages]
     uint4* s_ent_mask = reinterpret_cast<uint4*>(smem + (size_t)prm.stages * prm.tile_bytes + 256);
     int32_t* s_ent_chunk = reinterpret_cast<int32_t*>(s_ent_mask + prm.n_ent);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.x, B = gridDim.x;
     const int64_t t0 = (int64_t)b * prm.num_tiles / B, t1 = (int64_t)(b + 1) * prm.num_tiles / B;
+    const int ntiles = (int)(t1 - t0);
 
     for (int e = tid; e < prm.n_ent; e += K1_THREADS) {
         s_ent_mask[e] = prm.ent_mask[e];
         s_ent_chunk[e] = prm.ent_chunk[e];
     }
     if (tid == 0) {
-        for (int s = 0; s < prm.stages; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < prm.stages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], (uint32_t)prm.wpt);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
 
-    auto issue = [&](int64_t t, int stage) {
-        const int64_t s_lo = prm.site_begin + t * prm.T;
-        int64_t rows = prm.site_end - s_lo;
-        if (rows > prm.T) rows = prm.T;
-        const uint32_t bytes = (uint32_t)(rows * prm.pitch);
-        mbar_expect_tx(&full[stage], bytes);
-        const uint8_t* src = prm.geno + s_lo * prm.pitch;
-        uint8_t* dst = tiles + (size_t)stage * prm.tile_bytes;
-        for (uint32_t off = 0; off < bytes; off += 32768u) {
-            const uint32_t n = (bytes - off) < 32768u ? (bytes - off) : 32768u;
-            bulk_g2s(dst + off, src + off, n, &full[stage]);
+    if (warp == K1_WARPS) {
+        // ---------------- TMA producer: one elected lane keeps the ring full ----------------
+        if (lane == 0) {
+            for (int it = 0; it < ntiles; ++it) {
+                const int stage = it % prm.stages;
+                if (it >= prm.stages) mbar_wait(&empty[stage], (uint32_t)(((it / prm.stages) - 1) & 1));
+                const int64_t s_lo = prm.site_begin + (t0 + it) * prm.T;
+                int64_t rows = prm.site_end - s_lo;
+                if (rows > prm.T) rows = prm.T;
+                const uint32_t bytes = (uint32_t)(rows * prm.pitch);
+                mbar_expect_tx(&full[stage], bytes);
+                const uint8_t* src = prm.geno + s_lo * prm.pitch;
+                uint8_t* dst = tiles + (size_t)stage * prm.tile_bytes;
+                for (uint32_t off = 0; off < bytes; off += 32768u) {
+                    const uint32_t n = (bytes - off) < 32768u ? (bytes - off) : 32768u;
+                    bulk_g2s(dst + off, src + off, n, &full[stage]);
+                }
+            }
         }
-    };
-    if (tid == 0)
-        for (int s = 0; s < prm.stages; ++s)
-            if (t0 + s < t1) issue(t0 + s, s);
+        return;
+    }
 
-    // lane -> (site slot, sub-lane) mapping: the 32/G sites of a warp are contiguous in `sl`, the G lanes of
-    // one site are spw apart so that the 8 lanes of an LDS.128 phase read 8 different rows (odd chunk pitch).
+    // ---------------- consumers: team m = warp / wpt owns tiles m, m + nteams, ... ----------------
     const int G = prm.G;
-    const int spw = 32 / G;
-    const int gsub = lane / spw;
+    const int spw = 32 / G;              // sites per warp per iteration
+    const int gsub = lane / spw;         // which part of the row this lane walks
     const int sl = lane % spw;
-    const int sites_per_iter = K1_THREADS / G;
+    const int nteams = K1_WARPS / prm.wpt;
+    const int team = warp / prm.wpt, lw = warp % prm.wpt;
+    const int sites_per_iter = prm.wpt * spw;
 
     Acc<QI, QD> acc;
 #pragma unroll
@@ -228,80 +274,54 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_site_pass(const __grid_const
     const int seg_first = (MODE == MODE_COUNTS) ? 0 : prm.cta_seg_first[b];
     const int64_t slot_base = (MODE == MODE_COUNTS) ? 0 : prm.cta_slot_off[b];
 
-    for (int64_t t = t0; t < t1; ++t) {
-        const int it = (int)(t - t0);
+    for (int it = team; it < ntiles; it += nteams) {
         const int stage = it % prm.stages;
-        const uint32_t parity = (uint32_t)((it / prm.stages) & 1);
-        mbar_wait(&full[stage], parity);
+        mbar_wait(&full[stage], (uint32_t)((it / prm.stages) & 1));
         const uint8_t* tile = tiles + (size_t)stage * prm.tile_bytes;
-        const int64_t tile_site0 = prm.site_begin + t * prm.T;
+        const int64_t tile_site0 = prm.site_begin + (t0 + it) * prm.T;
 
         for (int i = 0; i < prm.I; ++i) {
-            const int slot = i * sites_per_iter + warp * spw + sl;
+            const int slot = i * sites_per_iter + lw * spw + sl;
             const int64_t site = tile_site0 + slot;
             const bool valid = site < prm.site_end;
+            const bool owner = valid && (gsub == 0);
             const uint4* row = reinterpret_cast<const uint4*>(tile + (size_t)(valid ? slot : 0) * prm.pitch);
+            // the position is needed last: issue its load first so that the counting hides the latency
+            int posv = 0;
+            if (MODE != MODE_COUNTS) posv = owner ? __ldg(prm.pos + site) : 0;
 
             uint32_t n[P], c[P][4];
 #pragma unroll
             for (int X = 0; X < P; ++X) {
-                uint32_t tn = 0, ts0 = 0, ts1 = 0, ts01 = 0;
-                // full 16-byte chunks of the population's main contiguous run (no mask loads)
-                {
+                Tally t;
+                tally_init(t);
+                {   // the population's main run of fully-owned 16-byte chunks: no masks
                     int ch = prm.full_lo[X] + gsub;
                     const int hi = prm.full_hi[X];
-                    while (ch < hi) {
-                        uint32_t av = 0, a0 = 0, a1 = 0, a01 = 0;
-                        int end = ch + 60 * G;           // byte lanes hold <= 4 per chunk: flush before 255
-                        if (end > hi) end = hi;
-#pragma unroll 2
-                        for (; ch < end; ch += G) {
-                            const uint4 w = row[ch];
-                            K1_ACC_CHUNK(w, 0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u)
-                        }
-                        tn = hsum4(av, tn);
-                        ts0 = hsum4(a0, ts0);
-                        ts1 = hsum4(a1, ts1);
-                        ts01 = hsum4(a01, ts01);
-                    }
+                    for (; ch + 2 * G < hi; ch += 3 * G) add_chunks3(t, row[ch], row[ch + G], row[ch + 2 * G]);
+                    if (ch + G < hi) add_chunks2(t, row[ch], row[ch + G]);
+                    else if (ch < hi) add_chunks1(t, row[ch]);
                 }
-                // chunks shared with other populations / unused haplotypes / row padding: masked
-                {
+                {   // chunks shared with other populations / unused haplotypes / row padding: masked
                     int e = prm.ent_lo[X] + gsub;
                     const int hi = prm.ent_hi[X];
-                    while (e < hi) {
-                        uint32_t av = 0, a0 = 0, a1 = 0, a01 = 0;
-                        int end = e + 60 * G;
-                        if (end > hi) end = hi;
-                        for (; e < end; e += G) {
-                            const uint4 m = s_ent_mask[e];
-                            const uint4 w = row[s_ent_chunk[e]];
-                            K1_ACC_CHUNK(w, m.x, m.y, m.z, m.w)
-                        }
-                        tn = hsum4(av, tn);
-                        ts0 = hsum4(a0, ts0);
-                        ts1 = hsum4(a1, ts1);
-                        ts01 = hsum4(a01, ts01);
-                    }
+                    for (; e + G < hi; e += 2 * G)
+                        add_chunks2(t, and4(row[s_ent_chunk[e]], s_ent_mask[e]), and4(row[s_ent_chunk[e + G]], s_ent_mask[e + G]));
+                    if (e < hi) add_chunks1(t, and4(row[s_ent_chunk[e]], s_ent_mask[e]));
                 }
+                byte_flush(t);
                 // combine the G lanes of this site (16-bit fields: counts < 65536)
-                uint32_t p0 = tn | (ts0 << 16), p1 = ts1 | (ts01 << 16);
+                uint32_t p0 = t.tA | (t.tC << 16), p1 = t.tG | (t.tT << 16);
                 for (int d = spw; d < 32; d <<= 1) {
                     p0 += __shfl_xor_sync(0xffffffffu, p0, d);
                     p1 += __shfl_xor_sync(0xffffffffu, p1, d);
                 }
-                tn = p0 & 0xffffu;
-                ts0 = p0 >> 16;
-                ts1 = p1 & 0xffffu;
-                ts01 = p1 >> 16;
-                n[X] = tn;
-                c[X][3] = ts01;
-                c[X][1] = ts0 - ts01;
-                c[X][2] = ts1 - ts01;
-                c[X][0] = tn - ts0 - ts1 + ts01;
+                c[X][0] = p0 & 0xffffu;
+                c[X][1] = p0 >> 16;
+                c[X][2] = p1 & 0xffffu;
+                c[X][3] = p1 >> 16;
+                n[X] = c[X][0] + c[X][1] + c[X][2] + c[X][3];
             }
-
-            const bool owner = valid && (gsub == 0);
 
             if (MODE == MODE_COUNTS) {
                 if (owner) {
@@ -339,7 +359,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_site_pass(const __grid_const
                 const bool ragged = owner && !allpres && !allmiss;
                 acc.i[0] += pres ? 1 : 0;
                 acc.i[1] += ragged ? 1 : 0;
-                acc.i[2] += owner ? (long long)__ldg(prm.pos + site) : 0ll;
+                acc.i[2] += (long long)posv;
                 const uint32_t f = pres ? 1u : 0u;
 #pragma unroll
                 for (int X = 0; X < P; ++X) {
@@ -370,42 +390,46 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_site_pass(const __grid_const
 #pragma unroll
                 for (int X = 0; X < 4; ++X) good = good && ((int)n[X] >= prm.thr[X]);
                 acc.i[1] += good ? 1 : 0;
-                acc.i[2] += owner ? (long long)__ldg(prm.pos + site) : 0ll;
-                if (good && n[3] > 0) {
+                acc.i[2] += (long long)posv;
+                // derived allele: present overall, absent in the outgroup (1672). With two alleles overall and a
+                // non-empty outgroup at most one allele qualifies, so one body serves the whole warp.
+                int da = -1;
 #pragma unroll
-                    for (int a = 0; a < 4; ++a) {
-                        if (tot[a] > 0 && c[3][a] == 0) {   // derived: present overall, absent in the outgroup (1672)
-                            const double p1 = (double)c[0][a] / (double)n[0];
-                            const double p2 = (double)c[1][a] / (double)n[1];
-                            const double p3 = (double)c[2][a] / (double)n[2];
-                            const double p4 = (double)c[3][a] / (double)n[3];
-                            const double abba = (1 - p1) * p2 * p3 * (1 - p4);
-                            const double baba = p1 * (1 - p2) * p3 * (1 - p4);
-                            const double pd = p2 * (p2 > p3 ? 1.0 : 0.0) + p3 * (p3 >= p2 ? 1.0 : 0.0);
-                            const double fd_den = (1 - p1) * pd * pd * (1 - p4) - p1 * (1 - pd) * pd * (1 - p4);
-                            const bool A = p3 > p1, Bq = p3 > p2, Xq = p1 > p2, Yq = !Xq;
-                            const double xa = (Xq && A) ? 1.0 : 0.0, yb = (Yq && Bq) ? 1.0 : 0.0;
-                            const double xna = (Xq && !A) ? 1.0 : 0.0, ynb = (Yq && !Bq) ? 1.0 : 0.0;
-                            const double pdm1 = p3 * xa + p1 * (1.0 - xa);
-                            const double pdm2 = p3 * yb + p2 * (1.0 - yb);
-                            const double pdm3 = -p3 * xa + p3 * yb - p1 * xna + p2 * ynb;
-                            const double fdm_den =
-                                (1 - pdm1) * pdm2 * pdm3 * (1 - p4) - pdm1 * (1 - pdm2) * pdm3 * (1 - p4);
-                            acc.i[0] += 1;
-                            acc.d[0] += abba;
-                            acc.d[1] += baba;
-                            acc.d[2] += abba - baba;
-                            acc.d[3] += abba + baba;
-                            acc.d[4] += fd_den;
-                            acc.d[5] += fdm_den;
-                        }
-                    }
+                for (int a = 0; a < 4; ++a)
+                    if (tot[a] > 0 && c[3][a] == 0) da = a;
+                const bool hit = good && n[3] > 0 && da >= 0;
+                if (hit) {
+                    const uint32_t k1 = da == 0 ? c[0][0] : (da == 1 ? c[0][1] : (da == 2 ? c[0][2] : c[0][3]));
+                    const uint32_t k2 = da == 0 ? c[1][0] : (da == 1 ? c[1][1] : (da == 2 ? c[1][2] : c[1][3]));
+                    const uint32_t k3 = da == 0 ? c[2][0] : (da == 1 ? c[2][1] : (da == 2 ? c[2][2] : c[2][3]));
+                    const double p1 = (double)k1 / (double)n[0];
+                    const double p2 = (double)k2 / (double)n[1];
+                    const double p3 = (double)k3 / (double)n[2];
+                    const double p4 = 0.0 / (double)n[3];
+                    const double abba = (1 - p1) * p2 * p3 * (1 - p4);
+                    const double baba = p1 * (1 - p2) * p3 * (1 - p4);
+                    const double pd = p2 * (p2 > p3 ? 1.0 : 0.0) + p3 * (p3 >= p2 ? 1.0 : 0.0);
+                    const double fd_den = (1 - p1) * pd * pd * (1 - p4) - p1 * (1 - pd) * pd * (1 - p4);
+                    const bool A = p3 > p1, Bq = p3 > p2, Xq = p1 > p2, Yq = !Xq;
+                    const double xa = (Xq && A) ? 1.0 : 0.0, yb = (Yq && Bq) ? 1.0 : 0.0;
+                    const double xna = (Xq && !A) ? 1.0 : 0.0, ynb = (Yq && !Bq) ? 1.0 : 0.0;
+                    const double pdm1 = p3 * xa + p1 * (1.0 - xa);
+                    const double pdm2 = p3 * yb + p2 * (1.0 - yb);
+                    const double pdm3 = -p3 * xa + p3 * yb - p1 * xna + p2 * ynb;
+                    const double fdm_den = (1 - pdm1) * pdm2 * pdm3 * (1 - p4) - pdm1 * (1 - pdm2) * pdm3 * (1 - p4);
+                    acc.i[0] += 1;
+                    acc.d[0] += abba;
+                    acc.d[1] += baba;
+                    acc.d[2] += abba - baba;
+                    acc.d[3] += abba + baba;
+                    acc.d[4] += fd_den;
+                    acc.d[5] += fdm_den;
                 }
             }
         }
 
-        __syncthreads();   // every lane is done with this stage's bytes
-        if (tid == 0 && t + prm.stages < t1) issue(t + prm.stages, stage);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);   // this warp is done with the stage's bytes
     }
     if (MODE != MODE_COUNTS) warp_flush<QI, QD>(acc, cur_seg, prm.part, slot_base, seg_first, warp, lane);
 }
@@ -590,12 +614,20 @@ void build_tables(const std::vector<int32_t>& hap_pop_local, int H, int chunks, 
             for (int wd = 0; wd < 4; ++wd) {
                 uint32_t m = 0;
                 for (int by = 0; by < 4; ++by)
-                    if (cm[cidx] & (1u << (wd * 4 + by))) m |= 0x01u << (8 * by);
+                    if (cm[cidx] & (1u << (wd * 4 + by))) m |= 0xffu << (8 * by);
                 t.ent_mask.push_back(m);
             }
         }
         t.ent_hi[X] = (int)t.ent_chunk.size();
     }
+}
+
+int check_plan(const K1Plan& pl) {
+    const bool pow2G = pl.G >= 1 && pl.G <= 32 && (pl.G & (pl.G - 1)) == 0;
+    const bool okw = pl.wpt == 1 || pl.wpt == 2 || pl.wpt == 4 || pl.wpt == 8;
+    PG_CHECK(pow2G && okw && pl.I >= 1 && pl.stages >= 2 && pl.stages <= 8 && pl.smem_bytes <= 227 * 1024,
+             "invalid site-pass geometry G=%d wpt=%d I=%d stages=%d smem=%d", pl.G, pl.wpt, pl.I, pl.stages, pl.smem_bytes);
+    return PG_OK;
 }
 
 struct K1Launch {
@@ -650,6 +682,8 @@ int prepare_windowed(pg_ctx* ctx, const std::vector<int32_t>& hap_pop_local, int
     L.plan = pg_make_k1_plan(ctx->S, ctx->H, ctx->sm_count, table_bytes);
     PG_CHECK(L.plan.stages >= 2, "rows of %d haplotypes are too long for the site-pass kernel (pitch %d bytes)", ctx->H,
              L.plan.pitch);
+    PG_TRY(check_plan(L.plan));
+    for (int X = 0; X < Ppad; ++X) PG_CHECK(pt.popN[X] <= 65535, "a population has more than 65535 haplotypes");
     const K1Plan& pl = L.plan;
     const int B = pl.ctas;
     const int nseg = (int)ctx->brk.size() - 1;
@@ -723,6 +757,7 @@ int prepare_windowed(pg_ctx* ctx, const std::vector<int32_t>& hap_pop_local, int
     p.G = pl.G;
     p.I = pl.I;
     p.T = pl.T;
+    p.wpt = pl.wpt;
     p.stages = pl.stages;
     p.tile_bytes = pl.tile_bytes;
     p.ent_chunk = dt.ent_chunk;
@@ -967,6 +1002,7 @@ extern "C" int pg_site_counts(pg_ctx* ctx, int64_t site0, int64_t n, uint16_t* c
             K1Launch L;
             L.plan = pg_make_k1_plan(cnt, ctx->H, ctx->sm_count, table_bytes);
             PG_CHECK(L.plan.stages >= 2, "rows of %d haplotypes are too long for the site-pass kernel", ctx->H);
+            PG_TRY(check_plan(L.plan));
             PG_TRY(ctx->tables.ensure((size_t)n_ent * 20 + 4096));
             uint8_t* base = (uint8_t*)ctx->tables.p;
             size_t o = 0;
@@ -985,6 +1021,7 @@ extern "C" int pg_site_counts(pg_ctx* ctx, int64_t site0, int64_t n, uint16_t* c
             p.G = L.plan.G;
             p.I = L.plan.I;
             p.T = L.plan.T;
+            p.wpt = L.plan.wpt;
             p.stages = L.plan.stages;
             p.tile_bytes = L.plan.tile_bytes;
             p.ent_chunk = d_chunk;

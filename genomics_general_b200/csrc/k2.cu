@@ -42,55 +42,72 @@ __device__ __forceinline__ void cp_async_wait() {
 // ------------------------------------------------------------------------------------------------
 // bit-plane build
 // ------------------------------------------------------------------------------------------------
-constexpr int BP_SITES = 256, BP_COLS = 256, BP_ROWW = BP_COLS / 4 + 1;   // 65 words per site row
-constexpr int BP_SMEM = BP_SITES * BP_ROWW * 4 + 3 * BP_COLS * 8 * 4 + BP_COLS * 4;
+constexpr int BP_SITES = 256, BP_COLS = 128, BP_ROWW = BP_COLS / 4 + 1;   // 33 words per site row (odd: no conflicts)
+constexpr int BP_SMEM = BP_SITES * BP_ROWW * 4 + 3 * BP_COLS * 8 * 4 + BP_COLS * 4 + BP_COLS * 4 + 16;
 
+// Resident code: A 0x01, C 0x04, G 0x10, T 0x40, missing 0x00  ->  bit0 = C|T (0x44), bit1 = G|T (0x50), valid = !=0
 __global__ void __launch_bounds__(256) k2_build_planes(const uint8_t* __restrict__ geno, int pitch, int64_t S,
                                                        int64_t site_base, const int32_t* __restrict__ col_to_row,
                                                        uint32_t* __restrict__ planes, int Hk, int64_t NWp) {
     extern __shared__ __align__(16) uint8_t bsm[];
-    uint32_t* tile = reinterpret_cast<uint32_t*>(bsm);                          // [256][65]
-    uint32_t* outp = tile + BP_SITES * BP_ROWW;                                  // [3][256][8]
-    int32_t* s_c2r = reinterpret_cast<int32_t*>(outp + 3 * BP_COLS * 8);        // [256]
+    uint32_t* tile = reinterpret_cast<uint32_t*>(bsm);                          // [256][33]
+    uint32_t* outp = tile + BP_SITES * BP_ROWW;                                  // [3][128][8]
+    int32_t* s_c2r = reinterpret_cast<int32_t*>(outp + 3 * BP_COLS * 8);        // [128] plane row of a local column
+    int32_t* s_used = s_c2r + BP_COLS;                                           // [128] compact list of used columns
+    int32_t* s_nused = s_used + BP_COLS;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int col0 = blockIdx.x * BP_COLS;
     const int64_t sblk = blockIdx.y;
     const int64_t site0 = site_base + sblk * BP_SITES;
 
-    {
+    if (tid < BP_COLS) {
         const int col = col0 + tid;
         s_c2r[tid] = (col < pitch) ? col_to_row[col] : -1;
     }
-    // load 256 sites x 256 columns (16-byte vectors, 2 rows per warp instruction)
-    for (int pass = 0; pass < 16; ++pass) {
-        const int r = pass * 16 + warp * 2 + (lane >> 4);
-        const int c16 = lane & 15;
-        const int64_t site = site0 + r;
-        const int col = col0 + c16 * 16;
-        uint4 v = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-        if (site < S && col < pitch) v = *reinterpret_cast<const uint4*>(geno + site * pitch + col);
-        uint32_t* d = tile + r * BP_ROWW + c16 * 4;
-        d[0] = v.x;
-        d[1] = v.y;
-        d[2] = v.z;
-        d[3] = v.w;
+    // 256 sites x 128 columns: 8 lanes cover one row segment; all 8 passes are in flight together
+    {
+        uint4 v[8];
+#pragma unroll
+        for (int pass = 0; pass < 8; ++pass) {
+            const int r = pass * 32 + warp * 4 + (lane >> 3);
+            const int64_t site = site0 + r;
+            const int col = col0 + (lane & 7) * 16;
+            v[pass] = make_uint4(0u, 0u, 0u, 0u);
+            if (site < S && col < pitch) v[pass] = *reinterpret_cast<const uint4*>(geno + site * pitch + col);
+        }
+#pragma unroll
+        for (int pass = 0; pass < 8; ++pass) {
+            const int r = pass * 32 + warp * 4 + (lane >> 3);
+            uint32_t* d = tile + r * BP_ROWW + (lane & 7) * 4;
+            d[0] = v[pass].x;
+            d[1] = v[pass].y;
+            d[2] = v[pass].z;
+            d[3] = v[pass].w;
+        }
     }
     __syncthreads();
-    // warp w transposes sites 32w..32w+31 (lane = site) for every used column
-    const uint32_t* myrow = tile + (warp * 32 + lane) * BP_ROWW;
-    for (int cw = 0; cw < BP_COLS / 4; ++cw) {
-        const uint32_t word = myrow[cw];
-#pragma unroll
-        for (int by = 0; by < 4; ++by) {
-            const int cl = cw * 4 + by;
-            if (s_c2r[cl] < 0) continue;                 // warp-uniform
-            const uint32_t b = (word >> (8 * by)) & 0xffu;
-            const bool valid = (b & 0x80u) == 0;
-            const uint32_t m = __ballot_sync(0xffffffffu, valid);
-            const uint32_t b0 = __ballot_sync(0xffffffffu, valid && (b & 1u));
-            const uint32_t b1 = __ballot_sync(0xffffffffu, valid && (b & 2u));
-            if (lane < 3) outp[(lane * BP_COLS + cl) * 8 + warp] = (lane == 0) ? b0 : (lane == 1 ? b1 : m);
+    if (warp == 0) {   // ordered compaction of the used columns
+        int base = 0;
+        for (int c = 0; c < BP_COLS; c += 32) {
+            const bool u = s_c2r[c + lane] >= 0;
+            const unsigned m = __ballot_sync(0xffffffffu, u);
+            if (u) s_used[base + __popc(m & ((1u << lane) - 1u))] = c + lane;
+            base += __popc(m);
         }
+        if (lane == 0) *s_nused = base;
+    }
+    __syncthreads();
+    const int nused = *s_nused;
+    // warp w transposes sites 32w..32w+31 (lane = site) for every used column
+    const uint8_t* myrow = reinterpret_cast<const uint8_t*>(tile + (warp * 32 + lane) * BP_ROWW);
+#pragma unroll 4
+    for (int u = 0; u < nused; ++u) {
+        const int cl = s_used[u];
+        const uint32_t b = myrow[cl];
+        const uint32_t m = __ballot_sync(0xffffffffu, b != 0u);
+        const uint32_t b0 = __ballot_sync(0xffffffffu, (b & 0x44u) != 0u);
+        const uint32_t b1 = __ballot_sync(0xffffffffu, (b & 0x50u) != 0u);
+        if (lane < 3) outp[(lane * BP_COLS + cl) * 8 + warp] = (lane == 0) ? b0 : (lane == 1 ? b1 : m);
     }
     __syncthreads();
     for (int idx = tid; idx < 3 * BP_COLS * 2; idx += 256) {

@@ -62,7 +62,8 @@ struct K1Plan {
     int chunks;       // 16-byte chunks per row
     int G;            // lanes cooperating on one site (power of two, <= 32)
     int I;            // sites per lane per tile
-    int T;            // sites per tile = (256 / G) * I
+    int wpt;          // consumer warps per tile (a "team"); 8 / wpt teams work on different tiles
+    int T;            // sites per tile = (32 * wpt / G) * I
     int stages;       // TMA ring depth
     int tile_bytes;   // T * pitch
     int smem_bytes;   // dynamic shared memory of the kernel
