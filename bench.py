@@ -1,0 +1,393 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark: sites/s of popgenWindows (pi + Fst + Dxy) on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's algorithm on the host cores
+
+Workload (BASELINE.json configs[1], "C2"): 4 populations x 50 diploid samples (H = 400 haplotypes),
+10 M synthetic sites per GPU, -w 50000 coordinate windows (~5000 sites each), -m 100, minData 0.01.
+A "step" is one pass of the hot path (site pass -> window statistics -> rows on the host) over that
+batch.  Headline variant: no missing genotypes (closed-form K1 path, the HBM-roofline kernel); the
+2 %-missing variant (pairwise K2 path) is reported next to it under "variants".
+
+  value : whole-job sites/s with the int8 matrix already resident in HBM (inputs 4 GB >> 126 MB L2)
+  e2e   : same metric through the public API from pinned HOST buffers: H2D of the matrix + positions,
+          device transcode, statistics, D2H of the rows — every step
+  roofline / cpu_baseline : see the task contract; cpu_baseline is the loop-faithful oracle port
+          (oracle/ref_port.py — the reference is Python and cannot travel to the GPU box) on a bounded sample.
+
+Multi-GPU: one process per GPU (torchrun); weak scaling — every rank owns 10 M sites of a longer genome,
+computes its own windows with no data-path collective, and the per-window records are all-gathered once
+per step (torch.distributed / NCCL).  Time = max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+METRIC = "sites/sec popgenWindows (pi+Fst+Dxy)"
+N_POPS, SAMPLES_PER_POP, PLOIDY = 4, 50, 2
+WIND_SIZE, MIN_SITES, MIN_DATA = 50000, 100, 0.01
+SEED = 20260923 + 2
+
+
+def env_int(name, dflt):
+    try:
+        return int(os.environ.get(name, dflt))
+    except ValueError:
+        return dflt
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampled DURING the timed regions
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        def pump():
+            for line in self.proc.stdout:
+                self.samples.append((time.perf_counter(), line.strip()))
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()          # exactly the process we started
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, intervals):
+        sm, mx, reasons = [], [], set()
+        for t, line in self.samples:
+            if not any(a <= t <= b for a, b in intervals):
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline: the reference's algorithm (loop-faithful port) on the host cores
+# ------------------------------------------------------------------------------------------------
+def _cpu_window(args):
+    seed, site0, L, miss = args
+    import warnings
+    from genomics_general_b200 import synth
+    from oracle import ref_port                                  # the checker, timed as the CPU baseline
+    spec = synth.SynthSpec(N_POPS, SAMPLES_PER_POP, PLOIDY, seed=seed, miss=miss)
+    g = synth.synth_genotypes(spec, site0, L)
+    t = time.perf_counter()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref_port.popgen_window_port(g, spec.hap_pop(), N_POPS, MIN_SITES, MIN_DATA)
+    return time.perf_counter() - t
+
+
+def cpu_sample(pool, cores, windows, L, miss, seed):
+    """`windows` windows of L sites spread over `cores` processes; returns (sites, wall seconds)."""
+    jobs = [(seed, k * L, L, miss) for k in range(windows)]
+    t = time.perf_counter()
+    pool.map(_cpu_window, jobs, chunksize=1)
+    return windows * L, time.perf_counter() - t
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path (oracle port), all host cores."""
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = host_cores()
+    L = env_int("PG_BENCH_CPU_WINDOW_SITES", 5000)
+    wins = cores
+    with mp.get_context("fork").Pool(cores) as pool:
+        for _ in range(max(args.warmup, 0)):
+            cpu_sample(pool, cores, wins, L, 0.0, SEED)
+        t0 = time.perf_counter()
+        sites = 0
+        for k in range(args.steps):
+            s, _ = cpu_sample(pool, cores, wins, L, 0.0, SEED + k)
+            sites += s
+        dt = time.perf_counter() - t0
+    value = sites / dt
+    sample = "%d windows x %d sites per step (one window per core), numeric core only (no text parsing)" % (wins, L)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "sites/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64",
+            "data": "synthetic", "config": workload_config(args, world),
+            "cpu_baseline": {"value": value, "unit": "sites/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "sites/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": "C2 popgenWindows: %d pops x %d diploid samples (H=%d), %d sites per GPU, -w %d coordinate "
+                        "windows, -m %d, minData %g, miss=0 (closed-form path)" %
+                        (N_POPS, SAMPLES_PER_POP, N_POPS * SAMPLES_PER_POP * PLOIDY, args.sites, WIND_SIZE, MIN_SITES,
+                         MIN_DATA),
+            "sites_per_gpu": args.sites, "haplotypes": N_POPS * SAMPLES_PER_POP * PLOIDY, "windows_per_gpu": None,
+            "sharding": "windows (one shard per GPU), one all-gather of rows" if world > 1 else "single GPU",
+            "l2": "inputs (%.1f GB per GPU) are larger than L2; no flush needed" %
+                  (args.sites * (N_POPS * SAMPLES_PER_POP * PLOIDY) / 1e9)}
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=("b200", "reference"))
+    ap.add_argument("--sites", type=int, default=env_int("PG_BENCH_SITES", 10_000_000))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    # fork the CPU-baseline workers BEFORE any CUDA state exists in this process
+    cpu_pool = None
+    if rank == 0 and not args.no_cpu_baseline:
+        import multiprocessing as mp
+        cpu_pool = mp.get_context("fork").Pool(host_cores())
+
+    from genomics_general_b200 import multigpu, synth, windows
+    from genomics_general_b200.engine import Engine, PinnedArray
+
+    dist = None
+    dev = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        torch.cuda.set_device(local_rank)
+        dev = torch.device("cuda", local_rank)
+        dist.init_process_group(backend="nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    S, P = args.sites, N_POPS
+    H = N_POPS * SAMPLES_PER_POP * PLOIDY
+    eng = Engine(local_rank)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    intervals = []
+
+    def positions():
+        pos = np.empty(S, dtype=np.int32)
+        step = 1 << 22
+        for s0 in range(0, S, step):
+            n = min(step, S - s0)
+            eng.download(s0, n, want_geno=False, into_pos=pos[s0:s0 + n])
+        return pos
+
+    def make_windows(pos):
+        ws = windows.sliding_coord_windows(np.zeros(S, dtype=np.int32), ["chr1"], pos, WIND_SIZE)
+        return ws.ranges()
+
+    counts = None
+
+    def step_resident():
+        r = eng.popgen(MIN_SITES, MIN_DATA)
+        if dist is not None:
+            rec = multigpu.all_gather_rows(multigpu.popgen_records(r), counts, device=dev)
+            return rec
+        return r
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        l0 = eng.launch_count()
+        t0 = time.perf_counter()
+        k1 = []
+        for _ in range(steps):
+            fn()
+            tm = eng.last_timings()
+            k1.append(tm)
+        dt_local = time.perf_counter() - t0          # every step ends with a device->host read (synchronised)
+        barrier()
+        intervals.append((t0, t0 + dt_local))
+        return max_over_ranks(dt_local), k1, eng.launch_count() - l0
+
+    # ---------------- leg 1: resident matrix, no missing data (K1 closed form) ----------------
+    spec0 = synth.SynthSpec(N_POPS, SAMPLES_PER_POP, PLOIDY, seed=SEED + 1000 * rank, miss=0.0)
+    eng.synth_fill(spec0, S)
+    eng.set_pops(spec0.hap_pop(), P)
+    pos = positions()
+    lo, hi = make_windows(pos)
+    W = len(lo)
+    eng.set_windows(lo, hi)
+    if dist is not None:
+        import torch
+        cnt = torch.tensor([W], dtype=torch.int64, device=dev)
+        allc = [torch.zeros_like(cnt) for _ in range(world)]
+        dist.all_gather(allc, cnt)
+        counts = [int(c.item()) for c in allc]
+    dt, tms, launches = timed(step_resident, args.steps, args.warmup)
+    value = world * S * args.steps / dt
+    k1_ms = float(np.mean([t["k1_popgen"]["ms"] for t in tms if "k1_popgen" in t]))
+    kernel_ms = {k: float(np.mean([t[k]["ms"] for t in tms if k in t])) for k in tms[-1]}
+    paths0 = np.bincount(eng.popgen(MIN_SITES, MIN_DATA)["path"], minlength=3).tolist()
+
+    # ---------------- leg 2: end to end from pinned host buffers ----------------
+    e2e = None
+    if not args.no_e2e:
+        hg = PinnedArray((S, H), np.int8)
+        hp = PinnedArray((S,), np.int32)
+        slab = 1 << 20
+        for s in range(0, S, slab):
+            n = min(slab, S - s)
+            eng.download(s, n, into_geno=hg.array[s:s + n], into_pos=hp.array[s:s + n])
+
+        def step_e2e():
+            eng.upload(hg.array, hp.array)            # H2D from pinned memory + device transcode
+            eng.set_windows(lo, hi)
+            return step_resident()                    # statistics + D2H of the rows (+ all-gather when N > 1)
+
+        e_steps = max(3, min(args.steps, 10))
+        dt_e, _, _ = timed(step_e2e, e_steps, 1)
+        npairs = P * (P - 1) // 2
+        e2e = {"value": world * S * e_steps / dt_e, "unit": "sites/s", "h2d_bytes_per_step": int(S) * (H + 4),
+               "d2h_bytes_per_step": int(W) * (8 * (P + 2 * npairs) + 20), "steps": e_steps,
+               "ms_per_step": 1e3 * dt_e / e_steps}
+        hg.close()
+        hp.close()
+
+    # ---------------- leg 3: 2 % missing genotypes (K2 pairwise path) ----------------
+    spec2 = synth.SynthSpec(N_POPS, SAMPLES_PER_POP, PLOIDY, seed=SEED + 1000 * rank, miss=0.02)
+    eng.synth_fill(spec2, S)
+    eng.set_pops(spec2.hap_pop(), P)
+    eng.set_windows(lo, hi)
+    v_steps = max(2, min(args.steps, 5))
+    dt2, tms2, _ = timed(step_resident, v_steps, 1)
+    kernel_ms2 = {k: float(np.mean([t[k]["ms"] for t in tms2 if k in t])) for k in tms2[-1]}
+    pair_sites = S * (H * (H - 1) // 2)
+    variants = {"miss=0.02 (pairwise K2 path)": {
+        "value": world * S * v_steps / dt2, "unit": "sites/s", "ms_per_step": 1e3 * dt2 / v_steps,
+        "kernel_ms": kernel_ms2,
+        "pair_sites_per_s": pair_sites / (kernel_ms2.get("k2_pair", float("nan")) * 1e-3),
+        "bound": "integer issue (POPC on the XU pipe), not HBM"}}
+
+    sampler.stop()
+    clocks = sampler.summary(intervals)
+
+    if rank != 0:
+        eng.close()
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline of the dominant kernel (k1_site_pass, popgen mode) ----------------
+    peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    try:
+        mp_ = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+        peak, peak_src = float(mp_["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    except Exception:
+        pass
+    alg_bytes = S * (H + 4)
+    achieved = alg_bytes / (k1_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(REPO, "profiles", "k1_traffic.json")))["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "k1_site_pass<POPGEN,4>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k1_ms}
+
+    # ---------------- CPU baseline on a bounded sample ----------------
+    cpu = None
+    if cpu_pool is not None:
+        cores = host_cores()
+        L = env_int("PG_BENCH_CPU_WINDOW_SITES", 5000)
+        with cpu_pool as pool:
+            sites, wall = cpu_sample(pool, cores, cores, L, 0.0, SEED)
+            reps = 1
+            while wall < 10.0 and reps < 4:      # bounded: ~10-30 s of CPU work
+                s2, w2 = cpu_sample(pool, cores, cores, L, 0.0, SEED + reps)
+                sites += s2
+                wall += w2
+                reps += 1
+        cpu = {"value": sites / wall, "unit": "sites/s", "cores": cores, "kind": "port",
+               "sample": "%d windows x %d sites, one window per core at a time (oracle/ref_port.py: the reference's "
+                         "O(N^2) pair loops; numeric core only, no text parsing)" % (reps * cores, L)}
+
+    cfg = workload_config(args, world)
+    cfg["windows_per_gpu"] = int(W)
+    cfg["paths"] = {"failed": paths0[0], "closed_form_K1": paths0[1], "pairwise_K2": paths0[2]}
+    line = {"metric": METRIC, "value": value, "unit": "sites/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": cfg, "clocks": clocks, "e2e": e2e,
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "kernel_ms": kernel_ms,
+            "variants": variants}
+    print(json.dumps(line), flush=True)
+    eng.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,159 @@
+"""Shared pieces of the four drop-in command lines (flag handling that the reference repeats in every
+script: windows, populations, ploidy, files).  Citations are /root/reference/<file>:<line>."""
+from __future__ import annotations
+
+import gzip
+import sys
+
+import numpy as np
+
+from .. import geno_io, windows as W
+
+
+def add_window_args(p, overlap_short=True, cat=False):
+    """popgenWindows.py:172-178 / ABBABABAwindows.py:111-117 / distMat.py:118-128"""
+    choices = ("sites", "coordinate", "predefined") + (("cat",) if cat else ())
+    p.add_argument("--windType", help="Type of windows to make", choices=choices, default="coordinate")
+    p.add_argument("-w", "--windSize", help="Window size in bases", type=int, metavar="sites")
+    p.add_argument("-s", "--stepSize", help="Step size for sliding window", type=int, metavar="sites")
+    p.add_argument("-m", "--minSites", help="Minumum good sites per window", type=int, metavar="sites", default=1)
+    if overlap_short:
+        p.add_argument("-O", "--overlap", help="Overlap for sites sliding window", type=int, metavar="sites")
+    else:
+        p.add_argument("--overlap", help="Overlap for sites sliding window", type=int, metavar="sites")
+    p.add_argument("-D", "--maxDist", help="Maximum span distance for sites window", type=int)
+    p.add_argument("--windCoords", help="Window coordinates file (scaffold start end)")
+
+
+def add_engine_args(p):
+    p.add_argument("--device", help="CUDA device index", type=int, default=0)
+    p.add_argument("--parseThreads", help="Host threads for the .geno tokenizer", type=int, default=None)
+
+
+def check_window_args(args, with_id=False):
+    """The reference's assertions (popgenWindows.py:218-244). Returns (minSites, windCoords)."""
+    coords = None
+    if args.windType == "coordinate":
+        assert args.windSize, "Window size must be provided."
+        assert not args.overlap, "Overlap does not apply to coordinate windows. Use --stepSize instead."
+        assert not args.maxDist, "Maximum distance only applies to sites windows."
+    elif args.windType == "sites":
+        assert args.windSize, "Window size (number of sites) must be provided."
+        assert not args.stepSize, "Step size only applies to coordinate windows. Use --overlap instead."
+    elif args.windType == "predefined":
+        assert args.windCoords, "Please provide a file of window coordinates."
+        assert not args.overlap, "Overlap does not apply for predefined windows."
+        assert not args.maxDist, "Maximum does not apply for predefined windows."
+        assert not args.stepSize, "Step size does not apply for predefined windows."
+        assert not args.include, "You cannot only include specific scaffolds if using predefined windows."
+        assert not args.exclude, "You cannot exclude specific scaffolds if using predefined windows."
+        coords = []
+        with open(args.windCoords, "rt") as wc:
+            for line in wc:
+                f = line.split()
+                if not f:
+                    continue
+                c = (f[0], int(f[1]), int(f[2]))
+                if with_id and len(f) > 3:
+                    c += (f[3],)
+                coords.append(c)
+    minSites = args.minSites
+    if not minSites:
+        minSites = args.windSize
+    return minSites, coords
+
+
+def read_scaffold_list(path):
+    if not path:
+        return None
+    with open(path, "rt") as f:
+        return [line.rstrip() for line in f.readlines()]
+
+
+def parse_pop_args(pop_args, pops_file):
+    """-p name [a,b,c] ... + --popsFile  (popgenWindows.py:259-277)."""
+    popNames, popInds = [], []
+    for p in pop_args:
+        popNames.append(p[0])
+        popInds.append(p[1].split(",") if len(p) > 1 else [])
+    if pops_file:
+        with open(pops_file, "rt") as pf:
+            popDict = dict([ln.split() for ln in pf if ln.strip()])
+        for ind in popDict.keys():
+            if popDict[ind] in popNames:
+                popInds[popNames.index(popDict[ind])].append(ind)
+    for p in popInds:
+        assert len(p) >= 1, "All populations must be represented by at least one sample."
+    return popNames, popInds
+
+
+def ploidy_dict(args, allInds, haploid_list):
+    """popgenWindows.py:293-305."""
+    if getattr(args, "ploidy", None) is not None:
+        ploidy = args.ploidy if len(args.ploidy) != 1 else args.ploidy * len(allInds)
+        assert len(ploidy) == len(allInds), "Incorrect number of ploidy values supplied."
+        return dict(zip(allInds, ploidy))
+    if getattr(args, "ploidyFile", None) is not None:
+        with open(args.ploidyFile, "rt") as pf:
+            return dict([[s[0], int(s[1])] for s in [l.split() for l in pf if l.strip()]])
+    if getattr(args, "inferPloidy", False):
+        raise NotImplementedError("--inferPloidy (per-window ploidy inference, 'NOT RECOMMENDED' in the reference) "
+                                  "is not supported by the dense engine")
+    base = 1 if args.genoFormat == "haplo" else 2
+    d = dict(zip(allInds, [base] * len(allInds)))
+    for s in haploid_list or []:
+        d[s] = 1
+    return d
+
+
+def header_names(path):
+    with (gzip.open(path, "rt") if path.endswith(".gz") else open(path, "rt")) as gf:
+        return gf.readline().split()[2:]
+
+
+def open_out(path):
+    if path:
+        return gzip.open(path, "wt") if path.endswith(".gz") else open(path, "wt")
+    return sys.stdout
+
+
+def load_geno(args, samples, ploidyDict, header=None):
+    src = args.genoFile if args.genoFile else sys.stdin.buffer
+    return geno_io.parse_geno(src, geno_format=args.genoFormat, samples=samples, ploidy=ploidyDict, header=header,
+                              threads=getattr(args, "parseThreads", None))
+
+
+def make_windows(args, gd, minSites, coords, include=None, exclude=None):
+    if args.windType == "coordinate":
+        return W.sliding_coord_windows(gd.scaf_ids, gd.scaf_names, gd.pos, args.windSize, args.stepSize or args.windSize,
+                                       include, exclude)
+    if args.windType == "sites":
+        return W.sliding_sites_windows(gd.scaf_ids, gd.scaf_names, gd.pos, args.windSize, args.overlap or 0,
+                                       args.maxDist if args.maxDist else None, minSites, include, exclude)
+    if args.windType == "predefined":
+        return W.predefined_coord_windows(gd.scaf_ids, gd.scaf_names, gd.pos, coords)
+    raise ValueError(args.windType)
+
+
+def window_prefix(args, ws, k, gd, sites, pos_sum):
+    """scaffold,start,end,mid,sites of one window (popgenWindows.py:37-39)."""
+    n = int(sites)
+    mid = W.mid_pos(int(pos_sum), n)
+    if args.windType in ("coordinate", "predefined"):
+        start, end = ws.start[k], ws.end[k]
+    else:
+        start, end = int(gd.pos[ws.lo[k]]), int(gd.pos[ws.hi[k] - 1])      # firstPos / lastPos
+    return [ws.scaffold[k], start, end, mid, n]
+
+
+def hap_pop_vector(gd, popNames, popInds):
+    """population index of every haplotype column (-1: in no population). A sample listed in several
+    populations is not representable by the reference either (Alignment.groups becomes a tuple)."""
+    samp_pop = {}
+    for k, inds in enumerate(popInds):
+        for i in inds:
+            if i in samp_pop and samp_pop[i] != k:
+                raise ValueError("sample %s is in more than one population" % i)
+            samp_pop[i] = k
+    per_sample = np.array([samp_pop.get(n, -1) for n in gd.names], dtype=np.int32)
+    return np.repeat(per_sample, gd.ploidy.astype(np.int64))

@@ -1,0 +1,80 @@
+#!/usr/bin/env python
+"""Drop-in for the reference's freq.py default mode (per-site per-population A,C,G,T counts;
+freq.py:52-58,100-111, flags 187-222), on the GPU.  --target minor|derived are not accelerated yet."""
+from __future__ import annotations
+
+import argparse
+import sys
+
+import numpy as np
+
+from .. import genomics
+from ..engine import Engine
+from . import _common as C
+
+
+def build_parser():
+    p = argparse.ArgumentParser()
+    p.add_argument("-g", "--genoFile")
+    p.add_argument("-o", "--outFile")
+    p.add_argument("-f", "--genoFormat", choices=("phased", "diplo", "alleles"), default="phased")
+    p.add_argument("-p", "--population", action="append", nargs="+", metavar=("popName", "[samples]"))
+    p.add_argument("--popsFile")
+    p.add_argument("--indFreqs", action="store_true")
+    p.add_argument("--target", choices=("minor", "derived"), default=None)
+    p.add_argument("--asCounts", action="store_true")
+    p.add_argument("--ploidy", type=int, nargs="+")
+    p.add_argument("--ploidyFile")
+    p.add_argument("--haploid", nargs="+")
+    p.add_argument("--minData", type=float, default=0, metavar="proportion")
+    p.add_argument("--threshold", type=float, metavar="proportion")
+    p.add_argument("--keepNanLines", action="store_true")
+    p.add_argument("-t", "--threads", type=int, default=1)
+    p.add_argument("--sliceSize", type=int, default=1000000)
+    p.add_argument("--verbose", action="store_true")
+    p.add_argument("--test", action="store_true")
+    C.add_engine_args(p)
+    return p
+
+
+def main(argv=None):
+    args = build_parser().parse_args(argv)
+    if args.target:
+        raise NotImplementedError("--target %s is not on the GPU path yet (SURVEY.md §8f rank 4)" % args.target)
+    headerInds = C.header_names(args.genoFile)
+    if not args.indFreqs and not args.population:
+        popNames, popInds = ["all"], [headerInds]
+    elif args.indFreqs:
+        popNames, popInds = list(headerInds), [[i] for i in headerInds]
+    else:
+        popNames, popInds = C.parse_pop_args(args.population, args.popsFile)
+    allInds = sorted(set(i for p in popInds for i in p))
+    args.inferPloidy = False
+    ploidyDict = C.ploidy_dict(args, allInds, args.haploid)
+    sampleData = genomics.SampleData(indNames=allInds, popNames=popNames, popInds=popInds, ploidyDict=ploidyDict)
+    out = C.open_out(args.outFile)
+    out.write("scaffold\tposition\t" + "\t".join(popNames) + "\n")
+    gd = C.load_geno(args, sampleData.indNames, ploidyDict)
+    P = len(popNames)
+    with Engine(args.device) as eng:
+        eng.upload(gd.geno, gd.pos)
+        eng.set_pops(C.hap_pop_vector(gd, popNames, popInds), P)
+        slab = 1 << 20
+        scaf = np.array(gd.scaf_names, dtype=object)
+        for s in range(0, gd.n_sites, slab):
+            n = min(slab, gd.n_sites - s)
+            c = eng.site_counts(s, n).astype(np.int64)                      # [n, P, 4]
+            cs = c.astype(str)
+            cols = [np.char.add(np.char.add(np.char.add(cs[:, x, 0], ","), np.char.add(cs[:, x, 1], ",")),
+                                np.char.add(np.char.add(cs[:, x, 2], ","), cs[:, x, 3])) for x in range(P)]
+            names = scaf[gd.scaf_ids[s:s + n]]
+            pos = gd.pos[s:s + n]
+            for i in range(n):
+                out.write(names[i] + "\t" + str(pos[i]) + "\t" + "\t".join(col[i] for col in cols) + "\n")
+    if out is not sys.stdout:
+        out.close()
+    sys.stderr.write("\nDone\n")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,136 @@
+#!/usr/bin/env python
+"""Drop-in for the reference's popgenWindows.py (same flags, header and rows), computed on the GPU.
+
+Reference: /root/reference/popgenWindows.py — argparse 170-213, sample/pop parsing 253-307, header 319-354,
+worker stats_wrapper 28-75.  The process pipeline (producer / -T workers / sorter / writer) is replaced by:
+parse the whole file once -> dense int8 matrix -> all windows in one engine call -> rows.
+Supported --analysis: popDist, popPairDist (the defaults), indPairDist.  popFreq / indHet / hapStats are
+not on the accelerated path yet.
+"""
+from __future__ import annotations
+
+import argparse
+import itertools
+import sys
+
+import numpy as np
+
+from .. import genomics
+from ..engine import Engine
+from . import _common as C
+
+
+def build_parser():
+    p = argparse.ArgumentParser()
+    C.add_window_args(p, overlap_short=True)
+    p.add_argument("--minData", help="Minumum proportion of individuals (or pairs) with >=minSites data", type=float,
+                   metavar="prop", default=0.01)
+    p.add_argument("-p", "--population", help="Pop name and optionally sample names (separated by commas)",
+                   action="append", nargs="+", metavar=("popName", "[samples]"))
+    p.add_argument("--popsFile", help="Optional file of sample names and populations")
+    p.add_argument("--samples", help="Samples to include for individual analysis", metavar="sample names")
+    p.add_argument("--ploidy", help="Ploidy for each sample", type=int, nargs="+")
+    p.add_argument("--ploidyFile", help="File with samples names and ploidy as columns")
+    p.add_argument("--haploid", help="Alternatively just name samples that are haploid (comma separated)",
+                   metavar="sample names")
+    p.add_argument("--inferPloidy", help="Ploidy will be inferred in each window (NOT RECOMMENED)", action="store_true")
+    p.add_argument("--analysis", help="Type of statistics to get", nargs="+",
+                   choices=("popFreq", "popDist", "popPairDist", "indPairDist", "indHet", "hapStats"),
+                   default=("popDist", "popPairDist",))
+    p.add_argument("--hapDist", type=float, default=0)
+    p.add_argument("--roundTo", help="Round stats to X decimal places", type=int, default=4)
+    p.add_argument("-g", "--genoFile", help="Input genotypes file")
+    p.add_argument("-o", "--outFile", help="Results file")
+    p.add_argument("--exclude", help="File of scaffolds to exclude")
+    p.add_argument("--include", help="File of scaffolds to analyse")
+    p.add_argument("-f", "--genoFormat", help="Format of genotypes in genotypes file",
+                   choices=("phased", "pairs", "haplo", "diplo"), required=True)
+    p.add_argument("--header", help="Header text if no header in input")
+    p.add_argument("-T", "--threads", help="accepted for compatibility (the GPU engine replaces the workers)", type=int,
+                   default=1, metavar="threads")
+    p.add_argument("--verbose", action="store_true")
+    p.add_argument("--addWindowID", help="Add window name or number as first column", action="store_true")
+    p.add_argument("--writeFailedWindows", help="Write output even for windows with too few sites.", action="store_true")
+    C.add_engine_args(p)
+    return p
+
+
+def main(argv=None):
+    args = build_parser().parse_args(argv)
+    minSites, coords = C.check_window_args(args)
+    unsupported = [a for a in args.analysis if a in ("popFreq", "indHet", "hapStats")]
+    if unsupported:
+        raise NotImplementedError("--analysis %s is not on the GPU path yet" % " ".join(unsupported))
+
+    popNames, popInds, allInds = [], [], []
+    if args.population is not None:
+        popNames, popInds = C.parse_pop_args(args.population, args.popsFile)
+        allInds += sorted(set(i for p in popInds for i in p))
+    if args.samples is not None:
+        allInds = sorted(set(allInds + args.samples.split(",")))
+    if len(allInds) == 0:
+        allInds = C.header_names(args.genoFile) if args.header is None else args.header.split()[2:]
+    if len(popNames) == 0 and ("popDist" in args.analysis or "popPairDist" in args.analysis):
+        popNames.append("all")
+        popInds.append(allInds)
+    ploidyDict = C.ploidy_dict(args, allInds, args.haploid.split(",") if args.haploid else None)
+    sampleData = genomics.SampleData(indNames=allInds, popNames=popNames, popInds=popInds, ploidyDict=ploidyDict)
+
+    out = C.open_out(args.outFile)
+    out.write("scaffold,start,end,mid,sites," if not args.addWindowID else "windowID,scaffold,start,end,mid,sites,")
+    stats = []
+    if "popDist" in args.analysis:
+        stats += ["pi_" + n for n in popNames]
+    if "popPairDist" in args.analysis:
+        stats += ["dxy_" + x + "_" + y for x, y in itertools.combinations(popNames, 2)]
+        stats += ["Fst_" + x + "_" + y for x, y in itertools.combinations(popNames, 2)]
+    ind_sorted = sorted(allInds)
+    if "indPairDist" in args.analysis:
+        stats += ["_".join(["d", i, j]) for i, j in itertools.combinations_with_replacement(ind_sorted, 2)]
+    out.write(",".join(stats) + "\n")
+
+    gd = C.load_geno(args, sampleData.indNames, ploidyDict, header=args.header)
+    ws = C.make_windows(args, gd, minSites, coords, C.read_scaffold_list(args.include), C.read_scaffold_list(args.exclude))
+    sys.stderr.write("\n%d sites x %d haplotypes, %d windows\n" % (gd.n_sites, gd.n_haps, len(ws)))
+    lo, hi = ws.ranges()
+    written = 0
+    with Engine(args.device) as eng:
+        eng.upload(gd.geno, gd.pos)
+        eng.set_windows(lo, hi)
+        P = len(popNames)
+        eng.set_pops(C.hap_pop_vector(gd, popNames, popInds), max(P, 1))
+        r = eng.popgen(minSites, args.minData)
+        npairs = P * (P - 1) // 2
+        dmat = None
+        if "indPairDist" in args.analysis:
+            inv = {gd.names.index(n): k for k, n in enumerate(ind_sorted)}
+            hap_ind = np.repeat(np.array([inv[i] for i in range(len(gd.names))], dtype=np.int32), gd.ploidy.astype(np.int64))
+            dmat = eng.pairdist(hap_ind, len(ind_sorted), False)["dist"]
+        iu = np.triu_indices(len(ind_sorted)) if dmat is not None else None
+        for k in range(len(ws)):
+            pre = C.window_prefix(args, ws, k, gd, r["sites"][k], r["pos_sum"][k])
+            good = pre[4] >= minSites
+            vals = []
+            if good:
+                if "popDist" in args.analysis:
+                    vals += list(r["pi"][k])
+                if "popPairDist" in args.analysis:
+                    vals += list(r["dxy"][k]) + list(r["fst"][k])
+                if dmat is not None:
+                    vals += list(dmat[k][iu])
+                vals = [round(np.float64(v), args.roundTo) for v in vals]
+            else:
+                vals = [np.nan] * len(stats)
+            if good or args.writeFailedWindows:
+                row = ([] if not args.addWindowID else [ws.ID[k]]) + pre + vals
+                out.write(",".join(str(x) for x in row) + "\n")
+                written += 1
+    if out is not sys.stdout:
+        out.close()
+    sys.stderr.write(str(len(ws)) + " windows were tested.\n")
+    sys.stderr.write(str(written) + " results were written.\n")
+    sys.stderr.write("\nDone.\n")
+
+
+if __name__ == "__main__":
+    main()

@@ -75,6 +75,15 @@ extern "C" int pg_ctx_destroy(pg_ctx* ctx) {
                      &ctx->planes, &ctx->pairs, &ctx->misc, &ctx->misc2, &ctx->misc3};
     for (PgBuf* b : bufs) b->release();
     for (cudaEvent_t ev : ctx->event_pool) cudaEventDestroy(ev);
+    ctx->stage[0].release();
+    ctx->stage[1].release();
+    if (ctx->copy_stream) {
+        for (int k = 0; k < 2; ++k) {
+            cudaEventDestroy(ctx->stage_full[k]);
+            cudaEventDestroy(ctx->stage_free[k]);
+        }
+        cudaStreamDestroy(ctx->copy_stream);
+    }
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -319,32 +328,82 @@ extern "C" int pg_alloc_sites(pg_ctx* ctx, int64_t S, int32_t H) {
     return PG_OK;
 }
 
+// dense staging rows [n x H] (reference codes) -> resident pitched rows (one-hot code)
+__global__ void k_ingest(const uint8_t* __restrict__ stage, uint8_t* __restrict__ geno, int64_t row0, int64_t n,
+                         int pitch, int H) {
+    const int wpr = (H + 3) / 4;
+    const int64_t total = n * wpr;
+    const bool aligned = (H & 3) == 0;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = idx / wpr;
+        const int wi = (int)(idx % wpr);
+        const uint8_t* src = stage + r * H + (int64_t)wi * 4;
+        uint32_t w;
+        if (aligned) w = *reinterpret_cast<const uint32_t*>(src);
+        else {
+            const int rem = H - wi * 4;
+            w = 0xffffffffu;                                   // bytes past the row end: missing
+            w = (w & ~0xffu) | src[0];
+            if (rem > 1) w = (w & ~0xff00u) | ((uint32_t)src[1] << 8);
+            if (rem > 2) w = (w & ~0xff0000u) | ((uint32_t)src[2] << 16);
+            if (rem > 3) w = (w & ~0xff000000u) | ((uint32_t)src[3] << 24);
+        }
+        reinterpret_cast<uint32_t*>(geno + (row0 + r) * pitch)[wi] = encode4(w);   // padding bytes encode to 0x00
+    }
+}
+
 extern "C" int pg_upload_range(pg_ctx* ctx, int64_t site0, int64_t n, const int8_t* geno, const int32_t* pos) {
     PG_CHECK(ctx && geno, "pg_upload_range: null argument");
     PG_CHECK(site0 >= 0 && n >= 0 && site0 + n <= ctx->S, "pg_upload_range: range [%lld,+%lld) outside S=%lld",
              (long long)site0, (long long)n, (long long)ctx->S);
     PG_CUDA(cudaSetDevice(ctx->device));
     if (n == 0) return PG_OK;
-    PG_CUDA(cudaMemcpy2DAsync(ctx->d_geno + site0 * ctx->pitch, ctx->pitch, geno, ctx->H, ctx->H, (size_t)n,
-                              cudaMemcpyHostToDevice, ctx->stream));
-    k_transcode<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>((uint8_t*)ctx->d_geno, site0, n, ctx->pitch, ctx->H, 0);
-    PG_CUDA(cudaGetLastError());
-    ctx->launches += 1;
-    if (pos)
+    if (!ctx->copy_stream) {
+        PG_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; ++k) {
+            PG_CUDA(cudaEventCreateWithFlags(&ctx->stage_full[k], cudaEventDisableTiming));
+            PG_CUDA(cudaEventCreateWithFlags(&ctx->stage_free[k], cudaEventDisableTiming));
+        }
+    }
+    // dense 1-D H2D copies (full PCIe rate) into two staging buffers on the copy stream; the ingest kernel
+    // (transcode + re-pitch) runs behind each copy on the compute stream.
+    const size_t stage_bytes = (size_t)128 << 20;
+    const int64_t rows_per = std::max<int64_t>(1, (int64_t)(stage_bytes / (size_t)ctx->H));
+    PG_TRY(ctx->stage[0].ensure((size_t)rows_per * ctx->H + 16));
+    PG_TRY(ctx->stage[1].ensure((size_t)rows_per * ctx->H + 16));
+    // the copy stream must not overtake work already queued on the compute stream that reads the staging buffers
+    int k = 0;
+    for (int64_t s = 0; s < n; s += rows_per, ++k) {
+        const int64_t cnt = std::min(rows_per, n - s);
+        const int b = k & 1;
+        if (k >= 2) PG_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->stage_free[b], 0));
+        PG_CUDA(cudaMemcpyAsync(ctx->stage[b].p, geno + (size_t)s * ctx->H, (size_t)cnt * ctx->H,
+                                cudaMemcpyHostToDevice, ctx->copy_stream));
+        PG_CUDA(cudaEventRecord(ctx->stage_full[b], ctx->copy_stream));
+        PG_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->stage_full[b], 0));
+        k_ingest<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>((const uint8_t*)ctx->stage[b].p, (uint8_t*)ctx->d_geno,
+                                                              site0 + s, cnt, ctx->pitch, ctx->H);
+        PG_CUDA(cudaGetLastError());
+        ctx->launches += 1;
+        PG_CUDA(cudaEventRecord(ctx->stage_free[b], ctx->stream));
+    }
+    if (pos) {
         PG_CUDA(cudaMemcpyAsync(ctx->d_pos + site0, pos, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice,
-                                ctx->stream));
+                                ctx->copy_stream));
+        PG_CUDA(cudaEventRecord(ctx->stage_full[0], ctx->copy_stream));
+        PG_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->stage_full[0], 0));
+    }
+    // the caller's buffers may be reused as soon as this returns
+    PG_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+    // staging buffers are reused by the next call: their last readers must be done before the next H2D lands
+    PG_CUDA(cudaStreamSynchronize(ctx->stream));
     return PG_OK;
 }
 
 extern "C" int pg_upload(pg_ctx* ctx, const int8_t* geno, int64_t S, int32_t H, const int32_t* pos) {
     PG_TRY(pg_alloc_sites(ctx, S, H));
-    // chunked so that the 2D copies pipeline through the DMA engines
-    const int64_t step = std::max<int64_t>(1, (int64_t)(256ll << 20) / std::max(H, 1));
-    for (int64_t s = 0; s < S; s += step) {
-        int64_t n = std::min(step, S - s);
-        PG_TRY(pg_upload_range(ctx, s, n, geno + s * H, pos ? pos + s : nullptr));
-    }
-    return PG_OK;
+    return pg_upload_range(ctx, 0, S, geno, pos);
 }
 
 extern "C" int pg_download(pg_ctx* ctx, int64_t site0, int64_t n, int8_t* geno, int32_t* pos) {

@@ -99,6 +99,10 @@ struct pg_ctx {
     int64_t launches = 0;
     // scratch
     PgBuf tables, part, segmeta, winmeta, out_d, out_i, planes, pairs, misc, misc2, misc3;
+    // upload pipeline: copy stream + two staging buffers
+    cudaStream_t copy_stream = nullptr;
+    PgBuf stage[2];
+    cudaEvent_t stage_full[2] = {nullptr, nullptr}, stage_free[2] = {nullptr, nullptr};
     void* h_pinned = nullptr;                 // small pinned staging for result read-back
     size_t h_pinned_cap = 0;
 };

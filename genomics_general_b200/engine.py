@@ -95,9 +95,15 @@ class Engine:
         self.S, self.H = int(n_sites), spec.n_haps
         self.W = 0
 
-    def download(self, site0: int, n: int, into_geno=None, into_pos=None):
-        g = into_geno if into_geno is not None else np.empty((n, self.H), dtype=np.int8)
-        p = into_pos if into_pos is not None else np.empty(n, dtype=np.int32)
+    def download(self, site0: int, n: int, into_geno=None, into_pos=None, want_geno=True, want_pos=True):
+        """Device -> host copy (decoded to A0 C1 G2 T3 / -1).  Destination arrays must be C-contiguous."""
+        g = p = None
+        if want_geno:
+            g = into_geno if into_geno is not None else np.empty((n, self.H), dtype=np.int8)
+            assert g.flags.c_contiguous and g.dtype == np.int8 and g.shape == (n, self.H)
+        if want_pos:
+            p = into_pos if into_pos is not None else np.empty(n, dtype=np.int32)
+            assert p.flags.c_contiguous and p.dtype == np.int32 and p.shape == (n,)
         check(self._lib.pg_download(self._ctx, int(site0), int(n), _ptr(g), _ptr(p)), "pg_download")
         return g, p
 

@@ -1,0 +1,125 @@
+"""Whole-file .geno ingest: text -> dense int8 [sites x haplotypes] + positions + scaffold runs.
+
+Replaces, for a whole file at once, the reference's streaming reader and per-window conversion
+(genomics.py:1884-1945 parseGenoLine/GenoFileReader, 390-396 splitSeq, 1101-1127 genoToAlignment,
+74-77 seqArrayToNumArray).  Tokenising runs in native code (csrc/geno_parse.cpp, multi-threaded);
+this module only handles files, the header line and sample selection.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import gzip
+import io
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from ._lib import PgError, check
+
+FORMATS = {"phased": 0, "diplo": 1, "pairs": 2, "haplo": 3, "alleles": 0}
+
+
+@dataclass
+class GenoData:
+    geno: np.ndarray          # int8 [S, H]  A0 C1 G2 T3, -1 missing; haplotypes of sample k at hap_off[k]..+ploidy[k]
+    pos: np.ndarray           # int32 [S]
+    scaf_ids: np.ndarray      # int32 [S] run index (a scaffold that re-appears later starts a new run)
+    scaf_names: list          # name of each run
+    names: list               # sample names (columns kept, in the order requested)
+    ploidy: np.ndarray        # int8 per sample
+    hap_off: np.ndarray       # first haplotype column of each sample
+    header: str
+
+    @property
+    def n_sites(self):
+        return int(self.geno.shape[0])
+
+    @property
+    def n_haps(self):
+        return int(self.geno.shape[1])
+
+    def hap_sample(self):
+        """sample index of every haplotype column"""
+        return np.repeat(np.arange(len(self.names), dtype=np.int32), self.ploidy.astype(np.int64))
+
+
+def _lib_parse():
+    L = _lib.lib()
+    if not hasattr(L, "_pg_parse_ready"):
+        L.pg_geno_count_lines.restype = C.c_int
+        L.pg_geno_count_lines.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_int64)]
+        L.pg_geno_parse.restype = C.c_int
+        L.pg_geno_parse.argtypes = [C.c_char_p, C.c_size_t, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+                                    C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
+        L._pg_parse_ready = True
+    return L
+
+
+def read_bytes(source):
+    """source: path (optionally .gz), bytes, or a text/binary file object."""
+    if isinstance(source, (bytes, bytearray)):
+        return bytes(source)
+    if isinstance(source, str):
+        if source.endswith(".gz"):
+            with gzip.open(source, "rb") as f:
+                return f.read()
+        with open(source, "rb") as f:
+            return f.read()
+    data = source.read()
+    return data.encode() if isinstance(data, str) else data
+
+
+def parse_geno(source, geno_format="phased", samples=None, ploidy=None, header=None, threads=None) -> GenoData:
+    """Parse a whole .geno file.
+
+    samples: sample names to keep (default: every column of the header, genomics.py:1918);
+    ploidy: dict sample -> ploidy (default 2; 1 for -f haplo, popgenWindows.py:302);
+    header: header text when the file has none (--header)."""
+    data = read_bytes(source)
+    if header is None:
+        nl = data.find(b"\n")
+        if nl < 0:
+            nl = len(data)
+        header = data[:nl].decode()
+        body = data[nl + 1:]
+    else:
+        body = data
+    file_names = header.split()[2:]
+    if samples is None:
+        samples = list(file_names)
+    col = {}
+    for i, n in enumerate(file_names):
+        col.setdefault(n, i)
+    missing = [s for s in samples if s not in col]
+    if missing:
+        raise KeyError("samples not in the genotype file header: %s" % ", ".join(missing[:5]))
+    fmt = FORMATS[geno_format]
+    default_pl = 1 if geno_format == "haplo" else 2
+    pl = np.array([int((ploidy or {}).get(s, default_pl) or default_pl) for s in samples], dtype=np.int8)
+    col_take = np.array([col[s] for s in samples], dtype=np.int32)
+    H = int(pl.astype(np.int64).sum())
+    L = _lib_parse()
+    n = C.c_int64(0)
+    check(L.pg_geno_count_lines(body, len(body), C.byref(n)), "pg_geno_count_lines")
+    S = int(n.value)
+    geno = np.empty((S, H), dtype=np.int8)
+    pos = np.empty(S, dtype=np.int32)
+    newsc = np.empty(S, dtype=np.int8)
+    off = np.empty(S, dtype=np.int64)
+    if threads is None:
+        threads = min(32, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
+    check(L.pg_geno_parse(body, len(body), fmt, len(samples), col_take.ctypes.data_as(C.c_void_p),
+                          pl.ctypes.data_as(C.c_void_p), H, S, geno.ctypes.data_as(C.c_void_p),
+                          pos.ctypes.data_as(C.c_void_p), newsc.ctypes.data_as(C.c_void_p),
+                          off.ctypes.data_as(C.c_void_p), int(threads)), "pg_geno_parse")
+    scaf_ids = (np.cumsum(newsc.astype(np.int64)) - 1).astype(np.int32) if S else np.zeros(0, dtype=np.int32)
+    starts = np.flatnonzero(newsc)
+    scaf_names = []
+    for s in starts:
+        o = int(off[s])
+        scaf_names.append(body[o:o + 256].split(None, 1)[0].decode())
+    hap_off = np.concatenate([[0], np.cumsum(pl.astype(np.int64))[:-1]]).astype(np.int32) if len(pl) else np.zeros(0, np.int32)
+    return GenoData(geno=geno, pos=pos, scaf_ids=scaf_ids, scaf_names=scaf_names, names=list(samples), ploidy=pl,
+                    hap_off=hap_off, header=header)
