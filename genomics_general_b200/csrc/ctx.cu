@@ -208,7 +208,7 @@ K1Plan pg_make_k1_plan(int64_t S, int H, int sm_count, int table_bytes) {
     p.pitch = pg_pitch_for(H);
     p.chunks = p.pitch / 16;
     const int smem_cap = 227 * 1024 - 2048 - table_bytes;   // per-CTA dynamic smem we allow ourselves
-    const int tile_target = env_int("PG_K1_TILE_KB", 32) * 1024;
+    const int tile_target = env_int("PG_K1_TILE_KB", 64) * 1024;
     int G = 1, wpt = 1, I = 1;
     if (32 * p.pitch <= tile_target) {
         while (wpt < 8 && 32 * (wpt * 2) * p.pitch <= tile_target) wpt *= 2;
@@ -227,7 +227,7 @@ K1Plan pg_make_k1_plan(int64_t S, int H, int sm_count, int table_bytes) {
     p.I = I;
     p.wpt = wpt;
     p.T = (32 * wpt / G) * I;
-    p.tile_bytes = p.T * p.pitch;
+    p.tile_bytes = ((p.T * p.pitch + p.T * 4 + 127) / 128) * 128;   // genotype rows + the tile's positions
     int stages = smem_cap / p.tile_bytes;
     if (stages > 8) stages = 8;
     stages = std::min(stages, std::max(2, env_int("PG_K1_STAGES", stages)));

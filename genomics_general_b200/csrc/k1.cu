@@ -243,13 +243,16 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_site_pass(const __grid_const
                 int64_t rows = prm.site_end - s_lo;
                 if (rows > prm.T) rows = prm.T;
                 const uint32_t bytes = (uint32_t)(rows * prm.pitch);
-                mbar_expect_tx(&full[stage], bytes);
+                // positions of the tile ride along (rounded up to 16 bytes; the array has zeroed slack)
+                const uint32_t pbytes = (MODE == MODE_COUNTS) ? 0u : (uint32_t)(((rows * 4 + 15) / 16) * 16);
+                mbar_expect_tx(&full[stage], bytes + pbytes);
                 const uint8_t* src = prm.geno + s_lo * prm.pitch;
                 uint8_t* dst = tiles + (size_t)stage * prm.tile_bytes;
                 for (uint32_t off = 0; off < bytes; off += 32768u) {
                     const uint32_t n = (bytes - off) < 32768u ? (bytes - off) : 32768u;
                     bulk_g2s(dst + off, src + off, n, &full[stage]);
                 }
+                if (pbytes) bulk_g2s(dst + (size_t)prm.T * prm.pitch, prm.pos + s_lo, pbytes, &full[stage]);
             }
         }
         return;
@@ -286,9 +289,10 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_site_pass(const __grid_const
             const bool valid = site < prm.site_end;
             const bool owner = valid && (gsub == 0);
             const uint4* row = reinterpret_cast<const uint4*>(tile + (size_t)(valid ? slot : 0) * prm.pitch);
-            // the position is needed last: issue its load first so that the counting hides the latency
+            // the tile's positions were staged behind its genotype rows by the producer
             int posv = 0;
-            if (MODE != MODE_COUNTS) posv = owner ? __ldg(prm.pos + site) : 0;
+            if (MODE != MODE_COUNTS)
+                posv = owner ? reinterpret_cast<const int32_t*>(tile + (size_t)prm.T * prm.pitch)[slot] : 0;
 
             uint32_t n[P], c[P][4];
 #pragma unroll
@@ -625,6 +629,7 @@ void build_tables(const std::vector<int32_t>& hap_pop_local, int H, int chunks, 
 int check_plan(const K1Plan& pl) {
     const bool pow2G = pl.G >= 1 && pl.G <= 32 && (pl.G & (pl.G - 1)) == 0;
     const bool okw = pl.wpt == 1 || pl.wpt == 2 || pl.wpt == 4 || pl.wpt == 8;
+    PG_CHECK((pl.T % 4) == 0, "rows of %d bytes are too long for the site-pass kernel", pl.pitch);
     PG_CHECK(pow2G && okw && pl.I >= 1 && pl.stages >= 2 && pl.stages <= 8 && pl.smem_bytes <= 227 * 1024,
              "invalid site-pass geometry G=%d wpt=%d I=%d stages=%d smem=%d", pl.G, pl.wpt, pl.I, pl.stages, pl.smem_bytes);
     return PG_OK;

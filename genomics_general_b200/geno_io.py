@@ -46,15 +46,7 @@ class GenoData:
 
 
 def _lib_parse():
-    L = _lib.lib()
-    if not hasattr(L, "_pg_parse_ready"):
-        L.pg_geno_count_lines.restype = C.c_int
-        L.pg_geno_count_lines.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_int64)]
-        L.pg_geno_parse.restype = C.c_int
-        L.pg_geno_parse.argtypes = [C.c_char_p, C.c_size_t, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
-                                    C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
-        L._pg_parse_ready = True
-    return L
+    return _lib.lib()
 
 
 def read_bytes(source):

@@ -92,6 +92,19 @@ int pg_pairdist(pg_ctx* ctx, int32_t n_ind, const int32_t* hap_ind, int32_t incl
  * diff, n int32 [H x H] (symmetric, diagonal: diff 0, n = non-missing sites of the haplotype). */
 int pg_pair_counts(pg_ctx* ctx, int64_t window, int32_t* diff, int32_t* n);
 
+/* ---- host-side .geno text ingest (no CUDA) ------------------------------------------------------ */
+/* Replaces parseGenoLine/GenoFileReader (genomics.py:1884-1945) + splitSeq/haplo/forceHomo (390-396, 27, 407)
+ * + seqArrayToNumArray (74-77) for a whole file: `buf` holds complete data lines (no header line);
+ * '#' lines and blank lines are skipped.  fmt: 0 phased, 1 diplo, 2 pairs, 3 haplo.
+ * col_take[k] = genotype column (0-based, after scaffold and position) of output sample k, ploidy[k] its
+ * haplotype count; output row layout: samples in the given order, haplotypes of a sample adjacent.
+ * geno [n_lines x H_out] int8, pos [n_lines] int32, new_scaffold [n_lines] (1 where the scaffold field differs
+ * from the previous data line), line_off [n_lines] byte offset of each data line in buf. */
+int pg_geno_count_lines(const char* buf, size_t len, int64_t* n_lines);
+int pg_geno_parse(const char* buf, size_t len, int32_t fmt, int32_t n_out, const int32_t* col_take,
+                  const int8_t* ploidy, int32_t H_out, int64_t n_lines, int8_t* geno, int32_t* pos,
+                  int8_t* new_scaffold, int64_t* line_off, int32_t n_threads);
+
 /* ---- introspection ---------------------------------------------------------------------------- */
 /* Device time (ms, CUDA events on the ctx stream) of the kernels launched by the last statistics call:
  * names[i] -> ms[i]; returns the number of entries through *count (at most cap). */
