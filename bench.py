@@ -162,7 +162,7 @@ def run_reference(args, rank, world):
             "data": "synthetic", "config": workload_config(args, world),
             "cpu_baseline": {"value": value, "unit": "sites/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "sites/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, world):
@@ -177,7 +177,27 @@ def workload_config(args, world):
 
 
 # ------------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Libraries (NCCL's version banner, torchrun notices) may write to fd 1; the contract is ONE JSON line on
+    stdout.  Route fd 1 to stderr for the whole run and keep the real stdout for the final line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -247,14 +267,14 @@ def main():
         ws = windows.sliding_coord_windows(np.zeros(S, dtype=np.int32), ["chr1"], pos, WIND_SIZE)
         return ws.ranges()
 
-    counts = None
+    gatherer = None
 
     def step_resident():
-        r = eng.popgen(MIN_SITES, MIN_DATA)
         if dist is not None:
-            rec = multigpu.all_gather_rows(multigpu.popgen_records(r), counts, device=dev)
-            return rec
-        return r
+            # records stay on the device: statistics kernel -> NCCL all-gather -> one D2H of the table
+            eng.popgen_device(gatherer.local.data_ptr(), MIN_SITES, MIN_DATA)
+            return gatherer.gather()
+        return eng.popgen(MIN_SITES, MIN_DATA)
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -286,6 +306,7 @@ def main():
         allc = [torch.zeros_like(cnt) for _ in range(world)]
         dist.all_gather(allc, cnt)
         counts = [int(c.item()) for c in allc]
+        gatherer = multigpu.DeviceGather(counts, eng.popgen_record_width(), dev)
     dt, tms, launches = timed(step_resident, args.steps, args.warmup)
     value = world * S * args.steps / dt
     k1_ms = float(np.mean([t["k1_popgen"]["ms"] for t in tms if "k1_popgen" in t]))
@@ -383,11 +404,17 @@ def main():
             "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": cfg, "clocks": clocks, "e2e": e2e,
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "kernel_ms": kernel_ms,
             "variants": variants}
-    print(json.dumps(line), flush=True)
+    emit(line)
     eng.close()
     if dist is not None:
         dist.destroy_process_group()
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except Exception:
+        import traceback
+        traceback.print_exc()
+        sys.stderr.flush()
+        sys.exit(1)

@@ -69,6 +69,7 @@ extern "C" int pg_ctx_destroy(pg_ctx* ctx) {
     if (!ctx) return PG_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    pg_k1_cache_free(ctx);
     if (ctx->d_geno) cudaFree(ctx->d_geno);
     if (ctx->d_pos) cudaFree(ctx->d_pos);
     PgBuf* bufs[] = {&ctx->tables, &ctx->part, &ctx->segmeta, &ctx->winmeta, &ctx->out_d, &ctx->out_i,
@@ -317,14 +318,16 @@ extern "C" int pg_alloc_sites(pg_ctx* ctx, int64_t S, int32_t H) {
         PG_CUDA(cudaMalloc((void**)&ctx->d_pos, pneed));
         ctx->pos_cap = pneed;
     }
+    const bool same_shape = (ctx->S == S && ctx->H == H && ctx->pitch == pitch);
     ctx->S = S;
     ctx->H = H;
     ctx->pitch = pitch;
+    if (!same_shape) ctx->epoch += 1;          // same shape: cached launch plans stay valid
     PG_CUDA(cudaMemsetAsync(ctx->d_pos, 0, pneed, ctx->stream));
     // every byte starts as "missing" (0x00): row padding and the slack rows never count
     PG_CUDA(cudaMemsetAsync(ctx->d_geno, 0, need, ctx->stream));
-    // data changed: windows/pops stay, segments depend on S
-    ctx->brk.clear();
+    // windows/pops stay; segments depend on S only
+    if (!same_shape) ctx->brk.clear();
     return PG_OK;
 }
 
@@ -525,6 +528,7 @@ extern "C" int pg_set_pops(pg_ctx* ctx, int32_t P, const int32_t* hap_pop) {
     for (int h = 0; h < ctx->H; ++h)
         PG_CHECK(hap_pop[h] >= -1 && hap_pop[h] < P, "pg_set_pops: hap_pop[%d]=%d outside [-1,%d)", h, hap_pop[h], P);
     ctx->P = P;
+    ctx->epoch += 1;
     return PG_OK;
 }
 
@@ -539,6 +543,7 @@ extern "C" int pg_set_windows(pg_ctx* ctx, int64_t W, const int64_t* lo, const i
     ctx->win_lo.assign(lo, lo + W);
     ctx->win_hi.assign(hi, hi + W);
     ctx->brk.clear();
+    ctx->epoch += 1;
     return PG_OK;
 }
 

@@ -457,16 +457,16 @@ struct FinParams {
     int min_sites;
     double min_data;
     int force_path;
-    // outputs
-    double* pi;
-    double* dxy;
-    double* fst;
-    double* abba_out;              // [W x 5]
-    double* sites_used;
-    long long* n_sites;
-    long long* pos_sum;
-    int32_t* path;
+    // outputs: fixed-width 8-byte records per window
+    //   popgen: [sites(i64) pos_sum(i64) path(i64) pi[P] dxy[npairs] fst[npairs]]
+    //   abba  : [sites(i64) pos_sum(i64) ABBA BABA D fd fdM sitesUsed]
+    unsigned long long* rec;
+    int RC;
+    int32_t* path;                 // [W] popgen routing, also counted in *n_pairwise
+    int* n_pairwise;
 };
+
+__device__ __forceinline__ unsigned long long d2u(double x) { return (unsigned long long)__double_as_longlong(x); }
 
 __device__ __forceinline__ double nan_d() { return __longlong_as_double(0x7ff8000000000000ll); }
 
@@ -506,27 +506,33 @@ __global__ void __launch_bounds__(64) k1_finalize(const __grid_constant__ FinPar
         __syncthreads();
         if (q != 0) continue;
         const long long sites = fp.win_hi[w] - fp.win_lo[w];
-        fp.n_sites[w] = sites;
-        fp.pos_sum[w] = (long long)sums[2];
+        unsigned long long* rec = fp.rec + (size_t)w * fp.RC;
+        rec[0] = (unsigned long long)sites;
+        rec[1] = sums[2];
         if (MODE == MODE_POPGEN) {
             const int P = fp.P, Pp = fp.Ppad;
             const int npairs = P * (P - 1) / 2;
+            double* pi_o = reinterpret_cast<double*>(rec + 3);
+            double* dxy_o = pi_o + P;
+            double* fst_o = dxy_o + npairs;
             const long long Lp = (long long)sums[0];
             const bool ragged = (long long)sums[1] > 0;
             int path = 1;
             if (sites < fp.min_sites) path = 0;
             else if (ragged || fp.force_path == 2) path = 2;
             fp.path[w] = path;
+            rec[2] = (unsigned long long)path;
+            if (path == 2) atomicAdd(fp.n_pairwise, 1);
             if (path != 1) {
-                for (int x = 0; x < P; ++x) fp.pi[w * P + x] = nan_d();
-                for (int k = 0; k < npairs; ++k) fp.dxy[w * npairs + k] = fp.fst[w * npairs + k] = nan_d();
+                for (int x = 0; x < P; ++x) pi_o[x] = nan_d();
+                for (int k = 0; k < npairs; ++k) dxy_o[k] = fst_o[k] = nan_d();
                 continue;
             }
             const bool all_nan = (Lp == 0) || (fp.min_sites > 0 && Lp < fp.min_sites);
             double piv[PG_MAX_K1_POPS];
             for (int x = 0; x < P; ++x) {
                 piv[x] = cf_pi(fp.popN[x], Lp, (long long)sums[3 + x], all_nan, fp.min_data);
-                fp.pi[w * P + x] = piv[x];
+                pi_o[x] = piv[x];
             }
             int k = 0;
             for (int x = 0; x < P; ++x)
@@ -548,16 +554,15 @@ __global__ void __launch_bounds__(64) k1_finalize(const __grid_constant__ FinPar
                     const double pi_t = cf_pi(Nx + Ny, Lp, sq_t, all_nan, fp.min_data);
                     const double wgt = 1.0 * (double)Nx / (double)(Nx + Ny);
                     const double pi_s = wgt * piv[x] + (1 - wgt) * piv[y];
-                    fp.dxy[w * npairs + k] = dxy;
-                    fp.fst[w * npairs + k] = 1 - pi_s / pi_t;
+                    dxy_o[k] = dxy;
+                    fst_o[k] = 1 - pi_s / pi_t;
                     ++k;
                 }
         } else {   // MODE_ABBA
             const long long used = (long long)sums[0], n_good = (long long)sums[1];
-            double* o = fp.abba_out + w * 5;
+            double* o = reinterpret_cast<double*>(rec + 2);
             if (n_good < 1) {   // genomics.py:1694-1695: every value nan, sitesUsed included
-                for (int k = 0; k < 5; ++k) o[k] = nan_d();
-                fp.sites_used[w] = nan_d();
+                for (int k = 0; k < 6; ++k) o[k] = nan_d();
                 continue;
             }
             const double s_abba = __longlong_as_double((long long)sums[3]), s_baba = __longlong_as_double((long long)sums[4]);
@@ -568,7 +573,7 @@ __global__ void __launch_bounds__(64) k1_finalize(const __grid_constant__ FinPar
             o[2] = s_f4 * 1.0 / s_ab;
             o[3] = s_f4 * 1.0 / s_fd;
             o[4] = s_f4 * 1.0 / s_fdm;
-            fp.sites_used[w] = (double)used;
+            o[5] = (double)used;
         }
     }
 }
@@ -676,9 +681,23 @@ int push(pg_ctx* ctx, uint8_t* base, size_t& off, const T* src, size_t n, T** ou
     return PG_OK;
 }
 
-// Common preparation for the windowed modes: tables, segments, slot layout, zeroed slots.
-int prepare_windowed(pg_ctx* ctx, const std::vector<int32_t>& hap_pop_local, int Ppad, int Q, K1Launch& L,
-                     DevTables& dt, PopTables& pt) {
+// Everything a windowed launch needs, cached per configuration (data shape, populations, windows): a repeated
+// statistics call on the same configuration only clears the slots and launches two kernels.
+struct K1Cache {
+    bool valid = false;
+    uint64_t epoch = 0;
+    int mode = -1;
+    int sel[4] = {-1, -1, -1, -1};
+    K1Launch L;
+    DevTables dt;
+    PopTables pt;
+    PgBuf tables;
+};
+
+int prepare_windowed(pg_ctx* ctx, K1Cache& c, const std::vector<int32_t>& hap_pop_local, int Ppad, int Q) {
+    K1Launch& L = c.L;
+    DevTables& dt = c.dt;
+    PopTables& pt = c.pt;
     PG_TRY(pg_build_segments(ctx));
     build_tables(hap_pop_local, ctx->H, ctx->pitch / 16, Ppad, pt);
     const int n_ent = (int)pt.ent_chunk.size();
@@ -702,36 +721,28 @@ int prepare_windowed(pg_ctx* ctx, const std::vector<int32_t>& hap_pop_local, int
         const int64_t t0 = (int64_t)b * pl.num_tiles / B, t1 = (int64_t)(b + 1) * pl.num_tiles / B;
         const int64_t s0 = t0 * pl.T, s1 = std::min<int64_t>(t1 * pl.T, ctx->S);
         L.cta_slot_off[b] = off;
-        if (s1 <= s0) {
-            L.cta_seg_first[b] = 0;
-            cta_seg_last[b] = -1;
-            continue;
-        }
+        if (s1 <= s0) continue;
         const int g0 = seg_of(ctx->brk, s0), g1 = seg_of(ctx->brk, s1 - 1);
         L.cta_seg_first[b] = g0;
         cta_seg_last[b] = g1;
         off += (int64_t)(g1 - g0 + 1) * K1_WARPS * Q;
     }
     L.total_slots = off;
-    // per segment: contiguous CTA range touching it
-    {
-        for (int g = 0; g < nseg; ++g) {
-            L.seg_cta_lo[g] = B;
-            L.seg_cta_hi[g] = -1;
-        }
-        for (int b = 0; b < B; ++b) {
-            if (cta_seg_last[b] < 0) continue;
-            for (int g = L.cta_seg_first[b]; g <= cta_seg_last[b]; ++g) {
-                L.seg_cta_lo[g] = std::min(L.seg_cta_lo[g], b);
-                L.seg_cta_hi[g] = std::max(L.seg_cta_hi[g], b);
-            }
+    for (int g = 0; g < nseg; ++g) {
+        L.seg_cta_lo[g] = B;
+        L.seg_cta_hi[g] = -1;
+    }
+    for (int b = 0; b < B; ++b) {
+        if (cta_seg_last[b] < 0) continue;
+        for (int g = L.cta_seg_first[b]; g <= cta_seg_last[b]; ++g) {
+            L.seg_cta_lo[g] = std::min(L.seg_cta_lo[g], b);
+            L.seg_cta_hi[g] = std::max(L.seg_cta_hi[g], b);
         }
     }
-    // upload tables
     size_t bytes = 4096 + pt.ent_mask.size() * 4 + pt.ent_chunk.size() * 4 + ctx->brk.size() * 8 + (size_t)B * 12 +
                    (size_t)std::max(nseg, 1) * 8 + (size_t)ctx->W * 24 + 16 * 16;
-    PG_TRY(ctx->tables.ensure(bytes));
-    uint8_t* base = (uint8_t*)ctx->tables.p;
+    PG_TRY(c.tables.ensure(bytes));
+    uint8_t* base = (uint8_t*)c.tables.p;
     size_t o = 0;
     uint32_t* d_mask_words = nullptr;
     PG_TRY(push(ctx, base, o, pt.ent_mask.data(), pt.ent_mask.size(), &d_mask_words));
@@ -746,10 +757,9 @@ int prepare_windowed(pg_ctx* ctx, const std::vector<int32_t>& hap_pop_local, int
     PG_TRY(push(ctx, base, o, ctx->win_seg_hi.data(), ctx->win_seg_hi.size(), &dt.win_seg_hi));
     PG_TRY(push(ctx, base, o, ctx->win_lo.data(), ctx->win_lo.size(), &dt.win_lo));
     PG_TRY(push(ctx, base, o, ctx->win_hi.data(), ctx->win_hi.size(), &dt.win_hi));
-    PG_CHECK(o <= ctx->tables.cap, "internal: table buffer overflow");
-    // slots
-    PG_TRY(ctx->part.ensure((size_t)std::max<int64_t>(L.total_slots, 1) * 8));
-    PG_CUDA(cudaMemsetAsync(ctx->part.p, 0, (size_t)std::max<int64_t>(L.total_slots, 1) * 8, ctx->stream));
+    PG_CHECK(o <= c.tables.cap, "internal: table buffer overflow");
+    // the host vectors must outlive the async copies
+    PG_CUDA(cudaStreamSynchronize(ctx->stream));
 
     K1Params& p = L.prm;
     memset(&p, 0, sizeof(p));
@@ -779,14 +789,28 @@ int prepare_windowed(pg_ctx* ctx, const std::vector<int32_t>& hap_pop_local, int
     p.nseg = nseg;
     p.cta_seg_first = dt.cta_seg_first;
     p.cta_slot_off = dt.cta_slot_off;
-    p.part = (unsigned long long*)ctx->part.p;
+    return PG_OK;
+}
+
+// per-call part: zeroed slots
+int arm_slots(pg_ctx* ctx, K1Cache& c) {
+    const size_t bytes = (size_t)std::max<int64_t>(c.L.total_slots, 1) * 8;
+    PG_TRY(ctx->part.ensure(bytes));
+    PG_CUDA(cudaMemsetAsync(ctx->part.p, 0, bytes, ctx->stream));
+    c.L.prm.part = (unsigned long long*)ctx->part.p;
+    c.L.prm.geno = (const uint8_t*)ctx->d_geno;
+    c.L.prm.pos = ctx->d_pos;
     return PG_OK;
 }
 
 template <int MODE, int P>
 int launch_site_pass(pg_ctx* ctx, const K1Launch& L, const char* name) {
     auto kern = k1_site_pass<MODE, P>;
-    PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.plan.smem_bytes));
+    static bool attr_set = false;     // per instantiation
+    if (!attr_set) {
+        PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
     const int ti = pg_time_begin(ctx, name);
     kern<<<L.plan.ctas, K1_THREADS, L.plan.smem_bytes, ctx->stream>>>(L.prm);
     pg_time_end(ctx, ti);
@@ -796,101 +820,160 @@ int launch_site_pass(pg_ctx* ctx, const K1Launch& L, const char* name) {
 
 int pad_pops(int P) { return P <= 2 ? 2 : (P <= 4 ? 4 : 8); }
 
+K1Cache* cache_of(pg_ctx* ctx, int slot) {
+    if (!ctx->k1_cache[slot]) ctx->k1_cache[slot] = new K1Cache();
+    return static_cast<K1Cache*>(ctx->k1_cache[slot]);
+}
+
+void fill_fin(FinParams& fp, pg_ctx* ctx, const K1Cache& c, int Q, int QI) {
+    memset(&fp, 0, sizeof(fp));
+    fp.part = (const unsigned long long*)ctx->part.p;
+    fp.seg_cta_lo = c.dt.seg_cta_lo;
+    fp.seg_cta_hi = c.dt.seg_cta_hi;
+    fp.cta_seg_first = c.dt.cta_seg_first;
+    fp.cta_slot_off = c.dt.cta_slot_off;
+    fp.win_seg_lo = c.dt.win_seg_lo;
+    fp.win_seg_hi = c.dt.win_seg_hi;
+    fp.win_lo = c.dt.win_lo;
+    fp.win_hi = c.dt.win_hi;
+    fp.W = ctx->W;
+    fp.Q = Q;
+    fp.QI = QI;
+    for (int X = 0; X < PG_MAX_K1_POPS; ++X) fp.popN[X] = c.pt.popN[X];
+}
+
 }  // namespace
+
+void pg_k1_cache_free(pg_ctx* ctx) {
+    for (int k = 0; k < 2; ++k)
+        if (ctx->k1_cache[k]) {
+            K1Cache* c = static_cast<K1Cache*>(ctx->k1_cache[k]);
+            c->tables.release();
+            delete c;
+            ctx->k1_cache[k] = nullptr;
+        }
+}
 
 // ================================================================================================
 // pg_popgen
 // ================================================================================================
+// Device-record variant: d_rec is a DEVICE buffer of W * (3 + P + 2*npairs) 8-byte words.
+extern "C" int pg_popgen_device(pg_ctx* ctx, int32_t min_sites, double min_data, int32_t force_path, void* d_rec,
+                                int64_t* n_pairwise) {
+    PG_CHECK(ctx && d_rec, "pg_popgen_device: null argument");
+    PG_CHECK(ctx->P >= 1, "pg_popgen: call pg_set_pops first");
+    PG_CHECK(force_path == 0 || force_path == 2, "pg_popgen: force_path must be 0 or 2");
+    PG_CHECK(ctx->P <= PG_MAX_K1_POPS, "pg_popgen: P=%d > %d populations is not supported yet", ctx->P, PG_MAX_K1_POPS);
+    PG_CUDA(cudaSetDevice(ctx->device));
+    pg_timings_reset(ctx);
+    if (n_pairwise) *n_pairwise = 0;
+    const int P = ctx->P;
+    const int npairs = P * (P - 1) / 2;
+    const int RC = 3 + P + 2 * npairs;
+    const int64_t W = ctx->W;
+    if (W == 0) return PG_OK;
+    if (ctx->S == 0) {
+        std::vector<unsigned long long> h((size_t)W * RC);
+        const double qn = NAN;
+        unsigned long long nanbits;
+        memcpy(&nanbits, &qn, 8);
+        for (int64_t w = 0; w < W; ++w) {
+            h[w * RC] = 0;
+            h[w * RC + 1] = 0;
+            h[w * RC + 2] = (0 < min_sites) ? 0 : 1;
+            for (int k = 3; k < RC; ++k) h[w * RC + k] = nanbits;
+        }
+        PG_CUDA(cudaMemcpy(d_rec, h.data(), h.size() * 8, cudaMemcpyHostToDevice));
+        return PG_OK;
+    }
+    const int Pp = pad_pops(P);
+    const int Q = 3 + Pp + Pp * (Pp - 1) / 2;
+    K1Cache& c = *cache_of(ctx, 0);
+    if (!c.valid || c.epoch != ctx->epoch) {
+        c.valid = false;
+        for (int x = 0; x < P; ++x) {
+            int N = 0;
+            for (int h = 0; h < ctx->H; ++h) N += ctx->hap_pop[h] == x;
+            PG_CHECK(N >= 1, "pg_popgen: population %d has no haplotypes", x);
+        }
+        PG_TRY(prepare_windowed(ctx, c, ctx->hap_pop, Pp, Q));
+        c.epoch = ctx->epoch;
+        c.valid = true;
+    }
+    PG_TRY(arm_slots(ctx, c));
+    if (Pp == 2) PG_TRY((launch_site_pass<MODE_POPGEN, 2>(ctx, c.L, "k1_popgen")));
+    else if (Pp == 4) PG_TRY((launch_site_pass<MODE_POPGEN, 4>(ctx, c.L, "k1_popgen")));
+    else PG_TRY((launch_site_pass<MODE_POPGEN, 8>(ctx, c.L, "k1_popgen")));
+
+    PG_TRY(ctx->out_i.ensure((size_t)W * 4 + 128));
+    int* d_cnt = (int*)ctx->out_i.p;
+    int32_t* d_path = (int32_t*)ctx->out_i.p + 16;
+    PG_CUDA(cudaMemsetAsync(d_cnt, 0, 4, ctx->stream));
+    FinParams fp;
+    fill_fin(fp, ctx, c, Q, Q);
+    fp.P = P;
+    fp.Ppad = Pp;
+    fp.min_sites = min_sites;
+    fp.min_data = min_data;
+    fp.force_path = force_path;
+    fp.rec = (unsigned long long*)d_rec;
+    fp.RC = RC;
+    fp.path = d_path;
+    fp.n_pairwise = d_cnt;
+    const int ti = pg_time_begin(ctx, "k1_finalize");
+    k1_finalize<MODE_POPGEN><<<(unsigned)std::min<int64_t>(W, 65535), 64, 0, ctx->stream>>>(fp);
+    pg_time_end(ctx, ti);
+    PG_CUDA(cudaGetLastError());
+    void* hp = nullptr;
+    PG_TRY(pg_pinned(ctx, (size_t)W * 4 + 256, &hp));
+    int* h_cnt = (int*)hp;
+    PG_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PG_CUDA(cudaStreamSynchronize(ctx->stream));
+    const int nk2 = *h_cnt;
+    if (n_pairwise) *n_pairwise = nk2;
+    if (nk2 > 0) {
+        int32_t* h_path = (int32_t*)hp + 16;
+        PG_CUDA(cudaMemcpyAsync(h_path, d_path, (size_t)W * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        PG_CUDA(cudaStreamSynchronize(ctx->stream));
+        std::vector<int64_t> k2_windows;
+        k2_windows.reserve((size_t)nk2);
+        for (int64_t w = 0; w < W; ++w)
+            if (h_path[w] == 2) k2_windows.push_back(w);
+        PG_TRY(pg_k2_popgen_windows(ctx, k2_windows, min_sites, min_data, d_rec, RC));
+    }
+    return PG_OK;
+}
+
 extern "C" int pg_popgen(pg_ctx* ctx, int32_t min_sites, double min_data, int32_t force_path, double* pi, double* dxy,
                          double* fst, int64_t* n_sites, int64_t* pos_sum, int32_t* path) {
     PG_CHECK(ctx && pi && dxy && fst && n_sites && pos_sum && path, "pg_popgen: null argument");
     PG_CHECK(ctx->P >= 1, "pg_popgen: call pg_set_pops first");
-    PG_CHECK(force_path == 0 || force_path == 2, "pg_popgen: force_path must be 0 or 2");
-    PG_CUDA(cudaSetDevice(ctx->device));
-    pg_timings_reset(ctx);
     const int P = ctx->P;
     const int npairs = P * (P - 1) / 2;
+    const int RC = 3 + P + 2 * npairs;
     const int64_t W = ctx->W;
-    if (W == 0) return PG_OK;
-    for (int x = 0; x < P; ++x) {
-        int N = 0;
-        for (int h = 0; h < ctx->H; ++h) N += ctx->hap_pop[h] == x;
-        PG_CHECK(N >= 1, "pg_popgen: population %d has no haplotypes", x);
-    }
-    std::vector<int64_t> k2_windows;
-    if (ctx->S == 0) {
-        for (int64_t w = 0; w < W; ++w) {
-            n_sites[w] = 0;
-            pos_sum[w] = 0;
-            path[w] = (0 < min_sites) ? 0 : 1;
-            for (int x = 0; x < P; ++x) pi[w * P + x] = NAN;
-            for (int k = 0; k < npairs; ++k) dxy[w * npairs + k] = fst[w * npairs + k] = NAN;
-        }
+    if (W == 0) {
+        pg_timings_reset(ctx);
         return PG_OK;
     }
-    if (P <= PG_MAX_K1_POPS) {
-        const int Pp = pad_pops(P);
-        const int Q = 3 + Pp + Pp * (Pp - 1) / 2;
-        K1Launch L;
-        DevTables dt;
-        PopTables pt;
-        PG_TRY(prepare_windowed(ctx, ctx->hap_pop, Pp, Q, L, dt, pt));
-        if (Pp == 2) PG_TRY((launch_site_pass<MODE_POPGEN, 2>(ctx, L, "k1_popgen")));
-        else if (Pp == 4) PG_TRY((launch_site_pass<MODE_POPGEN, 4>(ctx, L, "k1_popgen")));
-        else PG_TRY((launch_site_pass<MODE_POPGEN, 8>(ctx, L, "k1_popgen")));
-
-        // outputs on device: pi | dxy | fst | n_sites | pos_sum | path
-        const size_t nd = (size_t)W * (P + 2 * npairs);
-        PG_TRY(ctx->out_d.ensure(nd * 8 + 64));
-        PG_TRY(ctx->out_i.ensure((size_t)W * (8 + 8 + 4) + 64));
-        FinParams fp;
-        memset(&fp, 0, sizeof(fp));
-        fp.part = (const unsigned long long*)ctx->part.p;
-        fp.seg_cta_lo = dt.seg_cta_lo;
-        fp.seg_cta_hi = dt.seg_cta_hi;
-        fp.cta_seg_first = dt.cta_seg_first;
-        fp.cta_slot_off = dt.cta_slot_off;
-        fp.win_seg_lo = dt.win_seg_lo;
-        fp.win_seg_hi = dt.win_seg_hi;
-        fp.win_lo = dt.win_lo;
-        fp.win_hi = dt.win_hi;
-        fp.W = W;
-        fp.Q = Q;
-        fp.QI = Q;
-        fp.P = P;
-        fp.Ppad = Pp;
-        for (int X = 0; X < PG_MAX_K1_POPS; ++X) fp.popN[X] = pt.popN[X];
-        fp.min_sites = min_sites;
-        fp.min_data = min_data;
-        fp.force_path = force_path;
-        double* d_out = (double*)ctx->out_d.p;
-        fp.pi = d_out;
-        fp.dxy = d_out + (size_t)W * P;
-        fp.fst = d_out + (size_t)W * (P + npairs);
-        long long* d_i = (long long*)ctx->out_i.p;
-        fp.n_sites = d_i;
-        fp.pos_sum = d_i + W;
-        fp.path = (int32_t*)(d_i + 2 * W);
-        const int ti = pg_time_begin(ctx, "k1_finalize");
-        k1_finalize<MODE_POPGEN><<<(unsigned)std::min<int64_t>(W, 65535), 64, 0, ctx->stream>>>(fp);
-        pg_time_end(ctx, ti);
-        PG_CUDA(cudaGetLastError());
-        PG_CUDA(cudaMemcpyAsync(pi, fp.pi, (size_t)W * P * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    PG_CUDA(cudaSetDevice(ctx->device));
+    PG_TRY(ctx->out_d.ensure((size_t)W * RC * 8 + 64));
+    PG_TRY(pg_popgen_device(ctx, min_sites, min_data, force_path, ctx->out_d.p, nullptr));
+    std::vector<unsigned long long>& h = ctx->h_rec;
+    h.resize((size_t)W * RC);
+    PG_CUDA(cudaMemcpyAsync(h.data(), ctx->out_d.p, h.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    PG_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int64_t w = 0; w < W; ++w) {
+        const unsigned long long* r = h.data() + (size_t)w * RC;
+        n_sites[w] = (int64_t)r[0];
+        pos_sum[w] = (int64_t)r[1];
+        path[w] = (int32_t)r[2];
+        memcpy(pi + (size_t)w * P, r + 3, (size_t)P * 8);
         if (npairs) {
-            PG_CUDA(cudaMemcpyAsync(dxy, fp.dxy, (size_t)W * npairs * 8, cudaMemcpyDeviceToHost, ctx->stream));
-            PG_CUDA(cudaMemcpyAsync(fst, fp.fst, (size_t)W * npairs * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            memcpy(dxy + (size_t)w * npairs, r + 3 + P, (size_t)npairs * 8);
+            memcpy(fst + (size_t)w * npairs, r + 3 + P + npairs, (size_t)npairs * 8);
         }
-        PG_CUDA(cudaMemcpyAsync(n_sites, fp.n_sites, (size_t)W * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        PG_CUDA(cudaMemcpyAsync(pos_sum, fp.pos_sum, (size_t)W * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        PG_CUDA(cudaMemcpyAsync(path, fp.path, (size_t)W * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        PG_CUDA(cudaStreamSynchronize(ctx->stream));
-        for (int64_t w = 0; w < W; ++w)
-            if (path[w] == 2) k2_windows.push_back(w);
-    } else {
-        // more populations than K1 keeps in registers: bookkeeping on the host, statistics from K2
-        PG_CHECK(false, "pg_popgen: P=%d > %d populations is not supported yet", P, PG_MAX_K1_POPS);
     }
-    if (!k2_windows.empty()) PG_TRY(pg_k2_popgen_windows(ctx, k2_windows, min_sites, min_data, pi, dxy, fst));
     return PG_OK;
 }
 
@@ -919,60 +1002,54 @@ extern "C" int pg_abbababa(pg_ctx* ctx, int32_t p1, int32_t p2, int32_t p3, int3
         }
         return PG_OK;
     }
-    std::vector<int32_t> local(ctx->H, -1);
-    for (int h = 0; h < ctx->H; ++h)
-        for (int k = 0; k < 4; ++k)
-            if (ctx->hap_pop[h] == sel[k]) local[h] = k;
-    const int Q = 9;
-    K1Launch L;
-    DevTables dt;
-    PopTables pt;
-    PG_TRY(prepare_windowed(ctx, local, 4, Q, L, dt, pt));
+    const int Q = 9, RC = 8;
+    K1Cache& c = *cache_of(ctx, 1);
+    if (!c.valid || c.epoch != ctx->epoch || memcmp(c.sel, sel, sizeof(sel)) != 0) {
+        c.valid = false;
+        std::vector<int32_t> local(ctx->H, -1);
+        for (int h = 0; h < ctx->H; ++h)
+            for (int k = 0; k < 4; ++k)
+                if (ctx->hap_pop[h] == sel[k]) local[h] = k;
+        PG_TRY(prepare_windowed(ctx, c, local, 4, Q));
+        for (int k = 0; k < 4; ++k) PG_CHECK(c.pt.popN[k] >= 1, "pg_abbababa: population %d has no haplotypes", sel[k]);
+        memcpy(c.sel, sel, sizeof(sel));
+        c.epoch = ctx->epoch;
+        c.valid = true;
+    }
     for (int k = 0; k < 4; ++k) {
-        PG_CHECK(pt.popN[k] >= 1, "pg_abbababa: population %d has no haplotypes", sel[k]);
         // smallest n with (double)n / N >= minData  (genomics.py:1657-1660, exact in integers)
-        int thr = pt.popN[k] + 1;
-        for (int n = 0; n <= pt.popN[k]; ++n)
-            if ((double)n * 1.0 / (double)pt.popN[k] >= min_data) {
+        int thr = c.pt.popN[k] + 1;
+        for (int n = 0; n <= c.pt.popN[k]; ++n)
+            if ((double)n * 1.0 / (double)c.pt.popN[k] >= min_data) {
                 thr = n;
                 break;
             }
-        L.prm.thr[k] = thr;
+        c.L.prm.thr[k] = thr;
     }
-    PG_TRY((launch_site_pass<MODE_ABBA, 4>(ctx, L, "k1_abba")));
-    PG_TRY(ctx->out_d.ensure((size_t)W * 6 * 8 + 64));
-    PG_TRY(ctx->out_i.ensure((size_t)W * 16 + 64));
+    PG_TRY(arm_slots(ctx, c));
+    PG_TRY((launch_site_pass<MODE_ABBA, 4>(ctx, c.L, "k1_abba")));
+    PG_TRY(ctx->out_d.ensure((size_t)W * RC * 8 + 64));
     FinParams fp;
-    memset(&fp, 0, sizeof(fp));
-    fp.part = (const unsigned long long*)ctx->part.p;
-    fp.seg_cta_lo = dt.seg_cta_lo;
-    fp.seg_cta_hi = dt.seg_cta_hi;
-    fp.cta_seg_first = dt.cta_seg_first;
-    fp.cta_slot_off = dt.cta_slot_off;
-    fp.win_seg_lo = dt.win_seg_lo;
-    fp.win_seg_hi = dt.win_seg_hi;
-    fp.win_lo = dt.win_lo;
-    fp.win_hi = dt.win_hi;
-    fp.W = W;
-    fp.Q = Q;
-    fp.QI = 3;
+    fill_fin(fp, ctx, c, Q, 3);
     fp.P = 4;
     fp.Ppad = 4;
-    double* d_out = (double*)ctx->out_d.p;
-    fp.abba_out = d_out;
-    fp.sites_used = d_out + (size_t)W * 5;
-    long long* d_i = (long long*)ctx->out_i.p;
-    fp.n_sites = d_i;
-    fp.pos_sum = d_i + W;
+    fp.rec = (unsigned long long*)ctx->out_d.p;
+    fp.RC = RC;
     const int ti = pg_time_begin(ctx, "k1_finalize");
     k1_finalize<MODE_ABBA><<<(unsigned)std::min<int64_t>(W, 65535), 64, 0, ctx->stream>>>(fp);
     pg_time_end(ctx, ti);
     PG_CUDA(cudaGetLastError());
-    PG_CUDA(cudaMemcpyAsync(out, fp.abba_out, (size_t)W * 5 * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    PG_CUDA(cudaMemcpyAsync(sites_used, fp.sites_used, (size_t)W * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    PG_CUDA(cudaMemcpyAsync(n_sites, fp.n_sites, (size_t)W * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    PG_CUDA(cudaMemcpyAsync(pos_sum, fp.pos_sum, (size_t)W * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<unsigned long long>& h = ctx->h_rec;
+    h.resize((size_t)W * RC);
+    PG_CUDA(cudaMemcpyAsync(h.data(), ctx->out_d.p, h.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
     PG_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int64_t w = 0; w < W; ++w) {
+        const unsigned long long* r = h.data() + (size_t)w * RC;
+        n_sites[w] = (int64_t)r[0];
+        pos_sum[w] = (int64_t)r[1];
+        memcpy(out + (size_t)w * 5, r + 2, 40);
+        memcpy(sites_used + w, r + 7, 8);
+    }
     return PG_OK;
 }
 

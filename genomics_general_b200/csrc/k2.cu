@@ -303,9 +303,9 @@ struct PopEpiParams {
     const int32_t* pop_start;   // [P+1] plane-row offsets (rows sorted by population)
     int min_sites;
     double min_data;
-    double* pi;                 // [nb x P]
-    double* dxy;                // [nb x npairs]
-    double* fst;
+    unsigned long long* rec;    // device record table [W x RC]: pi at word 3, then dxy, then fst
+    int RC;
+    const int64_t* win_idx;     // [nb] global window index of each batch entry
 };
 
 __device__ __forceinline__ double nanmean_min_dev(double sum, double nonnan, double size, double min_data) {
@@ -355,11 +355,14 @@ __global__ void __launch_bounds__(256) k2_popgen_epi(const __grid_constant__ Pop
     __syncthreads();
     if (threadIdx.x != 0) return;
     const int npairs = P * (P - 1) / 2;
+    double* pi_o = reinterpret_cast<double*>(ep.rec + (size_t)ep.win_idx[wb] * ep.RC + 3);
+    double* dxy_o = pi_o + P;
+    double* fst_o = dxy_o + npairs;
     auto bidx = [&](int X, int Y) { return X * P - X * (X - 1) / 2 + (Y - X); };
     for (int X = 0; X < P; ++X) {
         const double Nx = ep.pop_start[X + 1] - ep.pop_start[X];
         const int b = bidx(X, X);
-        ep.pi[(size_t)wb * P + X] = nanmean_min_dev(2.0 * blk_s[b], 2.0 * (double)blk_c[b], Nx * Nx, ep.min_data);
+        pi_o[X] = nanmean_min_dev(2.0 * blk_s[b], 2.0 * (double)blk_c[b], Nx * Nx, ep.min_data);
     }
     int k = 0;
     for (int X = 0; X < P; ++X)
@@ -371,9 +374,9 @@ __global__ void __launch_bounds__(256) k2_popgen_epi(const __grid_constant__ Pop
             const double ct = (double)(blk_c[bxx] + blk_c[byy] + blk_c[bxy]);
             const double pi_t = nanmean_min_dev(2.0 * st, 2.0 * ct, (Nx + Ny) * (Nx + Ny), ep.min_data);
             const double w = 1.0 * Nx / (Nx + Ny);
-            const double pi_s = w * ep.pi[(size_t)wb * P + X] + (1 - w) * ep.pi[(size_t)wb * P + Y];
-            ep.dxy[(size_t)wb * npairs + k] = dxy;
-            ep.fst[(size_t)wb * npairs + k] = 1 - pi_s / pi_t;
+            const double pi_s = w * pi_o[X] + (1 - w) * pi_o[Y];
+            dxy_o[k] = dxy;
+            fst_o[k] = 1 - pi_s / pi_t;
         }
 }
 
@@ -498,12 +501,11 @@ int run_pair_batch(pg_ctx* ctx, const PlaneSet& ps, const std::vector<int64_t>& 
 
 }  // namespace
 
-// pi / dxy / Fst for the listed windows through the pairwise path; results are scattered into the
-// caller's [W x ...] arrays at the windows' own indices.
-int pg_k2_popgen_windows(pg_ctx* ctx, const std::vector<int64_t>& wins, int32_t min_sites, double min_data, double* pi,
-                         double* dxy, double* fst) {
+// pi / dxy / Fst for the listed windows through the pairwise path, written straight into the device
+// record table at the windows' own rows.
+int pg_k2_popgen_windows(pg_ctx* ctx, const std::vector<int64_t>& wins, int32_t min_sites, double min_data, void* d_rec,
+                         int RC) {
     const int P = ctx->P;
-    const int npairs = P * (P - 1) / 2;
     // plane rows: haplotypes that belong to a population, sorted by population (stable)
     std::vector<int32_t> order;
     std::vector<int32_t> pop_start(P + 1, 0);
@@ -523,13 +525,9 @@ int pg_k2_popgen_windows(pg_ctx* ctx, const std::vector<int64_t>& wins, int32_t 
     PG_TRY(build_planes(ctx, order, lo, hi, ps));
     const size_t HH = (size_t)ps.Hk * ps.Hk;
     const size_t per_batch = std::max<size_t>(1, std::min<size_t>(pair_budget_bytes() / (HH * 8), 65535));
-    PG_TRY(ctx->misc.ensure((size_t)(P + 1) * 4 + 64));
+    PG_TRY(ctx->misc.ensure((size_t)(P + 1) * 4 + per_batch * 8 + 128));
     PG_CUDA(cudaMemcpyAsync(ctx->misc.p, pop_start.data(), (size_t)(P + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
-    const size_t nd = (size_t)per_batch * (P + 2 * npairs);
-    PG_TRY(ctx->out_d.ensure(nd * 8 + 64));
-    void* hbuf = nullptr;
-    PG_TRY(pg_pinned(ctx, nd * 8 + 64, &hbuf));
-    double* hres = (double*)hbuf;
+    int64_t* d_widx = reinterpret_cast<int64_t*>((uint8_t*)ctx->misc.p + (((size_t)(P + 1) * 4 + 63) / 64) * 64);
     const int epi_smem = P * (P + 1) / 2 * 16 + 64;
     for (size_t b0 = 0; b0 < wins.size(); b0 += per_batch) {
         const size_t nb = std::min(per_batch, wins.size() - b0);
@@ -540,6 +538,7 @@ int pg_k2_popgen_windows(pg_ctx* ctx, const std::vector<int64_t>& wins, int32_t 
         }
         int32_t *d_diff = nullptr, *d_n = nullptr;
         PG_TRY(run_pair_batch(ctx, ps, blo, bhi, &d_diff, &d_n));
+        PG_CUDA(cudaMemcpyAsync(d_widx, wins.data() + b0, nb * 8, cudaMemcpyHostToDevice, ctx->stream));
         PopEpiParams ep;
         ep.diff = d_diff;
         ep.n = d_n;
@@ -548,23 +547,14 @@ int pg_k2_popgen_windows(pg_ctx* ctx, const std::vector<int64_t>& wins, int32_t 
         ep.pop_start = (const int32_t*)ctx->misc.p;
         ep.min_sites = min_sites;
         ep.min_data = min_data;
-        ep.pi = (double*)ctx->out_d.p;
-        ep.dxy = ep.pi + nb * P;
-        ep.fst = ep.dxy + nb * npairs;
+        ep.rec = (unsigned long long*)d_rec;
+        ep.RC = RC;
+        ep.win_idx = d_widx;
         const int ti = pg_time_begin(ctx, "k2_popgen_epi");
         k2_popgen_epi<<<(unsigned)nb, 256, epi_smem, ctx->stream>>>(ep);
         pg_time_end(ctx, ti);
         PG_CUDA(cudaGetLastError());
-        PG_CUDA(cudaMemcpyAsync(hres, ctx->out_d.p, nb * (P + 2 * npairs) * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        PG_CUDA(cudaStreamSynchronize(ctx->stream));
-        for (size_t k = 0; k < nb; ++k) {
-            const int64_t w = wins[b0 + k];
-            for (int x = 0; x < P; ++x) pi[w * P + x] = hres[k * P + x];
-            for (int q = 0; q < npairs; ++q) {
-                dxy[w * npairs + q] = hres[nb * P + k * npairs + q];
-                fst[w * npairs + q] = hres[nb * P + nb * npairs + k * npairs + q];
-            }
-        }
+        PG_CUDA(cudaStreamSynchronize(ctx->stream));     // host vectors and scratch are reused by the next batch
     }
     return PG_OK;
 }

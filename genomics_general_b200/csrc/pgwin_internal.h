@@ -103,6 +103,9 @@ struct pg_ctx {
     cudaStream_t copy_stream = nullptr;
     PgBuf stage[2];
     cudaEvent_t stage_full[2] = {nullptr, nullptr}, stage_free[2] = {nullptr, nullptr};
+    uint64_t epoch = 1;                       // bumped by every change of data shape / populations / windows
+    void* k1_cache[2] = {nullptr, nullptr};   // cached launch state (popgen, abba) — owned by k1.cu
+    std::vector<unsigned long long> h_rec;    // host copy of the per-window records
     void* h_pinned = nullptr;                 // small pinned staging for result read-back
     size_t h_pinned_cap = 0;
 };
@@ -115,5 +118,7 @@ int pg_pinned(pg_ctx* ctx, size_t bytes, void** out);
 int pg_build_segments(pg_ctx* ctx);
 
 // implemented in k1.cu / k2.cu
+// pairwise statistics for the listed windows, written into the DEVICE record table (stride RC words)
 int pg_k2_popgen_windows(pg_ctx* ctx, const std::vector<int64_t>& wins, int32_t min_sites, double min_data,
-                         double* pi, double* dxy, double* fst);
+                         void* d_rec, int RC);
+void pg_k1_cache_free(pg_ctx* ctx);

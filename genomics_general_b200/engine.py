@@ -138,6 +138,18 @@ class Engine:
         return dict(pi=pi, dxy=dxy, fst=fst, sites=sites, pos_sum=pos_sum, path=path,
                     pairs=list(itertools.combinations(range(P), 2)))
 
+    def popgen_record_width(self) -> int:
+        return 3 + self.P + 2 * (self.P * (self.P - 1) // 2)
+
+    def popgen_device(self, d_rec_ptr: int, min_sites: int = 1, min_data: float = 0.01, force_pairwise: bool = False) -> int:
+        """Statistics left on the device as fixed-width records (see pg_popgen_device); `d_rec_ptr` is a device
+        pointer to W * popgen_record_width() 8-byte words.  Returns the number of windows that took the pairwise path."""
+        n = C.c_int64(0)
+        check(self._lib.pg_popgen_device(self._ctx, int(min_sites) if min_sites else 0, float(min_data),
+                                         2 if force_pairwise else 0, C.c_void_p(int(d_rec_ptr)), C.byref(n)),
+              "pg_popgen_device")
+        return int(n.value)
+
     def abbababa(self, p1: int, p2: int, p3: int, o: int, min_data: float = 0.01):
         """-> dict(ABBA,BABA,D,fd,fdM [W], sitesUsed [W] (nan = no good site), sites, pos_sum)."""
         W = self.W

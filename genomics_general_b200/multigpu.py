@@ -69,3 +69,36 @@ def unpack_popgen_records(rec: np.ndarray, P: int) -> dict:
     npairs = P * (P - 1) // 2
     return dict(sites=rec[:, 0].astype(np.int64), pos_sum=rec[:, 1].astype(np.int64), path=rec[:, 2].astype(np.int32),
                 pi=rec[:, 3:3 + P], dxy=rec[:, 3 + P:3 + P + npairs], fst=rec[:, 3 + P + npairs:3 + P + 2 * npairs])
+
+
+class DeviceGather:
+    """Preallocated buffers for the per-step all-gather of device-resident popgen records (NCCL):
+    each rank's engine writes its records straight into `local` (pg_popgen_device), one
+    all_gather_into_tensor moves them, one D2H brings the table to the host."""
+
+    def __init__(self, counts, width, device):
+        import torch
+        self.counts = [int(c) for c in counts]
+        self.width = int(width)
+        self.wmax = max(max(self.counts), 1)
+        self.world = len(self.counts)
+        self.local = torch.zeros((self.wmax, self.width), dtype=torch.float64, device=device)
+        self.all = torch.zeros((self.world * self.wmax, self.width), dtype=torch.float64, device=device)
+        self.host = torch.zeros((self.world * self.wmax, self.width), dtype=torch.float64).pin_memory()
+
+    def gather(self) -> np.ndarray:
+        import torch
+        import torch.distributed as dist
+        dist.all_gather_into_tensor(self.all, self.local)
+        self.host.copy_(self.all, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        h = self.host.numpy()
+        return np.concatenate([h[r * self.wmax: r * self.wmax + self.counts[r]] for r in range(self.world)], axis=0)
+
+
+def unpack_device_records(rec: np.ndarray, P: int) -> dict:
+    """records as written by pg_popgen_device: the first three words are int64 bit patterns"""
+    npairs = P * (P - 1) // 2
+    ints = np.ascontiguousarray(rec[:, :3]).view(np.int64)
+    return dict(sites=ints[:, 0].copy(), pos_sum=ints[:, 1].copy(), path=ints[:, 2].astype(np.int32),
+                pi=rec[:, 3:3 + P], dxy=rec[:, 3 + P:3 + P + npairs], fst=rec[:, 3 + P + npairs:3 + P + 2 * npairs])

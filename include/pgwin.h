@@ -73,6 +73,13 @@ int pg_set_windows(pg_ctx* ctx, int64_t W, const int64_t* lo, const int64_t* hi)
 int pg_popgen(pg_ctx* ctx, int32_t min_sites, double min_data, int32_t force_path,
               double* pi, double* dxy, double* fst, int64_t* n_sites, int64_t* pos_sum, int32_t* path);
 
+/* Same statistics, left on the DEVICE as fixed-width records (so that the multi-GPU all-gather can read
+ * them in place): d_rec is a device buffer of W * (3 + P + 2*npairs) 8-byte words per window,
+ *   [sites (int64), pos_sum (int64), path (int64), pi[P], dxy[npairs], fst[npairs]] (statistics are doubles).
+ * *n_pairwise (optional) receives the number of windows that went through the pairwise path. */
+int pg_popgen_device(pg_ctx* ctx, int32_t min_sites, double min_data, int32_t force_path, void* d_rec,
+                     int64_t* n_pairwise);
+
 /* Replaces genomics.ABBABABA (genomics.py:1647-1695, polarize=True) per window.
  * out [W x 5] = ABBA, BABA, D, fd, fdM; sites_used [W] (double: nan when the window has no good site,
  * genomics.py:1694-1695); n_sites/pos_sum as above. p1,p2,p3,o are population indices of pg_set_pops. */
