@@ -211,6 +211,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_site_pass(const __grid_const
     uint8_t* tiles = smem;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)prm.stages * prm.tile_bytes);   // [stages]
     uint64_t* empty = full + 8;                                                                  // [stages]
+    volatile int* s_issued = reinterpret_cast<volatile int*>(empty + 8);   // tiles armed by the producer so far
     uint4* s_ent_mask = reinterpret_cast<uint4*>(smem + (size_t)prm.stages * prm.tile_bytes + 256);
     int32_t* s_ent_chunk = reinterpret_cast<int32_t*>(s_ent_mask + prm.n_ent);
 
@@ -228,6 +229,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_site_pass(const __grid_const
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], (uint32_t)prm.wpt);
         }
+        *s_issued = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -253,6 +255,10 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_site_pass(const __grid_const
                     bulk_g2s(dst + off, src + off, n, &full[stage]);
                 }
                 if (pbytes) bulk_g2s(dst + (size_t)prm.T * prm.pitch, prm.pos + s_lo, pbytes, &full[stage]);
+                // publish "tile `it` is armed": a consumer must not test a phase parity before its phase has
+                // been armed, or try_wait.parity would alias it with the previous (already complete) phase
+                __threadfence_block();
+                *s_issued = it + 1;
             }
         }
         return;
@@ -279,6 +285,9 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_site_pass(const __grid_const
 
     for (int it = team; it < ntiles; it += nteams) {
         const int stage = it % prm.stages;
+        if (lane == 0)
+            while (*s_issued <= it) __nanosleep(20);
+        __syncwarp();
         mbar_wait(&full[stage], (uint32_t)((it / prm.stages) & 1));
         const uint8_t* tile = tiles + (size_t)stage * prm.tile_bytes;
         const int64_t tile_site0 = prm.site_begin + (t0 + it) * prm.T;
