@@ -4,8 +4,8 @@
 Reference: /root/reference/popgenWindows.py — argparse 170-213, sample/pop parsing 253-307, header 319-354,
 worker stats_wrapper 28-75.  The process pipeline (producer / -T workers / sorter / writer) is replaced by:
 parse the whole file once -> dense int8 matrix -> all windows in one engine call -> rows.
-Supported --analysis: popDist, popPairDist (the defaults), indPairDist.  popFreq / indHet / hapStats are
-not on the accelerated path yet.
+Supported --analysis: popFreq, popDist, popPairDist, indPairDist.  indHet / hapStats are not on the accelerated
+path yet.
 """
 from __future__ import annotations
 
@@ -58,7 +58,7 @@ def build_parser():
 def main(argv=None):
     args = build_parser().parse_args(argv)
     minSites, coords = C.check_window_args(args)
-    unsupported = [a for a in args.analysis if a in ("popFreq", "indHet", "hapStats")]
+    unsupported = [a for a in args.analysis if a in ("indHet", "hapStats")]
     if unsupported:
         raise NotImplementedError("--analysis %s is not on the GPU path yet" % " ".join(unsupported))
 
@@ -70,7 +70,7 @@ def main(argv=None):
         allInds = sorted(set(allInds + args.samples.split(",")))
     if len(allInds) == 0:
         allInds = C.header_names(args.genoFile) if args.header is None else args.header.split()[2:]
-    if len(popNames) == 0 and ("popDist" in args.analysis or "popPairDist" in args.analysis):
+    if len(popNames) == 0 and ("popFreq" in args.analysis or "popDist" in args.analysis or "popPairDist" in args.analysis):
         popNames.append("all")
         popInds.append(allInds)
     ploidyDict = C.ploidy_dict(args, allInds, args.haploid.split(",") if args.haploid else None)
@@ -79,6 +79,9 @@ def main(argv=None):
     out = C.open_out(args.outFile)
     out.write("scaffold,start,end,mid,sites," if not args.addWindowID else "windowID,scaffold,start,end,mid,sites,")
     stats = []
+    if "popFreq" in args.analysis:
+        for key in ("l_", "S_", "thetaPi_", "thetaW_", "TajD_"):
+            stats += [key + n for n in popNames]
     if "popDist" in args.analysis:
         stats += ["pi_" + n for n in popNames]
     if "popPairDist" in args.analysis:
@@ -100,6 +103,12 @@ def main(argv=None):
         P = len(popNames)
         eng.set_pops(C.hap_pop_vector(gd, popNames, popInds), max(P, 1))
         r = eng.popgen(minSites, args.minData)
+        fq = None
+        if "popFreq" in args.analysis:
+            hp_all = C.hap_pop_vector(gd, popNames, popInds)
+            if np.any(hp_all < 0):
+                raise NotImplementedError("popFreq with samples outside every population (--samples) is not supported")
+            fq = eng.popgen_freqstats()
         npairs = P * (P - 1) // 2
         dmat = None
         if "indPairDist" in args.analysis:
@@ -112,13 +121,18 @@ def main(argv=None):
             good = pre[4] >= minSites
             vals = []
             if good:
+                if fq is not None:
+                    # l is a Python int, S a numpy integer in the reference: both print without a decimal point
+                    vals += [int(fq["l"][k])] * P
+                    vals += [np.nan if np.isnan(v) else int(v) for v in fq["S"][k]]
+                    vals += list(fq["thetaPi"][k]) + list(fq["thetaW"][k]) + list(fq["TajD"][k])
                 if "popDist" in args.analysis:
                     vals += list(r["pi"][k])
                 if "popPairDist" in args.analysis:
                     vals += list(r["dxy"][k]) + list(r["fst"][k])
                 if dmat is not None:
                     vals += list(dmat[k][iu])
-                vals = [round(np.float64(v), args.roundTo) for v in vals]
+                vals = [v if isinstance(v, int) else round(np.float64(v), args.roundTo) for v in vals]
             else:
                 vals = [np.nan] * len(stats)
             if good or args.writeFailedWindows:

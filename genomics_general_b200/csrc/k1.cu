@@ -193,7 +193,7 @@ template <int MODE, int P>
 struct ModeTraits;
 template <int P>
 struct ModeTraits<MODE_POPGEN, P> {
-    static constexpr int QI = 3 + P + P * (P - 1) / 2, QD = 0;
+    static constexpr int QI = 3 + P + P * (P - 1) / 2 + (P + 1) / 2, QD = 0;   // + segregating-site counts, 2 pops per word
 };
 template <int P>
 struct ModeTraits<MODE_ABBA, P> {
@@ -378,6 +378,9 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_site_pass(const __grid_const
                 for (int X = 0; X < P; ++X) {
                     const uint32_t sq = c[X][0] * c[X][0] + c[X][1] * c[X][1] + c[X][2] * c[X][2] + c[X][3] * c[X][3];
                     acc.i[3 + X] += (long long)(sq * f);
+                    // groupFreqStats (genomics.py:1002-1028): a complete site is segregating in X iff sum c^2 < N^2
+                    // (two populations share one 64-bit accumulator: 32-bit fields)
+                    acc.i[3 + P + P * (P - 1) / 2 + X / 2] += (pres && sq != n[X] * n[X]) ? (1ll << (32 * (X & 1))) : 0ll;
                 }
                 int k = 0;
 #pragma unroll
@@ -463,6 +466,7 @@ struct FinParams {
     int P;                         // real population count
     int Ppad;                      // template P used by the site pass
     int popN[PG_MAX_K1_POPS];
+    double harm_a[PG_MAX_K1_POPS], harm_a2[PG_MAX_K1_POPS];
     int min_sites;
     double min_data;
     int force_path;
@@ -526,6 +530,37 @@ __global__ void __launch_bounds__(64) k1_finalize(const __grid_constant__ FinPar
             double* fst_o = dxy_o + npairs;
             const long long Lp = (long long)sums[0];
             const bool ragged = (long long)sums[1] > 0;
+            {   // popFreq columns (valid for every window: they only use sites complete in all haplotypes)
+                double* fq = fst_o + npairs;           // [l, S[P], thetaPi[P], thetaW[P], TajD[P]]
+                fq[0] = (double)Lp;
+                const int npp = Pp * (Pp - 1) / 2;
+                for (int x = 0; x < P; ++x) {
+                    double Sx = nan_d(), tpi = nan_d(), tw = nan_d(), tD = nan_d();
+                    if (Lp >= 1) {
+                        const long long N = fp.popN[x];
+                        const long long seg = (long long)((sums[3 + Pp + npp + x / 2] >> (32 * (x & 1))) & 0xffffffffull);
+                        const long long pairs = (N * N * Lp - (long long)sums[3 + x]) / 2;   // sum over sites of sum_{a<b} c_a c_b
+                        Sx = (double)seg;
+                        tpi = (double)pairs / (.5 * (double)N * (double)(N - 1));
+                        const double a = fp.harm_a[x], a2 = fp.harm_a2[x];   // sum 1/i, sum 1/i^2 for i < N (host, same order)
+                        tw = (double)seg / a;
+                        // TajimaD (genomics.py:619-632)
+                        const double n_ = (double)N;
+                        const double b1 = (n_ + 1.) / (3 * (n_ - 1));
+                        const double b2 = (2. * (n_ * n_ + n_ + 3)) / (9 * n_ * (n_ - 1));
+                        const double c1 = b1 - (1. / a);
+                        const double c2 = b2 - ((n_ + 2) / (a * n_)) + a2 / (a * a);
+                        const double e1 = c1 / a;
+                        const double e2 = c2 / (a * a + a2);
+                        const double d = tpi - tw;
+                        tD = d / sqrt(e1 * Sx + e2 * Sx * (Sx - 1));
+                    }
+                    fq[1 + x] = Sx;
+                    fq[1 + P + x] = tpi;
+                    fq[1 + 2 * P + x] = tw;
+                    fq[1 + 3 * P + x] = tD;
+                }
+            }
             int path = 1;
             if (sites < fp.min_sites) path = 0;
             else if (ragged || fp.force_path == 2) path = 2;
@@ -848,7 +883,16 @@ void fill_fin(FinParams& fp, pg_ctx* ctx, const K1Cache& c, int Q, int QI) {
     fp.W = ctx->W;
     fp.Q = Q;
     fp.QI = QI;
-    for (int X = 0; X < PG_MAX_K1_POPS; ++X) fp.popN[X] = c.pt.popN[X];
+    for (int X = 0; X < PG_MAX_K1_POPS; ++X) {
+        fp.popN[X] = c.pt.popN[X];
+        double a = 0.0, a2 = 0.0;                       // TajimaD's python sums (genomics.py:621-623), same order
+        for (int i = 1; i < c.pt.popN[X]; ++i) {
+            a += 1. / (double)i;
+            a2 += 1. / ((double)i * (double)i);
+        }
+        fp.harm_a[X] = a;
+        fp.harm_a2[X] = a2;
+    }
 }
 
 }  // namespace
@@ -878,7 +922,7 @@ extern "C" int pg_popgen_device(pg_ctx* ctx, int32_t min_sites, double min_data,
     if (n_pairwise) *n_pairwise = 0;
     const int P = ctx->P;
     const int npairs = P * (P - 1) / 2;
-    const int RC = 3 + P + 2 * npairs;
+    const int RC = 3 + P + 2 * npairs + 1 + 4 * P;
     const int64_t W = ctx->W;
     if (W == 0) return PG_OK;
     if (ctx->S == 0) {
@@ -896,7 +940,7 @@ extern "C" int pg_popgen_device(pg_ctx* ctx, int32_t min_sites, double min_data,
         return PG_OK;
     }
     const int Pp = pad_pops(P);
-    const int Q = 3 + Pp + Pp * (Pp - 1) / 2;
+    const int Q = 3 + Pp + Pp * (Pp - 1) / 2 + (Pp + 1) / 2;
     K1Cache& c = *cache_of(ctx, 0);
     if (!c.valid || c.epoch != ctx->epoch) {
         c.valid = false;
@@ -959,7 +1003,7 @@ extern "C" int pg_popgen(pg_ctx* ctx, int32_t min_sites, double min_data, int32_
     PG_CHECK(ctx->P >= 1, "pg_popgen: call pg_set_pops first");
     const int P = ctx->P;
     const int npairs = P * (P - 1) / 2;
-    const int RC = 3 + P + 2 * npairs;
+    const int RC = 3 + P + 2 * npairs + 1 + 4 * P;
     const int64_t W = ctx->W;
     if (W == 0) {
         pg_timings_reset(ctx);
@@ -982,6 +1026,25 @@ extern "C" int pg_popgen(pg_ctx* ctx, int32_t min_sites, double min_data, int32_
             memcpy(dxy + (size_t)w * npairs, r + 3 + P, (size_t)npairs * 8);
             memcpy(fst + (size_t)w * npairs, r + 3 + P + npairs, (size_t)npairs * 8);
         }
+    }
+    return PG_OK;
+}
+
+// popFreq columns of the records produced by the most recent pg_popgen on this ctx
+extern "C" int pg_popgen_freqstats(pg_ctx* ctx, double* l, double* S, double* theta_pi, double* theta_w, double* taj_d) {
+    PG_CHECK(ctx && l && S && theta_pi && theta_w && taj_d, "pg_popgen_freqstats: null argument");
+    const int P = ctx->P;
+    const int npairs = P * (P - 1) / 2;
+    const int RC = 3 + P + 2 * npairs + 1 + 4 * P;
+    const int64_t W = ctx->W;
+    PG_CHECK(ctx->h_rec.size() == (size_t)W * RC, "pg_popgen_freqstats: call pg_popgen first (same pops / windows)");
+    for (int64_t w = 0; w < W; ++w) {
+        const double* f = reinterpret_cast<const double*>(ctx->h_rec.data() + (size_t)w * RC + 3 + P + 2 * npairs);
+        l[w] = f[0];
+        memcpy(S + (size_t)w * P, f + 1, (size_t)P * 8);
+        memcpy(theta_pi + (size_t)w * P, f + 1 + P, (size_t)P * 8);
+        memcpy(theta_w + (size_t)w * P, f + 1 + 2 * P, (size_t)P * 8);
+        memcpy(taj_d + (size_t)w * P, f + 1 + 3 * P, (size_t)P * 8);
     }
     return PG_OK;
 }

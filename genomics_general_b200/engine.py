@@ -139,7 +139,18 @@ class Engine:
                     pairs=list(itertools.combinations(range(P), 2)))
 
     def popgen_record_width(self) -> int:
-        return 3 + self.P + 2 * (self.P * (self.P - 1) // 2)
+        return 4 + 5 * self.P + 2 * (self.P * (self.P - 1) // 2)
+
+    def popgen_freqstats(self):
+        """popFreq columns (Alignment.groupFreqStats) of the most recent popgen() call:
+        dict(l [W], S, thetaPi, thetaW, TajD [W,P])."""
+        W, P = self.W, self.P
+        l = np.empty(W, dtype=np.float64)
+        out = {k: np.empty((W, P), dtype=np.float64) for k in ("S", "thetaPi", "thetaW", "TajD")}
+        check(self._lib.pg_popgen_freqstats(self._ctx, _ptr(l), _ptr(out["S"]), _ptr(out["thetaPi"]), _ptr(out["thetaW"]),
+                                            _ptr(out["TajD"])), "pg_popgen_freqstats")
+        out["l"] = l
+        return out
 
     def popgen_device(self, d_rec_ptr: int, min_sites: int = 1, min_data: float = 0.01, force_pairwise: bool = False) -> int:
         """Statistics left on the device as fixed-width records (see pg_popgen_device); `d_rec_ptr` is a device

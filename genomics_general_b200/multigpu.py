@@ -101,4 +101,5 @@ def unpack_device_records(rec: np.ndarray, P: int) -> dict:
     npairs = P * (P - 1) // 2
     ints = np.ascontiguousarray(rec[:, :3]).view(np.int64)
     return dict(sites=ints[:, 0].copy(), pos_sum=ints[:, 1].copy(), path=ints[:, 2].astype(np.int32),
-                pi=rec[:, 3:3 + P], dxy=rec[:, 3 + P:3 + P + npairs], fst=rec[:, 3 + P + npairs:3 + P + 2 * npairs])
+                pi=rec[:, 3:3 + P], dxy=rec[:, 3 + P:3 + P + npairs], fst=rec[:, 3 + P + npairs:3 + P + 2 * npairs],
+                popfreq=rec[:, 3 + P + 2 * npairs:])

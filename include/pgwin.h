@@ -74,11 +74,17 @@ int pg_popgen(pg_ctx* ctx, int32_t min_sites, double min_data, int32_t force_pat
               double* pi, double* dxy, double* fst, int64_t* n_sites, int64_t* pos_sum, int32_t* path);
 
 /* Same statistics, left on the DEVICE as fixed-width records (so that the multi-GPU all-gather can read
- * them in place): d_rec is a device buffer of W * (3 + P + 2*npairs) 8-byte words per window,
- *   [sites (int64), pos_sum (int64), path (int64), pi[P], dxy[npairs], fst[npairs]] (statistics are doubles).
+ * them in place): d_rec is a device buffer of W * (4 + 5P + 2*npairs) 8-byte words per window,
+ *   [sites (int64), pos_sum (int64), path (int64), pi[P], dxy[npairs], fst[npairs],
+ *    l, S[P], thetaPi[P], thetaW[P], TajD[P]] (statistics are doubles).
  * *n_pairwise (optional) receives the number of windows that went through the pairwise path. */
 int pg_popgen_device(pg_ctx* ctx, int32_t min_sites, double min_data, int32_t force_path, void* d_rec,
                      int64_t* n_pairwise);
+
+/* Replaces Alignment.groupFreqStats (genomics.py:1002-1028; popgenWindows --analysis popFreq): the columns
+ * computed alongside by the most recent pg_popgen call on this ctx.  l [W] = sites complete in every haplotype
+ * that belongs to a population; S, theta_pi, theta_w, taj_d [W x P]. */
+int pg_popgen_freqstats(pg_ctx* ctx, double* l, double* S, double* theta_pi, double* theta_w, double* taj_d);
 
 /* Replaces genomics.ABBABABA (genomics.py:1647-1695, polarize=True) per window.
  * out [W x 5] = ABBA, BABA, D, fd, fdM; sites_used [W] (double: nan when the window has no good site,

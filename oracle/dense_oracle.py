@@ -175,6 +175,45 @@ def group_dist_stats_closed_form(g, hap_pop, n_pops, min_sites=None, min_data=0.
 
 
 # ----------------------------------------------------------------------------------------
+# groupFreqStats  (genomics.py:1002-1028, baseCountPi 609-616, TajimaD 619-632)
+# ----------------------------------------------------------------------------------------
+def group_freq_stats(g, hap_pop, n_pops):
+    """dict of arrays l, S, thetaPi, thetaW, TajD (length P).  Only sites with no missing data in ANY
+    haplotype of the alignment are used (1010)."""
+    g = np.asarray(g)
+    hap_pop = np.asarray(hap_pop)
+    keep = np.all(g >= 0, axis=1)
+    gp = g[keep]
+    l = int(keep.sum())
+    out = dict(l=np.full(n_pops, float(l)), S=np.full(n_pops, np.nan), thetaPi=np.full(n_pops, np.nan),
+               thetaW=np.full(n_pops, np.nan), TajD=np.full(n_pops, np.nan))
+    if l < 1:
+        return out
+    counts = site_counts(gp, hap_pop, n_pops).astype(np.float64)          # [l,P,4]
+    for x in range(n_pops):
+        N = int((hap_pop == x).sum())
+        c = counts[:, x, :]
+        pairs = (c[:, 0] * c[:, 1] + c[:, 0] * c[:, 2] + c[:, 0] * c[:, 3] + c[:, 1] * c[:, 2] + c[:, 1] * c[:, 3]
+                 + c[:, 2] * c[:, 3])
+        with np.errstate(divide="ignore", invalid="ignore"):
+            site_pi = pairs / (.5 * N * (N - 1))
+            S = float((site_pi != 0.).sum())
+            theta_pi = float(site_pi.sum())
+            a = sum(1. / i for i in range(1, N))
+            a2 = sum(1. / (i ** 2) for i in range(1, N))
+            theta_w = np.float64(S) / np.float64(a)
+            b1 = (N + 1.) / (3 * (N - 1)) if N > 1 else np.nan
+            b2 = (2. * (N ** 2 + N + 3)) / (9 * N * (N - 1)) if N > 1 else np.nan
+            c1 = b1 - np.float64(1.) / np.float64(a)
+            c2 = b2 - np.float64(N + 2) / np.float64(a * N) + np.float64(a2) / np.float64(a ** 2)
+            e1 = c1 / np.float64(a)
+            e2 = c2 / np.float64(a ** 2 + a2)
+            D = (theta_pi - theta_w) / np.sqrt(e1 * S + e2 * S * (S - 1))
+        out["S"][x], out["thetaPi"][x], out["thetaW"][x], out["TajD"][x] = S, theta_pi, float(theta_w), float(D)
+    return out
+
+
+# ----------------------------------------------------------------------------------------
 # indPairDists  (genomics.py:934-954) in distMat.py's individual order (distMat.py:42-45)
 # ----------------------------------------------------------------------------------------
 def ind_pair_dists(g, hap_ind, n_ind, include_same_with_same=False, min_sites=None):

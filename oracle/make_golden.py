@@ -147,10 +147,18 @@ def make_window_cases():
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
             gds = aln.groupDistStats(doPairs=True, minSites=sp["minSites"], minData=sp["minData"])
+        alnf, _ = ref_alignment(g_file, names, ploidies, pop_names, pop_inds)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            try:
+                gfs = alnf.groupFreqStats()
+            except ZeroDivisionError:       # the reference raises for a single-haplotype population (TajimaD, 621-626)
+                gfs = None
         entry = dict(name=sp["name"], sample_names=names, ploidies=ploidies, pop_names=pop_names,
                      pop_inds=pop_inds, minSites=sp["minSites"], minData=sp["minData"],
                      hap_names=hap_names, hap_samples=hap_samples,
-                     groupDistStats={k: float(v) for k, v in gds.items()})
+                     groupDistStats={k: float(v) for k, v in gds.items()},
+                     groupFreqStats=None if gfs is None else {k: float(v) for k, v in gfs.items()})
         # per-pop site counts (freq.py default path, freq.py:52-58)
         sc = np.stack([aln.subset(groups=[p]).siteFreqs(asCounts=True) for p in pop_names], axis=1)
         arrays[sp["name"] + "__site_counts"] = sc.astype(np.int32)
@@ -294,6 +302,10 @@ def make_cli_cases():
                  "-m", "200", "-g", path, "-o", o, "-f", "phased", "-T", "1", "--popsFile", pops_file,
                  "--roundTo", "10"] + popargs)
             res["popgenWindows_sites"] = open(o).read()
+            run([sys.executable, os.path.join(REF, "popgenWindows.py"), "-w", str(c["w"]), "-m", str(c["m"]), "-g", path,
+                 "-o", o, "-f", "phased", "-T", "1", "--popsFile", pops_file, "--roundTo", "8",
+                 "--analysis", "popFreq", "popDist", "popPairDist", "indPairDist"] + popargs)
+            res["popgenWindows_popFreq_indPairDist"] = open(o).read()
             run([sys.executable, os.path.join(REF, "ABBABABAwindows.py"), "-w", str(c["w"]), "-m", str(c["m"]),
                  "-g", path, "-o", o, "-f", "phased", "-T", "1", "--popsFile", pops_file, "--minData", "0.5",
                  "-P1", "pop0", "-P2", "pop1", "-P3", "pop2", "-O", "pop3"])

@@ -200,3 +200,21 @@ def test_window_generators_yield_reference_windows(inputs):
     _, rows12 = _rows(CLI["four_pops"]["popgenWindows_roundTo12"])
     for name, val in zip(h.split(",")[5:], rows12[1][5:]):
         assert_close(gds[name], float(val), name, rtol=1e-6, atol=2e-12)
+
+
+def test_popgenWindows_popFreq_and_indPairDist_cli(inputs):
+    """--analysis popFreq popDist popPairDist indPairDist: same header (column order) and rows as the reference."""
+    from genomics_general_b200.cli import popgenWindows
+    i = inputs["four_pops"]
+    c = i["cfg"]
+    o = os.path.join(i["dir"], "pf.csv")
+    popgenWindows.main(["-w", str(c["w"]), "-m", str(c["m"]), "-g", i["geno"], "-o", o, "-f", "phased", "-T", "1",
+                        "--popsFile", i["pops"], "--roundTo", "8", "--analysis", "popFreq", "popDist", "popPairDist",
+                        "indPairDist"] + _popargs(i["spec"]))
+    ours, ref = open(o).read(), CLI["four_pops"]["popgenWindows_popFreq_indPairDist"]
+    _compare_csv(ours, ref, 5, 1e-6, 2e-8)
+    # integer columns (l_, S_) are printed without a decimal point, exactly like the reference
+    h, r1 = _rows(ours)
+    _, r2 = _rows(ref)
+    cols = [k for k, n in enumerate(h.split(",")) if n.startswith(("l_", "S_"))]
+    assert cols and all(a[k] == b[k] for a, b in zip(r1, r2) for k in cols)

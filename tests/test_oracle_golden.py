@@ -66,6 +66,15 @@ def test_closed_form_covers_some_cases():
     assert n_ok >= 3
 
 
+@pytest.mark.parametrize("case", [m for m in META if m.get("groupFreqStats")], ids=[m["name"] for m in META if m.get("groupFreqStats")])
+def test_group_freq_stats(case):
+    g = ARR[case["name"] + "__g_aln"]
+    r = do.group_freq_stats(g, ARR[case["name"] + "__hap_pop"], len(case["pop_names"]))
+    for x, p in enumerate(case["pop_names"]):
+        for k in ("l", "S", "thetaPi", "thetaW", "TajD"):
+            assert_close(r[k][x], case["groupFreqStats"]["%s_%s" % (k, p)], "%s_%s" % (k, p), rtol=1e-12)
+
+
 @pytest.mark.parametrize("case", META, ids=IDS)
 def test_site_counts_bit_exact(case):
     g = ARR[case["name"] + "__g_aln"]
