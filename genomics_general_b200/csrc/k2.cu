@@ -24,9 +24,14 @@ constexpr int TSP = TS + 1;     // padded (16-byte units) -> conflict-free STS/L
 constexpr int KW = 16;          // words (32 sites each) per pipeline stage
 constexpr int K4 = KW / 4;
 constexpr int NST = 3;          // cp.async ring depth
-constexpr int OPND_BYTES = 3 * K4 * TSP * 16;
-constexpr int STAGE_BYTES = 2 * OPND_BYTES;
-constexpr int PAIR_SMEM = NST * STAGE_BYTES;
+enum { PAIR_DIFF = 0, PAIR_N = 1 };
+template <int WHAT>
+struct PairGeom {
+    static constexpr int NP = (WHAT == PAIR_DIFF) ? 3 : 1;      // planes staged per operand
+    static constexpr int OPND_BYTES = NP * K4 * TSP * 16;
+    static constexpr int STAGE_BYTES = 2 * OPND_BYTES;
+    static constexpr int SMEM = NST * STAGE_BYTES;
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid) {
@@ -125,18 +130,74 @@ __global__ void __launch_bounds__(256) k2_build_planes(const uint8_t* __restrict
 // pair kernel
 // ------------------------------------------------------------------------------------------------
 struct PairParams {
-    const uint32_t* planes;
-    int Hk;
+    const uint32_t* planes;   // [3][Hk][NWp]
+    int Hk;                   // rows per plane in storage
     int64_t NWp;
     int64_t site_base;
     const int64_t* win_lo;    // [nb] absolute site indices (non-empty windows only)
     const int64_t* win_hi;
     int ntile;
-    int32_t* out_diff;        // [nb][Hk][Hk]
-    int32_t* out_n;
+    int n_rows;               // logical rows of this pass (haplotypes for DIFF, unique valid-masks for N)
+    const int32_t* row_map;   // logical row -> plane row (nullptr = identity)
+    int32_t* out;             // [nb][n_rows][n_rows]
 };
 
+// One pass over a window for one 64x64 tile pair.
+//   PAIR_DIFF: diff_ij = sum popc(((b0_i^b0_j)|(b1_i^b1_j)) & m_i & m_j)      (3 planes)
+//   PAIR_N   : n_ij    = sum popc(m_i & m_j)                                   (valid plane only, unique masks)
+// DIAG: the tile pair is on the diagonal -> pairs with a > b are mirror images, skip them.
+template <int WHAT, bool DIAG>
+__device__ __forceinline__ void pair_accumulate(const uint8_t* sb, int ty, int tx, int (&acc)[4][4]) {
+    using G = PairGeom<WHAT>;
+    const uint4* I4 = reinterpret_cast<const uint4*>(sb);
+    const uint4* J4 = reinterpret_cast<const uint4*>(sb + G::OPND_BYTES);
+#pragma unroll
+    for (int k4 = 0; k4 < K4; ++k4) {
+        if (WHAT == PAIR_DIFF) {
+            uint4 B0[4], B1[4], BM[4];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                B0[b] = J4[(0 * K4 + k4) * TSP + tx + 16 * b];
+                B1[b] = J4[(1 * K4 + k4) * TSP + tx + 16 * b];
+                BM[b] = J4[(2 * K4 + k4) * TSP + tx + 16 * b];
+            }
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const uint4 A0 = I4[(0 * K4 + k4) * TSP + ty + 16 * a];
+                const uint4 A1 = I4[(1 * K4 + k4) * TSP + ty + 16 * a];
+                const uint4 AM = I4[(2 * K4 + k4) * TSP + ty + 16 * a];
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    if (DIAG && a > b) continue;
+#define K2_DIFF_WORD(C) acc[a][b] += __popc(((A0.C ^ B0[b].C) | (A1.C ^ B1[b].C)) & AM.C & BM[b].C);
+                    K2_DIFF_WORD(x)
+                    K2_DIFF_WORD(y)
+                    K2_DIFF_WORD(z)
+                    K2_DIFF_WORD(w)
+#undef K2_DIFF_WORD
+                }
+            }
+        } else {
+            uint4 BM[4];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) BM[b] = J4[k4 * TSP + tx + 16 * b];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const uint4 AM = I4[k4 * TSP + ty + 16 * a];
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    if (DIAG && a > b) continue;
+                    acc[a][b] += __popc(AM.x & BM[b].x) + __popc(AM.y & BM[b].y) + __popc(AM.z & BM[b].z) +
+                                 __popc(AM.w & BM[b].w);
+                }
+            }
+        }
+    }
+}
+
+template <int WHAT>
 __global__ void __launch_bounds__(256, 2) k2_pair(const __grid_constant__ PairParams pp) {
+    using G = PairGeom<WHAT>;
     extern __shared__ __align__(16) uint8_t psm[];
     const int tid = threadIdx.x;
     const int ty = tid >> 4, tx = tid & 15;
@@ -154,29 +215,34 @@ __global__ void __launch_bounds__(256, 2) k2_pair(const __grid_constant__ PairPa
     const uint32_t mask_last = 0xffffffffu >> (31 - (int)((rel_hi - 1) & 31));
     const int64_t k_begin = w_first & ~(int64_t)3;
     const int nchunk = (int)((w_last - k_begin) / KW) + 1;
+    constexpr int VALID_PLANE = (WHAT == PAIR_DIFF) ? 2 : 0;    // index of the valid plane inside a staged operand
 
     auto fill = [&](int chunk, int stage) {
         const int64_t k0 = k_begin + (int64_t)chunk * KW;
-        uint8_t* sb = psm + stage * STAGE_BYTES;
+        uint8_t* sb = psm + stage * G::STAGE_BYTES;
 #pragma unroll
-        for (int it = 0; it < (2 * 3 * TS * K4) / 256; ++it) {
+        for (int it = 0; it < (2 * G::NP * TS * K4 + 255) / 256; ++it) {
             const int item = tid + it * 256;
+            if (item >= 2 * G::NP * TS * K4) break;
             const int k4 = item & (K4 - 1);
             const int hap = (item / K4) & (TS - 1);
-            const int p = (item / (K4 * TS)) % 3;
-            const int opnd = item / (K4 * TS * 3);
+            const int p = (item / (K4 * TS)) % G::NP;
+            const int opnd = item / (K4 * TS * G::NP);
             const int gh = (opnd == 0 ? ti : tj) * TS + hap;
-            const bool valid = gh < pp.Hk;
-            const uint32_t* src = pp.planes + ((size_t)p * pp.Hk + (valid ? gh : 0)) * pp.NWp + k0 + 4 * k4;
-            cp_async16(sb + opnd * OPND_BYTES + ((p * K4 + k4) * TSP + hap) * 16, src, valid);
+            const bool valid = gh < pp.n_rows;
+            int prow = valid ? gh : 0;
+            if (pp.row_map) prow = pp.row_map[prow];
+            const int plane = (WHAT == PAIR_DIFF) ? p : 2;
+            const uint32_t* src = pp.planes + ((size_t)plane * pp.Hk + prow) * pp.NWp + k0 + 4 * k4;
+            cp_async16(sb + opnd * G::OPND_BYTES + ((p * K4 + k4) * TSP + hap) * 16, src, valid);
         }
     };
 
-    int accd[4][4], accn[4][4];
+    int acc[4][4];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) accd[a][b] = accn[a][b] = 0;
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0;
 
     for (int s = 0; s < NST - 1; ++s) {
         if (s < nchunk) fill(s, s);
@@ -185,14 +251,12 @@ __global__ void __launch_bounds__(256, 2) k2_pair(const __grid_constant__ PairPa
     for (int ch = 0; ch < nchunk; ++ch) {
         cp_async_wait<NST - 2>();
         __syncthreads();
-        // prefetch chunk ch+NST-1 into the stage consumed at iteration ch-1 (all threads are past it)
-        {
+        {   // prefetch chunk ch+NST-1 into the stage consumed at iteration ch-1 (all threads are past it)
             const int nxt = ch + NST - 1;
             if (nxt < nchunk) fill(nxt, nxt % NST);
             cp_async_commit();
         }
-        const int stage = ch % NST;
-        uint8_t* sb = psm + stage * STAGE_BYTES;
+        uint8_t* sb = psm + (ch % NST) * G::STAGE_BYTES;
         const int64_t k0 = k_begin + (int64_t)ch * KW;
         const bool need_fix = (k0 <= w_first) || (k0 + KW - 1 >= w_last);
         if (need_fix) {   // block-uniform: clip the J operand's valid plane to the window
@@ -206,65 +270,69 @@ __global__ void __launch_bounds__(256, 2) k2_pair(const __grid_constant__ PairPa
                         if (word == w_last) mk &= mask_last;
                     }
                     if (mk != 0xffffffffu) {
-                        uint32_t* wp = reinterpret_cast<uint32_t*>(sb + OPND_BYTES + ((2 * K4 + (kk >> 2)) * TSP + tid) * 16) + (kk & 3);
+                        uint32_t* wp = reinterpret_cast<uint32_t*>(sb + G::OPND_BYTES +
+                                                                   ((VALID_PLANE * K4 + (kk >> 2)) * TSP + tid) * 16) + (kk & 3);
                         *wp &= mk;
                     }
                 }
             }
             __syncthreads();
         }
-        const uint4* I4 = reinterpret_cast<const uint4*>(sb);
-        const uint4* J4 = reinterpret_cast<const uint4*>(sb + OPND_BYTES);
-#pragma unroll
-        for (int k4 = 0; k4 < K4; ++k4) {
-            uint4 B0[4], B1[4], BM[4];
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                B0[b] = J4[(0 * K4 + k4) * TSP + tx + 16 * b];
-                B1[b] = J4[(1 * K4 + k4) * TSP + tx + 16 * b];
-                BM[b] = J4[(2 * K4 + k4) * TSP + tx + 16 * b];
-            }
-#pragma unroll
-            for (int a = 0; a < 4; ++a) {
-                const uint4 A0 = I4[(0 * K4 + k4) * TSP + ty + 16 * a];
-                const uint4 A1 = I4[(1 * K4 + k4) * TSP + ty + 16 * a];
-                const uint4 AM = I4[(2 * K4 + k4) * TSP + ty + 16 * a];
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-#define K2_PAIR_WORD(C)                                                   \
-    {                                                                     \
-        const uint32_t mm = AM.C & BM[b].C;                               \
-        const uint32_t df = ((A0.C ^ B0[b].C) | (A1.C ^ B1[b].C)) & mm;   \
-        accd[a][b] += __popc(df);                                         \
-        accn[a][b] += __popc(mm);                                         \
-    }
-                    K2_PAIR_WORD(x)
-                    K2_PAIR_WORD(y)
-                    K2_PAIR_WORD(z)
-                    K2_PAIR_WORD(w)
-#undef K2_PAIR_WORD
-                }
-            }
-        }
+        if (ti == tj) pair_accumulate<WHAT, true>(sb, ty, tx, acc);
+        else pair_accumulate<WHAT, false>(sb, ty, tx, acc);
     }
     cp_async_wait<0>();
-    const size_t HH = (size_t)pp.Hk * pp.Hk;
-    int32_t* od = pp.out_diff + (size_t)wb * HH;
-    int32_t* on = pp.out_n + (size_t)wb * HH;
+    const size_t RR = (size_t)pp.n_rows * pp.n_rows;
+    int32_t* o = pp.out + (size_t)wb * RR;
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
         const int i = ti * TS + ty + 16 * a;
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
+            if (ti == tj && a > b) continue;             // written as the mirror of the (b, a) pair of thread (tx, ty)
             const int j = tj * TS + tx + 16 * b;
-            if (i < pp.Hk && j < pp.Hk) {
-                od[(size_t)i * pp.Hk + j] = accd[a][b];
-                on[(size_t)i * pp.Hk + j] = accn[a][b];
-                od[(size_t)j * pp.Hk + i] = accd[a][b];
-                on[(size_t)j * pp.Hk + i] = accn[a][b];
+            if (i < pp.n_rows && j < pp.n_rows) {
+                o[(size_t)i * pp.n_rows + j] = acc[a][b];
+                o[(size_t)j * pp.n_rows + i] = acc[a][b];
             }
         }
     }
+}
+
+// ---- haplotypes with identical valid planes share their n_ij -------------------------------------------
+__device__ __forceinline__ unsigned long long mixu64(unsigned long long x) {
+    x ^= x >> 30;
+    x *= 0xBF58476D1CE4E5B9ull;
+    x ^= x >> 27;
+    x *= 0x94D049BB133111EBull;
+    x ^= x >> 31;
+    return x;
+}
+__global__ void __launch_bounds__(256) k2_hash_rows(const uint32_t* __restrict__ mplane, int64_t NWp,
+                                                    unsigned long long* __restrict__ hash) {
+    __shared__ unsigned long long sh[8];
+    const uint32_t* row = mplane + (size_t)blockIdx.x * NWp;
+    unsigned long long h = 0;
+    for (int64_t j = threadIdx.x; j < NWp; j += 256) h += mixu64(((unsigned long long)row[j] << 32) ^ (unsigned long long)j);
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) h += __shfl_xor_sync(0xffffffffu, h, d);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = h;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int w = 0; w < 8; ++w) t += sh[w];
+        hash[blockIdx.x] = t;
+    }
+}
+__global__ void __launch_bounds__(256) k2_verify_rows(const uint32_t* __restrict__ mplane, int64_t NWp,
+                                                      const int32_t* __restrict__ rep, int* __restrict__ mismatch) {
+    const int r = blockIdx.x, q = rep[r];
+    if (q == r) return;
+    const uint32_t* a = mplane + (size_t)r * NWp;
+    const uint32_t* b = mplane + (size_t)q * NWp;
+    bool bad = false;
+    for (int64_t j = threadIdx.x; j < NWp; j += 256) bad |= (a[j] != b[j]);
+    if (bad) atomicOr(mismatch, 1);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -297,8 +365,10 @@ __device__ __forceinline__ void block_sum(double& s, long long& c, double* sh_s,
 }
 
 struct PopEpiParams {
-    const int32_t* diff;
-    const int32_t* n;
+    const int32_t* diff;       // [nb][Hk][Hk]
+    const int32_t* n;          // [nb][Hm][Hm] over unique valid-masks
+    const int32_t* mid;        // [Hk] mask id of each plane row
+    int Hm;
     int Hk, P;
     const int32_t* pop_start;   // [P+1] plane-row offsets (rows sorted by population)
     int min_sites;
@@ -328,7 +398,7 @@ __global__ void __launch_bounds__(256) k2_popgen_epi(const __grid_constant__ Pop
     const int wb = blockIdx.x;
     const size_t HH = (size_t)ep.Hk * ep.Hk;
     const int32_t* D = ep.diff + (size_t)wb * HH;
-    const int32_t* N = ep.n + (size_t)wb * HH;
+    const int32_t* N = ep.n + (size_t)wb * ep.Hm * ep.Hm;
     int bi = 0;
     for (int X = 0; X < P; ++X)
         for (int Y = X; Y < P; ++Y, ++bi) {
@@ -341,7 +411,7 @@ __global__ void __launch_bounds__(256) k2_popgen_epi(const __grid_constant__ Pop
             for (int idx = threadIdx.x; idx < total; idx += 256) {
                 const int i = r0 + idx / nc, j = c0 + idx % nc;
                 if (X == Y && j <= i) continue;
-                const int nij = N[(size_t)i * ep.Hk + j];
+                const int nij = N[(size_t)ep.mid[i] * ep.Hm + ep.mid[j]];
                 if (nij == 0 || (ep.min_sites > 0 && nij < ep.min_sites)) continue;   // nan entries
                 s += (double)D[(size_t)i * ep.Hk + j] / (double)nij;
                 c += 1;
@@ -383,6 +453,8 @@ __global__ void __launch_bounds__(256) k2_popgen_epi(const __grid_constant__ Pop
 struct IndEpiParams {
     const int32_t* diff;
     const int32_t* n;
+    const int32_t* mid;
+    int Hm;
     int Hk, n_ind;
     const int32_t* ind_start;   // [n_ind+1]
     int include_same;
@@ -393,7 +465,7 @@ __global__ void __launch_bounds__(256) k2_ind_epi(const __grid_constant__ IndEpi
     const int wb = blockIdx.y;
     const size_t HH = (size_t)ep.Hk * ep.Hk;
     const int32_t* D = ep.diff + (size_t)wb * HH;
-    const int32_t* N = ep.n + (size_t)wb * HH;
+    const int32_t* N = ep.n + (size_t)wb * ep.Hm * ep.Hm;
     const int64_t total = (int64_t)ep.n_ind * ep.n_ind;
     for (int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * 256) {
         const int a = (int)(idx / ep.n_ind), b = (int)(idx % ep.n_ind);
@@ -406,7 +478,7 @@ __global__ void __launch_bounds__(256) k2_ind_epi(const __grid_constant__ IndEpi
                     if (!ep.include_same) continue;          // diagonal = nan (genomics.py:940)
                     d = 0.0;                                 // distMatrix leaves 0 on the diagonal (908)
                 } else {
-                    const int nij = N[(size_t)i * ep.Hk + j];
+                    const int nij = N[(size_t)ep.mid[i] * ep.Hm + ep.mid[j]];
                     if (nij == 0) continue;                  // np.mean of an empty array = nan
                     d = (double)D[(size_t)i * ep.Hk + j] / (double)nij;
                 }
@@ -425,6 +497,10 @@ struct PlaneSet {
     int64_t site_base = 0;
     int64_t NWp = 0;
     uint32_t* planes = nullptr;
+    int Hm = 0;                        // unique valid-masks
+    std::vector<int32_t> mid;          // [Hk] mask id per row
+    const int32_t* d_mid = nullptr;    // device copy
+    const int32_t* d_rowmap = nullptr; // [Hm] mask id -> a representative plane row
 };
 
 // Build bit-planes for sites [lo, hi) of the haplotype columns listed in `order` (plane row r = column order[r]).
@@ -457,6 +533,64 @@ int build_planes(pg_ctx* ctx, const std::vector<int32_t>& order, int64_t lo, int
     ps.site_base = sb;
     ps.NWp = NWp;
     ps.planes = (uint32_t*)ctx->planes.p;
+    // group rows by identical valid plane: hash, group on the host, verify on the device
+    PG_TRY(ctx->misc4.ensure((size_t)Hk * 8 + (size_t)Hk * 12 + 256));
+    unsigned long long* d_hash = (unsigned long long*)ctx->misc4.p;
+    int32_t* d_rep = (int32_t*)(d_hash + Hk);
+    int32_t* d_mid = d_rep + Hk;
+    int32_t* d_rowmap = d_mid + Hk;
+    int* d_flag = (int*)(d_rowmap + Hk);
+    const uint32_t* mplane = ps.planes + (size_t)2 * Hk * NWp;
+    {
+        const int ti = pg_time_begin(ctx, "k2_mask_groups");
+        k2_hash_rows<<<Hk, 256, 0, ctx->stream>>>(mplane, NWp, d_hash);
+        pg_time_end(ctx, ti);
+        PG_CUDA(cudaGetLastError());
+    }
+    std::vector<unsigned long long> hh(Hk);
+    PG_CUDA(cudaMemcpyAsync(hh.data(), d_hash, (size_t)Hk * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    PG_CUDA(cudaStreamSynchronize(ctx->stream));
+    std::vector<int32_t> rep(Hk), mid(Hk), rowmap;
+    {
+        std::vector<std::pair<unsigned long long, int>> first;   // (hash, first row) — Hk is small
+        for (int r = 0; r < Hk; ++r) {
+            int q = -1;
+            for (size_t k = 0; k < first.size(); ++k)
+                if (first[k].first == hh[r]) {
+                    q = (int)k;
+                    break;
+                }
+            if (q < 0) {
+                first.push_back({hh[r], r});
+                q = (int)first.size() - 1;
+                rowmap.push_back(r);
+            }
+            mid[r] = q;
+            rep[r] = first[q].second;
+        }
+    }
+    PG_CUDA(cudaMemcpyAsync(d_rep, rep.data(), (size_t)Hk * 4, cudaMemcpyHostToDevice, ctx->stream));
+    PG_CUDA(cudaMemsetAsync(d_flag, 0, 4, ctx->stream));
+    {
+        const int ti = pg_time_begin(ctx, "k2_mask_groups");
+        k2_verify_rows<<<Hk, 256, 0, ctx->stream>>>(mplane, NWp, d_rep, d_flag);
+        pg_time_end(ctx, ti);
+        PG_CUDA(cudaGetLastError());
+    }
+    int flag = 0;
+    PG_CUDA(cudaMemcpyAsync(&flag, d_flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PG_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (flag || getenv("PG_K2_NO_MASK_SHARING")) {     // hash collision (or disabled): every row is its own group
+        rowmap.resize(Hk);
+        for (int r = 0; r < Hk; ++r) mid[r] = rowmap[r] = r;
+    }
+    ps.Hm = (int)rowmap.size();
+    ps.mid = mid;
+    PG_CUDA(cudaMemcpyAsync(d_mid, mid.data(), (size_t)Hk * 4, cudaMemcpyHostToDevice, ctx->stream));
+    PG_CUDA(cudaMemcpyAsync(d_rowmap, rowmap.data(), (size_t)ps.Hm * 4, cudaMemcpyHostToDevice, ctx->stream));
+    PG_CUDA(cudaStreamSynchronize(ctx->stream));
+    ps.d_mid = d_mid;
+    ps.d_rowmap = d_rowmap;
     return PG_OK;
 }
 
@@ -467,12 +601,12 @@ size_t pair_budget_bytes() {
     return mb << 20;
 }
 
-// Pair matrices for a batch of non-empty windows (absolute site ranges) -> ctx->pairs (diff | n)
+// Pair matrices for a batch of non-empty windows (absolute site ranges) -> ctx->pairs: diff [nb][Hk^2] | n [nb][Hm^2]
 int run_pair_batch(pg_ctx* ctx, const PlaneSet& ps, const std::vector<int64_t>& lo, const std::vector<int64_t>& hi,
                    int32_t** d_diff, int32_t** d_n) {
     const int nb = (int)lo.size();
-    const size_t HH = (size_t)ps.Hk * ps.Hk;
-    PG_TRY(ctx->pairs.ensure((size_t)nb * HH * 8 + 64));
+    const size_t HH = (size_t)ps.Hk * ps.Hk, MM = (size_t)ps.Hm * ps.Hm;
+    PG_TRY(ctx->pairs.ensure((size_t)nb * (HH + MM) * 4 + 64));
     PG_TRY(ctx->misc3.ensure((size_t)nb * 16 + 64));
     int64_t* d_lo = (int64_t*)ctx->misc3.p;
     int64_t* d_hi = d_lo + nb;
@@ -485,17 +619,38 @@ int run_pair_batch(pg_ctx* ctx, const PlaneSet& ps, const std::vector<int64_t>& 
     pp.site_base = ps.site_base;
     pp.win_lo = d_lo;
     pp.win_hi = d_hi;
+    static bool attr = false;
+    if (!attr) {
+        PG_CUDA(cudaFuncSetAttribute(k2_pair<PAIR_DIFF>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairGeom<PAIR_DIFF>::SMEM));
+        PG_CUDA(cudaFuncSetAttribute(k2_pair<PAIR_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairGeom<PAIR_N>::SMEM));
+        attr = true;
+    }
+    // diff over all haplotype rows
+    pp.n_rows = ps.Hk;
+    pp.row_map = nullptr;
     pp.ntile = (ps.Hk + TS - 1) / TS;
-    pp.out_diff = (int32_t*)ctx->pairs.p;
-    pp.out_n = pp.out_diff + (size_t)nb * HH;
-    PG_CUDA(cudaFuncSetAttribute(k2_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM));
-    dim3 grid((unsigned)(pp.ntile * (pp.ntile + 1) / 2), (unsigned)nb);
-    const int ti = pg_time_begin(ctx, "k2_pair");
-    k2_pair<<<grid, 256, PAIR_SMEM, ctx->stream>>>(pp);
-    pg_time_end(ctx, ti);
-    PG_CUDA(cudaGetLastError());
-    *d_diff = pp.out_diff;
-    *d_n = pp.out_n;
+    pp.out = (int32_t*)ctx->pairs.p;
+    {
+        dim3 grid((unsigned)(pp.ntile * (pp.ntile + 1) / 2), (unsigned)nb);
+        const int ti = pg_time_begin(ctx, "k2_pair_diff");
+        k2_pair<PAIR_DIFF><<<grid, 256, PairGeom<PAIR_DIFF>::SMEM, ctx->stream>>>(pp);
+        pg_time_end(ctx, ti);
+        PG_CUDA(cudaGetLastError());
+    }
+    *d_diff = pp.out;
+    // n over the unique valid-masks
+    pp.n_rows = ps.Hm;
+    pp.row_map = ps.d_rowmap;
+    pp.ntile = (ps.Hm + TS - 1) / TS;
+    pp.out = (int32_t*)ctx->pairs.p + (size_t)nb * HH;
+    {
+        dim3 grid((unsigned)(pp.ntile * (pp.ntile + 1) / 2), (unsigned)nb);
+        const int ti = pg_time_begin(ctx, "k2_pair_n");
+        k2_pair<PAIR_N><<<grid, 256, PairGeom<PAIR_N>::SMEM, ctx->stream>>>(pp);
+        pg_time_end(ctx, ti);
+        PG_CUDA(cudaGetLastError());
+    }
+    *d_n = pp.out;
     return PG_OK;
 }
 
@@ -542,6 +697,8 @@ int pg_k2_popgen_windows(pg_ctx* ctx, const std::vector<int64_t>& wins, int32_t 
         PopEpiParams ep;
         ep.diff = d_diff;
         ep.n = d_n;
+        ep.mid = ps.d_mid;
+        ep.Hm = ps.Hm;
         ep.Hk = ps.Hk;
         ep.P = P;
         ep.pop_start = (const int32_t*)ctx->misc.p;
@@ -620,6 +777,8 @@ extern "C" int pg_pairdist(pg_ctx* ctx, int32_t n_ind, const int32_t* hap_ind, i
         IndEpiParams ep;
         ep.diff = d_diff;
         ep.n = d_n;
+        ep.mid = ps.d_mid;
+        ep.Hm = ps.Hm;
         ep.Hk = ps.Hk;
         ep.n_ind = n_ind;
         ep.ind_start = (const int32_t*)ctx->misc.p;
@@ -664,8 +823,11 @@ extern "C" int pg_pair_counts(pg_ctx* ctx, int64_t window, int32_t* diff, int32_
     std::vector<int64_t> blo(1, lo), bhi(1, hi);
     int32_t *d_diff = nullptr, *d_n = nullptr;
     PG_TRY(run_pair_batch(ctx, ps, blo, bhi, &d_diff, &d_n));
+    std::vector<int32_t> nu((size_t)ps.Hm * ps.Hm);
     PG_CUDA(cudaMemcpyAsync(diff, d_diff, HH * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    PG_CUDA(cudaMemcpyAsync(n, d_n, HH * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PG_CUDA(cudaMemcpyAsync(nu.data(), d_n, nu.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
     PG_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < H; ++i)
+        for (int j = 0; j < H; ++j) n[(size_t)i * H + j] = nu[(size_t)ps.mid[i] * ps.Hm + ps.mid[j]];
     return PG_OK;
 }

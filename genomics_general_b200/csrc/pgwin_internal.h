@@ -98,7 +98,7 @@ struct pg_ctx {
     size_t events_used = 0;
     int64_t launches = 0;
     // scratch
-    PgBuf tables, part, segmeta, winmeta, out_d, out_i, planes, pairs, misc, misc2, misc3;
+    PgBuf tables, part, segmeta, winmeta, out_d, out_i, planes, pairs, misc, misc2, misc3, misc4;
     // upload pipeline: copy stream + two staging buffers
     cudaStream_t copy_stream = nullptr;
     PgBuf stage[2];
