@@ -349,7 +349,8 @@ def main():
     variants = {"miss=0.02 (pairwise K2 path)": {
         "value": world * S * v_steps / dt2, "unit": "sites/s", "ms_per_step": 1e3 * dt2 / v_steps,
         "kernel_ms": kernel_ms2,
-        "pair_sites_per_s": pair_sites / (kernel_ms2.get("k2_pair", float("nan")) * 1e-3),
+        "pair_sites_per_s": pair_sites / ((kernel_ms2.get("k2_pair_diff", float("nan")) +
+                                           kernel_ms2.get("k2_pair_n", float("nan"))) * 1e-3),
         "bound": "integer issue (POPC on the XU pipe), not HBM"}}
 
     sampler.stop()

@@ -48,18 +48,19 @@ __device__ __forceinline__ void cp_async_wait() {
 // bit-plane build
 // ------------------------------------------------------------------------------------------------
 constexpr int BP_SITES = 256, BP_COLS = 128, BP_ROWW = BP_COLS / 4 + 1;   // 33 words per site row (odd: no conflicts)
-constexpr int BP_SMEM = BP_SITES * BP_ROWW * 4 + 3 * BP_COLS * 8 * 4 + BP_COLS * 4 + BP_COLS * 4 + 16;
+constexpr int BP_OUTW = 3 * BP_COLS + 4;                                     // words per warp in the ballot staging (+pad)
+constexpr int BP_SMEM = BP_SITES * BP_ROWW * 4 + 8 * BP_OUTW * 4 + BP_COLS * 4 + 64;
 
 // Resident code: A 0x01, C 0x04, G 0x10, T 0x40, missing 0x00  ->  bit0 = C|T (0x44), bit1 = G|T (0x50), valid = !=0
+// Each warp transposes 32 sites (lane = site): one LDS.32 brings 4 columns, a predicate LOP3 + VOTE per byte and plane
+// yields the 32-site word of that (plane, column); the 4 ballots of a plane leave as one STS.128.
 __global__ void __launch_bounds__(256) k2_build_planes(const uint8_t* __restrict__ geno, int pitch, int64_t S,
                                                        int64_t site_base, const int32_t* __restrict__ col_to_row,
                                                        uint32_t* __restrict__ planes, int Hk, int64_t NWp) {
     extern __shared__ __align__(16) uint8_t bsm[];
     uint32_t* tile = reinterpret_cast<uint32_t*>(bsm);                          // [256][33]
-    uint32_t* outp = tile + BP_SITES * BP_ROWW;                                  // [3][128][8]
-    int32_t* s_c2r = reinterpret_cast<int32_t*>(outp + 3 * BP_COLS * 8);        // [128] plane row of a local column
-    int32_t* s_used = s_c2r + BP_COLS;                                           // [128] compact list of used columns
-    int32_t* s_nused = s_used + BP_COLS;
+    uint32_t* outp = tile + BP_SITES * BP_ROWW;                                  // [8 warps][3 planes][128 cols] (+pad)
+    int32_t* s_c2r = reinterpret_cast<int32_t*>(outp + 8 * BP_OUTW);            // [128] plane row of a local column
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int col0 = blockIdx.x * BP_COLS;
     const int64_t sblk = blockIdx.y;
@@ -91,38 +92,45 @@ __global__ void __launch_bounds__(256) k2_build_planes(const uint8_t* __restrict
         }
     }
     __syncthreads();
-    if (warp == 0) {   // ordered compaction of the used columns
-        int base = 0;
-        for (int c = 0; c < BP_COLS; c += 32) {
-            const bool u = s_c2r[c + lane] >= 0;
-            const unsigned m = __ballot_sync(0xffffffffu, u);
-            if (u) s_used[base + __popc(m & ((1u << lane) - 1u))] = c + lane;
-            base += __popc(m);
+    const uint32_t* myrow = tile + (warp * 32 + lane) * BP_ROWW;
+    uint32_t* myout = outp + warp * BP_OUTW;
+#pragma unroll 2
+    for (int cw = 0; cw < BP_COLS / 4; ++cw) {
+        // skip words whose 4 columns are all unused (warp-uniform)
+        const int4 rr = *reinterpret_cast<const int4*>(s_c2r + cw * 4);
+        if ((rr.x & rr.y & rr.z & rr.w) < 0) continue;
+        const uint32_t w = myrow[cw];
+        uint4 m, b0, b1;
+        m.x = __ballot_sync(0xffffffffu, (w & 0x000000ffu) != 0u);
+        m.y = __ballot_sync(0xffffffffu, (w & 0x0000ff00u) != 0u);
+        m.z = __ballot_sync(0xffffffffu, (w & 0x00ff0000u) != 0u);
+        m.w = __ballot_sync(0xffffffffu, (w & 0xff000000u) != 0u);
+        b0.x = __ballot_sync(0xffffffffu, (w & 0x00000044u) != 0u);
+        b0.y = __ballot_sync(0xffffffffu, (w & 0x00004400u) != 0u);
+        b0.z = __ballot_sync(0xffffffffu, (w & 0x00440000u) != 0u);
+        b0.w = __ballot_sync(0xffffffffu, (w & 0x44000000u) != 0u);
+        b1.x = __ballot_sync(0xffffffffu, (w & 0x00000050u) != 0u);
+        b1.y = __ballot_sync(0xffffffffu, (w & 0x00005000u) != 0u);
+        b1.z = __ballot_sync(0xffffffffu, (w & 0x00500000u) != 0u);
+        b1.w = __ballot_sync(0xffffffffu, (w & 0x50000000u) != 0u);
+        if (lane == 0) {
+            *reinterpret_cast<uint4*>(myout + 0 * BP_COLS + cw * 4) = b0;
+            *reinterpret_cast<uint4*>(myout + 1 * BP_COLS + cw * 4) = b1;
+            *reinterpret_cast<uint4*>(myout + 2 * BP_COLS + cw * 4) = m;
         }
-        if (lane == 0) *s_nused = base;
     }
     __syncthreads();
-    const int nused = *s_nused;
-    // warp w transposes sites 32w..32w+31 (lane = site) for every used column
-    const uint8_t* myrow = reinterpret_cast<const uint8_t*>(tile + (warp * 32 + lane) * BP_ROWW);
-#pragma unroll 4
-    for (int u = 0; u < nused; ++u) {
-        const int cl = s_used[u];
-        const uint32_t b = myrow[cl];
-        const uint32_t m = __ballot_sync(0xffffffffu, b != 0u);
-        const uint32_t b0 = __ballot_sync(0xffffffffu, (b & 0x44u) != 0u);
-        const uint32_t b1 = __ballot_sync(0xffffffffu, (b & 0x50u) != 0u);
-        if (lane < 3) outp[(lane * BP_COLS + cl) * 8 + warp] = (lane == 0) ? b0 : (lane == 1 ? b1 : m);
-    }
-    __syncthreads();
-    for (int idx = tid; idx < 3 * BP_COLS * 2; idx += 256) {
-        const int p = idx / (BP_COLS * 2);
-        const int rem = idx % (BP_COLS * 2);
-        const int cl = rem >> 1, half = rem & 1;
+    // (plane, column) -> 8 consecutive words (one per warp) = 32 bytes of the plane row
+    for (int idx = tid; idx < 3 * BP_COLS; idx += 256) {
+        const int p = idx / BP_COLS, cl = idx % BP_COLS;
         const int r = s_c2r[cl];
         if (r < 0) continue;
-        const uint4 v = *reinterpret_cast<const uint4*>(outp + (p * BP_COLS + cl) * 8 + half * 4);
-        *reinterpret_cast<uint4*>(planes + ((size_t)p * Hk + r) * NWp + sblk * 8 + half * 4) = v;
+        uint32_t v[8];
+#pragma unroll
+        for (int wv = 0; wv < 8; ++wv) v[wv] = outp[wv * BP_OUTW + p * BP_COLS + cl];
+        uint4* dst = reinterpret_cast<uint4*>(planes + ((size_t)p * Hk + r) * NWp + sblk * 8);
+        dst[0] = make_uint4(v[0], v[1], v[2], v[3]);
+        dst[1] = make_uint4(v[4], v[5], v[6], v[7]);
     }
 }
 
