@@ -418,21 +418,22 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_site_pass(const __grid_const
                     const uint32_t k1 = da == 0 ? c[0][0] : (da == 1 ? c[0][1] : (da == 2 ? c[0][2] : c[0][3]));
                     const uint32_t k2 = da == 0 ? c[1][0] : (da == 1 ? c[1][1] : (da == 2 ? c[1][2] : c[1][3]));
                     const uint32_t k3 = da == 0 ? c[2][0] : (da == 1 ? c[2][1] : (da == 2 ? c[2][2] : c[2][3]));
+                    // the derived allele is absent from the outgroup: p4 = 0/n4 = 0 and every (1 - p4) factor of the
+                    // reference's formulas is exactly 1.0 — dropping those factors leaves the values bit-identical
                     const double p1 = (double)k1 / (double)n[0];
                     const double p2 = (double)k2 / (double)n[1];
                     const double p3 = (double)k3 / (double)n[2];
-                    const double p4 = 0.0 / (double)n[3];
-                    const double abba = (1 - p1) * p2 * p3 * (1 - p4);
-                    const double baba = p1 * (1 - p2) * p3 * (1 - p4);
+                    const double abba = (1 - p1) * p2 * p3;
+                    const double baba = p1 * (1 - p2) * p3;
                     const double pd = p2 * (p2 > p3 ? 1.0 : 0.0) + p3 * (p3 >= p2 ? 1.0 : 0.0);
-                    const double fd_den = (1 - p1) * pd * pd * (1 - p4) - p1 * (1 - pd) * pd * (1 - p4);
+                    const double fd_den = (1 - p1) * pd * pd - p1 * (1 - pd) * pd;
                     const bool A = p3 > p1, Bq = p3 > p2, Xq = p1 > p2, Yq = !Xq;
                     const double xa = (Xq && A) ? 1.0 : 0.0, yb = (Yq && Bq) ? 1.0 : 0.0;
                     const double xna = (Xq && !A) ? 1.0 : 0.0, ynb = (Yq && !Bq) ? 1.0 : 0.0;
                     const double pdm1 = p3 * xa + p1 * (1.0 - xa);
                     const double pdm2 = p3 * yb + p2 * (1.0 - yb);
                     const double pdm3 = -p3 * xa + p3 * yb - p1 * xna + p2 * ynb;
-                    const double fdm_den = (1 - pdm1) * pdm2 * pdm3 * (1 - p4) - pdm1 * (1 - pdm2) * pdm3 * (1 - p4);
+                    const double fdm_den = (1 - pdm1) * pdm2 * pdm3 - pdm1 * (1 - pdm2) * pdm3;
                     acc.i[0] += 1;
                     acc.d[0] += abba;
                     acc.d[1] += baba;
