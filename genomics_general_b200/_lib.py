@@ -57,6 +57,7 @@ _SIGS = {
                             C.c_void_p, C.c_void_p, C.c_void_p]),
     "pg_popgen_device": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_int32, C.c_void_p, C.POINTER(C.c_int64)]),
     "pg_popgen_freqstats": (C.c_int, [C.c_void_p] * 6),
+    "pg_set_freqstats": (C.c_int, [C.c_void_p, C.c_int32]),
     "pg_abbababa": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_void_p,
                               C.c_void_p, C.c_void_p, C.c_void_p]),
     "pg_site_counts": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),

@@ -102,6 +102,7 @@ def main(argv=None):
         eng.set_windows(lo, hi)
         P = len(popNames)
         eng.set_pops(C.hap_pop_vector(gd, popNames, popInds), max(P, 1))
+        eng.set_freqstats("popFreq" in args.analysis)
         r = eng.popgen(minSites, args.minData)
         fq = None
         if "popFreq" in args.analysis:

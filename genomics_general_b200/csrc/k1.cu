@@ -22,7 +22,7 @@ namespace {
 constexpr int K1_WARPS = 8;                       // consumer warps per CTA
 constexpr int K1_THREADS = (K1_WARPS + 1) * 32;   // + one TMA producer warp
 
-enum { MODE_POPGEN = 0, MODE_ABBA = 1, MODE_COUNTS = 2 };
+enum { MODE_POPGEN = 0, MODE_ABBA = 1, MODE_COUNTS = 2, MODE_POPGEN_FREQ = 3 };   // FREQ = POPGEN + popFreq counters
 
 struct K1Params {
     const uint8_t* geno;
@@ -193,6 +193,10 @@ template <int MODE, int P>
 struct ModeTraits;
 template <int P>
 struct ModeTraits<MODE_POPGEN, P> {
+    static constexpr int QI = 3 + P + P * (P - 1) / 2, QD = 0;
+};
+template <int P>
+struct ModeTraits<MODE_POPGEN_FREQ, P> {
     static constexpr int QI = 3 + P + P * (P - 1) / 2 + (P + 1) / 2, QD = 0;   // + segregating-site counts, 2 pops per word
 };
 template <int P>
@@ -361,7 +365,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_site_pass(const __grid_const
                 }
             }
 
-            if (MODE == MODE_POPGEN) {
+            if (MODE == MODE_POPGEN || MODE == MODE_POPGEN_FREQ) {
                 bool allpres = true, allmiss = true;
 #pragma unroll
                 for (int X = 0; X < P; ++X) {
@@ -380,7 +384,8 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_site_pass(const __grid_const
                     acc.i[3 + X] += (long long)(sq * f);
                     // groupFreqStats (genomics.py:1002-1028): a complete site is segregating in X iff sum c^2 < N^2
                     // (two populations share one 64-bit accumulator: 32-bit fields)
-                    acc.i[3 + P + P * (P - 1) / 2 + X / 2] += (pres && sq != n[X] * n[X]) ? (1ll << (32 * (X & 1))) : 0ll;
+                    if (MODE == MODE_POPGEN_FREQ)
+                        acc.i[3 + P + P * (P - 1) / 2 + X / 2] += (pres && sq != n[X] * n[X]) ? (1ll << (32 * (X & 1))) : 0ll;
                 }
                 int k = 0;
 #pragma unroll
@@ -471,6 +476,7 @@ struct FinParams {
     int min_sites;
     double min_data;
     int force_path;
+    int with_freq;                 // the site pass carried the popFreq counters
     // outputs: fixed-width 8-byte records per window
     //   popgen: [sites(i64) pos_sum(i64) path(i64) pi[P] dxy[npairs] fst[npairs]]
     //   abba  : [sites(i64) pos_sum(i64) ABBA BABA D fd fdM sitesUsed]
@@ -533,11 +539,11 @@ __global__ void __launch_bounds__(64) k1_finalize(const __grid_constant__ FinPar
             const bool ragged = (long long)sums[1] > 0;
             {   // popFreq columns (valid for every window: they only use sites complete in all haplotypes)
                 double* fq = fst_o + npairs;           // [l, S[P], thetaPi[P], thetaW[P], TajD[P]]
-                fq[0] = (double)Lp;
+                fq[0] = fp.with_freq ? (double)Lp : nan_d();
                 const int npp = Pp * (Pp - 1) / 2;
                 for (int x = 0; x < P; ++x) {
                     double Sx = nan_d(), tpi = nan_d(), tw = nan_d(), tD = nan_d();
-                    if (Lp >= 1) {
+                    if (Lp >= 1 && fp.with_freq) {
                         const long long N = fp.popN[x];
                         const long long seg = (long long)((sums[3 + Pp + npp + x / 2] >> (32 * (x & 1))) & 0xffffffffull);
                         const long long pairs = (N * N * Lp - (long long)sums[3 + x]) / 2;   // sum over sites of sum_{a<b} c_a c_b
@@ -941,7 +947,8 @@ extern "C" int pg_popgen_device(pg_ctx* ctx, int32_t min_sites, double min_data,
         return PG_OK;
     }
     const int Pp = pad_pops(P);
-    const int Q = 3 + Pp + Pp * (Pp - 1) / 2 + (Pp + 1) / 2;
+    const bool wf = ctx->want_freq;
+    const int Q = 3 + Pp + Pp * (Pp - 1) / 2 + (wf ? (Pp + 1) / 2 : 0);
     K1Cache& c = *cache_of(ctx, 0);
     if (!c.valid || c.epoch != ctx->epoch) {
         c.valid = false;
@@ -955,9 +962,15 @@ extern "C" int pg_popgen_device(pg_ctx* ctx, int32_t min_sites, double min_data,
         c.valid = true;
     }
     PG_TRY(arm_slots(ctx, c));
-    if (Pp == 2) PG_TRY((launch_site_pass<MODE_POPGEN, 2>(ctx, c.L, "k1_popgen")));
-    else if (Pp == 4) PG_TRY((launch_site_pass<MODE_POPGEN, 4>(ctx, c.L, "k1_popgen")));
-    else PG_TRY((launch_site_pass<MODE_POPGEN, 8>(ctx, c.L, "k1_popgen")));
+    if (!wf) {
+        if (Pp == 2) PG_TRY((launch_site_pass<MODE_POPGEN, 2>(ctx, c.L, "k1_popgen")));
+        else if (Pp == 4) PG_TRY((launch_site_pass<MODE_POPGEN, 4>(ctx, c.L, "k1_popgen")));
+        else PG_TRY((launch_site_pass<MODE_POPGEN, 8>(ctx, c.L, "k1_popgen")));
+    } else {
+        if (Pp == 2) PG_TRY((launch_site_pass<MODE_POPGEN_FREQ, 2>(ctx, c.L, "k1_popgen")));
+        else if (Pp == 4) PG_TRY((launch_site_pass<MODE_POPGEN_FREQ, 4>(ctx, c.L, "k1_popgen")));
+        else PG_TRY((launch_site_pass<MODE_POPGEN_FREQ, 8>(ctx, c.L, "k1_popgen")));
+    }
 
     PG_TRY(ctx->out_i.ensure((size_t)W * 4 + 128));
     int* d_cnt = (int*)ctx->out_i.p;
@@ -970,6 +983,7 @@ extern "C" int pg_popgen_device(pg_ctx* ctx, int32_t min_sites, double min_data,
     fp.min_sites = min_sites;
     fp.min_data = min_data;
     fp.force_path = force_path;
+    fp.with_freq = wf ? 1 : 0;
     fp.rec = (unsigned long long*)d_rec;
     fp.RC = RC;
     fp.path = d_path;
@@ -1031,6 +1045,17 @@ extern "C" int pg_popgen(pg_ctx* ctx, int32_t min_sites, double min_data, int32_
     return PG_OK;
 }
 
+extern "C" int pg_set_freqstats(pg_ctx* ctx, int32_t enable) {
+    PG_CHECK(ctx != nullptr, "pg_set_freqstats: null ctx");
+    const bool e = enable != 0;
+    if (e != ctx->want_freq) {
+        ctx->want_freq = e;
+        ctx->epoch += 1;              // the slot layout of the site pass changes
+        ctx->h_rec.clear();
+    }
+    return PG_OK;
+}
+
 // popFreq columns of the records produced by the most recent pg_popgen on this ctx
 extern "C" int pg_popgen_freqstats(pg_ctx* ctx, double* l, double* S, double* theta_pi, double* theta_w, double* taj_d) {
     PG_CHECK(ctx && l && S && theta_pi && theta_w && taj_d, "pg_popgen_freqstats: null argument");
@@ -1038,6 +1063,7 @@ extern "C" int pg_popgen_freqstats(pg_ctx* ctx, double* l, double* S, double* th
     const int npairs = P * (P - 1) / 2;
     const int RC = 3 + P + 2 * npairs + 1 + 4 * P;
     const int64_t W = ctx->W;
+    PG_CHECK(ctx->want_freq, "pg_popgen_freqstats: enable the popFreq counters first (pg_set_freqstats(ctx, 1))");
     PG_CHECK(ctx->h_rec.size() == (size_t)W * RC, "pg_popgen_freqstats: call pg_popgen first (same pops / windows)");
     for (int64_t w = 0; w < W; ++w) {
         const double* f = reinterpret_cast<const double*>(ctx->h_rec.data() + (size_t)w * RC + 3 + P + 2 * npairs);

@@ -103,6 +103,7 @@ struct pg_ctx {
     cudaStream_t copy_stream = nullptr;
     PgBuf stage[2];
     cudaEvent_t stage_full[2] = {nullptr, nullptr}, stage_free[2] = {nullptr, nullptr};
+    bool want_freq = false;                   // carry the popFreq counters in the popgen site pass
     uint64_t epoch = 1;                       // bumped by every change of data shape / populations / windows
     void* k1_cache[2] = {nullptr, nullptr};   // cached launch state (popgen, abba) — owned by k1.cu
     std::vector<unsigned long long> h_rec;    // host copy of the per-window records

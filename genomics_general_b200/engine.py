@@ -122,6 +122,10 @@ class Engine:
         self.W = len(lo)
 
     # ---- statistics ----
+    def set_freqstats(self, enable: bool = True):
+        """Carry the popFreq counters (groupFreqStats) in the popgen site pass (opt-in: ~4 % of the pass)."""
+        check(self._lib.pg_set_freqstats(self._ctx, 1 if enable else 0), "pg_set_freqstats")
+
     def popgen(self, min_sites: int = 1, min_data: float = 0.01, force_pairwise: bool = False):
         """-> dict(pi [W,P], dxy [W,npairs], fst [W,npairs], sites [W], pos_sum [W], path [W])."""
         W, P = self.W, self.P

@@ -82,9 +82,11 @@ int pg_popgen_device(pg_ctx* ctx, int32_t min_sites, double min_data, int32_t fo
                      int64_t* n_pairwise);
 
 /* Replaces Alignment.groupFreqStats (genomics.py:1002-1028; popgenWindows --analysis popFreq): the columns
- * computed alongside by the most recent pg_popgen call on this ctx.  l [W] = sites complete in every haplotype
+ * computed alongside by the most recent pg_popgen call on this ctx (after pg_set_freqstats(ctx, 1)).  l [W] = sites complete in every haplotype
  * that belongs to a population; S, theta_pi, theta_w, taj_d [W x P]. */
 int pg_popgen_freqstats(pg_ctx* ctx, double* l, double* S, double* theta_pi, double* theta_w, double* taj_d);
+/* The popFreq counters cost ~4 % of the site pass, so they are opt-in: enable before pg_popgen. */
+int pg_set_freqstats(pg_ctx* ctx, int32_t enable);
 
 /* Replaces genomics.ABBABABA (genomics.py:1647-1695, polarize=True) per window.
  * out [W x 5] = ABBA, BABA, D, fd, fdM; sites_used [W] (double: nan when the window has no good site,
