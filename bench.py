@@ -143,9 +143,16 @@ def run_reference(args, rank, world):
         return
     import multiprocessing as mp
     cores = host_cores()
-    L = env_int("PG_BENCH_CPU_WINDOW_SITES", 5000)
     wins = cores
     with mp.get_context("fork").Pool(cores) as pool:
+        # bounded sample: calibrate with one 250-site window per core (all cores busy, like the real run), then size
+        # the windows so that the whole --steps/--warmup run takes about PG_BENCH_REF_SECONDS (default 150 s).
+        # The port's cost is ~linear in window length above ~250 sites, so sites/s barely depends on it.
+        L = env_int("PG_BENCH_CPU_WINDOW_SITES", 0)
+        if L <= 0:
+            _, t250 = cpu_sample(pool, cores, wins, 250, 0.0, SEED - 1)
+            budget = float(env_int("PG_BENCH_REF_SECONDS", 150)) / max(args.steps + max(args.warmup, 0), 1)
+            L = int(min(5000, max(250, 250 * budget / max(t250, 1e-3))))
         for _ in range(max(args.warmup, 0)):
             cpu_sample(pool, cores, wins, L, 0.0, SEED)
         t0 = time.perf_counter()

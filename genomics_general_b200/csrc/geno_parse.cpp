@@ -120,6 +120,9 @@ extern "C" int pg_geno_parse(const char* buf, size_t len, int32_t fmt, int32_t n
         }
         col_to_out[col_take[k]] = k;
     }
+    int uniform_ploidy = n_out > 0 ? ploidy[0] : 0;     // 0 = mixed
+    for (int k = 1; k < n_out; ++k)
+        if (ploidy[k] != uniform_ploidy) uniform_ploidy = 0;
     if (n_threads < 1) n_threads = 1;
     if ((int64_t)n_threads > n_lines) n_threads = (int)(n_lines > 0 ? n_lines : 1);
     std::atomic<int> failed(0);
@@ -168,6 +171,54 @@ extern "C" int pg_geno_parse(const char* buf, size_t len, int32_t fmt, int32_t n
             pos[l] = (int32_t)(neg ? -v : v);
             int8_t* grow = geno + (size_t)l * H_out;
             int col = 0, found = 0;
+            // fast path: every token has the same width and single-character separators (the normal layout of
+            // .geno files) -> address the requested columns directly instead of tokenising the whole line
+            {
+                const char* q = p;
+                while (q < e && is_ws(*q)) ++q;
+                const char* e2 = e;
+                while (e2 > q && is_ws(e2[-1])) --e2;
+                const int tokw = (fmt == 0) ? 3 : (fmt == 2 ? 2 : 1);
+                const long rem = (long)(e2 - q);
+                bool fast = uniform_ploidy == ((fmt == 0 || fmt == 1 || fmt == 2) ? 2 : 1) && rem > 0 && ((rem + 1) % (tokw + 1)) == 0;
+                if (fmt == 1 && uniform_ploidy == 1) fast = false;
+                long ncols = fast ? (rem + 1) / (tokw + 1) : 0;
+                if (fast && max_col >= ncols) fast = false;
+                if (fast) {
+                    const char* sp = q + tokw;
+                    for (long c2 = 0; c2 + 1 < ncols; ++c2, sp += tokw + 1)
+                        if (!is_ws(*sp)) {
+                            fast = false;
+                            break;
+                        }
+                }
+                if (fast && fmt == 0) {
+                    // a 3-character token must not contain whitespace either ("A|T")
+                    for (int k = 0; k < n_out && fast; ++k) {
+                        const char* t0 = q + (long)col_take[k] * 4;
+                        if (is_ws(t0[0]) || is_ws(t0[1]) || is_ws(t0[2])) fast = false;
+                    }
+                }
+                if (fast) {
+                    for (int k = 0; k < n_out; ++k) {
+                        const char* t0 = q + (long)col_take[k] * (tokw + 1);
+                        int8_t* o = grow + hap_off[k];
+                        if (fmt == 0) {
+                            o[0] = LUT.base[(unsigned char)t0[0]];
+                            o[1] = LUT.base[(unsigned char)t0[2]];
+                        } else if (fmt == 2) {
+                            o[0] = LUT.base[(unsigned char)t0[0]];
+                            o[1] = LUT.base[(unsigned char)t0[1]];
+                        } else if (fmt == 1) {
+                            o[0] = LUT.dip0[(unsigned char)t0[0]];
+                            o[1] = LUT.dip1[(unsigned char)t0[0]];
+                        } else {
+                            o[0] = LUT.base[(unsigned char)t0[0]];
+                        }
+                    }
+                    continue;
+                }
+            }
             while (p < e) {
                 while (p < e && is_ws(*p)) ++p;
                 if (p >= e) break;
