@@ -203,7 +203,7 @@ static int env_int(const char* name, int dflt) {
 // Tile geometry: 8 consumer warps per CTA are split into teams of `wpt` warps; one team owns one tile
 // (T consecutive sites) at a time, so up to 8/wpt tiles are being consumed while `stages` tiles sit in the
 // TMA ring.  G lanes share one site row when a row is too long for one lane's tile share.
-K1Plan pg_make_k1_plan(int64_t S, int H, int sm_count, int table_bytes) {
+K1Plan pg_make_k1_plan(int64_t S, int H, int sm_count, int table_bytes, int nw) {
     K1Plan p;
     memset(&p, 0, sizeof(p));
     p.pitch = pg_pitch_for(H);
@@ -214,10 +214,11 @@ K1Plan pg_make_k1_plan(int64_t S, int H, int sm_count, int table_bytes) {
     // lanes per site: keep one lane's walk below ~64 chunks (measured: 1600-haplotype rows run 20 % faster with G = 2),
     // and a 32/G-site slab inside the tile target
     while (G < 32 && (p.chunks / G > 64 || (32 / G) * p.pitch > tile_target)) G *= 2;
-    // warps per tile: the largest team whose tile still fits the target
-    while (wpt < 8 && (32 * (wpt * 2) / G) * p.pitch <= tile_target) wpt *= 2;
-    if (wpt == 8 && G == 1) {
-        I = tile_target / (256 * p.pitch);
+    // warps per tile: the largest team (dividing the consumer-warp count) whose tile still fits the target
+    const int wpt_max = (nw % 8 == 0) ? 8 : 4;
+    while (wpt < wpt_max && (32 * (wpt * 2) / G) * p.pitch <= tile_target) wpt *= 2;
+    if (wpt == wpt_max && G == 1) {
+        I = tile_target / (32 * wpt * p.pitch);
         if (I < 1) I = 1;
         if (I > 8) I = 8;
     }
@@ -227,6 +228,7 @@ K1Plan pg_make_k1_plan(int64_t S, int H, int sm_count, int table_bytes) {
     p.G = G;
     p.I = I;
     p.wpt = wpt;
+    p.nw = nw;
     p.T = (32 * wpt / G) * I;
     p.tile_bytes = ((p.T * p.pitch + p.T * 4 + 127) / 128) * 128;   // genotype rows + the tile's positions
     int stages = smem_cap / p.tile_bytes;

@@ -12,6 +12,8 @@
 // site row and walks it with conflict-free LDS.128; alleles are counted with SWAR byte-lane accumulators
 // (8 integer ops per 4 genotypes).  Per-lane running sums are flushed per (warp, segment) into private
 // slots — no atomics, deterministic — and a finalize kernel folds slots -> segments -> windows -> statistics.
+#include <stdlib.h>
+
 #include <algorithm>
 #include <cmath>
 
@@ -19,8 +21,8 @@
 
 namespace {
 
-constexpr int K1_WARPS = 8;                       // consumer warps per CTA
-constexpr int K1_THREADS = (K1_WARPS + 1) * 32;   // + one TMA producer warp
+// consumer warps per CTA (+ one TMA producer warp): 8, or 12 where the register budget allows (65536 / 13 / 32 = 157)
+constexpr int K1_MAX_WARPS = 12;
 
 enum { MODE_POPGEN = 0, MODE_ABBA = 1, MODE_COUNTS = 2, MODE_POPGEN_FREQ = 3 };   // FREQ = POPGEN + popFreq counters
 
@@ -29,7 +31,7 @@ struct K1Params {
     const int32_t* pos;
     int64_t site_begin, site_end;     // sites processed by this launch
     int64_t num_tiles;
-    int pitch, G, I, T, wpt, stages, tile_bytes;
+    int pitch, G, I, T, wpt, stages, tile_bytes, nw;
     // hap -> pop tables (shared-memory copies are made at kernel start)
     const int32_t* ent_chunk;
     const uint4* ent_mask;
@@ -152,14 +154,14 @@ struct Acc {
 // Warp-cooperative flush of the per-lane running sums into this warp's private slots.
 template <int QI, int QD>
 __device__ __forceinline__ void warp_flush(Acc<QI, QD>& acc, int cur_seg, unsigned long long* part, int64_t slot_base,
-                                           int seg_first, int warp, int lane) {
+                                           int seg_first, int warp, int lane, int nw) {
     constexpr int Q = QI + QD;
     unsigned pending = __ballot_sync(0xffffffffu, cur_seg >= 0);
     while (pending) {
         const int leader = __ffs(pending) - 1;
         const int g = __shfl_sync(0xffffffffu, cur_seg, leader);
         const bool mine = (cur_seg == g);
-        unsigned long long* dst = part + slot_base + ((int64_t)(g - seg_first) * K1_WARPS + warp) * Q;
+        unsigned long long* dst = part + slot_base + ((int64_t)(g - seg_first) * nw + warp) * Q;
 #pragma unroll
         for (int q = 0; q < QI; ++q) {
             long long v = mine ? acc.i[q] : 0ll;
@@ -208,8 +210,9 @@ struct ModeTraits<MODE_COUNTS, P> {
     static constexpr int QI = 0, QD = 0;
 };
 
-template <int MODE, int P>
-__global__ void __launch_bounds__(K1_THREADS, 1) k1_site_pass(const __grid_constant__ K1Params prm) {
+template <int MODE, int P, int NW>
+__global__ void __launch_bounds__((NW + 1) * 32, 1) k1_site_pass(const __grid_constant__ K1Params prm) {
+    constexpr int K1_THREADS = (NW + 1) * 32;
     constexpr int QI = ModeTraits<MODE, P>::QI, QD = ModeTraits<MODE, P>::QD;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* tiles = smem;
@@ -239,7 +242,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_site_pass(const __grid_const
     }
     __syncthreads();
 
-    if (warp == K1_WARPS) {
+    if (warp == NW) {
         // ---------------- TMA producer: one elected lane keeps the ring full ----------------
         if (lane == 0) {
             for (int it = 0; it < ntiles; ++it) {
@@ -273,7 +276,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_site_pass(const __grid_const
     const int spw = 32 / G;              // sites per warp per iteration
     const int gsub = lane / spw;         // which part of the row this lane walks
     const int sl = lane % spw;
-    const int nteams = K1_WARPS / prm.wpt;
+    const int nteams = NW / prm.wpt;
     const int team = warp / prm.wpt, lw = warp % prm.wpt;
     const int sites_per_iter = prm.wpt * spw;
 
@@ -358,7 +361,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_site_pass(const __grid_const
             int sg = cur_seg;
             if (owner && site >= seg_end) sg = find_seg(prm.brk, prm.nseg, cur_seg + 1, site);
             if (__any_sync(0xffffffffu, sg != cur_seg)) {
-                warp_flush<QI, QD>(acc, cur_seg, prm.part, slot_base, seg_first, warp, lane);
+                warp_flush<QI, QD>(acc, cur_seg, prm.part, slot_base, seg_first, warp, lane, NW);
                 if (sg != cur_seg) {
                     cur_seg = sg;
                     seg_end = __ldg(prm.brk + sg + 1);
@@ -453,7 +456,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_site_pass(const __grid_const
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[stage]);   // this warp is done with the stage's bytes
     }
-    if (MODE != MODE_COUNTS) warp_flush<QI, QD>(acc, cur_seg, prm.part, slot_base, seg_first, warp, lane);
+    if (MODE != MODE_COUNTS) warp_flush<QI, QD>(acc, cur_seg, prm.part, slot_base, seg_first, warp, lane, NW);
 }
 
 // ---- finalize: slots -> segments -> windows -> statistics ------------------------------------------
@@ -468,7 +471,7 @@ struct FinParams {
     const int64_t* win_lo;
     const int64_t* win_hi;
     int64_t W;
-    int Q, QI;
+    int Q, QI, nw;
     int P;                         // real population count
     int Ppad;                      // template P used by the site pass
     int popN[PG_MAX_K1_POPS];
@@ -514,8 +517,8 @@ __global__ void __launch_bounds__(64) k1_finalize(const __grid_constant__ FinPar
             for (int g = fp.win_seg_lo[w]; g < fp.win_seg_hi[w]; ++g) {
                 for (int b = fp.seg_cta_lo[g]; b <= fp.seg_cta_hi[g]; ++b) {
                     const unsigned long long* src =
-                        fp.part + fp.cta_slot_off[b] + (int64_t)(g - fp.cta_seg_first[b]) * K1_WARPS * fp.Q;
-                    for (int wp = 0; wp < K1_WARPS; ++wp) {
+                        fp.part + fp.cta_slot_off[b] + (int64_t)(g - fp.cta_seg_first[b]) * fp.nw * fp.Q;
+                    for (int wp = 0; wp < fp.nw; ++wp) {
                         const unsigned long long v = src[wp * fp.Q + q];
                         if (q < fp.QI) si += (long long)v; else sd += __longlong_as_double((long long)v);
                     }
@@ -684,7 +687,7 @@ void build_tables(const std::vector<int32_t>& hap_pop_local, int H, int chunks, 
 
 int check_plan(const K1Plan& pl) {
     const bool pow2G = pl.G >= 1 && pl.G <= 32 && (pl.G & (pl.G - 1)) == 0;
-    const bool okw = pl.wpt == 1 || pl.wpt == 2 || pl.wpt == 4 || pl.wpt == 8;
+    const bool okw = (pl.wpt == 1 || pl.wpt == 2 || pl.wpt == 4 || pl.wpt == 8) && (pl.nw % pl.wpt) == 0;
     PG_CHECK((pl.T % 4) == 0, "rows of %d bytes are too long for the site-pass kernel", pl.pitch);
     PG_CHECK(pow2G && okw && pl.I >= 1 && pl.stages >= 2 && pl.stages <= 8 && pl.smem_bytes <= 227 * 1024,
              "invalid site-pass geometry G=%d wpt=%d I=%d stages=%d smem=%d", pl.G, pl.wpt, pl.I, pl.stages, pl.smem_bytes);
@@ -745,7 +748,7 @@ struct K1Cache {
     PgBuf tables;
 };
 
-int prepare_windowed(pg_ctx* ctx, K1Cache& c, const std::vector<int32_t>& hap_pop_local, int Ppad, int Q) {
+int prepare_windowed(pg_ctx* ctx, K1Cache& c, const std::vector<int32_t>& hap_pop_local, int Ppad, int Q, int nw) {
     K1Launch& L = c.L;
     DevTables& dt = c.dt;
     PopTables& pt = c.pt;
@@ -754,7 +757,7 @@ int prepare_windowed(pg_ctx* ctx, K1Cache& c, const std::vector<int32_t>& hap_po
     const int n_ent = (int)pt.ent_chunk.size();
     const int table_bytes = n_ent * 20 + 64;
     PG_CHECK(table_bytes <= 48 * 1024, "population layout needs %d bytes of mask tables (limit 48 KiB)", table_bytes);
-    L.plan = pg_make_k1_plan(ctx->S, ctx->H, ctx->sm_count, table_bytes);
+    L.plan = pg_make_k1_plan(ctx->S, ctx->H, ctx->sm_count, table_bytes, nw);
     PG_CHECK(L.plan.stages >= 2, "rows of %d haplotypes are too long for the site-pass kernel (pitch %d bytes)", ctx->H,
              L.plan.pitch);
     PG_TRY(check_plan(L.plan));
@@ -776,7 +779,7 @@ int prepare_windowed(pg_ctx* ctx, K1Cache& c, const std::vector<int32_t>& hap_po
         const int g0 = seg_of(ctx->brk, s0), g1 = seg_of(ctx->brk, s1 - 1);
         L.cta_seg_first[b] = g0;
         cta_seg_last[b] = g1;
-        off += (int64_t)(g1 - g0 + 1) * K1_WARPS * Q;
+        off += (int64_t)(g1 - g0 + 1) * nw * Q;
     }
     L.total_slots = off;
     for (int g = 0; g < nseg; ++g) {
@@ -824,6 +827,7 @@ int prepare_windowed(pg_ctx* ctx, K1Cache& c, const std::vector<int32_t>& hap_po
     p.I = pl.I;
     p.T = pl.T;
     p.wpt = pl.wpt;
+    p.nw = nw;
     p.stages = pl.stages;
     p.tile_bytes = pl.tile_bytes;
     p.ent_chunk = dt.ent_chunk;
@@ -854,19 +858,40 @@ int arm_slots(pg_ctx* ctx, K1Cache& c) {
     return PG_OK;
 }
 
-template <int MODE, int P>
-int launch_site_pass(pg_ctx* ctx, const K1Launch& L, const char* name) {
-    auto kern = k1_site_pass<MODE, P>;
+template <int MODE, int P, int NW>
+int launch_site_pass_nw(pg_ctx* ctx, const K1Launch& L, const char* name) {
+    auto kern = k1_site_pass<MODE, P, NW>;
     static bool attr_set = false;     // per instantiation
     if (!attr_set) {
         PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
     const int ti = pg_time_begin(ctx, name);
-    kern<<<L.plan.ctas, K1_THREADS, L.plan.smem_bytes, ctx->stream>>>(L.prm);
+    kern<<<L.plan.ctas, (NW + 1) * 32, L.plan.smem_bytes, ctx->stream>>>(L.prm);
     pg_time_end(ctx, ti);
     PG_CUDA(cudaGetLastError());
     return PG_OK;
+}
+
+// consumer-warp count per instantiation: 12 where ptxas needs <= 152 registers, else 8
+template <int MODE, int P>
+constexpr int warps_for() {
+    return (P == 8 && (MODE == MODE_POPGEN || MODE == MODE_POPGEN_FREQ)) ? 8 : 12;
+}
+int k1_env_nw(int dflt) {
+    const char* e = getenv("PG_K1_NW");
+    const int v = (e && *e) ? atoi(e) : dflt;
+    return (v == 12 && dflt == 12) ? 12 : 8;
+}
+template <int MODE, int P>
+int nw_for() { return k1_env_nw(warps_for<MODE, P>()); }
+
+template <int MODE, int P>
+int launch_site_pass(pg_ctx* ctx, const K1Launch& L, const char* name) {
+    if (L.prm.nw == 12) {
+        if constexpr (warps_for<MODE, P>() == 12) return launch_site_pass_nw<MODE, P, 12>(ctx, L, name);
+    }
+    return launch_site_pass_nw<MODE, P, 8>(ctx, L, name);
 }
 
 int pad_pops(int P) { return P <= 2 ? 2 : (P <= 4 ? 4 : 8); }
@@ -890,6 +915,7 @@ void fill_fin(FinParams& fp, pg_ctx* ctx, const K1Cache& c, int Q, int QI) {
     fp.W = ctx->W;
     fp.Q = Q;
     fp.QI = QI;
+    fp.nw = c.L.prm.nw;
     for (int X = 0; X < PG_MAX_K1_POPS; ++X) {
         fp.popN[X] = c.pt.popN[X];
         double a = 0.0, a2 = 0.0;                       // TajimaD's python sums (genomics.py:621-623), same order
@@ -957,7 +983,9 @@ extern "C" int pg_popgen_device(pg_ctx* ctx, int32_t min_sites, double min_data,
             for (int h = 0; h < ctx->H; ++h) N += ctx->hap_pop[h] == x;
             PG_CHECK(N >= 1, "pg_popgen: population %d has no haplotypes", x);
         }
-        PG_TRY(prepare_windowed(ctx, c, ctx->hap_pop, Pp, Q));
+        const int nw = wf ? (Pp == 2 ? nw_for<MODE_POPGEN_FREQ, 2>() : (Pp == 4 ? nw_for<MODE_POPGEN_FREQ, 4>() : nw_for<MODE_POPGEN_FREQ, 8>()))
+                          : (Pp == 2 ? nw_for<MODE_POPGEN, 2>() : (Pp == 4 ? nw_for<MODE_POPGEN, 4>() : nw_for<MODE_POPGEN, 8>()));
+        PG_TRY(prepare_windowed(ctx, c, ctx->hap_pop, Pp, Q, nw));
         c.epoch = ctx->epoch;
         c.valid = true;
     }
@@ -1109,7 +1137,7 @@ extern "C" int pg_abbababa(pg_ctx* ctx, int32_t p1, int32_t p2, int32_t p3, int3
         for (int h = 0; h < ctx->H; ++h)
             for (int k = 0; k < 4; ++k)
                 if (ctx->hap_pop[h] == sel[k]) local[h] = k;
-        PG_TRY(prepare_windowed(ctx, c, local, 4, Q));
+        PG_TRY(prepare_windowed(ctx, c, local, 4, Q, nw_for<MODE_ABBA, 4>()));
         for (int k = 0; k < 4; ++k) PG_CHECK(c.pt.popN[k] >= 1, "pg_abbababa: population %d has no haplotypes", sel[k]);
         memcpy(c.sel, sel, sizeof(sel));
         c.epoch = ctx->epoch;
@@ -1181,7 +1209,8 @@ extern "C" int pg_site_counts(pg_ctx* ctx, int64_t site0, int64_t n, uint16_t* c
             const int table_bytes = n_ent * 20 + 64;
             PG_CHECK(table_bytes <= 48 * 1024, "population layout needs too many mask entries");
             K1Launch L;
-            L.plan = pg_make_k1_plan(cnt, ctx->H, ctx->sm_count, table_bytes);
+            const int nw = Pp == 2 ? nw_for<MODE_COUNTS, 2>() : (Pp == 4 ? nw_for<MODE_COUNTS, 4>() : nw_for<MODE_COUNTS, 8>());
+            L.plan = pg_make_k1_plan(cnt, ctx->H, ctx->sm_count, table_bytes, nw);
             PG_CHECK(L.plan.stages >= 2, "rows of %d haplotypes are too long for the site-pass kernel", ctx->H);
             PG_TRY(check_plan(L.plan));
             PG_TRY(ctx->tables.ensure((size_t)n_ent * 20 + 4096));
@@ -1203,6 +1232,7 @@ extern "C" int pg_site_counts(pg_ctx* ctx, int64_t site0, int64_t n, uint16_t* c
             p.I = L.plan.I;
             p.T = L.plan.T;
             p.wpt = L.plan.wpt;
+            p.nw = nw;
             p.stages = L.plan.stages;
             p.tile_bytes = L.plan.tile_bytes;
             p.ent_chunk = d_chunk;

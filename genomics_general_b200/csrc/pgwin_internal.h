@@ -62,7 +62,8 @@ struct K1Plan {
     int chunks;       // 16-byte chunks per row
     int G;            // lanes cooperating on one site (power of two, <= 32)
     int I;            // sites per lane per tile
-    int wpt;          // consumer warps per tile (a "team"); 8 / wpt teams work on different tiles
+    int wpt;          // consumer warps per tile (a "team"); nw / wpt teams work on different tiles
+    int nw;           // consumer warps per CTA (8 or 12)
     int T;            // sites per tile = (32 * wpt / G) * I
     int stages;       // TMA ring depth
     int tile_bytes;   // T * pitch
@@ -70,7 +71,7 @@ struct K1Plan {
     int64_t num_tiles;
     int ctas;         // persistent CTAs, each owning a contiguous tile range
 };
-K1Plan pg_make_k1_plan(int64_t S, int H, int sm_count, int table_bytes);
+K1Plan pg_make_k1_plan(int64_t S, int H, int sm_count, int table_bytes, int nw = 8);
 int pg_pitch_for(int H);
 
 struct pg_ctx {
