@@ -876,15 +876,19 @@ int launch_site_pass_nw(pg_ctx* ctx, const K1Launch& L, const char* name) {
 // consumer-warp count per instantiation: 12 where ptxas needs <= 152 registers, else 8
 template <int MODE, int P>
 constexpr int warps_for() {
+    return 12;
+}
+template <int MODE, int P>
+constexpr int default_warps() {
     return (P == 8 && (MODE == MODE_POPGEN || MODE == MODE_POPGEN_FREQ)) ? 8 : 12;
 }
 int k1_env_nw(int dflt) {
     const char* e = getenv("PG_K1_NW");
     const int v = (e && *e) ? atoi(e) : dflt;
-    return (v == 12 && dflt == 12) ? 12 : 8;
+    return v == 12 ? 12 : 8;
 }
 template <int MODE, int P>
-int nw_for() { return k1_env_nw(warps_for<MODE, P>()); }
+int nw_for() { return k1_env_nw(default_warps<MODE, P>()); }
 
 template <int MODE, int P>
 int launch_site_pass(pg_ctx* ctx, const K1Launch& L, const char* name) {
@@ -1055,12 +1059,16 @@ extern "C" int pg_popgen(pg_ctx* ctx, int32_t min_sites, double min_data, int32_
     PG_CUDA(cudaSetDevice(ctx->device));
     PG_TRY(ctx->out_d.ensure((size_t)W * RC * 8 + 64));
     PG_TRY(pg_popgen_device(ctx, min_sites, min_data, force_path, ctx->out_d.p, nullptr));
-    std::vector<unsigned long long>& h = ctx->h_rec;
-    h.resize((size_t)W * RC);
-    PG_CUDA(cudaMemcpyAsync(h.data(), ctx->out_d.p, h.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    // one D2H of the record table into pinned staging (a pageable destination would be a synchronous staged copy)
+    void* hp = nullptr;
+    PG_TRY(pg_pinned(ctx, (size_t)W * RC * 8 + 64, &hp));
+    const unsigned long long* hrec = (const unsigned long long*)hp;
+    PG_CUDA(cudaMemcpyAsync(hp, ctx->out_d.p, (size_t)W * RC * 8, cudaMemcpyDeviceToHost, ctx->stream));
     PG_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->want_freq) ctx->h_rec.assign(hrec, hrec + (size_t)W * RC);     // kept for pg_popgen_freqstats
+    else ctx->h_rec.clear();
     for (int64_t w = 0; w < W; ++w) {
-        const unsigned long long* r = h.data() + (size_t)w * RC;
+        const unsigned long long* r = hrec + (size_t)w * RC;
         n_sites[w] = (int64_t)r[0];
         pos_sum[w] = (int64_t)r[1];
         path[w] = (int32_t)r[2];
@@ -1166,12 +1174,13 @@ extern "C" int pg_abbababa(pg_ctx* ctx, int32_t p1, int32_t p2, int32_t p3, int3
     k1_finalize<MODE_ABBA><<<(unsigned)std::min<int64_t>(W, 65535), 64, 0, ctx->stream>>>(fp);
     pg_time_end(ctx, ti);
     PG_CUDA(cudaGetLastError());
-    std::vector<unsigned long long>& h = ctx->h_rec;
-    h.resize((size_t)W * RC);
-    PG_CUDA(cudaMemcpyAsync(h.data(), ctx->out_d.p, h.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    void* hp = nullptr;
+    PG_TRY(pg_pinned(ctx, (size_t)W * RC * 8 + 64, &hp));
+    const unsigned long long* hrec = (const unsigned long long*)hp;
+    PG_CUDA(cudaMemcpyAsync(hp, ctx->out_d.p, (size_t)W * RC * 8, cudaMemcpyDeviceToHost, ctx->stream));
     PG_CUDA(cudaStreamSynchronize(ctx->stream));
     for (int64_t w = 0; w < W; ++w) {
-        const unsigned long long* r = h.data() + (size_t)w * RC;
+        const unsigned long long* r = hrec + (size_t)w * RC;
         n_sites[w] = (int64_t)r[0];
         pos_sum[w] = (int64_t)r[1];
         memcpy(out + (size_t)w * 5, r + 2, 40);
