@@ -286,13 +286,14 @@ def main():
         ws = windows.sliding_coord_windows(np.zeros(S, dtype=np.int32), ["chr1"], pos, WIND_SIZE)
         return ws.ranges()
 
-    gatherer = None
+    gather_table = None
+    w_max = 0
 
     def step_resident():
         if dist is not None:
-            # records stay on the device: statistics kernel -> NCCL all-gather -> one D2H of the table
-            eng.popgen_device(gatherer.local.data_ptr(), MIN_SITES, MIN_DATA)
-            return gatherer.gather()
+            # one C-ABI call: site pass -> finalize -> ncclAllGather (native, same stream, in place) -> D2H of the table
+            eng.popgen_allgather(w_max, gather_table.array, MIN_SITES, MIN_DATA)
+            return gather_table.array
         return eng.popgen(MIN_SITES, MIN_DATA)
 
     def timed(fn, steps, warmup):
@@ -325,7 +326,14 @@ def main():
         allc = [torch.zeros_like(cnt) for _ in range(world)]
         dist.all_gather(allc, cnt)
         counts = [int(c.item()) for c in allc]
-        gatherer = multigpu.DeviceGather(counts, eng.popgen_record_width(), dev)
+        w_max = max(max(counts), 1)
+        # NCCL communicator of the engine itself: rank 0 creates the id, torch.distributed only carries it
+        id_t = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            id_t.copy_(torch.frombuffer(bytearray(eng.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(id_t, 0)
+        eng.nccl_init(world, rank, bytes(id_t.cpu().numpy().tobytes()))
+        gather_table = PinnedArray((world * w_max, eng.popgen_record_width()), np.float64)
     dt, tms, launches = timed(step_resident, args.steps, args.warmup)
     value = world * S * args.steps / dt
     k1_ms = float(np.mean([t["k1_popgen"]["ms"] for t in tms if "k1_popgen" in t]))

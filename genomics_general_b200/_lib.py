@@ -66,6 +66,11 @@ _SIGS = {
     "pg_last_timings": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]),
     "pg_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "pg_debug_k1_plan": (C.c_int, [C.c_int64, C.c_int32] + [C.POINTER(C.c_int32)] * 5),
+    "pg_nccl_unique_id": (C.c_int, [C.c_void_p]),
+    "pg_nccl_init": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "pg_nccl_finalize": (C.c_int, [C.c_void_p]),
+    "pg_popgen_allgather": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_int32, C.c_int64, C.c_void_p,
+                                      C.POINTER(C.c_int64)]),
     "pg_geno_count_lines": (C.c_int, [C.c_char_p, C.c_size_t, C.POINTER(C.c_int64)]),
     "pg_geno_parse": (C.c_int, [C.c_char_p, C.c_size_t, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                 C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),

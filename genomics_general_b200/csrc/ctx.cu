@@ -70,6 +70,8 @@ extern "C" int pg_ctx_destroy(pg_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     pg_k1_cache_free(ctx);
+    pg_nccl_finalize(ctx);
+    ctx->gather.release();
     if (ctx->d_geno) cudaFree(ctx->d_geno);
     if (ctx->d_pos) cudaFree(ctx->d_pos);
     PgBuf* bufs[] = {&ctx->tables, &ctx->part, &ctx->segmeta, &ctx->winmeta, &ctx->out_d, &ctx->out_i,

@@ -947,16 +947,16 @@ void pg_k1_cache_free(pg_ctx* ctx) {
 // ================================================================================================
 // pg_popgen
 // ================================================================================================
-// Device-record variant: d_rec is a DEVICE buffer of W * (3 + P + 2*npairs) 8-byte words.
-extern "C" int pg_popgen_device(pg_ctx* ctx, int32_t min_sites, double min_data, int32_t force_path, void* d_rec,
-                                int64_t* n_pairwise) {
-    PG_CHECK(ctx && d_rec, "pg_popgen_device: null argument");
+// Enqueue the site pass + finalize on the ctx stream WITHOUT synchronising; *h_count (pinned) holds the number of
+// windows routed to the pairwise path once the stream has been synchronised (nullptr when nothing was launched).
+int pg_popgen_enqueue(pg_ctx* ctx, int32_t min_sites, double min_data, int32_t force_path, void* d_rec, int** h_count) {
+    PG_CHECK(ctx && d_rec && h_count, "pg_popgen_device: null argument");
+    *h_count = nullptr;
     PG_CHECK(ctx->P >= 1, "pg_popgen: call pg_set_pops first");
     PG_CHECK(force_path == 0 || force_path == 2, "pg_popgen: force_path must be 0 or 2");
     PG_CHECK(ctx->P <= PG_MAX_K1_POPS, "pg_popgen: P=%d > %d populations is not supported yet", ctx->P, PG_MAX_K1_POPS);
     PG_CUDA(cudaSetDevice(ctx->device));
     pg_timings_reset(ctx);
-    if (n_pairwise) *n_pairwise = 0;
     const int P = ctx->P;
     const int npairs = P * (P - 1) / 2;
     const int RC = 3 + P + 2 * npairs + 1 + 4 * P;
@@ -1027,22 +1027,42 @@ extern "C" int pg_popgen_device(pg_ctx* ctx, int32_t min_sites, double min_data,
     void* hp = nullptr;
     PG_TRY(pg_pinned(ctx, (size_t)W * 4 + 256, &hp));
     int* h_cnt = (int*)hp;
+    *h_cnt = 0;
     PG_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    PG_CUDA(cudaStreamSynchronize(ctx->stream));
-    const int nk2 = *h_cnt;
-    if (n_pairwise) *n_pairwise = nk2;
-    if (nk2 > 0) {
-        int32_t* h_path = (int32_t*)hp + 16;
-        PG_CUDA(cudaMemcpyAsync(h_path, d_path, (size_t)W * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        PG_CUDA(cudaStreamSynchronize(ctx->stream));
-        std::vector<int64_t> k2_windows;
-        k2_windows.reserve((size_t)nk2);
-        for (int64_t w = 0; w < W; ++w)
-            if (h_path[w] == 2) k2_windows.push_back(w);
-        PG_TRY(pg_k2_popgen_windows(ctx, k2_windows, min_sites, min_data, d_rec, RC));
-    }
+    *h_count = h_cnt;
     return PG_OK;
 }
+
+// After the stream has been synchronised: run the pairwise path for the windows the finalize kernel routed to it
+// (their rows of d_rec are overwritten in place).
+int pg_popgen_resolve(pg_ctx* ctx, int32_t min_sites, double min_data, void* d_rec, int nk2) {
+    if (nk2 <= 0) return PG_OK;
+    const int P = ctx->P;
+    const int RC = 3 + P + 2 * (P * (P - 1) / 2) + 1 + 4 * P;
+    const int64_t W = ctx->W;
+    const int32_t* d_path = (const int32_t*)ctx->out_i.p + 16;
+    std::vector<int32_t> h_path((size_t)W);
+    PG_CUDA(cudaMemcpyAsync(h_path.data(), d_path, (size_t)W * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PG_CUDA(cudaStreamSynchronize(ctx->stream));
+    std::vector<int64_t> k2_windows;
+    k2_windows.reserve((size_t)nk2);
+    for (int64_t w = 0; w < W; ++w)
+        if (h_path[w] == 2) k2_windows.push_back(w);
+    return pg_k2_popgen_windows(ctx, k2_windows, min_sites, min_data, d_rec, RC);
+}
+
+// Device-record variant: d_rec is a DEVICE buffer of W * (4 + 5P + 2*npairs) 8-byte words.
+extern "C" int pg_popgen_device(pg_ctx* ctx, int32_t min_sites, double min_data, int32_t force_path, void* d_rec,
+                                int64_t* n_pairwise) {
+    if (n_pairwise) *n_pairwise = 0;
+    int* h_cnt = nullptr;
+    PG_TRY(pg_popgen_enqueue(ctx, min_sites, min_data, force_path, d_rec, &h_cnt));
+    PG_CUDA(cudaStreamSynchronize(ctx->stream));
+    const int nk2 = h_cnt ? *h_cnt : 0;
+    if (n_pairwise) *n_pairwise = nk2;
+    return pg_popgen_resolve(ctx, min_sites, min_data, d_rec, nk2);
+}
+
 
 extern "C" int pg_popgen(pg_ctx* ctx, int32_t min_sites, double min_data, int32_t force_path, double* pi, double* dxy,
                          double* fst, int64_t* n_sites, int64_t* pos_sum, int32_t* path) {

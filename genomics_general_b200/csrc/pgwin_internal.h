@@ -108,6 +108,11 @@ struct pg_ctx {
     uint64_t epoch = 1;                       // bumped by every change of data shape / populations / windows
     void* k1_cache[2] = {nullptr, nullptr};   // cached launch state (popgen, abba) — owned by k1.cu
     std::vector<unsigned long long> h_rec;    // host copy of the per-window records
+    // native NCCL gather (nccl_gather.cu)
+    void* nccl_comm = nullptr;
+    int nccl_ranks = 1, nccl_rank = 0;
+    PgBuf gather;
+    size_t gather_words = 0;
     void* h_pinned = nullptr;                 // small pinned staging for result read-back
     size_t h_pinned_cap = 0;
 };
@@ -124,3 +129,5 @@ int pg_build_segments(pg_ctx* ctx);
 int pg_k2_popgen_windows(pg_ctx* ctx, const std::vector<int64_t>& wins, int32_t min_sites, double min_data,
                          void* d_rec, int RC);
 void pg_k1_cache_free(pg_ctx* ctx);
+int pg_popgen_enqueue(pg_ctx* ctx, int32_t min_sites, double min_data, int32_t force_path, void* d_rec, int** h_count);
+int pg_popgen_resolve(pg_ctx* ctx, int32_t min_sites, double min_data, void* d_rec, int nk2);

@@ -165,6 +165,30 @@ class Engine:
               "pg_popgen_device")
         return int(n.value)
 
+    # ---- multi-GPU: native NCCL gather (one process per GPU) ----
+    def nccl_unique_id(self) -> bytes:
+        buf = (C.c_uint8 * 128)()
+        check(self._lib.pg_nccl_unique_id(buf), "pg_nccl_unique_id")
+        return bytes(buf)
+
+    def nccl_init(self, world: int, rank: int, unique_id: bytes):
+        assert len(unique_id) == 128
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        check(self._lib.pg_nccl_init(self._ctx, int(world), int(rank), buf), "pg_nccl_init")
+        self._world, self._rank = int(world), int(rank)
+
+    def popgen_allgather(self, w_max: int, table: np.ndarray, min_sites: int = 1, min_data: float = 0.01,
+                         force_pairwise: bool = False) -> int:
+        """Statistics of this rank's windows, then ONE ncclAllGather of every rank's records into `table`
+        (float64 [world * w_max, popgen_record_width()], ideally pinned).  Returns this rank's pairwise-window count."""
+        assert table.dtype == np.float64 and table.flags.c_contiguous
+        assert table.shape == (self._world * int(w_max), self.popgen_record_width())
+        n = C.c_int64(0)
+        check(self._lib.pg_popgen_allgather(self._ctx, int(min_sites) if min_sites else 0, float(min_data),
+                                            2 if force_pairwise else 0, int(w_max), _ptr(table), C.byref(n)),
+              "pg_popgen_allgather")
+        return int(n.value)
+
     def abbababa(self, p1: int, p2: int, p3: int, o: int, min_data: float = 0.01):
         """-> dict(ABBA,BABA,D,fd,fdM [W], sitesUsed [W] (nan = no good site), sites, pos_sum)."""
         W = self.W

@@ -107,6 +107,19 @@ int pg_pairdist(pg_ctx* ctx, int32_t n_ind, const int32_t* hap_ind, int32_t incl
  * diff, n int32 [H x H] (symmetric, diagonal: diff 0, n = non-missing sites of the haplotype). */
 int pg_pair_counts(pg_ctx* ctx, int64_t window, int32_t* diff, int32_t* n);
 
+/* ---- multi-GPU: native NCCL all-gather of the per-window records -------------------------------- */
+/* One process per GPU.  Windows shard across ranks with no data-path collective; the only exchange is ONE
+ * ncclAllGather of the fixed-width records, enqueued on the ctx stream right behind the statistics kernels.
+ * NCCL is bound at run time (dlopen): rank 0 creates the 128-byte id, the host distributes it by any means
+ * (bench.py uses torch.distributed's broadcast), every rank calls pg_nccl_init.
+ * pg_popgen_allgather: h_table (host) receives nranks * w_max * (4 + 5P + 2*npairs) 8-byte words in rank order
+ * (record layout of pg_popgen_device; rows past a rank's own window count are zero); w_max >= every rank's W. */
+int pg_nccl_unique_id(void* id128);
+int pg_nccl_init(pg_ctx* ctx, int32_t nranks, int32_t rank, const void* id128);
+int pg_nccl_finalize(pg_ctx* ctx);
+int pg_popgen_allgather(pg_ctx* ctx, int32_t min_sites, double min_data, int32_t force_path, int64_t w_max,
+                        void* h_table, int64_t* n_pairwise);
+
 /* ---- host-side .geno text ingest (no CUDA) ------------------------------------------------------ */
 /* Replaces parseGenoLine/GenoFileReader (genomics.py:1884-1945) + splitSeq/haplo/forceHomo (390-396, 27, 407)
  * + seqArrayToNumArray (74-77) for a whole file: `buf` holds complete data lines (no header line);

@@ -1,0 +1,65 @@
+"""2-GPU worker for tests/test_gpu_multi.py: native NCCL gather through the C-ABI vs single-GPU results."""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from genomics_general_b200 import multigpu, synth  # noqa: E402
+from genomics_general_b200.engine import Engine, PinnedArray  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group(backend="nccl", device_id=dev)
+    eng = Engine(local)
+    id_t = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        id_t.copy_(torch.frombuffer(bytearray(eng.nccl_unique_id()), dtype=torch.uint8))
+    dist.broadcast(id_t, 0)
+    eng.nccl_init(world, rank, bytes(id_t.cpu().numpy().tobytes()))
+    for miss in (0.0, 0.03):
+        spec = synth.SynthSpec(4, 10, miss=miss, seed=3)
+        S = 60000
+        g = synth.synth_genotypes(spec, 0, S)
+        pos = synth.synth_positions(S)
+        lo = np.arange(0, S, 1700, dtype=np.int64)
+        hi = np.minimum(lo + 1700, S)
+        shards = multigpu.shard_windows(lo, hi, world)
+        b, e = shards[rank]
+        s0, s1 = multigpu.shard_site_range(lo, hi, b, e)
+        eng.upload(g[s0:s1], pos[s0:s1])                       # each rank holds only its shard of the sites
+        eng.set_pops(spec.hap_pop(), 4)
+        eng.set_windows(lo[b:e] - s0, hi[b:e] - s0)
+        counts = [x[1] - x[0] for x in shards]
+        w_max = max(counts)
+        table = PinnedArray((world * w_max, eng.popgen_record_width()), np.float64)
+        nk2 = eng.popgen_allgather(w_max, table.array, 100, 0.01)
+        rows = np.concatenate([table.array[r * w_max: r * w_max + counts[r]] for r in range(world)], axis=0)
+        got = multigpu.unpack_device_records(rows, 4)
+        # single-GPU truth on this rank
+        eng.upload(g, pos)
+        eng.set_pops(spec.hap_pop(), 4)
+        eng.set_windows(lo, hi)
+        ref = eng.popgen(100, 0.01)
+        assert np.array_equal(got["sites"], ref["sites"]) and np.array_equal(got["pos_sum"], ref["pos_sum"])
+        assert np.array_equal(got["path"], ref["path"])
+        assert (nk2 > 0) == (miss > 0)
+        for k in ("pi", "dxy", "fst"):
+            assert np.allclose(got[k], ref[k], rtol=1e-12, atol=0, equal_nan=True), k
+        table.close()
+    dist.barrier()
+    eng.close()
+    dist.destroy_process_group()
+    if rank == 0:
+        print("NCCL_GATHER_OK")
+
+
+if __name__ == "__main__":
+    main()
