@@ -323,6 +323,42 @@ def make_cli_cases():
             run([sys.executable, os.path.join(REF, "distMat.py"), "--windType", "cat", "-g", path,
                  "-o", o, "-f", "phased", "-T", "1", "--outFormat", "phylip", "--roundTo", "8"])
             res["distMat_cat_phylip"] = open(o).read()
+            # ---- more flag coverage (same input) ----
+            import gzip as _gz
+            gzpath = path + ".gz"
+            with open(path, "rb") as fi, _gz.open(gzpath, "wb") as fo:
+                fo.write(fi.read())
+            coords = os.path.join(tmp, "coords.txt")
+            with open(coords, "wt") as f:
+                f.write("chr1 1 15000 wA\nchr1 10000 30000 wB\nchr2 500 2500 wC\nchr3 1 100000 wD\n")
+            run([sys.executable, os.path.join(REF, "popgenWindows.py"), "--windType", "predefined", "--windCoords", coords,
+                 "-m", "10", "-g", gzpath, "-o", o, "-f", "phased", "-T", "1", "--popsFile", pops_file, "--roundTo", "9",
+                 "--addWindowID", "--writeFailedWindows"] + popargs)
+            res["popgenWindows_predefined_gz_id"] = open(o).read()
+            res["coords_file"] = open(coords).read()
+            # haploid samples: two samples of pop0 declared haploid need one-letter tokens -> use a diplo-coded file
+            dpath = os.path.join(tmp, "four_pops_diplo.geno")
+            synth.write_geno(dpath, g, pos, scafs, spec.sample_names(), fmt="diplo")
+            run([sys.executable, os.path.join(REF, "popgenWindows.py"), "-w", str(c["w"]), "-s", "10000", "-m", str(c["m"]),
+                 "-g", dpath, "-o", o, "-f", "diplo", "-T", "1", "--popsFile", pops_file, "--roundTo", "9"] + popargs)
+            res["popgenWindows_diplo_step"] = open(o).read()
+            run([sys.executable, os.path.join(REF, "ABBABABAwindows.py"), "--windType", "sites", "-w", "1000", "--overlap",
+                 "250", "-m", "100", "-g", path, "-o", o, "-f", "phased", "-T", "1", "--popsFile", pops_file,
+                 "--minData", "0.9", "-P1", "pop1", "-P2", "pop0", "-P3", "pop2", "-O", "pop3", "--writeFailedWindows",
+                 "--addWindowID"])
+            res["ABBABABAwindows_sites_overlap"] = open(o).read()
+            sub = spec.sample_names()[1::3]
+            wdo = os.path.join(tmp, "wd.txt")
+            run([sys.executable, os.path.join(REF, "distMat.py"), "-w", str(c["w"]), "-m", str(c["m"]), "-g", path,
+                 "-o", o, "-f", "phased", "-T", "1", "--outFormat", "nexus", "--roundTo", "7", "--includeSameWithSame",
+                 "--windowDataOutFile", wdo, "--samples"] + sub)
+            res["distMat_nexus_subset"] = open(o).read()
+            res["distMat_windowData"] = open(wdo).read()
+            res["distMat_subset_samples"] = sub
+            run([sys.executable, os.path.join(REF, "freq.py"), "-g", path, "-o", o, "-f", "phased", "-t", "1", "--indFreqs"])
+            txt = open(o).read().splitlines()
+            res["freq_indFreqs_head"] = txt[:50]
+            res["freq_indFreqs_sha256"] = hashlib.sha256(("\n".join(txt) + "\n").encode()).hexdigest()
         out[c["name"]] = res
         print("cli case", c["name"], "done")
     with open(os.path.join(GOLD, "cli_cases.json"), "wt") as f:

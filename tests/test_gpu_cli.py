@@ -218,3 +218,85 @@ def test_popgenWindows_popFreq_and_indPairDist_cli(inputs):
     _, r2 = _rows(ref)
     cols = [k for k, n in enumerate(h.split(",")) if n.startswith(("l_", "S_"))]
     assert cols and all(a[k] == b[k] for a, b in zip(r1, r2) for k in cols)
+
+
+# ------------------------------------------------------------------------------------------------
+# more flags, all against outputs of the unmodified reference scripts
+# ------------------------------------------------------------------------------------------------
+def test_popgenWindows_predefined_gz_windowID(inputs):
+    import gzip
+    from genomics_general_b200.cli import popgenWindows
+    i = inputs["four_pops"]
+    gz = i["geno"] + ".gz"
+    with open(i["geno"], "rb") as fi, gzip.open(gz, "wb") as fo:
+        fo.write(fi.read())
+    coords = os.path.join(i["dir"], "coords.txt")
+    open(coords, "wt").write(CLI["four_pops"]["coords_file"])
+    o = os.path.join(i["dir"], "pre.csv")
+    popgenWindows.main(["--windType", "predefined", "--windCoords", coords, "-m", "10", "-g", gz, "-o", o, "-f", "phased",
+                        "--popsFile", i["pops"], "--roundTo", "9", "--addWindowID", "--writeFailedWindows"] + _popargs(i["spec"]))
+    _compare_csv(open(o).read(), CLI["four_pops"]["popgenWindows_predefined_gz_id"], 6, 1e-6, 2e-9)
+
+
+def test_popgenWindows_diplo_format_and_step(inputs):
+    from genomics_general_b200 import synth
+    from genomics_general_b200.cli import popgenWindows
+    i = inputs["four_pops"]
+    c = i["cfg"]
+    spec = i["spec"]
+    g = synth.synth_genotypes(spec, 0, c["S"])
+    per = c["S"] // 3
+    scafs, pos = [], []
+    for k in range(3):
+        n = per if k < 2 else c["S"] - 2 * per
+        scafs += ["chr%d" % (k + 1)] * n
+        pos.append(synth.synth_positions(n, seed=c["seed"] + k))
+    dpath = os.path.join(i["dir"], "diplo.geno")
+    synth.write_geno(dpath, g, np.concatenate(pos), scafs, spec.sample_names(), fmt="diplo")
+    o = os.path.join(i["dir"], "dip.csv")
+    popgenWindows.main(["-w", str(c["w"]), "-s", "10000", "-m", str(c["m"]), "-g", dpath, "-o", o, "-f", "diplo",
+                        "--popsFile", i["pops"], "--roundTo", "9"] + _popargs(spec))
+    _compare_csv(open(o).read(), CLI["four_pops"]["popgenWindows_diplo_step"], 5, 1e-6, 2e-9)
+
+
+def test_ABBABABAwindows_sites_overlap_failed_windows(inputs):
+    from genomics_general_b200.cli import ABBABABAwindows
+    i = inputs["four_pops"]
+    o = os.path.join(i["dir"], "ab2.csv")
+    ABBABABAwindows.main(["--windType", "sites", "-w", "1000", "--overlap", "250", "-m", "100", "-g", i["geno"], "-o", o,
+                          "-f", "phased", "--popsFile", i["pops"], "--minData", "0.9", "-P1", "pop1", "-P2", "pop0",
+                          "-P3", "pop2", "-O", "pop3", "--writeFailedWindows", "--addWindowID"])
+    _compare_csv(open(o).read(), CLI["four_pops"]["ABBABABAwindows_sites_overlap"], 7, 0, 1.0001e-4)
+
+
+def test_distMat_nexus_subset_windowData(inputs):
+    from genomics_general_b200.cli import distMat
+    i = inputs["four_pops"]
+    c = i["cfg"]
+    o = os.path.join(i["dir"], "d.nex")
+    wd = os.path.join(i["dir"], "wd.txt")
+    distMat.main(["-w", str(c["w"]), "-m", str(c["m"]), "-g", i["geno"], "-o", o, "-f", "phased", "--outFormat", "nexus",
+                  "--roundTo", "7", "--includeSameWithSame", "--windowDataOutFile", wd, "--samples"]
+                 + CLI["four_pops"]["distMat_subset_samples"])
+    assert open(wd).read() == CLI["four_pops"]["distMat_windowData"]
+    ours, ref = open(o).read().splitlines(), CLI["four_pops"]["distMat_nexus_subset"].splitlines()
+    assert len(ours) == len(ref)
+    for a, b in zip(ours, ref):
+        if a.startswith("[") and "    " in a:
+            la, va = a.split("    ", 1)
+            lb, vb = b.split("    ", 1)
+            assert la == lb
+            assert_close(np.array([float(x) for x in va.split()]), np.array([float(x) for x in vb.split()]), la,
+                         rtol=1e-6, atol=2e-7)
+        else:
+            assert a == b
+
+
+def test_freq_indFreqs_bit_exact(inputs):
+    from genomics_general_b200.cli import freq
+    i = inputs["four_pops"]
+    o = os.path.join(i["dir"], "fi.tsv")
+    freq.main(["-g", i["geno"], "-o", o, "-f", "phased", "-t", "1", "--indFreqs"])
+    txt = open(o).read().splitlines()
+    assert txt[:50] == CLI["four_pops"]["freq_indFreqs_head"]
+    assert hashlib.sha256(("\n".join(txt) + "\n").encode()).hexdigest() == CLI["four_pops"]["freq_indFreqs_sha256"]
