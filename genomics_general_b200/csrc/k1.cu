@@ -480,6 +480,7 @@ struct FinParams {
     double min_data;
     int force_path;
     int with_freq;                 // the site pass carried the popFreq counters
+    int bookkeeping_only;          // P > 8: the site pass saw one collapsed population; statistics come from K2
     // outputs: fixed-width 8-byte records per window
     //   popgen: [sites(i64) pos_sum(i64) path(i64) pi[P] dxy[npairs] fst[npairs]]
     //   abba  : [sites(i64) pos_sum(i64) ABBA BABA D fd fdM sitesUsed]
@@ -540,6 +541,14 @@ __global__ void __launch_bounds__(64) k1_finalize(const __grid_constant__ FinPar
             double* fst_o = dxy_o + npairs;
             const long long Lp = (long long)sums[0];
             const bool ragged = (long long)sums[1] > 0;
+            if (fp.bookkeeping_only) {
+                const int path = sites < fp.min_sites ? 0 : 2;
+                fp.path[w] = path;
+                rec[2] = (unsigned long long)path;
+                if (path == 2) atomicAdd(fp.n_pairwise, 1);
+                for (int k = 3; k < fp.RC; ++k) rec[k] = d2u(nan_d());
+                continue;
+            }
             {   // popFreq columns (valid for every window: they only use sites complete in all haplotypes)
                 double* fq = fst_o + npairs;           // [l, S[P], thetaPi[P], thetaW[P], TajD[P]]
                 fq[0] = fp.with_freq ? (double)Lp : nan_d();
@@ -954,10 +963,14 @@ int pg_popgen_enqueue(pg_ctx* ctx, int32_t min_sites, double min_data, int32_t f
     *h_count = nullptr;
     PG_CHECK(ctx->P >= 1, "pg_popgen: call pg_set_pops first");
     PG_CHECK(force_path == 0 || force_path == 2, "pg_popgen: force_path must be 0 or 2");
-    PG_CHECK(ctx->P <= PG_MAX_K1_POPS, "pg_popgen: P=%d > %d populations is not supported yet", ctx->P, PG_MAX_K1_POPS);
+    PG_CHECK(ctx->P <= PG_MAX_POPS, "pg_popgen: P=%d > %d populations", ctx->P, PG_MAX_POPS);
     PG_CUDA(cudaSetDevice(ctx->device));
     pg_timings_reset(ctx);
     const int P = ctx->P;
+    // More populations than the site pass keeps in registers: it still does the bookkeeping (sites, position sums,
+    // failed / ragged windows) with all used haplotypes collapsed into one population, and every window that passes
+    // minSites goes through the pairwise path, whose epilogue handles up to PG_MAX_POPS populations.
+    const bool many = P > PG_MAX_K1_POPS;
     const int npairs = P * (P - 1) / 2;
     const int RC = 3 + P + 2 * npairs + 1 + 4 * P;
     const int64_t W = ctx->W;
@@ -976,8 +989,8 @@ int pg_popgen_enqueue(pg_ctx* ctx, int32_t min_sites, double min_data, int32_t f
         PG_CUDA(cudaMemcpy(d_rec, h.data(), h.size() * 8, cudaMemcpyHostToDevice));
         return PG_OK;
     }
-    const int Pp = pad_pops(P);
-    const bool wf = ctx->want_freq;
+    const int Pp = many ? 2 : pad_pops(P);
+    const bool wf = ctx->want_freq && !many;
     const int Q = 3 + Pp + Pp * (Pp - 1) / 2 + (wf ? (Pp + 1) / 2 : 0);
     K1Cache& c = *cache_of(ctx, 0);
     if (!c.valid || c.epoch != ctx->epoch) {
@@ -987,9 +1000,15 @@ int pg_popgen_enqueue(pg_ctx* ctx, int32_t min_sites, double min_data, int32_t f
             for (int h = 0; h < ctx->H; ++h) N += ctx->hap_pop[h] == x;
             PG_CHECK(N >= 1, "pg_popgen: population %d has no haplotypes", x);
         }
+        std::vector<int32_t> collapsed;
+        if (many) {
+            collapsed.assign(ctx->hap_pop.begin(), ctx->hap_pop.end());
+            for (int32_t& v : collapsed) v = v >= 0 ? 0 : -1;
+        }
+        const std::vector<int32_t>& pop_map = many ? collapsed : ctx->hap_pop;
         const int nw = wf ? (Pp == 2 ? nw_for<MODE_POPGEN_FREQ, 2>() : (Pp == 4 ? nw_for<MODE_POPGEN_FREQ, 4>() : nw_for<MODE_POPGEN_FREQ, 8>()))
                           : (Pp == 2 ? nw_for<MODE_POPGEN, 2>() : (Pp == 4 ? nw_for<MODE_POPGEN, 4>() : nw_for<MODE_POPGEN, 8>()));
-        PG_TRY(prepare_windowed(ctx, c, ctx->hap_pop, Pp, Q, nw));
+        PG_TRY(prepare_windowed(ctx, c, pop_map, Pp, Q, nw));
         c.epoch = ctx->epoch;
         c.valid = true;
     }
@@ -1014,7 +1033,8 @@ int pg_popgen_enqueue(pg_ctx* ctx, int32_t min_sites, double min_data, int32_t f
     fp.Ppad = Pp;
     fp.min_sites = min_sites;
     fp.min_data = min_data;
-    fp.force_path = force_path;
+    fp.force_path = many ? 2 : force_path;
+    fp.bookkeeping_only = many ? 1 : 0;
     fp.with_freq = wf ? 1 : 0;
     fp.rec = (unsigned long long*)d_rec;
     fp.RC = RC;

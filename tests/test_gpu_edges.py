@@ -135,3 +135,19 @@ def test_windows_that_skip_sites_and_repeat(eng):
     eng.set_windows(lo, hi)
     r = _check_popgen(eng, g, spec.hap_pop(), 2, lo, hi)
     assert np.array_equal(r["pi"][0], r["pi"][1], equal_nan=True)
+
+
+def test_more_than_eight_populations(eng):
+    """P = 11: the site pass only does the bookkeeping, every window's statistics come from the pairwise path."""
+    from genomics_general_b200 import synth
+    for miss in (0.0, 0.04):
+        spec = synth.SynthSpec(11, 3, miss=miss, seed=18)
+        S = 2400
+        g = synth.synth_genotypes(spec, 0, S)
+        eng.upload(g, synth.synth_positions(S))
+        eng.set_pops(spec.hap_pop(), 11)
+        lo = np.array([0, 800, 1600, 100, 2390], dtype=np.int64)
+        hi = np.array([800, 1600, 2400, 900, 2400], dtype=np.int64)
+        eng.set_windows(lo, hi)
+        r = _check_popgen(eng, g, spec.hap_pop(), 11, lo, hi, min_sites=20)
+        assert r["path"].tolist() == [2, 2, 2, 2, 0]
