@@ -61,7 +61,12 @@ _SIGS = {
     "pg_abbababa": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_void_p,
                               C.c_void_p, C.c_void_p, C.c_void_p]),
     "pg_site_counts": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
-    "pg_pairdist": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pg_site_target_freqs": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_double, C.c_int32, C.c_void_p,
+                                       C.c_void_p]),
+    "pg_pairdist": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                              C.c_void_p]),
+    "pg_ind_het": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
+    "pg_hapstats": (C.c_int, [C.c_void_p, C.c_double, C.c_int32, C.c_int32, C.c_void_p]),
     "pg_pair_counts": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "pg_last_timings": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]),
     "pg_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Drop-in for the reference's freq.py default mode (per-site per-population A,C,G,T counts;
-freq.py:52-58,100-111, flags 187-222), on the GPU.  --target minor|derived are not accelerated yet."""
+"""Drop-in for the reference's freq.py (flags 187-222), on the GPU: the default mode (per-site per-population A,C,G,T
+counts, freq.py:52-58,100-111) and --target derived|minor (frequency or count of one allele per population,
+freq.py:62-98; the reference's random pick between exactly tied minor alleles becomes "the lower allele")."""
 from __future__ import annotations
 
 import argparse
@@ -39,11 +40,13 @@ def build_parser():
 
 def main(argv=None):
     args = build_parser().parse_args(argv)
-    if args.target:
-        raise NotImplementedError("--target %s is not on the GPU path yet (SURVEY.md §8f rank 4)" % args.target)
     headerInds = C.header_names(args.genoFile)
     if not args.indFreqs and not args.population:
-        popNames, popInds = ["all"], [headerInds]
+        if args.target == "derived":       # freq.py:238-242
+            sys.stderr.write("\nNo populations specified. Assuming the final individual is the outgroup for polarising.\n")
+            popNames, popInds = ["ingroup", "outgroup"], [headerInds[:-1], [headerInds[-1]]]
+        else:
+            popNames, popInds = ["all"], [headerInds]
     elif args.indFreqs:
         popNames, popInds = list(headerInds), [[i] for i in headerInds]
     else:
@@ -63,6 +66,25 @@ def main(argv=None):
         scaf = np.array(gd.scaf_names, dtype=object)
         for s in range(0, gd.n_sites, slab):
             n = min(slab, gd.n_sites - s)
+            if args.target:
+                # freq.py:302-304: with a target the user's --asCounts / --keepNanLines / --minData apply
+                v, _ = eng.site_target_freqs(args.target, s, n, min_data=args.minData, as_counts=args.asCounts)
+                if args.asCounts:
+                    v = v.astype(np.int64)
+                    keep = np.arange(n) if args.keepNanLines else np.where(~np.all(v == 0, axis=1))[0]
+                else:
+                    v = np.around(v, 4)                                       # freq.py:91
+                    if args.threshold:                                        # freq.py:96-98
+                        hi, lo = v >= args.threshold, v < args.threshold
+                        v[hi] = 1
+                        v[lo] = 0
+                    keep = np.arange(n) if args.keepNanLines else np.where(~np.all(np.isnan(v), axis=1))[0]
+                vs = v.astype(str)
+                names = scaf[gd.scaf_ids[s:s + n]]
+                pos = gd.pos[s:s + n]
+                for i in keep:
+                    out.write(names[i] + "\t" + str(pos[i]) + "\t" + "\t".join(vs[i]) + "\n")
+                continue
             c = eng.site_counts(s, n).astype(np.int64)                      # [n, P, 4]
             cs = c.astype(str)
             cols = [np.char.add(np.char.add(np.char.add(cs[:, x, 0], ","), np.char.add(cs[:, x, 1], ",")),

@@ -4,8 +4,10 @@
 Reference: /root/reference/popgenWindows.py — argparse 170-213, sample/pop parsing 253-307, header 319-354,
 worker stats_wrapper 28-75.  The process pipeline (producer / -T workers / sorter / writer) is replaced by:
 parse the whole file once -> dense int8 matrix -> all windows in one engine call -> rows.
-Supported --analysis: popFreq, popDist, popPairDist, indPairDist.  indHet / hapStats are not on the accelerated
-path yet.
+All six --analysis modes run on the GPU.  The reference caches one haplotype distance matrix per window and its
+analyses modify it in place (groupDistStats masks pairs with n_ij < minSites and the diagonal, genomics.py:959-963;
+indPairDists masks the diagonal, 940), so later analyses of the same window see the masked matrix — the engine calls
+below take that state as arguments (min_sites / diag_nan).
 """
 from __future__ import annotations
 
@@ -58,9 +60,6 @@ def build_parser():
 def main(argv=None):
     args = build_parser().parse_args(argv)
     minSites, coords = C.check_window_args(args)
-    unsupported = [a for a in args.analysis if a in ("indHet", "hapStats")]
-    if unsupported:
-        raise NotImplementedError("--analysis %s is not on the GPU path yet" % " ".join(unsupported))
 
     popNames, popInds, allInds = [], [], []
     if args.population is not None:
@@ -70,7 +69,8 @@ def main(argv=None):
         allInds = sorted(set(allInds + args.samples.split(",")))
     if len(allInds) == 0:
         allInds = C.header_names(args.genoFile) if args.header is None else args.header.split()[2:]
-    if len(popNames) == 0 and ("popFreq" in args.analysis or "popDist" in args.analysis or "popPairDist" in args.analysis):
+    if len(popNames) == 0 and ("popFreq" in args.analysis or "popDist" in args.analysis or "popPairDist" in args.analysis
+                               or "hapStats" in args.analysis):
         popNames.append("all")
         popInds.append(allInds)
     ploidyDict = C.ploidy_dict(args, allInds, args.haploid.split(",") if args.haploid else None)
@@ -90,6 +90,11 @@ def main(argv=None):
     ind_sorted = sorted(allInds)
     if "indPairDist" in args.analysis:
         stats += ["_".join(["d", i, j]) for i, j in itertools.combinations_with_replacement(ind_sorted, 2)]
+    if "indHet" in args.analysis:      # the reference's column order here is that of list(set(...)) (popgenWindows.py:277)
+        stats += ["het_" + n for n in allInds]
+    if "hapStats" in args.analysis:
+        for key in ("H1_", "H12_", "H2_"):
+            stats += [key + n for n in popNames]
     out.write(",".join(stats) + "\n")
 
     gd = C.load_geno(args, sampleData.indNames, ploidyDict, header=args.header)
@@ -111,11 +116,20 @@ def main(argv=None):
                 raise NotImplementedError("popFreq with samples outside every population (--samples) is not supported")
             fq = eng.popgen_freqstats()
         npairs = P * (P - 1) // 2
-        dmat = None
+        # state of the reference's cached distance matrix when the later analyses run (popgenWindows.py:50-64)
+        masked = minSites if ("popDist" in args.analysis or "popPairDist" in args.analysis) else 0
+        dmat = het = hst = None
         if "indPairDist" in args.analysis:
             inv = {gd.names.index(n): k for k, n in enumerate(ind_sorted)}
             hap_ind = np.repeat(np.array([inv[i] for i in range(len(gd.names))], dtype=np.int32), gd.ploidy.astype(np.int64))
-            dmat = eng.pairdist(hap_ind, len(ind_sorted), False)["dist"]
+            dmat = eng.pairdist(hap_ind, len(ind_sorted), False, min_sites=masked)["dist"]
+        if "indHet" in args.analysis:
+            inv = {gd.names.index(n): k for k, n in enumerate(allInds)}
+            hap_ind = np.repeat(np.array([inv[i] for i in range(len(gd.names))], dtype=np.int32), gd.ploidy.astype(np.int64))
+            het = eng.ind_het(hap_ind, len(allInds), min_sites=masked)
+        if "hapStats" in args.analysis:
+            hst = eng.hapstats(args.hapDist, min_sites=masked, diag_nan=bool(masked) or "popDist" in args.analysis
+                               or "popPairDist" in args.analysis or "indPairDist" in args.analysis)
         iu = np.triu_indices(len(ind_sorted)) if dmat is not None else None
         for k in range(len(ws)):
             pre = C.window_prefix(args, ws, k, gd, r["sites"][k], r["pos_sum"][k])
@@ -133,6 +147,10 @@ def main(argv=None):
                     vals += list(r["dxy"][k]) + list(r["fst"][k])
                 if dmat is not None:
                     vals += list(dmat[k][iu])
+                if het is not None:
+                    vals += list(het[k])
+                if hst is not None:
+                    vals += list(hst[k][:, 0]) + list(hst[k][:, 1]) + list(hst[k][:, 2])
                 vals = [v if isinstance(v, int) else round(np.float64(v), args.roundTo) for v in vals]
             else:
                 vals = [np.nan] * len(stats)

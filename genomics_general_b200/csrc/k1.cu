@@ -1230,8 +1230,133 @@ extern "C" int pg_abbababa(pg_ctx* ctx, int32_t p1, int32_t p2, int32_t p3, int3
 }
 
 // ================================================================================================
-// pg_site_counts
+// pg_site_counts / pg_site_target_freqs
 // ================================================================================================
+namespace {
+// per-site counts of `cnt` sites starting at `first` -> ctx->misc as uint16 [cnt x P x 4]
+int site_counts_slab(pg_ctx* ctx, int64_t first, int64_t cnt) {
+    const int P = ctx->P;
+    const int64_t stride = (int64_t)P * 4;
+    for (int p0 = 0; p0 < P; p0 += PG_MAX_K1_POPS) {
+        const int pc = std::min(PG_MAX_K1_POPS, P - p0);
+        const int Pp = pad_pops(pc);
+        std::vector<int32_t> local(ctx->H, -1);
+        for (int h = 0; h < ctx->H; ++h)
+            if (ctx->hap_pop[h] >= p0 && ctx->hap_pop[h] < p0 + pc) local[h] = ctx->hap_pop[h] - p0;
+        PopTables pt;
+        build_tables(local, ctx->H, ctx->pitch / 16, Pp, pt);
+        const int n_ent = (int)pt.ent_chunk.size();
+        const int table_bytes = n_ent * 20 + 64;
+        PG_CHECK(table_bytes <= 48 * 1024, "population layout needs too many mask entries");
+        K1Launch L;
+        const int nw = Pp == 2 ? nw_for<MODE_COUNTS, 2>() : (Pp == 4 ? nw_for<MODE_COUNTS, 4>() : nw_for<MODE_COUNTS, 8>());
+        L.plan = pg_make_k1_plan(cnt, ctx->H, ctx->sm_count, table_bytes, nw);
+        PG_CHECK(L.plan.stages >= 2, "rows of %d haplotypes are too long for the site-pass kernel", ctx->H);
+        PG_TRY(check_plan(L.plan));
+        PG_TRY(ctx->tables.ensure((size_t)n_ent * 20 + 4096));
+        uint8_t* base = (uint8_t*)ctx->tables.p;
+        size_t o = 0;
+        uint32_t* d_mask_words = nullptr;
+        int32_t* d_chunk = nullptr;
+        PG_TRY(push(ctx, base, o, pt.ent_mask.data(), pt.ent_mask.size(), &d_mask_words));
+        PG_TRY(push(ctx, base, o, pt.ent_chunk.data(), pt.ent_chunk.size(), &d_chunk));
+        K1Params& p = L.prm;
+        memset(&p, 0, sizeof(p));
+        p.geno = (const uint8_t*)ctx->d_geno;
+        p.pos = ctx->d_pos;
+        p.site_begin = first;
+        p.site_end = first + cnt;
+        p.num_tiles = L.plan.num_tiles;
+        p.pitch = L.plan.pitch;
+        p.G = L.plan.G;
+        p.I = L.plan.I;
+        p.T = L.plan.T;
+        p.wpt = L.plan.wpt;
+        p.nw = nw;
+        p.stages = L.plan.stages;
+        p.tile_bytes = L.plan.tile_bytes;
+        p.ent_chunk = d_chunk;
+        p.ent_mask = reinterpret_cast<uint4*>(d_mask_words);
+        p.n_ent = n_ent;
+        for (int X = 0; X < PG_MAX_K1_POPS; ++X) {
+            p.ent_lo[X] = pt.ent_lo[X];
+            p.ent_hi[X] = pt.ent_hi[X];
+            p.full_lo[X] = pt.full_lo[X];
+            p.full_hi[X] = pt.full_hi[X];
+            p.popN[X] = pt.popN[X];
+        }
+        p.counts_out = (uint16_t*)ctx->misc.p + (size_t)p0 * 4;
+        p.counts_stride = stride;
+        p.counts_pops = pc;
+        if (Pp == 2) PG_TRY((launch_site_pass<MODE_COUNTS, 2>(ctx, L, "k1_counts")));
+        else if (Pp == 4) PG_TRY((launch_site_pass<MODE_COUNTS, 4>(ctx, L, "k1_counts")));
+        else PG_TRY((launch_site_pass<MODE_COUNTS, 8>(ctx, L, "k1_counts")));
+        // the table buffer (and the host vectors behind the async copies) are reused by the next group
+        PG_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return PG_OK;
+}
+
+// freq.py --target (freq.py:62-92): one thread per site turns the per-population counts into the frequency (or
+// count) of the target allele.  target 1 = derived (last population is the outgroup; derivedAllele, genomics.py:636-659),
+// 2 = minor (minorAllele, 663-668; an exact tie, random in the reference, takes the lower allele and is flagged).
+__global__ void __launch_bounds__(256) k1_target_freqs(const uint16_t* __restrict__ counts, int64_t n, int P, int target,
+                                                       double min_data, int as_counts, double* __restrict__ out,
+                                                       uint8_t* __restrict__ tie) {
+    const int64_t s = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (s >= n) return;
+    const ushort4* c = reinterpret_cast<const ushort4*>(counts) + s * P;
+    unsigned in[4] = {0, 0, 0, 0}, outg[4] = {0, 0, 0, 0};
+    for (int X = 0; X < P; ++X) {
+        const ushort4 v = c[X];
+        unsigned* dst = (target == 1 && X == P - 1) ? outg : in;
+        dst[0] += v.x;
+        dst[1] += v.y;
+        dst[2] += v.z;
+        dst[3] += v.w;
+    }
+    int tgt = -1;
+    bool tied = false;
+    if (target == 1) {
+        int n_in = 0, n_out = 0, oa = -1;
+        for (int a = 0; a < 4; ++a) {
+            n_in += in[a] > 0;
+            if (outg[a] > 0) {
+                ++n_out;
+                oa = a;
+            }
+        }
+        if (n_out == 1 && n_in == 2 && in[oa] > 0)
+            for (int a = 0; a < 4; ++a)
+                if (in[a] > 0 && a != oa) tgt = a;
+    } else {
+        int a0 = -1, a1 = -1, na = 0;
+        for (int a = 0; a < 4; ++a)
+            if (in[a] > 0) {
+                if (na == 0) a0 = a; else a1 = a;
+                ++na;
+            }
+        if (na == 2) {
+            tied = in[a0] == in[a1];
+            tgt = in[a1] < in[a0] ? a1 : a0;
+        }
+    }
+    if (tie) tie[s] = tied ? 1 : 0;
+    const double none = as_counts ? 0.0 : __longlong_as_double(0x7ff8000000000000ll);
+    for (int X = 0; X < P; ++X) {
+        const ushort4 v = c[X];
+        const unsigned nk = (unsigned)v.x + v.y + v.z + v.w;
+        double r = none;
+        if (tgt >= 0 && (double)nk >= min_data) {            // siteNonNan() >= minData compares a COUNT (freq.py:79)
+            const unsigned k = tgt == 0 ? v.x : (tgt == 1 ? v.y : (tgt == 2 ? v.z : v.w));
+            if (as_counts) r = (double)k;
+            else if (nk > 0) r = (double)k / (double)nk;     // nan when the population has no data (genomics.py:597)
+        }
+        out[s * P + X] = r;
+    }
+}
+}  // namespace
+
 extern "C" int pg_site_counts(pg_ctx* ctx, int64_t site0, int64_t n, uint16_t* counts) {
     PG_CHECK(ctx && counts, "pg_site_counts: null argument");
     PG_CHECK(ctx->P >= 1, "pg_site_counts: call pg_set_pops first");
@@ -1239,72 +1364,47 @@ extern "C" int pg_site_counts(pg_ctx* ctx, int64_t site0, int64_t n, uint16_t* c
     PG_CUDA(cudaSetDevice(ctx->device));
     pg_timings_reset(ctx);
     if (n == 0) return PG_OK;
-    const int P = ctx->P;
-    const int64_t stride = (int64_t)P * 4;
+    const int64_t stride = (int64_t)ctx->P * 4;
     // bounded device output buffer: process the range in slabs
     const int64_t slab = std::max<int64_t>(1, std::min<int64_t>(n, (int64_t)(1ll << 30) / (stride * 2)));
     PG_TRY(ctx->misc.ensure((size_t)slab * stride * 2 + 64));
     for (int64_t s = 0; s < n; s += slab) {
         const int64_t cnt = std::min(slab, n - s);
-        for (int p0 = 0; p0 < P; p0 += PG_MAX_K1_POPS) {
-            const int pc = std::min(PG_MAX_K1_POPS, P - p0);
-            const int Pp = pad_pops(pc);
-            std::vector<int32_t> local(ctx->H, -1);
-            for (int h = 0; h < ctx->H; ++h)
-                if (ctx->hap_pop[h] >= p0 && ctx->hap_pop[h] < p0 + pc) local[h] = ctx->hap_pop[h] - p0;
-            PopTables pt;
-            build_tables(local, ctx->H, ctx->pitch / 16, Pp, pt);
-            const int n_ent = (int)pt.ent_chunk.size();
-            const int table_bytes = n_ent * 20 + 64;
-            PG_CHECK(table_bytes <= 48 * 1024, "population layout needs too many mask entries");
-            K1Launch L;
-            const int nw = Pp == 2 ? nw_for<MODE_COUNTS, 2>() : (Pp == 4 ? nw_for<MODE_COUNTS, 4>() : nw_for<MODE_COUNTS, 8>());
-            L.plan = pg_make_k1_plan(cnt, ctx->H, ctx->sm_count, table_bytes, nw);
-            PG_CHECK(L.plan.stages >= 2, "rows of %d haplotypes are too long for the site-pass kernel", ctx->H);
-            PG_TRY(check_plan(L.plan));
-            PG_TRY(ctx->tables.ensure((size_t)n_ent * 20 + 4096));
-            uint8_t* base = (uint8_t*)ctx->tables.p;
-            size_t o = 0;
-            uint32_t* d_mask_words = nullptr;
-            int32_t* d_chunk = nullptr;
-            PG_TRY(push(ctx, base, o, pt.ent_mask.data(), pt.ent_mask.size(), &d_mask_words));
-            PG_TRY(push(ctx, base, o, pt.ent_chunk.data(), pt.ent_chunk.size(), &d_chunk));
-            K1Params& p = L.prm;
-            memset(&p, 0, sizeof(p));
-            p.geno = (const uint8_t*)ctx->d_geno;
-            p.pos = ctx->d_pos;
-            p.site_begin = site0 + s;
-            p.site_end = site0 + s + cnt;
-            p.num_tiles = L.plan.num_tiles;
-            p.pitch = L.plan.pitch;
-            p.G = L.plan.G;
-            p.I = L.plan.I;
-            p.T = L.plan.T;
-            p.wpt = L.plan.wpt;
-            p.nw = nw;
-            p.stages = L.plan.stages;
-            p.tile_bytes = L.plan.tile_bytes;
-            p.ent_chunk = d_chunk;
-            p.ent_mask = reinterpret_cast<uint4*>(d_mask_words);
-            p.n_ent = n_ent;
-            for (int X = 0; X < PG_MAX_K1_POPS; ++X) {
-                p.ent_lo[X] = pt.ent_lo[X];
-                p.ent_hi[X] = pt.ent_hi[X];
-                p.full_lo[X] = pt.full_lo[X];
-                p.full_hi[X] = pt.full_hi[X];
-                p.popN[X] = pt.popN[X];
-            }
-            p.counts_out = (uint16_t*)ctx->misc.p + (size_t)p0 * 4;
-            p.counts_stride = stride;
-            p.counts_pops = pc;
-            if (Pp == 2) PG_TRY((launch_site_pass<MODE_COUNTS, 2>(ctx, L, "k1_counts")));
-            else if (Pp == 4) PG_TRY((launch_site_pass<MODE_COUNTS, 4>(ctx, L, "k1_counts")));
-            else PG_TRY((launch_site_pass<MODE_COUNTS, 8>(ctx, L, "k1_counts")));
-            // the table buffer is reused by the next group: wait for this launch
-            if (p0 + PG_MAX_K1_POPS < P) PG_CUDA(cudaStreamSynchronize(ctx->stream));
-        }
+        PG_TRY(site_counts_slab(ctx, site0 + s, cnt));
         PG_CUDA(cudaMemcpyAsync(counts + (size_t)s * stride, ctx->misc.p, (size_t)cnt * stride * 2,
                                 cudaMemcpyDeviceToHost, ctx->stream));
+        PG_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return PG_OK;
+}
+
+extern "C" int pg_site_target_freqs(pg_ctx* ctx, int64_t site0, int64_t n, int32_t target, double min_data,
+                                    int32_t as_counts, double* out, uint8_t* tie) {
+    PG_CHECK(ctx && out, "pg_site_target_freqs: null argument");
+    PG_CHECK(ctx->P >= 1, "pg_site_target_freqs: call pg_set_pops first");
+    PG_CHECK(target == 1 || target == 2, "pg_site_target_freqs: target must be 1 (derived) or 2 (minor)");
+    PG_CHECK(target != 1 || ctx->P >= 2, "pg_site_target_freqs: derived needs an outgroup population (the last one)");
+    PG_CHECK(site0 >= 0 && n >= 0 && site0 + n <= ctx->S, "pg_site_target_freqs: range outside the uploaded sites");
+    PG_CUDA(cudaSetDevice(ctx->device));
+    pg_timings_reset(ctx);
+    if (n == 0) return PG_OK;
+    const int P = ctx->P;
+    const int64_t stride = (int64_t)P * 4;
+    const int64_t slab = std::max<int64_t>(1, std::min<int64_t>(n, (int64_t)(1ll << 28) / (stride * 2)));
+    PG_TRY(ctx->misc.ensure((size_t)slab * stride * 2 + 64));
+    PG_TRY(ctx->out_d.ensure((size_t)slab * P * 8 + (size_t)slab + 64));
+    double* d_out = (double*)ctx->out_d.p;
+    uint8_t* d_tie = (uint8_t*)(d_out + (size_t)slab * P);
+    for (int64_t s = 0; s < n; s += slab) {
+        const int64_t cnt = std::min(slab, n - s);
+        PG_TRY(site_counts_slab(ctx, site0 + s, cnt));
+        const int ti = pg_time_begin(ctx, "k1_target_freqs");
+        k1_target_freqs<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>((const uint16_t*)ctx->misc.p, cnt, P, target,
+                                                                              min_data, as_counts ? 1 : 0, d_out, d_tie);
+        pg_time_end(ctx, ti);
+        PG_CUDA(cudaGetLastError());
+        PG_CUDA(cudaMemcpyAsync(out + (size_t)s * P, d_out, (size_t)cnt * P * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if (tie) PG_CUDA(cudaMemcpyAsync(tie + s, d_tie, (size_t)cnt, cudaMemcpyDeviceToHost, ctx->stream));
         PG_CUDA(cudaStreamSynchronize(ctx->stream));
     }
     return PG_OK;

@@ -466,6 +466,8 @@ struct IndEpiParams {
     int Hk, n_ind;
     const int32_t* ind_start;   // [n_ind+1]
     int include_same;
+    int min_sites;              // > 0: entries with n_ij < min_sites are nan (an earlier groupDistStats masked the
+                                // cached matrix in place, genomics.py:959-961)
     double* out;                // [nb x n_ind x n_ind]
 };
 
@@ -488,12 +490,195 @@ __global__ void __launch_bounds__(256) k2_ind_epi(const __grid_constant__ IndEpi
                 } else {
                     const int nij = N[(size_t)ep.mid[i] * ep.Hm + ep.mid[j]];
                     if (nij == 0) continue;                  // np.mean of an empty array = nan
+                    if (ep.min_sites > 0 && nij < ep.min_sites) continue;
                     d = (double)D[(size_t)i * ep.Hk + j] / (double)nij;
                 }
                 s += d;
                 c += 1;
             }
         ep.out[(size_t)wb * total + idx] = c ? s / (double)c : nan_d();
+    }
+}
+
+// ---- sampleHet (genomics.py:918-929): distance between the two haplotypes of each individual ------------
+struct HetParams {
+    const uint32_t* planes;     // [3][Hk][NWp], rows sorted by individual
+    int Hk;
+    int64_t NWp;
+    int64_t site_base;
+    const int64_t* win_lo;      // [nb]
+    const int64_t* win_hi;
+    const int32_t* ind_start;   // [n_ind+1]
+    int n_ind;
+    int min_sites;              // in-place mask of an earlier groupDistStats (0 = none)
+    double* out;                // [nb x n_ind]
+};
+
+__global__ void __launch_bounds__(128) k2_het(const __grid_constant__ HetParams hp) {
+    __shared__ int sh_d[4], sh_n[4];
+    const int a = blockIdx.x, wb = blockIdx.y;
+    const int r0 = hp.ind_start[a], r1 = hp.ind_start[a + 1];
+    double* o = hp.out + (size_t)wb * hp.n_ind + a;
+    if (r1 - r0 != 2) {             // len(x) == 2 is required (the reference raises IndexError for len(x) == 1)
+        if (threadIdx.x == 0) *o = nan_d();
+        return;
+    }
+    const int64_t rel_lo = hp.win_lo[wb] - hp.site_base, rel_hi = hp.win_hi[wb] - hp.site_base;
+    const int64_t w_first = rel_lo >> 5, w_last = (rel_hi - 1) >> 5;
+    const uint32_t mask_first = 0xffffffffu << (rel_lo & 31);
+    const uint32_t mask_last = 0xffffffffu >> (31 - (int)((rel_hi - 1) & 31));
+    const size_t PS = (size_t)hp.Hk * hp.NWp;
+    const uint32_t* b0i = hp.planes + (size_t)r0 * hp.NWp;
+    const uint32_t* b0j = b0i + hp.NWp;
+    int diff = 0, n = 0;
+    for (int64_t w = w_first + threadIdx.x; w <= w_last; w += 128) {
+        uint32_t m = b0i[2 * PS + w] & b0j[2 * PS + w];
+        if (w == w_first) m &= mask_first;
+        if (w == w_last) m &= mask_last;
+        n += __popc(m);
+        diff += __popc(((b0i[w] ^ b0j[w]) | (b0i[PS + w] ^ b0j[PS + w])) & m);
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        diff += __shfl_xor_sync(0xffffffffu, diff, d);
+        n += __shfl_xor_sync(0xffffffffu, n, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        sh_d[threadIdx.x >> 5] = diff;
+        sh_n[threadIdx.x >> 5] = n;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        diff = sh_d[0] + sh_d[1] + sh_d[2] + sh_d[3];
+        n = sh_n[0] + sh_n[1] + sh_n[2] + sh_n[3];
+        // `len(x)==2 & np.sum(mask) >= 1` parses as len(x) == (2 & n) >= 1: bit 1 of n must be set (924, 927)
+        double v = nan_d();
+        if ((n & 2) == 2 && !(hp.min_sites > 0 && n < hp.min_sites)) v = (double)diff / (double)n;
+        *o = v;
+    }
+}
+
+// ---- H12stats (genomics.py:1079-1098) + distMat_to_cluster_sizes (1239-1261) ------------------------------
+struct HapEpiParams {
+    const int32_t* diff;        // [nb][Hk][Hk]
+    const int32_t* n;           // [nb][Hm][Hm]
+    const int32_t* mid;
+    int Hm, Hk, P;
+    const int32_t* pop_start;   // [P+1]
+    int min_sites;              // in-place mask of an earlier groupDistStats (0 = none)
+    int diag_nan;               // an earlier groupDistStats / indPairDists set the diagonal to nan
+    double max_dist;
+    double* out;                // [nb][P][3] = H1, H12, H2
+};
+
+// One CTA per (population, window). Shared memory: match bits [N][NWD] | alive [NWD] | sizes [N].
+__global__ void __launch_bounds__(256) k2_hap_epi(const __grid_constant__ HapEpiParams ep) {
+    extern __shared__ __align__(16) uint8_t hsm[];
+    __shared__ int sh_cnt[8], sh_row[8];
+    __shared__ int s_best_cnt, s_best_row;
+    const int X = blockIdx.x, wb = blockIdx.y;
+    const int r0 = ep.pop_start[X], N = ep.pop_start[X + 1] - r0;
+    const int NWD = (N + 31) / 32;
+    uint32_t* match = reinterpret_cast<uint32_t*>(hsm);
+    uint32_t* alive = match + (size_t)N * NWD;
+    int* sizes = reinterpret_cast<int*>(alive + NWD);
+    const int32_t* D = ep.diff + (size_t)wb * ep.Hk * ep.Hk;
+    const int32_t* Nn = ep.n + (size_t)wb * ep.Hm * ep.Hm;
+    const int tid = threadIdx.x;
+    for (int idx = tid; idx < N * NWD; idx += 256) {
+        const int i = idx / NWD, wj = idx % NWD;
+        uint32_t bits = 0;
+        for (int b = 0; b < 32; ++b) {
+            const int j = wj * 32 + b;
+            if (j >= N) break;
+            bool m;
+            if (i == j) m = !ep.diag_nan && (0.0 <= ep.max_dist);          // distMatrix leaves 0 on the diagonal
+            else {
+                const int nij = Nn[(size_t)ep.mid[r0 + i] * ep.Hm + ep.mid[r0 + j]];
+                m = nij > 0 && !(ep.min_sites > 0 && nij < ep.min_sites) &&
+                    ((double)D[(size_t)(r0 + i) * ep.Hk + r0 + j] / (double)nij <= ep.max_dist);
+            }
+            bits |= (m ? 1u : 0u) << b;
+        }
+        match[idx] = bits;
+    }
+    for (int w = tid; w < NWD; w += 256) alive[w] = (w == NWD - 1 && (N & 31)) ? ((1u << (N & 31)) - 1u) : 0xffffffffu;
+    __syncthreads();
+    int ncl = 0;
+    while (true) {
+        // row with the most matches among the rows still alive (first one on ties: np.argmax)
+        int best = -1, brow = 0x7fffffff;
+        for (int i = tid; i < N; i += 256) {
+            if (!((alive[i >> 5] >> (i & 31)) & 1u)) continue;
+            int c = 0;
+            for (int w = 0; w < NWD; ++w) c += __popc(match[(size_t)i * NWD + w] & alive[w]);
+            if (c > best) {         // i increases: the first maximum wins
+                best = c;
+                brow = i;
+            }
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            const int oc = __shfl_xor_sync(0xffffffffu, best, d), orow = __shfl_xor_sync(0xffffffffu, brow, d);
+            if (oc > best || (oc == best && orow < brow)) {
+                best = oc;
+                brow = orow;
+            }
+        }
+        if ((tid & 31) == 0) {
+            sh_cnt[tid >> 5] = best;
+            sh_row[tid >> 5] = brow;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int bc = -1, br = 0x7fffffff;
+            for (int w = 0; w < 8; ++w)
+                if (sh_cnt[w] > bc || (sh_cnt[w] == bc && sh_row[w] < br)) {
+                    bc = sh_cnt[w];
+                    br = sh_row[w];
+                }
+            s_best_cnt = bc;
+            s_best_row = br;
+        }
+        __syncthreads();
+        const int bc = s_best_cnt, br = s_best_row;
+        if (bc < 0) break;                       // nothing alive
+        if (bc > 1) {
+            if (tid == 0) sizes[ncl] = bc;
+            ++ncl;
+            __syncthreads();
+            for (int w = tid; w < NWD; w += 256) alive[w] &= ~match[(size_t)br * NWD + w];
+            __syncthreads();
+        } else {
+            if (tid == 0) {
+                int rest = 0;
+                for (int w = 0; w < NWD; ++w) rest += __popc(alive[w]);
+                for (int k = 0; k < rest; ++k) sizes[ncl + k] = 1;
+                s_best_cnt = rest;
+            }
+            __syncthreads();
+            ncl += s_best_cnt;
+            break;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double* o = ep.out + ((size_t)wb * ep.P + X) * 3;
+        long long tot = 0;
+        for (int k = 0; k < ncl; ++k) tot += sizes[k];
+        double H1 = 0.0, H2 = 0.0;
+        for (int k = 0; k < ncl; ++k) {
+            const double f = (double)sizes[k] / (double)tot;
+            H1 += f * f;
+            if (k >= 1) H2 += f * f;
+        }
+        double H12 = H1;
+        if (ncl > 1) H12 = H1 + 2 * ((double)sizes[0] / (double)tot) * ((double)sizes[1] / (double)tot);
+        else H2 = 0.0;
+        if (ncl == 0) H1 = H12 = H2 = nan_d();
+        o[0] = H1;
+        o[1] = H12;
+        o[2] = H2;
     }
 }
 
@@ -725,7 +910,7 @@ int pg_k2_popgen_windows(pg_ctx* ctx, const std::vector<int64_t>& wins, int32_t 
 }
 
 extern "C" int pg_pairdist(pg_ctx* ctx, int32_t n_ind, const int32_t* hap_ind, int32_t include_same_with_same,
-                           double* dist, int64_t* n_sites, int64_t* pos_sum) {
+                           int32_t min_sites, double* dist, int64_t* n_sites, int64_t* pos_sum) {
     PG_CHECK(ctx && hap_ind && dist, "pg_pairdist: null argument");
     PG_CHECK(n_ind >= 1, "pg_pairdist: n_ind must be >= 1");
     PG_CHECK(ctx->H > 0, "pg_pairdist: upload genotypes first");
@@ -791,6 +976,7 @@ extern "C" int pg_pairdist(pg_ctx* ctx, int32_t n_ind, const int32_t* hap_ind, i
         ep.n_ind = n_ind;
         ep.ind_start = (const int32_t*)ctx->misc.p;
         ep.include_same = include_same_with_same ? 1 : 0;
+        ep.min_sites = min_sites;
         ep.out = (double*)ctx->out_d.p;
         dim3 grid((unsigned)std::min<size_t>((nn + 255) / 256, 1024), (unsigned)nb);
         const int ti = pg_time_begin(ctx, "k2_ind_epi");
@@ -837,5 +1023,164 @@ extern "C" int pg_pair_counts(pg_ctx* ctx, int64_t window, int32_t* diff, int32_
     PG_CUDA(cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < H; ++i)
         for (int j = 0; j < H; ++j) n[(size_t)i * H + j] = nu[(size_t)ps.mid[i] * ps.Hm + ps.mid[j]];
+    return PG_OK;
+}
+
+namespace {
+// non-empty windows and the site span they cover
+void nonempty_windows(const pg_ctx* ctx, std::vector<int64_t>& idx, int64_t& lo, int64_t& hi) {
+    lo = ctx->S;
+    hi = 0;
+    for (int64_t w = 0; w < ctx->W; ++w)
+        if (ctx->win_hi[w] > ctx->win_lo[w]) {
+            idx.push_back(w);
+            lo = std::min(lo, ctx->win_lo[w]);
+            hi = std::max(hi, ctx->win_hi[w]);
+        }
+}
+
+// scatter batch rows (row_doubles each) of a device buffer to the windows' rows of a host array
+int copy_rows_back(pg_ctx* ctx, const std::vector<int64_t>& wins, size_t b0, size_t nb, const double* d_src,
+                   double* h_dst, size_t row_doubles) {
+    size_t k = 0;
+    while (k < nb) {
+        size_t e = k + 1;
+        while (e < nb && wins[b0 + e] == wins[b0 + e - 1] + 1) ++e;
+        PG_CUDA(cudaMemcpyAsync(h_dst + (size_t)wins[b0 + k] * row_doubles, d_src + k * row_doubles,
+                                (e - k) * row_doubles * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        k = e;
+    }
+    PG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PG_OK;
+}
+}  // namespace
+
+// Alignment.sampleHet() (genomics.py:918-929) for every window: het [W x n_ind]
+extern "C" int pg_ind_het(pg_ctx* ctx, int32_t n_ind, const int32_t* hap_ind, int32_t min_sites, double* het) {
+    PG_CHECK(ctx && hap_ind && het, "pg_ind_het: null argument");
+    PG_CHECK(n_ind >= 1, "pg_ind_het: n_ind must be >= 1");
+    PG_CHECK(ctx->H > 0, "pg_ind_het: upload genotypes first");
+    PG_CUDA(cudaSetDevice(ctx->device));
+    pg_timings_reset(ctx);
+    const int64_t W = ctx->W;
+    if (W == 0) return PG_OK;
+    std::vector<int32_t> order, ind_start(n_ind + 1, 0);
+    for (int h = 0; h < ctx->H; ++h)
+        PG_CHECK(hap_ind[h] >= -1 && hap_ind[h] < n_ind, "pg_ind_het: hap_ind[%d]=%d out of range", h, hap_ind[h]);
+    for (int a = 0; a < n_ind; ++a) {
+        ind_start[a] = (int32_t)order.size();
+        for (int h = 0; h < ctx->H; ++h)
+            if (hap_ind[h] == a) order.push_back(h);
+    }
+    ind_start[n_ind] = (int32_t)order.size();
+    for (size_t k = 0; k < (size_t)W * n_ind; ++k) het[k] = NAN;
+    std::vector<int64_t> wins;
+    int64_t lo, hi;
+    nonempty_windows(ctx, wins, lo, hi);
+    if (wins.empty() || order.empty()) return PG_OK;
+    PlaneSet ps;
+    PG_TRY(build_planes(ctx, order, lo, hi, ps));
+    const size_t per_batch = 65535;
+    PG_TRY(ctx->misc.ensure((size_t)(n_ind + 1) * 4 + 64));
+    PG_CUDA(cudaMemcpyAsync(ctx->misc.p, ind_start.data(), (size_t)(n_ind + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    for (size_t b0 = 0; b0 < wins.size(); b0 += per_batch) {
+        const size_t nb = std::min(per_batch, wins.size() - b0);
+        std::vector<int64_t> blo(nb), bhi(nb);
+        for (size_t k = 0; k < nb; ++k) {
+            blo[k] = ctx->win_lo[wins[b0 + k]];
+            bhi[k] = ctx->win_hi[wins[b0 + k]];
+        }
+        PG_TRY(ctx->misc3.ensure(nb * 16 + 64));
+        PG_TRY(ctx->out_d.ensure(nb * (size_t)n_ind * 8 + 64));
+        int64_t* d_lo = (int64_t*)ctx->misc3.p;
+        int64_t* d_hi = d_lo + nb;
+        PG_CUDA(cudaMemcpyAsync(d_lo, blo.data(), nb * 8, cudaMemcpyHostToDevice, ctx->stream));
+        PG_CUDA(cudaMemcpyAsync(d_hi, bhi.data(), nb * 8, cudaMemcpyHostToDevice, ctx->stream));
+        HetParams hp;
+        hp.planes = ps.planes;
+        hp.Hk = ps.Hk;
+        hp.NWp = ps.NWp;
+        hp.site_base = ps.site_base;
+        hp.win_lo = d_lo;
+        hp.win_hi = d_hi;
+        hp.ind_start = (const int32_t*)ctx->misc.p;
+        hp.n_ind = n_ind;
+        hp.min_sites = min_sites;
+        hp.out = (double*)ctx->out_d.p;
+        const int ti = pg_time_begin(ctx, "k2_het");
+        k2_het<<<dim3((unsigned)n_ind, (unsigned)nb), 128, 0, ctx->stream>>>(hp);
+        pg_time_end(ctx, ti);
+        PG_CUDA(cudaGetLastError());
+        PG_TRY(copy_rows_back(ctx, wins, b0, nb, (const double*)ctx->out_d.p, het, (size_t)n_ind));
+    }
+    return PG_OK;
+}
+
+// Alignment.H12stats(maxDist) (genomics.py:1079-1098) for every window and population of pg_set_pops:
+// out [W x P x 3] = H1, H12, H2.  min_sites / diag_nan describe what earlier analyses of the same window did to the
+// reference's cached distance matrix (popgenWindows.py:50-64): groupDistStats masks n_ij < minSites and the diagonal
+// in place, indPairDists masks the diagonal.
+extern "C" int pg_hapstats(pg_ctx* ctx, double max_dist, int32_t min_sites, int32_t diag_nan, double* out) {
+    PG_CHECK(ctx && out, "pg_hapstats: null argument");
+    PG_CHECK(ctx->P >= 1, "pg_hapstats: call pg_set_pops first");
+    PG_CHECK(ctx->P <= PG_MAX_POPS, "pg_hapstats: P=%d > %d populations", ctx->P, PG_MAX_POPS);
+    PG_CUDA(cudaSetDevice(ctx->device));
+    pg_timings_reset(ctx);
+    const int64_t W = ctx->W;
+    const int P = ctx->P;
+    if (W == 0) return PG_OK;
+    std::vector<int32_t> order;
+    std::vector<int32_t> pop_start(P + 1, 0);
+    int maxN = 0;
+    for (int X = 0; X < P; ++X) {
+        pop_start[X] = (int32_t)order.size();
+        for (int h = 0; h < ctx->H; ++h)
+            if (ctx->hap_pop[h] == X) order.push_back(h);
+        maxN = std::max(maxN, (int)order.size() - pop_start[X]);
+        PG_CHECK((int)order.size() > pop_start[X], "pg_hapstats: population %d has no haplotypes", X);
+    }
+    pop_start[P] = (int32_t)order.size();
+    const size_t smem = (size_t)maxN * ((maxN + 31) / 32) * 4 + (size_t)((maxN + 31) / 32) * 4 + (size_t)maxN * 4 + 64;
+    PG_CHECK(smem <= 200 * 1024, "pg_hapstats: a population of %d haplotypes is too large for the clustering kernel", maxN);
+    for (size_t k = 0; k < (size_t)W * P * 3; ++k) out[k] = NAN;
+    std::vector<int64_t> wins;
+    int64_t lo, hi;
+    nonempty_windows(ctx, wins, lo, hi);
+    if (wins.empty()) return PG_OK;
+    PlaneSet ps;
+    PG_TRY(build_planes(ctx, order, lo, hi, ps));
+    const size_t HH = (size_t)ps.Hk * ps.Hk;
+    const size_t per_batch = std::max<size_t>(1, std::min<size_t>(pair_budget_bytes() / (HH * 8), 65535));
+    PG_TRY(ctx->misc.ensure((size_t)(P + 1) * 4 + 64));
+    PG_CUDA(cudaMemcpyAsync(ctx->misc.p, pop_start.data(), (size_t)(P + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    PG_CUDA(cudaFuncSetAttribute(k2_hap_epi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (size_t b0 = 0; b0 < wins.size(); b0 += per_batch) {
+        const size_t nb = std::min(per_batch, wins.size() - b0);
+        std::vector<int64_t> blo(nb), bhi(nb);
+        for (size_t k = 0; k < nb; ++k) {
+            blo[k] = ctx->win_lo[wins[b0 + k]];
+            bhi[k] = ctx->win_hi[wins[b0 + k]];
+        }
+        int32_t *d_diff = nullptr, *d_n = nullptr;
+        PG_TRY(run_pair_batch(ctx, ps, blo, bhi, &d_diff, &d_n));
+        PG_TRY(ctx->out_d.ensure(nb * (size_t)P * 24 + 64));
+        HapEpiParams ep;
+        ep.diff = d_diff;
+        ep.n = d_n;
+        ep.mid = ps.d_mid;
+        ep.Hm = ps.Hm;
+        ep.Hk = ps.Hk;
+        ep.P = P;
+        ep.pop_start = (const int32_t*)ctx->misc.p;
+        ep.min_sites = min_sites;
+        ep.diag_nan = diag_nan ? 1 : 0;
+        ep.max_dist = max_dist;
+        ep.out = (double*)ctx->out_d.p;
+        const int ti = pg_time_begin(ctx, "k2_hap_epi");
+        k2_hap_epi<<<dim3((unsigned)P, (unsigned)nb), 256, smem, ctx->stream>>>(ep);
+        pg_time_end(ctx, ti);
+        PG_CUDA(cudaGetLastError());
+        PG_TRY(copy_rows_back(ctx, wins, b0, nb, (const double*)ctx->out_d.p, out, (size_t)P * 3));
+    }
     return PG_OK;
 }

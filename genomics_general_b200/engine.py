@@ -208,8 +208,20 @@ class Engine:
         check(self._lib.pg_site_counts(self._ctx, int(site0), n, _ptr(out)), "pg_site_counts")
         return out
 
-    def pairdist(self, hap_ind, n_ind: int, include_same_with_same: bool = False):
-        """-> dict(dist [W,n_ind,n_ind], sites [W], pos_sum [W])."""
+    def site_target_freqs(self, target: str, site0: int = 0, n: int | None = None, min_data: float = 0.0,
+                          as_counts: bool = False):
+        """freq.py --target derived|minor -> (values float64 [n,P], tie bool [n])."""
+        n = self.S - site0 if n is None else n
+        out = np.empty((n, self.P), dtype=np.float64)
+        tie = np.zeros(n, dtype=np.uint8)
+        code = {"derived": 1, "minor": 2}[target]
+        check(self._lib.pg_site_target_freqs(self._ctx, int(site0), int(n), code, float(min_data), 1 if as_counts else 0,
+                                             _ptr(out), _ptr(tie)), "pg_site_target_freqs")
+        return out, tie.astype(bool)
+
+    def pairdist(self, hap_ind, n_ind: int, include_same_with_same: bool = False, min_sites: int = 0):
+        """-> dict(dist [W,n_ind,n_ind], sites [W], pos_sum [W]).  min_sites > 0 masks haplotype pairs with fewer
+        jointly non-missing sites (what an earlier groupDistStats does to the reference's cached matrix)."""
         hap_ind = np.ascontiguousarray(hap_ind, dtype=np.int32)
         assert hap_ind.shape == (self.H,)
         W = self.W
@@ -217,8 +229,23 @@ class Engine:
         sites = np.empty(W, dtype=np.int64)
         pos_sum = np.empty(W, dtype=np.int64)
         check(self._lib.pg_pairdist(self._ctx, int(n_ind), _ptr(hap_ind), 1 if include_same_with_same else 0,
-                                    _ptr(dist), _ptr(sites), _ptr(pos_sum)), "pg_pairdist")
+                                    int(min_sites or 0), _ptr(dist), _ptr(sites), _ptr(pos_sum)), "pg_pairdist")
         return dict(dist=dist, sites=sites, pos_sum=pos_sum)
+
+    def ind_het(self, hap_ind, n_ind: int, min_sites: int = 0):
+        """Alignment.sampleHet() per window -> [W, n_ind]."""
+        hap_ind = np.ascontiguousarray(hap_ind, dtype=np.int32)
+        assert hap_ind.shape == (self.H,)
+        het = np.empty((self.W, n_ind), dtype=np.float64)
+        check(self._lib.pg_ind_het(self._ctx, int(n_ind), _ptr(hap_ind), int(min_sites or 0), _ptr(het)), "pg_ind_het")
+        return het
+
+    def hapstats(self, max_dist: float = 0.0, min_sites: int = 0, diag_nan: bool = False):
+        """Alignment.H12stats(maxDist) per window -> [W, P, 3] = H1, H12, H2."""
+        out = np.empty((self.W, self.P, 3), dtype=np.float64)
+        check(self._lib.pg_hapstats(self._ctx, float(max_dist), int(min_sites or 0), 1 if diag_nan else 0, _ptr(out)),
+              "pg_hapstats")
+        return out
 
     def pair_counts(self, window: int):
         """(diff, n) int32 [H,H] of one window (Alignment.distMatrix / pairNonNan numerators)."""

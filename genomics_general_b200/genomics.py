@@ -189,6 +189,9 @@ class Alignment:
         self._uploaded = False
         self._distMat_ = None
         self._pairNonNan_ = None
+        # what the reference's analyses did IN PLACE to its cached distance matrix (genomics.py:959-963, 940)
+        self._masked_min_sites = 0
+        self._diag_nan = False
         self.groupIndDict = {}
         for n, g in zip(self.names, self.groups):
             for gg in (g if isinstance(g, (tuple, list)) else [g]):
@@ -292,6 +295,8 @@ class Alignment:
         eng = self._engine()
         eng.set_pops(hp, len(pops))
         r = eng.popgen(minSites if minSites else 0, minData)
+        self._masked_min_sites = max(self._masked_min_sites, int(minSites or 0))
+        self._diag_nan = True
         out = {}
         for x, p in enumerate(pops):
             out["pi_" + str(p)] = float(r["pi"][0, x])
@@ -308,10 +313,37 @@ class Alignment:
         samples = list(dict.fromkeys(self.sampleNames.tolist()))
         hap_ind = np.array([samples.index(s) for s in self.sampleNames], dtype=np.int32)
         eng = self._engine()
-        m = eng.pairdist(hap_ind, len(samples), includeSameWithSame)["dist"][0]
+        self._masked_min_sites = max(self._masked_min_sites, int(minSites or 0))
+        m = eng.pairdist(hap_ind, len(samples), includeSameWithSame or False, min_sites=self._masked_min_sites)["dist"][0]
+        if not includeSameWithSame:
+            self._diag_nan = True
         if not asDict:
             return m
         return {a: {b: m[i, j] for j, b in enumerate(samples)} for i, a in enumerate(samples)}
+
+    def sampleHet(self, sampleNames=None, asList=False, minSites=None):
+        """genomics.py:918-929, operator-precedence quirk included (value iff exactly two haplotypes and bit 1 of
+        n_ij set).  Only the default minSites (None -> 1) has that simple closed form and is supported."""
+        if minSites not in (None, 1):
+            raise NotImplementedError("sampleHet(minSites=...) other than the default is not implemented")
+        samples = list(dict.fromkeys(self.sampleNames.tolist()))
+        hap_ind = np.array([samples.index(s) for s in self.sampleNames], dtype=np.int32)
+        het = self._engine().ind_het(hap_ind, len(samples), min_sites=self._masked_min_sites)[0]
+        if sampleNames is not None:
+            het = np.array([het[samples.index(s)] for s in sampleNames])
+            samples = list(sampleNames)
+        return dict(zip(samples, het.tolist())) if not asList else het.tolist()
+
+    def H12stats(self, maxDist=0):
+        """genomics.py:1079-1098 -> dict H1_X, H12_X, H2_X."""
+        pops, hp = self._pop_index()
+        eng = self._engine()
+        eng.set_pops(hp, len(pops))
+        r = eng.hapstats(maxDist, min_sites=self._masked_min_sites, diag_nan=self._diag_nan)[0]
+        out = {}
+        for x, p in enumerate(pops):
+            out["H1_" + str(p)], out["H12_" + str(p)], out["H2_" + str(p)] = (float(v) for v in r[x])
+        return out
 
 
 def genoToAlignment(seqDict, sampleData=None, genoFormat="diplo", positions=None):

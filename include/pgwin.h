@@ -98,10 +98,33 @@ int pg_abbababa(pg_ctx* ctx, int32_t p1, int32_t p2, int32_t p3, int32_t o, doub
  * counts uint16 [n x P x 4] (A,C,G,T) for sites site0 .. site0+n-1. */
 int pg_site_counts(pg_ctx* ctx, int64_t site0, int64_t n, uint16_t* counts);
 
-/* Replaces Alignment.indPairDists (genomics.py:934-954) as used by distMat.py:42-45.
- * hap_ind[h] = individual index in [0,n_ind) or -1; dist [W x n_ind x n_ind]; n_sites/pos_sum [W]. */
+/* Replaces freq.py --target derived|minor (freq.py:62-92; derivedAllele / minorAllele genomics.py:636-668):
+ * out double [n x P] = frequency (count/non-missing; nan = no value) or, with as_counts, count (0 = no value) of the
+ * target allele in each population.  target 1 = derived (the LAST population is the outgroup), 2 = minor allele over
+ * all populations' haplotypes.  min_data is compared with the population's non-missing COUNT, as the reference does
+ * (freq.py:79).  The reference draws at random when the two alleles are exactly tied (genomics.py:667): here the
+ * lower allele is used and tie[s] = 1 (tie may be NULL).  Values are not rounded (freq.py:91 rounds to 4 dp). */
+int pg_site_target_freqs(pg_ctx* ctx, int64_t site0, int64_t n, int32_t target, double min_data, int32_t as_counts,
+                         double* out, uint8_t* tie);
+
+/* Replaces Alignment.indPairDists (genomics.py:934-954) as used by distMat.py:42-45 and popgenWindows.py:54-57.
+ * hap_ind[h] = individual index in [0,n_ind) or -1; dist [W x n_ind x n_ind]; n_sites/pos_sum [W] (may be NULL).
+ * min_sites > 0: haplotype pairs with n_ij < min_sites are nan — the state of the reference's cached matrix when
+ * groupDistStats ran earlier on the same window (it masks in place, genomics.py:959-961); 0 = no mask (distMat.py). */
 int pg_pairdist(pg_ctx* ctx, int32_t n_ind, const int32_t* hap_ind, int32_t include_same_with_same,
-                double* dist, int64_t* n_sites, int64_t* pos_sum);
+                int32_t min_sites, double* dist, int64_t* n_sites, int64_t* pos_sum);
+
+/* Replaces Alignment.sampleHet() (genomics.py:918-929; popgenWindows.py:59-61 --analysis indHet): het [W x n_ind] =
+ * p-distance between the two haplotypes of each individual; nan unless the individual has exactly two haplotypes
+ * and bit 1 of n_ij is set (the reference's `len(x)==2 & n >= 1` is the chained comparison len(x) == (2 & n) >= 1).
+ * min_sites as in pg_pairdist. */
+int pg_ind_het(pg_ctx* ctx, int32_t n_ind, const int32_t* hap_ind, int32_t min_sites, double* het);
+
+/* Replaces Alignment.H12stats(maxDist) + distMat_to_cluster_sizes (genomics.py:1079-1098, 1239-1261;
+ * popgenWindows.py:63-64 --analysis hapStats): out [W x P x 3] = H1, H12, H2 for the populations of pg_set_pops.
+ * min_sites as in pg_pairdist; diag_nan != 0 when an earlier groupDistStats / indPairDists of the same window set
+ * the cached matrix's diagonal to nan (963, 940), which removes the self-matches from the greedy clustering. */
+int pg_hapstats(pg_ctx* ctx, double max_dist, int32_t min_sites, int32_t diag_nan, double* out);
 
 /* Replaces Alignment.distMatrix + pairNonNan (genomics.py:907-916, 1042-1047) for ONE window:
  * diff, n int32 [H x H] (symmetric, diagonal: diff 0, n = non-missing sites of the haplotype). */

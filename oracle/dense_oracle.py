@@ -239,6 +239,144 @@ def ind_pair_dists(g, hap_ind, n_ind, include_same_with_same=False, min_sites=No
 
 
 # ----------------------------------------------------------------------------------------
+# sampleHet  (genomics.py:918-929) as called by popgenWindows.py:59-61 (no arguments)
+# ----------------------------------------------------------------------------------------
+def _masked_dist(g, masked_min_sites=None, diag_nan=False):
+    """The state of Alignment._distMat_ inside one popgenWindows worker call: distMatrix()
+    (zero diagonal, 907-916); an earlier groupDistStats in the same window has set entries with
+    n_ij < minSites to nan IN PLACE (959-961) and the diagonal to nan (963); an earlier
+    indPairDists has set the diagonal to nan (940)."""
+    diff, n = pair_counts(g)
+    d = dist_matrix(diff, n)
+    if masked_min_sites:
+        nn = n.copy()
+        np.fill_diagonal(nn, 0)
+        d[nn < masked_min_sites] = np.nan
+    if diag_nan:
+        np.fill_diagonal(d, np.nan)
+    return d, n
+
+
+def sample_het(g, hap_ind, n_ind, masked_min_sites=None):
+    """het[a] for each individual.  The reference's condition (924, 927)
+
+        len(x)==2 & np.sum(mask_i & mask_j) >= _minSites        (_minSites = 1)
+
+    parses as the chained comparison  len(x) == (2 & n_ij) >= 1 : the value is d_ij iff the
+    individual has exactly two haplotypes AND bit 1 of n_ij is set, else nan.  Kept as is."""
+    hap_ind = np.asarray(hap_ind)
+    d, n = _masked_dist(g, masked_min_sites)
+    out = np.full(n_ind, np.nan)
+    for a in range(n_ind):
+        x = np.where(hap_ind == a)[0]
+        if len(x) == 2 and (2 & int(n[x[0], x[1]])) == 2:
+            out[a] = d[x[0], x[1]]
+    return out
+
+
+# ----------------------------------------------------------------------------------------
+# H12stats  (genomics.py:1079-1098) + distMat_to_cluster_sizes (1239-1261)
+# ----------------------------------------------------------------------------------------
+def cluster_sizes(match):
+    """Greedy clustering, restated step by step (1239-1261): take the row with the most matches
+    (first one on ties, np.argmax); if it has more than one match its matches form a cluster and
+    are removed (the row itself stays when the diagonal does not match, i.e. was nan); otherwise
+    every remaining entry is a cluster of one."""
+    match = np.asarray(match, dtype=bool)
+    alive = np.ones(match.shape[0], dtype=bool)
+    sizes = []
+    while alive.any():
+        idx = np.where(alive)[0]
+        sub = match[np.ix_(idx, idx)]
+        cnt = sub.sum(axis=1)
+        k = int(cnt.argmax())
+        m = int(cnt[k])
+        if m > 1:
+            sizes.append(m)
+            alive[idx[sub[k]]] = False
+        else:
+            sizes += [1] * len(idx)
+            break
+    return sizes
+
+
+def h12_stats(g, hap_pop, n_pops, max_dist=0.0, masked_min_sites=None, diag_nan=False):
+    """[P,3] = H1, H12, H2 per population.  ``masked_min_sites`` / ``diag_nan`` describe what
+    earlier analyses of the same window did to the cached matrix (see _masked_dist)."""
+    hap_pop = np.asarray(hap_pop)
+    d, _ = _masked_dist(g, masked_min_sites, diag_nan)
+    out = np.full((n_pops, 3), np.nan)
+    for x in range(n_pops):
+        idx = np.where(hap_pop == x)[0]
+        with np.errstate(invalid="ignore"):
+            match = d[np.ix_(idx, idx)] <= max_dist                            # nan <= x is False (1244)
+        cs = np.array(cluster_sizes(match))
+        f = cs / cs.sum()
+        H1 = float((f ** 2).sum())
+        if len(f) > 1:
+            H12 = H1 + 2 * f[0] * f[1]
+            H2 = float((f[1:] ** 2).sum())
+        else:
+            H12, H2 = H1, 0.0
+        out[x] = (H1, H12, H2)
+    return out
+
+
+# ----------------------------------------------------------------------------------------
+# freq.py --target derived | minor  (freq.py:62-92; genomics.py:636-668)
+# ----------------------------------------------------------------------------------------
+def target_freqs(g, hap_pop, n_pops, target, min_data=0.0, as_counts=False, threshold=None):
+    """float64 [L,P] (nan = no value; counts mode: 0).  ``target``: "derived" (last population is
+    the outgroup: the in-group allele that is not the outgroup's, when the in-group has exactly two
+    alleles and the outgroup exactly one of them, 654-655) or "minor" (the rarer of exactly two
+    alleles over all haplotypes that belong to a population; the reference picks at random on a
+    tie (667) — here ties give -1 in the second return value so that callers can skip them).
+    Returns (values, tie[L] bool).  Values are NOT rounded (freq.py:91 rounds to 4 dp)."""
+    c = site_counts(g, hap_pop, n_pops)                                        # [L,P,4]
+    L = c.shape[0]
+    tgt = np.full(L, -1, dtype=np.int64)
+    tie = np.zeros(L, dtype=bool)
+    if target == "derived":
+        cin = c[:, :-1, :].sum(axis=1)
+        cout = c[:, -1, :]
+        for s in range(L):
+            ia = np.where(cin[s] > 0)[0]
+            oa = np.where(cout[s] > 0)[0]
+            if len(oa) == 1 and len(ia) == 2 and oa[0] in ia:
+                tgt[s] = ia[ia != oa[0]][0]
+    elif target == "minor":
+        tot = c.sum(axis=1)
+        for s in range(L):
+            al = np.where(tot[s] > 0)[0]
+            if len(al) == 2:
+                if tot[s, al[0]] == tot[s, al[1]]:
+                    tie[s] = True
+                else:
+                    tgt[s] = al[np.argmin(tot[s, al])]
+    else:
+        raise ValueError(target)
+    nk = c.sum(axis=2)                                                         # [L,P]
+    out = np.zeros((L, n_pops)) if as_counts else np.full((L, n_pops), np.nan)
+    for s in range(L):
+        if tgt[s] < 0:
+            continue
+        for x in range(n_pops):
+            if not (nk[s, x] >= min_data):                                     # siteNonNan() >= minData: a COUNT (freq.py:79)
+                continue
+            if as_counts:
+                out[s, x] = c[s, x, tgt[s]]
+            else:
+                out[s, x] = c[s, x, tgt[s]] / nk[s, x] if nk[s, x] > 0 else np.nan
+    if threshold and not as_counts:                                            # 96-98
+        r = np.around(out, 4)                                                  # the comparison sees the rounded value (91)
+        hi = r >= threshold
+        lo = r < threshold
+        out[hi] = 1
+        out[lo] = 0
+    return out, tie
+
+
+# ----------------------------------------------------------------------------------------
 # per-site counts  (genomics.py:1049-1052 siteFreqs, 592-599 binBaseFreqs, 1032-1036)
 # ----------------------------------------------------------------------------------------
 def site_counts(g, hap_pop, n_pops):
@@ -313,6 +451,84 @@ def abbababa(g, hap_pop, P1, P2, P3, O, min_data):
         fdm = _f4(p1, p2, p3, p4).sum() * 1.0 / _f4(pdm1, pdm2, pdm3, p4).sum()  # 1470-1475
     return dict(D=float(D), fd=float(fd), fdM=float(fdm), ABBA=float(abba.sum()),
                 BABA=float(baba.sum()), sitesUsed=int(len(p1)))
+
+
+# ----------------------------------------------------------------------------------------
+# fourPop  (genomics.py:1585-1643; statistics 1409-1583)
+# ----------------------------------------------------------------------------------------
+FOURPOP_KEYS = ('fhom', "fhom'", 'D', 'fd', "fd'", 'fdm', "fdm'", 'fdh', 'fdh2', 'fh', "ABBA", "BABA", "ABAA", "BAAA",
+                "sitesUsed")
+
+
+def _f4c(p1, p2, p3, p4):                                                      # 1413-1418
+    return _f4(p1, p2, p3, p4) + _f4(1 - p1, 1 - p2, 1 - p3, 1 - p4)
+
+
+def four_pop_sites(g, hap_pop, P1, P2, P3, P4, min_data, polarize=False, fixed=False):
+    """(p1,p2,p3,p4) of every (site, allele) the reference selects (1595-1621), n_good_sites."""
+    hap_pop = np.asarray(hap_pop)
+    c = site_counts(g, hap_pop, max(P1, P2, P3, P4) + 1)[:, [P1, P2, P3, P4], :]
+    N = np.array([(hap_pop == x).sum() for x in (P1, P2, P3, P4)], dtype=np.float64)
+    nk = c.sum(axis=2)
+    tot = c.sum(axis=1)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        good = np.where(((tot > 0).sum(axis=1) == 2) & np.all(nk * 1.0 / N[None, :] >= min_data, axis=1))[0]
+        freqs = c[good].astype(np.float64) / nk[good].astype(np.float64)[:, :, None]
+        allf = tot[good] / tot[good].sum(axis=1, keepdims=True)
+    if polarize:
+        hs, ha = np.where((allf > 0) & (freqs[:, 3, :] == 0))
+    elif fixed:
+        fx = lambda f: (f == 0) | (f == 1)   # noqa: E731
+        hs, ha = np.where((allf > 0) & (freqs[:, 3, :] == 0) & fx(freqs[:, 0, :]) & fx(freqs[:, 1, :]) & fx(freqs[:, 2, :]))
+    else:
+        hs = np.arange(len(good))
+        ha = np.argsort(allf, axis=1, kind="stable")[:, 2] if len(good) else np.zeros(0, dtype=np.int64)   # 1615
+    return freqs[hs, 0, ha], freqs[hs, 1, ha], freqs[hs, 2, ha], freqs[hs, 3, ha], len(good)
+
+
+def four_pop(g, hap_pop, P1, P2, P3, P4, min_data, polarize=False, fixed=False):
+    p1, p2, p3, p4, n_good = four_pop_sites(g, hap_pop, P1, P2, P3, P4, min_data, polarize, fixed)
+    if n_good < 1:
+        return dict(zip(FOURPOP_KEYS, [NAN] * 14 + [0]))                      # 1641-1643
+    with np.errstate(divide="ignore", invalid="ignore"):
+        abba = (1 - p1) * p2 * p3 * (1 - p4)
+        baba = p1 * (1 - p2) * p3 * (1 - p4)
+        f4 = _f4(p1, p2, p3, p4)
+        f4c = _f4c(p1, p2, p3, p4)
+        pd = p2 * (p2 > p3) + p3 * (p3 >= p2)
+        a = p3 > p1
+        b = p3 > p2
+        x = p1 > p2
+        y = ~x
+        pdm1 = p3 * (x & a) + p1 * (~(x & a))
+        pdm2 = p3 * (y & b) + p2 * (~(y & b))
+        pdm3 = -p3 * (x & a) + p3 * (y & b) - p1 * (x & ~a) + p2 * (y & ~b)
+        t11 = _f4c(p1, p3, p3, p4)
+        t12 = _f4c(p4, p2, p3, p4)
+        t21 = _f4c(p3, p2, p3, p4)
+        t22 = _f4c(p1, p4, p3, p4)
+        t31 = _f4c(p1, p2, p2, p4)
+        t32 = _f4c(p1, p2, p3, p1)
+        t41 = _f4c(p1, p2, p1, p4)
+        t42 = _f4c(p1, p2, p3, p2)
+        u1 = np.abs(p1 - p2)
+        u2 = np.abs(p3 - p4)
+        vals = [
+            f4.sum() * 1. / _f4(p1, p3, p3, p4).sum(),                                              # fhom_old 1420
+            f4c.sum() * 1. / t11.sum(),                                                             # fhom_new 1423
+            f4.sum() * 1. / (abba + baba).sum(),                                                    # D 1430
+            f4.sum() * 1. / _f4(p1, pd, pd, p4).sum(),                                              # fd 1445
+            f4c.sum() * 1. / _f4c(p1, pd, pd, p4).sum(),                                            # fd_new 1450
+            f4.sum() * 1. / _f4(pdm1, pdm2, pdm3, p4).sum(),                                        # fdm 1470
+            f4c.sum() * 1. / _f4c(pdm1, pdm2, pdm3, p4).sum(),                                      # fdm_new 1476
+            f4c.sum() * 1. / np.amax([t11, t12, t21, t22], axis=0).sum() if len(p1) else NAN,       # fdh 1488
+            f4c.sum() * 1. / np.amax([t11, t12, t21, t22, t31, t32, t41, t42], axis=0).sum() if len(p1) else NAN,
+            f4c.sum() * 1. / ((u1 * (u1 > u2) + u2 * (u2 >= u1)) ** 2).sum(),                       # fh 1527
+            abba.sum(), baba.sum(),
+            ((1 - p1) * p2 * (1 - p3) * (1 - p4)).sum(),                                            # ABAA 1558
+            (p1 * (1 - p2) * (1 - p3) * (1 - p4)).sum(),                                            # BAAA 1561
+            len(p1)]
+    return dict(zip(FOURPOP_KEYS, [float(v) for v in vals]))
 
 
 # ----------------------------------------------------------------------------------------

@@ -1,0 +1,236 @@
+"""GPU parity tests, second batch (pytest -m gpu): sampleHet, H12stats, freq.py --target columns and the masked
+indPairDists through the C-ABI, against fixtures produced by the unmodified reference (oracle/make_golden2.py) and
+against the oracle on seeded inputs.  Integer-derived outputs bit-exact; doubles at 1e-9 (contract 1e-6)."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from helpers import GOLDEN, assert_close
+
+pytestmark = pytest.mark.gpu
+
+META = json.load(open(os.path.join(GOLDEN, "window_cases2.json")))
+ARR = np.load(os.path.join(GOLDEN, "window_cases2.npz"))
+IDS = [m["name"] for m in META]
+CLI2 = json.load(open(os.path.join(GOLDEN, "cli_cases2.json")))
+TOL = dict(rtol=1e-9, atol=1e-12)
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from genomics_general_b200.engine import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def _load(eng, m, key="__g_aln"):
+    g = ARR[m["name"] + key]
+    hp = ARR[m["name"] + "__hap_pop"]
+    L = g.shape[0]
+    eng.upload(g, np.arange(1, L + 1, dtype=np.int32))
+    eng.set_pops(hp, len(m["pop_names"]))
+    eng.set_windows([0], [L])
+    return g, hp, L
+
+
+def _hap_ind(m):
+    idx = {n: k for k, n in enumerate(m["sample_names"])}
+    return np.array([idx[s] for s in m["hap_samples"]], dtype=np.int32)
+
+
+@pytest.mark.parametrize("m", META, ids=IDS)
+def test_ind_het_golden(eng, m):
+    from oracle import dense_oracle as do
+    g, hp, L = _load(eng, m)
+    hi = _hap_ind(m)
+    n = len(m["sample_names"])
+    for key, masked in (("alone", 0), ("after_popDist", m["minSites"]), ("after_indPairDist", 0)):
+        got = eng.ind_het(hi, n, min_sites=masked)[0]
+        assert_close(got, do.sample_het(g, hi, n, masked_min_sites=masked or None), "oracle " + key, **TOL)
+        if m["sampleHet"]:
+            want = np.array([m["sampleHet"][key][s] for s in m["sample_names"]])
+            assert_close(got, want, key, **TOL)
+
+
+@pytest.mark.parametrize("m", META, ids=IDS)
+def test_hapstats_golden(eng, m):
+    g, hp, L = _load(eng, m)
+    for key, want in m["H12stats"].items():
+        state, md = key.rsplit("_", 1)
+        masked = m["minSites"] if state == "after_popDist" else 0
+        got = eng.hapstats(float(md), min_sites=masked, diag_nan=(state != "alone"))[0]
+        for x, pn in enumerate(m["pop_names"]):
+            assert_close(got[x], [want["H1_" + pn], want["H12_" + pn], want["H2_" + pn]], key + " " + pn, **TOL)
+
+
+@pytest.mark.parametrize("m", META, ids=IDS)
+def test_pairdist_masked_matches_oracle(eng, m):
+    from oracle import dense_oracle as do
+    g, hp, L = _load(eng, m)
+    hi = _hap_ind(m)
+    n = len(m["sample_names"])
+    for ms in (0, m["minSites"], L + 1):
+        got = eng.pairdist(hi, n, False, min_sites=ms)["dist"][0]
+        assert_close(got, do.ind_pair_dists(g, hi, n, False, min_sites=ms or None), "min_sites=%d" % ms, **TOL)
+
+
+@pytest.mark.parametrize("m", META, ids=IDS)
+def test_target_freqs_golden(eng, m):
+    g, hp, L = _load(eng, m)
+    for target in ("derived", "minor"):
+        for md in (0.0, 3.0):
+            for asCounts in (False, True):
+                want = ARR["%s__tf_%s_%g_%d" % (m["name"], target, md, int(asCounts))]
+                got, tie = eng.site_target_freqs(target, 0, L, min_data=md, as_counts=asCounts)
+                if target == "minor":
+                    gold_tie = ARR[m["name"] + "__minor_tie"]
+                    assert np.array_equal(tie, gold_tie)
+                    got, want = got[~gold_tie], want[~gold_tie]     # the reference draws at random on ties
+                assert got.shape == want.shape
+                assert np.array_equal(np.isnan(got), np.isnan(want))
+                assert np.array_equal(got[~np.isnan(got)], want[~np.isnan(want)]), (target, md, asCounts)   # bit-exact
+
+
+def test_hapstats_and_het_many_windows_vs_oracle(eng):
+    """Seeded low-diversity data, several windows (word-edge clipping), interleaved populations."""
+    from oracle import dense_oracle as do
+    rng = np.random.default_rng(99)
+    L, H = 1000, 44
+    hap_pop = np.repeat(rng.permutation(np.repeat([0, 1, 2, -1], [7, 8, 5, 2])), 2).astype(np.int32)
+    base = rng.integers(0, 4, L)
+    g = np.repeat(base[:, None], H, axis=1).astype(np.int8)
+    mut = rng.random((L, H)) < 0.004
+    g[mut] = (g[mut] + 1) % 4
+    # copies of haplotypes -> real clusters
+    for a, b in ((0, 5), (0, 9), (3, 20), (21, 33), (21, 40), (21, 41)):
+        g[:, b] = g[:, a]
+    g[rng.random((L, H)) < 0.03] = -1
+    eng.upload(g, np.arange(1, L + 1, dtype=np.int32))
+    eng.set_pops(hap_pop, 3)
+    lo = np.array([0, 37, 300, 640, 999], dtype=np.int64)
+    hi = np.array([37, 300, 640, 1000, 1000], dtype=np.int64)
+    eng.set_windows(lo, hi)
+    hap_ind = (np.arange(H) // 2).astype(np.int32)
+    for md, ms, dn in ((0.0, 0, False), (0.0, 30, True), (0.01, 0, True), (0.02, 250, True)):
+        got = eng.hapstats(md, min_sites=ms, diag_nan=dn)
+        het = eng.ind_het(hap_ind, H // 2, min_sites=ms)
+        for w in range(len(lo)):
+            want = do.h12_stats(g[lo[w]:hi[w]], hap_pop, 3, md, ms or None, dn)
+            assert_close(got[w], want, "h12 w%d md=%g ms=%d" % (w, md, ms), **TOL)
+            assert_close(het[w], do.sample_het(g[lo[w]:hi[w]], hap_ind, H // 2, ms or None), "het w%d" % w, **TOL)
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def inputs2(tmp_path_factory):
+    from genomics_general_b200 import synth
+    d = tmp_path_factory.mktemp("cli2")
+    c = CLI2["four_pops"]["cfg"]
+    spec = synth.SynthSpec(c["n_pops"], c["spp"], seed=c["seed"], miss=c["miss"])
+    g = synth.synth_genotypes(spec, 0, c["S"])
+    nsc = c["scaffolds"]
+    per = c["S"] // nsc
+    scafs, pos = [], []
+    for k in range(nsc):
+        n = per if k < nsc - 1 else c["S"] - per * (nsc - 1)
+        scafs += ["chr%d" % (k + 1)] * n
+        pos.append(synth.synth_positions(n, seed=c["seed"] + k))
+    path = str(d / "four_pops.geno")
+    synth.write_geno(path, g, np.concatenate(pos), scafs, spec.sample_names())
+    pops = str(d / "four_pops.pops")
+    with open(pops, "wt") as f:
+        for i, n in enumerate(spec.sample_names()):
+            f.write("%s pop%d\n" % (n, i // c["spp"]))
+    popargs = []
+    for p in spec.pop_names():
+        popargs += ["-p", p]
+    return dict(geno=path, pops=pops, popargs=popargs, dir=str(d))
+
+
+def _table(text):
+    lines = text.strip("\n").split("\n")
+    hdr = lines[0].split(",")
+    return hdr, [dict(zip(hdr, l.split(","))) for l in lines[1:]]
+
+
+def _compare_by_column(ours, ref, n_prefix=5, atol=2e-8):
+    """The reference's indHet column order is that of a Python set: compare by column name."""
+    h1, r1 = _table(ours)
+    h2, r2 = _table(ref)
+    assert sorted(h1) == sorted(h2)
+    assert len(r1) == len(r2)
+    for a, b in zip(r1, r2):
+        for k in h2[:n_prefix]:
+            assert a[k] == b[k], (k, a[k], b[k])
+        keys = h2[n_prefix:]
+        assert_close([float(a[k]) for k in keys], [float(b[k]) for k in keys], "row " + a["start"], rtol=1e-6, atol=atol)
+
+
+@pytest.mark.parametrize("key,extra", [
+    ("popgen_indHet_alone", ["--windType", "sites", "-w", "300", "-m", "290", "--analysis", "indHet"]),
+    ("popgen_popDist_indHet_hapStats", ["--windType", "sites", "-w", "300", "-m", "290", "--analysis", "popDist", "indHet",
+                                        "hapStats", "--hapDist", "0.05"]),
+    ("popgen_hapStats_alone", ["-w", "20000", "-m", "50", "--analysis", "hapStats", "--hapDist", "0.08"]),
+    ("popgen_indPairDist_hapStats_indHet", ["-w", "20000", "-m", "50", "--analysis", "indPairDist", "hapStats", "indHet",
+                                            "--hapDist", "0.08"]),
+])
+def test_popgenWindows_more_analyses_cli(inputs2, key, extra):
+    from genomics_general_b200.cli import popgenWindows
+    i = inputs2
+    o = os.path.join(i["dir"], key + ".csv")
+    popgenWindows.main(["-g", i["geno"], "-o", o, "-f", "phased", "-T", "1", "--popsFile", i["pops"], "--roundTo", "8"]
+                       + extra + i["popargs"])
+    _compare_by_column(open(o).read(), CLI2["four_pops"][key])
+
+
+@pytest.mark.parametrize("key,extra", [
+    ("freq_derived", ["--target", "derived"]),
+    ("freq_derived_counts", ["--target", "derived", "--asCounts"]),
+    ("freq_derived_keepnan_mindata", ["--target", "derived", "--keepNanLines", "--minData", "11"]),
+    ("freq_derived_threshold", ["--target", "derived", "--threshold", "0.5"]),
+])
+def test_freq_target_cli_bit_exact(inputs2, key, extra):
+    from genomics_general_b200.cli import freq
+    i = inputs2
+    o = os.path.join(i["dir"], key + ".tsv")
+    freq.main(["-g", i["geno"], "-o", o, "-f", "phased", "-t", "1", "--popsFile", i["pops"]] + extra + i["popargs"])
+    txt = open(o).read().splitlines()
+    res = CLI2["four_pops"]
+    assert txt[:300] == res[key + "_head"]
+    assert len(txt) == res[key + "_nlines"]
+    assert hashlib.sha256(("\n".join(txt) + "\n").encode()).hexdigest() == res[key + "_sha256"]
+
+
+@pytest.mark.parametrize("m", [m for m in META if m["sampleHet"]], ids=[m["name"] for m in META if m["sampleHet"]])
+def test_alignment_api_cache_states(m):
+    """genomics-compatible Alignment: sampleHet / H12stats after groupDistStats see the in-place masked matrix."""
+    import warnings
+    from genomics_general_b200 import genomics as G
+    g = ARR[m["name"] + "__g_aln"]
+    hp = ARR[m["name"] + "__hap_pop"]
+    groups = [m["pop_names"][x] if x >= 0 else None for x in hp]
+
+    def new():
+        return G.Alignment(g, names=m["hap_names"], groups=groups, sampleNames=m["hap_samples"])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        a = new()
+        het = a.sampleHet()
+        assert_close([het[s] for s in m["sample_names"]], [m["sampleHet"]["alone"][s] for s in m["sample_names"]], "alone", **TOL)
+        h = a.H12stats(maxDist=0.02)
+        assert_close([h[k] for k in sorted(h)], [m["H12stats"]["alone_0.02"][k] for k in sorted(h)], "h12 alone", **TOL)
+        a = new()
+        a.groupDistStats(doPairs=True, minSites=m["minSites"], minData=0.01)
+        het = a.sampleHet()
+        assert_close([het[s] for s in m["sample_names"]], [m["sampleHet"]["after_popDist"][s] for s in m["sample_names"]],
+                     "after_popDist", **TOL)
+        h = a.H12stats(maxDist=0.02)
+        assert_close([h[k] for k in sorted(h)], [m["H12stats"]["after_popDist_0.02"][k] for k in sorted(h)], "h12 masked", **TOL)
+        a = new()
+        a.indPairDists()
+        h = a.H12stats(maxDist=0.1)
+        assert_close([h[k] for k in sorted(h)], [m["H12stats"]["after_indPairDist_0.1"][k] for k in sorted(h)], "h12 diag", **TOL)

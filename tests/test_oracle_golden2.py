@@ -1,0 +1,90 @@
+"""The oracle's restatements of sampleHet / H12stats / fourPop / freq.py --target against fixtures produced by the
+reference itself (oracle/make_golden2.py).  CPU only."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import dense_oracle as do
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+META = json.load(open(os.path.join(GOLD, "window_cases2.json")))
+ARR = np.load(os.path.join(GOLD, "window_cases2.npz"))
+IDS = [m["name"] for m in META]
+
+
+def hap_ind_of(m):
+    """individual index (file sample order) of each alignment haplotype"""
+    idx = {n: k for k, n in enumerate(m["sample_names"])}
+    return np.array([idx[s] for s in m["hap_samples"]], dtype=np.int32)
+
+
+@pytest.mark.parametrize("m", META, ids=IDS)
+def test_sample_het(m):
+    if not m["sampleHet"]:
+        pytest.skip("reference raises for haploid samples")
+    g = ARR[m["name"] + "__g_aln"]
+    hi = hap_ind_of(m)
+    n = len(m["sample_names"])
+    for key, masked in (("alone", None), ("after_popDist", m["minSites"]), ("after_indPairDist", None)):
+        got = do.sample_het(g, hi, n, masked_min_sites=masked)
+        want = np.array([m["sampleHet"][key][s] for s in m["sample_names"]])
+        np.testing.assert_allclose(got, want, rtol=1e-12, atol=0, equal_nan=True, err_msg=key)
+
+
+@pytest.mark.parametrize("m", META, ids=IDS)
+def test_h12(m):
+    g = ARR[m["name"] + "__g_aln"]
+    hp = ARR[m["name"] + "__hap_pop"]
+    P = len(m["pop_names"])
+    for key, want in m["H12stats"].items():
+        state, md = key.rsplit("_", 1)
+        masked = m["minSites"] if state == "after_popDist" else None
+        diag = state != "alone"
+        got = do.h12_stats(g, hp, P, max_dist=float(md), masked_min_sites=masked, diag_nan=diag)
+        for x, pn in enumerate(m["pop_names"]):
+            for k, stat in enumerate(("H1", "H12", "H2")):
+                np.testing.assert_allclose(got[x, k], want[stat + "_" + pn], rtol=1e-12, atol=1e-15,
+                                           err_msg="%s %s %s" % (key, stat, pn))
+
+
+@pytest.mark.parametrize("m", [m for m in META if "fourPop" in m], ids=[m["name"] for m in META if "fourPop" in m])
+def test_four_pop(m):
+    hp = ARR[m["name"] + "__hap_pop"]
+    for key, want in m["fourPop"].items():
+        # default mode: fixtures were made on the input with exactly-tied sites blanked (see make_golden2.py)
+        g = ARR[m["name"] + ("__g_aln_notie" if key.startswith(("default", "perm")) else "__g_aln")]
+        if key.startswith("perm"):
+            sel, md, kw = (2, 0, 1, 3), 0.4, {}
+        else:
+            mode, md = key.rsplit("_", 1)
+            sel, md, kw = (0, 1, 2, 3), float(md), ({} if mode == "default" else {mode: True})
+        got = do.four_pop(g, hp, *sel, md, **kw)
+        for k in do.FOURPOP_KEYS:
+            np.testing.assert_allclose(got[k], want[k], rtol=1e-10, atol=1e-14, equal_nan=True, err_msg="%s %s" % (key, k))
+
+
+@pytest.mark.parametrize("m", META, ids=IDS)
+def test_target_freqs(m):
+    g = ARR[m["name"] + "__g_aln"]
+    hp = ARR[m["name"] + "__hap_pop"]
+    P = len(m["pop_names"])
+    for target in ("derived", "minor"):
+        for md in (0.0, 3.0):
+            for asCounts in (False, True):
+                want = ARR["%s__tf_%s_%g_%d" % (m["name"], target, md, int(asCounts))]
+                got, tie = do.target_freqs(g, hp, P, target, min_data=md, as_counts=asCounts)
+                if target == "minor":
+                    assert np.array_equal(tie, ARR[m["name"] + "__minor_tie"])
+                np.testing.assert_allclose(got, want, rtol=1e-15, atol=0, equal_nan=True,
+                                           err_msg="%s %g %d" % (target, md, asCounts))
+
+
+def test_sample_het_quirk_is_exercised():
+    """Some diploid individual with data must come out nan because bit 1 of n_ij is clear (genomics.py:924)."""
+    seen = False
+    for m in META:
+        if m["sampleHet"]:
+            seen |= bool(np.isnan([m["sampleHet"]["alone"][s] for s in m["sample_names"]]).any())
+    assert seen
