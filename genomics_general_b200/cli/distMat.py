@@ -74,7 +74,11 @@ def main(argv=None):
     with Engine(args.device) as eng:
         eng.upload(gd.geno, gd.pos)
         eng.set_windows(lo, hi)
-        r = eng.pairdist(hap_ind, nInd, args.includeSameWithSame)
+        if args.windType == "cat":
+            dcat, ntot = eng.pairdist_cat(hap_ind, nInd, args.includeSameWithSame)      # chunked over the site axis
+            r = dict(dist=dcat[None], sites=np.array([ntot], dtype=np.int64), pos_sum=np.zeros(1, dtype=np.int64))
+        else:
+            r = eng.pairdist(hap_ind, nInd, args.includeSameWithSame)
         per_ind_ok = np.ones(len(ws), dtype=bool)
         if args.minPerInd:
             csum = np.concatenate([np.zeros((1, gd.n_haps), dtype=np.int64), np.cumsum(gd.geno >= 0, axis=0, dtype=np.int64)])

@@ -1,0 +1,87 @@
+#!/usr/bin/env python
+"""Drop-in for the reference's fourPopWindows.py (flags 107-150, header 245-250, worker 27-52), on the GPU.
+(The reference script itself stops on numpy >= 2 at its `np.NaN`, fourPopWindows.py:36; genomics.fourPop runs.)"""
+from __future__ import annotations
+
+import argparse
+import sys
+
+import numpy as np
+
+from .. import genomics
+from ..engine import Engine
+from . import _common as C
+
+STATS = ["ABBA", "BABA", "ABAA", "BAAA", "D", "fd", "fd'", "fdm", "fdm'", "fdh", "fdh2", "fh"]     # fourPopWindows.py:248
+
+
+def build_parser():
+    p = argparse.ArgumentParser()
+    C.add_window_args(p, overlap_short=False)        # -O is the outgroup here
+    p.add_argument("--minData", help="Min proportion of samples genotped per site", type=float, default=0.01,
+                   metavar="proportion")
+    for flag, long in (("-P1", "--pop1"), ("-P2", "--pop2"), ("-P3", "--pop3"), ("-O", "--outgroup")):
+        p.add_argument(flag, long, help="Pop name and optionally sample names (separated by commas)", required=True,
+                       nargs="+", metavar=("popName", "[samples]"))
+    p.add_argument("--popsFile", help="Optional file of sample names and populations")
+    p.add_argument("--ploidy", type=int, nargs="+")
+    p.add_argument("--ploidyFile")
+    p.add_argument("--haploid", metavar="sample names")
+    p.add_argument("--inferPloidy", action="store_true")
+    p.add_argument("--polarize", help="Ensure outgroup is fixed for ancestral allele", action="store_true")
+    p.add_argument("--fixed", help="Only count fixed SNPs", action="store_true")
+    p.add_argument("-g", "--genoFile")
+    p.add_argument("-o", "--outFile")
+    p.add_argument("--exclude")
+    p.add_argument("--include")
+    p.add_argument("-f", "--genoFormat", choices=("phased", "pairs", "haplo", "diplo"), required=True)
+    p.add_argument("--header")
+    p.add_argument("-T", "--Threads", type=int, default=1, metavar="threads")
+    p.add_argument("--verbose", action="store_true")
+    p.add_argument("--addWindowID", action="store_true")
+    p.add_argument("--writeFailedWindows", action="store_true")
+    C.add_engine_args(p)
+    return p
+
+
+def main(argv=None):
+    args = build_parser().parse_args(argv)
+    minSites, coords = C.check_window_args(args, with_id=True)
+    assert 0 <= args.minData <= 1, "minimum data per site must be between 0 and 1."
+    popNames, popInds = C.parse_pop_args([args.pop1, args.pop2, args.pop3, args.outgroup], args.popsFile)
+    allInds = sorted(set(i for p in popInds for i in p))
+    ploidyDict = C.ploidy_dict(args, allInds, args.haploid.split(",") if args.haploid else None)
+    sampleData = genomics.SampleData(indNames=allInds, popNames=popNames, popInds=popInds, ploidyDict=ploidyDict)
+    out = C.open_out(args.outFile)
+    out.write(",".join((["windowID"] if args.addWindowID else []) + ["scaffold", "start", "end", "mid", "sites", "sitesUsed"]
+                       + STATS) + "\n")
+    gd = C.load_geno(args, sampleData.indNames, ploidyDict, header=args.header)
+    ws = C.make_windows(args, gd, minSites, coords, C.read_scaffold_list(args.include), C.read_scaffold_list(args.exclude))
+    lo, hi = ws.ranges()
+    written = 0
+    with Engine(args.device) as eng:
+        eng.upload(gd.geno, gd.pos)
+        eng.set_windows(lo, hi)
+        eng.set_pops(C.hap_pop_vector(gd, popNames, popInds), 4)
+        r = eng.fourpop(0, 1, 2, 3, args.minData, polarize=args.polarize, fixed=args.fixed)
+    for k in range(len(ws)):
+        pre = C.window_prefix(args, ws, k, gd, r["sites"][k], r["pos_sum"][k])
+        sitesUsed = np.nan
+        good = False
+        vals = [np.nan] * len(STATS)
+        if pre[4] >= minSites:
+            sitesUsed = int(r["sitesUsed"][k])
+            if sitesUsed >= minSites:
+                good = True
+                vals = [round(np.float64(r[s][k]), 4) for s in STATS]
+        if good or args.writeFailedWindows:
+            row = ([] if not args.addWindowID else [ws.ID[k]]) + pre + [sitesUsed] + vals
+            out.write(",".join(str(x) for x in row) + "\n")
+            written += 1
+    if out is not sys.stdout:
+        out.close()
+    sys.stderr.write("%d windows were tested.\n%d results were written.\n" % (len(ws), written))
+
+
+if __name__ == "__main__":
+    main()

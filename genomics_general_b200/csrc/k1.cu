@@ -24,7 +24,7 @@ namespace {
 // consumer warps per CTA (+ one TMA producer warp): 8, or 12 where the register budget allows (65536 / 13 / 32 = 157)
 constexpr int K1_MAX_WARPS = 12;
 
-enum { MODE_POPGEN = 0, MODE_ABBA = 1, MODE_COUNTS = 2, MODE_POPGEN_FREQ = 3 };   // FREQ = POPGEN + popFreq counters
+enum { MODE_POPGEN = 0, MODE_ABBA = 1, MODE_COUNTS = 2, MODE_POPGEN_FREQ = 3, MODE_FOURPOP = 4 };   // FREQ = POPGEN + popFreq counters
 
 struct K1Params {
     const uint8_t* geno;
@@ -44,8 +44,9 @@ struct K1Params {
     const int32_t* cta_seg_first;
     const int64_t* cta_slot_off;
     unsigned long long* part;
-    // ABBA: minimum non-missing count per population (exact integer form of n/N >= minData)
+    // ABBA / FOURPOP: minimum non-missing count per population (exact integer form of n/N >= minData)
     int thr[4];
+    int variant;             // FOURPOP allele choice: 0 = third of argsort (the rarer allele), 1 = polarize, 2 = fixed
     // COUNTS
     uint16_t* counts_out;
     int64_t counts_stride;   // uint16 elements per site
@@ -209,6 +210,20 @@ template <int P>
 struct ModeTraits<MODE_COUNTS, P> {
     static constexpr int QI = 0, QD = 0;
 };
+template <int P>
+struct ModeTraits<MODE_FOURPOP, P> {
+    static constexpr int QI = 3, QD = 16;
+};
+
+// genomics.py:1409-1418, operation order of the reference's numpy expressions
+__device__ __forceinline__ double f4_dev(double p1, double p2, double p3, double p4) {
+    return (1 - p1) * p2 * p3 * (1 - p4) - p1 * (1 - p2) * p3 * (1 - p4);
+}
+__device__ __forceinline__ double f4c_dev(double p1, double p2, double p3, double p4) {
+    return f4_dev(p1, p2, p3, p4) + f4_dev(1 - p1, 1 - p2, 1 - p3, 1 - p4);
+}
+// np.amax propagates nan
+__device__ __forceinline__ double nmax(double a, double b) { return (a != a) ? a : ((b != b) ? b : (a > b ? a : b)); }
 
 template <int MODE, int P, int NW>
 __global__ void __launch_bounds__((NW + 1) * 32, 1) k1_site_pass(const __grid_constant__ K1Params prm) {
@@ -451,6 +466,88 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k1_site_pass(const __grid_co
                     acc.d[5] += fdm_den;
                 }
             }
+
+            if (MODE == MODE_FOURPOP) {
+                // genomics.py:1595-1603: biallelic over P1+P2+P3+P4 and enough data in each population
+                uint32_t tot[4];
+                int nall = 0;
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    tot[a] = c[0][a] + c[1][a] + c[2][a] + c[3][a];
+                    nall += tot[a] > 0 ? 1 : 0;
+                }
+                bool good = owner && (nall == 2);
+#pragma unroll
+                for (int X = 0; X < 4; ++X) good = good && ((int)n[X] >= prm.thr[X]);
+                acc.i[1] += good ? 1 : 0;
+                acc.i[2] += (long long)posv;
+                int da = -1;
+                if (prm.variant == 0) {
+                    // np.argsort(all4freqs)[:,2] (1615): of the two alleles present, the rarer one; an exact tie is
+                    // resolved by numpy's sort implementation in the reference — here the lower allele index
+                    uint32_t best = 0xffffffffu;
+#pragma unroll
+                    for (int a = 3; a >= 0; --a)
+                        if (tot[a] > 0 && tot[a] <= best) {
+                            best = tot[a];
+                            da = a;
+                        }
+                } else {
+                    // polarize (1610): present overall, absent in P4 (needs data in P4: nan == 0 is False)
+#pragma unroll
+                    for (int a = 0; a < 4; ++a)
+                        if (tot[a] > 0 && c[3][a] == 0) da = a;
+                    if (n[3] == 0) da = -1;
+                }
+                bool hit = good && da >= 0;
+                const uint32_t k1 = da == 0 ? c[0][0] : (da == 1 ? c[0][1] : (da == 2 ? c[0][2] : c[0][3]));
+                const uint32_t k2 = da == 0 ? c[1][0] : (da == 1 ? c[1][1] : (da == 2 ? c[1][2] : c[1][3]));
+                const uint32_t k3 = da == 0 ? c[2][0] : (da == 1 ? c[2][1] : (da == 2 ? c[2][2] : c[2][3]));
+                const uint32_t k4 = da == 0 ? c[3][0] : (da == 1 ? c[3][1] : (da == 2 ? c[3][2] : c[3][3]));
+                if (prm.variant == 2)       // fixed (1611-1614): frequency exactly 0 or 1 in P1, P2, P3 (nan fails both)
+                    hit = hit && n[0] > 0 && n[1] > 0 && n[2] > 0 && (k1 == 0 || k1 == n[0]) && (k2 == 0 || k2 == n[1]) &&
+                          (k3 == 0 || k3 == n[2]);
+                if (hit) {
+                    const double p1 = (double)k1 / (double)n[0];      // 0/0 = nan, as in the reference (genomics.py:597)
+                    const double p2 = (double)k2 / (double)n[1];
+                    const double p3 = (double)k3 / (double)n[2];
+                    const double p4 = (double)k4 / (double)n[3];
+                    const double abba = (1 - p1) * p2 * p3 * (1 - p4);
+                    const double baba = p1 * (1 - p2) * p3 * (1 - p4);
+                    const double pd = p2 * (p2 > p3 ? 1.0 : 0.0) + p3 * (p3 >= p2 ? 1.0 : 0.0);
+                    const bool A = p3 > p1, Bq = p3 > p2, Xq = p1 > p2, Yq = !Xq;
+                    const double xa = (Xq && A) ? 1.0 : 0.0, yb = (Yq && Bq) ? 1.0 : 0.0;
+                    const double xna = (Xq && !A) ? 1.0 : 0.0, ynb = (Yq && !Bq) ? 1.0 : 0.0;
+                    const double pdm1 = p3 * xa + p1 * (1.0 - xa);
+                    const double pdm2 = p3 * yb + p2 * (1.0 - yb);
+                    const double pdm3 = -p3 * xa + p3 * yb - p1 * xna + p2 * ynb;
+                    const double t11 = f4c_dev(p1, p3, p3, p4), t12 = f4c_dev(p4, p2, p3, p4);
+                    const double t21 = f4c_dev(p3, p2, p3, p4), t22 = f4c_dev(p1, p4, p3, p4);
+                    const double t31 = f4c_dev(p1, p2, p2, p4), t32 = f4c_dev(p1, p2, p3, p1);
+                    const double t41 = f4c_dev(p1, p2, p1, p4), t42 = f4c_dev(p1, p2, p3, p2);
+                    const double m4 = nmax(nmax(t11, t12), nmax(t21, t22));
+                    const double m8 = nmax(nmax(m4, nmax(t31, t32)), nmax(t41, t42));
+                    const double u1 = fabs(p1 - p2), u2 = fabs(p3 - p4);
+                    const double um = u1 * (u1 > u2 ? 1.0 : 0.0) + u2 * (u2 >= u1 ? 1.0 : 0.0);
+                    acc.i[0] += 1;
+                    acc.d[0] += f4_dev(p1, p2, p3, p4);
+                    acc.d[1] += f4_dev(p1, p3, p3, p4);
+                    acc.d[2] += f4c_dev(p1, p2, p3, p4);
+                    acc.d[3] += t11;
+                    acc.d[4] += abba + baba;
+                    acc.d[5] += f4_dev(p1, pd, pd, p4);
+                    acc.d[6] += f4c_dev(p1, pd, pd, p4);
+                    acc.d[7] += f4_dev(pdm1, pdm2, pdm3, p4);
+                    acc.d[8] += f4c_dev(pdm1, pdm2, pdm3, p4);
+                    acc.d[9] += m4;
+                    acc.d[10] += m8;
+                    acc.d[11] += um * um;
+                    acc.d[12] += abba;
+                    acc.d[13] += baba;
+                    acc.d[14] += (1 - p1) * p2 * (1 - p3) * (1 - p4);
+                    acc.d[15] += p1 * (1 - p2) * (1 - p3) * (1 - p4);
+                }
+            }
         }
 
         __syncwarp();
@@ -621,6 +718,32 @@ __global__ void __launch_bounds__(64) k1_finalize(const __grid_constant__ FinPar
                     fst_o[k] = 1 - pi_s / pi_t;
                     ++k;
                 }
+        } else if (MODE == MODE_FOURPOP) {
+            // genomics.py:1623-1643: [fhom, fhom', D, fd, fd', fdm, fdm', fdh, fdh2, fh, ABBA, BABA, ABAA, BAAA, sitesUsed]
+            const long long used = (long long)sums[0], n_good = (long long)sums[1];
+            double* o = reinterpret_cast<double*>(rec + 2);
+            if (n_good < 1) {
+                for (int k = 0; k < 14; ++k) o[k] = nan_d();
+                o[14] = 0.0;
+                continue;
+            }
+            double d[16];
+            for (int k = 0; k < 16; ++k) d[k] = __longlong_as_double((long long)sums[3 + k]);
+            o[0] = d[0] * 1. / d[1];
+            o[1] = d[2] * 1. / d[3];
+            o[2] = d[0] * 1. / d[4];
+            o[3] = d[0] * 1. / d[5];
+            o[4] = d[2] * 1. / d[6];
+            o[5] = d[0] * 1. / d[7];
+            o[6] = d[2] * 1. / d[8];
+            o[7] = d[2] * 1. / d[9];
+            o[8] = d[2] * 1. / d[10];
+            o[9] = d[2] * 1. / d[11];
+            o[10] = d[12];
+            o[11] = d[13];
+            o[12] = d[14];
+            o[13] = d[15];
+            o[14] = (double)used;
         } else {   // MODE_ABBA
             const long long used = (long long)sums[0], n_good = (long long)sums[1];
             double* o = reinterpret_cast<double*>(rec + 2);
@@ -944,7 +1067,7 @@ void fill_fin(FinParams& fp, pg_ctx* ctx, const K1Cache& c, int Q, int QI) {
 }  // namespace
 
 void pg_k1_cache_free(pg_ctx* ctx) {
-    for (int k = 0; k < 2; ++k)
+    for (int k = 0; k < 3; ++k)
         if (ctx->k1_cache[k]) {
             K1Cache* c = static_cast<K1Cache*>(ctx->k1_cache[k]);
             c->tables.release();
@@ -1225,6 +1348,84 @@ extern "C" int pg_abbababa(pg_ctx* ctx, int32_t p1, int32_t p2, int32_t p3, int3
         pos_sum[w] = (int64_t)r[1];
         memcpy(out + (size_t)w * 5, r + 2, 40);
         memcpy(sites_used + w, r + 7, 8);
+    }
+    return PG_OK;
+}
+
+// ================================================================================================
+// pg_fourpop
+// ================================================================================================
+extern "C" int pg_fourpop(pg_ctx* ctx, int32_t p1, int32_t p2, int32_t p3, int32_t p4, double min_data, int32_t mode,
+                          double* out, double* sites_used, int64_t* n_sites, int64_t* pos_sum) {
+    PG_CHECK(ctx && out && sites_used && n_sites && pos_sum, "pg_fourpop: null argument");
+    PG_CHECK(ctx->P >= 1, "pg_fourpop: call pg_set_pops first");
+    PG_CHECK(mode >= 0 && mode <= 2, "pg_fourpop: mode must be 0 (default), 1 (polarize) or 2 (fixed)");
+    const int sel[4] = {p1, p2, p3, p4};
+    for (int k = 0; k < 4; ++k) {
+        PG_CHECK(sel[k] >= 0 && sel[k] < ctx->P, "pg_fourpop: population index %d out of range", sel[k]);
+        for (int j = 0; j < k; ++j) PG_CHECK(sel[j] != sel[k], "pg_fourpop: populations must be distinct");
+    }
+    PG_CUDA(cudaSetDevice(ctx->device));
+    pg_timings_reset(ctx);
+    const int64_t W = ctx->W;
+    if (W == 0) return PG_OK;
+    if (ctx->S == 0) {
+        for (int64_t w = 0; w < W; ++w) {
+            n_sites[w] = 0;
+            pos_sum[w] = 0;
+            sites_used[w] = 0.0;
+            for (int k = 0; k < 14; ++k) out[w * 14 + k] = NAN;
+        }
+        return PG_OK;
+    }
+    const int Q = 19, RC = 17;
+    K1Cache& c = *cache_of(ctx, 2);
+    if (!c.valid || c.epoch != ctx->epoch || memcmp(c.sel, sel, sizeof(sel)) != 0) {
+        c.valid = false;
+        std::vector<int32_t> local(ctx->H, -1);
+        for (int h = 0; h < ctx->H; ++h)
+            for (int k = 0; k < 4; ++k)
+                if (ctx->hap_pop[h] == sel[k]) local[h] = k;
+        PG_TRY(prepare_windowed(ctx, c, local, 4, Q, nw_for<MODE_FOURPOP, 4>()));
+        for (int k = 0; k < 4; ++k) PG_CHECK(c.pt.popN[k] >= 1, "pg_fourpop: population %d has no haplotypes", sel[k]);
+        memcpy(c.sel, sel, sizeof(sel));
+        c.epoch = ctx->epoch;
+        c.valid = true;
+    }
+    for (int k = 0; k < 4; ++k) {
+        int thr = c.pt.popN[k] + 1;       // smallest n with (double)n / N >= minData (genomics.py:1597-1600)
+        for (int n = 0; n <= c.pt.popN[k]; ++n)
+            if ((double)n * 1.0 / (double)c.pt.popN[k] >= min_data) {
+                thr = n;
+                break;
+            }
+        c.L.prm.thr[k] = thr;
+    }
+    c.L.prm.variant = mode;
+    PG_TRY(arm_slots(ctx, c));
+    PG_TRY((launch_site_pass<MODE_FOURPOP, 4>(ctx, c.L, "k1_fourpop")));
+    PG_TRY(ctx->out_d.ensure((size_t)W * RC * 8 + 64));
+    FinParams fp;
+    fill_fin(fp, ctx, c, Q, 3);
+    fp.P = 4;
+    fp.Ppad = 4;
+    fp.rec = (unsigned long long*)ctx->out_d.p;
+    fp.RC = RC;
+    const int ti = pg_time_begin(ctx, "k1_finalize");
+    k1_finalize<MODE_FOURPOP><<<(unsigned)std::min<int64_t>(W, 65535), 64, 0, ctx->stream>>>(fp);
+    pg_time_end(ctx, ti);
+    PG_CUDA(cudaGetLastError());
+    void* hp = nullptr;
+    PG_TRY(pg_pinned(ctx, (size_t)W * RC * 8 + 64, &hp));
+    const unsigned long long* hrec = (const unsigned long long*)hp;
+    PG_CUDA(cudaMemcpyAsync(hp, ctx->out_d.p, (size_t)W * RC * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    PG_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int64_t w = 0; w < W; ++w) {
+        const unsigned long long* r = hrec + (size_t)w * RC;
+        n_sites[w] = (int64_t)r[0];
+        pos_sum[w] = (int64_t)r[1];
+        memcpy(out + (size_t)w * 14, r + 2, 14 * 8);
+        memcpy(sites_used + w, r + 16, 8);
     }
     return PG_OK;
 }

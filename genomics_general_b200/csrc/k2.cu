@@ -682,6 +682,57 @@ __global__ void __launch_bounds__(256) k2_hap_epi(const __grid_constant__ HapEpi
     }
 }
 
+// ---- `--windType cat` (distMat.py:303-314): one window = every site; pair counts add over chunks and ranks -----
+// acc [2][Hk][Hk] int64 (diff, then n expanded from the unique-mask matrix) += sum over the nb chunk matrices
+__global__ void __launch_bounds__(256) k2_reduce_pairs(const int32_t* __restrict__ diff, const int32_t* __restrict__ n,
+                                                       const int32_t* __restrict__ mid, int Hk, int Hm, int nb,
+                                                       long long* __restrict__ acc) {
+    const size_t HH = (size_t)Hk * Hk, MM = (size_t)Hm * Hm;
+    for (size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x; idx < HH; idx += (size_t)gridDim.x * 256) {
+        const int i = (int)(idx / Hk), j = (int)(idx % Hk);
+        const size_t nidx = (size_t)mid[i] * Hm + mid[j];
+        long long sd = 0, sn = 0;
+        for (int b = 0; b < nb; ++b) {
+            sd += diff[(size_t)b * HH + idx];
+            sn += n[(size_t)b * MM + nidx];
+        }
+        acc[idx] += sd;
+        acc[HH + idx] += sn;
+    }
+}
+
+struct IndEpi64Params {
+    const long long* acc;       // [2][Hk][Hk]
+    int Hk, n_ind;
+    const int32_t* ind_start;
+    int include_same;
+    double* out;                // [n_ind x n_ind]
+};
+__global__ void __launch_bounds__(256) k2_ind_epi64(const __grid_constant__ IndEpi64Params ep) {
+    const size_t HH = (size_t)ep.Hk * ep.Hk;
+    const int64_t total = (int64_t)ep.n_ind * ep.n_ind;
+    for (int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * 256) {
+        const int a = (int)(idx / ep.n_ind), b = (int)(idx % ep.n_ind);
+        double s = 0.0;
+        int c = 0;
+        for (int i = ep.ind_start[a]; i < ep.ind_start[a + 1]; ++i)
+            for (int j = ep.ind_start[b]; j < ep.ind_start[b + 1]; ++j) {
+                double d;
+                if (i == j) {
+                    if (!ep.include_same) continue;
+                    d = 0.0;
+                } else {
+                    const long long nij = ep.acc[HH + (size_t)i * ep.Hk + j];
+                    if (nij == 0) continue;
+                    d = (double)ep.acc[(size_t)i * ep.Hk + j] / (double)nij;
+                }
+                s += d;
+                c += 1;
+            }
+        ep.out[idx] = c ? s / (double)c : nan_d();
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host orchestration
 // ------------------------------------------------------------------------------------------------
@@ -1182,5 +1233,82 @@ extern "C" int pg_hapstats(pg_ctx* ctx, double max_dist, int32_t min_sites, int3
         PG_CUDA(cudaGetLastError());
         PG_TRY(copy_rows_back(ctx, wins, b0, nb, (const double*)ctx->out_d.p, out, (size_t)P * 3));
     }
+    return PG_OK;
+}
+
+// distMat.py --windType cat (distMat.py:303-314: parseGenoFile -> ONE window over every site): dist [n_ind x n_ind].
+// The uploaded sites are this rank's shard of the window: they are cut into chunks (so that the pair kernel fills the
+// GPU), the chunk matrices are summed as int64, and — when a communicator is set (pg_nccl_init) — ONE ncclAllReduce
+// adds the ranks' matrices and site counts before the division.  *total_sites = sites over all ranks.
+extern "C" int pg_pairdist_cat(pg_ctx* ctx, int32_t n_ind, const int32_t* hap_ind, int32_t include_same_with_same,
+                               double* dist, int64_t* total_sites) {
+    PG_CHECK(ctx && hap_ind && dist, "pg_pairdist_cat: null argument");
+    PG_CHECK(n_ind >= 1, "pg_pairdist_cat: n_ind must be >= 1");
+    PG_CHECK(ctx->H > 0, "pg_pairdist_cat: upload genotypes first");
+    PG_CUDA(cudaSetDevice(ctx->device));
+    pg_timings_reset(ctx);
+    std::vector<int32_t> order, ind_start(n_ind + 1, 0);
+    for (int h = 0; h < ctx->H; ++h)
+        PG_CHECK(hap_ind[h] >= -1 && hap_ind[h] < n_ind, "pg_pairdist_cat: hap_ind[%d]=%d out of range", h, hap_ind[h]);
+    for (int a = 0; a < n_ind; ++a) {
+        ind_start[a] = (int32_t)order.size();
+        for (int h = 0; h < ctx->H; ++h)
+            if (hap_ind[h] == a) order.push_back(h);
+    }
+    ind_start[n_ind] = (int32_t)order.size();
+    const int Hk = (int)order.size();
+    PG_CHECK(Hk >= 1, "pg_pairdist_cat: no haplotypes selected");
+    const size_t HH = (size_t)Hk * Hk;
+    const size_t nn = (size_t)n_ind * n_ind;
+    // accumulator: diff | n | site count
+    PG_TRY(ctx->misc5.ensure((2 * HH + 1) * 8 + 64));
+    long long* d_acc = (long long*)ctx->misc5.p;
+    PG_CUDA(cudaMemsetAsync(d_acc, 0, (2 * HH + 1) * 8, ctx->stream));
+    const long long S_local = ctx->S;
+    PG_CUDA(cudaMemcpyAsync(d_acc + 2 * HH, &S_local, 8, cudaMemcpyHostToDevice, ctx->stream));
+    PG_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->S > 0) {
+        PlaneSet ps;
+        PG_TRY(build_planes(ctx, order, 0, ctx->S, ps));
+        const int64_t CH = 32768;                                  // sites per chunk (1024 plane words)
+        const int64_t nchunks = (ctx->S + CH - 1) / CH;
+        const size_t per_batch = std::max<size_t>(1, std::min<size_t>(pair_budget_bytes() / (HH * 8), 65535));
+        for (int64_t c0 = 0; c0 < nchunks; c0 += (int64_t)per_batch) {
+            const size_t nb = (size_t)std::min<int64_t>((int64_t)per_batch, nchunks - c0);
+            std::vector<int64_t> blo(nb), bhi(nb);
+            for (size_t k = 0; k < nb; ++k) {
+                blo[k] = (c0 + (int64_t)k) * CH;
+                bhi[k] = std::min<int64_t>(blo[k] + CH, ctx->S);
+            }
+            int32_t *d_diff = nullptr, *d_n = nullptr;
+            PG_TRY(run_pair_batch(ctx, ps, blo, bhi, &d_diff, &d_n));
+            const int ti = pg_time_begin(ctx, "k2_reduce_pairs");
+            k2_reduce_pairs<<<(unsigned)std::min<size_t>((HH + 255) / 256, 4096), 256, 0, ctx->stream>>>(d_diff, d_n, ps.d_mid, Hk,
+                                                                                                       ps.Hm, (int)nb, d_acc);
+            pg_time_end(ctx, ti);
+            PG_CUDA(cudaGetLastError());
+            PG_CUDA(cudaStreamSynchronize(ctx->stream));           // host vectors / scratch are reused by the next batch
+        }
+    }
+    if (ctx->nccl_comm && ctx->nccl_ranks > 1) PG_TRY(pg_nccl_allreduce_i64(ctx, d_acc, 2 * HH + 1));
+    PG_TRY(ctx->misc.ensure((size_t)(n_ind + 1) * 4 + 64));
+    PG_CUDA(cudaMemcpyAsync(ctx->misc.p, ind_start.data(), (size_t)(n_ind + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    PG_TRY(ctx->out_d.ensure(nn * 8 + 64));
+    IndEpi64Params ep;
+    ep.acc = d_acc;
+    ep.Hk = Hk;
+    ep.n_ind = n_ind;
+    ep.ind_start = (const int32_t*)ctx->misc.p;
+    ep.include_same = include_same_with_same ? 1 : 0;
+    ep.out = (double*)ctx->out_d.p;
+    const int ti = pg_time_begin(ctx, "k2_ind_epi");
+    k2_ind_epi64<<<(unsigned)std::min<size_t>((nn + 255) / 256, 1024), 256, 0, ctx->stream>>>(ep);
+    pg_time_end(ctx, ti);
+    PG_CUDA(cudaGetLastError());
+    long long tot = 0;
+    PG_CUDA(cudaMemcpyAsync(dist, ctx->out_d.p, nn * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    PG_CUDA(cudaMemcpyAsync(&tot, d_acc + 2 * HH, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    PG_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (total_sites) *total_sites = tot;
     return PG_OK;
 }

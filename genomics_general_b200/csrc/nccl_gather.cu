@@ -21,6 +21,7 @@ typedef void* NcclComm;
 typedef int (*fn_get_id)(NcclUniqueId*);
 typedef int (*fn_init_rank)(NcclComm*, int, NcclUniqueId, int);
 typedef int (*fn_all_gather)(const void*, void*, size_t, int, NcclComm, cudaStream_t);
+typedef int (*fn_all_reduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t);
 typedef int (*fn_destroy)(NcclComm);
 typedef const char* (*fn_errstr)(int);
 
@@ -29,6 +30,7 @@ struct NcclApi {
     fn_get_id get_id = nullptr;
     fn_init_rank init_rank = nullptr;
     fn_all_gather all_gather = nullptr;
+    fn_all_reduce all_reduce = nullptr;
     fn_destroy destroy = nullptr;
     fn_errstr errstr = nullptr;
 };
@@ -51,9 +53,11 @@ int load_nccl() {
     g_nccl.get_id = (fn_get_id)dlsym(h, "ncclGetUniqueId");
     g_nccl.init_rank = (fn_init_rank)dlsym(h, "ncclCommInitRank");
     g_nccl.all_gather = (fn_all_gather)dlsym(h, "ncclAllGather");
+    g_nccl.all_reduce = (fn_all_reduce)dlsym(h, "ncclAllReduce");
     g_nccl.destroy = (fn_destroy)dlsym(h, "ncclCommDestroy");
     g_nccl.errstr = (fn_errstr)dlsym(h, "ncclGetErrorString");
-    PG_CHECK(g_nccl.get_id && g_nccl.init_rank && g_nccl.all_gather && g_nccl.destroy, "NCCL symbols missing");
+    PG_CHECK(g_nccl.get_id && g_nccl.init_rank && g_nccl.all_gather && g_nccl.all_reduce && g_nccl.destroy,
+             "NCCL symbols missing");
     g_nccl.handle = h;
     return PG_OK;
 }
@@ -68,6 +72,8 @@ int load_nccl() {
     } while (0)
 
 constexpr int NCCL_UINT64 = 5;   // ncclUint64 in every NCCL 2.x
+constexpr int NCCL_INT64 = 4;    // ncclInt64
+constexpr int NCCL_SUM = 0;      // ncclSum
 
 }  // namespace
 
@@ -105,6 +111,15 @@ extern "C" int pg_nccl_finalize(pg_ctx* ctx) {
         g_nccl.destroy((NcclComm)ctx->nccl_comm);
         ctx->nccl_comm = nullptr;
     }
+    return PG_OK;
+}
+
+// In-place integer sum over the ranks, enqueued on the ctx stream (the one exchange of `--windType cat`: each rank
+// holds a shard of the SITES of the single window, the pair matrices add up).
+int pg_nccl_allreduce_i64(pg_ctx* ctx, void* d_buf, size_t count) {
+    PG_CHECK(ctx->nccl_comm != nullptr, "all-reduce: call pg_nccl_init first");
+    PG_NCCL(g_nccl.all_reduce(d_buf, d_buf, count, NCCL_INT64, NCCL_SUM, (NcclComm)ctx->nccl_comm, ctx->stream));
+    ctx->launches += 1;
     return PG_OK;
 }
 

@@ -99,14 +99,14 @@ struct pg_ctx {
     size_t events_used = 0;
     int64_t launches = 0;
     // scratch
-    PgBuf tables, part, segmeta, winmeta, out_d, out_i, planes, pairs, misc, misc2, misc3, misc4;
+    PgBuf tables, part, segmeta, winmeta, out_d, out_i, planes, pairs, misc, misc2, misc3, misc4, misc5;
     // upload pipeline: copy stream + two staging buffers
     cudaStream_t copy_stream = nullptr;
     PgBuf stage[2];
     cudaEvent_t stage_full[2] = {nullptr, nullptr}, stage_free[2] = {nullptr, nullptr};
     bool want_freq = false;                   // carry the popFreq counters in the popgen site pass
     uint64_t epoch = 1;                       // bumped by every change of data shape / populations / windows
-    void* k1_cache[2] = {nullptr, nullptr};   // cached launch state (popgen, abba) — owned by k1.cu
+    void* k1_cache[3] = {nullptr, nullptr, nullptr};   // cached launch state (popgen, abba, fourpop) — owned by k1.cu
     std::vector<unsigned long long> h_rec;    // host copy of the per-window records
     // native NCCL gather (nccl_gather.cu)
     void* nccl_comm = nullptr;
@@ -129,5 +129,6 @@ int pg_build_segments(pg_ctx* ctx);
 int pg_k2_popgen_windows(pg_ctx* ctx, const std::vector<int64_t>& wins, int32_t min_sites, double min_data,
                          void* d_rec, int RC);
 void pg_k1_cache_free(pg_ctx* ctx);
+int pg_nccl_allreduce_i64(pg_ctx* ctx, void* d_buf, size_t count);   // nccl_gather.cu
 int pg_popgen_enqueue(pg_ctx* ctx, int32_t min_sites, double min_data, int32_t force_path, void* d_rec, int** h_count);
 int pg_popgen_resolve(pg_ctx* ctx, int32_t min_sites, double min_data, void* d_rec, int nk2);

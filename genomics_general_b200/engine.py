@@ -177,6 +177,10 @@ class Engine:
         check(self._lib.pg_nccl_init(self._ctx, int(world), int(rank), buf), "pg_nccl_init")
         self._world, self._rank = int(world), int(rank)
 
+    def nccl_finalize(self):
+        check(self._lib.pg_nccl_finalize(self._ctx), "pg_nccl_finalize")
+        self._world, self._rank = 1, 0
+
     def popgen_allgather(self, w_max: int, table: np.ndarray, min_sites: int = 1, min_data: float = 0.01,
                          force_pairwise: bool = False) -> int:
         """Statistics of this rank's windows, then ONE ncclAllGather of every rank's records into `table`
@@ -200,6 +204,23 @@ class Engine:
                                     _ptr(pos_sum)), "pg_abbababa")
         return dict(ABBA=out[:, 0], BABA=out[:, 1], D=out[:, 2], fd=out[:, 3], fdM=out[:, 4], sitesUsed=used,
                     sites=sites, pos_sum=pos_sum)
+
+    FOURPOP_KEYS = ('fhom', "fhom'", 'D', 'fd', "fd'", 'fdm', "fdm'", 'fdh', 'fdh2', 'fh', "ABBA", "BABA", "ABAA", "BAAA")
+
+    def fourpop(self, p1: int, p2: int, p3: int, p4: int, min_data: float = 0.01, polarize: bool = False,
+                fixed: bool = False):
+        """genomics.fourPop per window -> dict(<14 statistics> [W], sitesUsed [W], sites, pos_sum)."""
+        W = self.W
+        out = np.empty((W, 14), dtype=np.float64)
+        used = np.empty(W, dtype=np.float64)
+        sites = np.empty(W, dtype=np.int64)
+        pos_sum = np.empty(W, dtype=np.int64)
+        mode = 1 if polarize else (2 if fixed else 0)          # genomics.py:1610-1615: polarize wins over fixed
+        check(self._lib.pg_fourpop(self._ctx, p1, p2, p3, p4, float(min_data), mode, _ptr(out), _ptr(used), _ptr(sites),
+                                   _ptr(pos_sum)), "pg_fourpop")
+        r = {k: out[:, i] for i, k in enumerate(self.FOURPOP_KEYS)}
+        r.update(sitesUsed=used, sites=sites, pos_sum=pos_sum)
+        return r
 
     def site_counts(self, site0: int = 0, n: int = None):
         """uint16 [n, P, 4] A,C,G,T counts per population."""
@@ -231,6 +252,17 @@ class Engine:
         check(self._lib.pg_pairdist(self._ctx, int(n_ind), _ptr(hap_ind), 1 if include_same_with_same else 0,
                                     int(min_sites or 0), _ptr(dist), _ptr(sites), _ptr(pos_sum)), "pg_pairdist")
         return dict(dist=dist, sites=sites, pos_sum=pos_sum)
+
+    def pairdist_cat(self, hap_ind, n_ind: int, include_same_with_same: bool = False):
+        """distMat.py --windType cat: one matrix over every uploaded site (summed over the ranks of the NCCL
+        communicator when one is set) -> (dist [n_ind,n_ind], total_sites)."""
+        hap_ind = np.ascontiguousarray(hap_ind, dtype=np.int32)
+        assert hap_ind.shape == (self.H,)
+        dist = np.empty((n_ind, n_ind), dtype=np.float64)
+        tot = C.c_int64(0)
+        check(self._lib.pg_pairdist_cat(self._ctx, int(n_ind), _ptr(hap_ind), 1 if include_same_with_same else 0,
+                                        _ptr(dist), C.byref(tot)), "pg_pairdist_cat")
+        return dist, int(tot.value)
 
     def ind_het(self, hap_ind, n_ind: int, min_sites: int = 0):
         """Alignment.sampleHet() per window -> [W, n_ind]."""

@@ -246,8 +246,11 @@ class Alignment:
         d[n == 0] = np.nan
         np.fill_diagonal(d, 0.0)
         self._distMat_ = d
+        # a fresh matrix replaces the cached one: earlier in-place masks are gone (genomics.py:908-912)
+        self._masked_min_sites, self._diag_nan = 0, False
         if minSites:
             d[self.pairNonNan() < minSites] = np.nan
+            self._masked_min_sites = int(minSites)
         return d
 
     def pairNonNan(self):
@@ -382,6 +385,22 @@ def ABBABABA(aln, P1, P2, P3, P4, minData, polarize=True, fixed=False):
     used = r["sitesUsed"][0]
     return {"D": float(r["D"][0]), "fd": float(r["fd"][0]), "fdM": float(r["fdM"][0]), "ABBA": float(r["ABBA"][0]),
             "BABA": float(r["BABA"][0]), "sitesUsed": (np.nan if np.isnan(used) else int(used))}
+
+
+def fourPop(aln, P1, P2, P3, P4, minData, polarize=False, fixed=False):
+    """genomics.py:1585-1643 -> dict of the 14 statistics + sitesUsed."""
+    pops = [P1, P2, P3, P4]
+    hp = np.full(aln.N, -1, dtype=np.int32)
+    for k, p in enumerate(pops):
+        for i, g in enumerate(aln.groups):
+            if g == p or (isinstance(g, tuple) and p in g):
+                hp[i] = k
+    eng = aln._engine()
+    eng.set_pops(hp, 4)
+    r = eng.fourpop(0, 1, 2, 3, minData, polarize=polarize, fixed=fixed)
+    out = {k: float(r[k][0]) for k in eng.FOURPOP_KEYS}
+    out["sitesUsed"] = int(r["sitesUsed"][0])
+    return out
 
 
 # ------------------------------------------------------------------------------------------------

@@ -94,6 +94,14 @@ int pg_set_freqstats(pg_ctx* ctx, int32_t enable);
 int pg_abbababa(pg_ctx* ctx, int32_t p1, int32_t p2, int32_t p3, int32_t o, double min_data,
                 double* out, double* sites_used, int64_t* n_sites, int64_t* pos_sum);
 
+/* Replaces genomics.fourPop (genomics.py:1585-1643; fourPopWindows.py:27-52) per window.
+ * out [W x 14] = fhom, fhom', D, fd, fd', fdm, fdm', fdh, fdh2, fh, ABBA, BABA, ABAA, BAAA; sites_used [W] (0 when the
+ * window has no good site, 1641-1643).  mode 0 = default (the allele np.argsort(all4freqs)[:,2] picks, i.e. the rarer of
+ * the two; on an exact tie the reference depends on numpy's sort implementation — here the lower allele index),
+ * 1 = polarize (allele absent from P4), 2 = fixed (polarize + P1,P2,P3 each fixed). */
+int pg_fourpop(pg_ctx* ctx, int32_t p1, int32_t p2, int32_t p3, int32_t p4, double min_data, int32_t mode,
+               double* out, double* sites_used, int64_t* n_sites, int64_t* pos_sum);
+
 /* Replaces Alignment.siteFreqs(asCounts=True) per population (genomics.py:1049-1052; freq.py:52-58):
  * counts uint16 [n x P x 4] (A,C,G,T) for sites site0 .. site0+n-1. */
 int pg_site_counts(pg_ctx* ctx, int64_t site0, int64_t n, uint16_t* counts);
@@ -113,6 +121,14 @@ int pg_site_target_freqs(pg_ctx* ctx, int64_t site0, int64_t n, int32_t target, 
  * groupDistStats ran earlier on the same window (it masks in place, genomics.py:959-961); 0 = no mask (distMat.py). */
 int pg_pairdist(pg_ctx* ctx, int32_t n_ind, const int32_t* hap_ind, int32_t include_same_with_same,
                 int32_t min_sites, double* dist, int64_t* n_sites, int64_t* pos_sum);
+
+/* Replaces distMat.py --windType cat (distMat.py:303-314: parseGenoFile turns the WHOLE file into one window, then
+ * indPairDists): dist [n_ind x n_ind] over every uploaded site.  With a communicator (pg_nccl_init, nranks > 1) the
+ * uploaded sites are this rank's shard of that window: the integer pair matrices diff_ij / n_ij are added across the
+ * ranks with ONE ncclAllReduce (int64 sum) before the division, and every rank receives the same matrix.
+ * *total_sites (may be NULL) = number of sites over all ranks. */
+int pg_pairdist_cat(pg_ctx* ctx, int32_t n_ind, const int32_t* hap_ind, int32_t include_same_with_same,
+                    double* dist, int64_t* total_sites);
 
 /* Replaces Alignment.sampleHet() (genomics.py:918-929; popgenWindows.py:59-61 --analysis indHet): het [W x n_ind] =
  * p-distance between the two haplotypes of each individual; nan unless the individual has exactly two haplotypes

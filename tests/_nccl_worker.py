@@ -54,6 +54,22 @@ def main():
         for k in ("pi", "dxy", "fst"):
             assert np.allclose(got[k], ref[k], rtol=1e-12, atol=0, equal_nan=True), k
         table.close()
+    # ---- distMat --windType cat: the single window is sharded along the SITE axis; one ncclAllReduce of the
+    # integer pair matrices ----
+    spec = synth.SynthSpec(3, 6, miss=0.04, seed=8)
+    S = 150001
+    g = synth.synth_genotypes(spec, 0, S)
+    hap_ind = (np.arange(g.shape[1]) // 2).astype(np.int32)
+    n_ind = g.shape[1] // 2
+    s0, s1 = rank * S // world, (rank + 1) * S // world
+    eng.upload(g[s0:s1], None)
+    got, tot = eng.pairdist_cat(hap_ind, n_ind, False)
+    assert tot == S
+    eng.nccl_finalize()                      # without a communicator the same call covers only the local sites
+    eng.upload(g, None)
+    eng.set_windows([0], [S])
+    ref = eng.pairdist(hap_ind, n_ind, False)["dist"][0]
+    assert np.array_equal(got, ref, equal_nan=True)          # integer sums, one division: bit-identical
     dist.barrier()
     eng.close()
     dist.destroy_process_group()

@@ -234,3 +234,116 @@ def test_alignment_api_cache_states(m):
         a.indPairDists()
         h = a.H12stats(maxDist=0.1)
         assert_close([h[k] for k in sorted(h)], [m["H12stats"]["after_indPairDist_0.1"][k] for k in sorted(h)], "h12 diag", **TOL)
+
+
+# ------------------------------------------------------------------------------------------------
+# fourPop (genomics.py:1585-1643)
+# ------------------------------------------------------------------------------------------------
+FP_KEYS = ('fhom', "fhom'", 'D', 'fd', "fd'", 'fdm', "fdm'", 'fdh', 'fdh2', 'fh', "ABBA", "BABA", "ABAA", "BAAA")
+FP_META = [m for m in META if "fourPop" in m]
+
+
+@pytest.mark.parametrize("m", FP_META, ids=[m["name"] for m in FP_META])
+def test_fourpop_golden(eng, m):
+    for key, want in m["fourPop"].items():
+        notie = key.startswith(("default", "perm"))
+        g, hp, L = _load(eng, m, "__g_aln_notie" if notie else "__g_aln")
+        if key.startswith("perm"):
+            sel, md, kw = (2, 0, 1, 3), 0.4, {}
+        else:
+            mode, md = key.rsplit("_", 1)
+            sel, md, kw = (0, 1, 2, 3), float(md), ({} if mode == "default" else {mode: True})
+        r = eng.fourpop(*sel, md, **kw)
+        assert r["sites"][0] == L
+        assert r["sitesUsed"][0] == want["sitesUsed"], key
+        assert_close([r[k][0] for k in FP_KEYS], [want[k] for k in FP_KEYS], key, rtol=1e-9, atol=1e-12)
+
+
+def test_fourpop_windows_vs_oracle(eng):
+    """Many windows (with overlap), 2 % missing data, every mode and several minData values."""
+    from genomics_general_b200 import synth
+    from oracle import dense_oracle as do
+    spec = synth.SynthSpec(4, 7, miss=0.02, seed=31)
+    S = 30000
+    g = synth.synth_genotypes(spec, 0, S)
+    hp = spec.hap_pop()
+    # exactly-tied sites are implementation-defined in the reference's default mode: blank them
+    tot = np.stack([(g == a).sum(axis=1) for a in range(4)], axis=1)
+    srt = np.sort(tot, axis=1)
+    g[(srt[:, 2] > 0) & (srt[:, 2] == srt[:, 3])] = -1
+    eng.upload(g, synth.synth_positions(S, seed=31))
+    eng.set_pops(hp, 4)
+    lo = np.arange(0, S - 3000, 1500, dtype=np.int64)
+    hi = lo + 3000
+    eng.set_windows(lo, hi)
+    import warnings
+    for kw in ({}, dict(polarize=True), dict(fixed=True)):
+        for md in (0.0, 0.6, 1.0):
+            r = eng.fourpop(1, 0, 2, 3, md, **kw)
+            for w in range(0, len(lo), 3):
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    want = do.four_pop(g[lo[w]:hi[w]], hp, 1, 0, 2, 3, md, **kw)
+                assert r["sitesUsed"][w] == want["sitesUsed"]
+                assert_close([r[k][w] for k in FP_KEYS], [want[k] for k in FP_KEYS], "%s md=%g w=%d" % (kw, md, w),
+                             rtol=1e-9, atol=1e-12)
+
+
+def test_fourpop_api_mirror(eng):
+    from genomics_general_b200 import genomics as G
+    m = FP_META[0]
+    g = ARR[m["name"] + "__g_aln"]
+    hp = ARR[m["name"] + "__hap_pop"]
+    groups = [m["pop_names"][x] if x >= 0 else None for x in hp]
+    a = G.Alignment(g, names=m["hap_names"], groups=groups, sampleNames=m["hap_samples"])
+    r = G.fourPop(a, "pop0", "pop1", "pop2", "pop3", 0.5, polarize=True)
+    want = m["fourPop"]["polarize_0.5"]
+    assert r["sitesUsed"] == want["sitesUsed"]
+    assert_close([r[k] for k in FP_KEYS], [want[k] for k in FP_KEYS], "api", rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("key,notie,extra", [
+    ("fourPopWindows_default", True, ["-w", "20000", "-m", "50", "--minData", "0.5"]),
+    ("fourPopWindows_polarize", False, ["-w", "20000", "-m", "50", "--minData", "0.5", "--polarize"]),
+    ("fourPopWindows_fixed_sites", False, ["--windType", "sites", "-w", "1000", "--overlap", "250", "-m", "20", "--minData", "0.9",
+                                           "--fixed", "--writeFailedWindows", "--addWindowID"]),
+])
+def test_fourPopWindows_cli(inputs2, key, notie, extra):
+    from genomics_general_b200 import geno_io, synth
+    from genomics_general_b200.cli import fourPopWindows
+    i = inputs2
+    path = i["geno"]
+    if notie:       # the default-mode fixture ran on the input with exactly-tied sites blanked (make_golden2.py)
+        c = CLI2["four_pops"]["cfg"]
+        spec = synth.SynthSpec(c["n_pops"], c["spp"], seed=c["seed"], miss=c["miss"])
+        g = synth.synth_genotypes(spec, 0, c["S"])
+        g[np.array(CLI2["four_pops"]["fourpop_tied_sites"], dtype=np.int64)] = -1
+        gd = geno_io.parse_geno(path, geno_format="phased")
+        path = os.path.join(i["dir"], "notie.geno")
+        synth.write_geno(path, g, gd.pos, [gd.scaf_names[k] for k in gd.scaf_ids], spec.sample_names())
+    o = os.path.join(i["dir"], key + ".csv")
+    fourPopWindows.main(["-g", path, "-o", o, "-f", "phased", "-T", "1", "--popsFile", i["pops"], "-P1", "pop0", "-P2", "pop1",
+                         "-P3", "pop2", "-O", "pop3"] + extra)
+    npre = 7 if "--addWindowID" in extra else 6
+    _compare_by_column(open(o).read(), CLI2["four_pops"][key], n_prefix=npre, atol=1.0001e-4)
+
+
+def test_pairdist_cat_equals_one_window(eng):
+    """--windType cat: chunked int64 accumulation over the site axis == the one-window pair matrix, bit for bit."""
+    from genomics_general_b200 import synth
+    from oracle import dense_oracle as do
+    spec = synth.SynthSpec(3, 5, miss=0.05, seed=12)
+    for S in (1000, 32768, 70001):
+        g = synth.synth_genotypes(spec, 0, S)
+        H = g.shape[1]
+        hap_ind = (np.arange(H) // 2).astype(np.int32)
+        hap_ind[-2:] = -1                                  # one sample left out (--samples subset)
+        eng.upload(g, None)
+        eng.set_windows([0], [S])
+        for inc in (False, True):
+            got, tot = eng.pairdist_cat(hap_ind, H // 2 - 1, inc)
+            assert tot == S
+            ref = eng.pairdist(hap_ind, H // 2 - 1, inc)["dist"][0]
+            assert np.array_equal(got, ref, equal_nan=True)
+        if S == 1000:
+            assert_close(got, do.ind_pair_dists(g, hap_ind, H // 2 - 1, True), "oracle", **TOL)
