@@ -46,6 +46,8 @@ struct K1Params {
     unsigned long long* part;
     // ABBA / FOURPOP: minimum non-missing count per population (exact integer form of n/N >= minData)
     int thr[4];
+    int acc_limit;           // POPGEN: sites a lane may add to its 32-bit sums between flushes
+    int bytes;               // POPGEN: every population has <= 255 haplotypes -> byte-packed counts (IDP.4A statistics)
     int variant;             // FOURPOP allele choice: 0 = third of argsort (the rarer allele), 1 = polarize, 2 = fixed
     // COUNTS
     uint16_t* counts_out;
@@ -146,17 +148,20 @@ __device__ __forceinline__ void add_chunks1(Tally& t, uint4 x) {
     if (t.load > 240) byte_flush(t);
 }
 
-template <int QI, int QD>
+// Per-lane running sums: 64-bit integers, 32-bit integers (flushed before they can overflow: K1Params::acc_limit),
+// doubles.  A slot in global memory holds them as QI + QU + QD 8-byte words in that order.
+template <int QI, int QU, int QD>
 struct Acc {
     long long i[QI > 0 ? QI : 1];
+    uint32_t u[QU > 0 ? QU : 1];
     double d[QD > 0 ? QD : 1];
 };
 
 // Warp-cooperative flush of the per-lane running sums into this warp's private slots.
-template <int QI, int QD>
-__device__ __forceinline__ void warp_flush(Acc<QI, QD>& acc, int cur_seg, unsigned long long* part, int64_t slot_base,
+template <int QI, int QU, int QD>
+__device__ __forceinline__ void warp_flush(Acc<QI, QU, QD>& acc, int cur_seg, unsigned long long* part, int64_t slot_base,
                                            int seg_first, int warp, int lane, int nw) {
-    constexpr int Q = QI + QD;
+    constexpr int Q = QI + QU + QD;
     unsigned pending = __ballot_sync(0xffffffffu, cur_seg >= 0);
     while (pending) {
         const int leader = __ffs(pending) - 1;
@@ -172,11 +177,23 @@ __device__ __forceinline__ void warp_flush(Acc<QI, QD>& acc, int cur_seg, unsign
             if (mine) acc.i[q] = 0;
         }
 #pragma unroll
+        for (int q = 0; q < QU; ++q) {
+            // 32-bit lane sums: the first butterfly step stays in 32 bits when two lanes cannot overflow... they can,
+            // so widen first (33 bits after one step) — 5 steps of 64-bit adds on a once-per-segment path
+            long long v = mine ? (long long)acc.u[q] : 0ll;
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+            if (lane == 0) dst[QI + q] = (unsigned long long)((long long)dst[QI + q] + v);
+            if (mine) acc.u[q] = 0u;
+        }
+#pragma unroll
         for (int q = 0; q < QD; ++q) {
             double v = mine ? acc.d[q] : 0.0;
 #pragma unroll
             for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);   // fixed butterfly order
-            if (lane == 0) dst[QI + q] = (unsigned long long)__double_as_longlong(__longlong_as_double((long long)dst[QI + q]) + v);
+            if (lane == 0)
+                dst[QI + QU + q] =
+                    (unsigned long long)__double_as_longlong(__longlong_as_double((long long)dst[QI + QU + q]) + v);
             if (mine) acc.d[q] = 0.0;
         }
         pending &= ~__ballot_sync(0xffffffffu, mine);
@@ -196,23 +213,23 @@ template <int MODE, int P>
 struct ModeTraits;
 template <int P>
 struct ModeTraits<MODE_POPGEN, P> {
-    static constexpr int QI = 3 + P + P * (P - 1) / 2, QD = 0;
+    static constexpr int QI = 3, QU = P + P * (P - 1) / 2, QD = 0;
 };
 template <int P>
 struct ModeTraits<MODE_POPGEN_FREQ, P> {
-    static constexpr int QI = 3 + P + P * (P - 1) / 2 + (P + 1) / 2, QD = 0;   // + segregating-site counts, 2 pops per word
+    static constexpr int QI = 3, QU = P + P * (P - 1) / 2 + P, QD = 0;   // + segregating-site counts
 };
 template <int P>
 struct ModeTraits<MODE_ABBA, P> {
-    static constexpr int QI = 3, QD = 6;
+    static constexpr int QI = 3, QU = 0, QD = 6;
 };
 template <int P>
 struct ModeTraits<MODE_COUNTS, P> {
-    static constexpr int QI = 0, QD = 0;
+    static constexpr int QI = 0, QU = 0, QD = 0;
 };
 template <int P>
 struct ModeTraits<MODE_FOURPOP, P> {
-    static constexpr int QI = 3, QD = 16;
+    static constexpr int QI = 3, QU = 0, QD = 16;
 };
 
 // genomics.py:1409-1418, operation order of the reference's numpy expressions
@@ -225,10 +242,12 @@ __device__ __forceinline__ double f4c_dev(double p1, double p2, double p3, doubl
 // np.amax propagates nan
 __device__ __forceinline__ double nmax(double a, double b) { return (a != a) ? a : ((b != b) ? b : (a > b ? a : b)); }
 
-template <int MODE, int P, int NW>
+// BYTES (POPGEN modes, every population <= 255 haplotypes): the four allele counts of a population travel as the
+// bytes of one word, so that sum c^2 and sum c_X c_Y are ONE IDP.4A each, accumulate included.
+template <int MODE, int P, int NW, bool BYTES = false>
 __global__ void __launch_bounds__((NW + 1) * 32, 1) k1_site_pass(const __grid_constant__ K1Params prm) {
     constexpr int K1_THREADS = (NW + 1) * 32;
-    constexpr int QI = ModeTraits<MODE, P>::QI, QD = ModeTraits<MODE, P>::QD;
+    constexpr int QI = ModeTraits<MODE, P>::QI, QU = ModeTraits<MODE, P>::QU, QD = ModeTraits<MODE, P>::QD;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* tiles = smem;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)prm.stages * prm.tile_bytes);   // [stages]
@@ -295,9 +314,12 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k1_site_pass(const __grid_co
     const int team = warp / prm.wpt, lw = warp % prm.wpt;
     const int sites_per_iter = prm.wpt * spw;
 
-    Acc<QI, QD> acc;
+    Acc<QI, QU, QD> acc;
 #pragma unroll
     for (int q = 0; q < QI; ++q) acc.i[q] = 0;
+#pragma unroll
+    for (int q = 0; q < QU; ++q) acc.u[q] = 0u;
+    int since_flush = 0;     // sites added to the 32-bit sums since they were last flushed (warp-uniform)
 #pragma unroll
     for (int q = 0; q < QD; ++q) acc.d[q] = 0.0;
     int cur_seg = -1;
@@ -325,7 +347,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k1_site_pass(const __grid_co
             if (MODE != MODE_COUNTS)
                 posv = owner ? reinterpret_cast<const int32_t*>(tile + (size_t)prm.T * prm.pitch)[slot] : 0;
 
-            uint32_t n[P], c[P][4];
+            uint32_t n[P], c[BYTES ? 1 : P][4], cb[BYTES ? P : 1];
 #pragma unroll
             for (int X = 0; X < P; ++X) {
                 Tally t;
@@ -345,17 +367,25 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k1_site_pass(const __grid_co
                     if (e < hi) add_chunks1(t, and4(row[s_ent_chunk[e]], s_ent_mask[e]));
                 }
                 byte_flush(t);
-                // combine the G lanes of this site (16-bit fields: counts < 65536)
-                uint32_t p0 = t.tA | (t.tC << 16), p1 = t.tG | (t.tT << 16);
-                for (int d = spw; d < 32; d <<= 1) {
-                    p0 += __shfl_xor_sync(0xffffffffu, p0, d);
-                    p1 += __shfl_xor_sync(0xffffffffu, p1, d);
+                if (BYTES) {
+                    // counts <= 255: one word per population, the G lanes of the site add their packed bytes
+                    uint32_t pk = t.tA | (t.tC << 8) | (t.tG << 16) | (t.tT << 24);
+                    for (int d = spw; d < 32; d <<= 1) pk += __shfl_xor_sync(0xffffffffu, pk, d);
+                    cb[X] = pk;
+                    n[X] = __dp4a(pk, 0x01010101u, 0u);
+                } else {
+                    // combine the G lanes of this site (16-bit fields: counts < 65536)
+                    uint32_t p0 = t.tA | (t.tC << 16), p1 = t.tG | (t.tT << 16);
+                    for (int d = spw; d < 32; d <<= 1) {
+                        p0 += __shfl_xor_sync(0xffffffffu, p0, d);
+                        p1 += __shfl_xor_sync(0xffffffffu, p1, d);
+                    }
+                    c[X][0] = p0 & 0xffffu;
+                    c[X][1] = p0 >> 16;
+                    c[X][2] = p1 & 0xffffu;
+                    c[X][3] = p1 >> 16;
+                    n[X] = c[X][0] + c[X][1] + c[X][2] + c[X][3];
                 }
-                c[X][0] = p0 & 0xffffu;
-                c[X][1] = p0 >> 16;
-                c[X][2] = p1 & 0xffffu;
-                c[X][3] = p1 >> 16;
-                n[X] = c[X][0] + c[X][1] + c[X][2] + c[X][3];
             }
 
             if (MODE == MODE_COUNTS) {
@@ -376,7 +406,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k1_site_pass(const __grid_co
             int sg = cur_seg;
             if (owner && site >= seg_end) sg = find_seg(prm.brk, prm.nseg, cur_seg + 1, site);
             if (__any_sync(0xffffffffu, sg != cur_seg)) {
-                warp_flush<QI, QD>(acc, cur_seg, prm.part, slot_base, seg_first, warp, lane, NW);
+                warp_flush<QI, QU, QD>(acc, cur_seg, prm.part, slot_base, seg_first, warp, lane, NW);
+                since_flush = 0;
                 if (sg != cur_seg) {
                     cur_seg = sg;
                     seg_end = __ldg(prm.brk + sg + 1);
@@ -392,26 +423,53 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k1_site_pass(const __grid_co
                 }
                 const bool pres = owner && allpres;
                 const bool ragged = owner && !allpres && !allmiss;
+                if (++since_flush > prm.acc_limit) {      // the 32-bit sums must not overflow (never taken for N < ~900)
+                    warp_flush<QI, QU, QD>(acc, cur_seg, prm.part, slot_base, seg_first, warp, lane, NW);
+                    since_flush = 1;
+                }
                 acc.i[0] += pres ? 1 : 0;
                 acc.i[1] += ragged ? 1 : 0;
                 acc.i[2] += (long long)posv;
+                if (BYTES) {
+                    uint32_t cf[P];      // counts of a site that does not count are zeroed once, instead of every product
+#pragma unroll
+                    for (int X = 0; X < P; ++X) cf[X] = pres ? cb[X] : 0u;
+#pragma unroll
+                    for (int X = 0; X < P; ++X) {
+                        if (MODE == MODE_POPGEN_FREQ) {
+                            const uint32_t sq = __dp4a(cf[X], cb[X], 0u);
+                            acc.u[X] += sq;
+                            acc.u[P + P * (P - 1) / 2 + X] += (pres && sq != n[X] * n[X]) ? 1u : 0u;
+                        } else {
+                            acc.u[X] = __dp4a(cf[X], cb[X], acc.u[X]);
+                        }
+                    }
+                    int kb = 0;
+#pragma unroll
+                    for (int X = 0; X < P; ++X)
+#pragma unroll
+                        for (int Y = X + 1; Y < P; ++Y) {
+                            acc.u[P + kb] = __dp4a(cf[X], cb[Y], acc.u[P + kb]);
+                            ++kb;
+                        }
+                }
                 const uint32_t f = pres ? 1u : 0u;
 #pragma unroll
-                for (int X = 0; X < P; ++X) {
+                for (int X = 0; X < (BYTES ? 0 : P); ++X) {
                     const uint32_t sq = c[X][0] * c[X][0] + c[X][1] * c[X][1] + c[X][2] * c[X][2] + c[X][3] * c[X][3];
-                    acc.i[3 + X] += (long long)(sq * f);
+                    acc.u[X] += sq * f;
                     // groupFreqStats (genomics.py:1002-1028): a complete site is segregating in X iff sum c^2 < N^2
                     // (two populations share one 64-bit accumulator: 32-bit fields)
                     if (MODE == MODE_POPGEN_FREQ)
-                        acc.i[3 + P + P * (P - 1) / 2 + X / 2] += (pres && sq != n[X] * n[X]) ? (1ll << (32 * (X & 1))) : 0ll;
+                        acc.u[P + P * (P - 1) / 2 + X] += (pres && sq != n[X] * n[X]) ? 1u : 0u;
                 }
                 int k = 0;
 #pragma unroll
-                for (int X = 0; X < P; ++X)
+                for (int X = 0; X < (BYTES ? 0 : P); ++X)
 #pragma unroll
                     for (int Y = X + 1; Y < P; ++Y) {
                         const uint32_t cr = c[X][0] * c[Y][0] + c[X][1] * c[Y][1] + c[X][2] * c[Y][2] + c[X][3] * c[Y][3];
-                        acc.i[3 + P + k] += (long long)(cr * f);
+                        acc.u[P + k] += cr * f;
                         ++k;
                     }
             }
@@ -553,7 +611,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k1_site_pass(const __grid_co
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[stage]);   // this warp is done with the stage's bytes
     }
-    if (MODE != MODE_COUNTS) warp_flush<QI, QD>(acc, cur_seg, prm.part, slot_base, seg_first, warp, lane, NW);
+    if (MODE != MODE_COUNTS) warp_flush<QI, QU, QD>(acc, cur_seg, prm.part, slot_base, seg_first, warp, lane, NW);
 }
 
 // ---- finalize: slots -> segments -> windows -> statistics ------------------------------------------
@@ -654,7 +712,7 @@ __global__ void __launch_bounds__(64) k1_finalize(const __grid_constant__ FinPar
                     double Sx = nan_d(), tpi = nan_d(), tw = nan_d(), tD = nan_d();
                     if (Lp >= 1 && fp.with_freq) {
                         const long long N = fp.popN[x];
-                        const long long seg = (long long)((sums[3 + Pp + npp + x / 2] >> (32 * (x & 1))) & 0xffffffffull);
+                        const long long seg = (long long)sums[3 + Pp + npp + x];
                         const long long pairs = (N * N * Lp - (long long)sums[3 + x]) / 2;   // sum over sites of sum_{a<b} c_a c_b
                         Sx = (double)seg;
                         tpi = (double)pairs / (.5 * (double)N * (double)(N - 1));
@@ -990,9 +1048,9 @@ int arm_slots(pg_ctx* ctx, K1Cache& c) {
     return PG_OK;
 }
 
-template <int MODE, int P, int NW>
+template <int MODE, int P, int NW, bool BYTES>
 int launch_site_pass_nw(pg_ctx* ctx, const K1Launch& L, const char* name) {
-    auto kern = k1_site_pass<MODE, P, NW>;
+    auto kern = k1_site_pass<MODE, P, NW, BYTES>;
     static bool attr_set = false;     // per instantiation
     if (!attr_set) {
         PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -1005,14 +1063,10 @@ int launch_site_pass_nw(pg_ctx* ctx, const K1Launch& L, const char* name) {
     return PG_OK;
 }
 
-// consumer-warp count per instantiation: 12 where ptxas needs <= 152 registers, else 8
-template <int MODE, int P>
-constexpr int warps_for() {
-    return 12;
-}
+// consumer warps per CTA: 12 (+ the producer = 416 threads, 128 registers each), or 8 with up to 168 registers
 template <int MODE, int P>
 constexpr int default_warps() {
-    return (P == 8 && (MODE == MODE_POPGEN || MODE == MODE_POPGEN_FREQ)) ? 8 : 12;
+    return 12;
 }
 int k1_env_nw(int dflt) {
     const char* e = getenv("PG_K1_NW");
@@ -1024,10 +1078,15 @@ int nw_for() { return k1_env_nw(default_warps<MODE, P>()); }
 
 template <int MODE, int P>
 int launch_site_pass(pg_ctx* ctx, const K1Launch& L, const char* name) {
-    if (L.prm.nw == 12) {
-        if constexpr (warps_for<MODE, P>() == 12) return launch_site_pass_nw<MODE, P, 12>(ctx, L, name);
+    constexpr bool POPGEN_MODE = (MODE == MODE_POPGEN || MODE == MODE_POPGEN_FREQ);
+    if constexpr (POPGEN_MODE) {
+        if (L.prm.bytes) {
+            if (L.prm.nw == 12) return launch_site_pass_nw<MODE, P, 12, true>(ctx, L, name);
+            return launch_site_pass_nw<MODE, P, 8, true>(ctx, L, name);
+        }
     }
-    return launch_site_pass_nw<MODE, P, 8>(ctx, L, name);
+    if (L.prm.nw == 12) return launch_site_pass_nw<MODE, P, 12, false>(ctx, L, name);
+    return launch_site_pass_nw<MODE, P, 8, false>(ctx, L, name);
 }
 
 int pad_pops(int P) { return P <= 2 ? 2 : (P <= 4 ? 4 : 8); }
@@ -1114,7 +1173,7 @@ int pg_popgen_enqueue(pg_ctx* ctx, int32_t min_sites, double min_data, int32_t f
     }
     const int Pp = many ? 2 : pad_pops(P);
     const bool wf = ctx->want_freq && !many;
-    const int Q = 3 + Pp + Pp * (Pp - 1) / 2 + (wf ? (Pp + 1) / 2 : 0);
+    const int Q = 3 + Pp + Pp * (Pp - 1) / 2 + (wf ? Pp : 0);
     K1Cache& c = *cache_of(ctx, 0);
     if (!c.valid || c.epoch != ctx->epoch) {
         c.valid = false;
@@ -1134,6 +1193,13 @@ int pg_popgen_enqueue(pg_ctx* ctx, int32_t min_sites, double min_data, int32_t f
         PG_TRY(prepare_windowed(ctx, c, pop_map, Pp, Q, nw));
         c.epoch = ctx->epoch;
         c.valid = true;
+    }
+    {
+        long long maxN = 1;
+        for (int X = 0; X < Pp; ++X) maxN = std::max<long long>(maxN, c.pt.popN[X]);
+        c.L.prm.acc_limit = (int)std::max<long long>(1, std::min<long long>(0xffffffffll / (maxN * maxN), 1 << 30));
+        if (const char* e = getenv("PG_K1_ACC_LIMIT")) c.L.prm.acc_limit = std::max(1, atoi(e));   // test hook: force early flushes
+        c.L.prm.bytes = (maxN <= 255 && !getenv("PG_K1_NO_BYTES")) ? 1 : 0;
     }
     PG_TRY(arm_slots(ctx, c));
     if (!wf) {

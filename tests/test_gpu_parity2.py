@@ -347,3 +347,57 @@ def test_pairdist_cat_equals_one_window(eng):
             assert np.array_equal(got, ref, equal_nan=True)
         if S == 1000:
             assert_close(got, do.ind_pair_dists(g, hap_ind, H // 2 - 1, True), "oracle", **TOL)
+
+
+# ------------------------------------------------------------------------------------------------
+# K1 instantiations: byte-packed IDP.4A statistics vs the general path, 8 vs 12 consumer warps, early 32-bit flushes
+# ------------------------------------------------------------------------------------------------
+K1_KNOBS = [{}, {"PG_K1_NO_BYTES": "1"}, {"PG_K1_NW": "8"}, {"PG_K1_NO_BYTES": "1", "PG_K1_NW": "8"}, {"PG_K1_ACC_LIMIT": "3"},
+            {"PG_K1_ACC_LIMIT": "1", "PG_K1_NO_BYTES": "1"}, {"PG_K1_G": "2"}, {"PG_K1_G": "4", "PG_K1_NO_BYTES": "1"}]
+
+
+@pytest.mark.parametrize("shape", [(2, 9), (3, 20), (5, 7), (8, 13), (2, 150)], ids=lambda s: "%dx%d" % s)
+def test_k1_variants_are_bit_identical_and_match_the_oracle(eng, shape, monkeypatch):
+    from genomics_general_b200 import synth
+    from oracle import dense_oracle as do
+    P, spp = shape
+    spec = synth.SynthSpec(P, spp, miss=0.0, seed=100 + P)
+    S = 20000
+    g = synth.synth_genotypes(spec, 0, S)
+    g[::97] = -1                                          # all-missing sites keep windows on the closed-form path
+    hp = spec.hap_pop()
+    pos = synth.synth_positions(S, seed=4)
+    lo = np.array([0, 10, 4000, 4001, 9000, 15000], dtype=np.int64)
+    hi = np.array([10, 4000, 4001, 9000, 15000, 20000], dtype=np.int64)
+    base = None
+    for knobs in K1_KNOBS:
+        for k in ("PG_K1_NO_BYTES", "PG_K1_NW", "PG_K1_ACC_LIMIT", "PG_K1_G"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in knobs.items():
+            monkeypatch.setenv(k, v)
+        eng.upload(g, pos)
+        eng.set_pops(hp, P)
+        eng.set_windows(lo, hi)
+        eng.set_freqstats(True)
+        r = eng.popgen(1, 0.01)
+        fq = eng.popgen_freqstats()
+        eng.set_freqstats(False)
+        r2 = eng.popgen(1, 0.01)
+        assert np.all(r["path"] == 1)
+        cur = [r["pi"], r["dxy"], r["fst"], fq["S"], fq["thetaPi"], fq["thetaW"], fq["TajD"], fq["l"]]
+        for a, b in zip([r2["pi"], r2["dxy"], r2["fst"]], cur[:3]):
+            assert np.array_equal(a, b, equal_nan=True)
+        if base is None:
+            base = cur
+            for w in (1, 3, 5):
+                ok, pi, dxy, fst = do.group_dist_stats_closed_form(g[lo[w]:hi[w]], hp, P, 1, 0.01)
+                assert ok
+                assert_close(r["pi"][w], pi, "pi", **TOL)
+                assert_close(r["dxy"][w], dxy, "dxy", **TOL)
+                assert_close(r["fst"][w], fst, "fst", rtol=1e-8, atol=1e-12)
+                f = do.group_freq_stats(g[lo[w]:hi[w]], hp, P)
+                for key in ("S", "thetaPi", "thetaW", "TajD"):
+                    assert_close(fq[key][w], f[key], key, **TOL)
+        else:
+            for a, b in zip(cur, base):
+                assert np.array_equal(a, b, equal_nan=True), knobs
