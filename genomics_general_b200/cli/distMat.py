@@ -81,8 +81,7 @@ def main(argv=None):
             r = eng.pairdist(hap_ind, nInd, args.includeSameWithSame)
         per_ind_ok = np.ones(len(ws), dtype=bool)
         if args.minPerInd:
-            csum = np.concatenate([np.zeros((1, gd.n_haps), dtype=np.int64), np.cumsum(gd.geno >= 0, axis=0, dtype=np.int64)])
-            per_ind_ok = (csum[hi] - csum[lo]).min(axis=1) >= args.minPerInd       # min(aln.seqNonNan()) (distMat.py:40)
+            per_ind_ok = eng.seq_nonnan().min(axis=1) >= args.minPerInd             # min(aln.seqNonNan()) (distMat.py:40)
     for k in range(len(ws)):
         sites = int(r["sites"][k])
         good = sites >= minSites and bool(per_ind_ok[k])

@@ -1063,18 +1063,13 @@ int launch_site_pass_nw(pg_ctx* ctx, const K1Launch& L, const char* name) {
     return PG_OK;
 }
 
-// consumer warps per CTA: 12 (+ the producer = 416 threads, 128 registers each), or 8 with up to 168 registers
-template <int MODE, int P>
-constexpr int default_warps() {
-    return 12;
-}
-int k1_env_nw(int dflt) {
+// consumer warps per CTA: 12 (+ the producer = 416 threads, 128 registers each) for rows below 1 KiB; 8 (up to 168
+// registers, no spills) for longer rows, where the 8-population instantiations measured 3-10 % faster (tools/k1_sweep2.py)
+int k1_nw_for(int pitch) {
     const char* e = getenv("PG_K1_NW");
-    const int v = (e && *e) ? atoi(e) : dflt;
+    const int v = (e && *e) ? atoi(e) : (pitch >= 1024 ? 8 : 12);
     return v == 12 ? 12 : 8;
 }
-template <int MODE, int P>
-int nw_for() { return k1_env_nw(default_warps<MODE, P>()); }
 
 template <int MODE, int P>
 int launch_site_pass(pg_ctx* ctx, const K1Launch& L, const char* name) {
@@ -1188,8 +1183,7 @@ int pg_popgen_enqueue(pg_ctx* ctx, int32_t min_sites, double min_data, int32_t f
             for (int32_t& v : collapsed) v = v >= 0 ? 0 : -1;
         }
         const std::vector<int32_t>& pop_map = many ? collapsed : ctx->hap_pop;
-        const int nw = wf ? (Pp == 2 ? nw_for<MODE_POPGEN_FREQ, 2>() : (Pp == 4 ? nw_for<MODE_POPGEN_FREQ, 4>() : nw_for<MODE_POPGEN_FREQ, 8>()))
-                          : (Pp == 2 ? nw_for<MODE_POPGEN, 2>() : (Pp == 4 ? nw_for<MODE_POPGEN, 4>() : nw_for<MODE_POPGEN, 8>()));
+        const int nw = k1_nw_for(ctx->pitch);
         PG_TRY(prepare_windowed(ctx, c, pop_map, Pp, Q, nw));
         c.epoch = ctx->epoch;
         c.valid = true;
@@ -1374,7 +1368,7 @@ extern "C" int pg_abbababa(pg_ctx* ctx, int32_t p1, int32_t p2, int32_t p3, int3
         for (int h = 0; h < ctx->H; ++h)
             for (int k = 0; k < 4; ++k)
                 if (ctx->hap_pop[h] == sel[k]) local[h] = k;
-        PG_TRY(prepare_windowed(ctx, c, local, 4, Q, nw_for<MODE_ABBA, 4>()));
+        PG_TRY(prepare_windowed(ctx, c, local, 4, Q, k1_nw_for(ctx->pitch)));
         for (int k = 0; k < 4; ++k) PG_CHECK(c.pt.popN[k] >= 1, "pg_abbababa: population %d has no haplotypes", sel[k]);
         memcpy(c.sel, sel, sizeof(sel));
         c.epoch = ctx->epoch;
@@ -1452,7 +1446,7 @@ extern "C" int pg_fourpop(pg_ctx* ctx, int32_t p1, int32_t p2, int32_t p3, int32
         for (int h = 0; h < ctx->H; ++h)
             for (int k = 0; k < 4; ++k)
                 if (ctx->hap_pop[h] == sel[k]) local[h] = k;
-        PG_TRY(prepare_windowed(ctx, c, local, 4, Q, nw_for<MODE_FOURPOP, 4>()));
+        PG_TRY(prepare_windowed(ctx, c, local, 4, Q, k1_nw_for(ctx->pitch)));
         for (int k = 0; k < 4; ++k) PG_CHECK(c.pt.popN[k] >= 1, "pg_fourpop: population %d has no haplotypes", sel[k]);
         memcpy(c.sel, sel, sizeof(sel));
         c.epoch = ctx->epoch;
@@ -1516,7 +1510,7 @@ int site_counts_slab(pg_ctx* ctx, int64_t first, int64_t cnt) {
         const int table_bytes = n_ent * 20 + 64;
         PG_CHECK(table_bytes <= 48 * 1024, "population layout needs too many mask entries");
         K1Launch L;
-        const int nw = Pp == 2 ? nw_for<MODE_COUNTS, 2>() : (Pp == 4 ? nw_for<MODE_COUNTS, 4>() : nw_for<MODE_COUNTS, 8>());
+        const int nw = k1_nw_for(ctx->pitch);
         L.plan = pg_make_k1_plan(cnt, ctx->H, ctx->sm_count, table_bytes, nw);
         PG_CHECK(L.plan.stages >= 2, "rows of %d haplotypes are too long for the site-pass kernel", ctx->H);
         PG_TRY(check_plan(L.plan));

@@ -558,6 +558,31 @@ __global__ void __launch_bounds__(128) k2_het(const __grid_constant__ HetParams 
     }
 }
 
+// ---- Alignment.seqNonNan (genomics.py:1038-1040): non-missing sites of each haplotype in each window ----------
+__global__ void __launch_bounds__(128) k2_seq_nonnan(const uint32_t* __restrict__ vplane, int64_t NWp, int64_t site_base,
+                                                     const int64_t* __restrict__ win_lo, const int64_t* __restrict__ win_hi,
+                                                     int Hk, long long* __restrict__ out) {
+    __shared__ int sh[4];
+    const int h = blockIdx.x, wb = blockIdx.y;
+    const int64_t rel_lo = win_lo[wb] - site_base, rel_hi = win_hi[wb] - site_base;
+    const int64_t w_first = rel_lo >> 5, w_last = (rel_hi - 1) >> 5;
+    const uint32_t mask_first = 0xffffffffu << (rel_lo & 31);
+    const uint32_t mask_last = 0xffffffffu >> (31 - (int)((rel_hi - 1) & 31));
+    const uint32_t* row = vplane + (size_t)h * NWp;
+    int n = 0;
+    for (int64_t w = w_first + threadIdx.x; w <= w_last; w += 128) {
+        uint32_t m = row[w];
+        if (w == w_first) m &= mask_first;
+        if (w == w_last) m &= mask_last;
+        n += __popc(m);
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) n += __shfl_xor_sync(0xffffffffu, n, d);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = n;
+    __syncthreads();
+    if (threadIdx.x == 0) out[(size_t)wb * Hk + h] = (long long)sh[0] + sh[1] + sh[2] + sh[3];
+}
+
 // ---- H12stats (genomics.py:1079-1098) + distMat_to_cluster_sizes (1239-1261) ------------------------------
 struct HapEpiParams {
     const int32_t* diff;        // [nb][Hk][Hk]
@@ -1310,5 +1335,48 @@ extern "C" int pg_pairdist_cat(pg_ctx* ctx, int32_t n_ind, const int32_t* hap_in
     PG_CUDA(cudaMemcpyAsync(&tot, d_acc + 2 * HH, 8, cudaMemcpyDeviceToHost, ctx->stream));
     PG_CUDA(cudaStreamSynchronize(ctx->stream));
     if (total_sites) *total_sites = tot;
+    return PG_OK;
+}
+
+// Alignment.seqNonNan() per window (distMat.py:40 --minPerInd gate): out int64 [W x H], haplotypes in upload order.
+extern "C" int pg_seq_nonnan(pg_ctx* ctx, int64_t* out) {
+    PG_CHECK(ctx && out, "pg_seq_nonnan: null argument");
+    PG_CHECK(ctx->H > 0, "pg_seq_nonnan: upload genotypes first");
+    PG_CUDA(cudaSetDevice(ctx->device));
+    pg_timings_reset(ctx);
+    const int64_t W = ctx->W;
+    const int H = ctx->H;
+    if (W == 0) return PG_OK;
+    memset(out, 0, (size_t)W * H * 8);
+    std::vector<int64_t> wins;
+    int64_t lo, hi;
+    nonempty_windows(ctx, wins, lo, hi);
+    if (wins.empty()) return PG_OK;
+    std::vector<int32_t> order(H);
+    for (int h = 0; h < H; ++h) order[h] = h;
+    PlaneSet ps;
+    PG_TRY(build_planes(ctx, order, lo, hi, ps));
+    const size_t per_batch = 65535;
+    for (size_t b0 = 0; b0 < wins.size(); b0 += per_batch) {
+        const size_t nb = std::min(per_batch, wins.size() - b0);
+        std::vector<int64_t> blo(nb), bhi(nb);
+        for (size_t k = 0; k < nb; ++k) {
+            blo[k] = ctx->win_lo[wins[b0 + k]];
+            bhi[k] = ctx->win_hi[wins[b0 + k]];
+        }
+        PG_TRY(ctx->misc3.ensure(nb * 16 + 64));
+        PG_TRY(ctx->out_d.ensure(nb * (size_t)H * 8 + 64));
+        int64_t* d_lo = (int64_t*)ctx->misc3.p;
+        int64_t* d_hi = d_lo + nb;
+        PG_CUDA(cudaMemcpyAsync(d_lo, blo.data(), nb * 8, cudaMemcpyHostToDevice, ctx->stream));
+        PG_CUDA(cudaMemcpyAsync(d_hi, bhi.data(), nb * 8, cudaMemcpyHostToDevice, ctx->stream));
+        const int ti = pg_time_begin(ctx, "k2_seq_nonnan");
+        k2_seq_nonnan<<<dim3((unsigned)H, (unsigned)nb), 128, 0, ctx->stream>>>(ps.planes + (size_t)2 * ps.Hk * ps.NWp, ps.NWp,
+                                                                               ps.site_base, d_lo, d_hi, H,
+                                                                               (long long*)ctx->out_d.p);
+        pg_time_end(ctx, ti);
+        PG_CUDA(cudaGetLastError());
+        PG_TRY(copy_rows_back(ctx, wins, b0, nb, (const double*)ctx->out_d.p, (double*)out, (size_t)H));
+    }
     return PG_OK;
 }

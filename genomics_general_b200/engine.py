@@ -264,6 +264,12 @@ class Engine:
                                         _ptr(dist), C.byref(tot)), "pg_pairdist_cat")
         return dist, int(tot.value)
 
+    def seq_nonnan(self):
+        """Alignment.seqNonNan() per window -> int64 [W, H]."""
+        out = np.empty((self.W, self.H), dtype=np.int64)
+        check(self._lib.pg_seq_nonnan(self._ctx, _ptr(out)), "pg_seq_nonnan")
+        return out
+
     def ind_het(self, hap_ind, n_ind: int, min_sites: int = 0):
         """Alignment.sampleHet() per window -> [W, n_ind]."""
         hap_ind = np.ascontiguousarray(hap_ind, dtype=np.int32)

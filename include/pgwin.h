@@ -130,6 +130,10 @@ int pg_pairdist(pg_ctx* ctx, int32_t n_ind, const int32_t* hap_ind, int32_t incl
 int pg_pairdist_cat(pg_ctx* ctx, int32_t n_ind, const int32_t* hap_ind, int32_t include_same_with_same,
                     double* dist, int64_t* total_sites);
 
+/* Replaces Alignment.seqNonNan() (genomics.py:1038-1040) per window — the --minPerInd gate of distMat.py:40:
+ * out int64 [W x H] = non-missing sites of each haplotype (upload order) inside each window. */
+int pg_seq_nonnan(pg_ctx* ctx, int64_t* out);
+
 /* Replaces Alignment.sampleHet() (genomics.py:918-929; popgenWindows.py:59-61 --analysis indHet): het [W x n_ind] =
  * p-distance between the two haplotypes of each individual; nan unless the individual has exactly two haplotypes
  * and bit 1 of n_ij is set (the reference's `len(x)==2 & n >= 1` is the chained comparison len(x) == (2 & n) >= 1).

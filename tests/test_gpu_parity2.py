@@ -401,3 +401,18 @@ def test_k1_variants_are_bit_identical_and_match_the_oracle(eng, shape, monkeypa
         else:
             for a, b in zip(cur, base):
                 assert np.array_equal(a, b, equal_nan=True), knobs
+
+
+def test_seq_nonnan_bit_exact(eng):
+    """Alignment.seqNonNan per window (the --minPerInd gate of distMat.py:40)."""
+    from genomics_general_b200 import synth
+    spec = synth.SynthSpec(3, 6, miss=0.07, seed=21)
+    S = 5000
+    g = synth.synth_genotypes(spec, 0, S)
+    eng.upload(g, None)
+    lo = np.array([0, 0, 31, 32, 33, 1000, 4999, 2500], dtype=np.int64)
+    hi = np.array([0, 5000, 64, 33, 97, 3000, 5000, 2500], dtype=np.int64)
+    eng.set_windows(lo, hi)
+    got = eng.seq_nonnan()
+    want = np.stack([(g[a:b] >= 0).sum(axis=0) for a, b in zip(lo, hi)])
+    assert np.array_equal(got, want)
