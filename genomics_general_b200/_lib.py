@@ -22,7 +22,7 @@ class PgError(RuntimeError):
 
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/*.cu -> libpgwin.so (nvcc, -gencode arch=compute_100a,code=sm_100a -lineinfo)."""
-    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".h"))]
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".h", ".cpp"))]
     srcs.append(os.path.join(_HERE, "..", "include", "pgwin.h"))
     if not force and os.path.exists(LIB_PATH):
         newest = max(os.path.getmtime(s) for s in srcs)
@@ -80,6 +80,10 @@ _SIGS = {
     "pg_nccl_finalize": (C.c_int, [C.c_void_p]),
     "pg_popgen_allgather": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_int32, C.c_int64, C.c_void_p,
                                       C.POINTER(C.c_int64)]),
+    "pg_ingest_text": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+                                 C.POINTER(C.c_int64)]),
+    "pg_ingest_meta": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pg_ingest_release": (C.c_int, [C.c_void_p]),
     "pg_geno_count_lines": (C.c_int, [C.c_char_p, C.c_size_t, C.POINTER(C.c_int64)]),
     "pg_geno_parse": (C.c_int, [C.c_char_p, C.c_size_t, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                 C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),

@@ -28,6 +28,7 @@ def add_window_args(p, overlap_short=True, cat=False):
 def add_engine_args(p):
     p.add_argument("--device", help="CUDA device index", type=int, default=0)
     p.add_argument("--parseThreads", help="Host threads for the .geno tokenizer", type=int, default=None)
+    p.add_argument("--hostParse", help="Tokenise the .geno text on the host instead of on the GPU", action="store_true")
 
 
 def check_window_args(args, with_id=False):
@@ -117,10 +118,27 @@ def open_out(path):
     return sys.stdout
 
 
-def load_geno(args, samples, ploidyDict, header=None):
+def load_geno(args, samples, ploidyDict, header=None, engine=None):
+    """The whole file as a dense matrix.  With an engine the text is tokenised on the GPU and the matrix stays there
+    (GenoData.geno is None); files too large for device memory, and --hostParse, go through the host tokenizer."""
     src = args.genoFile if args.genoFile else sys.stdin.buffer
+    if engine is not None and not getattr(args, "hostParse", False):
+        data = geno_io.read_bytes(src)
+        try:
+            return geno_io.ingest_geno(engine, data, geno_format=args.genoFormat, samples=samples, ploidy=ploidyDict,
+                                       header=header)
+        except geno_io.PgError as e:
+            if "do not fit in device memory" not in str(e):
+                raise
+            src = data
     return geno_io.parse_geno(src, geno_format=args.genoFormat, samples=samples, ploidy=ploidyDict, header=header,
                               threads=getattr(args, "parseThreads", None))
+
+
+def ensure_resident(eng, gd):
+    """Upload the host matrix unless the device-side tokenizer already built it in place."""
+    if gd.geno is not None:
+        eng.upload(gd.geno, gd.pos)
 
 
 def make_windows(args, gd, minSites, coords, include=None, exclude=None):

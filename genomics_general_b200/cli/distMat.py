@@ -57,7 +57,8 @@ def main(argv=None):
     ploidyDict = C.ploidy_dict(args, samples, args.haploid)
     sampleData = genomics.SampleData(indNames=list(samples), ploidyDict=ploidyDict)
     header = "\t".join(args.headers) if args.headers else None
-    gd = C.load_geno(args, sampleData.indNames, ploidyDict, header=header)
+    eng = Engine(args.device)
+    gd = C.load_geno(args, sampleData.indNames, ploidyDict, header=header, engine=eng)
     if args.windType == "cat":
         ws = W.WindowSet()
         ws.add(None, -np.inf, np.inf, 0, gd.n_sites, None)               # parseGenoFile: one window, positions ignored
@@ -71,8 +72,8 @@ def main(argv=None):
     lo, hi = ws.ranges()
     nInd = len(sampleData.indNames)
     hap_ind = gd.hap_sample()
-    with Engine(args.device) as eng:
-        eng.upload(gd.geno, gd.pos)
+    with eng:
+        C.ensure_resident(eng, gd)
         eng.set_windows(lo, hi)
         if args.windType == "cat":
             dcat, ntot = eng.pairdist_cat(hap_ind, nInd, args.includeSameWithSame)      # chunked over the site axis

@@ -55,12 +55,13 @@ def main(argv=None):
     out = C.open_out(args.outFile)
     out.write(",".join((["windowID"] if args.addWindowID else []) + ["scaffold", "start", "end", "mid", "sites", "sitesUsed"]
                        + STATS) + "\n")
-    gd = C.load_geno(args, sampleData.indNames, ploidyDict, header=args.header)
+    eng = Engine(args.device)
+    gd = C.load_geno(args, sampleData.indNames, ploidyDict, header=args.header, engine=eng)
     ws = C.make_windows(args, gd, minSites, coords, C.read_scaffold_list(args.include), C.read_scaffold_list(args.exclude))
     lo, hi = ws.ranges()
     written = 0
-    with Engine(args.device) as eng:
-        eng.upload(gd.geno, gd.pos)
+    with eng:
+        C.ensure_resident(eng, gd)
         eng.set_windows(lo, hi)
         eng.set_pops(C.hap_pop_vector(gd, popNames, popInds), 4)
         r = eng.fourpop(0, 1, 2, 3, args.minData, polarize=args.polarize, fixed=args.fixed)

@@ -57,10 +57,11 @@ def main(argv=None):
     sampleData = genomics.SampleData(indNames=allInds, popNames=popNames, popInds=popInds, ploidyDict=ploidyDict)
     out = C.open_out(args.outFile)
     out.write("scaffold\tposition\t" + "\t".join(popNames) + "\n")
-    gd = C.load_geno(args, sampleData.indNames, ploidyDict)
+    eng = Engine(args.device)
+    gd = C.load_geno(args, sampleData.indNames, ploidyDict, engine=eng)
     P = len(popNames)
-    with Engine(args.device) as eng:
-        eng.upload(gd.geno, gd.pos)
+    with eng:
+        C.ensure_resident(eng, gd)
         eng.set_pops(C.hap_pop_vector(gd, popNames, popInds), P)
         slab = 1 << 20
         scaf = np.array(gd.scaf_names, dtype=object)

@@ -97,13 +97,15 @@ def main(argv=None):
             stats += [key + n for n in popNames]
     out.write(",".join(stats) + "\n")
 
-    gd = C.load_geno(args, sampleData.indNames, ploidyDict, header=args.header)
+    eng = Engine(args.device)
+
+    gd = C.load_geno(args, sampleData.indNames, ploidyDict, header=args.header, engine=eng)
     ws = C.make_windows(args, gd, minSites, coords, C.read_scaffold_list(args.include), C.read_scaffold_list(args.exclude))
     sys.stderr.write("\n%d sites x %d haplotypes, %d windows\n" % (gd.n_sites, gd.n_haps, len(ws)))
     lo, hi = ws.ranges()
     written = 0
-    with Engine(args.device) as eng:
-        eng.upload(gd.geno, gd.pos)
+    with eng:
+        C.ensure_resident(eng, gd)
         eng.set_windows(lo, hi)
         P = len(popNames)
         eng.set_pops(C.hap_pop_vector(gd, popNames, popInds), max(P, 1))

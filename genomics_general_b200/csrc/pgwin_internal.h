@@ -100,6 +100,8 @@ struct pg_ctx {
     int64_t launches = 0;
     // scratch
     PgBuf tables, part, segmeta, winmeta, out_d, out_i, planes, pairs, misc, misc2, misc3, misc4, misc5;
+    PgBuf text, starts, meta;                 // device-side text ingest (ingest.cu)
+    int64_t ingest_sites = -1;
     // upload pipeline: copy stream + two staging buffers
     cudaStream_t copy_stream = nullptr;
     PgBuf stage[2];

@@ -222,6 +222,27 @@ class Engine:
         r.update(sitesUsed=used, sites=sites, pos_sum=pos_sum)
         return r
 
+    def ingest_text(self, body: bytes, fmt: int, col_hap, col_ploidy, H: int) -> int:
+        """Device-side .geno tokenizer (pg_ingest_text): `body` = the file's data lines.  Returns the number of sites now
+        resident."""
+        col_hap = np.ascontiguousarray(col_hap, dtype=np.int32)
+        col_ploidy = np.ascontiguousarray(col_ploidy, dtype=np.int8)
+        assert col_hap.shape == col_ploidy.shape
+        n = C.c_int64(0)
+        check(self._lib.pg_ingest_text(self._ctx, body, len(body), int(fmt), len(col_hap), _ptr(col_hap), _ptr(col_ploidy),
+                                       int(H), C.byref(n)), "pg_ingest_text")
+        self.S, self.H = int(n.value), int(H)
+        return self.S
+
+    def ingest_meta(self, S: int):
+        """(pos int32 [S], new_scaffold int8 [S], line_off int64 [S]) of the last ingest_text."""
+        pos = np.empty(S, dtype=np.int32)
+        newsc = np.empty(S, dtype=np.int8)
+        off = np.empty(S, dtype=np.int64)
+        check(self._lib.pg_ingest_meta(self._ctx, _ptr(pos), _ptr(newsc), _ptr(off)), "pg_ingest_meta")
+        check(self._lib.pg_ingest_release(self._ctx), "pg_ingest_release")
+        return pos, newsc, off
+
     def site_counts(self, site0: int = 0, n: int = None):
         """uint16 [n, P, 4] A,C,G,T counts per population."""
         n = self.S - site0 if n is None else int(n)

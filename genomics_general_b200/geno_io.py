@@ -24,6 +24,7 @@ FORMATS = {"phased": 0, "diplo": 1, "pairs": 2, "haplo": 3, "alleles": 0}
 @dataclass
 class GenoData:
     geno: np.ndarray          # int8 [S, H]  A0 C1 G2 T3, -1 missing; haplotypes of sample k at hap_off[k]..+ploidy[k]
+                              # (None after ingest_geno: the matrix was built on the device and lives there)
     pos: np.ndarray           # int32 [S]
     scaf_ids: np.ndarray      # int32 [S] run index (a scaffold that re-appears later starts a new run)
     scaf_names: list          # name of each run
@@ -34,11 +35,11 @@ class GenoData:
 
     @property
     def n_sites(self):
-        return int(self.geno.shape[0])
+        return int(self.pos.shape[0])
 
     @property
     def n_haps(self):
-        return int(self.geno.shape[1])
+        return int(self.ploidy.astype(np.int64).sum())
 
     def hap_sample(self):
         """sample index of every haplotype column"""
@@ -63,12 +64,8 @@ def read_bytes(source):
     return data.encode() if isinstance(data, str) else data
 
 
-def parse_geno(source, geno_format="phased", samples=None, ploidy=None, header=None, threads=None) -> GenoData:
-    """Parse a whole .geno file.
-
-    samples: sample names to keep (default: every column of the header, genomics.py:1918);
-    ploidy: dict sample -> ploidy (default 2; 1 for -f haplo, popgenWindows.py:302);
-    header: header text when the file has none (--header)."""
+def _prepare(source, geno_format, samples, ploidy, header):
+    """shared front end of parse_geno / ingest_geno: bytes, header line, sample -> column selection"""
     data = read_bytes(source)
     if header is None:
         nl = data.find(b"\n")
@@ -91,6 +88,47 @@ def parse_geno(source, geno_format="phased", samples=None, ploidy=None, header=N
     default_pl = 1 if geno_format == "haplo" else 2
     pl = np.array([int((ploidy or {}).get(s, default_pl) or default_pl) for s in samples], dtype=np.int8)
     col_take = np.array([col[s] for s in samples], dtype=np.int32)
+    return body, header, file_names, list(samples), fmt, pl, col_take
+
+
+def _scaffold_runs(body, newsc, off):
+    S = len(newsc)
+    scaf_ids = (np.cumsum(newsc.astype(np.int64)) - 1).astype(np.int32) if S else np.zeros(0, dtype=np.int32)
+    scaf_names = []
+    for s in np.flatnonzero(newsc):
+        o = int(off[s])
+        scaf_names.append(body[o:o + 256].split(None, 1)[0].decode())
+    return scaf_ids, scaf_names
+
+
+def ingest_geno(eng, source, geno_format="phased", samples=None, ploidy=None, header=None) -> GenoData:
+    """Like parse_geno, but the text is tokenised ON THE DEVICE (pg_ingest_text): the file's bytes are copied to the
+    GPU as they are and the resident matrix of `eng` is built there.  The returned GenoData has geno = None."""
+    body, header, file_names, samples, fmt, pl, col_take = _prepare(source, geno_format, samples, ploidy, header)
+    n_cols = len(file_names)
+    col_hap = np.full(max(n_cols, 1), -1, dtype=np.int32)
+    col_pl = np.ones(max(n_cols, 1), dtype=np.int8)
+    hap_off = np.concatenate([[0], np.cumsum(pl.astype(np.int64))[:-1]]).astype(np.int32) if len(pl) else np.zeros(0, np.int32)
+    for k, c in enumerate(col_take):
+        if col_hap[c] >= 0:
+            raise ValueError("sample %s requested twice" % samples[k])
+        col_hap[c] = hap_off[k]
+        col_pl[c] = pl[k]
+    H = int(pl.astype(np.int64).sum())
+    S = eng.ingest_text(body, fmt, col_hap, col_pl, H)
+    pos, newsc, off = eng.ingest_meta(S)
+    scaf_ids, scaf_names = _scaffold_runs(body, newsc, off)
+    return GenoData(geno=None, pos=pos, scaf_ids=scaf_ids, scaf_names=scaf_names, names=samples, ploidy=pl,
+                    hap_off=hap_off, header=header)
+
+
+def parse_geno(source, geno_format="phased", samples=None, ploidy=None, header=None, threads=None) -> GenoData:
+    """Parse a whole .geno file on the host (native multi-threaded tokenizer).
+
+    samples: sample names to keep (default: every column of the header, genomics.py:1918);
+    ploidy: dict sample -> ploidy (default 2; 1 for -f haplo, popgenWindows.py:302);
+    header: header text when the file has none (--header)."""
+    body, header, file_names, samples, fmt, pl, col_take = _prepare(source, geno_format, samples, ploidy, header)
     H = int(pl.astype(np.int64).sum())
     L = _lib_parse()
     n = C.c_int64(0)
@@ -106,12 +144,7 @@ def parse_geno(source, geno_format="phased", samples=None, ploidy=None, header=N
                           pl.ctypes.data_as(C.c_void_p), H, S, geno.ctypes.data_as(C.c_void_p),
                           pos.ctypes.data_as(C.c_void_p), newsc.ctypes.data_as(C.c_void_p),
                           off.ctypes.data_as(C.c_void_p), int(threads)), "pg_geno_parse")
-    scaf_ids = (np.cumsum(newsc.astype(np.int64)) - 1).astype(np.int32) if S else np.zeros(0, dtype=np.int32)
-    starts = np.flatnonzero(newsc)
-    scaf_names = []
-    for s in starts:
-        o = int(off[s])
-        scaf_names.append(body[o:o + 256].split(None, 1)[0].decode())
+    scaf_ids, scaf_names = _scaffold_runs(body, newsc, off)
     hap_off = np.concatenate([[0], np.cumsum(pl.astype(np.int64))[:-1]]).astype(np.int32) if len(pl) else np.zeros(0, np.int32)
     return GenoData(geno=geno, pos=pos, scaf_ids=scaf_ids, scaf_names=scaf_names, names=list(samples), ploidy=pl,
                     hap_off=hap_off, header=header)

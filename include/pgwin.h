@@ -176,6 +176,21 @@ int pg_geno_parse(const char* buf, size_t len, int32_t fmt, int32_t n_out, const
                   const int8_t* ploidy, int32_t H_out, int64_t n_lines, int8_t* geno, int32_t* pos,
                   int8_t* new_scaffold, int64_t* line_off, int32_t n_threads);
 
+/* ---- device-side .geno text ingest --------------------------------------------------------------- */
+/* Same job and grammar as pg_geno_parse, on the GPU: the text (complete data lines, no header line) is copied to
+ * device memory as it is and tokenised there, straight into this ctx's resident matrix (replaces pg_geno_parse +
+ * pg_upload when the text fits in device memory).  col_hap[c] = first output haplotype of genotype column c
+ * (0-based, after scaffold and position) or -1 for a column that is not wanted; col_ploidy[c] its haplotype count.
+ * *n_sites = number of data lines = sites now resident.  Errors (a token whose allele count does not match the
+ * ploidy, genomics.py:1111; a non-integer position; a short line) name the offending data line. */
+int pg_ingest_text(pg_ctx* ctx, const char* buf, size_t len, int32_t fmt, int32_t n_cols, const int32_t* col_hap,
+                   const int8_t* col_ploidy, int32_t H_out, int64_t* n_sites);
+/* pos int32 [S], new_scaffold int8 [S], line_off int64 [S] of the last pg_ingest_text (as pg_geno_parse returns them;
+ * any pointer may be NULL). */
+int pg_ingest_meta(pg_ctx* ctx, int32_t* pos, int8_t* new_scaffold, int64_t* line_off);
+/* Frees the device copy of the text. */
+int pg_ingest_release(pg_ctx* ctx);
+
 /* ---- introspection ---------------------------------------------------------------------------- */
 /* Device time (ms, CUDA events on the ctx stream) of the kernels launched by the last statistics call:
  * names[i] -> ms[i]; returns the number of entries through *count (at most cap). */
