@@ -80,7 +80,9 @@ _SIGS = {
     "pg_nccl_finalize": (C.c_int, [C.c_void_p]),
     "pg_popgen_allgather": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_int32, C.c_int64, C.c_void_p,
                                       C.POINTER(C.c_int64)]),
-    "pg_ingest_text": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+    "pg_ingest_file": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+                                 C.POINTER(C.c_int64)]),
+    "pg_ingest_text": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                  C.POINTER(C.c_int64)]),
     "pg_ingest_meta": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pg_ingest_release": (C.c_int, [C.c_void_p]),

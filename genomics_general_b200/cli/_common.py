@@ -123,14 +123,14 @@ def load_geno(args, samples, ploidyDict, header=None, engine=None):
     (GenoData.geno is None); files too large for device memory, and --hostParse, go through the host tokenizer."""
     src = args.genoFile if args.genoFile else sys.stdin.buffer
     if engine is not None and not getattr(args, "hostParse", False):
-        data = geno_io.read_bytes(src)
+        if not isinstance(src, str) or src.endswith(".gz"):
+            src = geno_io.read_bytes(src)          # stdin / gzip: decompressed in host memory
         try:
-            return geno_io.ingest_geno(engine, data, geno_format=args.genoFormat, samples=samples, ploidy=ploidyDict,
+            return geno_io.ingest_geno(engine, src, geno_format=args.genoFormat, samples=samples, ploidy=ploidyDict,
                                        header=header)
         except geno_io.PgError as e:
             if "do not fit in device memory" not in str(e):
                 raise
-            src = data
     return geno_io.parse_geno(src, geno_format=args.genoFormat, samples=samples, ploidy=ploidyDict, header=header,
                               threads=getattr(args, "parseThreads", None))
 

@@ -88,6 +88,11 @@ extern "C" int pg_ctx_destroy(pg_ctx* ctx) {
         cudaStreamDestroy(ctx->copy_stream);
     }
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    for (int k = 0; k < 2; ++k)
+        if (ctx->h_text[k]) {
+            cudaFreeHost(ctx->h_text[k]);
+            cudaEventDestroy(ctx->h_text_free[k]);
+        }
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return PG_OK;

@@ -16,10 +16,14 @@
 //                                     geno[site * pitch + first_hap(c) + a]
 //   k_scaffold_flags                : new_scaffold[i] = hash[i] != hash[i-1]
 // Bound: the H2D copy of the text (PCIe); the kernels read the text once and write the matrix once.
+#include <fcntl.h>
 #include <stdlib.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cub/cub.cuh>
+#include <thread>
 
 #include "pgwin_internal.h"
 
@@ -287,29 +291,90 @@ __global__ void k_scaffold_flags(const unsigned long long* __restrict__ h, int64
 
 }  // namespace
 
+namespace {
+
+// bytes [off, off + n) of the source (memory or file) -> dst (pinned), split over a few host threads: a single thread
+// copies ~5-10 GB/s out of pageable memory or the page cache, the H2D engine moves ~55 GB/s
+int fill_slab(const char* mem, int fd, size_t file_off, size_t off, size_t n, char* dst, int n_threads) {
+    if (n_threads < 1) n_threads = 1;
+    std::vector<std::thread> th;
+    std::vector<int> rc((size_t)n_threads, 0);
+    auto work = [&](int t) {
+        const size_t a = n * (size_t)t / (size_t)n_threads, b = n * (size_t)(t + 1) / (size_t)n_threads;
+        if (mem) {
+            memcpy(dst + a, mem + off + a, b - a);
+            return;
+        }
+        size_t done = a;
+        while (done < b) {
+            const ssize_t r = pread(fd, dst + done, b - done, (off_t)(file_off + off + done));
+            if (r <= 0) {
+                rc[(size_t)t] = 1;
+                return;
+            }
+            done += (size_t)r;
+        }
+    };
+    for (int t = 1; t < n_threads; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto& x : th) x.join();
+    for (int v : rc)
+        if (v) return 1;
+    return 0;
+}
+
+int ingest_core(pg_ctx* ctx, const char* mem, int fd, size_t file_off, size_t len, int32_t fmt, int32_t n_cols,
+                const int32_t* col_hap, const int8_t* col_ploidy, int32_t H_out, int64_t* n_sites);
+
+}  // namespace
+
 // Text (complete lines, no header line) -> resident matrix of this ctx.  Afterwards the ctx holds *n_sites sites of
 // H_out haplotypes; positions, new-scaffold flags and line offsets are read back with pg_ingest_meta.
 extern "C" int pg_ingest_text(pg_ctx* ctx, const char* buf, size_t len, int32_t fmt, int32_t n_cols, const int32_t* col_hap,
                               const int8_t* col_ploidy, int32_t H_out, int64_t* n_sites) {
     PG_CHECK(ctx && (buf || len == 0) && col_hap && col_ploidy && n_sites, "pg_ingest_text: null argument");
-    PG_CHECK(fmt >= 0 && fmt <= 3, "pg_ingest_text: unknown format %d", fmt);
-    PG_CHECK(n_cols >= 1 && H_out >= 1, "pg_ingest_text: no genotype columns requested");
+    return ingest_core(ctx, buf ? buf : "", -1, 0, len, fmt, n_cols, col_hap, col_ploidy, H_out, n_sites);
+}
+
+// The same for a file on disk: bytes [body_offset, EOF) of `path` (body_offset = length of the header line, or 0) are read
+// straight into the pinned staging buffers by a few host threads — no intermediate copy of the file in host memory.
+extern "C" int pg_ingest_file(pg_ctx* ctx, const char* path, int64_t body_offset, int32_t fmt, int32_t n_cols,
+                              const int32_t* col_hap, const int8_t* col_ploidy, int32_t H_out, int64_t* n_sites) {
+    PG_CHECK(ctx && path && col_hap && col_ploidy && n_sites, "pg_ingest_file: null argument");
+    const int fd = open(path, O_RDONLY);
+    PG_CHECK(fd >= 0, "pg_ingest_file: cannot open %s", path);
+    struct stat st;
+    if (fstat(fd, &st) != 0 || body_offset < 0 || (int64_t)st.st_size < body_offset) {
+        close(fd);
+        pg_set_error("pg_ingest_file: cannot stat %s (or the body offset is past its end)", path);
+        return PG_ERR;
+    }
+    const int rc = ingest_core(ctx, nullptr, fd, (size_t)body_offset, (size_t)st.st_size - (size_t)body_offset, fmt, n_cols,
+                               col_hap, col_ploidy, H_out, n_sites);
+    close(fd);
+    return rc;
+}
+
+namespace {
+int ingest_core(pg_ctx* ctx, const char* mem, int fd, size_t file_off, size_t len, int32_t fmt, int32_t n_cols,
+                const int32_t* col_hap, const int8_t* col_ploidy, int32_t H_out, int64_t* n_sites) {
+    PG_CHECK(fmt >= 0 && fmt <= 3, "pg_ingest: unknown format %d", fmt);
+    PG_CHECK(n_cols >= 1 && H_out >= 1, "pg_ingest: no genotype columns requested");
     int n_wanted = 0;
     {
         std::vector<char> used((size_t)H_out, 0);
         for (int c = 0; c < n_cols; ++c) {
             if (col_hap[c] < 0) continue;
-            PG_CHECK(col_ploidy[c] >= 1 && col_ploidy[c] <= 8, "pg_ingest_text: ploidy %d of column %d unsupported",
+            PG_CHECK(col_ploidy[c] >= 1 && col_ploidy[c] <= 8, "pg_ingest: ploidy %d of column %d unsupported",
                      (int)col_ploidy[c], c);
-            PG_CHECK(col_hap[c] + col_ploidy[c] <= H_out, "pg_ingest_text: column %d maps outside the %d output haplotypes", c,
-                     H_out);
+            PG_CHECK(col_hap[c] + col_ploidy[c] <= H_out, "pg_ingest: column %d maps outside the %d output haplotypes", c, H_out);
             for (int a = 0; a < col_ploidy[c]; ++a) {
-                PG_CHECK(!used[col_hap[c] + a], "pg_ingest_text: output haplotype %d is written by two columns", col_hap[c] + a);
+                PG_CHECK(!used[col_hap[c] + a], "pg_ingest: output haplotype %d is written by two columns", col_hap[c] + a);
                 used[col_hap[c] + a] = 1;
             }
             ++n_wanted;
         }
-        for (int h = 0; h < H_out; ++h) PG_CHECK(used[h], "pg_ingest_text: output haplotype %d has no source column", h);
+        for (int h = 0; h < H_out; ++h) PG_CHECK(used[h], "pg_ingest: output haplotype %d has no source column", h);
     }
     PG_CUDA(cudaSetDevice(ctx->device));
     pg_timings_reset(ctx);
@@ -320,12 +385,27 @@ extern "C" int pg_ingest_text(pg_ctx* ctx, const char* buf, size_t len, int32_t 
              "(%zu free) — use the host tokenizer (pg_geno_parse) and pg_upload", len, free_b);
     PG_TRY(ctx->text.ensure(len + 256));
     uint8_t* d_text = (uint8_t*)ctx->text.p;
-    // H2D of the text in slabs (pageable source: the driver stages it; pinned sources go at full PCIe rate)
+    // H2D of the text: host threads fill two pinned staging buffers in turn, the copy engine drains them
     {
+        const size_t slab = (size_t)64 << 20;
+        const int n_threads = std::max(1, std::min(16, (int)std::thread::hardware_concurrency() / 2));
+        if (!ctx->h_text[0]) {
+            for (int k = 0; k < 2; ++k) {
+                PG_CUDA(cudaHostAlloc(&ctx->h_text[k], slab, cudaHostAllocDefault));
+                PG_CUDA(cudaEventCreateWithFlags(&ctx->h_text_free[k], cudaEventDisableTiming));
+            }
+        }
         const int ti = pg_time_begin(ctx, "text_h2d");
-        const size_t slab = (size_t)256 << 20;
-        for (size_t o = 0; o < len; o += slab)
-            PG_CUDA(cudaMemcpyAsync(d_text + o, buf + o, std::min(slab, len - o), cudaMemcpyHostToDevice, ctx->stream));
+        int k = 0;
+        for (size_t o = 0; o < len; o += slab, ++k) {
+            const size_t n = std::min(slab, len - o);
+            const int b = k & 1;
+            if (k >= 2) PG_CUDA(cudaEventSynchronize(ctx->h_text_free[b]));
+            PG_CHECK(fill_slab(mem, fd, file_off, o, n, (char*)ctx->h_text[b], n_threads) == 0,
+                     "pg_ingest: reading the text failed at byte %zu", o);
+            PG_CUDA(cudaMemcpyAsync(d_text + o, ctx->h_text[b], n, cudaMemcpyHostToDevice, ctx->stream));
+            PG_CUDA(cudaEventRecord(ctx->h_text_free[b], ctx->stream));
+        }
         PG_CUDA(cudaMemsetAsync(d_text + len, '\n', 256, ctx->stream));
         pg_time_end(ctx, ti);
     }
@@ -368,6 +448,7 @@ extern "C" int pg_ingest_text(pg_ctx* ctx, const char* buf, size_t len, int32_t 
     PG_TRY(pg_alloc_sites(ctx, S, H_out));
     ctx->epoch += 1;
     *n_sites = S;
+    ctx->ingest_sites = S;
     if (S == 0) return PG_OK;
     // column tables + per-line scratch
     PG_TRY(ctx->misc4.ensure((size_t)n_cols * 5 + 64 + 32));
@@ -427,6 +508,8 @@ extern "C" int pg_ingest_text(pg_ctx* ctx, const char* buf, size_t len, int32_t 
     }
     return PG_OK;
 }
+
+}  // namespace
 
 // positions int32 [S], new_scaffold int8 [S] (1 where the scaffold field differs from the previous data line),
 // line_off int64 [S] (byte offset of each data line in the text) of the last pg_ingest_text; any may be NULL.

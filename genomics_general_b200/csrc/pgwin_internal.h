@@ -102,6 +102,8 @@ struct pg_ctx {
     PgBuf tables, part, segmeta, winmeta, out_d, out_i, planes, pairs, misc, misc2, misc3, misc4, misc5;
     PgBuf text, starts, meta;                 // device-side text ingest (ingest.cu)
     int64_t ingest_sites = -1;
+    void* h_text[2] = {nullptr, nullptr};     // pinned staging of the text
+    cudaEvent_t h_text_free[2] = {nullptr, nullptr};
     // upload pipeline: copy stream + two staging buffers
     cudaStream_t copy_stream = nullptr;
     PgBuf stage[2];

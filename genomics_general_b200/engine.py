@@ -222,15 +222,26 @@ class Engine:
         r.update(sitesUsed=used, sites=sites, pos_sum=pos_sum)
         return r
 
-    def ingest_text(self, body: bytes, fmt: int, col_hap, col_ploidy, H: int) -> int:
-        """Device-side .geno tokenizer (pg_ingest_text): `body` = the file's data lines.  Returns the number of sites now
-        resident."""
+    def ingest_text(self, data: bytes, fmt: int, col_hap, col_ploidy, H: int, offset: int = 0) -> int:
+        """Device-side .geno tokenizer (pg_ingest_text): data[offset:] = the file's data lines (no copy is made).
+        Returns the number of sites now resident."""
         col_hap = np.ascontiguousarray(col_hap, dtype=np.int32)
         col_ploidy = np.ascontiguousarray(col_ploidy, dtype=np.int8)
         assert col_hap.shape == col_ploidy.shape
         n = C.c_int64(0)
-        check(self._lib.pg_ingest_text(self._ctx, body, len(body), int(fmt), len(col_hap), _ptr(col_hap), _ptr(col_ploidy),
-                                       int(H), C.byref(n)), "pg_ingest_text")
+        addr = C.cast(C.c_char_p(data), C.c_void_p).value or 0        # `data` stays referenced by the caller
+        check(self._lib.pg_ingest_text(self._ctx, C.c_void_p(addr + offset), len(data) - offset, int(fmt), len(col_hap),
+                                       _ptr(col_hap), _ptr(col_ploidy), int(H), C.byref(n)), "pg_ingest_text")
+        self.S, self.H = int(n.value), int(H)
+        return self.S
+
+    def ingest_file(self, path: str, body_offset: int, fmt: int, col_hap, col_ploidy, H: int) -> int:
+        """The same, reading the file straight into the pinned staging buffers (pg_ingest_file)."""
+        col_hap = np.ascontiguousarray(col_hap, dtype=np.int32)
+        col_ploidy = np.ascontiguousarray(col_ploidy, dtype=np.int8)
+        n = C.c_int64(0)
+        check(self._lib.pg_ingest_file(self._ctx, path.encode(), int(body_offset), int(fmt), len(col_hap), _ptr(col_hap),
+                                       _ptr(col_ploidy), int(H), C.byref(n)), "pg_ingest_file")
         self.S, self.H = int(n.value), int(H)
         return self.S
 

@@ -64,17 +64,8 @@ def read_bytes(source):
     return data.encode() if isinstance(data, str) else data
 
 
-def _prepare(source, geno_format, samples, ploidy, header):
-    """shared front end of parse_geno / ingest_geno: bytes, header line, sample -> column selection"""
-    data = read_bytes(source)
-    if header is None:
-        nl = data.find(b"\n")
-        if nl < 0:
-            nl = len(data)
-        header = data[:nl].decode()
-        body = data[nl + 1:]
-    else:
-        body = data
+def _select(header, geno_format, samples, ploidy):
+    """header line + requested samples -> (file column names, samples, format code, ploidies, file column of each sample)"""
     file_names = header.split()[2:]
     if samples is None:
         samples = list(file_names)
@@ -88,23 +79,46 @@ def _prepare(source, geno_format, samples, ploidy, header):
     default_pl = 1 if geno_format == "haplo" else 2
     pl = np.array([int((ploidy or {}).get(s, default_pl) or default_pl) for s in samples], dtype=np.int8)
     col_take = np.array([col[s] for s in samples], dtype=np.int32)
-    return body, header, file_names, list(samples), fmt, pl, col_take
+    return file_names, list(samples), fmt, pl, col_take
 
 
-def _scaffold_runs(body, newsc, off):
+def _prepare(source, geno_format, samples, ploidy, header):
+    """shared front end of parse_geno / ingest_geno: bytes, header line, sample -> column selection.
+    Returns the whole data and the offset of the first data line (no copy of the body is made)."""
+    data = read_bytes(source)
+    off = 0
+    if header is None:
+        nl = data.find(b"\n")
+        if nl < 0:
+            nl = len(data)
+        header = data[:nl].decode()
+        off = min(nl + 1, len(data))
+    return (data, off, header) + _select(header, geno_format, samples, ploidy)
+
+
+def _scaffold_runs(newsc, off, name_at):
     S = len(newsc)
     scaf_ids = (np.cumsum(newsc.astype(np.int64)) - 1).astype(np.int32) if S else np.zeros(0, dtype=np.int32)
-    scaf_names = []
-    for s in np.flatnonzero(newsc):
-        o = int(off[s])
-        scaf_names.append(body[o:o + 256].split(None, 1)[0].decode())
+    scaf_names = [name_at(int(off[s])).split(None, 1)[0].decode() for s in np.flatnonzero(newsc)]
     return scaf_ids, scaf_names
 
 
 def ingest_geno(eng, source, geno_format="phased", samples=None, ploidy=None, header=None) -> GenoData:
-    """Like parse_geno, but the text is tokenised ON THE DEVICE (pg_ingest_text): the file's bytes are copied to the
-    GPU as they are and the resident matrix of `eng` is built there.  The returned GenoData has geno = None."""
-    body, header, file_names, samples, fmt, pl, col_take = _prepare(source, geno_format, samples, ploidy, header)
+    """Like parse_geno, but the text is tokenised ON THE DEVICE (pg_ingest_text / pg_ingest_file): the file's bytes are
+    copied to the GPU as they are and the resident matrix of `eng` is built there.  The returned GenoData has
+    geno = None.  A plain file path is read straight into pinned staging buffers by the library."""
+    from_file = isinstance(source, str) and not source.endswith(".gz")
+    if from_file:
+        boff = 0
+        if header is None:
+            with open(source, "rb") as f:
+                first = f.readline()
+            header = first.decode()
+            boff = len(first)
+        file_names, samples, fmt, pl, col_take = _select(header, geno_format, samples, ploidy)
+        data = None
+    else:
+        data, boff, header, file_names, samples, fmt, pl, col_take = _prepare(source, geno_format, samples, ploidy, header)
     n_cols = len(file_names)
     col_hap = np.full(max(n_cols, 1), -1, dtype=np.int32)
     col_pl = np.ones(max(n_cols, 1), dtype=np.int8)
@@ -115,9 +129,19 @@ def ingest_geno(eng, source, geno_format="phased", samples=None, ploidy=None, he
         col_hap[c] = hap_off[k]
         col_pl[c] = pl[k]
     H = int(pl.astype(np.int64).sum())
-    S = eng.ingest_text(body, fmt, col_hap, col_pl, H)
+    if from_file:
+        S = eng.ingest_file(source, boff, fmt, col_hap, col_pl, H)
+    else:
+        S = eng.ingest_text(data, fmt, col_hap, col_pl, H, offset=boff)
     pos, newsc, off = eng.ingest_meta(S)
-    scaf_ids, scaf_names = _scaffold_runs(body, newsc, off)
+    if from_file:
+        with open(source, "rb") as f:
+            def name_at(o):
+                f.seek(boff + o)
+                return f.read(256)
+            scaf_ids, scaf_names = _scaffold_runs(newsc, off, name_at)
+    else:
+        scaf_ids, scaf_names = _scaffold_runs(newsc, off, lambda o: data[boff + o:boff + o + 256])
     return GenoData(geno=None, pos=pos, scaf_ids=scaf_ids, scaf_names=scaf_names, names=samples, ploidy=pl,
                     hap_off=hap_off, header=header)
 
@@ -128,7 +152,8 @@ def parse_geno(source, geno_format="phased", samples=None, ploidy=None, header=N
     samples: sample names to keep (default: every column of the header, genomics.py:1918);
     ploidy: dict sample -> ploidy (default 2; 1 for -f haplo, popgenWindows.py:302);
     header: header text when the file has none (--header)."""
-    body, header, file_names, samples, fmt, pl, col_take = _prepare(source, geno_format, samples, ploidy, header)
+    data, boff, header, file_names, samples, fmt, pl, col_take = _prepare(source, geno_format, samples, ploidy, header)
+    body = data[boff:] if boff else data
     H = int(pl.astype(np.int64).sum())
     L = _lib_parse()
     n = C.c_int64(0)
@@ -144,7 +169,7 @@ def parse_geno(source, geno_format="phased", samples=None, ploidy=None, header=N
                           pl.ctypes.data_as(C.c_void_p), H, S, geno.ctypes.data_as(C.c_void_p),
                           pos.ctypes.data_as(C.c_void_p), newsc.ctypes.data_as(C.c_void_p),
                           off.ctypes.data_as(C.c_void_p), int(threads)), "pg_geno_parse")
-    scaf_ids, scaf_names = _scaffold_runs(body, newsc, off)
+    scaf_ids, scaf_names = _scaffold_runs(newsc, off, lambda o: body[o:o + 256])
     hap_off = np.concatenate([[0], np.cumsum(pl.astype(np.int64))[:-1]]).astype(np.int32) if len(pl) else np.zeros(0, np.int32)
     return GenoData(geno=geno, pos=pos, scaf_ids=scaf_ids, scaf_names=scaf_names, names=list(samples), ploidy=pl,
                     hap_off=hap_off, header=header)

@@ -185,7 +185,12 @@ int pg_geno_parse(const char* buf, size_t len, int32_t fmt, int32_t n_out, const
  * ploidy, genomics.py:1111; a non-integer position; a short line) name the offending data line. */
 int pg_ingest_text(pg_ctx* ctx, const char* buf, size_t len, int32_t fmt, int32_t n_cols, const int32_t* col_hap,
                    const int8_t* col_ploidy, int32_t H_out, int64_t* n_sites);
-/* pos int32 [S], new_scaffold int8 [S], line_off int64 [S] of the last pg_ingest_text (as pg_geno_parse returns them;
+/* The same for a file on disk: bytes [body_offset, EOF) of `path` (body_offset = length of the header line, or 0) are
+ * read straight into the pinned staging buffers by a few host threads — the file is never copied whole into host
+ * memory.  line_off values of pg_ingest_meta are relative to body_offset. */
+int pg_ingest_file(pg_ctx* ctx, const char* path, int64_t body_offset, int32_t fmt, int32_t n_cols, const int32_t* col_hap,
+                   const int8_t* col_ploidy, int32_t H_out, int64_t* n_sites);
+/* pos int32 [S], new_scaffold int8 [S], line_off int64 [S] of the last pg_ingest_text / pg_ingest_file (as pg_geno_parse returns them;
  * any pointer may be NULL). */
 int pg_ingest_meta(pg_ctx* ctx, int32_t* pos, int8_t* new_scaffold, int64_t* line_off);
 /* Frees the device copy of the text. */

@@ -161,3 +161,25 @@ def test_malformed_input_is_reported(eng):
     bad[5] = "\t".join(f)
     with pytest.raises(PgError, match="data line 5.*position"):
         geno_io.ingest_geno(eng, "\n".join(bad).encode(), geno_format="phased")
+
+
+def test_file_path_ingest_equals_bytes_ingest(eng, tmp_path):
+    """pg_ingest_file: the library reads the file itself (pread into pinned staging), header handled by the caller."""
+    from genomics_general_b200 import geno_io
+    names = ["s%02d" % i for i in range(9)]
+    text = _text("phased", 5000, names, [2] * 9, 21, scaffolds=("chrA", "chrB"))
+    path = str(tmp_path / "x.geno")
+    with open(path, "wb") as f:
+        f.write(text)
+    host = geno_io.parse_geno(path, geno_format="phased", samples=names[2:7])
+    dev = geno_io.ingest_geno(eng, path, geno_format="phased", samples=names[2:7])
+    g, p = eng.download(0, host.n_sites)
+    assert np.array_equal(g, host.geno) and np.array_equal(p, host.pos)
+    assert np.array_equal(dev.scaf_ids, host.scaf_ids) and dev.scaf_names == host.scaf_names
+    # gzip goes through host memory
+    import gzip
+    with gzip.open(path + ".gz", "wb") as f:
+        f.write(text)
+    dev2 = geno_io.ingest_geno(eng, path + ".gz", geno_format="phased", samples=names[2:7])
+    g2, _ = eng.download(0, host.n_sites)
+    assert np.array_equal(g2, host.geno) and dev2.scaf_names == host.scaf_names
