@@ -65,6 +65,8 @@ _SIGS = {
     "pg_site_counts": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     "pg_site_target_freqs": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_double, C.c_int32, C.c_void_p,
                                        C.c_void_p]),
+    "pg_sfs": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                         C.c_void_p, C.POINTER(C.c_int64)]),
     "pg_pairdist": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                               C.c_void_p]),
     "pg_pairdist_cat": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_int64)]),

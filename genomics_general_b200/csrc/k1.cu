@@ -1670,3 +1670,179 @@ extern "C" int pg_site_target_freqs(pg_ctx* ctx, int64_t site0, int64_t n, int32
     }
     return PG_OK;
 }
+
+// ================================================================================================
+// pg_sfs — sfs.py's per-site loop for --inputType genotypes (sfs.py:430-470, getTargetCounts 68-92, SparseFS 94-125)
+// ================================================================================================
+namespace {
+struct SfsParams {
+    const uint16_t* counts;     // [n x P x 4] of this slab
+    int64_t n, site0;           // sites of the slab, absolute index of its first site
+    int P, n_in, outgroup;      // in-group = populations 0 .. n_in-1; outgroup = population index or -1
+    int popN[PG_MAX_POPS];      // haplotypes per population: an in-group population must be complete (sfs.py:449)
+    const uint8_t* mask;        // [S] absolute, or nullptr
+    int n_groups;
+    const int32_t* group_off;   // [n_groups+1] into group_pops
+    const int32_t* group_pops;
+    const long long* hist_off;  // [n_groups] first cell of each group's dense histogram
+    unsigned long long* hist;
+    long long* first;           // first site (absolute) that hit the cell
+    unsigned long long* n_counted;
+};
+
+__global__ void __launch_bounds__(256) k1_sfs(const __grid_constant__ SfsParams sp) {
+    const int64_t s = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (s >= sp.n) return;
+    const int64_t site = sp.site0 + s;
+    if (sp.mask && !sp.mask[site]) return;
+    const ushort4* c = reinterpret_cast<const ushort4*>(sp.counts) + s * sp.P;
+    unsigned tot[4] = {0, 0, 0, 0};
+    for (int X = 0; X < sp.n_in; ++X) {
+        const ushort4 v = c[X];
+        if ((int)v.x + v.y + v.z + v.w != sp.popN[X]) return;      // every in-group haplotype must be called (449)
+        tot[0] += v.x;
+        tot[1] += v.y;
+        tot[2] += v.z;
+        tot[3] += v.w;
+    }
+    int target;
+    if (sp.outgroup >= 0) {
+        const ushort4 o = c[sp.outgroup];
+        const unsigned oc[4] = {o.x, o.y, o.z, o.w};
+        int n_all = 0, n_out = 0;
+        for (int a = 0; a < 4; ++a) {
+            n_all += (tot[a] > 0 || oc[a] > 0) ? 1 : 0;
+            n_out += oc[a] > 0 ? 1 : 0;
+        }
+        if (n_all < 1 || n_all > 2) return;                          // 79
+        // `outgroupMono & nOutAlleles != 1` is (outgroupMono & nOutAlleles) != 1: the count must be odd, i.e. 1 (84)
+        if (n_out == 0 || (n_out & 1) != 1) return;
+        target = -1;
+        for (int a = 3; a >= 0; --a)
+            if (tot[a] > 0 && oc[a] == 0) target = a;               // first in-group allele the outgroup lacks (86)
+        if (target < 0)
+            for (int a = 3; a >= 0; --a)
+                if (tot[a] == 0) target = a;                         // invariant: first absent allele (87), count 0
+        if (target < 0) return;
+    } else {
+        int n_all = 0;
+        for (int a = 0; a < 4; ++a) n_all += tot[a] > 0 ? 1 : 0;
+        if (n_all < 1 || n_all > 2) return;
+        // totalBaseCounts.argsort()[-2] (90): second in a stable ascending order = with two alleles the rarer one, the
+        // lower allele on an exact tie; with one allele an absent allele (count 0 everywhere)
+        int best = -1, second = -1;                                  // positions [-1] and [-2] of the stable argsort
+        for (int a = 0; a < 4; ++a) {
+            if (best < 0 || tot[a] >= tot[best]) {
+                second = best;
+                best = a;
+            } else if (second < 0 || tot[a] >= tot[second]) second = a;
+        }
+        target = second;
+    }
+    atomicAdd(sp.n_counted, 1ull);
+    for (int g = 0; g < sp.n_groups; ++g) {
+        long long idx = 0;
+        for (int k = sp.group_off[g]; k < sp.group_off[g + 1]; ++k) {
+            const int X = sp.group_pops[k];
+            const ushort4 v = c[X];
+            const unsigned t = target == 0 ? v.x : (target == 1 ? v.y : (target == 2 ? v.z : v.w));
+            idx = idx * (sp.popN[X] + 1) + t;
+        }
+        atomicAdd(sp.hist + sp.hist_off[g] + idx, 1ull);
+        atomicMin(sp.first + sp.hist_off[g] + idx, (long long)site);
+    }
+}
+}  // namespace
+
+extern "C" int pg_sfs(pg_ctx* ctx, int32_t n_in, int32_t outgroup, int32_t n_groups, const int32_t* group_off,
+                      const int32_t* group_pops, const uint8_t* site_mask, int64_t* hist, int64_t* first, int64_t* n_counted) {
+    PG_CHECK(ctx && group_off && group_pops && hist && first, "pg_sfs: null argument");
+    PG_CHECK(ctx->P >= 1 && ctx->P <= PG_MAX_POPS, "pg_sfs: call pg_set_pops first (at most %d populations)", PG_MAX_POPS);
+    PG_CHECK(n_in >= 1 && n_in <= ctx->P, "pg_sfs: n_in out of range");
+    PG_CHECK(outgroup == -1 || (outgroup >= n_in && outgroup < ctx->P), "pg_sfs: the outgroup must be a population after the in-group");
+    PG_CHECK(n_groups >= 1, "pg_sfs: no spectra requested");
+    PG_CUDA(cudaSetDevice(ctx->device));
+    pg_timings_reset(ctx);
+    const int P = ctx->P;
+    std::vector<int> popN(P, 0);
+    for (int h = 0; h < ctx->H; ++h)
+        if (ctx->hap_pop[h] >= 0) popN[ctx->hap_pop[h]] += 1;
+    std::vector<long long> hist_off(n_groups, 0);
+    long long cells = 0;
+    for (int g = 0; g < n_groups; ++g) {
+        hist_off[g] = cells;
+        long long sz = 1;
+        PG_CHECK(group_off[g + 1] > group_off[g], "pg_sfs: spectrum %d has no population", g);
+        for (int k = group_off[g]; k < group_off[g + 1]; ++k) {
+            PG_CHECK(group_pops[k] >= 0 && group_pops[k] < n_in, "pg_sfs: spectrum %d uses a population outside the in-group", g);
+            sz *= (long long)popN[group_pops[k]] + 1;
+            PG_CHECK(sz <= (1ll << 28), "pg_sfs: spectrum %d is too large for a dense histogram", g);
+        }
+        cells += sz;
+        PG_CHECK(cells <= (1ll << 28), "pg_sfs: the spectra need more than 2^28 cells");
+    }
+    if (n_counted) *n_counted = 0;
+    const int n_gp = group_off[n_groups];
+    // device buffers: histograms | first | tables | counter
+    PG_TRY(ctx->pairs.ensure((size_t)cells * 16 + 64));
+    unsigned long long* d_hist = (unsigned long long*)ctx->pairs.p;
+    long long* d_first = (long long*)(d_hist + cells);
+    PG_CUDA(cudaMemsetAsync(d_hist, 0, (size_t)cells * 8, ctx->stream));
+    PG_CUDA(cudaMemsetAsync(d_first, 0x7f, (size_t)cells * 8, ctx->stream));
+    PG_TRY(ctx->misc2.ensure((size_t)(n_groups + 1) * 4 + (size_t)n_gp * 4 + (size_t)n_groups * 8 + 64 + 64));
+    uint8_t* tb = (uint8_t*)ctx->misc2.p;
+    size_t o = 0;
+    int32_t* d_goff = nullptr;
+    int32_t* d_gpops = nullptr;
+    long long* d_hoff = nullptr;
+    PG_TRY(push(ctx, tb, o, group_off, (size_t)n_groups + 1, &d_goff));
+    PG_TRY(push(ctx, tb, o, group_pops, (size_t)n_gp, &d_gpops));
+    PG_TRY(push(ctx, tb, o, hist_off.data(), (size_t)n_groups, &d_hoff));
+    PG_TRY(ctx->out_i.ensure(64));
+    unsigned long long* d_cnt = (unsigned long long*)ctx->out_i.p;
+    PG_CUDA(cudaMemsetAsync(d_cnt, 0, 8, ctx->stream));
+    uint8_t* d_mask = nullptr;
+    if (site_mask && ctx->S > 0) {
+        PG_TRY(ctx->misc3.ensure((size_t)ctx->S + 64));
+        d_mask = (uint8_t*)ctx->misc3.p;
+        PG_CUDA(cudaMemcpyAsync(d_mask, site_mask, (size_t)ctx->S, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    PG_CUDA(cudaStreamSynchronize(ctx->stream));       // host tables behind the async copies
+    const int64_t stride = (int64_t)P * 4;
+    const int64_t slab = std::max<int64_t>(1, std::min<int64_t>(std::max<int64_t>(ctx->S, 1), (int64_t)(1ll << 28) / (stride * 2)));
+    PG_TRY(ctx->misc.ensure((size_t)slab * stride * 2 + 64));
+    for (int64_t s0 = 0; s0 < ctx->S; s0 += slab) {
+        const int64_t cnt = std::min(slab, ctx->S - s0);
+        PG_TRY(site_counts_slab(ctx, s0, cnt));
+        SfsParams sp;
+        memset(&sp, 0, sizeof(sp));
+        sp.counts = (const uint16_t*)ctx->misc.p;
+        sp.n = cnt;
+        sp.site0 = s0;
+        sp.P = P;
+        sp.n_in = n_in;
+        sp.outgroup = outgroup;
+        for (int X = 0; X < P; ++X) sp.popN[X] = popN[X];
+        sp.mask = d_mask;
+        sp.n_groups = n_groups;
+        sp.group_off = d_goff;
+        sp.group_pops = d_gpops;
+        sp.hist_off = d_hoff;
+        sp.hist = d_hist;
+        sp.first = d_first;
+        sp.n_counted = d_cnt;
+        const int ti = pg_time_begin(ctx, "k1_sfs");
+        k1_sfs<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>(sp);
+        pg_time_end(ctx, ti);
+        PG_CUDA(cudaGetLastError());
+    }
+    unsigned long long h_cnt = 0;
+    PG_CUDA(cudaMemcpyAsync(hist, d_hist, (size_t)cells * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    PG_CUDA(cudaMemcpyAsync(first, d_first, (size_t)cells * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    PG_CUDA(cudaMemcpyAsync(&h_cnt, d_cnt, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    PG_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (long long k = 0; k < cells; ++k)
+        if (hist[k] == 0) first[k] = -1;
+    if (n_counted) *n_counted = (int64_t)h_cnt;
+    return PG_OK;
+}

@@ -485,7 +485,7 @@ __global__ void __launch_bounds__(256) k2_ind_epi(const __grid_constant__ IndEpi
             for (int j = ep.ind_start[b]; j < ep.ind_start[b + 1]; ++j) {
                 double d;
                 if (i == j) {
-                    if (!ep.include_same) continue;          // diagonal = nan (genomics.py:940)
+                    if (!ep.include_same || ep.min_sites > 0) continue;   // diagonal = nan (genomics.py:940; 937-938 masks it too)
                     d = 0.0;                                 // distMatrix leaves 0 on the diagonal (908)
                 } else {
                     const int nij = N[(size_t)ep.mid[i] * ep.Hm + ep.mid[j]];
@@ -617,7 +617,8 @@ __global__ void __launch_bounds__(256) k2_hap_epi(const __grid_constant__ HapEpi
             const int j = wj * 32 + b;
             if (j >= N) break;
             bool m;
-            if (i == j) m = !ep.diag_nan && (0.0 <= ep.max_dist);          // distMatrix leaves 0 on the diagonal
+            // distMatrix leaves 0 on the diagonal; a minSites mask also removes it (pairNonNan's diagonal is 0, 1043)
+            if (i == j) m = !ep.diag_nan && ep.min_sites <= 0 && (0.0 <= ep.max_dist);
             else {
                 const int nij = Nn[(size_t)ep.mid[r0 + i] * ep.Hm + ep.mid[r0 + j]];
                 m = nij > 0 && !(ep.min_sites > 0 && nij < ep.min_sites) &&

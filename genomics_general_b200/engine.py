@@ -272,6 +272,27 @@ class Engine:
                                              _ptr(out), _ptr(tie)), "pg_site_target_freqs")
         return out, tie.astype(bool)
 
+    def sfs(self, n_in: int, groups, pop_sizes, outgroup: int = -1, site_mask=None):
+        """sfs.py for genotype input: `groups` = list of tuples of in-group population indices; pop_sizes[X] = haplotypes of
+        population X.  Returns (list of dense int64 spectra shaped (N_k+1, ...), list of first-site arrays, sites counted)."""
+        goff = np.zeros(len(groups) + 1, dtype=np.int32)
+        for k, grp in enumerate(groups):
+            goff[k + 1] = goff[k] + len(grp)
+        gp = np.array([x for grp in groups for x in grp], dtype=np.int32)
+        shapes = [tuple(int(pop_sizes[x]) + 1 for x in grp) for grp in groups]
+        cells = [int(np.prod(sh)) for sh in shapes]
+        hist = np.zeros(sum(cells), dtype=np.int64)
+        first = np.zeros(sum(cells), dtype=np.int64)
+        mask = None if site_mask is None else np.ascontiguousarray(site_mask, dtype=np.uint8)
+        if mask is not None:
+            assert mask.shape == (self.S,)
+        n = C.c_int64(0)
+        check(self._lib.pg_sfs(self._ctx, int(n_in), int(outgroup), len(groups), _ptr(goff), _ptr(gp), _ptr(mask), _ptr(hist),
+                               _ptr(first), C.byref(n)), "pg_sfs")
+        offs = np.concatenate([[0], np.cumsum(cells)])
+        return ([hist[offs[k]:offs[k + 1]].reshape(shapes[k]) for k in range(len(groups))],
+                [first[offs[k]:offs[k + 1]].reshape(shapes[k]) for k in range(len(groups))], int(n.value))
+
     def pairdist(self, hap_ind, n_ind: int, include_same_with_same: bool = False, min_sites: int = 0):
         """-> dict(dist [W,n_ind,n_ind], sites [W], pos_sum [W]).  min_sites > 0 masks haplotype pairs with fewer
         jointly non-missing sites (what an earlier groupDistStats does to the reference's cached matrix)."""

@@ -115,6 +115,17 @@ int pg_site_counts(pg_ctx* ctx, int64_t site0, int64_t n, uint16_t* counts);
 int pg_site_target_freqs(pg_ctx* ctx, int64_t site0, int64_t n, int32_t target, double min_data, int32_t as_counts,
                          double* out, uint8_t* tie);
 
+/* Replaces the per-site loop of sfs.py for --inputType genotypes without subsampling (sfs.py:430-470: population base
+ * counts, the completeness test of 449, getTargetCounts 68-92) and the SparseFS accumulation (94-125, 484-487).
+ * In-group = populations 0..n_in-1 of pg_set_pops; outgroup = a later population index (polarized spectra) or -1 (the
+ * second most frequent allele, `totalBaseCounts.argsort()[-2]`; on an exact tie of the two alleles the reference depends
+ * on numpy's sort, here the lower allele).  Spectrum g is over the populations group_pops[group_off[g] .. group_off[g+1]);
+ * hist holds the spectra one after the other as dense row-major arrays of prod(N_k + 1) cells, first[cell] = index of
+ * the first site that hit the cell (-1 = empty; gives the reference's first-appearance output order).
+ * site_mask (may be NULL): only sites with mask 1 are counted (--include / --exclude). */
+int pg_sfs(pg_ctx* ctx, int32_t n_in, int32_t outgroup, int32_t n_groups, const int32_t* group_off,
+           const int32_t* group_pops, const uint8_t* site_mask, int64_t* hist, int64_t* first, int64_t* n_counted);
+
 /* Replaces Alignment.indPairDists (genomics.py:934-954) as used by distMat.py:42-45 and popgenWindows.py:54-57.
  * hap_ind[h] = individual index in [0,n_ind) or -1; dist [W x n_ind x n_ind]; n_sites/pos_sum [W] (may be NULL).
  * min_sites > 0: haplotype pairs with n_ij < min_sites are nan — the state of the reference's cached matrix when

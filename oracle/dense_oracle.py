@@ -532,6 +532,72 @@ def four_pop(g, hap_pop, P1, P2, P3, P4, min_data, polarize=False, fixed=False):
 
 
 # ----------------------------------------------------------------------------------------
+# sfs.py, --inputType genotypes without subsampling  (sfs.py:430-470, 68-92, 94-125)
+# ----------------------------------------------------------------------------------------
+def sfs_target_counts(g, hap_pop, n_in, outgroup=-1):
+    """Per-site target-allele counts of the in-group populations: (counts int64 [L, n_in], used bool [L]).
+    A site is used iff every in-group haplotype is called (449) and getTargetCounts (68-92) returns a value."""
+    hap_pop = np.asarray(hap_pop)
+    P = int(hap_pop.max()) + 1
+    c = site_counts(g, hap_pop, P)
+    N = np.array([(hap_pop == x).sum() for x in range(P)])
+    L = c.shape[0]
+    out = np.zeros((L, n_in), dtype=np.int64)
+    used = np.zeros(L, dtype=bool)
+    for s in range(L):
+        cin = c[s, :n_in]
+        if not np.all(cin.sum(axis=1) == N[:n_in]):
+            continue
+        tot = cin.sum(axis=0)
+        alleles = tot > 0
+        if outgroup >= 0:
+            oa = c[s, outgroup] > 0
+            alla = alleles | oa
+            if not 1 <= alla.sum() <= 2:
+                continue
+            n_out = int(oa.sum())
+            if n_out == 0 or (True & n_out) != 1:           # `outgroupMono & nOutAlleles != 1` (84): precedence kept
+                continue
+            cand = np.where(~oa & alleles)[0]
+            target = cand[0] if len(cand) else np.where(~alleles)[0][0]
+        else:
+            if not 1 <= alleles.sum() <= 2:
+                continue
+            target = np.argsort(tot, kind="stable")[-2]     # (90); the reference's unstable sort is free on exact ties
+        out[s] = cin[:, target]
+        used[s] = True
+    return out, used
+
+
+def sfs(g, hap_pop, n_in, groups, outgroup=-1, site_mask=None):
+    """For each group of populations: the spectrum as an insertion-ordered list of (key tuple, count) in the order the
+    reference's nested SparseFS dicts are written (asChains, 117-125): first appearance at each nesting level."""
+    tc, used = sfs_target_counts(g, hap_pop, n_in, outgroup)
+    if site_mask is not None:
+        used = used & np.asarray(site_mask, dtype=bool)
+    out = []
+    for grp in groups:
+        nested = {}
+        for s in np.where(used)[0]:
+            d = nested
+            for x in grp[:-1]:
+                d = d.setdefault(int(tc[s, x]), {})
+            k = int(tc[s, grp[-1]])
+            d[k] = d.get(k, 0) + 1
+        chains = []
+
+        def walk(d, prefix):
+            for k, v in d.items():
+                if isinstance(v, dict):
+                    walk(v, prefix + (k,))
+                else:
+                    chains.append((prefix + (k,), v))
+        walk(nested, ())
+        out.append(chains)
+    return out, int(used.sum())
+
+
+# ----------------------------------------------------------------------------------------
 # window generators restated over (scaffold id, position) arrays -> half-open site ranges
 # ----------------------------------------------------------------------------------------
 def _scaffold_runs(scaf):

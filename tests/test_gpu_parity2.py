@@ -416,3 +416,52 @@ def test_seq_nonnan_bit_exact(eng):
     got = eng.seq_nonnan()
     want = np.stack([(g[a:b] >= 0).sum(axis=0) for a, b in zip(lo, hi)])
     assert np.array_equal(got, want)
+
+
+# ------------------------------------------------------------------------------------------------
+# sfs.py (genotype input)
+# ------------------------------------------------------------------------------------------------
+def _sfs_keys():
+    d = CLI2["four_pops"]
+    return [k for k in d if k.startswith("sfs_") and k + "_args" in d]
+
+
+@pytest.mark.parametrize("key", _sfs_keys())
+def test_sfs_engine_and_cli_match_the_reference_text(eng, key, tmp_path, capsys):
+    from genomics_general_b200 import synth
+    from genomics_general_b200.cli import sfs as sfs_cli
+    from oracle import dense_oracle as do
+    from test_oracle_golden2 import sfs_inputs, sfs_plan
+    d = CLI2["four_pops"]
+    spec, g, scaf = sfs_inputs()
+    extra = d[key + "_args"]
+    inpops, outgroup, groups, keep = sfs_plan(extra)
+    order = inpops + ([outgroup] if outgroup else [])
+    remap = {int(p[3:]): k for k, p in enumerate(order)}
+    hp = np.array([remap[x] for x in spec.hap_pop()], dtype=np.int32)
+    mask = None
+    if keep is not None:
+        mask = np.isin(scaf, keep[1]) if keep[0] else ~np.isin(scaf, keep[1])
+    gi = [tuple(inpops.index(p) for p in grp) for grp in groups]
+    eng.upload(g, None)
+    eng.set_pops(hp, len(order))
+    sizes = [int((hp == x).sum()) for x in range(len(order))]
+    hists, firsts, n = eng.sfs(len(inpops), gi, sizes, outgroup=len(inpops) if outgroup else -1, site_mask=mask)
+    chains, n_or = do.sfs(g, hp, len(inpops), gi, outgroup=len(inpops) if outgroup else -1, site_mask=mask)
+    assert n == n_or
+    text = "".join("\n".join("\t".join(str(x) for x in row) for row in sfs_cli.ordered_chains(h, f)) + "\n"
+                   for h, f in zip(hists, firsts))
+    assert text == d[key]                                   # the unmodified script's own stdout, byte for byte
+    # the command line on a .geno file
+    c = d["sfs_cfg"]
+    path = str(tmp_path / "sfs.geno")
+    scaf_names = ["chr%d" % (k + 1) for k in scaf]
+    synth.write_geno(path, g, synth.synth_positions(c["S"], seed=c["seed"]), scaf_names, spec.sample_names())
+    pops = str(tmp_path / "sfs.pops")
+    with open(pops, "wt") as f:
+        for i, nm in enumerate(spec.sample_names()):
+            f.write("%s pop%d\n" % (nm, i // c["spp"]))
+    capsys.readouterr()
+    sfs_cli.main(["-i", path, "--inputType", "genotypes", "--popsFile", pops, "--pipe", "-p", "pop0", "-p", "pop1", "-p", "pop2",
+                  "-p", "pop3"] + extra)
+    assert capsys.readouterr().out == d[key]

@@ -88,3 +88,75 @@ def test_sample_het_quirk_is_exercised():
         if m["sampleHet"]:
             seen |= bool(np.isnan([m["sampleHet"]["alone"][s] for s in m["sample_names"]]).any())
     assert seen
+
+
+# ------------------------------------------------------------------------------------------------
+# sfs.py (genotype input): the oracle against the reference script's own --pipe output
+# ------------------------------------------------------------------------------------------------
+CLI2 = json.load(open(os.path.join(GOLD, "cli_cases2.json")))["four_pops"]
+
+
+def sfs_inputs():
+    from genomics_general_b200 import synth
+    c = CLI2["sfs_cfg"]
+    spec = synth.SynthSpec(c["n_pops"], c["spp"], seed=c["seed"], miss=0.0)
+    g = synth.synth_genotypes(spec, 0, c["S"])
+    for a, b in CLI2["sfs_missing"]:
+        g[a, b] = -1
+    g[np.array(CLI2["sfs_blank"], dtype=np.int64)] = -1
+    scaf = np.repeat(np.arange(len(c["scaffolds"])), c["scaffolds"])
+    return spec, g, scaf
+
+
+def sfs_plan(extra):
+    """population order / groups / mask the reference derives from the flags of one golden run (sfs.py:369-407)"""
+    import itertools
+    pops = ["pop0", "pop1", "pop2", "pop3"]
+    outgroup = None
+    if "--polarized" in extra:
+        outgroup = pops[-1]
+    if "--outgroup" in extra:
+        outgroup = extra[extra.index("--outgroup") + 1]
+    inpops = [p for p in pops if p != outgroup]
+    if "--FSpops" in extra:
+        groups, cur = [], None
+        for tok in extra:
+            if tok == "--FSpops":
+                cur = []
+                groups.append(cur)
+            elif tok.startswith("--"):
+                cur = None
+            elif cur is not None:
+                cur.append(tok)
+    else:
+        groups = [[p] for p in inpops]
+        for flag, k in (("--doPairs", 2), ("--doTrios", 3), ("--doQuartets", 4)):
+            if flag in extra:
+                groups += [list(c) for c in itertools.combinations(inpops, k)]
+    keep = None
+    for flag, inc in (("--include", True), ("--exclude", False)):
+        if flag in extra:
+            names = []
+            for tok in extra[extra.index(flag) + 1:]:
+                if tok.startswith("--"):
+                    break
+                names.append(tok)
+            keep = (inc, [int(n[3:]) - 1 for n in names])
+    return inpops, outgroup, groups, keep
+
+
+@pytest.mark.parametrize("key", [k for k in CLI2 if k.startswith("sfs_") and k + "_args" in CLI2])
+def test_sfs_oracle_matches_reference_output(key):
+    spec, g, scaf = sfs_inputs()
+    extra = CLI2[key + "_args"]
+    inpops, outgroup, groups, keep = sfs_plan(extra)
+    order = inpops + ([outgroup] if outgroup else [])
+    remap = {int(p[3:]): k for k, p in enumerate(order)}
+    hp = np.array([remap[x] for x in spec.hap_pop()], dtype=np.int32)
+    mask = None
+    if keep is not None:
+        mask = np.isin(scaf, keep[1]) if keep[0] else ~np.isin(scaf, keep[1])
+    chains, _ = do.sfs(g, hp, len(inpops), [tuple(inpops.index(p) for p in grp) for grp in groups],
+                       outgroup=len(inpops) if outgroup else -1, site_mask=mask)
+    text = "".join("\n".join("\t".join(str(x) for x in list(k) + [v]) for k, v in ch) + "\n" for ch in chains)
+    assert text == CLI2[key]
