@@ -9,7 +9,7 @@ import sys
 
 import numpy as np
 
-from .. import genomics
+from .. import genomics, geno_io
 from ..engine import Engine
 from . import _common as C
 
@@ -63,37 +63,37 @@ def main(argv=None):
     with eng:
         C.ensure_resident(eng, gd)
         eng.set_pops(C.hap_pop_vector(gd, popNames, popInds), P)
-        slab = 1 << 20
-        scaf = np.array(gd.scaf_names, dtype=object)
+        # rows are formatted by native host threads (pg_format_freq_rows) and written as bytes
+        raw = out.buffer if hasattr(out, "buffer") else None
+        if raw is not None:
+            out.flush()
+
+        def emit(segments):
+            for seg in segments:
+                if raw is not None:
+                    raw.write(seg)
+                else:
+                    out.write(bytes(seg).decode())
+        slab = 1 << 21
         for s in range(0, gd.n_sites, slab):
             n = min(slab, gd.n_sites - s)
+            ids, pos = gd.scaf_ids[s:s + n], gd.pos[s:s + n]
             if args.target:
                 # freq.py:302-304: with a target the user's --asCounts / --keepNanLines / --minData apply
                 v, _ = eng.site_target_freqs(args.target, s, n, min_data=args.minData, as_counts=args.asCounts)
                 if args.asCounts:
-                    v = v.astype(np.int64)
-                    keep = np.arange(n) if args.keepNanLines else np.where(~np.all(v == 0, axis=1))[0]
+                    keep = None if args.keepNanLines else ~np.all(v == 0, axis=1)
+                    emit(geno_io.format_freq_rows(2, v, pos, ids, gd.scaf_names, keep))
                 else:
                     v = np.around(v, 4)                                       # freq.py:91
                     if args.threshold:                                        # freq.py:96-98
                         hi, lo = v >= args.threshold, v < args.threshold
                         v[hi] = 1
                         v[lo] = 0
-                    keep = np.arange(n) if args.keepNanLines else np.where(~np.all(np.isnan(v), axis=1))[0]
-                vs = v.astype(str)
-                names = scaf[gd.scaf_ids[s:s + n]]
-                pos = gd.pos[s:s + n]
-                for i in keep:
-                    out.write(names[i] + "\t" + str(pos[i]) + "\t" + "\t".join(vs[i]) + "\n")
+                    keep = None if args.keepNanLines else ~np.all(np.isnan(v), axis=1)
+                    emit(geno_io.format_freq_rows(1, v, pos, ids, gd.scaf_names, keep))
                 continue
-            c = eng.site_counts(s, n).astype(np.int64)                      # [n, P, 4]
-            cs = c.astype(str)
-            cols = [np.char.add(np.char.add(np.char.add(cs[:, x, 0], ","), np.char.add(cs[:, x, 1], ",")),
-                                np.char.add(np.char.add(cs[:, x, 2], ","), cs[:, x, 3])) for x in range(P)]
-            names = scaf[gd.scaf_ids[s:s + n]]
-            pos = gd.pos[s:s + n]
-            for i in range(n):
-                out.write(names[i] + "\t" + str(pos[i]) + "\t" + "\t".join(col[i] for col in cols) + "\n")
+            emit(geno_io.format_freq_rows(0, eng.site_counts(s, n), pos, ids, gd.scaf_names))
     if out is not sys.stdout:
         out.close()
     sys.stderr.write("\nDone\n")

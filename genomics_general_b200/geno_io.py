@@ -173,3 +173,57 @@ def parse_geno(source, geno_format="phased", samples=None, ploidy=None, header=N
     hap_off = np.concatenate([[0], np.cumsum(pl.astype(np.int64))[:-1]]).astype(np.int32) if len(pl) else np.zeros(0, np.int32)
     return GenoData(geno=geno, pos=pos, scaf_ids=scaf_ids, scaf_names=scaf_names, names=list(samples), ploidy=pl,
                     hap_off=hap_off, header=header)
+
+
+def format_freq_rows(mode, data, pos, scaf_ids, scaf_names, keep=None, threads=None):
+    """freq.py's output rows for a block of sites, formatted by native host threads (pg_format_freq_rows).
+    mode 0: data uint16 [n,P,4] counts; 1: float64 [n,P] (numpy's float -> str); 2: float64 [n,P] as integers.
+    Returns a list of memoryviews to write in order."""
+    n, P = int(data.shape[0]), int(data.shape[1])
+    if n == 0:
+        return []
+    if threads is None:
+        threads = min(16, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
+    threads = max(1, min(int(threads), n))
+    data = np.ascontiguousarray(data, dtype=np.uint16 if mode == 0 else np.float64)
+    pos = np.ascontiguousarray(pos, dtype=np.int32)
+    scaf_ids = np.ascontiguousarray(scaf_ids, dtype=np.int32)
+    names = (C.c_char_p * len(scaf_names))(*[s.encode() for s in scaf_names])
+    longest = max((len(s) for s in scaf_names), default=0)
+    per_row = longest + 16 + P * 48
+    seg_cap = ((n + threads - 1) // threads + 1) * per_row
+    buf = np.empty(threads * seg_cap, dtype=np.uint8)
+    seg_len = np.zeros(threads, dtype=np.uint64)
+    kp = None if keep is None else np.ascontiguousarray(keep, dtype=np.uint8)
+    check(_lib.lib().pg_format_freq_rows(int(mode), data.ctypes.data_as(C.c_void_p), n, P, pos.ctypes.data_as(C.c_void_p),
+                                         scaf_ids.ctypes.data_as(C.c_void_p), C.cast(names, C.c_void_p),
+                                         None if kp is None else kp.ctypes.data_as(C.c_void_p),
+                                         buf.ctypes.data_as(C.c_void_p), seg_cap, threads, seg_len.ctypes.data_as(C.c_void_p)),
+          "pg_format_freq_rows")
+    mv = memoryview(buf)
+    return [mv[t * seg_cap: t * seg_cap + int(seg_len[t])] for t in range(threads)]
+
+
+def format_matrix_rows(m, sep=" ", prefixes=None, threads=None) -> str:
+    """Rows of a float64 matrix as newline-terminated text, numbers printed like numpy's float64 -> str
+    (pg_format_matrix_rows); `prefixes` = one string per row or None."""
+    m = np.ascontiguousarray(m, dtype=np.float64)
+    rows, cols = m.shape
+    if rows == 0:
+        return ""
+    if threads is None:
+        threads = min(16, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
+    threads = max(1, min(int(threads), rows, max(1, rows * cols // 4096)))
+    pre = None
+    longest = 0
+    if prefixes is not None:
+        enc = [p.encode() for p in prefixes]
+        longest = max(len(e) for e in enc)
+        pre = (C.c_char_p * rows)(*enc)
+    seg_cap = ((rows + threads - 1) // threads + 1) * (longest + cols * 42 + 2)
+    buf = np.empty(threads * seg_cap, dtype=np.uint8)
+    seg_len = np.zeros(threads, dtype=np.uint64)
+    check(_lib.lib().pg_format_matrix_rows(m.ctypes.data_as(C.c_void_p), rows, cols, ord(sep),
+                                           None if pre is None else C.cast(pre, C.c_void_p), buf.ctypes.data_as(C.c_void_p),
+                                           seg_cap, threads, seg_len.ctypes.data_as(C.c_void_p)), "pg_format_matrix_rows")
+    return b"".join(buf[t * seg_cap: t * seg_cap + int(seg_len[t])].tobytes() for t in range(threads)).decode()

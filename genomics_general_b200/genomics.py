@@ -447,25 +447,25 @@ def parseGenoFile(genoFile, headerLine=None, names=None, includePositions=False,
 
 
 # ------------------------------------------------------------------------------------------------
-def _fmt_rows(distArray, roundTo):
-    """rows of a distance matrix as space-joined strings — numpy's own float->str conversion after rounding,
-    which is exactly what the reference prints (genomics.py:2288-2306)"""
-    return [" ".join(r) for r in np.asarray(distArray).round(roundTo).astype(str)]
+def _rounded(distArray, roundTo):
+    return np.asarray(distArray, dtype=np.float64).round(roundTo)
 
 
 def makeDistMatString(distArray, roundTo=10):
-    return "\n".join(_fmt_rows(distArray, roundTo))
+    """genomics.py:2288-2289: rows joined with spaces, no trailing newline.  Numbers are printed by the native formatter
+    (pg_format_matrix_rows) exactly as numpy's round(roundTo).astype(str) prints them."""
+    return geno_io.format_matrix_rows(_rounded(distArray, roundTo))[:-1]
 
 
 def makeDistMatPhylipString(distArray, names, roundTo=10):
-    rows = _fmt_rows(distArray, roundTo)
-    return "%d\n" % np.asarray(distArray).shape[0] + "".join("%s  %s\n" % (nm, r) for nm, r in zip(names, rows))
+    m = _rounded(distArray, roundTo)
+    return "%d\n" % m.shape[0] + geno_io.format_matrix_rows(m, prefixes=["%s  " % nm for nm in names])
 
 
 def makeDistMatNexusString(distArray, names, roundTo=10):
-    rows = _fmt_rows(distArray, roundTo)
+    m = _rounded(distArray, roundTo)
     taxa = "".join("[%d] '%s'\n" % (i + 1, nm) for i, nm in enumerate(names))
-    body = "".join("[%d] '%s'    %s\n" % (i + 1, nm, r) for i, (nm, r) in enumerate(zip(names, rows)))
+    body = geno_io.format_matrix_rows(m, prefixes=["[%d] '%s'    " % (i + 1, nm) for i, nm in enumerate(names)])
     return ("\nBEGIN Taxa;\nDIMENSIONS ntax=%d;\nTAXLABELS\n%s;\nEND; [Taxa]\n"
             "\nBEGIN Distances;\nDIMENSIONS ntax=%d;\nFORMAT labels=left diagonal triangle=both;\nMATRIX\n%s;\nEND; [Distances]\n"
             % (len(names), taxa, len(names), body))

@@ -187,6 +187,22 @@ int pg_geno_parse(const char* buf, size_t len, int32_t fmt, int32_t n_out, const
                   const int8_t* ploidy, int32_t H_out, int64_t n_lines, int8_t* geno, int32_t* pos,
                   int8_t* new_scaffold, int64_t* line_off, int32_t n_threads);
 
+/* ---- host-side output rows (no CUDA) ------------------------------------------------------------- */
+/* Replaces the row assembly of freq.py (freq.py:100-111) for n sites: "<scaffold>\t<position>\t<col>...\n".
+ * mode 0: data = counts uint16 [n x P x 4], a column is "cA,cC,cG,cT"; mode 1: data = double [n x P] printed like
+ * numpy's float64 -> str ("0.25", "1.0", "nan"); mode 2: double [n x P] printed as integers (--asCounts).
+ * keep (may be NULL): uint8 [n], rows with 0 are skipped.  Thread t formats its share of the sites into
+ * out + t * seg_cap and reports the bytes written in seg_len[t]; the caller writes the segments in order. */
+int pg_format_freq_rows(int32_t mode, const void* data, int64_t n, int32_t P, const int32_t* pos, const int32_t* scaf_id,
+                        const char* const* scaf_names, const uint8_t* keep, char* out, size_t seg_cap, int32_t n_threads,
+                        size_t* seg_len);
+
+/* Rows of a float64 matrix [rows x cols] as text, "<prefix[r]><v0><sep><v1>...\n" with numbers printed like numpy's
+ * float64 -> str: the " ".join(row) over ndarray.round(roundTo).astype(str) of makeDistMat*String (genomics.py:2288-2306)
+ * for distMat.py's per-window matrices (the caller rounds).  prefix may be NULL.  Segments as in pg_format_freq_rows. */
+int pg_format_matrix_rows(const double* v, int64_t rows, int32_t cols, int32_t sep, const char* const* prefix, char* out,
+                          size_t seg_cap, int32_t n_threads, size_t* seg_len);
+
 /* ---- device-side .geno text ingest --------------------------------------------------------------- */
 /* Same job and grammar as pg_geno_parse, on the GPU: the text (complete data lines, no header line) is copied to
  * device memory as it is and tokenised there, straight into this ctx's resident matrix (replaces pg_geno_parse +

@@ -36,8 +36,11 @@ with Engine(0) as eng:
         print("P=%d spp=%d S=%d %-40s %s" % (P, spp, S, cfg or "(default)", " | ".join(out)), flush=True)
 '''
 shapes = [("8", "100", "8000000"), ("4", "50", "10000000"), ("2", "10", "20000000")]
-cfgs = ["", "PG_K1_NW=8", "PG_K1_NO_BYTES=1", "PG_K1_NO_BYTES=1 PG_K1_NW=8", "PG_K1_G=1", "PG_K1_G=1 PG_K1_NW=8", "PG_K1_G=4",
-        "PG_K1_TILE_KB=32", "PG_K1_TILE_KB=128"]
+cfgs = ["", "PG_K1_NW=8", "PG_K1_NW=12", "PG_K1_NO_BYTES=1", "PG_K1_G=1", "PG_K1_G=4", "PG_K1_TILE_KB=32", "PG_K1_TILE_KB=128"]
+if len(sys.argv) > 1:
+    cfgs = sys.argv[1].split(";")
+if len(sys.argv) > 2:
+    shapes = [tuple(x.split(",")) for x in sys.argv[2].split(";")]
 for sh in shapes:
     r = subprocess.run([sys.executable, "-c", code] + list(sh) + [";".join(cfgs)], stdout=subprocess.PIPE,
                        stderr=subprocess.STDOUT, text=True, timeout=600)
