@@ -458,7 +458,36 @@ def main():
                     t_best = (t2 - t0, t1 - t0)
             res_t[how] = {"sites_per_s": St / t_best[0], "tokenize_s": t_best[1], "total_s": t_best[0],
                           "text_GBps": len(text) / t_best[1] / 1e9}
-        os.remove(tpath)
+        # the complete drop-in command lines on that file (argument parsing -> text ingest -> windows -> statistics -> rows)
+        from genomics_general_b200.cli import freq as freq_cli, popgenWindows as pgw_cli
+        ppath, opath = tpath + ".pops", tpath + ".out"
+        with open(ppath, "wt") as f:
+            for i, nm in enumerate(spec_t.sample_names()):
+                f.write("%s pop%d\n" % (nm, i // SAMPLES_PER_POP))
+        popargs = []
+        for k in range(N_POPS):
+            popargs += ["-p", "pop%d" % k]
+        err_, sys.stderr = sys.stderr, open(os.devnull, "w")
+        try:
+            cli_t = {}
+            for name, fn, argv in (
+                    ("popgenWindows.py -w 50000 -m 100 -f phased", pgw_cli.main,
+                     ["-w", str(WIND_SIZE), "-m", str(MIN_SITES), "-g", tpath, "-o", opath, "-f", "phased", "--popsFile", ppath] + popargs),
+                    ("freq.py -f phased (one row of counts per site)", freq_cli.main,
+                     ["-g", tpath, "-o", opath, "-f", "phased", "--popsFile", ppath] + popargs)):
+                best = None
+                for _ in range(2):
+                    t0 = time.perf_counter()
+                    fn(argv)
+                    dt_ = time.perf_counter() - t0
+                    best = dt_ if best is None else min(best, dt_)
+                cli_t[name] = {"wall_s": best, "sites_per_s": St / best, "output_bytes": os.path.getsize(opath)}
+        finally:
+            sys.stderr.close()
+            sys.stderr = err_
+        res_t["whole command line, in process"] = cli_t
+        for pth in (tpath, ppath, opath):
+            os.remove(pth)
         g_back, _ = eng.download(0, min(St, 100000))
         assert np.array_equal(g_back, gt[:len(g_back)])
         variants["from .geno text (C2 shape, %d sites, %.0f MB)" % (St, len(text) / 1e6)] = dict(

@@ -22,6 +22,11 @@ def run(name, P, spp, S, miss, what, wsites=5000, eng=None, reps=2):
             out["paths"] = np.bincount(r["path"], minlength=3).tolist()
         elif what == "abba":
             eng.set_pops(spec.hap_pop(), P); r = eng.abbababa(0, 1, 2, P - 1, 0.5)
+        elif what == "fourpop":
+            eng.set_pops(spec.hap_pop(), P); r = eng.fourpop(0, 1, 2, P - 1, 0.5)
+        elif what == "distcat":
+            hap_ind = np.repeat(np.arange(spec.n_samples, dtype=np.int32), 2)
+            r = eng.pairdist_cat(hap_ind, spec.n_samples, False)
         elif what == "counts":
             eng.set_pops(spec.hap_pop(), P); n = min(S, 2_000_000); r = eng.site_counts(0, n); out["count_sites"] = n
         elif what == "distmat":
@@ -30,7 +35,7 @@ def run(name, P, spp, S, miss, what, wsites=5000, eng=None, reps=2):
         out["wall_ms"] = round((time.perf_counter() - t) * 1e3, 2)
         out["kernel_ms"] = tm(eng)
     k = out["kernel_ms"]
-    main = {"popgen": "k1_popgen", "abba": "k1_abba", "counts": "k1_counts"}.get(what)
+    main = {"popgen": "k1_popgen", "abba": "k1_abba", "counts": "k1_counts", "fourpop": "k1_fourpop"}.get(what)
     if main and main in k:
         n = out.get("count_sites", S)
         out["k1_GBps"] = round(n * (H + 4) / (k[main] * 1e-3) / 1e9, 1)
@@ -46,7 +51,9 @@ if __name__ == "__main__":
         run("C2 popgen 4x50 10M", 4, 50, int(10_000_000 * scale), 0.0, "popgen", eng=eng)
         run("C2 popgen 4x50 10M miss", 4, 50, int(10_000_000 * scale), 0.02, "popgen", eng=eng)
         run("C3 abba 4x50 10M", 4, 50, int(10_000_000 * scale), 0.02, "abba", eng=eng)
+        run("C3 fourpop 4x50 10M", 4, 50, int(10_000_000 * scale), 0.02, "fourpop", eng=eng)
         run("C4 distmat 500 2M", 1, 500, int(2_000_000 * scale), 0.02, "distmat", eng=eng, reps=1)
+        run("C4 distmat --windType cat 500 2M", 1, 500, int(2_000_000 * scale), 0.02, "distcat", eng=eng, reps=1)
         run("C5 popgen 8x100 (1/8 of 100M)", 8, 100, int(12_500_000 * scale), 0.0, "popgen", eng=eng)
         run("C5 freq counts 8x100", 8, 100, int(12_500_000 * scale), 0.02, "counts", eng=eng)
         run("C5 popgen 8x100 miss (1M sites)", 8, 100, int(1_000_000 * scale), 0.02, "popgen", eng=eng, reps=1)
