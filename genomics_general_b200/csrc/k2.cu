@@ -384,6 +384,8 @@ struct PopEpiParams {
     unsigned long long* rec;    // device record table [W x RC]: pi at word 3, then dxy, then fst
     int RC;
     const int64_t* win_idx;     // [nb] global window index of each batch entry
+    double* blk_s;              // [nb][P(P+1)/2] block sums (stage 1 -> stage 2)
+    long long* blk_c;           // [nb][P(P+1)/2] block counts
 };
 
 __device__ __forceinline__ double nanmean_min_dev(double sum, double nonnan, double size, double min_data) {
@@ -395,43 +397,51 @@ __device__ __forceinline__ double nanmean_min_dev(double sum, double nonnan, dou
     return sum / nonnan;
 }
 
-__global__ void __launch_bounds__(256) k2_popgen_epi(const __grid_constant__ PopEpiParams ep) {
-    extern __shared__ __align__(16) uint8_t esm[];
-    const int P = ep.P;
-    const int nblk = P * (P + 1) / 2;
-    double* blk_s = reinterpret_cast<double*>(esm);                 // [nblk] upper-triangle sums
-    long long* blk_c = reinterpret_cast<long long*>(blk_s + nblk);  // [nblk] upper-triangle counts
+// Stage 1: one CTA per (population block X <= Y, window) sums d_ij = diff/n over the block's valid pairs in a fixed order.
+__global__ void __launch_bounds__(256) k2_popgen_epi_blocks(const __grid_constant__ PopEpiParams ep) {
     __shared__ double sh_s[8];
     __shared__ long long sh_c[8];
-    const int wb = blockIdx.x;
+    const int P = ep.P;
+    const int wb = blockIdx.y;
+    int bi = blockIdx.x, X = 0;
+    while (bi >= P - X) {           // decode the upper-triangular block index
+        bi -= P - X;
+        ++X;
+    }
+    const int Y = X + bi;
     const size_t HH = (size_t)ep.Hk * ep.Hk;
     const int32_t* D = ep.diff + (size_t)wb * HH;
     const int32_t* N = ep.n + (size_t)wb * ep.Hm * ep.Hm;
-    int bi = 0;
-    for (int X = 0; X < P; ++X)
-        for (int Y = X; Y < P; ++Y, ++bi) {
-            const int r0 = ep.pop_start[X], r1 = ep.pop_start[X + 1];
-            const int c0 = ep.pop_start[Y], c1 = ep.pop_start[Y + 1];
-            const int nr = r1 - r0, nc = c1 - c0;
-            double s = 0.0;
-            long long c = 0;
-            const int total = nr * nc;
-            for (int idx = threadIdx.x; idx < total; idx += 256) {
-                const int i = r0 + idx / nc, j = c0 + idx % nc;
-                if (X == Y && j <= i) continue;
-                const int nij = N[(size_t)ep.mid[i] * ep.Hm + ep.mid[j]];
-                if (nij == 0 || (ep.min_sites > 0 && nij < ep.min_sites)) continue;   // nan entries
-                s += (double)D[(size_t)i * ep.Hk + j] / (double)nij;
-                c += 1;
-            }
-            block_sum(s, c, sh_s, sh_c);
-            if (threadIdx.x == 0) {
-                blk_s[bi] = s;
-                blk_c[bi] = c;
-            }
-        }
-    __syncthreads();
-    if (threadIdx.x != 0) return;
+    const int r0 = ep.pop_start[X], r1 = ep.pop_start[X + 1];
+    const int c0 = ep.pop_start[Y], c1 = ep.pop_start[Y + 1];
+    const int nr = r1 - r0, nc = c1 - c0;
+    double s = 0.0;
+    long long c = 0;
+    const int total = nr * nc;
+    for (int idx = threadIdx.x; idx < total; idx += 256) {
+        const int i = r0 + idx / nc, j = c0 + idx % nc;
+        if (X == Y && j <= i) continue;
+        const int nij = N[(size_t)ep.mid[i] * ep.Hm + ep.mid[j]];
+        if (nij == 0 || (ep.min_sites > 0 && nij < ep.min_sites)) continue;   // nan entries
+        s += (double)D[(size_t)i * ep.Hk + j] / (double)nij;
+        c += 1;
+    }
+    block_sum(s, c, sh_s, sh_c);
+    if (threadIdx.x == 0) {
+        const int nblk = P * (P + 1) / 2;
+        ep.blk_s[(size_t)wb * nblk + blockIdx.x] = s;
+        ep.blk_c[(size_t)wb * nblk + blockIdx.x] = c;
+    }
+}
+
+// Stage 2: block sums -> pi / dxy / Fst of one window per thread (nanmean_min fractions, genomics.py:976-993).
+__global__ void __launch_bounds__(128) k2_popgen_epi_final(const __grid_constant__ PopEpiParams ep, int nb) {
+    const int wb = blockIdx.x * 128 + threadIdx.x;
+    if (wb >= nb) return;
+    const int P = ep.P;
+    const int nblk = P * (P + 1) / 2;
+    const double* blk_s = ep.blk_s + (size_t)wb * nblk;
+    const long long* blk_c = ep.blk_c + (size_t)wb * nblk;
     const int npairs = P * (P - 1) / 2;
     double* pi_o = reinterpret_cast<double*>(ep.rec + (size_t)ep.win_idx[wb] * ep.RC + 3);
     double* dxy_o = pi_o + P;
@@ -953,7 +963,6 @@ int pg_k2_popgen_windows(pg_ctx* ctx, const std::vector<int64_t>& wins, int32_t 
     PG_TRY(ctx->misc.ensure((size_t)(P + 1) * 4 + per_batch * 8 + 128));
     PG_CUDA(cudaMemcpyAsync(ctx->misc.p, pop_start.data(), (size_t)(P + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
     int64_t* d_widx = reinterpret_cast<int64_t*>((uint8_t*)ctx->misc.p + (((size_t)(P + 1) * 4 + 63) / 64) * 64);
-    const int epi_smem = P * (P + 1) / 2 * 16 + 64;
     for (size_t b0 = 0; b0 < wins.size(); b0 += per_batch) {
         const size_t nb = std::min(per_batch, wins.size() - b0);
         std::vector<int64_t> blo(nb), bhi(nb);
@@ -977,10 +986,16 @@ int pg_k2_popgen_windows(pg_ctx* ctx, const std::vector<int64_t>& wins, int32_t 
         ep.rec = (unsigned long long*)d_rec;
         ep.RC = RC;
         ep.win_idx = d_widx;
+        const int nblk = P * (P + 1) / 2;
+        PG_TRY(ctx->misc5.ensure(nb * (size_t)nblk * 16 + 64));
+        ep.blk_s = (double*)ctx->misc5.p;
+        ep.blk_c = (long long*)(ep.blk_s + nb * (size_t)nblk);
         const int ti = pg_time_begin(ctx, "k2_popgen_epi");
-        k2_popgen_epi<<<(unsigned)nb, 256, epi_smem, ctx->stream>>>(ep);
+        k2_popgen_epi_blocks<<<dim3((unsigned)nblk, (unsigned)nb), 256, 0, ctx->stream>>>(ep);
+        k2_popgen_epi_final<<<(unsigned)((nb + 127) / 128), 128, 0, ctx->stream>>>(ep, (int)nb);
         pg_time_end(ctx, ti);
         PG_CUDA(cudaGetLastError());
+        ctx->launches += 1;
         PG_CUDA(cudaStreamSynchronize(ctx->stream));     // host vectors and scratch are reused by the next batch
     }
     return PG_OK;
