@@ -465,3 +465,30 @@ def test_sfs_engine_and_cli_match_the_reference_text(eng, key, tmp_path, capsys)
     sfs_cli.main(["-i", path, "--inputType", "genotypes", "--popsFile", pops, "--pipe", "-p", "pop0", "-p", "pop1", "-p", "pop2",
                   "-p", "pop3"] + extra)
     assert capsys.readouterr().out == d[key]
+
+
+def test_popgenWindows_haplo_and_pairs_formats_cli(inputs2, tmp_path):
+    """-f haplo (ploidy 1) and -f pairs through the device tokenizer, against the reference script's rows."""
+    from genomics_general_b200 import geno_io, synth
+    from genomics_general_b200.cli import popgenWindows
+    d = CLI2["four_pops"]
+    c = d["haplo_cfg"]
+    spec = synth.SynthSpec(c["n_pops"], c["spp"], ploidy=1, seed=c["seed"], miss=c["miss"])
+    g = synth.synth_genotypes(spec, 0, c["S"])
+    hpath = str(tmp_path / "haplo.geno")
+    synth.write_geno(hpath, g, synth.synth_positions(c["S"], seed=c["seed"]), ["chr1"] * c["S"], spec.sample_names(), ploidy=1,
+                     fmt="haplo")
+    hpops = str(tmp_path / "haplo.pops")
+    with open(hpops, "wt") as f:
+        for i, n in enumerate(spec.sample_names()):
+            f.write("%s pop%d\n" % (n, i // c["spp"]))
+    o = str(tmp_path / "o.csv")
+    base = ["-o", o, "-T", "1", "--roundTo", "9", "-w", "20000", "-m", "50"]
+    popgenWindows.main(base + ["-g", hpath, "-f", "haplo", "--popsFile", hpops, "-p", "pop0", "-p", "pop1", "-p", "pop2"])
+    _compare_by_column(open(o).read(), d["popgen_haplo"], atol=2e-9)
+    # pairs: the four_pops input re-written without separators
+    gd = geno_io.parse_geno(inputs2["geno"], geno_format="phased")
+    ppath = str(tmp_path / "pairs.geno")
+    synth.write_geno(ppath, gd.geno, gd.pos, [gd.scaf_names[k] for k in gd.scaf_ids], gd.names, fmt="pairs")
+    popgenWindows.main(base + ["-g", ppath, "-f", "pairs", "--popsFile", inputs2["pops"]] + inputs2["popargs"])
+    _compare_by_column(open(o).read(), d["popgen_pairs"], atol=2e-9)
