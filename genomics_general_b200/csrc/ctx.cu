@@ -210,7 +210,7 @@ static int env_int(const char* name, int dflt) {
 // Tile geometry: 8 consumer warps per CTA are split into teams of `wpt` warps; one team owns one tile
 // (T consecutive sites) at a time, so up to 8/wpt tiles are being consumed while `stages` tiles sit in the
 // TMA ring.  G lanes share one site row when a row is too long for one lane's tile share.
-K1Plan pg_make_k1_plan(int64_t S, int H, int sm_count, int table_bytes, int nw) {
+K1Plan pg_make_k1_plan(int64_t S, int H, int sm_count, int table_bytes, int nw, int force_G) {
     K1Plan p;
     memset(&p, 0, sizeof(p));
     p.pitch = pg_pitch_for(H);
@@ -221,6 +221,7 @@ K1Plan pg_make_k1_plan(int64_t S, int H, int sm_count, int table_bytes, int nw) 
     // lanes per site: keep one lane's walk below ~64 chunks (measured: 1600-haplotype rows run 20 % faster with G = 2),
     // and a 32/G-site slab inside the tile target
     while (G < 32 && (p.chunks / G > 64 || (32 / G) * p.pitch > tile_target)) G *= 2;
+    if (force_G > 0) G = force_G;           // lane-per-population variant: G = number of populations
     // warps per tile: the largest team (dividing the consumer-warp count) whose tile still fits the target
     const int wpt_max = (nw % 8 == 0) ? 8 : 4;
     while (wpt < wpt_max && (32 * (wpt * 2) / G) * p.pitch <= tile_target) wpt *= 2;
@@ -229,7 +230,7 @@ K1Plan pg_make_k1_plan(int64_t S, int H, int sm_count, int table_bytes, int nw) 
         if (I < 1) I = 1;
         if (I > 8) I = 8;
     }
-    G = env_int("PG_K1_G", G);
+    if (force_G <= 0) G = env_int("PG_K1_G", G);
     wpt = env_int("PG_K1_WPT", wpt);
     I = env_int("PG_K1_I", I);
     p.G = G;

@@ -47,6 +47,7 @@ struct K1Params {
     // ABBA / FOURPOP: minimum non-missing count per population (exact integer form of n/N >= minData)
     int thr[4];
     int acc_limit;           // POPGEN: sites a lane may add to its 32-bit sums between flushes
+    int lanepop;             // POPGEN: launch the lane-per-population variant (G == P lanes per site)
     int bytes;               // POPGEN: every population has <= 255 haplotypes -> byte-packed counts (IDP.4A statistics)
     int variant;             // FOURPOP allele choice: 0 = third of argsort (the rarer allele), 1 = polarize, 2 = fixed
     // COUNTS
@@ -242,6 +243,34 @@ __device__ __forceinline__ double f4c_dev(double p1, double p2, double p3, doubl
 // np.amax propagates nan
 __device__ __forceinline__ double nmax(double a, double b) { return (a != a) ? a : ((b != b) ? b : (a > b ? a : b)); }
 
+// TMA producer (one elected lane of the producer warp): keeps the ring of tiles full.
+template <int MODE>
+__device__ __forceinline__ void k1_producer(const K1Params& prm, uint8_t* tiles, uint64_t* full, uint64_t* empty,
+                                            volatile int* s_issued, int ntiles, int64_t t0) {
+    for (int it = 0; it < ntiles; ++it) {
+        const int stage = it % prm.stages;
+        if (it >= prm.stages) mbar_wait(&empty[stage], (uint32_t)(((it / prm.stages) - 1) & 1));
+        const int64_t s_lo = prm.site_begin + (t0 + it) * prm.T;
+        int64_t rows = prm.site_end - s_lo;
+        if (rows > prm.T) rows = prm.T;
+        const uint32_t bytes = (uint32_t)(rows * prm.pitch);
+        // positions of the tile ride along (rounded up to 16 bytes; the array has zeroed slack)
+        const uint32_t pbytes = (MODE == MODE_COUNTS) ? 0u : (uint32_t)(((rows * 4 + 15) / 16) * 16);
+        mbar_expect_tx(&full[stage], bytes + pbytes);
+        const uint8_t* src = prm.geno + s_lo * prm.pitch;
+        uint8_t* dst = tiles + (size_t)stage * prm.tile_bytes;
+        for (uint32_t off = 0; off < bytes; off += 32768u) {
+            const uint32_t n = (bytes - off) < 32768u ? (bytes - off) : 32768u;
+            bulk_g2s(dst + off, src + off, n, &full[stage]);
+        }
+        if (pbytes) bulk_g2s(dst + (size_t)prm.T * prm.pitch, prm.pos + s_lo, pbytes, &full[stage]);
+        // publish "tile `it` is armed": a consumer must not test a phase parity before its phase has
+        // been armed, or try_wait.parity would alias it with the previous (already complete) phase
+        __threadfence_block();
+        *s_issued = it + 1;
+    }
+}
+
 // BYTES (POPGEN modes, every population <= 255 haplotypes): the four allele counts of a population travel as the
 // bytes of one word, so that sum c^2 and sum c_X c_Y are ONE IDP.4A each, accumulate included.
 template <int MODE, int P, int NW, bool BYTES = false>
@@ -277,31 +306,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k1_site_pass(const __grid_co
     __syncthreads();
 
     if (warp == NW) {
-        // ---------------- TMA producer: one elected lane keeps the ring full ----------------
-        if (lane == 0) {
-            for (int it = 0; it < ntiles; ++it) {
-                const int stage = it % prm.stages;
-                if (it >= prm.stages) mbar_wait(&empty[stage], (uint32_t)(((it / prm.stages) - 1) & 1));
-                const int64_t s_lo = prm.site_begin + (t0 + it) * prm.T;
-                int64_t rows = prm.site_end - s_lo;
-                if (rows > prm.T) rows = prm.T;
-                const uint32_t bytes = (uint32_t)(rows * prm.pitch);
-                // positions of the tile ride along (rounded up to 16 bytes; the array has zeroed slack)
-                const uint32_t pbytes = (MODE == MODE_COUNTS) ? 0u : (uint32_t)(((rows * 4 + 15) / 16) * 16);
-                mbar_expect_tx(&full[stage], bytes + pbytes);
-                const uint8_t* src = prm.geno + s_lo * prm.pitch;
-                uint8_t* dst = tiles + (size_t)stage * prm.tile_bytes;
-                for (uint32_t off = 0; off < bytes; off += 32768u) {
-                    const uint32_t n = (bytes - off) < 32768u ? (bytes - off) : 32768u;
-                    bulk_g2s(dst + off, src + off, n, &full[stage]);
-                }
-                if (pbytes) bulk_g2s(dst + (size_t)prm.T * prm.pitch, prm.pos + s_lo, pbytes, &full[stage]);
-                // publish "tile `it` is armed": a consumer must not test a phase parity before its phase has
-                // been armed, or try_wait.parity would alias it with the previous (already complete) phase
-                __threadfence_block();
-                *s_issued = it + 1;
-            }
-        }
+        if (lane == 0) k1_producer<MODE>(prm, tiles, full, empty, s_issued, ntiles, t0);
         return;
     }
 
@@ -612,6 +617,212 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k1_site_pass(const __grid_co
         if (lane == 0) mbar_arrive(&empty[stage]);   // this warp is done with the stage's bytes
     }
     if (MODE != MODE_COUNTS) warp_flush<QI, QU, QD>(acc, cur_seg, prm.part, slot_base, seg_first, warp, lane, NW);
+}
+
+
+// ---- lane-per-population variant for LONG rows (popgen modes, byte-packed counts) ----------------------------------
+// P lanes share one site and lane X walks population X's chunks alone: no per-population cross-lane combine, every
+// lane holds ONE packed count word, and the pair products are spread over the lanes — lane X accumulates
+// sum c_X^2 and sum c_X c_{X+d} for d = 1 .. P/2 (partner words arrive by shuffle) — so a lane carries 1 + P/2 32-bit
+// sums instead of P + P(P-1)/2.  The slot layout in global memory is the same as k1_site_pass's.
+template <int QI, int QU>
+__device__ __forceinline__ void warp_flush_lp(long long (&ai)[QI], uint32_t (&au)[QU], int cur_seg, unsigned long long* part,
+                                              int64_t slot_base, int seg_first, int warp, int lane, int nw, int Q, int spw,
+                                              int X, const int* s_q) {
+    unsigned pending = __ballot_sync(0xffffffffu, cur_seg >= 0);
+    while (pending) {
+        const int leader = __ffs(pending) - 1;
+        const int g = __shfl_sync(0xffffffffu, cur_seg, leader);
+        const bool mine = (cur_seg == g);
+        unsigned long long* dst = part + slot_base + ((int64_t)(g - seg_first) * nw + warp) * Q;
+        const bool head = (lane % spw) == 0;
+#pragma unroll
+        for (int q = 0; q < QI; ++q) {      // site bookkeeping lives in the lanes of population 0
+            long long v = (mine && X == 0) ? ai[q] : 0ll;
+            for (int d = spw >> 1; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+            if (lane == 0) dst[q] = (unsigned long long)((long long)dst[q] + v);
+            if (mine) ai[q] = 0;
+        }
+#pragma unroll
+        for (int q = 0; q < QU; ++q) {      // lanes of the same population are neighbours: butterfly inside the group
+            long long v = mine ? (long long)au[q] : 0ll;
+            for (int d = spw >> 1; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+            const int slot = s_q[X * QU + q];
+            if (head && slot >= 0) dst[slot] = (unsigned long long)((long long)dst[slot] + v);
+            if (mine) au[q] = 0u;
+        }
+        pending &= ~__ballot_sync(0xffffffffu, mine);
+    }
+}
+
+template <int MODE, int P, int NW>
+__global__ void __launch_bounds__((NW + 1) * 32, 1) k1_site_pass_lp(const __grid_constant__ K1Params prm) {
+    static_assert(MODE == MODE_POPGEN || MODE == MODE_POPGEN_FREQ, "lane-per-population: popgen modes only");
+    constexpr int K1_THREADS = (NW + 1) * 32;
+    constexpr int HP = P / 2;
+    constexpr int QU = 1 + HP + (MODE == MODE_POPGEN_FREQ ? 1 : 0);      // sq, cross d = 1..P/2, (segregating sites)
+    constexpr int spw = 32 / P;                                            // sites per warp per step
+    const int Q = 3 + P + P * (P - 1) / 2 + (MODE == MODE_POPGEN_FREQ ? P : 0);
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* tiles = smem;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)prm.stages * prm.tile_bytes);
+    uint64_t* empty = full + 8;
+    volatile int* s_issued = reinterpret_cast<volatile int*>(empty + 8);
+    uint4* s_ent_mask = reinterpret_cast<uint4*>(smem + (size_t)prm.stages * prm.tile_bytes + 256);
+    int32_t* s_ent_chunk = reinterpret_cast<int32_t*>(s_ent_mask + prm.n_ent);
+    int* s_pop = s_ent_chunk + prm.n_ent;            // [5][P]: full_lo, full_hi, ent_lo, ent_hi, popN
+    int* s_q = s_pop + 5 * P;                        // [P][QU]: slot word of each lane-local sum (-1 = unused)
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.x, B = gridDim.x;
+    const int64_t t0 = (int64_t)b * prm.num_tiles / B, t1 = (int64_t)(b + 1) * prm.num_tiles / B;
+    const int ntiles = (int)(t1 - t0);
+
+    for (int e = tid; e < prm.n_ent; e += K1_THREADS) {
+        s_ent_mask[e] = prm.ent_mask[e];
+        s_ent_chunk[e] = prm.ent_chunk[e];
+    }
+    if (tid < P) {
+        s_pop[0 * P + tid] = prm.full_lo[tid];
+        s_pop[1 * P + tid] = prm.full_hi[tid];
+        s_pop[2 * P + tid] = prm.ent_lo[tid];
+        s_pop[3 * P + tid] = prm.ent_hi[tid];
+        s_pop[4 * P + tid] = prm.popN[tid];
+        // slot words (layout of k1_site_pass): [3 ints][P sq][pairs (x<y) in order][P segregating]
+        const int x = tid;
+        s_q[x * QU + 0] = 3 + x;
+        for (int d = 1; d <= HP; ++d) {
+            int slot = -1;
+            if (d < HP || x < HP) {
+                const int y = (x + d) % P;
+                const int lo = x < y ? x : y, hi = x < y ? y : x;
+                int kp = 0;
+                for (int xx = 0; xx < lo; ++xx) kp += P - 1 - xx;
+                kp += hi - lo - 1;
+                slot = 3 + P + kp;
+            }
+            s_q[x * QU + d] = slot;
+        }
+        if (MODE == MODE_POPGEN_FREQ) s_q[x * QU + 1 + HP] = 3 + P + P * (P - 1) / 2 + x;
+    }
+    if (tid == 0) {
+        for (int st = 0; st < prm.stages; ++st) {
+            mbar_init(&full[st], 1);
+            mbar_init(&empty[st], (uint32_t)prm.wpt);
+        }
+        *s_issued = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == NW) {
+        if (lane == 0) k1_producer<MODE>(prm, tiles, full, empty, s_issued, ntiles, t0);
+        return;
+    }
+
+    const int X = lane / spw;                // this lane's population
+    const int sl = lane % spw;               // its site within the warp's step
+    unsigned site_lanes = 0;                 // the P lanes that share this lane's site
+#pragma unroll
+    for (int k = 0; k < P; ++k) site_lanes |= 1u << (sl + k * spw);
+    const int nteams = NW / prm.wpt;
+    const int team = warp / prm.wpt, lw = warp % prm.wpt;
+    const int sites_per_iter = prm.wpt * spw;
+    const int f_lo = s_pop[0 * P + X], f_hi = s_pop[1 * P + X], e_lo = s_pop[2 * P + X], e_hi = s_pop[3 * P + X];
+    const uint32_t myN = (uint32_t)s_pop[4 * P + X];
+
+    long long ai[3] = {0, 0, 0};
+    uint32_t au[QU];
+#pragma unroll
+    for (int q = 0; q < QU; ++q) au[q] = 0u;
+    int since_flush = 0;
+    int cur_seg = -1;
+    int64_t seg_end = -1;
+    const int seg_first = prm.cta_seg_first[b];
+    const int64_t slot_base = prm.cta_slot_off[b];
+
+    for (int it = team; it < ntiles; it += nteams) {
+        const int stage = it % prm.stages;
+        if (lane == 0)
+            while (*s_issued <= it) __nanosleep(20);
+        __syncwarp();
+        mbar_wait(&full[stage], (uint32_t)((it / prm.stages) & 1));
+        const uint8_t* tile = tiles + (size_t)stage * prm.tile_bytes;
+        const int64_t tile_site0 = prm.site_begin + (t0 + it) * prm.T;
+
+        for (int i = 0; i < prm.I; ++i) {
+            const int slot = i * sites_per_iter + lw * spw + sl;
+            const int64_t site = tile_site0 + slot;
+            const bool valid = site < prm.site_end;
+            const bool owner = valid && (X == 0);
+            const uint4* row = reinterpret_cast<const uint4*>(tile + (size_t)(valid ? slot : 0) * prm.pitch);
+            const int posv = owner ? reinterpret_cast<const int32_t*>(tile + (size_t)prm.T * prm.pitch)[slot] : 0;
+
+            Tally t;
+            tally_init(t);
+            {
+                int ch = f_lo;
+                for (; ch + 2 < f_hi; ch += 3) add_chunks3(t, row[ch], row[ch + 1], row[ch + 2]);
+                if (ch + 1 < f_hi) add_chunks2(t, row[ch], row[ch + 1]);
+                else if (ch < f_hi) add_chunks1(t, row[ch]);
+            }
+            {
+                int e = e_lo;
+                for (; e + 1 < e_hi; e += 2)
+                    add_chunks2(t, and4(row[s_ent_chunk[e]], s_ent_mask[e]), and4(row[s_ent_chunk[e + 1]], s_ent_mask[e + 1]));
+                if (e < e_hi) add_chunks1(t, and4(row[s_ent_chunk[e]], s_ent_mask[e]));
+            }
+            byte_flush(t);
+            const uint32_t cb = t.tA | (t.tC << 8) | (t.tG << 16) | (t.tT << 24);
+            const uint32_t n = __dp4a(cb, 0x01010101u, 0u);
+
+            // ---- segment bookkeeping: the site's owner lane looks it up, its P lanes share it ----
+            int sg = cur_seg;
+            if (owner && site >= seg_end) sg = find_seg(prm.brk, prm.nseg, cur_seg + 1, site);
+            sg = __shfl_sync(0xffffffffu, sg, sl);                   // lane sl is population 0 of this site
+            if (!valid) sg = cur_seg;
+            if (__any_sync(0xffffffffu, sg != cur_seg)) {
+                warp_flush_lp<3, QU>(ai, au, cur_seg, prm.part, slot_base, seg_first, warp, lane, NW, Q, spw, X, s_q);
+                since_flush = 0;
+                if (sg != cur_seg) {
+                    cur_seg = sg;
+                    seg_end = __ldg(prm.brk + sg + 1);
+                }
+            }
+            if (++since_flush > prm.acc_limit) {
+                warp_flush_lp<3, QU>(ai, au, cur_seg, prm.part, slot_base, seg_first, warp, lane, NW, Q, spw, X, s_q);
+                since_flush = 1;
+            }
+
+            const unsigned bf = __ballot_sync(0xffffffffu, valid && n == myN);
+            const unsigned bz = __ballot_sync(0xffffffffu, valid && n == 0u);
+            const bool allpres = (bf & site_lanes) == site_lanes;
+            const bool allmiss = (bz & site_lanes) == site_lanes;
+            const bool pres = valid && allpres;
+            ai[0] += (owner && allpres) ? 1 : 0;
+            ai[1] += (owner && !allpres && !allmiss) ? 1 : 0;
+            ai[2] += (long long)posv;
+            const uint32_t cf = pres ? cb : 0u;
+            if (MODE == MODE_POPGEN_FREQ) {
+                const uint32_t sq = __dp4a(cf, cb, 0u);
+                au[0] += sq;
+                au[1 + HP] += (pres && sq != n * n) ? 1u : 0u;
+            } else {
+                au[0] = __dp4a(cf, cb, au[0]);
+            }
+#pragma unroll
+            for (int d = 1; d <= HP; ++d) {
+                int px = X + d;
+                if (px >= P) px -= P;
+                const uint32_t cbp = __shfl_sync(0xffffffffu, cb, px * spw + sl);
+                if (d < HP || X < HP) au[d] = __dp4a(cf, cbp, au[d]);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);
+    }
+    warp_flush_lp<3, QU>(ai, au, cur_seg, prm.part, slot_base, seg_first, warp, lane, NW, Q, spw, X, s_q);
 }
 
 // ---- finalize: slots -> segments -> windows -> statistics ------------------------------------------
@@ -929,6 +1140,7 @@ int push(pg_ctx* ctx, uint8_t* base, size_t& off, const T* src, size_t n, T** ou
 // statistics call on the same configuration only clears the slots and launches two kernels.
 struct K1Cache {
     bool valid = false;
+    bool lanepop = false;
     uint64_t epoch = 0;
     int mode = -1;
     int sel[4] = {-1, -1, -1, -1};
@@ -938,16 +1150,17 @@ struct K1Cache {
     PgBuf tables;
 };
 
-int prepare_windowed(pg_ctx* ctx, K1Cache& c, const std::vector<int32_t>& hap_pop_local, int Ppad, int Q, int nw) {
+int prepare_windowed(pg_ctx* ctx, K1Cache& c, const std::vector<int32_t>& hap_pop_local, int Ppad, int Q, int nw,
+                     int force_G = 0) {
     K1Launch& L = c.L;
     DevTables& dt = c.dt;
     PopTables& pt = c.pt;
     PG_TRY(pg_build_segments(ctx));
     build_tables(hap_pop_local, ctx->H, ctx->pitch / 16, Ppad, pt);
     const int n_ent = (int)pt.ent_chunk.size();
-    const int table_bytes = n_ent * 20 + 64;
+    const int table_bytes = n_ent * 20 + 64 + 512;        // + the per-population tables of the lane-per-population variant
     PG_CHECK(table_bytes <= 48 * 1024, "population layout needs %d bytes of mask tables (limit 48 KiB)", table_bytes);
-    L.plan = pg_make_k1_plan(ctx->S, ctx->H, ctx->sm_count, table_bytes, nw);
+    L.plan = pg_make_k1_plan(ctx->S, ctx->H, ctx->sm_count, table_bytes, nw, force_G);
     PG_CHECK(L.plan.stages >= 2, "rows of %d haplotypes are too long for the site-pass kernel (pitch %d bytes)", ctx->H,
              L.plan.pitch);
     PG_TRY(check_plan(L.plan));
@@ -1065,15 +1278,40 @@ int launch_site_pass_nw(pg_ctx* ctx, const K1Launch& L, const char* name) {
 
 // consumer warps per CTA: 12 (+ the producer = 416 threads, 128 registers each) for rows below 1 KiB; 8 (up to 168
 // registers, no spills) for longer rows, where the 8-population instantiations measured 3-10 % faster (tools/k1_sweep2.py)
+int k1_env_nw12() {
+    const char* e = getenv("PG_K1_NW");
+    return (e && *e && atoi(e) == 8) ? 8 : 12;
+}
 int k1_nw_for(int pitch) {
     const char* e = getenv("PG_K1_NW");
     const int v = (e && *e) ? atoi(e) : (pitch >= 1024 ? 8 : 12);
     return v == 12 ? 12 : 8;
 }
 
+template <int MODE, int P, int NW>
+int launch_site_pass_lp(pg_ctx* ctx, const K1Launch& L, const char* name) {
+    auto kern = k1_site_pass_lp<MODE, P, NW>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    const int ti = pg_time_begin(ctx, name);
+    kern<<<L.plan.ctas, (NW + 1) * 32, L.plan.smem_bytes, ctx->stream>>>(L.prm);
+    pg_time_end(ctx, ti);
+    PG_CUDA(cudaGetLastError());
+    return PG_OK;
+}
+
 template <int MODE, int P>
 int launch_site_pass(pg_ctx* ctx, const K1Launch& L, const char* name) {
     constexpr bool POPGEN_MODE = (MODE == MODE_POPGEN || MODE == MODE_POPGEN_FREQ);
+    if constexpr (POPGEN_MODE && (P == 4 || P == 8)) {
+        if (L.prm.lanepop) {
+            if (L.prm.nw == 12) return launch_site_pass_lp<MODE, P, 12>(ctx, L, name);
+            return launch_site_pass_lp<MODE, P, 8>(ctx, L, name);
+        }
+    }
     if constexpr (POPGEN_MODE) {
         if (L.prm.bytes) {
             if (L.prm.nw == 12) return launch_site_pass_nw<MODE, P, 12, true>(ctx, L, name);
@@ -1183,8 +1421,19 @@ int pg_popgen_enqueue(pg_ctx* ctx, int32_t min_sites, double min_data, int32_t f
             for (int32_t& v : collapsed) v = v >= 0 ? 0 : -1;
         }
         const std::vector<int32_t>& pop_map = many ? collapsed : ctx->hap_pop;
-        const int nw = k1_nw_for(ctx->pitch);
-        PG_TRY(prepare_windowed(ctx, c, pop_map, Pp, Q, nw));
+        // long rows, 4 or 8 real populations of <= 255 haplotypes: one lane per population (k1_site_pass_lp)
+        int maxN = 0;
+        for (int x = 0; x < P && !many; ++x) {
+            int N = 0;
+            for (int h = 0; h < ctx->H; ++h) N += ctx->hap_pop[h] == x;
+            maxN = std::max(maxN, N);
+        }
+        bool lp = !many && (Pp == 4 || Pp == 8) && Pp == P && maxN <= 255 && ctx->pitch >= 1024 && !getenv("PG_K1_NO_BYTES");
+        if (const char* e = getenv("PG_K1_LANEPOP"))
+            lp = atoi(e) != 0 && !many && (Pp == 4 || Pp == 8) && maxN <= 255 && !getenv("PG_K1_NO_BYTES");
+        c.lanepop = lp;
+        const int nw = lp ? k1_env_nw12() : k1_nw_for(ctx->pitch);
+        PG_TRY(prepare_windowed(ctx, c, pop_map, Pp, Q, nw, lp ? Pp : 0));
         c.epoch = ctx->epoch;
         c.valid = true;
     }
@@ -1194,6 +1443,7 @@ int pg_popgen_enqueue(pg_ctx* ctx, int32_t min_sites, double min_data, int32_t f
         c.L.prm.acc_limit = (int)std::max<long long>(1, std::min<long long>(0xffffffffll / (maxN * maxN), 1 << 30));
         if (const char* e = getenv("PG_K1_ACC_LIMIT")) c.L.prm.acc_limit = std::max(1, atoi(e));   // test hook: force early flushes
         c.L.prm.bytes = (maxN <= 255 && !getenv("PG_K1_NO_BYTES")) ? 1 : 0;
+        c.L.prm.lanepop = c.lanepop ? 1 : 0;
     }
     PG_TRY(arm_slots(ctx, c));
     if (!wf) {

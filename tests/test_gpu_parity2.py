@@ -353,10 +353,12 @@ def test_pairdist_cat_equals_one_window(eng):
 # K1 instantiations: byte-packed IDP.4A statistics vs the general path, 8 vs 12 consumer warps, early 32-bit flushes
 # ------------------------------------------------------------------------------------------------
 K1_KNOBS = [{}, {"PG_K1_NO_BYTES": "1"}, {"PG_K1_NW": "8"}, {"PG_K1_NO_BYTES": "1", "PG_K1_NW": "8"}, {"PG_K1_ACC_LIMIT": "3"},
-            {"PG_K1_ACC_LIMIT": "1", "PG_K1_NO_BYTES": "1"}, {"PG_K1_G": "2"}, {"PG_K1_G": "4", "PG_K1_NO_BYTES": "1"}]
+            {"PG_K1_ACC_LIMIT": "1", "PG_K1_NO_BYTES": "1"}, {"PG_K1_G": "2"}, {"PG_K1_G": "4", "PG_K1_NO_BYTES": "1"},
+            {"PG_K1_LANEPOP": "0"}, {"PG_K1_LANEPOP": "1"}, {"PG_K1_LANEPOP": "1", "PG_K1_NW": "8"},
+            {"PG_K1_LANEPOP": "1", "PG_K1_ACC_LIMIT": "2"}, {"PG_K1_LANEPOP": "1", "PG_K1_WPT": "1"}]
 
 
-@pytest.mark.parametrize("shape", [(2, 9), (3, 20), (5, 7), (8, 13), (2, 150)], ids=lambda s: "%dx%d" % s)
+@pytest.mark.parametrize("shape", [(2, 9), (3, 20), (5, 7), (8, 13), (2, 150), (8, 100), (4, 127)], ids=lambda s: "%dx%d" % s)
 def test_k1_variants_are_bit_identical_and_match_the_oracle(eng, shape, monkeypatch):
     from genomics_general_b200 import synth
     from oracle import dense_oracle as do
@@ -371,7 +373,7 @@ def test_k1_variants_are_bit_identical_and_match_the_oracle(eng, shape, monkeypa
     hi = np.array([10, 4000, 4001, 9000, 15000, 20000], dtype=np.int64)
     base = None
     for knobs in K1_KNOBS:
-        for k in ("PG_K1_NO_BYTES", "PG_K1_NW", "PG_K1_ACC_LIMIT", "PG_K1_G"):
+        for k in ("PG_K1_NO_BYTES", "PG_K1_NW", "PG_K1_ACC_LIMIT", "PG_K1_G", "PG_K1_LANEPOP", "PG_K1_WPT"):
             monkeypatch.delenv(k, raising=False)
         for k, v in knobs.items():
             monkeypatch.setenv(k, v)

@@ -13,7 +13,7 @@ with Engine(0) as eng:
     lo = np.arange(0, S, 5000, dtype=np.int64)
     H = spec.n_haps
     for cfg in cfgs:
-        for k in ("PG_K1_NW", "PG_K1_NO_BYTES", "PG_K1_G", "PG_K1_WPT", "PG_K1_I", "PG_K1_TILE_KB", "PG_K1_STAGES"):
+        for k in ("PG_K1_NW", "PG_K1_NO_BYTES", "PG_K1_G", "PG_K1_WPT", "PG_K1_I", "PG_K1_TILE_KB", "PG_K1_STAGES", "PG_K1_LANEPOP"):
             os.environ.pop(k, None)
         for kv in cfg.split():
             k, v = kv.split("="); os.environ[k] = v
