@@ -657,7 +657,7 @@ __device__ __forceinline__ void warp_flush_lp(long long (&ai)[QI], uint32_t (&au
 
 template <int MODE, int P, int NW>
 __global__ void __launch_bounds__((NW + 1) * 32, 1) k1_site_pass_lp(const __grid_constant__ K1Params prm) {
-    static_assert(MODE == MODE_POPGEN || MODE == MODE_POPGEN_FREQ, "lane-per-population: popgen modes only");
+    static_assert(MODE == MODE_POPGEN || MODE == MODE_POPGEN_FREQ || MODE == MODE_COUNTS, "lane-per-population: popgen / counts");
     constexpr int K1_THREADS = (NW + 1) * 32;
     constexpr int HP = P / 2;
     constexpr int QU = 1 + HP + (MODE == MODE_POPGEN_FREQ ? 1 : 0);      // sq, cross d = 1..P/2, (segregating sites)
@@ -739,8 +739,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k1_site_pass_lp(const __grid
     int since_flush = 0;
     int cur_seg = -1;
     int64_t seg_end = -1;
-    const int seg_first = prm.cta_seg_first[b];
-    const int64_t slot_base = prm.cta_slot_off[b];
+    const int seg_first = (MODE == MODE_COUNTS) ? 0 : prm.cta_seg_first[b];
+    const int64_t slot_base = (MODE == MODE_COUNTS) ? 0 : prm.cta_slot_off[b];
 
     for (int it = team; it < ntiles; it += nteams) {
         const int stage = it % prm.stages;
@@ -757,7 +757,9 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k1_site_pass_lp(const __grid
             const bool valid = site < prm.site_end;
             const bool owner = valid && (X == 0);
             const uint4* row = reinterpret_cast<const uint4*>(tile + (size_t)(valid ? slot : 0) * prm.pitch);
-            const int posv = owner ? reinterpret_cast<const int32_t*>(tile + (size_t)prm.T * prm.pitch)[slot] : 0;
+            int posv = 0;
+            if (MODE != MODE_COUNTS)
+                posv = owner ? reinterpret_cast<const int32_t*>(tile + (size_t)prm.T * prm.pitch)[slot] : 0;
 
             Tally t;
             tally_init(t);
@@ -774,6 +776,12 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k1_site_pass_lp(const __grid
                 if (e < e_hi) add_chunks1(t, and4(row[s_ent_chunk[e]], s_ent_mask[e]));
             }
             byte_flush(t);
+            if (MODE == MODE_COUNTS) {       // every lane writes its own population's four counts
+                if (valid && X < prm.counts_pops)
+                    *reinterpret_cast<ushort4*>(prm.counts_out + (site - prm.site_begin) * prm.counts_stride + X * 4) =
+                        make_ushort4((unsigned short)t.tA, (unsigned short)t.tC, (unsigned short)t.tG, (unsigned short)t.tT);
+                continue;
+            }
             const uint32_t cb = t.tA | (t.tC << 8) | (t.tG << 16) | (t.tT << 24);
             const uint32_t n = __dp4a(cb, 0x01010101u, 0u);
 
@@ -822,7 +830,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k1_site_pass_lp(const __grid
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[stage]);
     }
-    warp_flush_lp<3, QU>(ai, au, cur_seg, prm.part, slot_base, seg_first, warp, lane, NW, Q, spw, X, s_q);
+    if (MODE != MODE_COUNTS) warp_flush_lp<3, QU>(ai, au, cur_seg, prm.part, slot_base, seg_first, warp, lane, NW, Q, spw, X, s_q);
 }
 
 // ---- finalize: slots -> segments -> windows -> statistics ------------------------------------------
@@ -1306,7 +1314,7 @@ int launch_site_pass_lp(pg_ctx* ctx, const K1Launch& L, const char* name) {
 template <int MODE, int P>
 int launch_site_pass(pg_ctx* ctx, const K1Launch& L, const char* name) {
     constexpr bool POPGEN_MODE = (MODE == MODE_POPGEN || MODE == MODE_POPGEN_FREQ);
-    if constexpr (POPGEN_MODE && (P == 4 || P == 8)) {
+    if constexpr ((POPGEN_MODE || MODE == MODE_COUNTS) && (P == 4 || P == 8)) {
         if (L.prm.lanepop) {
             if (L.prm.nw == 12) return launch_site_pass_lp<MODE, P, 12>(ctx, L, name);
             return launch_site_pass_lp<MODE, P, 8>(ctx, L, name);
@@ -1757,11 +1765,14 @@ int site_counts_slab(pg_ctx* ctx, int64_t first, int64_t cnt) {
         PopTables pt;
         build_tables(local, ctx->H, ctx->pitch / 16, Pp, pt);
         const int n_ent = (int)pt.ent_chunk.size();
-        const int table_bytes = n_ent * 20 + 64;
+        const int table_bytes = n_ent * 20 + 64 + 512;
         PG_CHECK(table_bytes <= 48 * 1024, "population layout needs too many mask entries");
         K1Launch L;
-        const int nw = k1_nw_for(ctx->pitch);
-        L.plan = pg_make_k1_plan(cnt, ctx->H, ctx->sm_count, table_bytes, nw);
+        // long rows, a full group of 4 or 8 populations: one lane per population (counts fit 16 bits in any case)
+        bool lp = (Pp == 4 || Pp == 8) && Pp == pc && ctx->pitch >= 1024;
+        if (const char* e = getenv("PG_K1_LANEPOP")) lp = atoi(e) != 0 && (Pp == 4 || Pp == 8);
+        const int nw = lp ? k1_env_nw12() : k1_nw_for(ctx->pitch);
+        L.plan = pg_make_k1_plan(cnt, ctx->H, ctx->sm_count, table_bytes, nw, lp ? Pp : 0);
         PG_CHECK(L.plan.stages >= 2, "rows of %d haplotypes are too long for the site-pass kernel", ctx->H);
         PG_TRY(check_plan(L.plan));
         PG_TRY(ctx->tables.ensure((size_t)n_ent * 20 + 4096));
@@ -1799,6 +1810,7 @@ int site_counts_slab(pg_ctx* ctx, int64_t first, int64_t cnt) {
         p.counts_out = (uint16_t*)ctx->misc.p + (size_t)p0 * 4;
         p.counts_stride = stride;
         p.counts_pops = pc;
+        p.lanepop = lp ? 1 : 0;
         if (Pp == 2) PG_TRY((launch_site_pass<MODE_COUNTS, 2>(ctx, L, "k1_counts")));
         else if (Pp == 4) PG_TRY((launch_site_pass<MODE_COUNTS, 4>(ctx, L, "k1_counts")));
         else PG_TRY((launch_site_pass<MODE_COUNTS, 8>(ctx, L, "k1_counts")));

@@ -386,11 +386,13 @@ def test_k1_variants_are_bit_identical_and_match_the_oracle(eng, shape, monkeypa
         eng.set_freqstats(False)
         r2 = eng.popgen(1, 0.01)
         assert np.all(r["path"] == 1)
-        cur = [r["pi"], r["dxy"], r["fst"], fq["S"], fq["thetaPi"], fq["thetaW"], fq["TajD"], fq["l"]]
+        cnt = eng.site_counts(17, 3000)
+        cur = [r["pi"], r["dxy"], r["fst"], fq["S"], fq["thetaPi"], fq["thetaW"], fq["TajD"], fq["l"], cnt]
         for a, b in zip([r2["pi"], r2["dxy"], r2["fst"]], cur[:3]):
             assert np.array_equal(a, b, equal_nan=True)
         if base is None:
             base = cur
+            assert np.array_equal(cnt.astype(np.int64), do.site_counts(g[17:3017], hp, P))
             for w in (1, 3, 5):
                 ok, pi, dxy, fst = do.group_dist_stats_closed_form(g[lo[w]:hi[w]], hp, P, 1, 0.01)
                 assert ok
