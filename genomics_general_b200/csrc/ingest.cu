@@ -388,7 +388,8 @@ int ingest_core(pg_ctx* ctx, const char* mem, int fd, size_t file_off, size_t le
     // H2D of the text: host threads fill two pinned staging buffers in turn, the copy engine drains them
     {
         const size_t slab = (size_t)64 << 20;
-        const int n_threads = std::max(1, std::min(16, (int)std::thread::hardware_concurrency() / 2));
+        int n_threads = std::max(1, std::min(16, (int)std::thread::hardware_concurrency() / 2));
+        if (const char* e = getenv("PG_INGEST_THREADS")) n_threads = std::max(1, std::min(128, atoi(e)));
         if (!ctx->h_text[0]) {
             for (int k = 0; k < 2; ++k) {
                 PG_CUDA(cudaHostAlloc(&ctx->h_text[k], slab, cudaHostAllocDefault));
