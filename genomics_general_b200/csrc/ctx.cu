@@ -533,7 +533,9 @@ extern "C" int pg_synth_fill(pg_ctx* ctx, int64_t S, int32_t n_pops, int32_t sam
 extern "C" int pg_set_pops(pg_ctx* ctx, int32_t P, const int32_t* hap_pop) {
     PG_CHECK(ctx && hap_pop, "pg_set_pops: null argument");
     PG_CHECK(ctx->H > 0, "pg_set_pops: upload genotypes first");
-    PG_CHECK(P >= 1 && P <= PG_MAX_POPS, "pg_set_pops: P=%d outside [1,%d]", P, PG_MAX_POPS);
+    // the windowed statistics take at most PG_MAX_POPS populations (checked there); per-site counts / target
+    // frequencies (freq.py --indFreqs: one population per individual) take any number
+    PG_CHECK(P >= 1 && P <= 65535, "pg_set_pops: P=%d outside [1,65535]", P);
     ctx->hap_pop.assign(hap_pop, hap_pop + ctx->H);
     for (int h = 0; h < ctx->H; ++h)
         PG_CHECK(hap_pop[h] >= -1 && hap_pop[h] < P, "pg_set_pops: hap_pop[%d]=%d outside [-1,%d)", h, hap_pop[h], P);

@@ -1529,6 +1529,7 @@ extern "C" int pg_popgen(pg_ctx* ctx, int32_t min_sites, double min_data, int32_
                          double* fst, int64_t* n_sites, int64_t* pos_sum, int32_t* path) {
     PG_CHECK(ctx && pi && dxy && fst && n_sites && pos_sum && path, "pg_popgen: null argument");
     PG_CHECK(ctx->P >= 1, "pg_popgen: call pg_set_pops first");
+    PG_CHECK(ctx->P <= PG_MAX_POPS, "pg_popgen: P=%d > %d populations", ctx->P, PG_MAX_POPS);
     const int P = ctx->P;
     const int npairs = P * (P - 1) / 2;
     const int RC = 3 + P + 2 * npairs + 1 + 4 * P;
@@ -1752,10 +1753,55 @@ extern "C" int pg_fourpop(pg_ctx* ctx, int32_t p1, int32_t p2, int32_t p3, int32
 // pg_site_counts / pg_site_target_freqs
 // ================================================================================================
 namespace {
+// Many small populations (freq.py --indFreqs: one population per individual): one thread per (site, population) gathers
+// the population's few haplotype bytes — ONE pass over the rows instead of P/8 site passes.
+__global__ void __launch_bounds__(256) k1_counts_gather(const uint8_t* __restrict__ geno, int pitch, int64_t site0, int64_t n,
+                                                        int P, const int32_t* __restrict__ pop_off,
+                                                        const int32_t* __restrict__ pop_cols, uint16_t* __restrict__ out) {
+    const int64_t total = n * P;
+    for (int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * 256) {
+        const int64_t s = idx / P;
+        const int X = (int)(idx % P);
+        const uint8_t* row = geno + (site0 + s) * pitch;
+        unsigned a = 0, c = 0, g = 0, t = 0;
+        for (int k = pop_off[X]; k < pop_off[X + 1]; ++k) {
+            const unsigned b = row[pop_cols[k]];            // one-hot: A 0x01, C 0x04, G 0x10, T 0x40
+            a += b & 1u;
+            c += (b >> 2) & 1u;
+            g += (b >> 4) & 1u;
+            t += (b >> 6) & 1u;
+        }
+        reinterpret_cast<ushort4*>(out)[idx] = make_ushort4((unsigned short)a, (unsigned short)c, (unsigned short)g, (unsigned short)t);
+    }
+}
+
 // per-site counts of `cnt` sites starting at `first` -> ctx->misc as uint16 [cnt x P x 4]
 int site_counts_slab(pg_ctx* ctx, int64_t first, int64_t cnt) {
     const int P = ctx->P;
     const int64_t stride = (int64_t)P * 4;
+    if (P > 16 && !getenv("PG_COUNTS_NO_GATHER")) {
+        std::vector<int32_t> off(P + 1, 0), cols;
+        cols.reserve((size_t)ctx->H);
+        for (int X = 0; X < P; ++X) {
+            off[X] = (int32_t)cols.size();
+            for (int h = 0; h < ctx->H; ++h)
+                if (ctx->hap_pop[h] == X) cols.push_back(h);
+        }
+        off[P] = (int32_t)cols.size();
+        PG_TRY(ctx->tables.ensure((size_t)(P + 1) * 4 + cols.size() * 4 + 256));
+        uint8_t* base = (uint8_t*)ctx->tables.p;
+        size_t o = 0;
+        int32_t *d_off = nullptr, *d_cols = nullptr;
+        PG_TRY(push(ctx, base, o, off.data(), off.size(), &d_off));
+        PG_TRY(push(ctx, base, o, cols.data(), cols.size(), &d_cols));
+        const int ti = pg_time_begin(ctx, "k1_counts");
+        k1_counts_gather<<<(unsigned)std::min<int64_t>((cnt * P + 255) / 256, (int64_t)ctx->sm_count * 32), 256, 0, ctx->stream>>>(
+            (const uint8_t*)ctx->d_geno, ctx->pitch, first, cnt, P, d_off, d_cols, (uint16_t*)ctx->misc.p);
+        pg_time_end(ctx, ti);
+        PG_CUDA(cudaGetLastError());
+        PG_CUDA(cudaStreamSynchronize(ctx->stream));       // host vectors behind the async copies
+        return PG_OK;
+    }
     for (int p0 = 0; p0 < P; p0 += PG_MAX_K1_POPS) {
         const int pc = std::min(PG_MAX_K1_POPS, P - p0);
         const int Pp = pad_pops(pc);

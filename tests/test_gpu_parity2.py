@@ -496,3 +496,27 @@ def test_popgenWindows_haplo_and_pairs_formats_cli(inputs2, tmp_path):
     synth.write_geno(ppath, gd.geno, gd.pos, [gd.scaf_names[k] for k in gd.scaf_ids], gd.names, fmt="pairs")
     popgenWindows.main(base + ["-g", ppath, "-f", "pairs", "--popsFile", inputs2["pops"]] + inputs2["popargs"])
     _compare_by_column(open(o).read(), d["popgen_pairs"], atol=2e-9)
+
+
+def test_many_small_populations_counts_and_target_freqs(eng, monkeypatch):
+    """freq.py --indFreqs: one population per individual (more than 64 populations) — gather kernel vs site passes vs oracle."""
+    from genomics_general_b200 import synth
+    from oracle import dense_oracle as do
+    spec = synth.SynthSpec(5, 17, miss=0.05, seed=77)          # 85 individuals
+    S = 3000
+    g = synth.synth_genotypes(spec, 0, S)
+    H = g.shape[1]
+    hp = (np.arange(H) // 2).astype(np.int32)                  # population = individual
+    hp[-4:] = -1                                               # two individuals left out
+    P = int(hp.max()) + 1
+    eng.upload(g, None)
+    eng.set_pops(hp, P)
+    want = do.site_counts(g, hp, P)
+    a = eng.site_counts()
+    monkeypatch.setenv("PG_COUNTS_NO_GATHER", "1")
+    b = eng.site_counts()
+    monkeypatch.delenv("PG_COUNTS_NO_GATHER")
+    assert np.array_equal(a.astype(np.int64), want) and np.array_equal(a, b)
+    v, tie = eng.site_target_freqs("derived")
+    wv, _ = do.target_freqs(g, hp, P, "derived")
+    assert np.array_equal(v, wv, equal_nan=True)
