@@ -1540,13 +1540,22 @@ extern "C" int pg_popgen(pg_ctx* ctx, int32_t min_sites, double min_data, int32_
     }
     PG_CUDA(cudaSetDevice(ctx->device));
     PG_TRY(ctx->out_d.ensure((size_t)W * RC * 8 + 64));
-    PG_TRY(pg_popgen_device(ctx, min_sites, min_data, force_path, ctx->out_d.p, nullptr));
-    // one D2H of the record table into pinned staging (a pageable destination would be a synchronous staged copy)
+    // site pass -> finalize -> D2H of the record table into pinned staging, ONE host synchronisation; only when the
+    // finalize kernel routed windows to the pairwise path are those rows recomputed and the table read again
     void* hp = nullptr;
-    PG_TRY(pg_pinned(ctx, (size_t)W * RC * 8 + 64, &hp));
+    PG_TRY(pg_pinned(ctx, (size_t)W * RC * 8 + 64 + 256, &hp));     // (+ the routed-window counter of the enqueue step)
+    int* h_cnt = nullptr;
+    PG_TRY(pg_popgen_enqueue(ctx, min_sites, min_data, force_path, ctx->out_d.p, &h_cnt));
+    hp = (uint8_t*)hp + 256;
     const unsigned long long* hrec = (const unsigned long long*)hp;
     PG_CUDA(cudaMemcpyAsync(hp, ctx->out_d.p, (size_t)W * RC * 8, cudaMemcpyDeviceToHost, ctx->stream));
     PG_CUDA(cudaStreamSynchronize(ctx->stream));
+    const int nk2 = h_cnt ? *h_cnt : 0;
+    if (nk2 > 0) {
+        PG_TRY(pg_popgen_resolve(ctx, min_sites, min_data, ctx->out_d.p, nk2));
+        PG_CUDA(cudaMemcpyAsync(hp, ctx->out_d.p, (size_t)W * RC * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        PG_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
     if (ctx->want_freq) ctx->h_rec.assign(hrec, hrec + (size_t)W * RC);     // kept for pg_popgen_freqstats
     else ctx->h_rec.clear();
     for (int64_t w = 0; w < W; ++w) {
