@@ -520,3 +520,45 @@ def test_many_small_populations_counts_and_target_freqs(eng, monkeypatch):
     v, tie = eng.site_target_freqs("derived")
     wv, _ = do.target_freqs(g, hp, P, "derived")
     assert np.array_equal(v, wv, equal_nan=True)
+
+
+@pytest.mark.parametrize("P", [3, 4, 6, 8])
+def test_lane_per_population_with_interleaved_columns(eng, P, monkeypatch):
+    """k1_site_pass_lp forced on a layout it is not tuned for: populations interleaved column by column, unused
+    haplotypes, unequal sizes (masked chunks only, P padded to 4 / 8)."""
+    from genomics_general_b200 import synth
+    from oracle import dense_oracle as do
+    rng = np.random.default_rng(50 + P)
+    sizes = rng.integers(3, 40, P)
+    hp = np.concatenate([np.full(n, x) for x, n in enumerate(sizes)] + [np.full(5, -1)]).astype(np.int32)
+    hp = rng.permutation(hp)
+    H, S = len(hp), 9000
+    ref = rng.integers(0, 4, S)
+    alt = (ref + rng.integers(1, 4, S)) % 4
+    freq = rng.random((S, P + 1)) * (rng.random(S) < 0.4)[:, None]
+    g = np.where(rng.random((S, H)) < freq[:, hp], alt[:, None], ref[:, None]).astype(np.int8)
+    g[rng.random(S) < 0.1] = -1
+    pos = np.cumsum(rng.integers(1, 30, S)).astype(np.int32)
+    lo = np.arange(0, S, 750, dtype=np.int64)
+    hi = np.minimum(lo + 1000, S)                       # overlapping windows
+    res = []
+    for lp in ("0", "1"):
+        monkeypatch.setenv("PG_K1_LANEPOP", lp)
+        eng.upload(g, pos)
+        eng.set_pops(hp, P)
+        eng.set_windows(lo, hi)
+        eng.set_freqstats(True)
+        r = eng.popgen(10, 0.01)
+        fq = eng.popgen_freqstats()
+        eng.set_freqstats(False)
+        res.append([r["pi"], r["dxy"], r["fst"], r["sites"], r["pos_sum"], r["path"], fq["S"], fq["thetaPi"], eng.site_counts()])
+    monkeypatch.delenv("PG_K1_LANEPOP")
+    for a, b in zip(*res):
+        assert np.array_equal(a, b, equal_nan=True)
+    assert np.all(res[0][5] == 1)
+    assert np.array_equal(res[1][8].astype(np.int64), do.site_counts(g, hp, P))
+    for w in (0, 5, len(lo) - 1):
+        ok, pi, dxy, fst = do.group_dist_stats_closed_form(g[lo[w]:hi[w]], hp, P, 10, 0.01)
+        assert ok
+        assert_close(res[1][0][w], pi, "pi", **TOL)
+        assert_close(res[1][1][w], dxy, "dxy", **TOL)
