@@ -154,9 +154,7 @@ struct PairParams {
 //   PAIR_DIFF: diff_ij = sum popc(((b0_i^b0_j)|(b1_i^b1_j)) & m_i & m_j)      (3 planes)
 //   PAIR_N   : n_ij    = sum popc(m_i & m_j)                                   (valid plane only, unique masks)
 // DIAG: the tile pair is on the diagonal -> pairs with a > b are mirror images, skip them.
-// CSA: the four 32-site difference words of a pair go through one carry-save adder (x + y + z = s + 2c) before the
-// population counts: 3 POPC instead of 4 on the XU pipe, which is the busiest one of this kernel, for 2 more LOP3.
-template <int WHAT, bool DIAG, bool CSA>
+template <int WHAT, bool DIAG>
 __device__ __forceinline__ void pair_accumulate(const uint8_t* sb, int ty, int tx, int (&acc)[4][4]) {
     using G = PairGeom<WHAT>;
     const uint4* I4 = reinterpret_cast<const uint4*>(sb);
@@ -179,19 +177,12 @@ __device__ __forceinline__ void pair_accumulate(const uint8_t* sb, int ty, int t
 #pragma unroll
                 for (int b = 0; b < 4; ++b) {
                     if (DIAG && a > b) continue;
-#define K2_DIFF_BITS(C) (((A0.C ^ B0[b].C) | (A1.C ^ B1[b].C)) & AM.C & BM[b].C)
-                    if (CSA) {
-                        const uint32_t dx = K2_DIFF_BITS(x), dy = K2_DIFF_BITS(y), dz = K2_DIFF_BITS(z);
-                        acc[a][b] += __popc(dx ^ dy ^ dz);
-                        acc[a][b] += 2 * __popc((dx & dy) | (dz & (dx ^ dy)));
-                        acc[a][b] += __popc(K2_DIFF_BITS(w));
-                    } else {
-                        acc[a][b] += __popc(K2_DIFF_BITS(x));
-                        acc[a][b] += __popc(K2_DIFF_BITS(y));
-                        acc[a][b] += __popc(K2_DIFF_BITS(z));
-                        acc[a][b] += __popc(K2_DIFF_BITS(w));
-                    }
-#undef K2_DIFF_BITS
+#define K2_DIFF_WORD(C) acc[a][b] += __popc(((A0.C ^ B0[b].C) | (A1.C ^ B1[b].C)) & AM.C & BM[b].C);
+                    K2_DIFF_WORD(x)
+                    K2_DIFF_WORD(y)
+                    K2_DIFF_WORD(z)
+                    K2_DIFF_WORD(w)
+#undef K2_DIFF_WORD
                 }
             }
         } else {
@@ -212,7 +203,7 @@ __device__ __forceinline__ void pair_accumulate(const uint8_t* sb, int ty, int t
     }
 }
 
-template <int WHAT, bool CSA>
+template <int WHAT>
 __global__ void __launch_bounds__(256, 2) k2_pair(const __grid_constant__ PairParams pp) {
     using G = PairGeom<WHAT>;
     extern __shared__ __align__(16) uint8_t psm[];
@@ -295,8 +286,8 @@ __global__ void __launch_bounds__(256, 2) k2_pair(const __grid_constant__ PairPa
             }
             __syncthreads();
         }
-        if (ti == tj) pair_accumulate<WHAT, true, CSA>(sb, ty, tx, acc);
-        else pair_accumulate<WHAT, false, CSA>(sb, ty, tx, acc);
+        if (ti == tj) pair_accumulate<WHAT, true>(sb, ty, tx, acc);
+        else pair_accumulate<WHAT, false>(sb, ty, tx, acc);
     }
     cp_async_wait<0>();
     const size_t RR = (size_t)pp.n_rows * pp.n_rows;
@@ -910,13 +901,10 @@ int run_pair_batch(pg_ctx* ctx, const PlaneSet& ps, const std::vector<int64_t>& 
     pp.win_hi = d_hi;
     static bool attr = false;
     if (!attr) {
-        PG_CUDA(cudaFuncSetAttribute(k2_pair<PAIR_DIFF, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairGeom<PAIR_DIFF>::SMEM));
-        PG_CUDA(cudaFuncSetAttribute(k2_pair<PAIR_DIFF, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairGeom<PAIR_DIFF>::SMEM));
-        PG_CUDA(cudaFuncSetAttribute(k2_pair<PAIR_N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairGeom<PAIR_N>::SMEM));
+        PG_CUDA(cudaFuncSetAttribute(k2_pair<PAIR_DIFF>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairGeom<PAIR_DIFF>::SMEM));
+        PG_CUDA(cudaFuncSetAttribute(k2_pair<PAIR_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairGeom<PAIR_N>::SMEM));
         attr = true;
     }
-    const char* csa_env = getenv("PG_K2_CSA");
-    const bool csa = csa_env ? atoi(csa_env) != 0 : true;
     // diff over all haplotype rows
     pp.n_rows = ps.Hk;
     pp.row_map = nullptr;
@@ -925,8 +913,7 @@ int run_pair_batch(pg_ctx* ctx, const PlaneSet& ps, const std::vector<int64_t>& 
     {
         dim3 grid((unsigned)(pp.ntile * (pp.ntile + 1) / 2), (unsigned)nb);
         const int ti = pg_time_begin(ctx, "k2_pair_diff");
-        if (csa) k2_pair<PAIR_DIFF, true><<<grid, 256, PairGeom<PAIR_DIFF>::SMEM, ctx->stream>>>(pp);
-        else k2_pair<PAIR_DIFF, false><<<grid, 256, PairGeom<PAIR_DIFF>::SMEM, ctx->stream>>>(pp);
+        k2_pair<PAIR_DIFF><<<grid, 256, PairGeom<PAIR_DIFF>::SMEM, ctx->stream>>>(pp);
         pg_time_end(ctx, ti);
         PG_CUDA(cudaGetLastError());
     }
@@ -939,7 +926,7 @@ int run_pair_batch(pg_ctx* ctx, const PlaneSet& ps, const std::vector<int64_t>& 
     {
         dim3 grid((unsigned)(pp.ntile * (pp.ntile + 1) / 2), (unsigned)nb);
         const int ti = pg_time_begin(ctx, "k2_pair_n");
-        k2_pair<PAIR_N, false><<<grid, 256, PairGeom<PAIR_N>::SMEM, ctx->stream>>>(pp);
+        k2_pair<PAIR_N><<<grid, 256, PairGeom<PAIR_N>::SMEM, ctx->stream>>>(pp);
         pg_time_end(ctx, ti);
         PG_CUDA(cudaGetLastError());
     }
