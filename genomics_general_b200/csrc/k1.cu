@@ -1606,11 +1606,10 @@ extern "C" int pg_popgen_freqstats(pg_ctx* ctx, double* l, double* S, double* th
 // ================================================================================================
 // pg_abbababa
 // ================================================================================================
-extern "C" int pg_abbababa(pg_ctx* ctx, int32_t p1, int32_t p2, int32_t p3, int32_t o, double min_data, double* out,
-                           double* sites_used, int64_t* n_sites, int64_t* pos_sum) {
-    PG_CHECK(ctx && out && sites_used && n_sites && pos_sum, "pg_abbababa: null argument");
+// Enqueue site pass + finalize of the ABBA-BABA statistics on the ctx stream; records [W x 8] 8-byte words
+// [sites, pos_sum, ABBA, BABA, D, fd, fdM, sitesUsed] are left in the DEVICE buffer d_rec.  No synchronisation.
+int pg_abba_enqueue(pg_ctx* ctx, const int* sel, double min_data, void* d_rec) {
     PG_CHECK(ctx->P >= 1, "pg_abbababa: call pg_set_pops first");
-    const int sel[4] = {p1, p2, p3, o};
     for (int k = 0; k < 4; ++k) {
         PG_CHECK(sel[k] >= 0 && sel[k] < ctx->P, "pg_abbababa: population index %d out of range", sel[k]);
         for (int j = 0; j < k; ++j) PG_CHECK(sel[j] != sel[k], "pg_abbababa: populations must be distinct");
@@ -1619,18 +1618,20 @@ extern "C" int pg_abbababa(pg_ctx* ctx, int32_t p1, int32_t p2, int32_t p3, int3
     pg_timings_reset(ctx);
     const int64_t W = ctx->W;
     if (W == 0) return PG_OK;
+    const int Q = 9, RC = 8;
     if (ctx->S == 0) {
-        for (int64_t w = 0; w < W; ++w) {
-            n_sites[w] = 0;
-            pos_sum[w] = 0;
-            sites_used[w] = NAN;
-            for (int k = 0; k < 5; ++k) out[w * 5 + k] = NAN;
-        }
+        std::vector<unsigned long long> h((size_t)W * RC, 0ull);
+        const double qn = NAN;
+        unsigned long long nanbits;
+        memcpy(&nanbits, &qn, 8);
+        for (int64_t w = 0; w < W; ++w)
+            for (int k = 2; k < RC; ++k) h[(size_t)w * RC + k] = nanbits;
+        PG_CUDA(cudaMemcpyAsync(d_rec, h.data(), h.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+        PG_CUDA(cudaStreamSynchronize(ctx->stream));
         return PG_OK;
     }
-    const int Q = 9, RC = 8;
     K1Cache& c = *cache_of(ctx, 1);
-    if (!c.valid || c.epoch != ctx->epoch || memcmp(c.sel, sel, sizeof(sel)) != 0) {
+    if (!c.valid || c.epoch != ctx->epoch || memcmp(c.sel, sel, 4 * sizeof(int)) != 0) {
         c.valid = false;
         std::vector<int32_t> local(ctx->H, -1);
         for (int h = 0; h < ctx->H; ++h)
@@ -1638,7 +1639,7 @@ extern "C" int pg_abbababa(pg_ctx* ctx, int32_t p1, int32_t p2, int32_t p3, int3
                 if (ctx->hap_pop[h] == sel[k]) local[h] = k;
         PG_TRY(prepare_windowed(ctx, c, local, 4, Q, k1_nw_for(ctx->pitch)));
         for (int k = 0; k < 4; ++k) PG_CHECK(c.pt.popN[k] >= 1, "pg_abbababa: population %d has no haplotypes", sel[k]);
-        memcpy(c.sel, sel, sizeof(sel));
+        memcpy(c.sel, sel, 4 * sizeof(int));
         c.epoch = ctx->epoch;
         c.valid = true;
     }
@@ -1654,17 +1655,29 @@ extern "C" int pg_abbababa(pg_ctx* ctx, int32_t p1, int32_t p2, int32_t p3, int3
     }
     PG_TRY(arm_slots(ctx, c));
     PG_TRY((launch_site_pass<MODE_ABBA, 4>(ctx, c.L, "k1_abba")));
-    PG_TRY(ctx->out_d.ensure((size_t)W * RC * 8 + 64));
     FinParams fp;
     fill_fin(fp, ctx, c, Q, 3);
     fp.P = 4;
     fp.Ppad = 4;
-    fp.rec = (unsigned long long*)ctx->out_d.p;
+    fp.rec = (unsigned long long*)d_rec;
     fp.RC = RC;
     const int ti = pg_time_begin(ctx, "k1_finalize");
     k1_finalize<MODE_ABBA><<<(unsigned)std::min<int64_t>(W, 65535), 64, 0, ctx->stream>>>(fp);
     pg_time_end(ctx, ti);
     PG_CUDA(cudaGetLastError());
+    return PG_OK;
+}
+
+extern "C" int pg_abbababa(pg_ctx* ctx, int32_t p1, int32_t p2, int32_t p3, int32_t o, double min_data, double* out,
+                           double* sites_used, int64_t* n_sites, int64_t* pos_sum) {
+    PG_CHECK(ctx && out && sites_used && n_sites && pos_sum, "pg_abbababa: null argument");
+    const int sel[4] = {p1, p2, p3, o};
+    const int RC = 8;
+    const int64_t W = ctx->W;
+    PG_CUDA(cudaSetDevice(ctx->device));
+    PG_TRY(ctx->out_d.ensure((size_t)std::max<int64_t>(W, 1) * RC * 8 + 64));
+    PG_TRY(pg_abba_enqueue(ctx, sel, min_data, ctx->out_d.p));
+    if (W == 0) return PG_OK;
     void* hp = nullptr;
     PG_TRY(pg_pinned(ctx, (size_t)W * RC * 8 + 64, &hp));
     const unsigned long long* hrec = (const unsigned long long*)hp;
@@ -1683,12 +1696,11 @@ extern "C" int pg_abbababa(pg_ctx* ctx, int32_t p1, int32_t p2, int32_t p3, int3
 // ================================================================================================
 // pg_fourpop
 // ================================================================================================
-extern "C" int pg_fourpop(pg_ctx* ctx, int32_t p1, int32_t p2, int32_t p3, int32_t p4, double min_data, int32_t mode,
-                          double* out, double* sites_used, int64_t* n_sites, int64_t* pos_sum) {
-    PG_CHECK(ctx && out && sites_used && n_sites && pos_sum, "pg_fourpop: null argument");
+// Enqueue site pass + finalize of genomics.fourPop; records [W x 17] words [sites, pos_sum, 14 statistics, sitesUsed]
+// are left in the DEVICE buffer d_rec.  No synchronisation.
+int pg_fourpop_enqueue(pg_ctx* ctx, const int* sel, double min_data, int mode, void* d_rec) {
     PG_CHECK(ctx->P >= 1, "pg_fourpop: call pg_set_pops first");
     PG_CHECK(mode >= 0 && mode <= 2, "pg_fourpop: mode must be 0 (default), 1 (polarize) or 2 (fixed)");
-    const int sel[4] = {p1, p2, p3, p4};
     for (int k = 0; k < 4; ++k) {
         PG_CHECK(sel[k] >= 0 && sel[k] < ctx->P, "pg_fourpop: population index %d out of range", sel[k]);
         for (int j = 0; j < k; ++j) PG_CHECK(sel[j] != sel[k], "pg_fourpop: populations must be distinct");
@@ -1697,18 +1709,20 @@ extern "C" int pg_fourpop(pg_ctx* ctx, int32_t p1, int32_t p2, int32_t p3, int32
     pg_timings_reset(ctx);
     const int64_t W = ctx->W;
     if (W == 0) return PG_OK;
+    const int Q = 19, RC = 17;
     if (ctx->S == 0) {
-        for (int64_t w = 0; w < W; ++w) {
-            n_sites[w] = 0;
-            pos_sum[w] = 0;
-            sites_used[w] = 0.0;
-            for (int k = 0; k < 14; ++k) out[w * 14 + k] = NAN;
-        }
+        std::vector<unsigned long long> h((size_t)W * RC, 0ull);       // sites, pos_sum, sitesUsed = 0.0
+        const double qn = NAN;
+        unsigned long long nanbits;
+        memcpy(&nanbits, &qn, 8);
+        for (int64_t w = 0; w < W; ++w)
+            for (int k = 2; k < 16; ++k) h[(size_t)w * RC + k] = nanbits;
+        PG_CUDA(cudaMemcpyAsync(d_rec, h.data(), h.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+        PG_CUDA(cudaStreamSynchronize(ctx->stream));
         return PG_OK;
     }
-    const int Q = 19, RC = 17;
     K1Cache& c = *cache_of(ctx, 2);
-    if (!c.valid || c.epoch != ctx->epoch || memcmp(c.sel, sel, sizeof(sel)) != 0) {
+    if (!c.valid || c.epoch != ctx->epoch || memcmp(c.sel, sel, 4 * sizeof(int)) != 0) {
         c.valid = false;
         std::vector<int32_t> local(ctx->H, -1);
         for (int h = 0; h < ctx->H; ++h)
@@ -1716,7 +1730,7 @@ extern "C" int pg_fourpop(pg_ctx* ctx, int32_t p1, int32_t p2, int32_t p3, int32
                 if (ctx->hap_pop[h] == sel[k]) local[h] = k;
         PG_TRY(prepare_windowed(ctx, c, local, 4, Q, k1_nw_for(ctx->pitch)));
         for (int k = 0; k < 4; ++k) PG_CHECK(c.pt.popN[k] >= 1, "pg_fourpop: population %d has no haplotypes", sel[k]);
-        memcpy(c.sel, sel, sizeof(sel));
+        memcpy(c.sel, sel, 4 * sizeof(int));
         c.epoch = ctx->epoch;
         c.valid = true;
     }
@@ -1732,17 +1746,29 @@ extern "C" int pg_fourpop(pg_ctx* ctx, int32_t p1, int32_t p2, int32_t p3, int32
     c.L.prm.variant = mode;
     PG_TRY(arm_slots(ctx, c));
     PG_TRY((launch_site_pass<MODE_FOURPOP, 4>(ctx, c.L, "k1_fourpop")));
-    PG_TRY(ctx->out_d.ensure((size_t)W * RC * 8 + 64));
     FinParams fp;
     fill_fin(fp, ctx, c, Q, 3);
     fp.P = 4;
     fp.Ppad = 4;
-    fp.rec = (unsigned long long*)ctx->out_d.p;
+    fp.rec = (unsigned long long*)d_rec;
     fp.RC = RC;
     const int ti = pg_time_begin(ctx, "k1_finalize");
     k1_finalize<MODE_FOURPOP><<<(unsigned)std::min<int64_t>(W, 65535), 64, 0, ctx->stream>>>(fp);
     pg_time_end(ctx, ti);
     PG_CUDA(cudaGetLastError());
+    return PG_OK;
+}
+
+extern "C" int pg_fourpop(pg_ctx* ctx, int32_t p1, int32_t p2, int32_t p3, int32_t p4, double min_data, int32_t mode,
+                          double* out, double* sites_used, int64_t* n_sites, int64_t* pos_sum) {
+    PG_CHECK(ctx && out && sites_used && n_sites && pos_sum, "pg_fourpop: null argument");
+    const int sel[4] = {p1, p2, p3, p4};
+    const int RC = 17;
+    const int64_t W = ctx->W;
+    PG_CUDA(cudaSetDevice(ctx->device));
+    PG_TRY(ctx->out_d.ensure((size_t)std::max<int64_t>(W, 1) * RC * 8 + 64));
+    PG_TRY(pg_fourpop_enqueue(ctx, sel, min_data, mode, ctx->out_d.p));
+    if (W == 0) return PG_OK;
     void* hp = nullptr;
     PG_TRY(pg_pinned(ctx, (size_t)W * RC * 8 + 64, &hp));
     const unsigned long long* hrec = (const unsigned long long*)hp;

@@ -168,3 +168,45 @@ extern "C" int pg_popgen_allgather(pg_ctx* ctx, int32_t min_sites, double min_da
     }
     return PG_OK;
 }
+
+namespace {
+// this rank's records (rc words per window, written by `enqueue` into its slot of the gather buffer) + all-gather + D2H
+template <typename F>
+int gather_fixed_records(pg_ctx* ctx, int rc, int64_t w_max, void* h_table, const char* what, F enqueue) {
+    PG_CHECK(ctx && h_table, "%s: null argument", what);
+    PG_CHECK(ctx->nccl_comm != nullptr, "%s: call pg_nccl_init first", what);
+    PG_CHECK(w_max >= ctx->W && w_max >= 1, "%s: w_max (%lld) is smaller than this rank's window count (%lld)", what,
+             (long long)w_max, (long long)ctx->W);
+    PG_CUDA(cudaSetDevice(ctx->device));
+    const size_t slot_words = (size_t)w_max * rc;
+    const size_t total_words = slot_words * (size_t)ctx->nccl_ranks;
+    PG_TRY(ctx->gather.ensure(total_words * 8));
+    unsigned long long* base = (unsigned long long*)ctx->gather.p;
+    unsigned long long* mine = base + slot_words * (size_t)ctx->nccl_rank;
+    PG_CUDA(cudaMemsetAsync(mine, 0, slot_words * 8, ctx->stream));
+    ctx->gather_words = 0;                                   // the popgen gather re-zeroes its layout next time
+    PG_TRY(enqueue(mine));
+    PG_NCCL(g_nccl.all_gather(mine, base, slot_words, NCCL_UINT64, (NcclComm)ctx->nccl_comm, ctx->stream));
+    ctx->launches += 1;
+    PG_CUDA(cudaMemcpyAsync(h_table, base, total_words * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    PG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PG_OK;
+}
+}  // namespace
+
+// ABBA-BABA statistics of this rank's windows + ONE ncclAllGather of every rank's records (config 3: ABBABABAwindows
+// window-sharded over the GPUs).  h_table: nranks * w_max * 8 words [sites, pos_sum, ABBA, BABA, D, fd, fdM, sitesUsed].
+extern "C" int pg_abbababa_allgather(pg_ctx* ctx, int32_t p1, int32_t p2, int32_t p3, int32_t o, double min_data,
+                                     int64_t w_max, void* h_table) {
+    const int sel[4] = {p1, p2, p3, o};
+    return gather_fixed_records(ctx, 8, w_max, h_table, "pg_abbababa_allgather",
+                                [&](void* d_rec) { return pg_abba_enqueue(ctx, sel, min_data, d_rec); });
+}
+
+// The same for genomics.fourPop: 17 words per window [sites, pos_sum, 14 statistics (pg_fourpop order), sitesUsed].
+extern "C" int pg_fourpop_allgather(pg_ctx* ctx, int32_t p1, int32_t p2, int32_t p3, int32_t p4, double min_data,
+                                    int32_t mode, int64_t w_max, void* h_table) {
+    const int sel[4] = {p1, p2, p3, p4};
+    return gather_fixed_records(ctx, 17, w_max, h_table, "pg_fourpop_allgather",
+                                [&](void* d_rec) { return pg_fourpop_enqueue(ctx, sel, min_data, mode, d_rec); });
+}

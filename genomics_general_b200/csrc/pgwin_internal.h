@@ -136,3 +136,5 @@ void pg_k1_cache_free(pg_ctx* ctx);
 int pg_nccl_allreduce_i64(pg_ctx* ctx, void* d_buf, size_t count);   // nccl_gather.cu
 int pg_popgen_enqueue(pg_ctx* ctx, int32_t min_sites, double min_data, int32_t force_path, void* d_rec, int** h_count);
 int pg_popgen_resolve(pg_ctx* ctx, int32_t min_sites, double min_data, void* d_rec, int nk2);
+int pg_abba_enqueue(pg_ctx* ctx, const int* sel, double min_data, void* d_rec);                 // records [W x 8]
+int pg_fourpop_enqueue(pg_ctx* ctx, const int* sel, double min_data, int mode, void* d_rec);    // records [W x 17]

@@ -193,6 +193,21 @@ class Engine:
               "pg_popgen_allgather")
         return int(n.value)
 
+    def abbababa_allgather(self, p1: int, p2: int, p3: int, o: int, min_data: float, w_max: int, table: np.ndarray):
+        """ABBA-BABA statistics of this rank's windows + ONE ncclAllGather: `table` float64 [world * w_max, 8] receives
+        [sites, pos_sum (int64 bit patterns), ABBA, BABA, D, fd, fdM, sitesUsed] per window (multigpu.unpack_abba_records)."""
+        assert table.dtype == np.float64 and table.flags.c_contiguous and table.shape == (self._world * int(w_max), 8)
+        check(self._lib.pg_abbababa_allgather(self._ctx, p1, p2, p3, o, float(min_data), int(w_max), _ptr(table)),
+              "pg_abbababa_allgather")
+
+    def fourpop_allgather(self, p1: int, p2: int, p3: int, p4: int, min_data: float, w_max: int, table: np.ndarray,
+                          polarize: bool = False, fixed: bool = False):
+        """genomics.fourPop of this rank's windows + ONE ncclAllGather: `table` float64 [world * w_max, 17]."""
+        assert table.dtype == np.float64 and table.flags.c_contiguous and table.shape == (self._world * int(w_max), 17)
+        mode = 1 if polarize else (2 if fixed else 0)
+        check(self._lib.pg_fourpop_allgather(self._ctx, p1, p2, p3, p4, float(min_data), mode, int(w_max), _ptr(table)),
+              "pg_fourpop_allgather")
+
     def abbababa(self, p1: int, p2: int, p3: int, o: int, min_data: float = 0.01):
         """-> dict(ABBA,BABA,D,fd,fdM [W], sitesUsed [W] (nan = no good site), sites, pos_sum)."""
         W = self.W

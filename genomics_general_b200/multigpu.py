@@ -103,3 +103,26 @@ def unpack_device_records(rec: np.ndarray, P: int) -> dict:
     return dict(sites=ints[:, 0].copy(), pos_sum=ints[:, 1].copy(), path=ints[:, 2].astype(np.int32),
                 pi=rec[:, 3:3 + P], dxy=rec[:, 3 + P:3 + P + npairs], fst=rec[:, 3 + P + npairs:3 + P + 2 * npairs],
                 popfreq=rec[:, 3 + P + 2 * npairs:])
+
+
+def gathered_rows(table: np.ndarray, counts, w_max: int) -> np.ndarray:
+    """rows of every rank (rank order) out of a gathered [world * w_max, C] table"""
+    return np.concatenate([table[r * w_max: r * w_max + int(counts[r])] for r in range(len(counts))], axis=0)
+
+
+def unpack_abba_records(rec: np.ndarray) -> dict:
+    """records of pg_abbababa_allgather: [sites, pos_sum (int64 bit patterns), ABBA, BABA, D, fd, fdM, sitesUsed]"""
+    ints = np.ascontiguousarray(rec[:, :2]).view(np.int64)
+    return dict(sites=ints[:, 0].copy(), pos_sum=ints[:, 1].copy(), ABBA=rec[:, 2], BABA=rec[:, 3], D=rec[:, 4], fd=rec[:, 5],
+                fdM=rec[:, 6], sitesUsed=rec[:, 7])
+
+
+FOURPOP_KEYS = ('fhom', "fhom'", 'D', 'fd', "fd'", 'fdm', "fdm'", 'fdh', 'fdh2', 'fh', "ABBA", "BABA", "ABAA", "BAAA")
+
+
+def unpack_fourpop_records(rec: np.ndarray) -> dict:
+    """records of pg_fourpop_allgather: [sites, pos_sum, 14 statistics, sitesUsed]"""
+    ints = np.ascontiguousarray(rec[:, :2]).view(np.int64)
+    out = {k: rec[:, 2 + i] for i, k in enumerate(FOURPOP_KEYS)}
+    out.update(sites=ints[:, 0].copy(), pos_sum=ints[:, 1].copy(), sitesUsed=rec[:, 16])
+    return out

@@ -173,6 +173,13 @@ int pg_nccl_init(pg_ctx* ctx, int32_t nranks, int32_t rank, const void* id128);
 int pg_nccl_finalize(pg_ctx* ctx);
 int pg_popgen_allgather(pg_ctx* ctx, int32_t min_sites, double min_data, int32_t force_path, int64_t w_max,
                         void* h_table, int64_t* n_pairwise);
+/* The same for the ABBA-BABA statistics (ABBABABAwindows.py window-sharded over the GPUs): h_table receives
+ * nranks * w_max * 8 words per window [sites (int64), pos_sum (int64), ABBA, BABA, D, fd, fdM, sitesUsed (doubles)],
+ * and for genomics.fourPop: 17 words [sites, pos_sum, the 14 statistics in pg_fourpop's order, sitesUsed]. */
+int pg_abbababa_allgather(pg_ctx* ctx, int32_t p1, int32_t p2, int32_t p3, int32_t o, double min_data, int64_t w_max,
+                          void* h_table);
+int pg_fourpop_allgather(pg_ctx* ctx, int32_t p1, int32_t p2, int32_t p3, int32_t p4, double min_data, int32_t mode,
+                         int64_t w_max, void* h_table);
 
 /* ---- host-side .geno text ingest (no CUDA) ------------------------------------------------------ */
 /* Replaces parseGenoLine/GenoFileReader (genomics.py:1884-1945) + splitSeq/haplo/forceHomo (390-396, 27, 407)

@@ -54,6 +54,30 @@ def main():
         for k in ("pi", "dxy", "fst"):
             assert np.allclose(got[k], ref[k], rtol=1e-12, atol=0, equal_nan=True), k
         table.close()
+        # ABBA-BABA and fourPop, window-sharded the same way (config 3)
+        eng.upload(g[s0:s1], pos[s0:s1])
+        eng.set_pops(spec.hap_pop(), 4)
+        eng.set_windows(lo[b:e] - s0, hi[b:e] - s0)
+        ta = PinnedArray((world * w_max, 8), np.float64)
+        eng.abbababa_allgather(0, 1, 2, 3, 0.5, w_max, ta.array)
+        ga = multigpu.unpack_abba_records(multigpu.gathered_rows(ta.array, counts, w_max))
+        tf = PinnedArray((world * w_max, 17), np.float64)
+        eng.fourpop_allgather(0, 1, 2, 3, 0.5, w_max, tf.array, polarize=True)
+        gf = multigpu.unpack_fourpop_records(multigpu.gathered_rows(tf.array, counts, w_max))
+        eng.upload(g, pos)
+        eng.set_pops(spec.hap_pop(), 4)
+        eng.set_windows(lo, hi)
+        ra = eng.abbababa(0, 1, 2, 3, 0.5)
+        rf = eng.fourpop(0, 1, 2, 3, 0.5, polarize=True)
+        for k in ("sites", "pos_sum"):
+            assert np.array_equal(ga[k], ra[k]) and np.array_equal(gf[k], rf[k]), k
+        # fp64 sums: a shard tiles its sites differently, so the summation order differs from the single-GPU run
+        for k in ("ABBA", "BABA", "D", "fd", "fdM", "sitesUsed"):
+            assert np.allclose(ga[k], ra[k], rtol=1e-11, atol=1e-13, equal_nan=True), k
+        for k in multigpu.FOURPOP_KEYS + ("sitesUsed",):
+            assert np.allclose(gf[k], rf[k], rtol=1e-10, atol=1e-13, equal_nan=True), k
+        ta.close()
+        tf.close()
     # ---- distMat --windType cat: the single window is sharded along the SITE axis; one ncclAllReduce of the
     # integer pair matrices ----
     spec = synth.SynthSpec(3, 6, miss=0.04, seed=8)
