@@ -160,3 +160,33 @@ def test_sfs_oracle_matches_reference_output(key):
                        outgroup=len(inpops) if outgroup else -1, site_mask=mask)
     text = "".join("\n".join("\t".join(str(x) for x in list(k) + [v]) for k, v in ch) + "\n" for ch in chains)
     assert text == CLI2[key]
+
+
+@pytest.mark.parametrize("key", [k for k in CLI2 if k.startswith("sfs_") and k + "_args" in CLI2])
+def test_sfs_row_order_from_dense_histograms(key):
+    """Host logic of the sfs command line (no GPU): dense spectrum + first-site array -> the reference's sparse rows in
+    nested-dict insertion order (cli/sfs.py::ordered_chains), against the reference script's own output."""
+    from genomics_general_b200.cli.sfs import ordered_chains
+    spec, g, scaf = sfs_inputs()
+    extra = CLI2[key + "_args"]
+    inpops, outgroup, groups, keep = sfs_plan(extra)
+    order = inpops + ([outgroup] if outgroup else [])
+    remap = {int(p[3:]): k for k, p in enumerate(order)}
+    hp = np.array([remap[x] for x in spec.hap_pop()], dtype=np.int32)
+    tc, used = do.sfs_target_counts(g, hp, len(inpops), len(inpops) if outgroup else -1)
+    if keep is not None:
+        used &= np.isin(scaf, keep[1]) if keep[0] else ~np.isin(scaf, keep[1])
+    sizes = [int((hp == x).sum()) for x in range(len(inpops))]
+    text = ""
+    for grp in groups:
+        gi = [inpops.index(p) for p in grp]
+        shape = tuple(sizes[x] + 1 for x in gi)
+        hist = np.zeros(shape, dtype=np.int64)
+        first = np.full(shape, -1, dtype=np.int64)
+        for s in np.where(used)[0]:                     # what pg_sfs's atomicAdd / atomicMin leave behind
+            cell = tuple(int(tc[s, x]) for x in gi)
+            hist[cell] += 1
+            if first[cell] < 0:
+                first[cell] = s
+        text += "\n".join("\t".join(str(x) for x in row) for row in ordered_chains(hist, first)) + "\n"
+    assert text == CLI2[key]
