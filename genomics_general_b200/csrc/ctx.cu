@@ -4,6 +4,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <thread>
 
 #include "pgwin_internal.h"
 
@@ -118,6 +119,53 @@ int pg_pinned(pg_ctx* ctx, size_t bytes, void** out) {
         ctx->h_pinned_cap = want;
     }
     *out = ctx->h_pinned;
+    return PG_OK;
+}
+
+// Large device -> PAGEABLE host copy (the 800 MB of distMat matrices): a cudaMemcpy into pageable memory is staged by the
+// driver at a few GB/s.  Here the copy engine fills two pinned 64 MB buffers in turn while host threads move the previous
+// one to its destination.  Synchronous: dst is complete on return (work queued on the ctx stream before is waited for).
+int pg_d2h_staged(pg_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (bytes == 0) return PG_OK;
+    const size_t slab = (size_t)64 << 20;
+    if (bytes < ((size_t)8 << 20)) {
+        PG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        PG_CUDA(cudaStreamSynchronize(ctx->stream));
+        return PG_OK;
+    }
+    if (!ctx->h_text[0]) {
+        for (int k = 0; k < 2; ++k) {
+            PG_CUDA(cudaHostAlloc(&ctx->h_text[k], slab, cudaHostAllocDefault));
+            PG_CUDA(cudaEventCreateWithFlags(&ctx->h_text_free[k], cudaEventDisableTiming));
+        }
+    }
+    const int n_threads = std::max(1, std::min(16, (int)std::thread::hardware_concurrency() / 2));
+    auto drain = [&](int b, size_t off, size_t n) {
+        std::vector<std::thread> th;
+        auto work = [&](int t) {
+            const size_t a = n * (size_t)t / (size_t)n_threads, e = n * (size_t)(t + 1) / (size_t)n_threads;
+            memcpy((char*)dst + off + a, (const char*)ctx->h_text[b] + a, e - a);
+        };
+        for (int t = 1; t < n_threads; ++t) th.emplace_back(work, t);
+        work(0);
+        for (auto& x : th) x.join();
+    };
+    size_t prev_off = 0, prev_n = 0;
+    int k = 0;
+    for (size_t off = 0; off < bytes; off += slab, ++k) {
+        const size_t n = std::min(slab, bytes - off);
+        const int b = k & 1;
+        PG_CUDA(cudaMemcpyAsync(ctx->h_text[b], (const char*)src + off, n, cudaMemcpyDeviceToHost, ctx->stream));
+        PG_CUDA(cudaEventRecord(ctx->h_text_free[b], ctx->stream));
+        if (k > 0) {                                           // the previous slab: wait for its copy, move it out
+            PG_CUDA(cudaEventSynchronize(ctx->h_text_free[b ^ 1]));
+            drain(b ^ 1, prev_off, prev_n);
+        }
+        prev_off = off;
+        prev_n = n;
+    }
+    PG_CUDA(cudaEventSynchronize(ctx->h_text_free[(k - 1) & 1]));
+    drain((k - 1) & 1, prev_off, prev_n);
     return PG_OK;
 }
 

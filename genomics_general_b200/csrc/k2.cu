@@ -1080,8 +1080,7 @@ extern "C" int pg_pairdist(pg_ctx* ctx, int32_t n_ind, const int32_t* hap_ind, i
         while (k < nb) {
             size_t e = k + 1;
             while (e < nb && nonempty[b0 + e] == nonempty[b0 + e - 1] + 1) ++e;
-            PG_CUDA(cudaMemcpyAsync(dist + (size_t)nonempty[b0 + k] * nn, (double*)ctx->out_d.p + k * nn,
-                                    (e - k) * nn * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            PG_TRY(pg_d2h_staged(ctx, dist + (size_t)nonempty[b0 + k] * nn, (double*)ctx->out_d.p + k * nn, (e - k) * nn * 8));
             k = e;
         }
         PG_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -126,6 +126,7 @@ void pg_timings_reset(pg_ctx* ctx);
 int pg_time_begin(pg_ctx* ctx, const char* name);   // returns timing index
 void pg_time_end(pg_ctx* ctx, int idx);
 int pg_pinned(pg_ctx* ctx, size_t bytes, void** out);
+int pg_d2h_staged(pg_ctx* ctx, void* dst, const void* src, size_t bytes);   // large device -> pageable host copy
 int pg_build_segments(pg_ctx* ctx);
 
 // implemented in k1.cu / k2.cu
