@@ -1975,9 +1975,7 @@ extern "C" int pg_site_counts(pg_ctx* ctx, int64_t site0, int64_t n, uint16_t* c
     for (int64_t s = 0; s < n; s += slab) {
         const int64_t cnt = std::min(slab, n - s);
         PG_TRY(site_counts_slab(ctx, site0 + s, cnt));
-        PG_CUDA(cudaMemcpyAsync(counts + (size_t)s * stride, ctx->misc.p, (size_t)cnt * stride * 2,
-                                cudaMemcpyDeviceToHost, ctx->stream));
-        PG_CUDA(cudaStreamSynchronize(ctx->stream));
+        PG_TRY(pg_d2h_staged(ctx, counts + (size_t)s * stride, ctx->misc.p, (size_t)cnt * stride * 2));
     }
     return PG_OK;
 }
@@ -2007,9 +2005,8 @@ extern "C" int pg_site_target_freqs(pg_ctx* ctx, int64_t site0, int64_t n, int32
                                                                               min_data, as_counts ? 1 : 0, d_out, d_tie);
         pg_time_end(ctx, ti);
         PG_CUDA(cudaGetLastError());
-        PG_CUDA(cudaMemcpyAsync(out + (size_t)s * P, d_out, (size_t)cnt * P * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        if (tie) PG_CUDA(cudaMemcpyAsync(tie + s, d_tie, (size_t)cnt, cudaMemcpyDeviceToHost, ctx->stream));
-        PG_CUDA(cudaStreamSynchronize(ctx->stream));
+        PG_TRY(pg_d2h_staged(ctx, out + (size_t)s * P, d_out, (size_t)cnt * P * 8));
+        if (tie) PG_TRY(pg_d2h_staged(ctx, tie + s, d_tie, (size_t)cnt));
     }
     return PG_OK;
 }
