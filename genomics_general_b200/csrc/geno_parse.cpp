@@ -15,6 +15,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
 #include <string>
 #include <thread>
@@ -60,6 +61,45 @@ void index_lines(const char* buf, size_t begin, size_t end, std::vector<size_t>&
     }
 }
 
+// the same over the whole buffer with several threads: a line belongs to the thread whose byte range holds its first byte
+void index_lines_parallel(const char* buf, size_t len, int n_threads, std::vector<size_t>& starts) {
+    if (n_threads < 2 || len < ((size_t)1 << 22)) {
+        index_lines(buf, 0, len, starts);
+        return;
+    }
+    std::vector<std::vector<size_t>> part((size_t)n_threads);
+    auto work = [&](int t) {
+        size_t b = len * (size_t)t / (size_t)n_threads, e = len * (size_t)(t + 1) / (size_t)n_threads;
+        if (t > 0 && buf[b - 1] != '\n') {            // the line that straddles the boundary belongs to the previous thread
+            const char* nl = (const char*)memchr(buf + b, '\n', len - b);
+            b = nl ? (size_t)(nl - buf) + 1 : len;
+        }
+        // index_lines stops at `end`; lines that START before e are wanted in full, so scan line by line here
+        size_t i = b;
+        while (i < e) {
+            const char* nl = (const char*)memchr(buf + i, '\n', len - i);
+            const size_t le = nl ? (size_t)(nl - buf) : len;
+            size_t j = i;
+            while (j < le && is_ws(buf[j])) ++j;
+            if (j < le && buf[i] != '#') part[(size_t)t].push_back(i);
+            i = le + 1;
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < n_threads; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto& x : th) x.join();
+    size_t total = 0;
+    for (auto& v : part) total += v.size();
+    starts.reserve(starts.size() + total);
+    for (auto& v : part) starts.insert(starts.end(), v.begin(), v.end());
+}
+
+int default_threads() {
+    const unsigned hc = std::thread::hardware_concurrency();
+    return (int)std::max(1u, std::min(16u, hc / 2));
+}
+
 }  // namespace
 
 extern "C" int pg_geno_count_lines(const char* buf, size_t len, int64_t* n) {
@@ -68,7 +108,7 @@ extern "C" int pg_geno_count_lines(const char* buf, size_t len, int64_t* n) {
         return 1;
     }
     std::vector<size_t> st;
-    index_lines(buf, 0, len, st);
+    index_lines_parallel(buf, len, default_threads(), st);
     *n = (int64_t)st.size();
     return 0;
 }
@@ -87,7 +127,7 @@ extern "C" int pg_geno_parse(const char* buf, size_t len, int32_t fmt, int32_t n
     }
     std::vector<size_t> starts;
     starts.reserve((size_t)n_lines + 1);
-    index_lines(buf, 0, len, starts);
+    index_lines_parallel(buf, len, n_threads > 0 ? n_threads : default_threads(), starts);
     if ((int64_t)starts.size() != n_lines) {
         pg_set_error("pg_geno_parse: buffer holds %lld data lines, caller allocated %lld", (long long)starts.size(),
                      (long long)n_lines);
