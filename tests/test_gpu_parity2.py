@@ -562,3 +562,29 @@ def test_lane_per_population_with_interleaved_columns(eng, P, monkeypatch):
         assert ok
         assert_close(res[1][0][w], pi, "pi", **TOL)
         assert_close(res[1][1][w], dxy, "dxy", **TOL)
+
+
+def test_haploid_samples_in_a_phased_file_cli(inputs2, tmp_path):
+    """--haploid: the named samples carry one-letter tokens (ploidy 1) — popgenWindows and ABBABABAwindows rows against the
+    reference scripts' own output on the same mixed-ploidy file."""
+    from genomics_general_b200 import geno_io
+    from genomics_general_b200.cli import ABBABABAwindows, popgenWindows
+    d = CLI2["four_pops"]
+    hap = d["popgen_phased_haploid_samples"]
+    gd = geno_io.parse_geno(inputs2["geno"], geno_format="phased")
+    lut = np.array(list("ACGTN"))
+    ch = lut[np.where(gd.geno < 0, 4, gd.geno)]
+    mpath = str(tmp_path / "mixed.geno")
+    hap_idx = {gd.names.index(n) for n in hap}
+    with open(mpath, "wt") as f:
+        f.write("#CHROM\tPOS\t" + "\t".join(gd.names) + "\n")
+        for s in range(gd.n_sites):
+            toks = [ch[s, 2 * k] if k in hap_idx else ch[s, 2 * k] + "/" + ch[s, 2 * k + 1] for k in range(len(gd.names))]
+            f.write("%s\t%d\t%s\n" % (gd.scaf_names[gd.scaf_ids[s]], gd.pos[s], "\t".join(toks)))
+    o = str(tmp_path / "o.csv")
+    popgenWindows.main(["-o", o, "-T", "1", "--roundTo", "9", "-w", "20000", "-m", "50", "-g", mpath, "-f", "phased",
+                        "--popsFile", inputs2["pops"], "--haploid", ",".join(hap)] + inputs2["popargs"])
+    _compare_by_column(open(o).read(), d["popgen_phased_haploid"], atol=2e-9)
+    ABBABABAwindows.main(["-w", "20000", "-m", "50", "-g", mpath, "-o", o, "-f", "phased", "-T", "1", "--popsFile", inputs2["pops"],
+                          "--minData", "0.5", "--haploid", ",".join(hap), "-P1", "pop0", "-P2", "pop1", "-P3", "pop2", "-O", "pop3"])
+    _compare_by_column(open(o).read(), d["abba_phased_haploid"], n_prefix=6, atol=1.0001e-4)
