@@ -588,3 +588,25 @@ def test_haploid_samples_in_a_phased_file_cli(inputs2, tmp_path):
     ABBABABAwindows.main(["-w", "20000", "-m", "50", "-g", mpath, "-o", o, "-f", "phased", "-T", "1", "--popsFile", inputs2["pops"],
                           "--minData", "0.5", "--haploid", ",".join(hap), "-P1", "pop0", "-P2", "pop1", "-P3", "pop2", "-O", "pop3"])
     _compare_by_column(open(o).read(), d["abba_phased_haploid"], n_prefix=6, atol=1.0001e-4)
+
+
+def test_freq_target_minor_cli_rows_without_ties(inputs2):
+    """freq.py --target minor: byte-identical rows wherever the reference's choice is not random (no exact tie)."""
+    from genomics_general_b200 import synth
+    from genomics_general_b200.cli import freq
+    d = CLI2["four_pops"]
+    c = d["cfg"]
+    spec = synth.SynthSpec(c["n_pops"], c["spp"], seed=c["seed"], miss=c["miss"])
+    g = synth.synth_genotypes(spec, 0, c["S"])
+    tot = np.stack([(g == a).sum(axis=1) for a in range(4)], axis=1)
+    srt = np.sort(tot, axis=1)
+    tied = (srt[:, 2] > 0) & (srt[:, 2] == srt[:, 3]) & (srt[:, 1] == 0)
+    o = os.path.join(inputs2["dir"], "minor.tsv")
+    freq.main(["-g", inputs2["geno"], "-o", o, "-f", "phased", "-t", "1", "--popsFile", inputs2["pops"], "--target", "minor",
+               "--keepNanLines"] + inputs2["popargs"])
+    ours = open(o).read().splitlines()
+    ref = d["freq_minor_keepnan"]
+    assert len(ours) == len(ref) == c["S"] + 1 and ours[0] == ref[0]
+    same = [a == b for a, b in zip(ours[1:], ref[1:])]
+    assert all(s or t for s, t in zip(same, tied)), "a row without a tie differs"
+    assert tied.sum() > 0 and sum(same) >= c["S"] - int(tied.sum())
