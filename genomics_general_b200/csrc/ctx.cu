@@ -18,7 +18,7 @@ void pg_set_error(const char* fmt, ...) {
 }
 
 extern "C" const char* pg_last_error(void) { return g_err; }
-extern "C" int pg_version(void) { return 100; }
+extern "C" int pg_version(void) { return 110; }
 
 extern "C" int pg_device_count(int* n) {
     PG_CHECK(n != nullptr, "pg_device_count: null argument");
