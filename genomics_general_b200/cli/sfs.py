@@ -1,10 +1,11 @@
 #!/usr/bin/env python
-"""Drop-in for the reference's sfs.py on genotype input (`--inputType genotypes`, flags sfs.py:158-236): site frequency
-spectra of each population and, on request, the joint spectra of pairs / trios / quartets, computed on the GPU
-(per-site counts -> target allele -> dense histograms, `pg_sfs`) and written in the reference's sparse format and order.
+"""Drop-in for the reference's sfs.py (flags sfs.py:158-236): site frequency spectra of each population and, on request,
+the joint spectra of pairs / trios / quartets, computed on the GPU — from genotypes (`--inputType genotypes`: per-site
+counts -> target allele -> dense histograms, `pg_sfs`) or from tables of counts (`baseCounts`: the rows freq.py writes;
+`targetCounts`, the script's default: e.g. freq.py --target derived --asCounts; `pg_sfs_tables`) — and written in the
+reference's sparse format and order.
 
-Not covered: `--inputType baseCounts|targetCounts` (text tables of counts), `--subsample` (the reference draws with
-numpy's global RNG per site), `--regions`.  Where the reference's choice of the minor allele depends on numpy's unstable
+Not covered: `--subsample` (the reference draws with numpy's global RNG per site), `--regions`.  Where the reference's choice of the minor allele depends on numpy's unstable
 sort (two alleles with exactly equal counts, sfs.py:90) the lower allele is used.
 """
 from __future__ import annotations
@@ -76,16 +77,78 @@ def ordered_chains(hist, first):
     return [list(map(int, nz[i])) + [int(cnt[i])] for i in order]
 
 
+def write_spectra(args, FSpops, hists, firsts):
+    write_spectra(args, FSpops, hists, firsts)
+
+
+def main_tables(args, include, exclude):
+    """--inputType baseCounts | targetCounts (sfs.py:330-365, 456-474): one column per population."""
+    import gzip
+    import io
+    import pandas as pd
+    opener = gzip.open if args.inputFile and args.inputFile.endswith(".gz") else open
+    with (opener(args.inputFile, "rt") if args.inputFile else sys.stdin) as f:
+        header = args.header if args.header else f.readline()
+        body = "".join(line for line in f if line[:1] != "#")
+    names = header.split()[2:]
+    popNames = []
+    if args.pop or args.FSpops:
+        for pop in args.pop or []:
+            popNames.append(pop[0])
+        for pop in [p for pops in (args.FSpops or []) for p in pops]:
+            if pop not in popNames:
+                popNames.append(pop)
+    else:
+        popNames = list(names)
+    sys.stderr.write("\nPopulations:\n" + " ".join(popNames) + "\n")
+    outgroup = None
+    inPopNames = list(popNames)
+    if args.inputType == "baseCounts" and (args.polarized or args.outgroup):
+        outgroup = args.outgroup if args.outgroup else popNames[-1]
+        inPopNames = [pn for pn in popNames if pn != outgroup]
+        sys.stderr.write("\nFrequencies will be polarized assuming outgroup is {}\n".format(outgroup))
+    if args.FSpops:
+        FSpops = [list(g) for g in args.FSpops]
+    else:
+        FSpops = [[pn] for pn in inPopNames]
+        if args.doPairs:
+            FSpops += [list(c) for c in itertools.combinations(inPopNames, 2)]
+        if args.doTrios:
+            FSpops += [list(c) for c in itertools.combinations(inPopNames, 3)]
+        if args.doQuartets:
+            FSpops += [list(c) for c in itertools.combinations(inPopNames, 4)]
+    df = pd.read_csv(io.StringIO(body), sep=r"\s+", header=None, names=["scaffold", "position"] + names, dtype=str)
+    order = inPopNames + ([outgroup] if outgroup else [])
+    mask = None
+    if include or exclude:
+        sc = df["scaffold"].to_numpy()
+        mask = np.array([(not include or x in include) and (x not in exclude) for x in sc], dtype=np.uint8)
+    if args.inputType == "baseCounts":
+        cols = []
+        for pn in order:
+            parts = df[pn].str.split(",", expand=True).to_numpy(dtype=np.float64)      # "a,c,g,t" (floats allowed, 459)
+            cols.append(parts.astype(np.int64))
+        table = np.stack(cols, axis=1) if len(df) else np.zeros((0, len(order), 4), dtype=np.int64)
+        assert table.max(initial=0) <= 65535, "counts above 65535 are not supported"
+        kind = "base"
+    else:
+        table = df[order].to_numpy(dtype=np.int64) if len(df) else np.zeros((0, len(order)), dtype=np.int64)
+        kind = "target"
+    groups = [tuple(inPopNames.index(pn) for pn in grp) for grp in FSpops]
+    with Engine(args.device) as eng:
+        hists, firsts, _ = eng.sfs_tables(kind, table, len(inPopNames), groups, outgroup=len(inPopNames) if outgroup else -1,
+                                          site_mask=mask)
+    write_spectra(args, FSpops, hists, firsts)
+
+
 def main(argv=None):
     args = build_parser().parse_args(argv)
-    if args.inputType != "genotypes":
-        raise NotImplementedError("--inputType %s is not on the GPU path (genotypes only)" % args.inputType)
     if args.subsample or args.subsampleIndividuals:
         raise NotImplementedError("--subsample draws with numpy's global RNG per site in the reference; not supported")
     if args.regions or args.regionsFile:
         raise NotImplementedError("--regions is not supported")
     assert (args.scafCol, args.posCol, args.firstSampleCol) == (0, 1, 2), "non-default column layout is not supported"
-    if not args.polarized and args.outgroup is None:
+    if not args.polarized and args.outgroup is None and args.inputType != "targetCounts":
         sys.stderr.write("\nNo outgroup provided. Minor allele frequency will be used.\n")
     include = set(args.include or [])
     exclude = set(args.exclude or [])
@@ -93,6 +156,8 @@ def main(argv=None):
         include |= set(open(args.includeFile, "rt").read().split())
     if args.excludeFile:
         exclude |= set(open(args.excludeFile, "rt").read().split())
+    if args.inputType != "genotypes":
+        return main_tables(args, include, exclude)
 
     headerInds = C.header_names(args.inputFile) if args.header is None else args.header.split()[2:]
     popNames, popDict = [], {}
@@ -162,13 +227,7 @@ def main(argv=None):
         sizes = [int((hp == x).sum()) for x in range(len(enginePops))]
         groups = [tuple(inPopNames.index(pn) for pn in grp) for grp in FSpops]
         hists, firsts, _ = eng.sfs(len(inPopNames), groups, sizes, outgroup=len(inPopNames) if outgroup else -1, site_mask=mask)
-    for i, grp in enumerate(FSpops):
-        text = "\n".join("\t".join(str(x) for x in row) for row in ordered_chains(hists[i], firsts[i])) + "\n"
-        if args.pipe:
-            sys.stdout.write(text)
-        else:
-            with open(args.pref + "_".join(grp) + args.suff, "w") as out:
-                out.write(text)
+    write_spectra(args, FSpops, hists, firsts)
 
 
 if __name__ == "__main__":

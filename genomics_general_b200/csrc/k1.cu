@@ -2020,6 +2020,9 @@ struct SfsParams {
     int64_t n, site0;           // sites of the slab, absolute index of its first site
     int P, n_in, outgroup;      // in-group = populations 0 .. n_in-1; outgroup = population index or -1
     int popN[PG_MAX_POPS];      // haplotypes per population: an in-group population must be complete (sfs.py:449)
+    int dims[PG_MAX_POPS];      // radix of each population in the histograms (largest possible count + 1)
+    int require_complete;       // genotype input only
+    const int32_t* targets;     // targetCounts input: [n x P] counts of the target allele, no allele logic at all
     const uint8_t* mask;        // [S] absolute, or nullptr
     int n_groups;
     const int32_t* group_off;   // [n_groups+1] into group_pops
@@ -2035,11 +2038,22 @@ __global__ void __launch_bounds__(256) k1_sfs(const __grid_constant__ SfsParams 
     if (s >= sp.n) return;
     const int64_t site = sp.site0 + s;
     if (sp.mask && !sp.mask[site]) return;
+    if (sp.targets) {                                                // sfs.py:472-474: the table already holds the counts
+        const int32_t* t = sp.targets + s * sp.P;
+        atomicAdd(sp.n_counted, 1ull);
+        for (int g = 0; g < sp.n_groups; ++g) {
+            long long idx = 0;
+            for (int k = sp.group_off[g]; k < sp.group_off[g + 1]; ++k) idx = idx * sp.dims[sp.group_pops[k]] + t[sp.group_pops[k]];
+            atomicAdd(sp.hist + sp.hist_off[g] + idx, 1ull);
+            atomicMin(sp.first + sp.hist_off[g] + idx, (long long)site);
+        }
+        return;
+    }
     const ushort4* c = reinterpret_cast<const ushort4*>(sp.counts) + s * sp.P;
     unsigned tot[4] = {0, 0, 0, 0};
     for (int X = 0; X < sp.n_in; ++X) {
         const ushort4 v = c[X];
-        if ((int)v.x + v.y + v.z + v.w != sp.popN[X]) return;      // every in-group haplotype must be called (449)
+        if (sp.require_complete && (int)v.x + v.y + v.z + v.w != sp.popN[X]) return;   // every in-group haplotype called (449)
         tot[0] += v.x;
         tot[1] += v.y;
         tot[2] += v.z;
@@ -2086,7 +2100,7 @@ __global__ void __launch_bounds__(256) k1_sfs(const __grid_constant__ SfsParams 
             const int X = sp.group_pops[k];
             const ushort4 v = c[X];
             const unsigned t = target == 0 ? v.x : (target == 1 ? v.y : (target == 2 ? v.z : v.w));
-            idx = idx * (sp.popN[X] + 1) + t;
+            idx = idx * sp.dims[X] + t;
         }
         atomicAdd(sp.hist + sp.hist_off[g] + idx, 1ull);
         atomicMin(sp.first + sp.hist_off[g] + idx, (long long)site);
@@ -2162,7 +2176,11 @@ extern "C" int pg_sfs(pg_ctx* ctx, int32_t n_in, int32_t outgroup, int32_t n_gro
         sp.P = P;
         sp.n_in = n_in;
         sp.outgroup = outgroup;
-        for (int X = 0; X < P; ++X) sp.popN[X] = popN[X];
+        for (int X = 0; X < P; ++X) {
+            sp.popN[X] = popN[X];
+            sp.dims[X] = popN[X] + 1;
+        }
+        sp.require_complete = 1;
         sp.mask = d_mask;
         sp.n_groups = n_groups;
         sp.group_off = d_goff;
@@ -2175,6 +2193,105 @@ extern "C" int pg_sfs(pg_ctx* ctx, int32_t n_in, int32_t outgroup, int32_t n_gro
         k1_sfs<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>(sp);
         pg_time_end(ctx, ti);
         PG_CUDA(cudaGetLastError());
+    }
+    unsigned long long h_cnt = 0;
+    PG_CUDA(cudaMemcpyAsync(hist, d_hist, (size_t)cells * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    PG_CUDA(cudaMemcpyAsync(first, d_first, (size_t)cells * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    PG_CUDA(cudaMemcpyAsync(&h_cnt, d_cnt, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    PG_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (long long k = 0; k < cells; ++k)
+        if (hist[k] == 0) first[k] = -1;
+    if (n_counted) *n_counted = (int64_t)h_cnt;
+    return PG_OK;
+}
+
+// The same spectra from TABLES of counts on the host (sfs.py --inputType baseCounts | targetCounts, sfs.py:456-474): no
+// genotype matrix, no completeness test.  kind 0: table = uint16 [n x P x 4] base counts per population (freq.py's
+// default output); kind 1: table = int32 [n x P] counts of the target allele.  dims[X] = largest count of population X + 1.
+extern "C" int pg_sfs_tables(pg_ctx* ctx, int32_t kind, const void* table, int64_t n, int32_t P, const int32_t* dims,
+                             int32_t n_in, int32_t outgroup, int32_t n_groups, const int32_t* group_off,
+                             const int32_t* group_pops, const uint8_t* site_mask, int64_t* hist, int64_t* first,
+                             int64_t* n_counted) {
+    PG_CHECK(ctx && (table || n == 0) && dims && group_off && group_pops && hist && first, "pg_sfs_tables: null argument");
+    PG_CHECK(kind == 0 || kind == 1, "pg_sfs_tables: kind must be 0 (base counts) or 1 (target counts)");
+    PG_CHECK(P >= 1 && P <= PG_MAX_POPS, "pg_sfs_tables: at most %d populations", PG_MAX_POPS);
+    PG_CHECK(n_in >= 1 && n_in <= P && n >= 0, "pg_sfs_tables: bad shape");
+    PG_CHECK(outgroup == -1 || (kind == 0 && outgroup >= n_in && outgroup < P), "pg_sfs_tables: bad outgroup");
+    PG_CHECK(n_groups >= 1, "pg_sfs_tables: no spectra requested");
+    PG_CUDA(cudaSetDevice(ctx->device));
+    pg_timings_reset(ctx);
+    std::vector<long long> hist_off(n_groups, 0);
+    long long cells = 0;
+    for (int g = 0; g < n_groups; ++g) {
+        hist_off[g] = cells;
+        long long sz = 1;
+        PG_CHECK(group_off[g + 1] > group_off[g], "pg_sfs_tables: spectrum %d has no population", g);
+        for (int k = group_off[g]; k < group_off[g + 1]; ++k) {
+            PG_CHECK(group_pops[k] >= 0 && group_pops[k] < n_in, "pg_sfs_tables: spectrum %d uses a population outside the in-group", g);
+            PG_CHECK(dims[group_pops[k]] >= 1, "pg_sfs_tables: dims must be >= 1");
+            sz *= (long long)dims[group_pops[k]];
+            PG_CHECK(sz <= (1ll << 28), "pg_sfs_tables: spectrum %d is too large for a dense histogram", g);
+        }
+        cells += sz;
+        PG_CHECK(cells <= (1ll << 28), "pg_sfs_tables: the spectra need more than 2^28 cells");
+    }
+    if (n_counted) *n_counted = 0;
+    const int n_gp = group_off[n_groups];
+    PG_TRY(ctx->pairs.ensure((size_t)cells * 16 + 64));
+    unsigned long long* d_hist = (unsigned long long*)ctx->pairs.p;
+    long long* d_first = (long long*)(d_hist + cells);
+    PG_CUDA(cudaMemsetAsync(d_hist, 0, (size_t)cells * 8, ctx->stream));
+    PG_CUDA(cudaMemsetAsync(d_first, 0x7f, (size_t)cells * 8, ctx->stream));
+    PG_TRY(ctx->misc2.ensure((size_t)(n_groups + 1) * 4 + (size_t)n_gp * 4 + (size_t)n_groups * 8 + 128));
+    uint8_t* tb = (uint8_t*)ctx->misc2.p;
+    size_t o = 0;
+    int32_t* d_goff = nullptr;
+    int32_t* d_gpops = nullptr;
+    long long* d_hoff = nullptr;
+    PG_TRY(push(ctx, tb, o, group_off, (size_t)n_groups + 1, &d_goff));
+    PG_TRY(push(ctx, tb, o, group_pops, (size_t)n_gp, &d_gpops));
+    PG_TRY(push(ctx, tb, o, hist_off.data(), (size_t)n_groups, &d_hoff));
+    PG_TRY(ctx->out_i.ensure(64));
+    unsigned long long* d_cnt = (unsigned long long*)ctx->out_i.p;
+    PG_CUDA(cudaMemsetAsync(d_cnt, 0, 8, ctx->stream));
+    uint8_t* d_mask = nullptr;
+    if (site_mask && n > 0) {
+        PG_TRY(ctx->misc3.ensure((size_t)n + 64));
+        d_mask = (uint8_t*)ctx->misc3.p;
+        PG_CUDA(cudaMemcpyAsync(d_mask, site_mask, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    PG_CUDA(cudaStreamSynchronize(ctx->stream));
+    const size_t row_bytes = kind == 0 ? (size_t)P * 8 : (size_t)P * 4;
+    const int64_t slab = std::max<int64_t>(1, std::min<int64_t>(std::max<int64_t>(n, 1), (int64_t)(((size_t)256 << 20) / row_bytes)));
+    PG_TRY(ctx->misc.ensure((size_t)slab * row_bytes + 64));
+    for (int64_t s0 = 0; s0 < n; s0 += slab) {
+        const int64_t cnt = std::min(slab, n - s0);
+        PG_CUDA(cudaMemcpyAsync(ctx->misc.p, (const uint8_t*)table + (size_t)s0 * row_bytes, (size_t)cnt * row_bytes,
+                                cudaMemcpyHostToDevice, ctx->stream));
+        SfsParams sp;
+        memset(&sp, 0, sizeof(sp));
+        sp.counts = kind == 0 ? (const uint16_t*)ctx->misc.p : nullptr;
+        sp.targets = kind == 1 ? (const int32_t*)ctx->misc.p : nullptr;
+        sp.n = cnt;
+        sp.site0 = s0;
+        sp.P = P;
+        sp.n_in = n_in;
+        sp.outgroup = outgroup;
+        for (int X = 0; X < P; ++X) sp.dims[X] = dims[X];
+        sp.require_complete = 0;
+        sp.mask = d_mask;
+        sp.n_groups = n_groups;
+        sp.group_off = d_goff;
+        sp.group_pops = d_gpops;
+        sp.hist_off = d_hoff;
+        sp.hist = d_hist;
+        sp.first = d_first;
+        sp.n_counted = d_cnt;
+        const int ti = pg_time_begin(ctx, "k1_sfs");
+        k1_sfs<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>(sp);
+        pg_time_end(ctx, ti);
+        PG_CUDA(cudaGetLastError());
+        PG_CUDA(cudaStreamSynchronize(ctx->stream));           // the staging buffer is reused by the next slab
     }
     unsigned long long h_cnt = 0;
     PG_CUDA(cudaMemcpyAsync(hist, d_hist, (size_t)cells * 8, cudaMemcpyDeviceToHost, ctx->stream));

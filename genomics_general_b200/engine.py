@@ -308,6 +308,35 @@ class Engine:
         return ([hist[offs[k]:offs[k + 1]].reshape(shapes[k]) for k in range(len(groups))],
                 [first[offs[k]:offs[k + 1]].reshape(shapes[k]) for k in range(len(groups))], int(n.value))
 
+    def sfs_tables(self, kind: str, table, n_in: int, groups, outgroup: int = -1, site_mask=None):
+        """sfs.py on count tables: kind "base" = uint16 [n,P,4] base counts per population, "target" = int32 [n,P] counts of
+        the target allele.  Returns (dense spectra, first-site arrays, sites counted) like sfs()."""
+        if kind == "base":
+            table = np.ascontiguousarray(table, dtype=np.uint16)
+            n, P = table.shape[0], table.shape[1]
+            dims = (table.sum(axis=2, dtype=np.int64).max(axis=0) + 1 if n else np.ones(P, np.int64)).astype(np.int32)
+        else:
+            table = np.ascontiguousarray(table, dtype=np.int32)
+            n, P = table.shape
+            dims = (table.max(axis=0) + 1 if n else np.ones(P, np.int64)).astype(np.int32)
+            assert n == 0 or table.min() >= 0
+        goff = np.zeros(len(groups) + 1, dtype=np.int32)
+        for k, grp in enumerate(groups):
+            goff[k + 1] = goff[k] + len(grp)
+        gp = np.array([x for grp in groups for x in grp], dtype=np.int32)
+        shapes = [tuple(int(dims[x]) for x in grp) for grp in groups]
+        cells = [int(np.prod(sh)) for sh in shapes]
+        hist = np.zeros(sum(cells), dtype=np.int64)
+        first = np.zeros(sum(cells), dtype=np.int64)
+        mask = None if site_mask is None else np.ascontiguousarray(site_mask, dtype=np.uint8)
+        cnt = C.c_int64(0)
+        check(self._lib.pg_sfs_tables(self._ctx, 0 if kind == "base" else 1, _ptr(table), int(n), int(P), _ptr(dims), int(n_in),
+                                      int(outgroup), len(groups), _ptr(goff), _ptr(gp), _ptr(mask), _ptr(hist), _ptr(first),
+                                      C.byref(cnt)), "pg_sfs_tables")
+        offs = np.concatenate([[0], np.cumsum(cells)])
+        return ([hist[offs[k]:offs[k + 1]].reshape(shapes[k]) for k in range(len(groups))],
+                [first[offs[k]:offs[k + 1]].reshape(shapes[k]) for k in range(len(groups))], int(cnt.value))
+
     def pairdist(self, hap_ind, n_ind: int, include_same_with_same: bool = False, min_sites: int = 0):
         """-> dict(dist [W,n_ind,n_ind], sites [W], pos_sum [W]).  min_sites > 0 masks haplotype pairs with fewer
         jointly non-missing sites (what an earlier groupDistStats does to the reference's cached matrix)."""

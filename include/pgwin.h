@@ -127,6 +127,14 @@ int pg_site_target_freqs(pg_ctx* ctx, int64_t site0, int64_t n, int32_t target, 
 int pg_sfs(pg_ctx* ctx, int32_t n_in, int32_t outgroup, int32_t n_groups, const int32_t* group_off,
            const int32_t* group_pops, const uint8_t* site_mask, int64_t* hist, int64_t* first, int64_t* n_counted);
 
+/* The same spectra from TABLES of counts on the host (sfs.py --inputType baseCounts | targetCounts, sfs.py:456-474):
+ * kind 0: table = uint16 [n x P x 4] base counts per population (the rows freq.py writes); kind 1: int32 [n x P] counts of
+ * the target allele (sfs.py's default input, e.g. freq.py --target derived --asCounts).  No completeness test.
+ * dims[X] = radix of population X in the dense histograms (its largest count + 1). */
+int pg_sfs_tables(pg_ctx* ctx, int32_t kind, const void* table, int64_t n, int32_t P, const int32_t* dims, int32_t n_in,
+                  int32_t outgroup, int32_t n_groups, const int32_t* group_off, const int32_t* group_pops,
+                  const uint8_t* site_mask, int64_t* hist, int64_t* first, int64_t* n_counted);
+
 /* Replaces Alignment.indPairDists (genomics.py:934-954) as used by distMat.py:42-45 and popgenWindows.py:54-57.
  * hap_ind[h] = individual index in [0,n_ind) or -1; dist [W x n_ind x n_ind]; n_sites/pos_sum [W] (may be NULL).
  * min_sites > 0: haplotype pairs with n_ij < min_sites are nan — the state of the reference's cached matrix when

@@ -534,19 +534,17 @@ def four_pop(g, hap_pop, P1, P2, P3, P4, min_data, polarize=False, fixed=False):
 # ----------------------------------------------------------------------------------------
 # sfs.py, --inputType genotypes without subsampling  (sfs.py:430-470, 68-92, 94-125)
 # ----------------------------------------------------------------------------------------
-def sfs_target_counts(g, hap_pop, n_in, outgroup=-1):
-    """Per-site target-allele counts of the in-group populations: (counts int64 [L, n_in], used bool [L]).
-    A site is used iff every in-group haplotype is called (449) and getTargetCounts (68-92) returns a value."""
-    hap_pop = np.asarray(hap_pop)
-    P = int(hap_pop.max()) + 1
-    c = site_counts(g, hap_pop, P)
-    N = np.array([(hap_pop == x).sum() for x in range(P)])
+def sfs_target_counts_from_counts(c, n_in, outgroup=-1, N=None):
+    """Per-site target-allele counts from base counts c int [L, P, 4]: (counts int64 [L, n_in], used bool [L]).
+    N (haplotypes per population) switches on the completeness test of genotype input (sfs.py:449); base-count input
+    (sfs.py:456-470) has none.  getTargetCounts: sfs.py:68-92."""
+    c = np.asarray(c, dtype=np.int64)
     L = c.shape[0]
     out = np.zeros((L, n_in), dtype=np.int64)
     used = np.zeros(L, dtype=bool)
     for s in range(L):
         cin = c[s, :n_in]
-        if not np.all(cin.sum(axis=1) == N[:n_in]):
+        if N is not None and not np.all(cin.sum(axis=1) == np.asarray(N)[:n_in]):
             continue
         tot = cin.sum(axis=0)
         alleles = tot > 0
@@ -569,12 +567,18 @@ def sfs_target_counts(g, hap_pop, n_in, outgroup=-1):
     return out, used
 
 
-def sfs(g, hap_pop, n_in, groups, outgroup=-1, site_mask=None):
-    """For each group of populations: the spectrum as an insertion-ordered list of (key tuple, count) in the order the
-    reference's nested SparseFS dicts are written (asChains, 117-125): first appearance at each nesting level."""
-    tc, used = sfs_target_counts(g, hap_pop, n_in, outgroup)
-    if site_mask is not None:
-        used = used & np.asarray(site_mask, dtype=bool)
+def sfs_target_counts(g, hap_pop, n_in, outgroup=-1):
+    """The same from genotypes: a site is used iff every in-group haplotype is called (449) and getTargetCounts returns
+    a value."""
+    hap_pop = np.asarray(hap_pop)
+    P = int(hap_pop.max()) + 1
+    c = site_counts(g, hap_pop, P)
+    N = np.array([(hap_pop == x).sum() for x in range(P)])
+    return sfs_target_counts_from_counts(c, n_in, outgroup, N)
+
+
+def sfs_chains(tc, used, groups):
+    """insertion-ordered (key tuple, count) lists, one per group, from per-site target counts (SparseFS.add / asChains)"""
     out = []
     for grp in groups:
         nested = {}
@@ -594,7 +598,16 @@ def sfs(g, hap_pop, n_in, groups, outgroup=-1, site_mask=None):
                     chains.append((prefix + (k,), v))
         walk(nested, ())
         out.append(chains)
-    return out, int(used.sum())
+    return out
+
+
+def sfs(g, hap_pop, n_in, groups, outgroup=-1, site_mask=None):
+    """For each group of populations: the spectrum as an insertion-ordered list of (key tuple, count) in the order the
+    reference's nested SparseFS dicts are written (asChains, 117-125): first appearance at each nesting level."""
+    tc, used = sfs_target_counts(g, hap_pop, n_in, outgroup)
+    if site_mask is not None:
+        used = used & np.asarray(site_mask, dtype=bool)
+    return sfs_chains(tc, used, groups), int(used.sum())
 
 
 # ----------------------------------------------------------------------------------------

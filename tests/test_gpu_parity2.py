@@ -427,7 +427,7 @@ def test_seq_nonnan_bit_exact(eng):
 # ------------------------------------------------------------------------------------------------
 def _sfs_keys():
     d = CLI2["four_pops"]
-    return [k for k in d if k.startswith("sfs_") and k + "_args" in d]
+    return [k for k in d if k.startswith("sfs_") and not k.startswith(("sfs_base", "sfs_target")) and k + "_args" in d]
 
 
 @pytest.mark.parametrize("key", _sfs_keys())
@@ -610,3 +610,43 @@ def test_freq_target_minor_cli_rows_without_ties(inputs2):
     same = [a == b for a, b in zip(ours[1:], ref[1:])]
     assert all(s or t for s, t in zip(same, tied)), "a row without a tie differs"
     assert tied.sum() > 0 and sum(same) >= c["S"] - int(tied.sum())
+
+
+
+def _sfs_table_keys():
+    d = CLI2["four_pops"]
+    return [k for k in d if k.startswith(("sfs_base", "sfs_target")) and k + "_args" in d]
+
+
+@pytest.mark.parametrize("key", _sfs_table_keys())
+def test_sfs_from_count_tables_matches_the_reference_pipeline(eng, key, tmp_path, capsys):
+    """freq.py -> sfs.py, both ours, against the same pipeline of the reference scripts (byte-identical spectra)."""
+    from genomics_general_b200 import synth
+    from genomics_general_b200.cli import freq as freq_cli, sfs as sfs_cli
+    from test_oracle_golden2 import sfs_inputs, sfs_table_plan, sfs_tables
+    d = CLI2["four_pops"]
+    c = d["sfs_cfg"]
+    spec, g, scaf = sfs_inputs()
+    base, target, _ = sfs_tables()
+    kind, order, n_in, og, groups, inpops, excl = sfs_table_plan(key)
+    cols = [int(p[3:]) for p in order]
+    mask = ~np.isin(scaf, excl) if excl else None
+    gi = [tuple(inpops.index(p) for p in grp) for grp in groups]
+    table = base[:, cols, :] if kind == "base" else target[:, cols]
+    hists, firsts, _ = eng.sfs_tables(kind, table, n_in, gi, outgroup=og, site_mask=mask)
+    text = "".join("\n".join("\t".join(str(x) for x in row) for row in sfs_cli.ordered_chains(h, f)) + "\n"
+                   for h, f in zip(hists, firsts))
+    assert text == d[key]
+    # the command lines: our freq.py writes the table, our sfs.py reads it
+    path = str(tmp_path / "sfs.geno")
+    synth.write_geno(path, g, synth.synth_positions(c["S"], seed=c["seed"]), ["chr%d" % (k + 1) for k in scaf], spec.sample_names())
+    pops = str(tmp_path / "sfs.pops")
+    with open(pops, "wt") as f:
+        for i, nm in enumerate(spec.sample_names()):
+            f.write("%s pop%d\n" % (nm, i // c["spp"]))
+    tab = str(tmp_path / "table.tsv")
+    fa = ["-g", path, "-o", tab, "-f", "phased", "-t", "1", "--popsFile", pops, "-p", "pop0", "-p", "pop1", "-p", "pop2", "-p", "pop3"]
+    freq_cli.main(fa if kind == "base" else fa + ["--target", "derived", "--asCounts", "--keepNanLines"])
+    capsys.readouterr()
+    sfs_cli.main(["-i", tab, "--pipe"] + d[key + "_args"])
+    assert capsys.readouterr().out == d[key]

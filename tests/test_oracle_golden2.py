@@ -145,7 +145,10 @@ def sfs_plan(extra):
     return inpops, outgroup, groups, keep
 
 
-@pytest.mark.parametrize("key", [k for k in CLI2 if k.startswith("sfs_") and k + "_args" in CLI2])
+GENO_SFS_KEYS = [k for k in CLI2 if k.startswith("sfs_") and not k.startswith(("sfs_base", "sfs_target")) and k + "_args" in CLI2]
+
+
+@pytest.mark.parametrize("key", GENO_SFS_KEYS)
 def test_sfs_oracle_matches_reference_output(key):
     spec, g, scaf = sfs_inputs()
     extra = CLI2[key + "_args"]
@@ -162,7 +165,7 @@ def test_sfs_oracle_matches_reference_output(key):
     assert text == CLI2[key]
 
 
-@pytest.mark.parametrize("key", [k for k in CLI2 if k.startswith("sfs_") and k + "_args" in CLI2])
+@pytest.mark.parametrize("key", GENO_SFS_KEYS)
 def test_sfs_row_order_from_dense_histograms(key):
     """Host logic of the sfs command line (no GPU): dense spectrum + first-site array -> the reference's sparse rows in
     nested-dict insertion order (cli/sfs.py::ordered_chains), against the reference script's own output."""
@@ -189,4 +192,66 @@ def test_sfs_row_order_from_dense_histograms(key):
             if first[cell] < 0:
                 first[cell] = s
         text += "\n".join("\t".join(str(x) for x in row) for row in ordered_chains(hist, first)) + "\n"
+    assert text == CLI2[key]
+
+
+# ------------------------------------------------------------------------------------------------
+# sfs.py on count tables (freq.py -> sfs.py): oracle vs the reference pipeline's output
+# ------------------------------------------------------------------------------------------------
+def sfs_table_plan(key):
+    """(table kind, population columns in engine order, n_in, outgroup index, groups, scaffold filter) of one golden run"""
+    import itertools
+    extra = CLI2[key + "_args"]
+    kind = CLI2[key + "_input"]
+    names = ["pop0", "pop1", "pop2", "pop3"]
+    pops = [extra[i + 1] for i, t in enumerate(extra) if t == "-p"]
+    fsp = []
+    cur = None
+    for tok in extra:
+        if tok == "--FSpops":
+            cur = []
+            fsp.append(cur)
+        elif tok.startswith("-"):
+            cur = None
+        elif cur is not None:
+            cur.append(tok)
+    for p in [x for g in fsp for x in g]:
+        if p not in pops:
+            pops.append(p)
+    if not pops:
+        pops = list(names)
+    outgroup = pops[-1] if (kind == "base" and "--polarized" in extra) else None
+    inpops = [p for p in pops if p != outgroup]
+    if fsp:
+        groups = fsp
+    else:
+        groups = [[p] for p in inpops]
+        for flag, k in (("--doPairs", 2), ("--doTrios", 3)):
+            if flag in extra:
+                groups += [list(c) for c in itertools.combinations(inpops, k)]
+    excl = [int(extra[i + 1][3:]) - 1 for i, t in enumerate(extra) if t == "--exclude"]
+    return kind, inpops + ([outgroup] if outgroup else []), len(inpops), (len(inpops) if outgroup else -1), groups, inpops, excl
+
+
+def sfs_tables():
+    """the two tables the reference's freq.py writes for the sfs input file: base counts [S,4,4] and derived-allele counts"""
+    spec, g, scaf = sfs_inputs()
+    hp = spec.hap_pop()
+    base = do.site_counts(g, hp, 4)
+    target, _ = do.target_freqs(g, hp, 4, "derived", as_counts=True)
+    return base, target.astype(np.int64), scaf
+
+
+@pytest.mark.parametrize("key", [k for k in CLI2 if k.startswith(("sfs_base", "sfs_target")) and k + "_args" in CLI2])
+def test_sfs_tables_oracle_matches_reference_pipeline(key):
+    base, target, scaf = sfs_tables()
+    kind, order, n_in, og, groups, inpops, excl = sfs_table_plan(key)
+    cols = [int(p[3:]) for p in order]
+    used_mask = ~np.isin(scaf, excl) if excl else np.ones(len(scaf), dtype=bool)
+    if kind == "base":
+        tc, used = do.sfs_target_counts_from_counts(base[:, cols, :], n_in, og)
+    else:
+        tc, used = target[:, cols], np.ones(len(scaf), dtype=bool)
+    chains = do.sfs_chains(tc, used & used_mask, [tuple(inpops.index(p) for p in grp) for grp in groups])
+    text = "".join("\n".join("\t".join(str(x) for x in list(k) + [v]) for k, v in ch) + "\n" for ch in chains)
     assert text == CLI2[key]
