@@ -78,7 +78,14 @@ def ordered_chains(hist, first):
 
 
 def write_spectra(args, FSpops, hists, firsts):
-    write_spectra(args, FSpops, hists, firsts)
+    """one file per spectrum (<pref><pops joined by _><suff>, sfs.py:495-497) or everything to stdout (--pipe, 491-493)"""
+    for i, grp in enumerate(FSpops):
+        text = "\n".join("\t".join(str(x) for x in row) for row in ordered_chains(hists[i], firsts[i])) + "\n"
+        if args.pipe:
+            sys.stdout.write(text)
+        else:
+            with open(args.pref + "_".join(grp) + args.suff, "w") as out:
+                out.write(text)
 
 
 def main_tables(args, include, exclude):

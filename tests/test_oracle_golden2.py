@@ -255,3 +255,80 @@ def test_sfs_tables_oracle_matches_reference_pipeline(key):
     chains = do.sfs_chains(tc, used & used_mask, [tuple(inpops.index(p) for p in grp) for grp in groups])
     text = "".join("\n".join("\t".join(str(x) for x in list(k) + [v]) for k, v in ch) + "\n" for ch in chains)
     assert text == CLI2[key]
+
+
+def test_sfs_write_spectra_files_and_pipe(tmp_path, capsys):
+    """host logic of the sfs command line: file naming (<pref><pops>_<...><suff>) and --pipe"""
+    import argparse
+    from genomics_general_b200.cli import sfs as sfs_cli
+    hist = np.zeros((3, 4), dtype=np.int64)
+    first = np.full((3, 4), -1, dtype=np.int64)
+    for k, (cell, n) in enumerate([((2, 1), 5), ((0, 3), 1), ((2, 0), 7)]):
+        hist[cell] = n
+        first[cell] = 10 - k                      # the later cells were seen first
+    args = argparse.Namespace(pipe=False, pref=str(tmp_path / "x_"), suff=".sfs")
+    sfs_cli.write_spectra(args, [["a", "b"]], [hist], [first])
+    assert open(str(tmp_path / "x_a_b.sfs")).read() == "2\t0\t7\n2\t1\t5\n0\t3\t1\n"
+    args.pipe = True
+    sfs_cli.write_spectra(args, [["a", "b"]], [hist], [first])
+    assert capsys.readouterr().out == "2\t0\t7\n2\t1\t5\n0\t3\t1\n"
+
+
+class _FakeEngine:
+    """Stands in for the GPU engine in the CPU test below: same sfs_tables contract, histogram built with the oracle."""
+
+    def __init__(self, device=0):
+        pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        pass
+
+    def sfs_tables(self, kind, table, n_in, groups, outgroup=-1, site_mask=None):
+        table = np.asarray(table)
+        n = table.shape[0]
+        if kind == "base":
+            tc, used = do.sfs_target_counts_from_counts(table, n_in, outgroup)
+            dims = table.sum(axis=2).max(axis=0) + 1
+        else:
+            tc, used = table, np.ones(n, dtype=bool)
+            dims = table.max(axis=0) + 1
+        if site_mask is not None:
+            used = used & np.asarray(site_mask, dtype=bool)
+        hists, firsts = [], []
+        for grp in groups:
+            shape = tuple(int(dims[x]) for x in grp)
+            h = np.zeros(shape, dtype=np.int64)
+            f = np.full(shape, -1, dtype=np.int64)
+            for s in np.where(used)[0]:
+                cell = tuple(int(tc[s, x]) for x in grp)
+                h[cell] += 1
+                if f[cell] < 0:
+                    f[cell] = s
+            hists.append(h)
+            firsts.append(f)
+        return hists, firsts, int(used.sum())
+
+
+@pytest.mark.parametrize("key", [k for k in CLI2 if k.startswith(("sfs_base", "sfs_target")) and k + "_args" in CLI2])
+def test_sfs_table_command_line_host_logic(key, tmp_path, capsys, monkeypatch):
+    """cli/sfs.py on count tables with the engine replaced by the oracle: table parsing, population / outgroup / FSpops
+    plumbing, --exclude and the output order against the reference pipeline's text (the GPU tests run the real engine)."""
+    from genomics_general_b200.cli import sfs as sfs_cli
+    monkeypatch.setattr(sfs_cli, "Engine", _FakeEngine)
+    base, target, scaf = sfs_tables()
+    pos = np.arange(1, len(scaf) + 1)
+    tab = str(tmp_path / "t.tsv")
+    with open(tab, "wt") as f:
+        f.write("scaffold\tposition\tpop0\tpop1\tpop2\tpop3\n")
+        for s in range(len(scaf)):
+            if CLI2[key + "_input"] == "base":
+                cols = [",".join(str(v) for v in base[s, x]) for x in range(4)]
+            else:
+                cols = [str(v) for v in target[s]]
+            f.write("chr%d\t%d\t%s\n" % (scaf[s] + 1, pos[s], "\t".join(cols)))
+    capsys.readouterr()
+    sfs_cli.main(["-i", tab, "--pipe"] + CLI2[key + "_args"])
+    assert capsys.readouterr().out == CLI2[key]
