@@ -382,120 +382,123 @@ def main():
 
     # ---------------- more legs (single-GPU runs only): the other K1 modes, the config-5 row shape, text ingest ---------
     if world == 1:
-        def k1_leg(fn, name, S_, H_, reps=5):
-            for _ in range(2):
-                fn()
-            ms = []
-            for _ in range(reps):
-                fn()
-                ms.append(eng.last_timings()[name]["ms"])
-            m = float(np.mean(ms))
-            return {"kernel_ms": m, "sites_per_s": S_ / (m * 1e-3), "GBps": S_ * (H_ + 4) / (m * 1e-3) / 1e9}
-        # config 3 (ABBABABAwindows) and fourPopWindows on the same resident matrix (2 % missing genotypes)
-        variants["C3 ABBABABAwindows P1/P2/P3/O x 50 (k1_site_pass<ABBA>)"] = k1_leg(
-            lambda: eng.abbababa(0, 1, 2, 3, 0.5), "k1_abba", S, H)
-        variants["fourPopWindows (k1_site_pass<FOURPOP>)"] = k1_leg(lambda: eng.fourpop(0, 1, 2, 3, 0.5), "k1_fourpop", S, H)
-        # config 5 row shape: 8 populations x 100 diploid samples (1600 haplotypes); one GPU's share is 12.5 M sites
-        S5 = min(env_int("PG_BENCH_C5_SITES", 5_000_000), S)
-        spec5 = synth.SynthSpec(8, 100, PLOIDY, seed=SEED + 5, miss=0.0)
-        eng.synth_fill(spec5, S5)
-        eng.set_pops(spec5.hap_pop(), 8)
-        lo5 = np.arange(0, S5, 5000, dtype=np.int64)
-        eng.set_windows(lo5, np.minimum(lo5 + 5000, S5))                      # --windType sites -w 5000
-        variants["C5 shape popgenWindows 8 pops x 100 (k1_site_pass<POPGEN,8>)"] = k1_leg(
-            lambda: eng.popgen(MIN_SITES, MIN_DATA), "k1_popgen", S5, 1600)
-        n5 = min(S5, 2_000_000)
-        variants["C5 shape freq.py counts 8 pops x 100 (k1_site_pass<COUNTS,8>)"] = k1_leg(
-            lambda: eng.site_counts(0, n5), "k1_counts", n5, 1600 + 64, reps=3)
-        # .geno TEXT -> rows, the path of the drop-in command line: native tokenizer (host threads) + upload + statistics
-        from genomics_general_b200 import geno_io
-        St = env_int("PG_BENCH_TEXT_SITES", 500_000)
-        spec_t = synth.SynthSpec(N_POPS, SAMPLES_PER_POP, PLOIDY, seed=SEED + 9, miss=0.0)
-        gt = synth.synth_genotypes(spec_t, 0, St)
-        pos_t = synth.synth_positions(St, seed=SEED + 9)
-        nS = N_POPS * SAMPLES_PER_POP
-        width = 5 + 9 + nS * 4 + 1
-        txt = np.empty((St, width), dtype=np.uint8)
-        txt[:, :5] = np.frombuffer(b"chr1\t", dtype=np.uint8)
-        digits = (pos_t[:, None].astype(np.int64) // 10 ** np.arange(8, -1, -1)[None, :]) % 10
-        txt[:, 5:14] = digits + 48
-        lut = np.frombuffer(b"ACGTN", dtype=np.uint8)
-        ch = lut[np.where(gt < 0, 4, gt)]
-        body_v = txt[:, 14:14 + nS * 4].reshape(St, nS, 4)
-        body_v[:, :, 0] = 9                                                    # tab
-        body_v[:, :, 1] = ch[:, 0::2]
-        body_v[:, :, 2] = ord("|")
-        body_v[:, :, 3] = ch[:, 1::2]
-        txt[:, -1] = 10
-        text = ("#CHROM\tPOS\t" + "\t".join(spec_t.sample_names()) + "\n").encode() + txt.tobytes()
-        del txt, ch, digits
-        import io as _io
-        res_t = {}
-        tpath = os.path.join(os.environ.get("TMPDIR", "/tmp"), "pg_bench_%d.geno" % os.getpid())
-        with open(tpath, "wb") as f:
-            f.write(text)
-        for how in ("host tokenizer", "device tokenizer", "device tokenizer, file path"):
-            t_best = None
-            for _ in range(3):
-                t0 = time.perf_counter()
-                if how == "host tokenizer":
-                    gd = geno_io.parse_geno(_io.BytesIO(text), geno_format="phased")
-                    t1 = time.perf_counter()
-                    eng.upload(gd.geno, gd.pos)
-                elif how == "device tokenizer":
-                    gd = geno_io.ingest_geno(eng, text, geno_format="phased")
-                    t1 = time.perf_counter()
-                else:
-                    gd = geno_io.ingest_geno(eng, tpath, geno_format="phased")
-                    t1 = time.perf_counter()
-                    res_t.setdefault("device tokenizer stages (ms)", {k: round(v["ms"], 3) for k, v in eng.last_timings().items()})
-                eng.set_pops(spec_t.hap_pop(), P)
-                ws_t = windows.sliding_coord_windows(gd.scaf_ids, gd.scaf_names, gd.pos, WIND_SIZE)
-                eng.set_windows(*ws_t.ranges())
-                eng.popgen(MIN_SITES, MIN_DATA)
-                t2 = time.perf_counter()
-                if t_best is None or t2 - t0 < t_best[0]:
-                    t_best = (t2 - t0, t1 - t0)
-            res_t[how] = {"sites_per_s": St / t_best[0], "tokenize_s": t_best[1], "total_s": t_best[0],
-                          "text_GBps": len(text) / t_best[1] / 1e9}
-        # the complete drop-in command lines on that file (argument parsing -> text ingest -> windows -> statistics -> rows)
-        from genomics_general_b200.cli import freq as freq_cli, popgenWindows as pgw_cli
-        ppath, opath = tpath + ".pops", tpath + ".out"
-        with open(ppath, "wt") as f:
-            for i, nm in enumerate(spec_t.sample_names()):
-                f.write("%s pop%d\n" % (nm, i // SAMPLES_PER_POP))
-        popargs = []
-        for k in range(N_POPS):
-            popargs += ["-p", "pop%d" % k]
-        err_, sys.stderr = sys.stderr, open(os.devnull, "w")
-        try:
-            cli_t = {}
-            for name, fn, argv in (
-                    ("popgenWindows.py -w 50000 -m 100 -f phased", pgw_cli.main,
-                     ["-w", str(WIND_SIZE), "-m", str(MIN_SITES), "-g", tpath, "-o", opath, "-f", "phased", "--popsFile", ppath] + popargs),
-                    ("freq.py -f phased (one row of counts per site)", freq_cli.main,
-                     ["-g", tpath, "-o", opath, "-f", "phased", "--popsFile", ppath] + popargs)):
-                best = None
+        try:        # a failing extra leg must never cost the headline line
+            def k1_leg(fn, name, S_, H_, reps=5):
                 for _ in range(2):
+                    fn()
+                ms = []
+                for _ in range(reps):
+                    fn()
+                    ms.append(eng.last_timings()[name]["ms"])
+                m = float(np.mean(ms))
+                return {"kernel_ms": m, "sites_per_s": S_ / (m * 1e-3), "GBps": S_ * (H_ + 4) / (m * 1e-3) / 1e9}
+            # config 3 (ABBABABAwindows) and fourPopWindows on the same resident matrix (2 % missing genotypes)
+            variants["C3 ABBABABAwindows P1/P2/P3/O x 50 (k1_site_pass<ABBA>)"] = k1_leg(
+                lambda: eng.abbababa(0, 1, 2, 3, 0.5), "k1_abba", S, H)
+            variants["fourPopWindows (k1_site_pass<FOURPOP>)"] = k1_leg(lambda: eng.fourpop(0, 1, 2, 3, 0.5), "k1_fourpop", S, H)
+            # config 5 row shape: 8 populations x 100 diploid samples (1600 haplotypes); one GPU's share is 12.5 M sites
+            S5 = min(env_int("PG_BENCH_C5_SITES", 5_000_000), S)
+            spec5 = synth.SynthSpec(8, 100, PLOIDY, seed=SEED + 5, miss=0.0)
+            eng.synth_fill(spec5, S5)
+            eng.set_pops(spec5.hap_pop(), 8)
+            lo5 = np.arange(0, S5, 5000, dtype=np.int64)
+            eng.set_windows(lo5, np.minimum(lo5 + 5000, S5))                      # --windType sites -w 5000
+            variants["C5 shape popgenWindows 8 pops x 100 (k1_site_pass<POPGEN,8>)"] = k1_leg(
+                lambda: eng.popgen(MIN_SITES, MIN_DATA), "k1_popgen", S5, 1600)
+            n5 = min(S5, 2_000_000)
+            variants["C5 shape freq.py counts 8 pops x 100 (k1_site_pass<COUNTS,8>)"] = k1_leg(
+                lambda: eng.site_counts(0, n5), "k1_counts", n5, 1600 + 64, reps=3)
+            # .geno TEXT -> rows, the path of the drop-in command line: native tokenizer (host threads) + upload + statistics
+            from genomics_general_b200 import geno_io
+            St = env_int("PG_BENCH_TEXT_SITES", 500_000)
+            spec_t = synth.SynthSpec(N_POPS, SAMPLES_PER_POP, PLOIDY, seed=SEED + 9, miss=0.0)
+            gt = synth.synth_genotypes(spec_t, 0, St)
+            pos_t = synth.synth_positions(St, seed=SEED + 9)
+            nS = N_POPS * SAMPLES_PER_POP
+            width = 5 + 9 + nS * 4 + 1
+            txt = np.empty((St, width), dtype=np.uint8)
+            txt[:, :5] = np.frombuffer(b"chr1\t", dtype=np.uint8)
+            digits = (pos_t[:, None].astype(np.int64) // 10 ** np.arange(8, -1, -1)[None, :]) % 10
+            txt[:, 5:14] = digits + 48
+            lut = np.frombuffer(b"ACGTN", dtype=np.uint8)
+            ch = lut[np.where(gt < 0, 4, gt)]
+            body_v = txt[:, 14:14 + nS * 4].reshape(St, nS, 4)
+            body_v[:, :, 0] = 9                                                    # tab
+            body_v[:, :, 1] = ch[:, 0::2]
+            body_v[:, :, 2] = ord("|")
+            body_v[:, :, 3] = ch[:, 1::2]
+            txt[:, -1] = 10
+            text = ("#CHROM\tPOS\t" + "\t".join(spec_t.sample_names()) + "\n").encode() + txt.tobytes()
+            del txt, ch, digits
+            import io as _io
+            res_t = {}
+            tpath = os.path.join(os.environ.get("TMPDIR", "/tmp"), "pg_bench_%d.geno" % os.getpid())
+            with open(tpath, "wb") as f:
+                f.write(text)
+            for how in ("host tokenizer", "device tokenizer", "device tokenizer, file path"):
+                t_best = None
+                for _ in range(3):
                     t0 = time.perf_counter()
-                    fn(argv)
-                    dt_ = time.perf_counter() - t0
-                    best = dt_ if best is None else min(best, dt_)
-                cli_t[name] = {"wall_s": best, "sites_per_s": St / best, "output_bytes": os.path.getsize(opath)}
-        finally:
-            sys.stderr.close()
-            sys.stderr = err_
-        res_t["whole command line, in process"] = cli_t
-        for pth in (tpath, ppath, opath):
-            os.remove(pth)
-        g_back, _ = eng.download(0, min(St, 100000))
-        assert np.array_equal(g_back, gt[:len(g_back)])
-        variants["from .geno text (C2 shape, %d sites, %.0f MB)" % (St, len(text) / 1e6)] = dict(
-            res_t, note="text -> int8 matrix -> statistics -> rows, the path of the drop-in command lines; 'device tokenizer' "
-                        "copies the file's bytes to the GPU and tokenises there (pg_ingest_text), 'host tokenizer' is the "
-                        "multi-threaded C++ one + H2D of the matrix; the reference's parser reads ~17 k lines/s at this "
-                        "width (SURVEY.md section 6)")
-        del text, gt
+                    if how == "host tokenizer":
+                        gd = geno_io.parse_geno(_io.BytesIO(text), geno_format="phased")
+                        t1 = time.perf_counter()
+                        eng.upload(gd.geno, gd.pos)
+                    elif how == "device tokenizer":
+                        gd = geno_io.ingest_geno(eng, text, geno_format="phased")
+                        t1 = time.perf_counter()
+                    else:
+                        gd = geno_io.ingest_geno(eng, tpath, geno_format="phased")
+                        t1 = time.perf_counter()
+                        res_t.setdefault("device tokenizer stages (ms)", {k: round(v["ms"], 3) for k, v in eng.last_timings().items()})
+                    eng.set_pops(spec_t.hap_pop(), P)
+                    ws_t = windows.sliding_coord_windows(gd.scaf_ids, gd.scaf_names, gd.pos, WIND_SIZE)
+                    eng.set_windows(*ws_t.ranges())
+                    eng.popgen(MIN_SITES, MIN_DATA)
+                    t2 = time.perf_counter()
+                    if t_best is None or t2 - t0 < t_best[0]:
+                        t_best = (t2 - t0, t1 - t0)
+                res_t[how] = {"sites_per_s": St / t_best[0], "tokenize_s": t_best[1], "total_s": t_best[0],
+                              "text_GBps": len(text) / t_best[1] / 1e9}
+            # the complete drop-in command lines on that file (argument parsing -> text ingest -> windows -> statistics -> rows)
+            from genomics_general_b200.cli import freq as freq_cli, popgenWindows as pgw_cli
+            ppath, opath = tpath + ".pops", tpath + ".out"
+            with open(ppath, "wt") as f:
+                for i, nm in enumerate(spec_t.sample_names()):
+                    f.write("%s pop%d\n" % (nm, i // SAMPLES_PER_POP))
+            popargs = []
+            for k in range(N_POPS):
+                popargs += ["-p", "pop%d" % k]
+            err_, sys.stderr = sys.stderr, open(os.devnull, "w")
+            try:
+                cli_t = {}
+                for name, fn, argv in (
+                        ("popgenWindows.py -w 50000 -m 100 -f phased", pgw_cli.main,
+                         ["-w", str(WIND_SIZE), "-m", str(MIN_SITES), "-g", tpath, "-o", opath, "-f", "phased", "--popsFile", ppath] + popargs),
+                        ("freq.py -f phased (one row of counts per site)", freq_cli.main,
+                         ["-g", tpath, "-o", opath, "-f", "phased", "--popsFile", ppath] + popargs)):
+                    best = None
+                    for _ in range(2):
+                        t0 = time.perf_counter()
+                        fn(argv)
+                        dt_ = time.perf_counter() - t0
+                        best = dt_ if best is None else min(best, dt_)
+                    cli_t[name] = {"wall_s": best, "sites_per_s": St / best, "output_bytes": os.path.getsize(opath)}
+            finally:
+                sys.stderr.close()
+                sys.stderr = err_
+            res_t["whole command line, in process"] = cli_t
+            for pth in (tpath, ppath, opath):
+                os.remove(pth)
+            g_back, _ = eng.download(0, min(St, 100000))
+            assert np.array_equal(g_back, gt[:len(g_back)])
+            variants["from .geno text (C2 shape, %d sites, %.0f MB)" % (St, len(text) / 1e6)] = dict(
+                res_t, note="text -> int8 matrix -> statistics -> rows, the path of the drop-in command lines; 'device tokenizer' "
+                            "copies the file's bytes to the GPU and tokenises there (pg_ingest_text), 'host tokenizer' is the "
+                            "multi-threaded C++ one + H2D of the matrix; the reference's parser reads ~17 k lines/s at this "
+                            "width (SURVEY.md section 6)")
+            del text, gt
+        except Exception as exc:      # recorded, not raised
+            variants["extra legs failed"] = "%s: %s" % (type(exc).__name__, exc)
 
     sampler.stop()
     clocks = sampler.summary(intervals)
