@@ -525,7 +525,10 @@ def main():
         pass
     roofline = {"bound": "hbm", "kernel": "k1_site_pass<POPGEN,4>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k1_ms}
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k1_ms,
+                "note": "the kernel only READS (4.04 GB in, a few MB out); the peak is the driver's copy figure (read + write "
+                        "traffic), so a fraction slightly above 1 is a read-only stream beating a copy, not a measurement error: "
+                        "ncu reports 4.050 GB of DRAM traffic for the 4.040 GB of algorithmic bytes (profiles/k1_traffic.json)"}
 
     # ---------------- CPU baseline on a bounded sample ----------------
     cpu = None
