@@ -1272,10 +1272,10 @@ int arm_slots(pg_ctx* ctx, K1Cache& c) {
 template <int MODE, int P, int NW, bool BYTES>
 int launch_site_pass_nw(pg_ctx* ctx, const K1Launch& L, const char* name) {
     auto kern = k1_site_pass<MODE, P, NW, BYTES>;
-    static bool attr_set = false;     // per instantiation
-    if (!attr_set) {
+    static bool attr_set[64] = {};    // per instantiation and per device (the attribute is per device)
+    if (!attr_set[ctx->device & 63]) {
         PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
+        attr_set[ctx->device & 63] = true;
     }
     const int ti = pg_time_begin(ctx, name);
     kern<<<L.plan.ctas, (NW + 1) * 32, L.plan.smem_bytes, ctx->stream>>>(L.prm);
@@ -1299,10 +1299,10 @@ int k1_nw_for(int pitch) {
 template <int MODE, int P, int NW>
 int launch_site_pass_lp(pg_ctx* ctx, const K1Launch& L, const char* name) {
     auto kern = k1_site_pass_lp<MODE, P, NW>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};
+    if (!attr_set[ctx->device & 63]) {
         PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
+        attr_set[ctx->device & 63] = true;
     }
     const int ti = pg_time_begin(ctx, name);
     kern<<<L.plan.ctas, (NW + 1) * 32, L.plan.smem_bytes, ctx->stream>>>(L.prm);

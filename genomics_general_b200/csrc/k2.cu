@@ -899,11 +899,11 @@ int run_pair_batch(pg_ctx* ctx, const PlaneSet& ps, const std::vector<int64_t>& 
     pp.site_base = ps.site_base;
     pp.win_lo = d_lo;
     pp.win_hi = d_hi;
-    static bool attr = false;
-    if (!attr) {
+    static bool attr_dev[64] = {};      // per device
+    if (!attr_dev[ctx->device & 63]) {
         PG_CUDA(cudaFuncSetAttribute(k2_pair<PAIR_DIFF>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairGeom<PAIR_DIFF>::SMEM));
         PG_CUDA(cudaFuncSetAttribute(k2_pair<PAIR_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairGeom<PAIR_N>::SMEM));
-        attr = true;
+        attr_dev[ctx->device & 63] = true;
     }
     // diff over all haplotype rows
     pp.n_rows = ps.Hk;
