@@ -14,6 +14,11 @@ numerics (all citations are /root/reference/<file>:<line>):
   indPairDists ................ genomics.py:934-954  (+ distMat.py:42-45)
   siteFreqs / siteNonNan ...... genomics.py:1032-1036, 1049-1052, 592-599
   ABBABABA (+ f4,D,fd,fdM) .... genomics.py:1647-1695, 1409-1475, 1565-1569
+  sampleHet / H12stats ........ genomics.py:918-929, 1079-1098, 1239-1261 (in the cache states of popgenWindows.py:50-64)
+  groupFreqStats .............. genomics.py:1002-1028, 609-632
+  fourPop ..................... genomics.py:1585-1643, 1409-1583
+  freq.py --target ............ freq.py:62-98; genomics.py:636-668
+  sfs.py ...................... sfs.py:68-92, 94-125, 430-474
   window generators ........... genomics.py:1971-2027, 2032-2108, 2112-2171
   row prefix (start,end,mid) .. popgenWindows.py:37-39, genomics.py:1795-1797
 
@@ -21,8 +26,8 @@ PINNING: the reference has no tests or golden vectors, so this
 oracle is pinned against outputs of the *reference itself* executed in the
 build container: ``oracle/make_golden.py`` imports /root/reference/genomics.py,
 runs it on small seeded inputs and commits inputs + outputs under
-``tests/golden/``; ``tests/test_oracle_golden.py`` checks every function here
-against those fixtures.
+``tests/golden/`` (``oracle/make_golden2.py`` adds the second batch); ``tests/test_oracle_golden.py`` and
+``tests/test_oracle_golden2.py`` check every function here against those fixtures.
 
 Data model: ``g`` is int8 ``[L sites, H haplotypes]`` with A0 C1 G2 T3 and any
 negative value = missing (the reference's ``numArray`` transposed,
