@@ -107,7 +107,29 @@ def ploidy_dict(args, allInds, haploid_list):
     return d
 
 
+_STDIN = {}        # the piped input is read once: the header comes from its first line, load_geno gets the same bytes
+
+
+def stdin_bytes():
+    if "data" not in _STDIN:
+        _STDIN["data"] = geno_io.read_bytes(sys.stdin.buffer)
+    return _STDIN["data"]
+
+
+def alignment_order(indNames, ploidyDict, genoFormat="phased"):
+    """Samples in the order their haplotypes take in the reference's Alignment: genoToAlignment sorts the sequence names
+    (`ind_A`, `ind_B`, ...; the plain name for haploids) with np.argsort (genomics.py:1111-1121), e.g. s10 before s1
+    ('0' < '_').  The order only matters where ties are broken by position (H12's greedy clustering, 1239-1261)."""
+    base = 1 if genoFormat == "haplo" else 2
+    keys = [n if int((ploidyDict or {}).get(n, base) or base) == 1 else n + "_A" for n in indNames]
+    return [indNames[i] for i in np.argsort(keys)] if keys else list(indNames)
+
+
 def header_names(path):
+    """Sample names of the header line; with no path the genotypes are piped in (freq.py:228-233, sfs.py:282-287)."""
+    if path is None:
+        data = stdin_bytes()
+        return data[:data.find(b"\n") if b"\n" in data else len(data)].decode().split()[2:]
     with (gzip.open(path, "rt") if path.endswith(".gz") else open(path, "rt")) as gf:
         return gf.readline().split()[2:]
 
@@ -121,7 +143,7 @@ def open_out(path):
 def load_geno(args, samples, ploidyDict, header=None, engine=None):
     """The whole file as a dense matrix.  With an engine the text is tokenised on the GPU and the matrix stays there
     (GenoData.geno is None); files too large for device memory, and --hostParse, go through the host tokenizer."""
-    src = args.genoFile if args.genoFile else sys.stdin.buffer
+    src = args.genoFile if args.genoFile else stdin_bytes()
     if engine is not None and not getattr(args, "hostParse", False):
         if not isinstance(src, str) or src.endswith(".gz"):
             src = geno_io.read_bytes(src)          # stdin / gzip: decompressed in host memory

@@ -54,6 +54,8 @@ def main(argv=None):
     allInds = sorted(set(i for p in popInds for i in p))
     args.inferPloidy = False
     ploidyDict = C.ploidy_dict(args, allInds, args.haploid)
+    for s in args.haploid or []:           # freq.py:283-284: --haploid also overrides --ploidy / --ploidyFile
+        ploidyDict[s] = 1
     sampleData = genomics.SampleData(indNames=allInds, popNames=popNames, popInds=popInds, ploidyDict=ploidyDict)
     out = C.open_out(args.outFile)
     out.write("scaffold\tposition\t" + "\t".join(popNames) + "\n")

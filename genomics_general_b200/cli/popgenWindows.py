@@ -99,7 +99,9 @@ def main(argv=None):
 
     eng = Engine(args.device)
 
-    gd = C.load_geno(args, sampleData.indNames, ploidyDict, header=args.header, engine=eng)
+    # columns in the reference's haplotype order (sorted sequence names): H12's greedy clustering breaks ties by row
+    gd = C.load_geno(args, C.alignment_order(sampleData.indNames, ploidyDict, args.genoFormat), ploidyDict, header=args.header,
+                     engine=eng)
     ws = C.make_windows(args, gd, minSites, coords, C.read_scaffold_list(args.include), C.read_scaffold_list(args.exclude))
     sys.stderr.write("\n%d sites x %d haplotypes, %d windows\n" % (gd.n_sites, gd.n_haps, len(ws)))
     lo, hi = ws.ranges()

@@ -781,12 +781,25 @@ struct PlaneSet {
     std::vector<int32_t> mid;          // [Hk] mask id per row
     const int32_t* d_mid = nullptr;    // device copy
     const int32_t* d_rowmap = nullptr; // [Hm] mask id -> a representative plane row
+    bool tensor = false;               // planes of the tensor-core path (k2t.cu) instead of the three bit-planes
+    K2TPlanes t;
 };
 
 // Build bit-planes for sites [lo, hi) of the haplotype columns listed in `order` (plane row r = column order[r]).
 int build_planes(pg_ctx* ctx, const std::vector<int32_t>& order, int64_t lo, int64_t hi, PlaneSet& ps) {
     const int Hk = (int)order.size();
     PG_CHECK(Hk >= 1, "pairwise path: no haplotypes selected");
+    if (pg_k2_use_tensor()) {
+        PG_TRY(pg_k2t_build(ctx, order, lo, hi, ps.t));
+        ps.tensor = true;
+        ps.Hk = Hk;
+        ps.site_base = ps.t.site_base;
+        ps.Hm = Hk;                                // n_ij is computed for every haplotype pair: mask id = row
+        ps.mid.resize(Hk);
+        for (int r = 0; r < Hk; ++r) ps.mid[r] = r;
+        ps.d_mid = ps.t.d_iota;
+        return PG_OK;
+    }
     const int64_t sb = lo & ~(int64_t)(BP_SITES - 1);
     const int64_t nblk = (hi - sb + BP_SITES - 1) / BP_SITES;
     const int64_t NWp = nblk * 8 + KW + 8;     // zero tail: chunk over-reads contribute nothing
@@ -892,6 +905,11 @@ int run_pair_batch(pg_ctx* ctx, const PlaneSet& ps, const std::vector<int64_t>& 
     int64_t* d_hi = d_lo + nb;
     PG_CUDA(cudaMemcpyAsync(d_lo, lo.data(), (size_t)nb * 8, cudaMemcpyHostToDevice, ctx->stream));
     PG_CUDA(cudaMemcpyAsync(d_hi, hi.data(), (size_t)nb * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (ps.tensor) {
+        *d_diff = (int32_t*)ctx->pairs.p;
+        *d_n = (int32_t*)ctx->pairs.p + (size_t)nb * HH;
+        return pg_k2t_pairs(ctx, ps.t, d_lo, d_hi, nb, *d_diff, *d_n);
+    }
     PairParams pp;
     pp.planes = ps.planes;
     pp.Hk = ps.Hk;
@@ -1187,6 +1205,11 @@ extern "C" int pg_ind_het(pg_ctx* ctx, int32_t n_ind, const int32_t* hap_ind, in
         int64_t* d_hi = d_lo + nb;
         PG_CUDA(cudaMemcpyAsync(d_lo, blo.data(), nb * 8, cudaMemcpyHostToDevice, ctx->stream));
         PG_CUDA(cudaMemcpyAsync(d_hi, bhi.data(), nb * 8, cudaMemcpyHostToDevice, ctx->stream));
+        if (ps.tensor) {
+            PG_TRY(pg_k2t_het(ctx, ps.t, d_lo, d_hi, (int)nb, (const int32_t*)ctx->misc.p, n_ind, min_sites, (double*)ctx->out_d.p));
+            PG_TRY(copy_rows_back(ctx, wins, b0, nb, (const double*)ctx->out_d.p, het, (size_t)n_ind));
+            continue;
+        }
         HetParams hp;
         hp.planes = ps.planes;
         hp.Hk = ps.Hk;
@@ -1385,6 +1408,11 @@ extern "C" int pg_seq_nonnan(pg_ctx* ctx, int64_t* out) {
         int64_t* d_hi = d_lo + nb;
         PG_CUDA(cudaMemcpyAsync(d_lo, blo.data(), nb * 8, cudaMemcpyHostToDevice, ctx->stream));
         PG_CUDA(cudaMemcpyAsync(d_hi, bhi.data(), nb * 8, cudaMemcpyHostToDevice, ctx->stream));
+        if (ps.tensor) {
+            PG_TRY(pg_k2t_seq_nonnan(ctx, ps.t, d_lo, d_hi, (int)nb, (long long*)ctx->out_d.p));
+            PG_TRY(copy_rows_back(ctx, wins, b0, nb, (const double*)ctx->out_d.p, (double*)out, (size_t)H));
+            continue;
+        }
         const int ti = pg_time_begin(ctx, "k2_seq_nonnan");
         k2_seq_nonnan<<<dim3((unsigned)H, (unsigned)nb), 128, 0, ctx->stream>>>(ps.planes + (size_t)2 * ps.Hk * ps.NWp, ps.NWp,
                                                                                ps.site_base, d_lo, d_hi, H,

@@ -99,7 +99,7 @@ struct pg_ctx {
     size_t events_used = 0;
     int64_t launches = 0;
     // scratch
-    PgBuf tables, part, segmeta, winmeta, out_d, out_i, planes, pairs, misc, misc2, misc3, misc4, misc5;
+    PgBuf tables, part, segmeta, winmeta, out_d, out_i, planes, planes2, pairs, misc, misc2, misc3, misc4, misc5;
     PgBuf text, starts, meta;                 // device-side text ingest (ingest.cu)
     int64_t ingest_sites = -1;
     void* h_text[2] = {nullptr, nullptr};     // pinned staging of the text
@@ -128,6 +128,25 @@ void pg_time_end(pg_ctx* ctx, int idx);
 int pg_pinned(pg_ctx* ctx, size_t bytes, void** out);
 int pg_d2h_staged(pg_ctx* ctx, void* dst, const void* src, size_t bytes);   // large device -> pageable host copy
 int pg_build_segments(pg_ctx* ctx);
+
+// tensor-core pairwise path (k2t.cu): bit-packed operand planes of one site span
+struct K2TPlanes {
+    int Hk = 0, R = 0;                 // plane rows (haplotypes in `order`), rows allocated (multiple of 16, pad rows zero)
+    int64_t site_base = 0;             // first site of valid-plane chunk 0 (multiple of 64)
+    int64_t nchunk_v = 0;
+    const uint64_t* vplane = nullptr;  // [nchunk_v][R]: bit b of word (c, r) = haplotype r non-missing at site site_base + 64 c + b
+    const int32_t* cps = nullptr;      // [64 nchunk_v + 1]: pseudo-sites before each site of the span
+    int64_t npseudo = 0;
+    const uint64_t* pq = nullptr;      // [ceil(npseudo / 64)][2][R]: P and Q planes of the pseudo-sites
+    const int32_t* d_iota = nullptr;   // [Hk] 0..Hk-1 (identity "mask id" for the epilogues)
+};
+bool pg_k2_use_tensor();               // false when PG_K2_POPC is set (the bit-plane POPC kernels, kept as a checker)
+int pg_k2t_build(pg_ctx* ctx, const std::vector<int32_t>& order, int64_t lo, int64_t hi, K2TPlanes& ps);
+int pg_k2t_pairs(pg_ctx* ctx, const K2TPlanes& ps, const int64_t* d_lo, const int64_t* d_hi, int nb, int32_t* d_diff,
+                 int32_t* d_n);
+int pg_k2t_seq_nonnan(pg_ctx* ctx, const K2TPlanes& ps, const int64_t* d_lo, const int64_t* d_hi, int nb, long long* d_out);
+int pg_k2t_het(pg_ctx* ctx, const K2TPlanes& ps, const int64_t* d_lo, const int64_t* d_hi, int nb, const int32_t* d_ind_start,
+               int n_ind, int min_sites, double* d_out);
 
 // implemented in k1.cu / k2.cu
 // pairwise statistics for the listed windows, written into the DEVICE record table (stride RC words)

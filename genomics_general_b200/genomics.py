@@ -325,13 +325,13 @@ class Alignment:
         return {a: {b: m[i, j] for j, b in enumerate(samples)} for i, a in enumerate(samples)}
 
     def sampleHet(self, sampleNames=None, asList=False, minSites=None):
-        """genomics.py:918-929, operator-precedence quirk included (value iff exactly two haplotypes and bit 1 of
-        n_ij set).  Only the default minSites (None -> 1) has that simple closed form and is supported."""
-        if minSites not in (None, 1):
-            raise NotImplementedError("sampleHet(minSites=...) other than the default is not implemented")
+        """genomics.py:918-929, operator-precedence quirk included: `len(x)==2 & n >= minSites` is the chained comparison
+        len(x) == (2 & n) >= minSites, so a two-haplotype sample has a value iff bit 1 of n_ij is set AND minSites <= 2."""
         samples = list(dict.fromkeys(self.sampleNames.tolist()))
         hap_ind = np.array([samples.index(s) for s in self.sampleNames], dtype=np.int32)
         het = self._engine().ind_het(hap_ind, len(samples), min_sites=self._masked_min_sites)[0]
+        if minSites is not None and minSites > 2:
+            het = np.full(len(samples), np.nan)
         if sampleNames is not None:
             het = np.array([het[samples.index(s)] for s in sampleNames])
             samples = list(sampleNames)
@@ -366,13 +366,15 @@ def genoToAlignment(seqDict, sampleData=None, genoFormat="diplo", positions=None
         sampleNames += [ind] * pl
         groups += [sampleData.getPop(ind)] * pl
     geno = np.concatenate(cols, axis=1) if cols else np.zeros((0, 0), dtype=np.int8)
-    return Alignment(geno, names=names, groups=groups, sampleNames=sampleNames, positions=positions)
+    order = np.argsort(names)                       # genomics.py:1121: haplotypes sorted by sequence name
+    return Alignment(geno[:, order], names=[names[i] for i in order], groups=[groups[i] for i in order],
+                     sampleNames=[sampleNames[i] for i in order], positions=positions)
 
 
 def ABBABABA(aln, P1, P2, P3, P4, minData, polarize=True, fixed=False):
-    """genomics.py:1647-1695 (polarize=True path)."""
-    if not polarize or fixed:
-        raise NotImplementedError("only the default polarize=True, fixed=False mode is implemented on the GPU")
+    """genomics.py:1647-1695.  polarize=True (default): the derived allele is the one absent from P4 (1672);
+    polarize=False, fixed=True: additionally fixed in P1..P3 (1673-1676); both False: the less common of the two
+    alleles (1677) — the latter two share fourPop's allele selection (the K1 FOURPOP site pass)."""
     pops = [P1, P2, P3, P4]
     hp = np.full(aln.N, -1, dtype=np.int32)
     for k, p in enumerate(pops):
@@ -381,10 +383,15 @@ def ABBABABA(aln, P1, P2, P3, P4, minData, polarize=True, fixed=False):
                 hp[i] = k
     eng = aln._engine()
     eng.set_pops(hp, 4)
-    r = eng.abbababa(0, 1, 2, 3, minData)
-    used = r["sitesUsed"][0]
-    return {"D": float(r["D"][0]), "fd": float(r["fd"][0]), "fdM": float(r["fdM"][0]), "ABBA": float(r["ABBA"][0]),
-            "BABA": float(r["BABA"][0]), "sitesUsed": (np.nan if np.isnan(used) else int(used))}
+    if polarize:
+        r = eng.abbababa(0, 1, 2, 3, minData)
+        used = r["sitesUsed"][0]
+        return {"D": float(r["D"][0]), "fd": float(r["fd"][0]), "fdM": float(r["fdM"][0]), "ABBA": float(r["ABBA"][0]),
+                "BABA": float(r["BABA"][0]), "sitesUsed": (np.nan if np.isnan(used) else int(used))}
+    r = eng.fourpop(0, 1, 2, 3, minData, polarize=False, fixed=fixed)
+    no_good = bool(np.isnan(r["ABBA"][0]))         # ABBA is a plain sum: nan only when no site passed (1694-1695)
+    return {"D": float(r["D"][0]), "fd": float(r["fd"][0]), "fdM": float(r["fdm"][0]), "ABBA": float(r["ABBA"][0]),
+            "BABA": float(r["BABA"][0]), "sitesUsed": (np.nan if no_good else int(r["sitesUsed"][0]))}
 
 
 def fourPop(aln, P1, P2, P3, P4, minData, polarize=False, fixed=False):

@@ -127,6 +127,7 @@ def sliding_sites_windows(scaf_ids, scaf_names, pos, wind_sites, overlap=0, max_
             continue
         if pending_dup is not None:
             _dup_after_skip(ws, pending_dup)
+            wid += 1                                # windowsDone += 1 for the duplicate too (genomics.py:2062-2066)
             pending_dup = None
         run_end_emitted = None
         n = int(rb - ra)

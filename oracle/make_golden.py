@@ -239,6 +239,11 @@ def make_generator_cases():
                            (20, 0, 150, 5), (20, 5, 100, 20), (7, 3, None, 1), (200, 0, None, 1)):
         record("sites", dict(windSites=ws, overlap=ov, maxDist=md, minSites=ms),
                ref.slidingSitesWindows(io.StringIO(text), ws, ov, md if md else np.inf, ms, names=names))
+    for ex in (["chrB"], ["chrC"], ["chrB", "chrC"]):            # the duplicate window after a skipped scaffold keeps its ID
+        record("sites", dict(windSites=50, overlap=0, maxDist=None, minSites=20, exclude=ex),
+               ref.slidingSitesWindows(io.StringIO(text), 50, 0, np.inf, 20, names=names, exclude=ex))
+    record("coordinate", dict(windSize=300, stepSize=None, exclude=["chrB"]),
+           ref.slidingCoordWindows(io.StringIO(text), 300, 300, names=names, exclude=["chrB"]))
     coords = [("chrA", 1, 400, "w1"), ("chrA", 300, 900, "w2"), ("chrA", 1500, 1600, "w3"), ("chrC", 1, 5000, "w4"),
               ("chrD", 100, 200, "w5"), ("chrD", 150, 160, "w6"), ("chrD", 390, 400, "w7")]
     record("predefined", dict(windCoords=[list(c) for c in coords]),

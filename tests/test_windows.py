@@ -33,7 +33,8 @@ def _run(kind, p, scaf, pos):
     if kind == "coordinate":
         return W.sliding_coord_windows(ids, names, pos, p["windSize"], p["stepSize"], exclude=p.get("exclude"))
     if kind == "sites":
-        return W.sliding_sites_windows(ids, names, pos, p["windSites"], p["overlap"], p["maxDist"], p["minSites"])
+        return W.sliding_sites_windows(ids, names, pos, p["windSites"], p["overlap"], p["maxDist"], p["minSites"],
+                                       exclude=p.get("exclude"))
     return W.predefined_coord_windows(ids, names, pos, [tuple(c) for c in p["windCoords"]])
 
 
@@ -48,8 +49,7 @@ def test_against_reference_generators(idx):
         assert [pos[i] for i in range(ws.lo[k], ws.hi[k])] == r["positions"], (k, ws.lo[k], ws.hi[k])
         if case["kind"] != "sites":
             assert [ws.start[k], ws.end[k]] == r["limits"]
-        if case["kind"] == "predefined":
-            assert ws.ID[k] == r["ID"]
+        assert ws.ID[k] == r["ID"], (k, ws.ID[k], r["ID"])       # windowID column of --addWindowID
 
 
 def _random_layout(rng):
