@@ -36,6 +36,14 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     do {
@@ -82,18 +90,27 @@ __global__ void __launch_bounds__(256) k2t_valid_class(const __grid_constant__ V
         uint32_t pres[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) pres[k] = 0u;
-        for (int cw = lane; cw < p.pw; cw += 32) {
-            const uint32_t cm = p.cmask[cw];
-            uint32_t w[8];
+        // one lane owns 4 column words (16 haplotype bytes) of the warp's 8 sites: 8 x LDG.128 in flight per lane
+        const uint4* g4 = reinterpret_cast<const uint4*>(p.geno32);
+        const int pw4 = p.pw >> 2;
+        for (int q = lane; q < pw4; q += 32) {
+            const uint4 cm = reinterpret_cast<const uint4*>(p.cmask)[q];
+            uint4 w[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const int64_t s = site0 + k;
-                w[k] = (s < p.S) ? __ldg(p.geno32 + s * p.pw + cw) : 0u;
+                w[k] = (s < p.S) ? __ldg(g4 + s * pw4 + q) : make_uint4(0u, 0u, 0u, 0u);
             }
 #pragma unroll
-            for (int k = 0; k < 8; ++k) pres[k] |= w[k] & cm;
-            vc_st[o * p.pw + cw] = valid2(w[0], w[1]) | (valid2(w[2], w[3]) << 2) | (valid2(w[4], w[5]) << 4) |
-                                   (valid2(w[6], w[7]) << 6);
+            for (int k = 0; k < 8; ++k) pres[k] |= (w[k].x & cm.x) | (w[k].y & cm.y) | (w[k].z & cm.z) | (w[k].w & cm.w);
+            uint4 o4;
+#define VC_WORD(C) (valid2(w[0].C, w[1].C) | (valid2(w[2].C, w[3].C) << 2) | (valid2(w[4].C, w[5].C) << 4) | (valid2(w[6].C, w[7].C) << 6))
+            o4.x = VC_WORD(x);
+            o4.y = VC_WORD(y);
+            o4.z = VC_WORD(z);
+            o4.w = VC_WORD(w);
+#undef VC_WORD
+            reinterpret_cast<uint4*>(vc_st + o * p.pw)[q] = o4;
         }
         uint32_t mine = 0u;
 #pragma unroll
@@ -136,15 +153,22 @@ __global__ void __launch_bounds__(256) k2t_valid_class(const __grid_constant__ V
     }
 }
 
-// exclusive scan of the chunk totals (single CTA; 1e8 sites = 1.6 M chunks = 1.6 k iterations)
+// exclusive scan of the chunk totals (single CTA, 4 elements per thread and iteration; 1e8 sites = 1.6 M chunks = 400 iterations)
 __global__ void __launch_bounds__(1024) k2t_scan(const int32_t* __restrict__ tot, int32_t* __restrict__ off, int64_t n) {
     __shared__ int wsum[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int carry = 0;
-    for (int64_t base = 0; base < n; base += 1024) {
-        const int64_t i = base + tid;
-        const int v = (i < n) ? tot[i] : 0;
-        int incl = v;
+    for (int64_t base = 0; base < n; base += 4096) {
+        const int64_t i = base + 4 * tid;
+        int4 v = make_int4(0, 0, 0, 0);
+        if (i + 3 < n) v = *reinterpret_cast<const int4*>(tot + i);
+        else {
+            if (i < n) v.x = tot[i];
+            if (i + 1 < n) v.y = tot[i + 1];
+            if (i + 2 < n) v.z = tot[i + 2];
+        }
+        const int mine = v.x + v.y + v.z + v.w;
+        int incl = mine;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const int t = __shfl_up_sync(0xffffffffu, incl, d);
@@ -162,8 +186,13 @@ __global__ void __launch_bounds__(1024) k2t_scan(const int32_t* __restrict__ tot
             wsum[lane] = x;
         }
         __syncthreads();
-        const int wbase = warp ? wsum[warp - 1] : 0;
-        if (i < n) off[i] = carry + wbase + incl - v;
+        const int e0 = carry + (warp ? wsum[warp - 1] : 0) + incl - mine;
+        if (i + 3 < n) *reinterpret_cast<int4*>(off + i) = make_int4(e0, e0 + v.x, e0 + v.x + v.y, e0 + v.x + v.y + v.z);
+        else {
+            if (i < n) off[i] = e0;
+            if (i + 1 < n) off[i + 1] = e0 + v.x;
+            if (i + 2 < n) off[i + 2] = e0 + v.x + v.y;
+        }
         carry += wsum[31];
         __syncthreads();
     }
@@ -239,19 +268,31 @@ __global__ void __launch_bounds__(256) k2t_build_pq(const __grid_constant__ PqPa
             qm[k] = ok ? ((e.y >> 8) & 0xffu) * 0x01010101u : 0u;
             if (!ok) row[k] = nullptr;
         }
-        for (int cw = lane; cw < p.pw; cw += 32) {
-            uint32_t outp = 0u, outq = 0u;
+        const int pw4 = p.pw >> 2;
+        for (int q = lane; q < pw4; q += 32) {
+            uint4 w[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                w[k] = row[k] ? __ldg(reinterpret_cast<const uint4*>(row[k]) + q) : make_uint4(0u, 0u, 0u, 0u);
+            uint4 op = make_uint4(0u, 0u, 0u, 0u), oq = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                const uint32_t w = row[k] ? __ldg(row[k] + cw) : 0u;
-                outp |= ((w >> psh[k]) & 0x01010101u) << k;
-                uint32_t t = w & qm[k];
-                t |= t >> 4;
-                t |= t >> 2;
-                outq |= (t & 0x01010101u) << k;
+#define PQ_WORD(C)                                         \
+    {                                                      \
+        op.C |= ((w[k].C >> psh[k]) & 0x01010101u) << k;   \
+        uint32_t t = w[k].C & qm[k];                       \
+        t |= t >> 4;                                       \
+        t |= t >> 2;                                       \
+        oq.C |= (t & 0x01010101u) << k;                    \
+    }
+                PQ_WORD(x)
+                PQ_WORD(y)
+                PQ_WORD(z)
+                PQ_WORD(w)
+#undef PQ_WORD
             }
-            pq_st[(0 * 8 + o) * p.pw + cw] = outp;
-            pq_st[(1 * 8 + o) * p.pw + cw] = outq;
+            reinterpret_cast<uint4*>(pq_st + (0 * 8 + o) * p.pw)[q] = op;
+            reinterpret_cast<uint4*>(pq_st + (1 * 8 + o) * p.pw)[q] = oq;
         }
         __syncthreads();
         const uint8_t* st8 = reinterpret_cast<const uint8_t*>(pq_st);
@@ -293,14 +334,16 @@ struct GramParams {
     const int32_t* cps;         // NPL == 2: plane coordinate = cps[site - site_base]
     const GramGroup* groups;
     int nbmax;                  // max nb_rows over the groups (shared-memory geometry)
-    int nstages;
+    int nstages;                // operand ring depth
+    int nraw;                   // raw plane-word ring depth
     int32_t* out;               // [nb][Hk][Hk]
 };
 
-constexpr int GRAM_PRODUCERS = 128;
-constexpr int GRAM_THREADS = 160;          // warps 0-3: producers, then epilogue; warp 4: TMEM allocation + MMA issue
+constexpr int GRAM_PRODUCERS = 256;        // 8 expanding warps: two per scheduler, so that dependent ALU chains interleave
+constexpr int GRAM_THREADS = 320;          // warps 0-7: expand, then epilogue; warp 8: TMEM allocation + MMA issue; warp 9: TMA
 constexpr int GRAM_MAX_STAGES = 4;
-constexpr int GRAM_MAX_ITEMS = (128 + 512) * 2 / GRAM_PRODUCERS;    // plane words per producer thread and stage
+constexpr int GRAM_MAX_RAW = 8;            // depth of the raw plane-word ring (TMA runs this many chunks ahead)
+constexpr int GRAM_MAX_ITEMS = ((128 + 512) * 2 + GRAM_PRODUCERS - 1) / GRAM_PRODUCERS;    // plane words per thread and stage
 
 // 16 bits -> 16 bytes of 0/1 (byte k = bit k)
 __device__ __forceinline__ uint4 expand16(uint32_t x) {
@@ -335,17 +378,24 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                  : "memory");
 }
 
+// Shared memory: [raw ring: nraw slots of NPL x (128 + nbmax) plane words, filled by 1-D TMA bulk copies]
+//                [operand ring: nstages stages of 2 K steps x NPL planes x (128 + nbmax) rows x 32 bytes]
 template <int NPL>
 __global__ void __launch_bounds__(GRAM_THREADS, 1) k2t_gram(const __grid_constant__ GramParams gp) {
     extern __shared__ __align__(128) uint8_t gsm[];
-    __shared__ __align__(8) uint64_t full[GRAM_MAX_STAGES], empty[GRAM_MAX_STAGES], done;
+    __shared__ __align__(8) uint64_t full[GRAM_MAX_STAGES], empty[GRAM_MAX_STAGES], raw_full[GRAM_MAX_RAW],
+        raw_empty[GRAM_MAX_RAW], done;
     __shared__ uint32_t s_tmem;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const GramGroup g = gp.groups[blockIdx.x];
     const int wb = blockIdx.y;
-    const int NS = gp.nstages;
-    const int BLK = (128 + gp.nbmax) * 32;              // one (K step, plane) block: A region 128 rows, then the B region
+    const int NS = gp.nstages, RD = gp.nraw;
+    const int RROWS = 128 + gp.nbmax;                   // rows of one plane in a raw slot / operand block
+    const int RAW = NPL * RROWS * 8;                    // bytes of one raw slot
+    const int BLK = RROWS * 32;                         // one (K step, plane) block: A region 128 rows, then the B region
     const int STAGE = 2 * NPL * BLK;
+    uint8_t* const raw_base = gsm;
+    uint8_t* const op_base = gsm + (size_t)RD * RAW;
 
     // window in plane coordinates
     int64_t lo = gp.win_lo[wb] - gp.site_base, hi = gp.win_hi[wb] - gp.site_base;
@@ -358,11 +408,17 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) k2t_gram(const __grid_constan
 
     uint32_t ncols = 32;
     while ((int)ncols < g.nb_rows) ncols <<= 1;
-    if (warp == 4) {
+    // rows of the A tile past the last plane row are never copied: they must read as zero
+    for (int i = tid; i < RD * RAW / 16; i += GRAM_THREADS) reinterpret_cast<uint4*>(raw_base)[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (warp == 8) {
         if (lane == 0) {
             for (int s = 0; s < NS; ++s) {
                 mbar_init(&full[s], GRAM_PRODUCERS);
                 mbar_init(&empty[s], 1);
+            }
+            for (int s = 0; s < RD; ++s) {
+                mbar_init(&raw_full[s], 1);
+                mbar_init(&raw_empty[s], GRAM_PRODUCERS);
             }
             mbar_init(&done, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -372,18 +428,57 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) k2t_gram(const __grid_constan
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the zero fill above precedes the bulk copies
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = s_tmem;
 
-    if (warp < 4) {
+    if (warp == 9) {
+        // ---------------- TMA: plane words of chunk c_first + it -> raw slot it % RD ----------------
+        if (lane == 0) {
+            const int a_rows = min(128, gp.R - g.a_row0);
+            const uint32_t bytes_a = (uint32_t)a_rows * 8u, bytes_b = (uint32_t)g.nb_rows * 8u;
+            int slot = 0;
+            uint32_t ph = 0;
+            for (int it = 0; it < nst; ++it) {
+                if (it >= RD) mbar_wait(&raw_empty[slot], ph ^ 1u);
+                mbar_expect_tx(&raw_full[slot], NPL * (bytes_a + bytes_b));
+                const int64_t chunk = c_first + it;
+#pragma unroll
+                for (int pl = 0; pl < NPL; ++pl) {
+                    const uint64_t* src = gp.plane + (chunk * NPL + pl) * gp.R;
+                    uint8_t* dst = raw_base + (size_t)slot * RAW + (size_t)pl * RROWS * 8;
+                    bulk_g2s(dst, src + g.a_row0, bytes_a, &raw_full[slot]);
+                    bulk_g2s(dst + 128 * 8, src + g.b_row0, bytes_b, &raw_full[slot]);
+                }
+                if (++slot == RD) {
+                    slot = 0;
+                    ph ^= 1u;
+                }
+            }
+        }
+    } else if (warp < 8) {
         // ---------------- producers: plane words -> 0/1 bytes in the core-matrix layout ----------------
         const int rows_tot = 128 + g.nb_rows;
         const int nitems = rows_tot * NPL;
+        int r_idx[GRAM_MAX_ITEMS], d_off[GRAM_MAX_ITEMS];          // raw word index / byte offset in a K-step block, -1: none
+#pragma unroll
+        for (int q = 0; q < GRAM_MAX_ITEMS; ++q) {
+            const int item = tid + q * GRAM_PRODUCERS;
+            r_idx[q] = -1;
+            d_off[q] = 0;
+            if (item < nitems) {
+                const int pl = (NPL == 2 && item >= rows_tot) ? 1 : 0;
+                const int rr = item - pl * rows_tot;
+                const int x = (rr < 128) ? rr : rr - 128;
+                r_idx[q] = pl * RROWS + rr;
+                d_off[q] = pl * BLK + ((rr < 128) ? 0 : 4096) + (x >> 3) * 256 + (x & 7) * 16;
+            }
+        }
+        int s = 0, slot = 0;
+        uint32_t ph_s = 0, ph_r = 0;
         for (int it = 0; it < nst; ++it) {
-            const int s = it % NS;
-            if (it >= NS) mbar_wait(&empty[s], (uint32_t)(((it / NS) - 1) & 1));
             const int64_t chunk = c_first + it;
             uint64_t mask = ~0ull;
             {
@@ -391,30 +486,19 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) k2t_gram(const __grid_constan
                 if (lo > b0) mask &= ~0ull << (int)(lo - b0);
                 if (hi < b0 + 64) mask &= ~0ull >> (int)(b0 + 64 - hi);
             }
+            mbar_wait(&raw_full[slot], ph_r);
+            const uint64_t* rw = reinterpret_cast<const uint64_t*>(raw_base + (size_t)slot * RAW);
             uint64_t v[GRAM_MAX_ITEMS];
 #pragma unroll
-            for (int q = 0; q < GRAM_MAX_ITEMS; ++q) {
-                const int item = tid + q * GRAM_PRODUCERS;
-                v[q] = 0ull;
-                if (item < nitems) {
-                    const int pl = (NPL == 2 && item >= rows_tot) ? 1 : 0;
-                    const int rr = item - pl * rows_tot;
-                    const int row = (rr < 128) ? g.a_row0 + rr : g.b_row0 + rr - 128;
-                    if (row < gp.R) v[q] = __ldg(gp.plane + (chunk * NPL + pl) * gp.R + row) & mask;
-                }
-            }
-            uint8_t* sb = gsm + (size_t)s * STAGE;
+            for (int q = 0; q < GRAM_MAX_ITEMS; ++q) v[q] = (r_idx[q] >= 0) ? (rw[r_idx[q]] & mask) : 0ull;
+            if (it >= NS) mbar_wait(&empty[s], ph_s ^ 1u);
+            uint8_t* sb = op_base + (size_t)s * STAGE;
 #pragma unroll
             for (int q = 0; q < GRAM_MAX_ITEMS; ++q) {
-                const int item = tid + q * GRAM_PRODUCERS;
-                if (item < nitems) {
-                    const int pl = (NPL == 2 && item >= rows_tot) ? 1 : 0;
-                    const int rr = item - pl * rows_tot;
-                    const int x = (rr < 128) ? rr : rr - 128;
-                    const int ro = ((rr < 128) ? 0 : 4096) + (x >> 3) * 256 + (x & 7) * 16;
+                if (r_idx[q] >= 0) {
                     const uint32_t wlo = (uint32_t)v[q], whi = (uint32_t)(v[q] >> 32);
-                    uint8_t* d0 = sb + (0 * NPL + pl) * BLK + ro;
-                    uint8_t* d1 = sb + (1 * NPL + pl) * BLK + ro;
+                    uint8_t* d0 = sb + d_off[q];
+                    uint8_t* d1 = d0 + NPL * BLK;
                     *reinterpret_cast<uint4*>(d0) = expand16(wlo & 0xffffu);
                     *reinterpret_cast<uint4*>(d0 + 128) = expand16(wlo >> 16);
                     *reinterpret_cast<uint4*>(d1) = expand16(whi & 0xffffu);
@@ -423,13 +507,25 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) k2t_gram(const __grid_constan
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
             mbar_arrive(&full[s]);
+            // released only now: the stores above consumed the words, so the loads from the slot have completed before the
+            // TMA (async proxy) may overwrite it — an arrive right after issuing the loads raced with the refill
+            mbar_arrive(&raw_empty[slot]);
+            if (++s == NS) {
+                s = 0;
+                ph_s ^= 1u;
+            }
+            if (++slot == RD) {
+                slot = 0;
+                ph_r ^= 1u;
+            }
         }
     } else if (lane == 0) {
         // ---------------- MMA issue (one thread) ----------------
-        const uint32_t sbase = smem_u32(gsm);
+        const uint32_t sbase = smem_u32(op_base);
+        int s = 0;
+        uint32_t ph = 0;
         for (int it = 0; it < nst; ++it) {
-            const int s = it % NS;
-            mbar_wait(&full[s], (uint32_t)((it / NS) & 1));
+            mbar_wait(&full[s], ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t st = sbase + (uint32_t)s * STAGE;
 #pragma unroll
@@ -449,48 +545,66 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) k2t_gram(const __grid_constan
                 }
             }
             umma_commit(&empty[s]);       // arrives when the MMAs above have read the stage
+            if (++s == NS) {
+                s = 0;
+                ph ^= 1u;
+            }
         }
         umma_commit(&done);
     }
 
-    if (warp < 4) {
+    if (warp < 8) {
         // ---------------- epilogue: TMEM -> registers -> symmetric int32 matrix ----------------
         if (nst > 0) {
             mbar_wait(&done, 0u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
-        const int i = g.a_row0 + warp * 32 + lane;
+        // Lane = matrix row in TMEM (warp w may touch lanes 32 (w % 4) ..): warps w and w + 4 take alternate 32-column
+        // blocks of the same rows.  The mirror element [j][i] is written straight from the registers (lanes run along i:
+        // coalesced); the direct element [i][j] goes through a 32 x 32 transpose in shared memory (the operand ring is idle
+        // now) so that lanes run along j as well.
+        const int qd = warp & 3;
+        const int i0 = g.a_row0 + qd * 32;
         int32_t* o = gp.out + (size_t)wb * gp.Hk * gp.Hk;
-        for (int c0 = 0; c0 < g.nb_rows; c0 += 16) {
-            uint32_t v[16];
+        uint32_t* tr = reinterpret_cast<uint32_t*>(op_base) + warp * (32 * 33);
+        for (int c0 = (warp >> 2) * 32; c0 < g.nb_rows; c0 += 64) {
+            uint32_t v[32];
             if (nst > 0) {
-                const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+                const uint32_t taddr = tmem + ((uint32_t)(qd * 32) << 16) + (uint32_t)c0;
                 asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,"
+                    "%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-                      "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                      "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+                      "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+                      "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                     : "r"(taddr)
                     : "memory");
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             } else {
 #pragma unroll
-                for (int e = 0; e < 16; ++e) v[e] = 0u;
+                for (int e = 0; e < 32; ++e) v[e] = 0u;
             }
-            if (i < gp.Hk) {
+            const int i = i0 + lane;
 #pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    const int j = g.b_row0 + c0 + e;
-                    if (j < gp.Hk) {
-                        o[(size_t)i * gp.Hk + j] = (int32_t)v[e];
-                        o[(size_t)j * gp.Hk + i] = (int32_t)v[e];
-                    }
-                }
+            for (int e = 0; e < 32; ++e) {
+                const int j = g.b_row0 + c0 + e;
+                if (i < gp.Hk && j < gp.Hk) o[(size_t)j * gp.Hk + i] = (int32_t)v[e];
+                tr[lane * 33 + e] = v[e];
             }
+            __syncwarp();
+            const int j = g.b_row0 + c0 + lane;
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) {
+                const uint32_t x = tr[r * 33 + lane];
+                if (i0 + r < gp.Hk && j < gp.Hk) o[(size_t)(i0 + r) * gp.Hk + j] = (int32_t)x;
+            }
+            __syncwarp();
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 4) {
+    if (warp == 8) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(ncols) : "memory");
     }
@@ -708,30 +822,39 @@ int pg_k2t_pairs(pg_ctx* ctx, const K2TPlanes& ps, const int64_t* d_lo, const in
     gp.nbmax = nbmax;
     static bool attr_dev[64] = {};
     if (!attr_dev[ctx->device & 63]) {
-        PG_CUDA(cudaFuncSetAttribute(k2t_gram<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        PG_CUDA(cudaFuncSetAttribute(k2t_gram<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        PG_CUDA(cudaFuncSetAttribute(k2t_gram<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        PG_CUDA(cudaFuncSetAttribute(k2t_gram<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         attr_dev[ctx->device & 63] = true;
     }
     const dim3 grid((unsigned)groups.size(), (unsigned)nb);
+    // shared memory: an operand ring of >= 2 stages, the rest (up to 8 slots) for the raw plane words
+    const int budget = 210 * 1024;
+    auto geometry = [&](int npl, int& nstages, int& nraw) {
+        const int stage = 2 * npl * (128 + nbmax) * 32, raw = npl * (128 + nbmax) * 8;
+        nstages = std::max(2, std::min(3, (budget - 4 * raw) / stage));
+        nraw = std::max(2, std::min(GRAM_MAX_RAW, (budget - nstages * stage) / raw));
+        if (const char* e = getenv("PG_K2T_NRAW")) nraw = std::max(1, std::min(nraw, atoi(e)));
+        if (const char* e = getenv("PG_K2T_NSTAGES")) nstages = std::max(1, std::min(nstages, atoi(e)));
+        // the epilogue's 8 transpose tiles (32 x 33 words each) reuse the operand ring
+        return std::max((size_t)nstages * stage, (size_t)8 * 32 * 33 * 4) + (size_t)nraw * raw;
+    };
     {
-        const int stage = 2 * 1 * (128 + nbmax) * 32;
-        gp.nstages = std::max(2, std::min(GRAM_MAX_STAGES, (200 * 1024) / stage));
+        const size_t smem = geometry(1, gp.nstages, gp.nraw);
         gp.plane = ps.vplane;
         gp.cps = nullptr;
         gp.out = d_n;
         const int ti = pg_time_begin(ctx, "k2t_gram_n");
-        k2t_gram<1><<<grid, GRAM_THREADS, (size_t)gp.nstages * stage, ctx->stream>>>(gp);
+        k2t_gram<1><<<grid, GRAM_THREADS, smem, ctx->stream>>>(gp);
         pg_time_end(ctx, ti);
         PG_CUDA(cudaGetLastError());
     }
     {
-        const int stage = 2 * 2 * (128 + nbmax) * 32;
-        gp.nstages = std::max(2, std::min(GRAM_MAX_STAGES, (200 * 1024) / stage));
+        const size_t smem = geometry(2, gp.nstages, gp.nraw);
         gp.plane = ps.pq;
         gp.cps = ps.cps;
         gp.out = d_diff;
         const int ti = pg_time_begin(ctx, "k2t_gram_diff");
-        k2t_gram<2><<<grid, GRAM_THREADS, (size_t)gp.nstages * stage, ctx->stream>>>(gp);
+        k2t_gram<2><<<grid, GRAM_THREADS, smem, ctx->stream>>>(gp);
         pg_time_end(ctx, ti);
         PG_CUDA(cudaGetLastError());
     }

@@ -389,7 +389,9 @@ def ABBABABA(aln, P1, P2, P3, P4, minData, polarize=True, fixed=False):
         return {"D": float(r["D"][0]), "fd": float(r["fd"][0]), "fdM": float(r["fdM"][0]), "ABBA": float(r["ABBA"][0]),
                 "BABA": float(r["BABA"][0]), "sitesUsed": (np.nan if np.isnan(used) else int(used))}
     r = eng.fourpop(0, 1, 2, 3, minData, polarize=False, fixed=fixed)
-    no_good = bool(np.isnan(r["ABBA"][0]))         # ABBA is a plain sum: nan only when no site passed (1694-1695)
+    # no site passed the filters: every value nan, sitesUsed included (1694-1695).  With sites but no selected allele the
+    # sums run over empty arrays: ABBA = 0.0, sitesUsed = 0.
+    no_good = int(r["sitesUsed"][0]) == 0 and bool(np.isnan(r["ABBA"][0]))
     return {"D": float(r["D"][0]), "fd": float(r["fd"][0]), "fdM": float(r["fdm"][0]), "ABBA": float(r["ABBA"][0]),
             "BABA": float(r["BABA"][0]), "sitesUsed": (np.nan if no_good else int(r["sitesUsed"][0]))}
 
