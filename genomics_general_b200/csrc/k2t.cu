@@ -339,8 +339,9 @@ struct GramParams {
     int32_t* out;               // [nb][Hk][Hk]
 };
 
-constexpr int GRAM_PRODUCERS = 256;        // 8 expanding warps: two per scheduler, so that dependent ALU chains interleave
-constexpr int GRAM_THREADS = 320;          // warps 0-7: expand, then epilogue; warp 8: TMEM allocation + MMA issue; warp 9: TMA
+constexpr int GRAM_PRODUCERS = 384;        // 12 expanding warps: three per scheduler, so that dependent ALU chains interleave
+constexpr int GRAM_NPW = GRAM_PRODUCERS / 32;
+constexpr int GRAM_THREADS = GRAM_PRODUCERS + 64;   // warps 0..NPW-1: expand, then (0-7) epilogue; then TMEM allocation + MMA issue; then TMA
 constexpr int GRAM_MAX_STAGES = 4;
 constexpr int GRAM_MAX_RAW = 8;            // depth of the raw plane-word ring (TMA runs this many chunks ahead)
 constexpr int GRAM_MAX_ITEMS = ((128 + 512) * 2 + GRAM_PRODUCERS - 1) / GRAM_PRODUCERS;    // plane words per thread and stage
@@ -408,17 +409,19 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) k2t_gram(const __grid_constan
 
     uint32_t ncols = 32;
     while ((int)ncols < g.nb_rows) ncols <<= 1;
+    const bool a_in_b = (g.a_row0 == g.b_row0);
+    const uint32_t a_base = a_in_b ? 4096u : 0u;       // byte offset of the A tile inside a (K step, plane) block
     // rows of the A tile past the last plane row are never copied: they must read as zero
     for (int i = tid; i < RD * RAW / 16; i += GRAM_THREADS) reinterpret_cast<uint4*>(raw_base)[i] = make_uint4(0u, 0u, 0u, 0u);
-    if (warp == 8) {
+    if (warp == GRAM_NPW) {
         if (lane == 0) {
             for (int s = 0; s < NS; ++s) {
-                mbar_init(&full[s], GRAM_PRODUCERS);
+                mbar_init(&full[s], GRAM_NPW);            // one arrival per expanding warp
                 mbar_init(&empty[s], 1);
             }
             for (int s = 0; s < RD; ++s) {
                 mbar_init(&raw_full[s], 1);
-                mbar_init(&raw_empty[s], GRAM_PRODUCERS);
+                mbar_init(&raw_empty[s], GRAM_NPW);
             }
             mbar_init(&done, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -434,7 +437,7 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) k2t_gram(const __grid_constan
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = s_tmem;
 
-    if (warp == 9) {
+    if (warp == GRAM_NPW + 1) {
         // ---------------- TMA: plane words of chunk c_first + it -> raw slot it % RD ----------------
         if (lane == 0) {
             const int a_rows = min(128, gp.R - g.a_row0);
@@ -443,13 +446,13 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) k2t_gram(const __grid_constan
             uint32_t ph = 0;
             for (int it = 0; it < nst; ++it) {
                 if (it >= RD) mbar_wait(&raw_empty[slot], ph ^ 1u);
-                mbar_expect_tx(&raw_full[slot], NPL * (bytes_a + bytes_b));
+                mbar_expect_tx(&raw_full[slot], NPL * ((a_in_b ? 0u : bytes_a) + bytes_b));
                 const int64_t chunk = c_first + it;
 #pragma unroll
                 for (int pl = 0; pl < NPL; ++pl) {
                     const uint64_t* src = gp.plane + (chunk * NPL + pl) * gp.R;
                     uint8_t* dst = raw_base + (size_t)slot * RAW + (size_t)pl * RROWS * 8;
-                    bulk_g2s(dst, src + g.a_row0, bytes_a, &raw_full[slot]);
+                    if (!a_in_b) bulk_g2s(dst, src + g.a_row0, bytes_a, &raw_full[slot]);
                     bulk_g2s(dst + 128 * 8, src + g.b_row0, bytes_b, &raw_full[slot]);
                 }
                 if (++slot == RD) {
@@ -458,9 +461,11 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) k2t_gram(const __grid_constan
                 }
             }
         }
-    } else if (warp < 8) {
+    } else if (warp < GRAM_NPW) {
         // ---------------- producers: plane words -> 0/1 bytes in the core-matrix layout ----------------
-        const int rows_tot = 128 + g.nb_rows;
+        // a diagonal group (A tile = first rows of the B range) expands the B rows only: the A descriptor points into them
+        const int skip_a = a_in_b ? 128 : 0;
+        const int rows_tot = 128 + g.nb_rows - skip_a;
         const int nitems = rows_tot * NPL;
         int r_idx[GRAM_MAX_ITEMS], d_off[GRAM_MAX_ITEMS];          // raw word index / byte offset in a K-step block, -1: none
 #pragma unroll
@@ -470,7 +475,7 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) k2t_gram(const __grid_constan
             d_off[q] = 0;
             if (item < nitems) {
                 const int pl = (NPL == 2 && item >= rows_tot) ? 1 : 0;
-                const int rr = item - pl * rows_tot;
+                const int rr = item - pl * rows_tot + skip_a;
                 const int x = (rr < 128) ? rr : rr - 128;
                 r_idx[q] = pl * RROWS + rr;
                 d_off[q] = pl * BLK + ((rr < 128) ? 0 : 4096) + (x >> 3) * 256 + (x & 7) * 16;
@@ -506,10 +511,13 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) k2t_gram(const __grid_constan
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
-            mbar_arrive(&full[s]);
-            // released only now: the stores above consumed the words, so the loads from the slot have completed before the
-            // TMA (async proxy) may overwrite it — an arrive right after issuing the loads raced with the refill
-            mbar_arrive(&raw_empty[slot]);
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&full[s]);
+                // released only now: the stores above consumed the words, so the loads from the slot have completed before
+                // the TMA (async proxy) may overwrite it — an arrive right after issuing the loads raced with the refill
+                mbar_arrive(&raw_empty[slot]);
+            }
             if (++s == NS) {
                 s = 0;
                 ph_s ^= 1u;
@@ -536,11 +544,11 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) k2t_gram(const __grid_constan
                     const uint32_t idesc = umma_idesc(nn);
                     if (NPL == 1) {
                         const uint32_t blk = st + ks * BLK;
-                        umma_i8(tmem + n0, umma_desc(blk), umma_desc(blk + 4096 + n0 * 32), idesc, acc0);
+                        umma_i8(tmem + n0, umma_desc(blk + a_base), umma_desc(blk + 4096 + n0 * 32), idesc, acc0);
                     } else {
                         const uint32_t bp = st + (ks * 2 + 0) * BLK, bq = st + (ks * 2 + 1) * BLK;
-                        umma_i8(tmem + n0, umma_desc(bp), umma_desc(bq + 4096 + n0 * 32), idesc, acc0);
-                        umma_i8(tmem + n0, umma_desc(bq), umma_desc(bp + 4096 + n0 * 32), idesc, 1u);
+                        umma_i8(tmem + n0, umma_desc(bp + a_base), umma_desc(bq + 4096 + n0 * 32), idesc, acc0);
+                        umma_i8(tmem + n0, umma_desc(bq + a_base), umma_desc(bp + 4096 + n0 * 32), idesc, 1u);
                     }
                 }
             }
@@ -604,7 +612,7 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) k2t_gram(const __grid_constan
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 8) {
+    if (warp == GRAM_NPW) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(ncols) : "memory");
     }
@@ -828,7 +836,7 @@ int pg_k2t_pairs(pg_ctx* ctx, const K2TPlanes& ps, const int64_t* d_lo, const in
     }
     const dim3 grid((unsigned)groups.size(), (unsigned)nb);
     // shared memory: an operand ring of >= 2 stages, the rest (up to 8 slots) for the raw plane words
-    const int budget = 210 * 1024;
+    const int budget = 206 * 1024;
     auto geometry = [&](int npl, int& nstages, int& nraw) {
         const int stage = 2 * npl * (128 + nbmax) * 32, raw = npl * (128 + nbmax) * 8;
         nstages = std::max(2, std::min(3, (budget - 4 * raw) / stage));
@@ -836,7 +844,8 @@ int pg_k2t_pairs(pg_ctx* ctx, const K2TPlanes& ps, const int64_t* d_lo, const in
         if (const char* e = getenv("PG_K2T_NRAW")) nraw = std::max(1, std::min(nraw, atoi(e)));
         if (const char* e = getenv("PG_K2T_NSTAGES")) nstages = std::max(1, std::min(nstages, atoi(e)));
         // the epilogue's 8 transpose tiles (32 x 33 words each) reuse the operand ring
-        return std::max((size_t)nstages * stage, (size_t)8 * 32 * 33 * 4) + (size_t)nraw * raw;
+        // (+ 4 KB: the 128-row A tile of a diagonal group may reach past a B range of fewer than 128 rows)
+        return std::max((size_t)nstages * stage, (size_t)8 * 32 * 33 * 4) + (size_t)nraw * raw + 4096;
     };
     {
         const size_t smem = geometry(1, gp.nstages, gp.nraw);
