@@ -333,18 +333,29 @@ struct GramParams {
     const int64_t* win_hi;
     const int32_t* cps;         // NPL == 2: plane coordinate = cps[site - site_base]
     const GramGroup* groups;
+    int ngroups;
+    int nb;                     // windows
     int nbmax;                  // max nb_rows over the groups (shared-memory geometry)
+    int a_sep;                  // some group's A tile lies outside its B range: blocks carry a separate 128-row A region
     int nstages;                // operand ring depth
     int nraw;                   // raw plane-word ring depth
     int32_t* out;               // [nb][Hk][Hk]
 };
 
-constexpr int GRAM_PRODUCERS = 384;        // 12 expanding warps: three per scheduler, so that dependent ALU chains interleave
-constexpr int GRAM_NPW = GRAM_PRODUCERS / 32;
-constexpr int GRAM_THREADS = GRAM_PRODUCERS + 64;   // warps 0..NPW-1: expand, then (0-7) epilogue; then TMEM allocation + MMA issue; then TMA
+// Warp roles of the persistent CTA (one per SM):
+//   0..11  expand: three groups of four warps (one warp per scheduler each); group k owns the stages k, k+3, k+6, ... so
+//          that while one group waits (shared-memory loads, the proxy fence) the other two keep the ALUs busy
+//   12     TMEM allocation + MMA issue (one thread)
+//   13     TMA: plane words -> raw ring (one thread)
+//   14..21 epilogue: TMEM -> registers -> global; warps w and w+4 share TMEM lane quarter w % 4
+constexpr int GRAM_XGROUPS = 3;
+constexpr int GRAM_XWARPS = 4 * GRAM_XGROUPS;
+constexpr int GRAM_WARP_MMA = GRAM_XWARPS, GRAM_WARP_TMA = GRAM_XWARPS + 1, GRAM_WARP_EPI = GRAM_XWARPS + 2;
+constexpr int GRAM_EPI_WARPS = 8;
+constexpr int GRAM_THREADS = (GRAM_WARP_EPI + GRAM_EPI_WARPS) * 32;
 constexpr int GRAM_MAX_STAGES = 4;
 constexpr int GRAM_MAX_RAW = 8;            // depth of the raw plane-word ring (TMA runs this many chunks ahead)
-constexpr int GRAM_MAX_ITEMS = ((128 + 512) * 2 + GRAM_PRODUCERS - 1) / GRAM_PRODUCERS;    // plane words per thread and stage
+constexpr int GRAM_MAX_ITEMS = (128 + 512) * 2 / 128;    // plane words per expanding thread and stage
 
 // 16 bits -> 16 bytes of 0/1 (byte k = bit k)
 __device__ __forceinline__ uint4 expand16(uint32_t x) {
@@ -379,242 +390,304 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                  : "memory");
 }
 
-// Shared memory: [raw ring: nraw slots of NPL x (128 + nbmax) plane words, filled by 1-D TMA bulk copies]
-//                [operand ring: nstages stages of 2 K steps x NPL planes x (128 + nbmax) rows x 32 bytes]
+// position in a ring of `n` slots + the parity of the current pass; advances by small steps
+struct RingPos {
+    int s;
+    uint32_t ph;
+    __device__ __forceinline__ void advance(int delta, int n) {
+        s += delta;
+        while (s >= n) {
+            s -= n;
+            ph ^= 1u;
+        }
+    }
+};
+
+// work item j of this launch -> (window, group) and the chunk range of the window in plane coordinates
+struct GramItem {
+    GramGroup g;
+    int wb;
+    int64_t lo, hi, c_first;
+    int nst;
+};
+template <int NPL>
+__device__ __forceinline__ GramItem gram_item(const GramParams& gp, int64_t j) {
+    GramItem it;
+    it.wb = (int)(j / gp.ngroups);
+    it.g = gp.groups[j - (int64_t)it.wb * gp.ngroups];
+    it.lo = gp.win_lo[it.wb] - gp.site_base;
+    it.hi = gp.win_hi[it.wb] - gp.site_base;
+    if (NPL == 2) {
+        it.lo = gp.cps[it.lo];
+        it.hi = gp.cps[it.hi];
+    }
+    it.c_first = it.lo >> 6;
+    it.nst = (it.hi > it.lo) ? (int)(((it.hi - 1) >> 6) - it.c_first + 1) : 0;
+    return it;
+}
+
+// Shared memory: [raw ring: nraw slots of NPL x RROWS plane words, filled by 1-D TMA bulk copies]
+//                [operand ring: nstages stages of 2 K steps x NPL planes x RROWS rows x 32 bytes] [+ slack]
+//                [8 transpose tiles (32 x 17 words) of the epilogue warps]
+// RROWS = (128 rows of a separate A tile, only when some group needs one) + nbmax rows of the B range.
 template <int NPL>
 __global__ void __launch_bounds__(GRAM_THREADS, 1) k2t_gram(const __grid_constant__ GramParams gp) {
     extern __shared__ __align__(128) uint8_t gsm[];
     __shared__ __align__(8) uint64_t full[GRAM_MAX_STAGES], empty[GRAM_MAX_STAGES], raw_full[GRAM_MAX_RAW],
-        raw_empty[GRAM_MAX_RAW], done;
+        raw_empty[GRAM_MAX_RAW], tmem_full, tmem_empty;
     __shared__ uint32_t s_tmem;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const GramGroup g = gp.groups[blockIdx.x];
-    const int wb = blockIdx.y;
     const int NS = gp.nstages, RD = gp.nraw;
-    const int RROWS = 128 + gp.nbmax;                   // rows of one plane in a raw slot / operand block
+    const int AOFF = gp.a_sep ? 128 : 0;                // rows of the separate A region in front of the B rows
+    const int RROWS = AOFF + gp.nbmax;                  // rows of one plane in a raw slot / operand block
     const int RAW = NPL * RROWS * 8;                    // bytes of one raw slot
-    const int BLK = RROWS * 32;                         // one (K step, plane) block: A region 128 rows, then the B region
+    const int BLK = RROWS * 32;                         // one (K step, plane) operand block
     const int STAGE = 2 * NPL * BLK;
     uint8_t* const raw_base = gsm;
     uint8_t* const op_base = gsm + (size_t)RD * RAW;
+    uint32_t* const tr_base = reinterpret_cast<uint32_t*>(op_base + (size_t)NS * STAGE + 4096);
 
-    // window in plane coordinates
-    int64_t lo = gp.win_lo[wb] - gp.site_base, hi = gp.win_hi[wb] - gp.site_base;
-    if (NPL == 2) {
-        lo = gp.cps[lo];
-        hi = gp.cps[hi];
-    }
-    const int64_t c_first = lo >> 6;
-    const int nst = (hi > lo) ? (int)(((hi - 1) >> 6) - c_first + 1) : 0;
+    // contiguous range of work items (window-major, groups of a window adjacent) of this CTA
+    const int64_t n_items = (int64_t)gp.nb * gp.ngroups;
+    const int64_t j0 = n_items * blockIdx.x / gridDim.x, j1 = n_items * (blockIdx.x + 1) / gridDim.x;
 
-    uint32_t ncols = 32;
-    while ((int)ncols < g.nb_rows) ncols <<= 1;
-    const bool a_in_b = (g.a_row0 == g.b_row0);
-    const uint32_t a_base = a_in_b ? 4096u : 0u;       // byte offset of the A tile inside a (K step, plane) block
-    // rows of the A tile past the last plane row are never copied: they must read as zero
-    for (int i = tid; i < RD * RAW / 16; i += GRAM_THREADS) reinterpret_cast<uint4*>(raw_base)[i] = make_uint4(0u, 0u, 0u, 0u);
-    if (warp == GRAM_NPW) {
+    if (warp == GRAM_WARP_MMA) {
         if (lane == 0) {
             for (int s = 0; s < NS; ++s) {
-                mbar_init(&full[s], GRAM_NPW);            // one arrival per expanding warp
+                mbar_init(&full[s], 4);                 // the four warps of the expanding group that owns the stage
                 mbar_init(&empty[s], 1);
             }
             for (int s = 0; s < RD; ++s) {
                 mbar_init(&raw_full[s], 1);
-                mbar_init(&raw_empty[s], GRAM_NPW);
+                mbar_init(&raw_empty[s], 4);
             }
-            mbar_init(&done, 1);
+            mbar_init(&tmem_full, 1);
+            mbar_init(&tmem_empty, GRAM_EPI_WARPS);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(ncols)
-                     : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&s_tmem)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the zero fill above precedes the bulk copies
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = s_tmem;
 
-    if (warp == GRAM_NPW + 1) {
-        // ---------------- TMA: plane words of chunk c_first + it -> raw slot it % RD ----------------
+    if (warp == GRAM_WARP_TMA) {
+        // ---------------- TMA: plane words of every chunk of every item -> raw ring ----------------
         if (lane == 0) {
-            const int a_rows = min(128, gp.R - g.a_row0);
-            const uint32_t bytes_a = (uint32_t)a_rows * 8u, bytes_b = (uint32_t)g.nb_rows * 8u;
-            int slot = 0;
-            uint32_t ph = 0;
-            for (int it = 0; it < nst; ++it) {
-                if (it >= RD) mbar_wait(&raw_empty[slot], ph ^ 1u);
-                mbar_expect_tx(&raw_full[slot], NPL * ((a_in_b ? 0u : bytes_a) + bytes_b));
-                const int64_t chunk = c_first + it;
+            RingPos rp = {0, 0u};
+            int64_t gstage = 0;
+            for (int64_t j = j0; j < j1; ++j) {
+                const GramItem im = gram_item<NPL>(gp, j);
+                const bool a_in_b = (im.g.a_row0 == im.g.b_row0);
+                const int a_rows = a_in_b ? 0 : min(128, gp.R - im.g.a_row0);
+                const uint32_t bytes_a = (uint32_t)a_rows * 8u, bytes_b = (uint32_t)im.g.nb_rows * 8u;
+                for (int it = 0; it < im.nst; ++it, ++gstage) {
+                    if (gstage >= RD) mbar_wait(&raw_empty[rp.s], rp.ph ^ 1u);
+                    mbar_expect_tx(&raw_full[rp.s], NPL * (bytes_a + bytes_b));
+                    const int64_t chunk = im.c_first + it;
 #pragma unroll
-                for (int pl = 0; pl < NPL; ++pl) {
-                    const uint64_t* src = gp.plane + (chunk * NPL + pl) * gp.R;
-                    uint8_t* dst = raw_base + (size_t)slot * RAW + (size_t)pl * RROWS * 8;
-                    if (!a_in_b) bulk_g2s(dst, src + g.a_row0, bytes_a, &raw_full[slot]);
-                    bulk_g2s(dst + 128 * 8, src + g.b_row0, bytes_b, &raw_full[slot]);
-                }
-                if (++slot == RD) {
-                    slot = 0;
-                    ph ^= 1u;
+                    for (int pl = 0; pl < NPL; ++pl) {
+                        const uint64_t* src = gp.plane + (chunk * NPL + pl) * gp.R;
+                        uint8_t* dst = raw_base + (size_t)rp.s * RAW + (size_t)pl * RROWS * 8;
+                        if (bytes_a) bulk_g2s(dst, src + im.g.a_row0, bytes_a, &raw_full[rp.s]);
+                        bulk_g2s(dst + AOFF * 8, src + im.g.b_row0, bytes_b, &raw_full[rp.s]);
+                    }
+                    rp.advance(1, RD);
                 }
             }
         }
-    } else if (warp < GRAM_NPW) {
-        // ---------------- producers: plane words -> 0/1 bytes in the core-matrix layout ----------------
-        // a diagonal group (A tile = first rows of the B range) expands the B rows only: the A descriptor points into them
-        const int skip_a = a_in_b ? 128 : 0;
-        const int rows_tot = 128 + g.nb_rows - skip_a;
-        const int nitems = rows_tot * NPL;
-        int r_idx[GRAM_MAX_ITEMS], d_off[GRAM_MAX_ITEMS];          // raw word index / byte offset in a K-step block, -1: none
-#pragma unroll
-        for (int q = 0; q < GRAM_MAX_ITEMS; ++q) {
-            const int item = tid + q * GRAM_PRODUCERS;
-            r_idx[q] = -1;
-            d_off[q] = 0;
-            if (item < nitems) {
-                const int pl = (NPL == 2 && item >= rows_tot) ? 1 : 0;
-                const int rr = item - pl * rows_tot + skip_a;
-                const int x = (rr < 128) ? rr : rr - 128;
-                r_idx[q] = pl * RROWS + rr;
-                d_off[q] = pl * BLK + ((rr < 128) ? 0 : 4096) + (x >> 3) * 256 + (x & 7) * 16;
-            }
-        }
-        int s = 0, slot = 0;
-        uint32_t ph_s = 0, ph_r = 0;
-        for (int it = 0; it < nst; ++it) {
-            const int64_t chunk = c_first + it;
-            uint64_t mask = ~0ull;
-            {
-                const int64_t b0 = chunk << 6;
-                if (lo > b0) mask &= ~0ull << (int)(lo - b0);
-                if (hi < b0 + 64) mask &= ~0ull >> (int)(b0 + 64 - hi);
-            }
-            mbar_wait(&raw_full[slot], ph_r);
-            const uint64_t* rw = reinterpret_cast<const uint64_t*>(raw_base + (size_t)slot * RAW);
-            uint64_t v[GRAM_MAX_ITEMS];
-#pragma unroll
-            for (int q = 0; q < GRAM_MAX_ITEMS; ++q) v[q] = (r_idx[q] >= 0) ? (rw[r_idx[q]] & mask) : 0ull;
-            if (it >= NS) mbar_wait(&empty[s], ph_s ^ 1u);
-            uint8_t* sb = op_base + (size_t)s * STAGE;
+    } else if (warp < GRAM_XWARPS) {
+        // ---------------- expand: plane words -> 0/1 bytes in the core-matrix layout ----------------
+        // Group xg owns the global stages gs with gs % NS == xg, i.e. always operand slot xg, and (RD being a multiple of NS)
+        // always the same raw slots: every barrier a group waits on is one whose previous phase the same group consumed, so
+        // a parity wait can never alias with an older phase.  Groups >= NS stay idle (NS < 3 only when shared memory is short).
+        const int xg = warp >> 2, xt = tid & 127;          // expanding group, thread inside the group
+        const int RM = RD / NS;                            // raw slots of this group: xg, xg + NS, ...
+        int n_done = 0;                                    // stages this group has processed: stage n is gs = xg + n NS
+        int rm = 0;                                        // n_done % RM
+        uint32_t rph = 0;                                  // (n_done / RM) & 1
+        int64_t gbase = 0;                                 // global stage index of the item's first stage
+        for (int64_t j = j0; j < j1 && xg < NS; ++j) {
+            const GramItem im = gram_item<NPL>(gp, j);
+            const bool a_in_b = (im.g.a_row0 == im.g.b_row0);
+            // rows expanded per plane: [separate A tile (128 rows)] + B range
+            const int skip_a = a_in_b ? 128 : 0;
+            const int rows_tot = 128 + im.g.nb_rows - skip_a;
+            const int nitems = rows_tot * NPL;
+            int r_idx[GRAM_MAX_ITEMS], d_off[GRAM_MAX_ITEMS];      // raw word index (-1 none, -2 zero row) / byte offset in a block
 #pragma unroll
             for (int q = 0; q < GRAM_MAX_ITEMS; ++q) {
-                if (r_idx[q] >= 0) {
-                    const uint32_t wlo = (uint32_t)v[q], whi = (uint32_t)(v[q] >> 32);
-                    uint8_t* d0 = sb + d_off[q];
-                    uint8_t* d1 = d0 + NPL * BLK;
-                    *reinterpret_cast<uint4*>(d0) = expand16(wlo & 0xffffu);
-                    *reinterpret_cast<uint4*>(d0 + 128) = expand16(wlo >> 16);
-                    *reinterpret_cast<uint4*>(d1) = expand16(whi & 0xffffu);
-                    *reinterpret_cast<uint4*>(d1 + 128) = expand16(whi >> 16);
+                const int item = xt + q * 128;
+                r_idx[q] = -1;
+                d_off[q] = 0;
+                if (item < nitems) {
+                    const int pl = (NPL == 2 && item >= rows_tot) ? 1 : 0;
+                    const int rr = item - pl * rows_tot + skip_a;          // < 128: row of the separate A tile
+                    const int x = (rr < 128) ? rr : rr - 128;
+                    const int row = (rr < 128) ? x : AOFF + x;             // row inside the block / raw slot
+                    r_idx[q] = (rr < 128 && im.g.a_row0 + x >= gp.R) ? -2 : pl * RROWS + row;
+                    d_off[q] = pl * BLK + (row >> 3) * 256 + (row & 7) * 16;
                 }
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(&full[s]);
-                // released only now: the stores above consumed the words, so the loads from the slot have completed before
-                // the TMA (async proxy) may overwrite it — an arrive right after issuing the loads raced with the refill
-                mbar_arrive(&raw_empty[slot]);
-            }
-            if (++s == NS) {
-                s = 0;
-                ph_s ^= 1u;
-            }
-            if (++slot == RD) {
-                slot = 0;
-                ph_r ^= 1u;
-            }
-        }
-    } else if (lane == 0) {
-        // ---------------- MMA issue (one thread) ----------------
-        const uint32_t sbase = smem_u32(op_base);
-        int s = 0;
-        uint32_t ph = 0;
-        for (int it = 0; it < nst; ++it) {
-            mbar_wait(&full[s], ph);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t st = sbase + (uint32_t)s * STAGE;
+            // first local stage of this group: (gbase + it) % NS == xg
+            int it = (int)(((int64_t)xg - gbase % NS + NS) % NS);
+            for (; it < im.nst; it += NS) {
+                const int rslot = xg + NS * rm;
+                const int64_t chunk = im.c_first + it;
+                uint64_t mask = ~0ull;
+                {
+                    const int64_t b0 = chunk << 6;
+                    if (im.lo > b0) mask &= ~0ull << (int)(im.lo - b0);
+                    if (im.hi < b0 + 64) mask &= ~0ull >> (int)(b0 + 64 - im.hi);
+                }
+                mbar_wait(&raw_full[rslot], rph);
+                const uint64_t* rw = reinterpret_cast<const uint64_t*>(raw_base + (size_t)rslot * RAW);
+                uint64_t v[GRAM_MAX_ITEMS];
 #pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-                const uint32_t acc0 = (it > 0 || ks > 0) ? 1u : 0u;
-                for (int n0 = 0; n0 < g.nb_rows; n0 += 256) {
-                    const int nn = min(256, g.nb_rows - n0);
-                    const uint32_t idesc = umma_idesc(nn);
-                    if (NPL == 1) {
-                        const uint32_t blk = st + ks * BLK;
-                        umma_i8(tmem + n0, umma_desc(blk + a_base), umma_desc(blk + 4096 + n0 * 32), idesc, acc0);
-                    } else {
-                        const uint32_t bp = st + (ks * 2 + 0) * BLK, bq = st + (ks * 2 + 1) * BLK;
-                        umma_i8(tmem + n0, umma_desc(bp + a_base), umma_desc(bq + 4096 + n0 * 32), idesc, acc0);
-                        umma_i8(tmem + n0, umma_desc(bq + a_base), umma_desc(bp + 4096 + n0 * 32), idesc, 1u);
+                for (int q = 0; q < GRAM_MAX_ITEMS; ++q) v[q] = (r_idx[q] >= 0) ? (rw[r_idx[q]] & mask) : 0ull;
+                if (n_done > 0) mbar_wait(&empty[xg], (uint32_t)((n_done - 1) & 1));
+                uint8_t* sb = op_base + (size_t)xg * STAGE;
+#pragma unroll
+                for (int q = 0; q < GRAM_MAX_ITEMS; ++q) {
+                    if (q * 128 < nitems) {                 // warp-uniform: no instructions for item slots nobody uses
+                        if (r_idx[q] != -1) {
+                            const uint32_t wlo = (uint32_t)v[q], whi = (uint32_t)(v[q] >> 32);
+                            uint8_t* d0 = sb + d_off[q];
+                            uint8_t* d1 = d0 + NPL * BLK;
+                            *reinterpret_cast<uint4*>(d0) = expand16(wlo & 0xffffu);
+                            *reinterpret_cast<uint4*>(d0 + 128) = expand16(wlo >> 16);
+                            *reinterpret_cast<uint4*>(d1) = expand16(whi & 0xffffu);
+                            *reinterpret_cast<uint4*>(d1 + 128) = expand16(whi >> 16);
+                        }
                     }
                 }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(&full[xg]);
+                    // released only now: the stores above consumed the words, so the loads from the slot have completed
+                    // before the TMA (async proxy) may overwrite it — an arrive right after issuing the loads raced with
+                    // the refill
+                    mbar_arrive(&raw_empty[rslot]);
+                }
+                ++n_done;
+                if (++rm == RM) {
+                    rm = 0;
+                    rph ^= 1u;
+                }
             }
-            umma_commit(&empty[s]);       // arrives when the MMAs above have read the stage
-            if (++s == NS) {
-                s = 0;
-                ph ^= 1u;
+            gbase += im.nst;
+        }
+    } else if (warp == GRAM_WARP_MMA) {
+        // ---------------- MMA issue (one thread) ----------------
+        if (lane == 0) {
+            const uint32_t sbase = smem_u32(op_base);
+            RingPos sp = {0, 0u};
+            int64_t k = 0;                                  // items done by this CTA
+            for (int64_t j = j0; j < j1; ++j, ++k) {
+                const GramItem im = gram_item<NPL>(gp, j);
+                const uint32_t a_base = (im.g.a_row0 == im.g.b_row0) ? (uint32_t)AOFF * 32u : 0u;   // A tile inside the B rows
+                const uint32_t b_base = (uint32_t)AOFF * 32u;
+                if (k > 0) {                                // the epilogue must have drained the previous accumulators
+                    mbar_wait(&tmem_empty, (uint32_t)((k - 1) & 1));
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
+                for (int it = 0; it < im.nst; ++it) {
+                    mbar_wait(&full[sp.s], sp.ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t st = sbase + (uint32_t)sp.s * STAGE;
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks) {
+                        const uint32_t acc0 = (it > 0 || ks > 0) ? 1u : 0u;
+                        for (int n0 = 0; n0 < im.g.nb_rows; n0 += 256) {
+                            const int nn = min(256, im.g.nb_rows - n0);
+                            const uint32_t idesc = umma_idesc(nn);
+                            if (NPL == 1) {
+                                const uint32_t blk = st + ks * BLK;
+                                umma_i8(tmem + n0, umma_desc(blk + a_base), umma_desc(blk + b_base + n0 * 32), idesc, acc0);
+                            } else {
+                                const uint32_t bp = st + (ks * 2 + 0) * BLK, bq = st + (ks * 2 + 1) * BLK;
+                                umma_i8(tmem + n0, umma_desc(bp + a_base), umma_desc(bq + b_base + n0 * 32), idesc, acc0);
+                                umma_i8(tmem + n0, umma_desc(bq + a_base), umma_desc(bp + b_base + n0 * 32), idesc, 1u);
+                            }
+                        }
+                    }
+                    umma_commit(&empty[sp.s]);      // arrives when the MMAs above have read the stage
+                    sp.advance(1, NS);
+                }
+                umma_commit(&tmem_full);            // arrives when every MMA of the item has completed
             }
         }
-        umma_commit(&done);
-    }
-
-    if (warp < 8) {
+    } else {
         // ---------------- epilogue: TMEM -> registers -> symmetric int32 matrix ----------------
-        if (nst > 0) {
-            mbar_wait(&done, 0u);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        }
-        // Lane = matrix row in TMEM (warp w may touch lanes 32 (w % 4) ..): warps w and w + 4 take alternate 32-column
-        // blocks of the same rows.  The mirror element [j][i] is written straight from the registers (lanes run along i:
-        // coalesced); the direct element [i][j] goes through a 32 x 32 transpose in shared memory (the operand ring is idle
-        // now) so that lanes run along j as well.
+        // Lane = matrix row in TMEM (a warp may touch lanes 32 (warp % 4) ..): the two warps of a quarter take alternate
+        // 32-column blocks.  The mirror element [j][i] is written straight from the registers (lanes run along i: coalesced);
+        // the direct element [i][j] goes through a 32 x 32 transpose in shared memory so that lanes run along j as well.
+        const int ew = warp - GRAM_WARP_EPI;
         const int qd = warp & 3;
-        const int i0 = g.a_row0 + qd * 32;
-        int32_t* o = gp.out + (size_t)wb * gp.Hk * gp.Hk;
-        uint32_t* tr = reinterpret_cast<uint32_t*>(op_base) + warp * (32 * 33);
-        for (int c0 = (warp >> 2) * 32; c0 < g.nb_rows; c0 += 64) {
-            uint32_t v[32];
-            if (nst > 0) {
-                const uint32_t taddr = tmem + ((uint32_t)(qd * 32) << 16) + (uint32_t)c0;
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,"
-                    "%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-                      "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-                      "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-                      "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                    : "r"(taddr)
-                    : "memory");
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            } else {
-#pragma unroll
-                for (int e = 0; e < 32; ++e) v[e] = 0u;
+        uint32_t* tr = tr_base + ew * (32 * 17);
+        int64_t k = 0;
+        for (int64_t j = j0; j < j1; ++j, ++k) {
+            const GramItem im = gram_item<NPL>(gp, j);
+            mbar_wait(&tmem_full, (uint32_t)(k & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int i0 = im.g.a_row0 + qd * 32;
+            int32_t* o = gp.out + (size_t)im.wb * gp.Hk * gp.Hk;
+            const int cfirst = (ew >> 2) * 16;
+            int c_last = cfirst;                            // last block this warp reads
+            while (c_last + 32 < im.g.nb_rows) c_last += 32;
+            if (cfirst >= im.g.nb_rows) {                   // nothing to read: release the accumulators right away
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty);
             }
-            const int i = i0 + lane;
+            for (int c0 = cfirst; c0 < im.g.nb_rows; c0 += 32) {
+                uint32_t v[16];
+                if (im.nst > 0) {
+                    const uint32_t taddr = tmem + ((uint32_t)(qd * 32) << 16) + (uint32_t)c0;
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                        : "r"(taddr)
+                        : "memory");
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                } else {
 #pragma unroll
-            for (int e = 0; e < 32; ++e) {
-                const int j = g.b_row0 + c0 + e;
-                if (i < gp.Hk && j < gp.Hk) o[(size_t)j * gp.Hk + i] = (int32_t)v[e];
-                tr[lane * 33 + e] = v[e];
-            }
-            __syncwarp();
-            const int j = g.b_row0 + c0 + lane;
+                    for (int e = 0; e < 16; ++e) v[e] = 0u;
+                }
+                if (c0 == c_last) {                         // last read of the accumulators: the next item's MMAs may start
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty);
+                }
+                const int i = i0 + lane;
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    const int jj = im.g.b_row0 + c0 + e;
+                    if (i < gp.Hk && jj < gp.Hk) o[(size_t)jj * gp.Hk + i] = (int32_t)v[e];
+                    tr[lane * 17 + e] = v[e];
+                }
+                __syncwarp();
+                const int jj = im.g.b_row0 + c0 + (lane & 15);          // two rows per instruction, 16 columns each
 #pragma unroll 8
-            for (int r = 0; r < 32; ++r) {
-                const uint32_t x = tr[r * 33 + lane];
-                if (i0 + r < gp.Hk && j < gp.Hk) o[(size_t)(i0 + r) * gp.Hk + j] = (int32_t)x;
+                for (int r2 = 0; r2 < 16; ++r2) {
+                    const int r = 2 * r2 + (lane >> 4);
+                    const uint32_t x = tr[r * 17 + (lane & 15)];
+                    if (i0 + r < gp.Hk && jj < gp.Hk) o[(size_t)(i0 + r) * gp.Hk + jj] = (int32_t)x;
+                }
+                __syncwarp();
             }
-            __syncwarp();
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == GRAM_NPW) {
+    if (warp == GRAM_WARP_MMA) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(ncols) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
     }
 }
 
@@ -807,7 +880,7 @@ int pg_k2t_pairs(pg_ctx* ctx, const K2TPlanes& ps, const int64_t* d_lo, const in
                  int32_t* d_n) {
     // tile groups: one 128-row A tile x up to 512 B rows (TMEM has 512 int32 columns per SM)
     std::vector<GramGroup> groups;
-    int nbmax = 16;
+    int nbmax = 16, a_sep = 0;
     for (int a0 = 0; a0 < ps.R; a0 += 128)
         for (int c = a0; c < ps.R; c += 512) {
             GramGroup g;
@@ -816,6 +889,7 @@ int pg_k2t_pairs(pg_ctx* ctx, const K2TPlanes& ps, const int64_t* d_lo, const in
             g.nb_rows = std::min(512, ps.R - c);
             g.pad = 0;
             nbmax = std::max(nbmax, g.nb_rows);
+            if (c != a0) a_sep = 1;
             groups.push_back(g);
         }
     PG_TRY(ctx->misc4.ensure(groups.size() * sizeof(GramGroup) + 64));
@@ -827,25 +901,33 @@ int pg_k2t_pairs(pg_ctx* ctx, const K2TPlanes& ps, const int64_t* d_lo, const in
     gp.win_lo = d_lo;
     gp.win_hi = d_hi;
     gp.groups = (const GramGroup*)ctx->misc4.p;
+    gp.ngroups = (int)groups.size();
+    gp.nb = nb;
     gp.nbmax = nbmax;
+    gp.a_sep = a_sep;
     static bool attr_dev[64] = {};
     if (!attr_dev[ctx->device & 63]) {
-        PG_CUDA(cudaFuncSetAttribute(k2t_gram<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        PG_CUDA(cudaFuncSetAttribute(k2t_gram<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        PG_CUDA(cudaFuncSetAttribute(k2t_gram<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+        PG_CUDA(cudaFuncSetAttribute(k2t_gram<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
         attr_dev[ctx->device & 63] = true;
     }
-    const dim3 grid((unsigned)groups.size(), (unsigned)nb);
-    // shared memory: an operand ring of >= 2 stages, the rest (up to 8 slots) for the raw plane words
-    const int budget = 206 * 1024;
+    // persistent CTAs: one per SM, each works through a contiguous range of (window, group) items
+    const int64_t n_items = (int64_t)nb * (int64_t)groups.size();
+    const unsigned grid = (unsigned)std::min<int64_t>(n_items, ctx->sm_count);
+    // shared memory: transpose tiles of the epilogue + an operand ring of (ideally) one stage per expanding group + the raw
+    // plane-word ring (up to 8 slots) + 4 KB slack (the 128-row A tile of a diagonal group may reach past a short B range)
+    const int budget = 224 * 1024;
+    const int fixed = GRAM_EPI_WARPS * 32 * 17 * 4 + 4096;
     auto geometry = [&](int npl, int& nstages, int& nraw) {
-        const int stage = 2 * npl * (128 + nbmax) * 32, raw = npl * (128 + nbmax) * 8;
-        nstages = std::max(2, std::min(3, (budget - 4 * raw) / stage));
-        nraw = std::max(2, std::min(GRAM_MAX_RAW, (budget - nstages * stage) / raw));
-        if (const char* e = getenv("PG_K2T_NRAW")) nraw = std::max(1, std::min(nraw, atoi(e)));
+        const int rrows = (a_sep ? 128 : 0) + nbmax;
+        const int stage = 2 * npl * rrows * 32, raw = npl * rrows * 8;
+        nstages = std::max(2, std::min(GRAM_XGROUPS, (budget - fixed - 3 * raw) / stage));
         if (const char* e = getenv("PG_K2T_NSTAGES")) nstages = std::max(1, std::min(nstages, atoi(e)));
-        // the epilogue's 8 transpose tiles (32 x 33 words each) reuse the operand ring
-        // (+ 4 KB: the 128-row A tile of a diagonal group may reach past a B range of fewer than 128 rows)
-        return std::max((size_t)nstages * stage, (size_t)8 * 32 * 33 * 4) + (size_t)nraw * raw + 4096;
+        // one expanding group per operand stage; raw slots in multiples of that, so that every slot has ONE consumer group
+        int mult = std::min(GRAM_MAX_RAW / nstages, (budget - fixed - nstages * stage) / (raw * nstages));
+        if (const char* e = getenv("PG_K2T_NRAW")) mult = std::min(mult, atoi(e));
+        nraw = std::max(1, mult) * nstages;
+        return (size_t)nstages * stage + (size_t)nraw * raw + fixed;
     };
     {
         const size_t smem = geometry(1, gp.nstages, gp.nraw);
