@@ -346,6 +346,11 @@ __global__ void __launch_bounds__(256) k2_verify_rows(const uint32_t* __restrict
 // ------------------------------------------------------------------------------------------------
 // epilogues
 // ------------------------------------------------------------------------------------------------
+// The pair matrices are symmetric; the tensor-core kernel writes the upper triangle only (i <= j), so every read goes
+// through (min, max).
+__device__ __forceinline__ size_t upper_idx(int i, int j, int ld) {
+    return (i <= j) ? (size_t)i * ld + j : (size_t)j * ld + i;
+}
 __device__ __forceinline__ double nan_d() { return __longlong_as_double(0x7ff8000000000000ll); }
 
 // deterministic block-wide sum: butterfly inside warps, then warp 0 adds the 8 partials in order
@@ -421,9 +426,9 @@ __global__ void __launch_bounds__(256) k2_popgen_epi_blocks(const __grid_constan
     for (int idx = threadIdx.x; idx < total; idx += 256) {
         const int i = r0 + idx / nc, j = c0 + idx % nc;
         if (X == Y && j <= i) continue;
-        const int nij = N[(size_t)ep.mid[i] * ep.Hm + ep.mid[j]];
+        const int nij = N[upper_idx(ep.mid[i], ep.mid[j], ep.Hm)];
         if (nij == 0 || (ep.min_sites > 0 && nij < ep.min_sites)) continue;   // nan entries
-        s += (double)D[(size_t)i * ep.Hk + j] / (double)nij;
+        s += (double)D[upper_idx(i, j, ep.Hk)] / (double)nij;
         c += 1;
     }
     block_sum(s, c, sh_s, sh_c);
@@ -498,10 +503,10 @@ __global__ void __launch_bounds__(256) k2_ind_epi(const __grid_constant__ IndEpi
                     if (!ep.include_same || ep.min_sites > 0) continue;   // diagonal = nan (genomics.py:940; 937-938 masks it too)
                     d = 0.0;                                 // distMatrix leaves 0 on the diagonal (908)
                 } else {
-                    const int nij = N[(size_t)ep.mid[i] * ep.Hm + ep.mid[j]];
+                    const int nij = N[upper_idx(ep.mid[i], ep.mid[j], ep.Hm)];
                     if (nij == 0) continue;                  // np.mean of an empty array = nan
                     if (ep.min_sites > 0 && nij < ep.min_sites) continue;
-                    d = (double)D[(size_t)i * ep.Hk + j] / (double)nij;
+                    d = (double)D[upper_idx(i, j, ep.Hk)] / (double)nij;
                 }
                 s += d;
                 c += 1;
@@ -630,9 +635,9 @@ __global__ void __launch_bounds__(256) k2_hap_epi(const __grid_constant__ HapEpi
             // distMatrix leaves 0 on the diagonal; a minSites mask also removes it (pairNonNan's diagonal is 0, 1043)
             if (i == j) m = !ep.diag_nan && ep.min_sites <= 0 && (0.0 <= ep.max_dist);
             else {
-                const int nij = Nn[(size_t)ep.mid[r0 + i] * ep.Hm + ep.mid[r0 + j]];
+                const int nij = Nn[upper_idx(ep.mid[r0 + i], ep.mid[r0 + j], ep.Hm)];
                 m = nij > 0 && !(ep.min_sites > 0 && nij < ep.min_sites) &&
-                    ((double)D[(size_t)(r0 + i) * ep.Hk + r0 + j] / (double)nij <= ep.max_dist);
+                    ((double)D[upper_idx(r0 + i, r0 + j, ep.Hk)] / (double)nij <= ep.max_dist);
             }
             bits |= (m ? 1u : 0u) << b;
         }
@@ -726,7 +731,8 @@ __global__ void __launch_bounds__(256) k2_reduce_pairs(const int32_t* __restrict
     const size_t HH = (size_t)Hk * Hk, MM = (size_t)Hm * Hm;
     for (size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x; idx < HH; idx += (size_t)gridDim.x * 256) {
         const int i = (int)(idx / Hk), j = (int)(idx % Hk);
-        const size_t nidx = (size_t)mid[i] * Hm + mid[j];
+        if (j < i) continue;                                 // upper triangle only (see upper_idx)
+        const size_t nidx = upper_idx(mid[i], mid[j], Hm);
         long long sd = 0, sn = 0;
         for (int b = 0; b < nb; ++b) {
             sd += diff[(size_t)b * HH + idx];
@@ -758,9 +764,9 @@ __global__ void __launch_bounds__(256) k2_ind_epi64(const __grid_constant__ IndE
                     if (!ep.include_same) continue;
                     d = 0.0;
                 } else {
-                    const long long nij = ep.acc[HH + (size_t)i * ep.Hk + j];
+                    const long long nij = ep.acc[HH + upper_idx(i, j, ep.Hk)];
                     if (nij == 0) continue;
-                    d = (double)ep.acc[(size_t)i * ep.Hk + j] / (double)nij;
+                    d = (double)ep.acc[upper_idx(i, j, ep.Hk)] / (double)nij;
                 }
                 s += d;
                 c += 1;
@@ -1131,7 +1137,11 @@ extern "C" int pg_pair_counts(pg_ctx* ctx, int64_t window, int32_t* diff, int32_
     PG_CUDA(cudaMemcpyAsync(nu.data(), d_n, nu.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
     PG_CUDA(cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < H; ++i)
-        for (int j = 0; j < H; ++j) n[(size_t)i * H + j] = nu[(size_t)ps.mid[i] * ps.Hm + ps.mid[j]];
+        for (int j = 0; j < H; ++j) {
+            const int a = std::min(ps.mid[i], ps.mid[j]), b = std::max(ps.mid[i], ps.mid[j]);
+            n[(size_t)i * H + j] = nu[(size_t)a * ps.Hm + b];
+            if (j < i) diff[(size_t)i * H + j] = diff[(size_t)j * H + i];      // only the upper triangle is computed
+        }
     return PG_OK;
 }
 

@@ -339,7 +339,7 @@ struct GramParams {
     int a_sep;                  // some group's A tile lies outside its B range: blocks carry a separate 128-row A region
     int nstages;                // operand ring depth
     int nraw;                   // raw plane-word ring depth
-    int32_t* out;               // [nb][Hk][Hk]
+    int32_t* out;               // [nb][Hk][Hk], upper triangle (i <= j) only
 };
 
 // Warp roles of the persistent CTA (one per SM):
@@ -584,13 +584,24 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) k2t_gram(const __grid_constan
     } else if (warp == GRAM_WARP_MMA) {
         // ---------------- MMA issue (one thread) ----------------
         if (lane == 0) {
-            const uint32_t sbase = smem_u32(op_base);
+            // The issuing thread is a serial instruction stream: everything that does not change per stage is hoisted, a
+            // descriptor is one 32-bit add (the shared-memory address field sits in the low word), and the MMAs of a stage are
+            // straight-line code.  (A first version rebuilt descriptors and loop bounds per MMA: ~450 instructions and
+            // ~1000 cycles per stage — the issuing thread, not the tensor pipe, set the pace.)
+            const uint32_t sbase16 = smem_u32(op_base) >> 4;
+            const uint32_t DLO = (128u >> 4) << 16;                       // LBO
+            const uint32_t DHI = (256u >> 4) | (1u << 14);                // SBO | descriptor version 1
+            const uint32_t stage16 = (uint32_t)STAGE >> 4, blk16 = (uint32_t)BLK >> 4;
+            auto D = [&](uint32_t a16) { return ((uint64_t)DHI << 32) | (uint64_t)(DLO + a16); };
             RingPos sp = {0, 0u};
             int64_t k = 0;                                  // items done by this CTA
             for (int64_t j = j0; j < j1; ++j, ++k) {
                 const GramItem im = gram_item<NPL>(gp, j);
-                const uint32_t a_base = (im.g.a_row0 == im.g.b_row0) ? (uint32_t)AOFF * 32u : 0u;   // A tile inside the B rows
-                const uint32_t b_base = (uint32_t)AOFF * 32u;
+                // A tile inside the B rows for a diagonal group, else the separate A region in front of them
+                const uint32_t a16 = (im.g.a_row0 == im.g.b_row0) ? (uint32_t)AOFF * 2u : 0u;
+                const uint32_t b16 = (uint32_t)AOFF * 2u;                 // 32 bytes per row = 2 units of 16 bytes
+                const int n_a = min(256, im.g.nb_rows), n_b = im.g.nb_rows - n_a;
+                const uint32_t id_a = umma_idesc(n_a), id_b = umma_idesc(n_b > 0 ? n_b : 16);
                 if (k > 0) {                                // the epilogue must have drained the previous accumulators
                     mbar_wait(&tmem_empty, (uint32_t)((k - 1) & 1));
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -598,20 +609,21 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) k2t_gram(const __grid_constan
                 for (int it = 0; it < im.nst; ++it) {
                     mbar_wait(&full[sp.s], sp.ph);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t st = sbase + (uint32_t)sp.s * STAGE;
+                    const uint32_t st16 = sbase16 + (uint32_t)sp.s * stage16;
 #pragma unroll
                     for (int ks = 0; ks < 2; ++ks) {
                         const uint32_t acc0 = (it > 0 || ks > 0) ? 1u : 0u;
-                        for (int n0 = 0; n0 < im.g.nb_rows; n0 += 256) {
-                            const int nn = min(256, im.g.nb_rows - n0);
-                            const uint32_t idesc = umma_idesc(nn);
-                            if (NPL == 1) {
-                                const uint32_t blk = st + ks * BLK;
-                                umma_i8(tmem + n0, umma_desc(blk + a_base), umma_desc(blk + b_base + n0 * 32), idesc, acc0);
-                            } else {
-                                const uint32_t bp = st + (ks * 2 + 0) * BLK, bq = st + (ks * 2 + 1) * BLK;
-                                umma_i8(tmem + n0, umma_desc(bp + a_base), umma_desc(bq + b_base + n0 * 32), idesc, acc0);
-                                umma_i8(tmem + n0, umma_desc(bq + a_base), umma_desc(bp + b_base + n0 * 32), idesc, 1u);
+                        if (NPL == 1) {
+                            const uint32_t blk = st16 + ks * blk16;
+                            umma_i8(tmem, D(blk + a16), D(blk + b16), id_a, acc0);
+                            if (n_b > 0) umma_i8(tmem + 256, D(blk + a16), D(blk + b16 + 512), id_b, acc0);
+                        } else {
+                            const uint32_t bp = st16 + (ks * 2) * blk16, bq = bp + blk16;
+                            umma_i8(tmem, D(bp + a16), D(bq + b16), id_a, acc0);
+                            umma_i8(tmem, D(bq + a16), D(bp + b16), id_a, 1u);
+                            if (n_b > 0) {
+                                umma_i8(tmem + 256, D(bp + a16), D(bq + b16 + 512), id_b, acc0);
+                                umma_i8(tmem + 256, D(bq + a16), D(bp + b16 + 512), id_b, 1u);
                             }
                         }
                     }
@@ -624,8 +636,9 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) k2t_gram(const __grid_constan
     } else {
         // ---------------- epilogue: TMEM -> registers -> symmetric int32 matrix ----------------
         // Lane = matrix row in TMEM (a warp may touch lanes 32 (warp % 4) ..): the two warps of a quarter take alternate
-        // 32-column blocks.  The mirror element [j][i] is written straight from the registers (lanes run along i: coalesced);
-        // the direct element [i][j] goes through a 32 x 32 transpose in shared memory so that lanes run along j as well.
+        // 16-column blocks.  Only [i][j] with i in the A tile and j in the B range is written — the upper triangle of the
+        // symmetric matrix (readers index it through (min, max)); a 32 x 16 transpose in shared memory makes the lanes run
+        // along j (coalesced rows).
         const int ew = warp - GRAM_WARP_EPI;
         const int qd = warp & 3;
         uint32_t* tr = tr_base + ew * (32 * 17);
@@ -664,13 +677,8 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) k2t_gram(const __grid_constan
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tmem_empty);
                 }
-                const int i = i0 + lane;
 #pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    const int jj = im.g.b_row0 + c0 + e;
-                    if (i < gp.Hk && jj < gp.Hk) o[(size_t)jj * gp.Hk + i] = (int32_t)v[e];
-                    tr[lane * 17 + e] = v[e];
-                }
+                for (int e = 0; e < 16; ++e) tr[lane * 17 + e] = v[e];
                 __syncwarp();
                 const int jj = im.g.b_row0 + c0 + (lane & 15);          // two rows per instruction, 16 columns each
 #pragma unroll 8
