@@ -422,15 +422,19 @@ __global__ void __launch_bounds__(256) k2_popgen_epi_blocks(const __grid_constan
     const int nr = r1 - r0, nc = c1 - c0;
     double s = 0.0;
     long long c = 0;
-    const int total = nr * nc;
-    for (int idx = threadIdx.x; idx < total; idx += 256) {
-        const int i = r0 + idx / nc, j = c0 + idx % nc;
-        if (X == Y && j <= i) continue;
-        const int nij = N[upper_idx(ep.mid[i], ep.mid[j], ep.Hm)];
-        if (nij == 0 || (ep.min_sites > 0 && nij < ep.min_sites)) continue;   // nan entries
-        s += (double)D[upper_idx(i, j, ep.Hk)] / (double)nij;
-        c += 1;
+    // a warp walks one matrix row at a time, lanes along the columns (coalesced, no integer division per element)
+    for (int i = r0 + (threadIdx.x >> 5); i < r1; i += 8) {
+        const int mi = ep.mid[i];
+        const int32_t* Drow = D + (size_t)i * ep.Hk;
+        for (int j = ((X == Y) ? i + 1 : c0) + (threadIdx.x & 31); j < c1; j += 32) {
+            const int nij = N[upper_idx(mi, ep.mid[j], ep.Hm)];
+            if (nij == 0 || (ep.min_sites > 0 && nij < ep.min_sites)) continue;   // nan entries
+            s += (double)Drow[j] / (double)nij;
+            c += 1;
+        }
     }
+    (void)nr;
+    (void)nc;
     block_sum(s, c, sh_s, sh_c);
     if (threadIdx.x == 0) {
         const int nblk = P * (P + 1) / 2;
@@ -800,10 +804,10 @@ int build_planes(pg_ctx* ctx, const std::vector<int32_t>& order, int64_t lo, int
         ps.tensor = true;
         ps.Hk = Hk;
         ps.site_base = ps.t.site_base;
-        ps.Hm = Hk;                                // n_ij is computed for every haplotype pair: mask id = row
+        ps.Hm = ps.t.Hm;                           // mask rows: one per row, or one per sample (see K2TPlanes)
         ps.mid.resize(Hk);
-        for (int r = 0; r < Hk; ++r) ps.mid[r] = r;
-        ps.d_mid = ps.t.d_iota;
+        for (int r = 0; r < Hk; ++r) ps.mid[r] = (ps.t.Hm == Hk) ? r : r / 2;
+        ps.d_mid = ps.t.d_mid;
         return PG_OK;
     }
     const int64_t sb = lo & ~(int64_t)(BP_SITES - 1);

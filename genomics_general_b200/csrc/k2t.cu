@@ -72,6 +72,9 @@ struct VcParams {
     int R, Hk;
     uint8_t* cls;               // [nchunk*64] presence nibble (bit a: allele a present among the used haplotypes)
     int32_t* chunk_tot;         // [nchunk] pseudo-sites of the chunk
+    uint64_t* vpair;            // [nchunk][R2] valid words of the even rows (nullptr: not wanted)
+    int R2;
+    int32_t* pair_flag;         // set to 1 when some row 2k and 2k+1 differ in a valid word
 };
 
 // one-hot bytes (bits 0,2,4,6) of two sites -> per byte: bit0 = site0 valid, bit1 = site1 valid
@@ -135,6 +138,7 @@ __global__ void __launch_bounds__(256) k2t_valid_class(const __grid_constant__ V
         if (lane == 0) s_wtot[o] = ps;
         __syncthreads();
         const uint8_t* st8 = reinterpret_cast<const uint8_t*>(vc_st);
+        uint64_t* s_v = reinterpret_cast<uint64_t*>(vc_st + 8 * p.pw);      // [R] this chunk's words by plane row
         for (int c = tid; c < p.pitch; c += 256) {
             const int r = p.c2r[c];
             if (r < 0) continue;
@@ -142,8 +146,24 @@ __global__ void __launch_bounds__(256) k2t_valid_class(const __grid_constant__ V
 #pragma unroll
             for (int q = 0; q < 8; ++q) v |= (uint64_t)st8[(size_t)q * p.pitch + c] << (8 * q);
             p.vplane[chunk * p.R + r] = v;
+            s_v[r] = v;
         }
         for (int r = p.Hk + tid; r < p.R; r += 256) p.vplane[chunk * p.R + r] = 0ull;
+        if (p.vpair) {
+            // Missingness is usually per genotype: the two haplotypes of a sample then share their valid words, n_ij needs
+            // one row per sample, and the co-valid Gram shrinks 4x.  Checked here for every word; the flag decides later.
+            __syncthreads();
+            bool bad = false;
+            for (int k2 = tid; k2 < p.R2; k2 += 256) {
+                uint64_t a = 0;
+                if (2 * k2 + 1 < p.Hk) {
+                    a = s_v[2 * k2];
+                    bad |= (a != s_v[2 * k2 + 1]);
+                }
+                p.vpair[chunk * p.R2 + k2] = a;
+            }
+            if (bad) atomicOr(p.pair_flag, 1);
+        }
         if (tid == 0) {
             int t = 0;
             for (int q = 0; q < 8; ++q) t += s_wtot[q];
@@ -428,7 +448,6 @@ __device__ __forceinline__ GramItem gram_item(const GramParams& gp, int64_t j) {
 
 // Shared memory: [raw ring: nraw slots of NPL x RROWS plane words, filled by 1-D TMA bulk copies]
 //                [operand ring: nstages stages of 2 K steps x NPL planes x RROWS rows x 32 bytes] [+ slack]
-//                [8 transpose tiles (32 x 17 words) of the epilogue warps]
 // RROWS = (128 rows of a separate A tile, only when some group needs one) + nbmax rows of the B range.
 template <int NPL>
 __global__ void __launch_bounds__(GRAM_THREADS, 1) k2t_gram(const __grid_constant__ GramParams gp) {
@@ -445,7 +464,6 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) k2t_gram(const __grid_constan
     const int STAGE = 2 * NPL * BLK;
     uint8_t* const raw_base = gsm;
     uint8_t* const op_base = gsm + (size_t)RD * RAW;
-    uint32_t* const tr_base = reinterpret_cast<uint32_t*>(op_base + (size_t)NS * STAGE + 4096);
 
     // contiguous range of work items (window-major, groups of a window adjacent) of this CTA
     const int64_t n_items = (int64_t)gp.nb * gp.ngroups;
@@ -636,58 +654,63 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) k2t_gram(const __grid_constan
     } else {
         // ---------------- epilogue: TMEM -> registers -> symmetric int32 matrix ----------------
         // Lane = matrix row in TMEM (a warp may touch lanes 32 (warp % 4) ..): the two warps of a quarter take alternate
-        // 16-column blocks.  Only [i][j] with i in the A tile and j in the B range is written — the upper triangle of the
-        // symmetric matrix (readers index it through (min, max)); a 32 x 16 transpose in shared memory makes the lanes run
-        // along j (coalesced rows).
+        // 32-column blocks; a lane stores its 32 consecutive columns (128 contiguous bytes of its row) with 16-byte stores.
+        // Only [i][j] with i in the A tile and j in the B range is written — the upper triangle of the symmetric matrix
+        // (readers index it through (min, max)).
         const int ew = warp - GRAM_WARP_EPI;
         const int qd = warp & 3;
-        uint32_t* tr = tr_base + ew * (32 * 17);
+        const bool vec_ok = (gp.Hk & 3) == 0;              // rows are 16-byte aligned: a lane stores its 32 columns as 8 x 16 bytes
         int64_t k = 0;
         for (int64_t j = j0; j < j1; ++j, ++k) {
             const GramItem im = gram_item<NPL>(gp, j);
             mbar_wait(&tmem_full, (uint32_t)(k & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int i0 = im.g.a_row0 + qd * 32;
-            int32_t* o = gp.out + (size_t)im.wb * gp.Hk * gp.Hk;
-            const int cfirst = (ew >> 2) * 16;
+            const int i = im.g.a_row0 + qd * 32 + lane;     // this lane's matrix row
+            int32_t* orow = gp.out + (size_t)im.wb * gp.Hk * gp.Hk + (size_t)i * gp.Hk;
+            const int cfirst = (ew >> 2) * 32;
             int c_last = cfirst;                            // last block this warp reads
-            while (c_last + 32 < im.g.nb_rows) c_last += 32;
+            while (c_last + 64 < im.g.nb_rows) c_last += 64;
             if (cfirst >= im.g.nb_rows) {                   // nothing to read: release the accumulators right away
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tmem_empty);
             }
-            for (int c0 = cfirst; c0 < im.g.nb_rows; c0 += 32) {
-                uint32_t v[16];
+            for (int c0 = cfirst; c0 < im.g.nb_rows; c0 += 64) {
+                uint32_t v[32];
                 if (im.nst > 0) {
                     const uint32_t taddr = tmem + ((uint32_t)(qd * 32) << 16) + (uint32_t)c0;
                     asm volatile(
-                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,"
+                        "%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-                          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+                          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+                          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                         : "r"(taddr)
                         : "memory");
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 } else {
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) v[e] = 0u;
+                    for (int e = 0; e < 32; ++e) v[e] = 0u;
                 }
                 if (c0 == c_last) {                         // last read of the accumulators: the next item's MMAs may start
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tmem_empty);
                 }
+                if (i < gp.Hk) {
+                    const int jb = im.g.b_row0 + c0;        // first column of the block (multiple of 16)
+                    if (vec_ok) {
 #pragma unroll
-                for (int e = 0; e < 16; ++e) tr[lane * 17 + e] = v[e];
-                __syncwarp();
-                const int jj = im.g.b_row0 + c0 + (lane & 15);          // two rows per instruction, 16 columns each
-#pragma unroll 8
-                for (int r2 = 0; r2 < 16; ++r2) {
-                    const int r = 2 * r2 + (lane >> 4);
-                    const uint32_t x = tr[r * 17 + (lane & 15)];
-                    if (i0 + r < gp.Hk && jj < gp.Hk) o[(size_t)(i0 + r) * gp.Hk + jj] = (int32_t)x;
+                        for (int e = 0; e < 32; e += 4)
+                            if (jb + e + 4 <= gp.Hk)
+                                *reinterpret_cast<uint4*>(orow + jb + e) = make_uint4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e)
+                            if (jb + e < gp.Hk) orow[jb + e] = (int32_t)v[e];
+                    }
                 }
-                __syncwarp();
             }
         }
     }
@@ -752,6 +775,10 @@ __global__ void __launch_bounds__(128) k2t_het(const uint64_t* __restrict__ vpla
     out[(size_t)wb * n_ind + a] = v;
 }
 
+__global__ void k2t_half(int32_t* p, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = i >> 1;
+}
 __global__ void k2t_iota(int32_t* p, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = i;
@@ -773,7 +800,7 @@ int pg_k2t_build(pg_ctx* ctx, const std::vector<int32_t>& order, int64_t lo, int
     const int64_t nchunk = (hi - sb + 63) / 64;
     PG_CHECK(nchunk * 64 < (int64_t)1 << 31, "pairwise path: site span too large for one call");
     const int pitch = ctx->pitch, pw = pitch / 4;
-    PG_CHECK((size_t)16 * pw * 4 <= 96 * 1024, "pairwise path: %d haplotype columns are too many for the plane builders", pitch);
+    PG_CHECK((size_t)16 * pw * 4 + (size_t)R * 8 <= 96 * 1024, "pairwise path: %d haplotype columns are too many for the plane builders", pitch);
     {
         static bool attr_dev[64] = {};
         if (!attr_dev[ctx->device & 63]) {
@@ -803,8 +830,11 @@ int pg_k2t_build(pg_ctx* ctx, const std::vector<int32_t>& order, int64_t lo, int
         off += (bytes + 255) / 256 * 256;
         return o;
     };
+    const bool want_pairs = (Hk % 2 == 0) && !getenv("PG_K2T_NO_PAIRS");
+    const int R2 = (Hk / 2 + 15) / 16 * 16;
     const size_t o_v = carve((size_t)nchunk * R * 8), o_cls = carve(span), o_tot = carve((size_t)nchunk * 4),
-                 o_off = carve((size_t)(nchunk + 1) * 4), o_cps = carve((span + 1) * 4);
+                 o_off = carve((size_t)(nchunk + 2) * 4), o_cps = carve((span + 1) * 4),
+                 o_vp = carve(want_pairs ? (size_t)nchunk * R2 * 8 : 0), o_mid = carve((size_t)Hk * 4);
     PG_TRY(ctx->planes.ensure(off));
     uint8_t* base = (uint8_t*)ctx->planes.p;
     VcParams vp;
@@ -823,10 +853,14 @@ int pg_k2t_build(pg_ctx* ctx, const std::vector<int32_t>& order, int64_t lo, int
     vp.chunk_tot = (int32_t*)(base + o_tot);
     int32_t* d_off = (int32_t*)(base + o_off);
     int32_t* d_cps = (int32_t*)(base + o_cps);
+    vp.vpair = want_pairs ? (uint64_t*)(base + o_vp) : nullptr;
+    vp.R2 = R2;
+    vp.pair_flag = d_off + nchunk + 1;
+    PG_CUDA(cudaMemsetAsync(vp.pair_flag, 0, 4, ctx->stream));
     const int grid1 = (int)std::min<int64_t>(nchunk, (int64_t)ctx->sm_count * 8);
     {
         const int ti = pg_time_begin(ctx, "k2t_valid_class");
-        k2t_valid_class<<<grid1, 256, (size_t)8 * pw * 4, ctx->stream>>>(vp);
+        k2t_valid_class<<<grid1, 256, (size_t)8 * pw * 4 + (size_t)R * 8, ctx->stream>>>(vp);
         pg_time_end(ctx, ti);
         PG_CUDA(cudaGetLastError());
     }
@@ -836,9 +870,11 @@ int pg_k2t_build(pg_ctx* ctx, const std::vector<int32_t>& order, int64_t lo, int
         pg_time_end(ctx, ti);
         PG_CUDA(cudaGetLastError());
     }
-    int32_t total = 0;
-    PG_CUDA(cudaMemcpyAsync(&total, d_off + nchunk, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    int32_t tf[2] = {0, 0};                       // pseudo-sites, "some sample's haplotypes differ in missingness"
+    PG_CUDA(cudaMemcpyAsync(tf, d_off + nchunk, 8, cudaMemcpyDeviceToHost, ctx->stream));
     PG_CUDA(cudaStreamSynchronize(ctx->stream));
+    const int32_t total = tf[0];
+    const bool pairs_ok = want_pairs && tf[1] == 0;
     const int64_t nchunk_d = ((int64_t)total + 63) / 64;
     off = 0;
     const size_t o_inv = carve((size_t)std::max<int64_t>(total, 1) * 8), o_pq = carve((size_t)std::max<int64_t>(nchunk_d, 1) * 2 * R * 8);
@@ -880,53 +916,70 @@ int pg_k2t_build(pg_ctx* ctx, const std::vector<int32_t>& order, int64_t lo, int
     ps.npseudo = total;
     ps.pq = (uint64_t*)(base2 + o_pq);
     ps.d_iota = d_iota;
+    // mask ids for the epilogues: row r -> r / 2 when the valid words are shared by consecutive rows
+    ps.Hm = pairs_ok ? Hk / 2 : Hk;
+    ps.R2 = R2;
+    ps.vpair = pairs_ok ? vp.vpair : nullptr;
+    if (pairs_ok) {
+        int32_t* d_mid = (int32_t*)(base + o_mid);
+        k2t_half<<<(Hk + 255) / 256, 256, 0, ctx->stream>>>(d_mid, Hk);
+        ps.d_mid = d_mid;
+    } else {
+        ps.d_mid = d_iota;
+    }
     return PG_OK;
 }
 
 // diff [nb][Hk^2] and n [nb][Hk^2] for nb windows (absolute site ranges on the device)
-int pg_k2t_pairs(pg_ctx* ctx, const K2TPlanes& ps, const int64_t* d_lo, const int64_t* d_hi, int nb, int32_t* d_diff,
-                 int32_t* d_n) {
-    // tile groups: one 128-row A tile x up to 512 B rows (TMEM has 512 int32 columns per SM)
-    std::vector<GramGroup> groups;
-    int nbmax = 16, a_sep = 0;
-    for (int a0 = 0; a0 < ps.R; a0 += 128)
-        for (int c = a0; c < ps.R; c += 512) {
+namespace {
+// tile groups of an R-row Gram: one 128-row A tile x up to 512 B rows (TMEM has 512 int32 columns per SM)
+void gram_groups(int R, std::vector<GramGroup>& groups, int& nbmax, int& a_sep) {
+    groups.clear();
+    nbmax = 16;
+    a_sep = 0;
+    for (int a0 = 0; a0 < R; a0 += 128)
+        for (int c = a0; c < R; c += 512) {
             GramGroup g;
             g.a_row0 = a0;
             g.b_row0 = c;
-            g.nb_rows = std::min(512, ps.R - c);
+            g.nb_rows = std::min(512, R - c);
             g.pad = 0;
             nbmax = std::max(nbmax, g.nb_rows);
             if (c != a0) a_sep = 1;
             groups.push_back(g);
         }
-    PG_TRY(ctx->misc4.ensure(groups.size() * sizeof(GramGroup) + 64));
-    PG_CUDA(cudaMemcpyAsync(ctx->misc4.p, groups.data(), groups.size() * sizeof(GramGroup), cudaMemcpyHostToDevice, ctx->stream));
-    GramParams gp;
-    gp.R = ps.R;
-    gp.Hk = ps.Hk;
-    gp.site_base = ps.site_base;
-    gp.win_lo = d_lo;
-    gp.win_hi = d_hi;
-    gp.groups = (const GramGroup*)ctx->misc4.p;
-    gp.ngroups = (int)groups.size();
-    gp.nb = nb;
-    gp.nbmax = nbmax;
-    gp.a_sep = a_sep;
+}
+}  // namespace
+
+int pg_k2t_pairs(pg_ctx* ctx, const K2TPlanes& ps, const int64_t* d_lo, const int64_t* d_hi, int nb, int32_t* d_diff,
+                 int32_t* d_n) {
     static bool attr_dev[64] = {};
     if (!attr_dev[ctx->device & 63]) {
         PG_CUDA(cudaFuncSetAttribute(k2t_gram<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
         PG_CUDA(cudaFuncSetAttribute(k2t_gram<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
         attr_dev[ctx->device & 63] = true;
     }
-    // persistent CTAs: one per SM, each works through a contiguous range of (window, group) items
-    const int64_t n_items = (int64_t)nb * (int64_t)groups.size();
-    const unsigned grid = (unsigned)std::min<int64_t>(n_items, ctx->sm_count);
-    // shared memory: transpose tiles of the epilogue + an operand ring of (ideally) one stage per expanding group + the raw
-    // plane-word ring (up to 8 slots) + 4 KB slack (the 128-row A tile of a diagonal group may reach past a short B range)
+    // n_ij over the mask rows (one per sample when the haplotypes of a sample share their missingness), diff_ij over all rows
+    const int Rn = ps.vpair ? ps.R2 : ps.R;
+    std::vector<GramGroup> gn, gd;
+    int nbmax_n, asep_n, nbmax_d, asep_d;
+    gram_groups(Rn, gn, nbmax_n, asep_n);
+    gram_groups(ps.R, gd, nbmax_d, asep_d);
+    PG_TRY(ctx->misc4.ensure((gn.size() + gd.size()) * sizeof(GramGroup) + 64));
+    GramGroup* d_gn = (GramGroup*)ctx->misc4.p;
+    GramGroup* d_gd = d_gn + gn.size();
+    PG_CUDA(cudaMemcpyAsync(d_gn, gn.data(), gn.size() * sizeof(GramGroup), cudaMemcpyHostToDevice, ctx->stream));
+    PG_CUDA(cudaMemcpyAsync(d_gd, gd.data(), gd.size() * sizeof(GramGroup), cudaMemcpyHostToDevice, ctx->stream));
+    GramParams gp;
+    gp.site_base = ps.site_base;
+    gp.win_lo = d_lo;
+    gp.win_hi = d_hi;
+    gp.nb = nb;
+    // shared memory: an operand ring of (ideally) one stage per expanding group + the raw plane-word ring + 4 KB slack (the
+    // 128-row A tile of a diagonal group may reach past a short B range)
     const int budget = 224 * 1024;
-    const int fixed = GRAM_EPI_WARPS * 32 * 17 * 4 + 4096;
-    auto geometry = [&](int npl, int& nstages, int& nraw) {
+    const int fixed = 4096;
+    auto geometry = [&](int npl, int nbmax, int a_sep, int& nstages, int& nraw) {
         const int rrows = (a_sep ? 128 : 0) + nbmax;
         const int stage = 2 * npl * rrows * 32, raw = npl * rrows * 8;
         nstages = std::max(2, std::min(GRAM_XGROUPS, (budget - fixed - 3 * raw) / stage));
@@ -937,21 +990,35 @@ int pg_k2t_pairs(pg_ctx* ctx, const K2TPlanes& ps, const int64_t* d_lo, const in
         nraw = std::max(1, mult) * nstages;
         return (size_t)nstages * stage + (size_t)nraw * raw + fixed;
     };
-    {
-        const size_t smem = geometry(1, gp.nstages, gp.nraw);
-        gp.plane = ps.vplane;
+    {   // persistent CTAs: one per SM, each works through a contiguous range of (window, group) items
+        gp.R = Rn;
+        gp.Hk = ps.Hm;
+        gp.groups = d_gn;
+        gp.ngroups = (int)gn.size();
+        gp.nbmax = nbmax_n;
+        gp.a_sep = asep_n;
+        const size_t smem = geometry(1, nbmax_n, asep_n, gp.nstages, gp.nraw);
+        gp.plane = ps.vpair ? ps.vpair : ps.vplane;
         gp.cps = nullptr;
         gp.out = d_n;
+        const unsigned grid = (unsigned)std::min<int64_t>((int64_t)nb * gp.ngroups, ctx->sm_count);
         const int ti = pg_time_begin(ctx, "k2t_gram_n");
         k2t_gram<1><<<grid, GRAM_THREADS, smem, ctx->stream>>>(gp);
         pg_time_end(ctx, ti);
         PG_CUDA(cudaGetLastError());
     }
     {
-        const size_t smem = geometry(2, gp.nstages, gp.nraw);
+        gp.R = ps.R;
+        gp.Hk = ps.Hk;
+        gp.groups = d_gd;
+        gp.ngroups = (int)gd.size();
+        gp.nbmax = nbmax_d;
+        gp.a_sep = asep_d;
+        const size_t smem = geometry(2, nbmax_d, asep_d, gp.nstages, gp.nraw);
         gp.plane = ps.pq;
         gp.cps = ps.cps;
         gp.out = d_diff;
+        const unsigned grid = (unsigned)std::min<int64_t>((int64_t)nb * gp.ngroups, ctx->sm_count);
         const int ti = pg_time_begin(ctx, "k2t_gram_diff");
         k2t_gram<2><<<grid, GRAM_THREADS, smem, ctx->stream>>>(gp);
         pg_time_end(ctx, ti);

@@ -138,7 +138,12 @@ struct K2TPlanes {
     const int32_t* cps = nullptr;      // [64 nchunk_v + 1]: pseudo-sites before each site of the span
     int64_t npseudo = 0;
     const uint64_t* pq = nullptr;      // [ceil(npseudo / 64)][2][R]: P and Q planes of the pseudo-sites
-    const int32_t* d_iota = nullptr;   // [Hk] 0..Hk-1 (identity "mask id" for the epilogues)
+    const int32_t* d_iota = nullptr;   // [Hk] 0..Hk-1
+    // n_ij is computed over "mask rows": one per plane row, or — when rows 2k and 2k+1 have identical valid planes (the two
+    // haplotypes of a sample with per-genotype missingness) — one per pair of rows
+    int Hm = 0, R2 = 0;
+    const uint64_t* vpair = nullptr;   // [nchunk_v][R2] valid words of the even rows (nullptr: every row is its own mask row)
+    const int32_t* d_mid = nullptr;    // [Hk] mask row of each plane row
 };
 bool pg_k2_use_tensor();               // false when PG_K2_POPC is set (the bit-plane POPC kernels, kept as a checker)
 int pg_k2t_build(pg_ctx* ctx, const std::vector<int32_t>& order, int64_t lo, int64_t hi, K2TPlanes& ps);
