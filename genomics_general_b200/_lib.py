@@ -48,6 +48,7 @@ _SIGS = {
     "pg_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
     "pg_alloc_sites": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32]),
     "pg_upload_range": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
+    "pg_append_sites": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "pg_synth_fill": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, C.c_uint64,
                                 C.c_uint64, C.c_uint64, C.c_uint64, C.c_int32]),
     "pg_download": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
@@ -86,6 +87,8 @@ _SIGS = {
                                       C.POINTER(C.c_int64)]),
     "pg_ingest_file": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                  C.POINTER(C.c_int64)]),
+    "pg_ingest_file_range": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                       C.c_int32, C.POINTER(C.c_int64)]),
     "pg_ingest_text": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                  C.POINTER(C.c_int64)]),
     "pg_ingest_meta": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -29,6 +29,8 @@ def add_engine_args(p):
     p.add_argument("--device", help="CUDA device index", type=int, default=0)
     p.add_argument("--parseThreads", help="Host threads for the .geno tokenizer", type=int, default=None)
     p.add_argument("--hostParse", help="Tokenise the .geno text on the host instead of on the GPU", action="store_true")
+    p.add_argument("--devices", help="Number of GPUs: every GPU tokenises its share of the file and computes the windows that "
+                                     "start there (one process per GPU, one NCCL all-gather of the rows)", type=int, default=None)
 
 
 def check_window_args(args, with_id=False):

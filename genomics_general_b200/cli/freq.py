@@ -5,11 +5,12 @@ freq.py:62-98; the reference's random pick between exactly tied minor alleles be
 from __future__ import annotations
 
 import argparse
+import os
 import sys
 
 import numpy as np
 
-from .. import genomics, geno_io
+from .. import genomics, geno_io, mgpu
 from ..engine import Engine
 from . import _common as C
 
@@ -57,16 +58,25 @@ def main(argv=None):
     for s in args.haploid or []:           # freq.py:283-284: --haploid also overrides --ploidy / --ploidyFile
         ploidyDict[s] = 1
     sampleData = genomics.SampleData(indNames=allInds, popNames=popNames, popInds=popInds, ploidyDict=ploidyDict)
-    out = C.open_out(args.outFile)
-    out.write("scaffold\tposition\t" + "\t".join(popNames) + "\n")
-    eng = Engine(args.device)
-    gd = C.load_geno(args, sampleData.indNames, ploidyDict, engine=eng)
+    # --devices N: every rank tokenises its share of the file and formats its own rows (freq.py:328-360's slices, one
+    # process per GPU here); rank 0 then appends the parts in rank order
+    rdv = mgpu.init("genomics_general_b200.cli.freq", argv, args.devices)
+    if rdv is None or rdv.rank == 0:
+        out = C.open_out(args.outFile)
+        out.write("scaffold\tposition\t" + "\t".join(popNames) + "\n")
+    else:
+        out = open(os.path.join(rdv.dir, "rows.r%d.part" % rdv.rank), "wb")
+    eng = Engine(args.device if rdv is None else mgpu.device_for(rdv, args.device))
+    if rdv is None:
+        gd = C.load_geno(args, sampleData.indNames, ploidyDict, engine=eng)
+    else:
+        gd = mgpu.local_ingest(eng, rdv, args.genoFile, args.genoFormat, sampleData.indNames, ploidyDict)
     P = len(popNames)
     with eng:
         C.ensure_resident(eng, gd)
         eng.set_pops(C.hap_pop_vector(gd, popNames, popInds), P)
         # rows are formatted by native host threads (pg_format_freq_rows) and written as bytes
-        raw = out.buffer if hasattr(out, "buffer") else None
+        raw = out if (rdv is not None and rdv.rank != 0) else (out.buffer if hasattr(out, "buffer") else None)
         if raw is not None:
             out.flush()
 
@@ -96,8 +106,29 @@ def main(argv=None):
                     emit(geno_io.format_freq_rows(1, v, pos, ids, gd.scaf_names, keep))
                 continue
             emit(geno_io.format_freq_rows(0, eng.site_counts(s, n), pos, ids, gd.scaf_names))
+    if rdv is not None:
+        if rdv.rank != 0:
+            out.close()
+            rdv.put_bytes("rows_done", b"1")
+            rdv.finish()
+            return
+        out.flush()
+        sink = out.buffer if hasattr(out, "buffer") else None
+        for q in range(1, rdv.world):
+            rdv.get_bytes("rows_done", q)
+            with open(os.path.join(rdv.dir, "rows.r%d.part" % q), "rb") as part:
+                while True:
+                    blk = part.read(1 << 24)
+                    if not blk:
+                        break
+                    if sink is not None:
+                        sink.write(blk)
+                    else:
+                        out.write(blk.decode())
     if out is not sys.stdout:
         out.close()
+    if rdv is not None:
+        rdv.finish()
     sys.stderr.write("\nDone\n")
 
 

@@ -13,11 +13,12 @@ from __future__ import annotations
 
 import argparse
 import itertools
+import os
 import sys
 
 import numpy as np
 
-from .. import genomics
+from .. import genomics, mgpu, multigpu
 from ..engine import Engine
 from . import _common as C
 
@@ -76,7 +77,13 @@ def main(argv=None):
     ploidyDict = C.ploidy_dict(args, allInds, args.haploid.split(",") if args.haploid else None)
     sampleData = genomics.SampleData(indNames=allInds, popNames=popNames, popInds=popInds, ploidyDict=ploidyDict)
 
-    out = C.open_out(args.outFile)
+    # --devices N: this process becomes rank 0 of N (ranks 1.. are re-launched copies of this command line)
+    rdv = mgpu.init("genomics_general_b200.cli.popgenWindows", argv, args.devices)
+    if rdv is not None:
+        unsupported = [a for a in args.analysis if a not in ("popDist", "popPairDist")]
+        if unsupported:
+            raise NotImplementedError("--devices > 1 supports --analysis popDist popPairDist (got %s)" % " ".join(unsupported))
+    out = C.open_out(args.outFile) if (rdv is None or rdv.rank == 0) else open(os.devnull, "wt")
     out.write("scaffold,start,end,mid,sites," if not args.addWindowID else "windowID,scaffold,start,end,mid,sites,")
     stats = []
     if "popFreq" in args.analysis:
@@ -97,22 +104,43 @@ def main(argv=None):
             stats += [key + n for n in popNames]
     out.write(",".join(stats) + "\n")
 
-    eng = Engine(args.device)
+    eng = Engine(args.device if rdv is None else mgpu.device_for(rdv, args.device))
 
     # columns in the reference's haplotype order (sorted sequence names): H12's greedy clustering breaks ties by row
-    gd = C.load_geno(args, C.alignment_order(sampleData.indNames, ploidyDict, args.genoFormat), ploidyDict, header=args.header,
-                     engine=eng)
+    col_order = C.alignment_order(sampleData.indNames, ploidyDict, args.genoFormat)
+    if rdv is None:
+        gd = C.load_geno(args, col_order, ploidyDict, header=args.header, engine=eng)
+    else:
+        gd, starts, off_all = mgpu.sharded_ingest(eng, rdv, args.genoFile, args.genoFormat, col_order, ploidyDict, args.header)
     ws = C.make_windows(args, gd, minSites, coords, C.read_scaffold_list(args.include), C.read_scaffold_list(args.exclude))
     sys.stderr.write("\n%d sites x %d haplotypes, %d windows\n" % (gd.n_sites, gd.n_haps, len(ws)))
     lo, hi = ws.ranges()
     written = 0
     with eng:
-        C.ensure_resident(eng, gd)
-        eng.set_windows(lo, hi)
         P = len(popNames)
-        eng.set_pops(C.hap_pop_vector(gd, popNames, popInds), max(P, 1))
-        eng.set_freqstats("popFreq" in args.analysis)
-        r = eng.popgen(minSites, args.minData)
+        if rdv is None:
+            C.ensure_resident(eng, gd)
+            eng.set_windows(lo, hi)
+            eng.set_pops(C.hap_pop_vector(gd, popNames, popInds), max(P, 1))
+            eng.set_freqstats("popFreq" in args.analysis)
+            r = eng.popgen(minSites, args.minData)
+        else:
+            # this rank's windows (those that start in its share of the file) + the sites they need from the next share
+            idx, llo, lhi, halo = mgpu.assign_windows(lo, hi, starts, rdv.rank)
+            mgpu.fetch_halo(eng, args.genoFile, gd, starts, off_all, rdv.rank, halo, args.genoFormat, ploidyDict)
+            eng.set_windows(llo, lhi)
+            eng.set_pops(C.hap_pop_vector(gd, popNames, popInds), max(P, 1))
+            all_idx = [mgpu.assign_windows(lo, hi, starts, q)[0] for q in range(rdv.world)]
+            w_max, row_of = mgpu.gathered_order(all_idx)
+            mgpu.nccl_connect(eng, rdv)
+            table = np.zeros((rdv.world * w_max, eng.popgen_record_width()), dtype=np.float64)
+            eng.popgen_allgather(w_max, table, minSites, args.minData)          # ONE ncclAllGather of the records
+            eng.nccl_finalize()
+            rows = np.array([row_of[w] for w in range(len(ws))], dtype=np.int64)
+            r = multigpu.unpack_device_records(table[rows] if len(rows) else table[:0], P)
+            if rdv.rank != 0:
+                rdv.finish()
+                return
         fq = None
         if "popFreq" in args.analysis:
             hp_all = C.hap_pop_vector(gd, popNames, popInds)
@@ -164,6 +192,8 @@ def main(argv=None):
                 written += 1
     if out is not sys.stdout:
         out.close()
+    if rdv is not None:
+        rdv.finish()
     sys.stderr.write(str(len(ws)) + " windows were tested.\n")
     sys.stderr.write(str(written) + " results were written.\n")
     sys.stderr.write("\nDone.\n")

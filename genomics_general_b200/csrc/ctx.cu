@@ -389,6 +389,43 @@ extern "C" int pg_alloc_sites(pg_ctx* ctx, int64_t S, int32_t H) {
     return PG_OK;
 }
 
+// Grows the resident matrix by n sites appended after the current ones (multi-GPU command lines: the few sites of the
+// next rank's byte range that this rank's last windows reach into).  The matrix is re-allocated when its capacity is short.
+extern "C" int pg_append_sites(pg_ctx* ctx, int64_t n, const int8_t* geno, const int32_t* pos) {
+    PG_CHECK(ctx && (n == 0 || geno), "pg_append_sites: null argument");
+    PG_CHECK(n >= 0 && ctx->H > 0, "pg_append_sites: no matrix to append to");
+    if (n == 0) return PG_OK;
+    PG_CUDA(cudaSetDevice(ctx->device));
+    const int64_t S0 = ctx->S, S1 = S0 + n;
+    const size_t need = (size_t)(S1 + 64) * ctx->pitch + 4096;
+    if (need > ctx->geno_cap) {
+        int8_t* fresh = nullptr;
+        PG_CUDA(cudaMalloc((void**)&fresh, need));
+        PG_CUDA(cudaMemsetAsync(fresh, 0, need, ctx->stream));
+        PG_CUDA(cudaMemcpyAsync(fresh, ctx->d_geno, (size_t)S0 * ctx->pitch, cudaMemcpyDeviceToDevice, ctx->stream));
+        PG_CUDA(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->d_geno);
+        ctx->d_geno = fresh;
+        ctx->geno_cap = need;
+    }
+    const size_t pneed = (size_t)(S1 + 64) * sizeof(int32_t);
+    if (pneed > ctx->pos_cap) {
+        int32_t* fresh = nullptr;
+        PG_CUDA(cudaMalloc((void**)&fresh, pneed));
+        PG_CUDA(cudaMemsetAsync(fresh, 0, pneed, ctx->stream));
+        PG_CUDA(cudaMemcpyAsync(fresh, ctx->d_pos, (size_t)S0 * sizeof(int32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+        PG_CUDA(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->d_pos);
+        ctx->d_pos = fresh;
+        ctx->pos_cap = pneed;
+    }
+    ctx->S = S1;
+    ctx->epoch += 1;
+    ctx->brk.clear();
+    ctx->ingest_sites = -1;
+    return pg_upload_range(ctx, S0, n, geno, pos);
+}
+
 // dense staging rows [n x H] (reference codes) -> resident pitched rows (one-hot code)
 __global__ void k_ingest(const uint8_t* __restrict__ stage, uint8_t* __restrict__ geno, int64_t row0, int64_t n,
                          int pitch, int H) {

@@ -355,6 +355,31 @@ extern "C" int pg_ingest_file(pg_ctx* ctx, const char* path, int64_t body_offset
     return rc;
 }
 
+// Bytes [byte_lo, byte_hi) of the file (both at line starts; byte_hi < 0: end of file): one rank's share of the data lines in
+// the multi-GPU command lines.  line_off values of pg_ingest_meta are relative to byte_lo.
+extern "C" int pg_ingest_file_range(pg_ctx* ctx, const char* path, int64_t byte_lo, int64_t byte_hi, int32_t fmt, int32_t n_cols,
+                                    const int32_t* col_hap, const int8_t* col_ploidy, int32_t H_out, int64_t* n_sites) {
+    PG_CHECK(ctx && path && col_hap && col_ploidy && n_sites, "pg_ingest_file_range: null argument");
+    const int fd = open(path, O_RDONLY);
+    PG_CHECK(fd >= 0, "pg_ingest_file_range: cannot open %s", path);
+    struct stat st;
+    if (fstat(fd, &st) != 0) {
+        close(fd);
+        pg_set_error("pg_ingest_file_range: cannot stat %s", path);
+        return PG_ERR;
+    }
+    if (byte_hi < 0 || byte_hi > (int64_t)st.st_size) byte_hi = (int64_t)st.st_size;
+    if (byte_lo < 0 || byte_lo > byte_hi) {
+        close(fd);
+        pg_set_error("pg_ingest_file_range: bad byte range [%lld, %lld)", (long long)byte_lo, (long long)byte_hi);
+        return PG_ERR;
+    }
+    const int rc = ingest_core(ctx, nullptr, fd, (size_t)byte_lo, (size_t)(byte_hi - byte_lo), fmt, n_cols, col_hap, col_ploidy,
+                               H_out, n_sites);
+    close(fd);
+    return rc;
+}
+
 namespace {
 int ingest_core(pg_ctx* ctx, const char* mem, int fd, size_t file_off, size_t len, int32_t fmt, int32_t n_cols,
                 const int32_t* col_hap, const int8_t* col_ploidy, int32_t H_out, int64_t* n_sites) {

@@ -260,6 +260,25 @@ class Engine:
         self.S, self.H = int(n.value), int(H)
         return self.S
 
+    def ingest_file_range(self, path: str, byte_lo: int, byte_hi: int, fmt: int, col_hap, col_ploidy, H: int) -> int:
+        """One rank's share of the file: bytes [byte_lo, byte_hi) (line starts; byte_hi < 0 = end of file)."""
+        col_hap = np.ascontiguousarray(col_hap, dtype=np.int32)
+        col_ploidy = np.ascontiguousarray(col_ploidy, dtype=np.int8)
+        n = C.c_int64(0)
+        check(self._lib.pg_ingest_file_range(self._ctx, path.encode(), int(byte_lo), int(byte_hi), int(fmt), len(col_hap),
+                                             _ptr(col_hap), _ptr(col_ploidy), int(H), C.byref(n)), "pg_ingest_file_range")
+        self.S, self.H = int(n.value), int(H)
+        return self.S
+
+    def append_sites(self, geno: np.ndarray, pos=None):
+        """Append sites (int8 [n, H]) after the resident ones (halo of the next rank's first sites)."""
+        geno = np.ascontiguousarray(geno, dtype=np.int8)
+        assert geno.ndim == 2 and geno.shape[1] == self.H
+        if pos is not None:
+            pos = np.ascontiguousarray(pos, dtype=np.int32)
+        check(self._lib.pg_append_sites(self._ctx, geno.shape[0], _ptr(geno), _ptr(pos)), "pg_append_sites")
+        self.S += geno.shape[0]
+
     def ingest_meta(self, S: int):
         """(pos int32 [S], new_scaffold int8 [S], line_off int64 [S]) of the last ingest_text."""
         pos = np.empty(S, dtype=np.int32)

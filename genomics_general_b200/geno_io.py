@@ -103,6 +103,20 @@ def _scaffold_runs(newsc, off, name_at):
     return scaf_ids, scaf_names
 
 
+def _column_maps(file_names, samples, pl, col_take):
+    """file column -> first output haplotype (-1: not wanted) and ploidy, for the device tokenizer"""
+    n_cols = len(file_names)
+    col_hap = np.full(max(n_cols, 1), -1, dtype=np.int32)
+    col_pl = np.ones(max(n_cols, 1), dtype=np.int8)
+    hap_off = np.concatenate([[0], np.cumsum(pl.astype(np.int64))[:-1]]).astype(np.int32) if len(pl) else np.zeros(0, np.int32)
+    for k, c in enumerate(col_take):
+        if col_hap[c] >= 0:
+            raise ValueError("sample %s requested twice" % samples[k])
+        col_hap[c] = hap_off[k]
+        col_pl[c] = pl[k]
+    return col_hap, col_pl, hap_off, int(pl.astype(np.int64).sum())
+
+
 def ingest_geno(eng, source, geno_format="phased", samples=None, ploidy=None, header=None) -> GenoData:
     """Like parse_geno, but the text is tokenised ON THE DEVICE (pg_ingest_text / pg_ingest_file): the file's bytes are
     copied to the GPU as they are and the resident matrix of `eng` is built there.  The returned GenoData has
@@ -119,16 +133,7 @@ def ingest_geno(eng, source, geno_format="phased", samples=None, ploidy=None, he
         data = None
     else:
         data, boff, header, file_names, samples, fmt, pl, col_take = _prepare(source, geno_format, samples, ploidy, header)
-    n_cols = len(file_names)
-    col_hap = np.full(max(n_cols, 1), -1, dtype=np.int32)
-    col_pl = np.ones(max(n_cols, 1), dtype=np.int8)
-    hap_off = np.concatenate([[0], np.cumsum(pl.astype(np.int64))[:-1]]).astype(np.int32) if len(pl) else np.zeros(0, np.int32)
-    for k, c in enumerate(col_take):
-        if col_hap[c] >= 0:
-            raise ValueError("sample %s requested twice" % samples[k])
-        col_hap[c] = hap_off[k]
-        col_pl[c] = pl[k]
-    H = int(pl.astype(np.int64).sum())
+    col_hap, col_pl, hap_off, H = _column_maps(file_names, samples, pl, col_take)
     if from_file:
         S = eng.ingest_file(source, boff, fmt, col_hap, col_pl, H)
     else:

@@ -48,6 +48,9 @@ int pg_upload(pg_ctx* ctx, const int8_t* geno, int64_t S, int32_t H, const int32
 /* Two-step variant: allocate, then fill site ranges (each call is an async H2D on the ctx stream). */
 int pg_alloc_sites(pg_ctx* ctx, int64_t S, int32_t H);
 int pg_upload_range(pg_ctx* ctx, int64_t site0, int64_t n, const int8_t* geno, const int32_t* pos);
+/* Appends n sites (int8 [n x H], reference codes; pos int32 [n] or NULL) after the resident ones; the matrix grows.  Used by
+ * the multi-GPU command lines for the halo sites of windows that reach into the next rank's share of the file. */
+int pg_append_sites(pg_ctx* ctx, int64_t n, const int8_t* geno, const int32_t* pos);
 /* Device-side synthetic data (SURVEY.md §8d distribution; bit-identical to synth.py::synth_genotypes /
  * synth_positions).  Thresholds are 32-bit integer probabilities (p * 2^32). */
 int pg_synth_fill(pg_ctx* ctx, int64_t S, int32_t n_pops, int32_t samples_per_pop, int32_t ploidy,
@@ -233,6 +236,11 @@ int pg_ingest_text(pg_ctx* ctx, const char* buf, size_t len, int32_t fmt, int32_
  * memory.  line_off values of pg_ingest_meta are relative to body_offset. */
 int pg_ingest_file(pg_ctx* ctx, const char* path, int64_t body_offset, int32_t fmt, int32_t n_cols, const int32_t* col_hap,
                    const int8_t* col_ploidy, int32_t H_out, int64_t* n_sites);
+/* One rank's share of a file in the multi-GPU command lines (replaces the single producer that feeds the -T workers,
+ * popgenWindows.py:398-446): bytes [byte_lo, byte_hi) — both at line starts, byte_hi < 0 = end of file.  line_off values of
+ * pg_ingest_meta are relative to byte_lo. */
+int pg_ingest_file_range(pg_ctx* ctx, const char* path, int64_t byte_lo, int64_t byte_hi, int32_t fmt, int32_t n_cols,
+                         const int32_t* col_hap, const int8_t* col_ploidy, int32_t H_out, int64_t* n_sites);
 /* pos int32 [S], new_scaffold int8 [S], line_off int64 [S] of the last pg_ingest_text / pg_ingest_file (as pg_geno_parse returns them;
  * any pointer may be NULL). */
 int pg_ingest_meta(pg_ctx* ctx, int32_t* pos, int8_t* new_scaffold, int64_t* line_off);
