@@ -288,10 +288,15 @@ class Engine:
         check(self._lib.pg_ingest_release(self._ctx), "pg_ingest_release")
         return pos, newsc, off
 
-    def site_counts(self, site0: int = 0, n: int = None):
-        """uint16 [n, P, 4] A,C,G,T counts per population."""
+    def site_counts(self, site0: int = 0, n: int = None, out=None):
+        """uint16 [n, P, 4] A,C,G,T counts per population (`out`: a caller-owned array to fill, e.g. one whose pages are
+        already resident — a fresh 100 MB array costs more in page faults than the kernel and the copy together)."""
         n = self.S - site0 if n is None else int(n)
-        out = np.empty((n, self.P, 4), dtype=np.uint16)
+        if out is None:
+            out = np.empty((n, self.P, 4), dtype=np.uint16)
+        else:
+            out = out[:n]
+            assert out.dtype == np.uint16 and out.flags.c_contiguous and out.shape == (n, self.P, 4)
         check(self._lib.pg_site_counts(self._ctx, int(site0), n, _ptr(out)), "pg_site_counts")
         return out
 
