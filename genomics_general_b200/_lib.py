@@ -83,6 +83,8 @@ _SIGS = {
     "pg_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "pg_nccl_init": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "pg_nccl_finalize": (C.c_int, [C.c_void_p]),
+    "pg_popgen_gather_begin": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_int64, C.c_int32]),
+    "pg_popgen_gather_end": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     "pg_popgen_allgather": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_int32, C.c_int64, C.c_void_p,
                                       C.POINTER(C.c_int64)]),
     "pg_ingest_file": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,

@@ -89,6 +89,13 @@ extern "C" int pg_ctx_destroy(pg_ctx* ctx) {
         cudaStreamDestroy(ctx->copy_stream);
     }
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    for (int k = 0; k < 2; ++k) {
+        ctx->gslot[k].release();
+        if (ctx->gslot_host[k]) cudaFreeHost(ctx->gslot_host[k]);
+        if (ctx->g_rec[k]) cudaEventDestroy(ctx->g_rec[k]);
+        if (ctx->g_done[k]) cudaEventDestroy(ctx->g_done[k]);
+    }
+    if (ctx->gather_stream) cudaStreamDestroy(ctx->gather_stream);
     for (int k = 0; k < 2; ++k)
         if (ctx->h_text[k]) {
             cudaFreeHost(ctx->h_text[k]);
@@ -128,7 +135,13 @@ int pg_pinned(pg_ctx* ctx, size_t bytes, void** out) {
 int pg_d2h_staged(pg_ctx* ctx, void* dst, const void* src, size_t bytes) {
     if (bytes == 0) return PG_OK;
     const size_t slab = (size_t)64 << 20;
-    if (bytes < ((size_t)8 << 20)) {
+    bool pinned = false;                                       // a caller buffer from pg_host_alloc: the copy engine writes it directly
+    {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, dst) == cudaSuccess) pinned = (at.type == cudaMemoryTypeHost);
+        else cudaGetLastError();
+    }
+    if (pinned || bytes < ((size_t)8 << 20)) {
         PG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
         PG_CUDA(cudaStreamSynchronize(ctx->stream));
         return PG_OK;

@@ -496,26 +496,32 @@ __global__ void __launch_bounds__(256) k2_ind_epi(const __grid_constant__ IndEpi
     const int32_t* D = ep.diff + (size_t)wb * HH;
     const int32_t* N = ep.n + (size_t)wb * ep.Hm * ep.Hm;
     const int64_t total = (int64_t)ep.n_ind * ep.n_ind;
-    for (int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * 256) {
-        const int a = (int)(idx / ep.n_ind), b = (int)(idx % ep.n_ind);
-        double s = 0.0;
-        int c = 0;
-        for (int i = ep.ind_start[a]; i < ep.ind_start[a + 1]; ++i)
-            for (int j = ep.ind_start[b]; j < ep.ind_start[b + 1]; ++j) {
-                double d;
-                if (i == j) {
-                    if (!ep.include_same || ep.min_sites > 0) continue;   // diagonal = nan (genomics.py:940; 937-938 masks it too)
-                    d = 0.0;                                 // distMatrix leaves 0 on the diagonal (908)
-                } else {
-                    const int nij = N[upper_idx(ep.mid[i], ep.mid[j], ep.Hm)];
-                    if (nij == 0) continue;                  // np.mean of an empty array = nan
-                    if (ep.min_sites > 0 && nij < ep.min_sites) continue;
-                    d = (double)D[upper_idx(i, j, ep.Hk)] / (double)nij;
+    double* o = ep.out + (size_t)wb * total;
+    // a warp walks one output row (individual a), lanes along b: no integer division per element, coalesced stores
+    const int lane = threadIdx.x & 31;
+    for (int a = blockIdx.x * 8 + (threadIdx.x >> 5); a < ep.n_ind; a += gridDim.x * 8) {
+        const int i0 = ep.ind_start[a], i1 = ep.ind_start[a + 1];
+        for (int b = lane; b < ep.n_ind; b += 32) {
+            const int j0 = ep.ind_start[b], j1 = ep.ind_start[b + 1];
+            double s = 0.0;
+            int c = 0;
+            for (int i = i0; i < i1; ++i)
+                for (int j = j0; j < j1; ++j) {
+                    double d;
+                    if (i == j) {
+                        if (!ep.include_same || ep.min_sites > 0) continue;   // diagonal = nan (genomics.py:940; 937-938 masks it too)
+                        d = 0.0;                                 // distMatrix leaves 0 on the diagonal (908)
+                    } else {
+                        const int nij = N[upper_idx(ep.mid[i], ep.mid[j], ep.Hm)];
+                        if (nij == 0) continue;                  // np.mean of an empty array = nan
+                        if (ep.min_sites > 0 && nij < ep.min_sites) continue;
+                        d = (double)D[upper_idx(i, j, ep.Hk)] / (double)nij;
+                    }
+                    s += d;
+                    c += 1;
                 }
-                s += d;
-                c += 1;
-            }
-        ep.out[(size_t)wb * total + idx] = c ? s / (double)c : nan_d();
+            o[(size_t)a * ep.n_ind + b] = c ? s / (double)c : nan_d();
+        }
     }
 }
 
@@ -1098,7 +1104,7 @@ extern "C" int pg_pairdist(pg_ctx* ctx, int32_t n_ind, const int32_t* hap_ind, i
         ep.include_same = include_same_with_same ? 1 : 0;
         ep.min_sites = min_sites;
         ep.out = (double*)ctx->out_d.p;
-        dim3 grid((unsigned)std::min<size_t>((nn + 255) / 256, 1024), (unsigned)nb);
+        dim3 grid((unsigned)std::min<int>((n_ind + 7) / 8, 64), (unsigned)nb);
         const int ti = pg_time_begin(ctx, "k2_ind_epi");
         k2_ind_epi<<<grid, 256, 0, ctx->stream>>>(ep);
         pg_time_end(ctx, ti);

@@ -169,6 +169,92 @@ extern "C" int pg_popgen_allgather(pg_ctx* ctx, int32_t min_sites, double min_da
     return PG_OK;
 }
 
+// Pipelined form of pg_popgen_allgather: `begin` enqueues the site pass + finalize of one batch on the ctx stream and the
+// exchange (ncclAllGather, when a communicator is set) + the read-back of the table on a SIDE stream; `end` waits for that
+// batch's table.  With two slots the exchange and the D2H of batch k run under the site pass of batch k+1:
+//     begin(0); begin(1); end(0); begin(0); end(1); ...
+// Windows that need the pairwise path are resolved in `end` (synchronously, then gathered again).
+extern "C" int pg_popgen_gather_begin(pg_ctx* ctx, int32_t min_sites, double min_data, int64_t w_max, int32_t slot) {
+    PG_CHECK(ctx && (slot == 0 || slot == 1), "pg_popgen_gather_begin: bad argument");
+    PG_CHECK(w_max >= ctx->W && w_max >= 1, "pg_popgen_gather_begin: w_max (%lld) is smaller than this rank's window count (%lld)",
+             (long long)w_max, (long long)ctx->W);
+    PG_CUDA(cudaSetDevice(ctx->device));
+    const int ranks = ctx->nccl_comm ? ctx->nccl_ranks : 1, rank = ctx->nccl_comm ? ctx->nccl_rank : 0;
+    const int P = ctx->P;
+    const int RC = 4 + 5 * P + 2 * (P * (P - 1) / 2);
+    const size_t slot_words = (size_t)w_max * RC, total_words = slot_words * (size_t)ranks;
+    if (!ctx->gather_stream) {
+        PG_CUDA(cudaStreamCreateWithFlags(&ctx->gather_stream, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; ++k) {
+            PG_CUDA(cudaEventCreateWithFlags(&ctx->g_rec[k], cudaEventDisableTiming));
+            PG_CUDA(cudaEventCreateWithFlags(&ctx->g_done[k], cudaEventDisableTiming));
+        }
+    }
+    if (ctx->gslot_words[slot] != total_words || ctx->gslot[slot].cap < total_words * 8) {
+        PG_TRY(ctx->gslot[slot].ensure(total_words * 8));
+        PG_CUDA(cudaMemsetAsync(ctx->gslot[slot].p, 0, total_words * 8, ctx->stream));
+        ctx->gslot_words[slot] = total_words;
+    }
+    if (ctx->gslot_host_cap[slot] < total_words * 8) {
+        if (ctx->gslot_host[slot]) cudaFreeHost(ctx->gslot_host[slot]);
+        ctx->gslot_host[slot] = nullptr;
+        PG_CUDA(cudaHostAlloc(&ctx->gslot_host[slot], total_words * 8, cudaHostAllocDefault));
+        ctx->gslot_host_cap[slot] = total_words * 8;
+    }
+    ctx->gslot_wmax[slot] = w_max;
+    ctx->gslot_min_sites[slot] = min_sites;
+    ctx->gslot_min_data[slot] = min_data;
+    unsigned long long* base = (unsigned long long*)ctx->gslot[slot].p;
+    unsigned long long* mine = base + slot_words * (size_t)rank;
+    int* h_cnt = nullptr;
+    PG_TRY(pg_popgen_enqueue(ctx, min_sites, min_data, 0, mine, &h_cnt));
+    PG_CUDA(cudaEventRecord(ctx->g_rec[slot], ctx->stream));
+    PG_CUDA(cudaStreamWaitEvent(ctx->gather_stream, ctx->g_rec[slot], 0));
+    if (ranks > 1) {
+        PG_NCCL(g_nccl.all_gather(mine, base, slot_words, NCCL_UINT64, (NcclComm)ctx->nccl_comm, ctx->gather_stream));
+        ctx->launches += 1;
+    }
+    PG_CUDA(cudaMemcpyAsync(ctx->gslot_host[slot], base, total_words * 8, cudaMemcpyDeviceToHost, ctx->gather_stream));
+    PG_CUDA(cudaEventRecord(ctx->g_done[slot], ctx->gather_stream));
+    return PG_OK;
+}
+
+// *h_table: the slot's pinned table (nranks * w_max records, rank order; valid until the slot's next `begin`).
+extern "C" int pg_popgen_gather_end(pg_ctx* ctx, int32_t slot, const void** h_table, int64_t* n_pairwise) {
+    PG_CHECK(ctx && h_table && (slot == 0 || slot == 1) && ctx->gslot_host[slot], "pg_popgen_gather_end: no batch in this slot");
+    PG_CUDA(cudaSetDevice(ctx->device));
+    PG_CUDA(cudaEventSynchronize(ctx->g_done[slot]));
+    const int ranks = ctx->nccl_comm ? ctx->nccl_ranks : 1, rank = ctx->nccl_comm ? ctx->nccl_rank : 0;
+    const int P = ctx->P;
+    const int RC = 4 + 5 * P + 2 * (P * (P - 1) / 2);
+    const int64_t w_max = ctx->gslot_wmax[slot];
+    const size_t slot_words = (size_t)w_max * RC, total_words = slot_words * (size_t)ranks;
+    const unsigned long long* tab = (const unsigned long long*)ctx->gslot_host[slot];
+    // windows routed to the pairwise path: a collective decision read off the gathered path column
+    bool any = false;
+    int64_t mine_k2 = 0;
+    for (size_t r = 0; r < (size_t)ranks * (size_t)w_max; ++r) {
+        const bool k2 = tab[r * RC + 2] == 2ull;
+        any = any || k2;
+        if (k2 && r / (size_t)w_max == (size_t)rank) ++mine_k2;
+    }
+    if (n_pairwise) *n_pairwise = mine_k2;
+    if (any) {
+        unsigned long long* base = (unsigned long long*)ctx->gslot[slot].p;
+        unsigned long long* mine = base + slot_words * (size_t)rank;
+        PG_CUDA(cudaStreamSynchronize(ctx->gather_stream));
+        PG_TRY(pg_popgen_resolve(ctx, ctx->gslot_min_sites[slot], ctx->gslot_min_data[slot], mine, (int)mine_k2));
+        if (ranks > 1) {
+            PG_NCCL(g_nccl.all_gather(mine, base, slot_words, NCCL_UINT64, (NcclComm)ctx->nccl_comm, ctx->stream));
+            ctx->launches += 1;
+        }
+        PG_CUDA(cudaMemcpyAsync(ctx->gslot_host[slot], base, total_words * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        PG_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    *h_table = ctx->gslot_host[slot];
+    return PG_OK;
+}
+
 namespace {
 // this rank's records (rc words per window, written by `enqueue` into its slot of the gather buffer) + all-gather + D2H
 template <typename F>

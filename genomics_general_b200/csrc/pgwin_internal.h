@@ -117,6 +117,15 @@ struct pg_ctx {
     int nccl_ranks = 1, nccl_rank = 0;
     PgBuf gather;
     size_t gather_words = 0;
+    // pipelined gather (pg_popgen_gather_begin / _end): two record tables, exchange + read-back on a side stream
+    cudaStream_t gather_stream = nullptr;
+    cudaEvent_t g_rec[2] = {nullptr, nullptr}, g_done[2] = {nullptr, nullptr};
+    PgBuf gslot[2];
+    void* gslot_host[2] = {nullptr, nullptr};
+    size_t gslot_host_cap[2] = {0, 0}, gslot_words[2] = {0, 0};
+    int64_t gslot_wmax[2] = {0, 0};
+    int32_t gslot_min_sites[2] = {0, 0};
+    double gslot_min_data[2] = {0, 0};
     void* h_pinned = nullptr;                 // small pinned staging for result read-back
     size_t h_pinned_cap = 0;
 };

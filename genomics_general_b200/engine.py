@@ -193,6 +193,21 @@ class Engine:
               "pg_popgen_allgather")
         return int(n.value)
 
+    def popgen_gather_begin(self, w_max: int, slot: int, min_sites: int = 1, min_data: float = 0.01):
+        """Pipelined popgen_allgather: enqueue one batch (statistics on the main stream, all-gather + D2H on a side stream)."""
+        check(self._lib.pg_popgen_gather_begin(self._ctx, int(min_sites) if min_sites else 0, float(min_data), int(w_max),
+                                               int(slot)), "pg_popgen_gather_begin")
+
+    def popgen_gather_end(self, w_max: int, slot: int) -> np.ndarray:
+        """-> float64 [world * w_max, popgen_record_width()] view of the slot's pinned table (valid until its next begin)."""
+        p = C.c_void_p()
+        n = C.c_int64(0)
+        check(self._lib.pg_popgen_gather_end(self._ctx, int(slot), C.byref(p), C.byref(n)), "pg_popgen_gather_end")
+        world = getattr(self, "_world", 1) or 1
+        shape = (world * int(w_max), self.popgen_record_width())
+        buf = (C.c_double * (shape[0] * shape[1])).from_address(p.value)
+        return np.frombuffer(buf, dtype=np.float64).reshape(shape)
+
     def abbababa_allgather(self, p1: int, p2: int, p3: int, o: int, min_data: float, w_max: int, table: np.ndarray):
         """ABBA-BABA statistics of this rank's windows + ONE ncclAllGather: `table` float64 [world * w_max, 8] receives
         [sites, pos_sum (int64 bit patterns), ABBA, BABA, D, fd, fdM, sitesUsed] per window (multigpu.unpack_abba_records)."""
@@ -361,13 +376,17 @@ class Engine:
         return ([hist[offs[k]:offs[k + 1]].reshape(shapes[k]) for k in range(len(groups))],
                 [first[offs[k]:offs[k + 1]].reshape(shapes[k]) for k in range(len(groups))], int(cnt.value))
 
-    def pairdist(self, hap_ind, n_ind: int, include_same_with_same: bool = False, min_sites: int = 0):
+    def pairdist(self, hap_ind, n_ind: int, include_same_with_same: bool = False, min_sites: int = 0, out=None):
         """-> dict(dist [W,n_ind,n_ind], sites [W], pos_sum [W]).  min_sites > 0 masks haplotype pairs with fewer
-        jointly non-missing sites (what an earlier groupDistStats does to the reference's cached matrix)."""
+        jointly non-missing sites (what an earlier groupDistStats does to the reference's cached matrix).
+        `out`: a caller-owned float64 [W, n_ind, n_ind] array; a PinnedArray's `.array` is written by the copy engine
+        directly (hundreds of MB of matrices otherwise spend most of their time in page faults of a fresh array)."""
         hap_ind = np.ascontiguousarray(hap_ind, dtype=np.int32)
         assert hap_ind.shape == (self.H,)
         W = self.W
-        dist = np.empty((W, n_ind, n_ind), dtype=np.float64)
+        if out is not None:
+            assert out.dtype == np.float64 and out.flags.c_contiguous and out.shape == (W, n_ind, n_ind)
+        dist = out if out is not None else np.empty((W, n_ind, n_ind), dtype=np.float64)
         sites = np.empty(W, dtype=np.int64)
         pos_sum = np.empty(W, dtype=np.int64)
         check(self._lib.pg_pairdist(self._ctx, int(n_ind), _ptr(hap_ind), 1 if include_same_with_same else 0,

@@ -185,6 +185,13 @@ int pg_nccl_init(pg_ctx* ctx, int32_t nranks, int32_t rank, const void* id128);
 int pg_nccl_finalize(pg_ctx* ctx);
 int pg_popgen_allgather(pg_ctx* ctx, int32_t min_sites, double min_data, int32_t force_path, int64_t w_max,
                         void* h_table, int64_t* n_pairwise);
+/* Pipelined form (two slots): `begin` enqueues site pass + finalize on the ctx stream and the exchange + read-back of the
+ * table on a side stream; `end` waits for that batch and returns the slot's pinned table (nranks * w_max records, valid until
+ * the slot's next `begin`).  begin(0); begin(1); end(0); begin(0); end(1); ... hides the all-gather and the D2H of one batch
+ * under the site pass of the next (the reference's sorter + writer run concurrently with its workers,
+ * popgenWindows.py:108-160).  Works without a communicator too (one rank). */
+int pg_popgen_gather_begin(pg_ctx* ctx, int32_t min_sites, double min_data, int64_t w_max, int32_t slot);
+int pg_popgen_gather_end(pg_ctx* ctx, int32_t slot, const void** h_table, int64_t* n_pairwise);
 /* The same for the ABBA-BABA statistics (ABBABABAwindows.py window-sharded over the GPUs): h_table receives
  * nranks * w_max * 8 words per window [sites (int64), pos_sum (int64), ABBA, BABA, D, fd, fdM, sitesUsed (doubles)],
  * and for genomics.fourPop: 17 words [sites, pos_sum, the 14 statistics in pg_fourpop's order, sitesUsed]. */
