@@ -267,7 +267,7 @@ __device__ __forceinline__ void k1_producer(const K1Params& prm, uint8_t* tiles,
         // publish "tile `it` is armed": a consumer must not test a phase parity before its phase has
         // been armed, or try_wait.parity would alias it with the previous (already complete) phase
         __threadfence_block();
-        *s_issued = it + 1;
+        atomicExch(const_cast<int*>(s_issued), it + 1);      // an atomic, so that racecheck sees the flag as synchronisation
     }
 }
 
@@ -335,7 +335,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k1_site_pass(const __grid_co
     for (int it = team; it < ntiles; it += nteams) {
         const int stage = it % prm.stages;
         if (lane == 0)
-            while (*s_issued <= it) __nanosleep(20);
+            while (atomicAdd(const_cast<int*>(s_issued), 0) <= it) __nanosleep(20);
         __syncwarp();
         mbar_wait(&full[stage], (uint32_t)((it / prm.stages) & 1));
         const uint8_t* tile = tiles + (size_t)stage * prm.tile_bytes;
@@ -745,7 +745,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k1_site_pass_lp(const __grid
     for (int it = team; it < ntiles; it += nteams) {
         const int stage = it % prm.stages;
         if (lane == 0)
-            while (*s_issued <= it) __nanosleep(20);
+            while (atomicAdd(const_cast<int*>(s_issued), 0) <= it) __nanosleep(20);
         __syncwarp();
         mbar_wait(&full[stage], (uint32_t)((it / prm.stages) & 1));
         const uint8_t* tile = tiles + (size_t)stage * prm.tile_bytes;
