@@ -84,7 +84,7 @@ __device__ __forceinline__ uint32_t valid2(uint32_t w0, uint32_t w1) {
     return (t | (t >> 2)) & 0x03030303u;
 }
 
-__global__ void __launch_bounds__(256) k2t_valid_class(const __grid_constant__ VcParams p) {
+__global__ void __launch_bounds__(256, 4) k2t_valid_class(const __grid_constant__ VcParams p) {
     extern __shared__ __align__(16) uint32_t vc_st[];      // [8 octets][pw]: byte (o, c) = valid bits of 8 sites of column c
     __shared__ int s_wtot[8];
     const int tid = threadIdx.x, lane = tid & 31, o = tid >> 5;
@@ -272,7 +272,7 @@ struct PqParams {
     int R, Hk;
 };
 
-__global__ void __launch_bounds__(256) k2t_build_pq(const __grid_constant__ PqParams p) {
+__global__ void __launch_bounds__(256, 4) k2t_build_pq(const __grid_constant__ PqParams p) {
     extern __shared__ __align__(16) uint32_t pq_st[];      // [2][8][pw]
     const int tid = threadIdx.x, lane = tid & 31, o = tid >> 5;
     for (int64_t chunk = blockIdx.x; chunk < p.nchunk; chunk += gridDim.x) {
@@ -377,14 +377,11 @@ constexpr int GRAM_MAX_STAGES = 4;
 constexpr int GRAM_MAX_RAW = 8;            // depth of the raw plane-word ring (TMA runs this many chunks ahead)
 constexpr int GRAM_MAX_ITEMS = (128 + 512) * 2 / 128;    // plane words per expanding thread and stage
 
-// 16 bits -> 16 bytes of 0/1 (byte k = bit k)
-__device__ __forceinline__ uint4 expand16(uint32_t x) {
-    uint4 r;
-    r.x = ((x & 0xfu) * 0x00204081u) & 0x01010101u;
-    r.y = (((x >> 4) & 0xfu) * 0x00204081u) & 0x01010101u;
-    r.z = (((x >> 8) & 0xfu) * 0x00204081u) & 0x01010101u;
-    r.w = (((x >> 12) & 0xfu) * 0x00204081u) & 0x01010101u;
-    return r;
+// 16 bits -> 16 bytes of 0/1 (byte k = bit k) through a 256-entry table in shared memory (8 bits -> 8 bytes per LDS.64):
+// 2 integer instructions + one load per byte of plane data instead of ~8 — the expansion, not the tensor pipe, paces the kernel
+__device__ __forceinline__ uint4 expand16(const uint2* lut, uint32_t x) {
+    const uint2 a = lut[x & 0xffu], b = lut[(x >> 8) & 0xffu];
+    return make_uint4(a.x, a.y, b.x, b.y);
 }
 
 // shared-memory matrix descriptor: K-major, no swizzle; core matrix = 8 rows x 16 bytes stored as 128 contiguous bytes;
@@ -455,7 +452,10 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) k2t_gram(const __grid_constan
     __shared__ __align__(8) uint64_t full[GRAM_MAX_STAGES], empty[GRAM_MAX_STAGES], raw_full[GRAM_MAX_RAW],
         raw_empty[GRAM_MAX_RAW], tmem_full, tmem_empty;
     __shared__ uint32_t s_tmem;
+    __shared__ __align__(8) uint2 s_lut[256];           // byte -> its 8 bits as 8 bytes of 0/1
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 256)
+        s_lut[tid] = make_uint2(((tid & 0xfu) * 0x00204081u) & 0x01010101u, (((tid >> 4) & 0xfu) * 0x00204081u) & 0x01010101u);
     const int NS = gp.nstages, RD = gp.nraw;
     const int AOFF = gp.a_sep ? 128 : 0;                // rows of the separate A region in front of the B rows
     const int RROWS = AOFF + gp.nbmax;                  // rows of one plane in a raw slot / operand block
@@ -575,10 +575,10 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) k2t_gram(const __grid_constan
                             const uint32_t wlo = (uint32_t)v[q], whi = (uint32_t)(v[q] >> 32);
                             uint8_t* d0 = sb + d_off[q];
                             uint8_t* d1 = d0 + NPL * BLK;
-                            *reinterpret_cast<uint4*>(d0) = expand16(wlo & 0xffffu);
-                            *reinterpret_cast<uint4*>(d0 + 128) = expand16(wlo >> 16);
-                            *reinterpret_cast<uint4*>(d1) = expand16(whi & 0xffffu);
-                            *reinterpret_cast<uint4*>(d1 + 128) = expand16(whi >> 16);
+                            *reinterpret_cast<uint4*>(d0) = expand16(s_lut, wlo);
+                            *reinterpret_cast<uint4*>(d0 + 128) = expand16(s_lut, wlo >> 16);
+                            *reinterpret_cast<uint4*>(d1) = expand16(s_lut, whi);
+                            *reinterpret_cast<uint4*>(d1 + 128) = expand16(s_lut, whi >> 16);
                         }
                     }
                 }

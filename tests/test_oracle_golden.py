@@ -151,7 +151,8 @@ def test_window_generators(idx):
         wins = do.sliding_coord_windows(scaf, pos, p["windSize"], p["stepSize"], exclude=p.get("exclude"))
     elif case["kind"] == "sites":
         wins = do.sliding_sites_windows(scaf, pos, p["windSites"], p["overlap"],
-                                        p["maxDist"] if p["maxDist"] else float("inf"), p["minSites"])
+                                        p["maxDist"] if p["maxDist"] else float("inf"), p["minSites"],
+                                        exclude=p.get("exclude"))
     else:
         wins = do.predefined_coord_windows(scaf, pos, [tuple(c) for c in p["windCoords"]])
     assert len(wins) == len(case["windows"]), (len(wins), len(case["windows"]))
