@@ -357,8 +357,9 @@ struct GramParams {
     int nb;                     // windows
     int nbmax;                  // max nb_rows over the groups (shared-memory geometry)
     int a_sep;                  // some group's A tile lies outside its B range: blocks carry a separate 128-row A region
-    int nstages;                // operand ring depth
-    int nraw;                   // raw plane-word ring depth
+    int nstages;                // operand ring depth (a multiple of xg)
+    int nraw;                   // raw plane-word ring depth (a multiple of xg)
+    int xg;                     // expanding groups at work (3, or 2 when only two operand stages fit)
     int32_t* out;               // [nb][Hk][Hk], upper triangle (i <= j) only
 };
 
@@ -373,15 +374,20 @@ constexpr int GRAM_XWARPS = 4 * GRAM_XGROUPS;
 constexpr int GRAM_WARP_MMA = GRAM_XWARPS, GRAM_WARP_TMA = GRAM_XWARPS + 1, GRAM_WARP_EPI = GRAM_XWARPS + 2;
 constexpr int GRAM_EPI_WARPS = 8;
 constexpr int GRAM_THREADS = (GRAM_WARP_EPI + GRAM_EPI_WARPS) * 32;
-constexpr int GRAM_MAX_STAGES = 4;
-constexpr int GRAM_MAX_RAW = 8;            // depth of the raw plane-word ring (TMA runs this many chunks ahead)
+constexpr int GRAM_MAX_STAGES = 9;
+constexpr int GRAM_MAX_RAW = 9;            // depth of the raw plane-word ring (TMA runs this many chunks ahead)
 constexpr int GRAM_MAX_ITEMS = (128 + 512) * 2 / 128;    // plane words per expanding thread and stage
 
-// 16 bits -> 16 bytes of 0/1 (byte k = bit k) through a 256-entry table in shared memory (8 bits -> 8 bytes per LDS.64):
-// 2 integer instructions + one load per byte of plane data instead of ~8 — the expansion, not the tensor pipe, paces the kernel
-__device__ __forceinline__ uint4 expand16(const uint2* lut, uint32_t x) {
-    const uint2 a = lut[x & 0xffu], b = lut[(x >> 8) & 0xffu];
-    return make_uint4(a.x, a.y, b.x, b.y);
+// 16 bits -> 16 bytes of 0/1 (byte k = bit k): 4 bits -> 4 bytes is one IMAD + LOP3.  (A 256-entry shared-memory table,
+// 8 bits -> 8 bytes per LDS.64, was measured and dropped: the kernel is short of shared-memory bandwidth — the SS-mode MMAs
+// read (128 + N) x 32 bytes per instruction — not of integer issue slots; gram_diff went from 1.07 to 1.35 ms with it.)
+__device__ __forceinline__ uint4 expand16(uint32_t x) {
+    uint4 r;
+    r.x = ((x & 0xfu) * 0x00204081u) & 0x01010101u;
+    r.y = (((x >> 4) & 0xfu) * 0x00204081u) & 0x01010101u;
+    r.z = (((x >> 8) & 0xfu) * 0x00204081u) & 0x01010101u;
+    r.w = (((x >> 12) & 0xfu) * 0x00204081u) & 0x01010101u;
+    return r;
 }
 
 // shared-memory matrix descriptor: K-major, no swizzle; core matrix = 8 rows x 16 bytes stored as 128 contiguous bytes;
@@ -401,6 +407,13 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t a, uint64_t b,
         "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
         "l"(a), "l"(b), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+// one lane of a converged warp (the MMA warp runs its loop with all 32 lanes so that addresses and descriptors stay in
+// uniform registers; only the elected lane issues)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -452,10 +465,7 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) k2t_gram(const __grid_constan
     __shared__ __align__(8) uint64_t full[GRAM_MAX_STAGES], empty[GRAM_MAX_STAGES], raw_full[GRAM_MAX_RAW],
         raw_empty[GRAM_MAX_RAW], tmem_full, tmem_empty;
     __shared__ uint32_t s_tmem;
-    __shared__ __align__(8) uint2 s_lut[256];           // byte -> its 8 bits as 8 bytes of 0/1
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid < 256)
-        s_lut[tid] = make_uint2(((tid & 0xfu) * 0x00204081u) & 0x01010101u, (((tid >> 4) & 0xfu) * 0x00204081u) & 0x01010101u);
     const int NS = gp.nstages, RD = gp.nraw;
     const int AOFF = gp.a_sep ? 128 : 0;                // rows of the separate A region in front of the B rows
     const int RROWS = AOFF + gp.nbmax;                  // rows of one plane in a raw slot / operand block
@@ -472,7 +482,7 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) k2t_gram(const __grid_constan
     if (warp == GRAM_WARP_MMA) {
         if (lane == 0) {
             for (int s = 0; s < NS; ++s) {
-                mbar_init(&full[s], 4);                 // the four warps of the expanding group that owns the stage
+                mbar_init(&full[s], 4);                 // the four warps of the expanding group that owns the slot
                 mbar_init(&empty[s], 1);
             }
             for (int s = 0; s < RD; ++s) {
@@ -519,16 +529,19 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) k2t_gram(const __grid_constan
         }
     } else if (warp < GRAM_XWARPS) {
         // ---------------- expand: plane words -> 0/1 bytes in the core-matrix layout ----------------
-        // Group xg owns the global stages gs with gs % NS == xg, i.e. always operand slot xg, and (RD being a multiple of NS)
-        // always the same raw slots: every barrier a group waits on is one whose previous phase the same group consumed, so
-        // a parity wait can never alias with an older phase.  Groups >= NS stay idle (NS < 3 only when shared memory is short).
+        // Group xg owns the global stages gs with gs % XG == xg.  NS and RD are multiples of XG, so a group always cycles
+        // through the same operand slots (xg, xg + XG, ...) and the same raw slots in the same order: every barrier it waits on
+        // is one whose previous phase the same group consumed, and a parity wait can never alias with an older phase.
+        // Several slots per group matter: a slot comes back only after the MMAs that read it have completed (the tensor
+        // pipe's latency), and with one slot per group that latency sat in every group's critical path.
+        const int XG = gp.xg;
         const int xg = warp >> 2, xt = tid & 127;          // expanding group, thread inside the group
-        const int RM = RD / NS;                            // raw slots of this group: xg, xg + NS, ...
-        int n_done = 0;                                    // stages this group has processed: stage n is gs = xg + n NS
-        int rm = 0;                                        // n_done % RM
-        uint32_t rph = 0;                                  // (n_done / RM) & 1
+        const int SM_ = NS / XG, RM = RD / XG;             // operand / raw slots of this group
+        int n_done = 0;                                    // stages this group has processed: stage n is gs = xg + n XG
+        int sm = 0, rm = 0;                                // n_done % SM_, n_done % RM
+        uint32_t sph = 0, rph = 0;                         // (n_done / SM_) & 1, (n_done / RM) & 1
         int64_t gbase = 0;                                 // global stage index of the item's first stage
-        for (int64_t j = j0; j < j1 && xg < NS; ++j) {
+        for (int64_t j = j0; j < j1 && xg < XG; ++j) {
             const GramItem im = gram_item<NPL>(gp, j);
             const bool a_in_b = (im.g.a_row0 == im.g.b_row0);
             // rows expanded per plane: [separate A tile (128 rows)] + B range
@@ -550,10 +563,10 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) k2t_gram(const __grid_constan
                     d_off[q] = pl * BLK + (row >> 3) * 256 + (row & 7) * 16;
                 }
             }
-            // first local stage of this group: (gbase + it) % NS == xg
-            int it = (int)(((int64_t)xg - gbase % NS + NS) % NS);
-            for (; it < im.nst; it += NS) {
-                const int rslot = xg + NS * rm;
+            // first local stage of this group: (gbase + it) % XG == xg
+            int it = (int)(((int64_t)xg - gbase % XG + XG) % XG);
+            for (; it < im.nst; it += XG) {
+                const int rslot = xg + XG * rm, sslot = xg + XG * sm;
                 const int64_t chunk = im.c_first + it;
                 uint64_t mask = ~0ull;
                 {
@@ -566,8 +579,8 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) k2t_gram(const __grid_constan
                 uint64_t v[GRAM_MAX_ITEMS];
 #pragma unroll
                 for (int q = 0; q < GRAM_MAX_ITEMS; ++q) v[q] = (r_idx[q] >= 0) ? (rw[r_idx[q]] & mask) : 0ull;
-                if (n_done > 0) mbar_wait(&empty[xg], (uint32_t)((n_done - 1) & 1));
-                uint8_t* sb = op_base + (size_t)xg * STAGE;
+                if (n_done >= SM_) mbar_wait(&empty[sslot], sph ^ 1u);
+                uint8_t* sb = op_base + (size_t)sslot * STAGE;
 #pragma unroll
                 for (int q = 0; q < GRAM_MAX_ITEMS; ++q) {
                     if (q * 128 < nitems) {                 // warp-uniform: no instructions for item slots nobody uses
@@ -575,17 +588,17 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) k2t_gram(const __grid_constan
                             const uint32_t wlo = (uint32_t)v[q], whi = (uint32_t)(v[q] >> 32);
                             uint8_t* d0 = sb + d_off[q];
                             uint8_t* d1 = d0 + NPL * BLK;
-                            *reinterpret_cast<uint4*>(d0) = expand16(s_lut, wlo);
-                            *reinterpret_cast<uint4*>(d0 + 128) = expand16(s_lut, wlo >> 16);
-                            *reinterpret_cast<uint4*>(d1) = expand16(s_lut, whi);
-                            *reinterpret_cast<uint4*>(d1 + 128) = expand16(s_lut, whi >> 16);
+                            *reinterpret_cast<uint4*>(d0) = expand16(wlo & 0xffffu);
+                            *reinterpret_cast<uint4*>(d0 + 128) = expand16(wlo >> 16);
+                            *reinterpret_cast<uint4*>(d1) = expand16(whi & 0xffffu);
+                            *reinterpret_cast<uint4*>(d1 + 128) = expand16(whi >> 16);
                         }
                     }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
                 __syncwarp();
                 if (lane == 0) {
-                    mbar_arrive(&full[xg]);
+                    mbar_arrive(&full[sslot]);
                     // released only now: the stores above consumed the words, so the loads from the slot have completed
                     // before the TMA (async proxy) may overwrite it — an arrive right after issuing the loads raced with
                     // the refill
@@ -596,16 +609,21 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) k2t_gram(const __grid_constan
                     rm = 0;
                     rph ^= 1u;
                 }
+                if (++sm == SM_) {
+                    sm = 0;
+                    sph ^= 1u;
+                }
             }
             gbase += im.nst;
         }
     } else if (warp == GRAM_WARP_MMA) {
-        // ---------------- MMA issue (one thread) ----------------
-        if (lane == 0) {
-            // The issuing thread is a serial instruction stream: everything that does not change per stage is hoisted, a
-            // descriptor is one 32-bit add (the shared-memory address field sits in the low word), and the MMAs of a stage are
-            // straight-line code.  (A first version rebuilt descriptors and loop bounds per MMA: ~450 instructions and
-            // ~1000 cycles per stage — the issuing thread, not the tensor pipe, set the pace.)
+        // ---------------- MMA issue ----------------
+        // The whole warp runs the loop (waits included) so that everything stays warp-uniform — the compiler keeps ring
+        // positions, shared-memory addresses and descriptors in uniform registers, which is what UTCIMMA takes; one elected lane
+        // issues.  Everything that does not change per stage is hoisted and a descriptor is one 32-bit add (the shared-memory
+        // address field sits in the low word).  (Earlier versions ran the loop in lane 0 alone: ~450, then ~110 dependent
+        // instructions per stage through R2UR moves — the issuing thread, not the tensor pipe, set the pace.)
+        {
             const uint32_t sbase16 = smem_u32(op_base) >> 4;
             const uint32_t DLO = (128u >> 4) << 16;                       // LBO
             const uint32_t DHI = (256u >> 4) | (1u << 14);                // SBO | descriptor version 1
@@ -628,27 +646,31 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) k2t_gram(const __grid_constan
                     mbar_wait(&full[sp.s], sp.ph);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t st16 = sbase16 + (uint32_t)sp.s * stage16;
+                    if (elect_one()) {
 #pragma unroll
-                    for (int ks = 0; ks < 2; ++ks) {
-                        const uint32_t acc0 = (it > 0 || ks > 0) ? 1u : 0u;
-                        if (NPL == 1) {
-                            const uint32_t blk = st16 + ks * blk16;
-                            umma_i8(tmem, D(blk + a16), D(blk + b16), id_a, acc0);
-                            if (n_b > 0) umma_i8(tmem + 256, D(blk + a16), D(blk + b16 + 512), id_b, acc0);
-                        } else {
-                            const uint32_t bp = st16 + (ks * 2) * blk16, bq = bp + blk16;
-                            umma_i8(tmem, D(bp + a16), D(bq + b16), id_a, acc0);
-                            umma_i8(tmem, D(bq + a16), D(bp + b16), id_a, 1u);
-                            if (n_b > 0) {
-                                umma_i8(tmem + 256, D(bp + a16), D(bq + b16 + 512), id_b, acc0);
-                                umma_i8(tmem + 256, D(bq + a16), D(bp + b16 + 512), id_b, 1u);
+                        for (int ks = 0; ks < 2; ++ks) {
+                            const uint32_t acc0 = (it > 0 || ks > 0) ? 1u : 0u;
+                            if (NPL == 1) {
+                                const uint32_t blk = st16 + ks * blk16;
+                                umma_i8(tmem, D(blk + a16), D(blk + b16), id_a, acc0);
+                                if (n_b > 0) umma_i8(tmem + 256, D(blk + a16), D(blk + b16 + 512), id_b, acc0);
+                            } else {
+                                const uint32_t bp = st16 + (ks * 2) * blk16, bq = bp + blk16;
+                                umma_i8(tmem, D(bp + a16), D(bq + b16), id_a, acc0);
+                                umma_i8(tmem, D(bq + a16), D(bp + b16), id_a, 1u);
+                                if (n_b > 0) {
+                                    umma_i8(tmem + 256, D(bp + a16), D(bq + b16 + 512), id_b, acc0);
+                                    umma_i8(tmem + 256, D(bq + a16), D(bp + b16 + 512), id_b, 1u);
+                                }
                             }
                         }
+                        umma_commit(&empty[sp.s]);  // arrives when the MMAs above have read the stage
                     }
-                    umma_commit(&empty[sp.s]);      // arrives when the MMAs above have read the stage
+                    __syncwarp();
                     sp.advance(1, NS);
                 }
-                umma_commit(&tmem_full);            // arrives when every MMA of the item has completed
+                if (elect_one()) umma_commit(&tmem_full);   // arrives when every MMA of the item has completed
+                __syncwarp();
             }
         }
     } else {
@@ -955,8 +977,8 @@ int pg_k2t_pairs(pg_ctx* ctx, const K2TPlanes& ps, const int64_t* d_lo, const in
                  int32_t* d_n) {
     static bool attr_dev[64] = {};
     if (!attr_dev[ctx->device & 63]) {
-        PG_CUDA(cudaFuncSetAttribute(k2t_gram<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-        PG_CUDA(cudaFuncSetAttribute(k2t_gram<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+        PG_CUDA(cudaFuncSetAttribute(k2t_gram<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+        PG_CUDA(cudaFuncSetAttribute(k2t_gram<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
         attr_dev[ctx->device & 63] = true;
     }
     // n_ij over the mask rows (one per sample when the haplotypes of a sample share their missingness), diff_ij over all rows
@@ -977,17 +999,25 @@ int pg_k2t_pairs(pg_ctx* ctx, const K2TPlanes& ps, const int64_t* d_lo, const in
     gp.nb = nb;
     // shared memory: an operand ring of (ideally) one stage per expanding group + the raw plane-word ring + 4 KB slack (the
     // 128-row A tile of a diagonal group may reach past a short B range)
-    const int budget = 224 * 1024;
+    const int budget = 222 * 1024;            // + 2.3 KB of static shared memory (barriers, the expansion table) <= 227 KB
     const int fixed = 4096;
-    auto geometry = [&](int npl, int nbmax, int a_sep, int& nstages, int& nraw) {
+    auto geometry = [&](int npl, int nbmax, int a_sep, int& nstages, int& nraw, int& xg) {
         const int rrows = (a_sep ? 128 : 0) + nbmax;
         const int stage = 2 * npl * rrows * 32, raw = npl * rrows * 8;
-        nstages = std::max(2, std::min(GRAM_XGROUPS, (budget - fixed - 3 * raw) / stage));
+        // operand stages: 9, 6 or 3 (three expanding groups with 3 / 2 / 1 slots each), else 2 (two groups); raw slots a
+        // multiple of the group count too, so that every slot has ONE consumer group
+        const int avail = budget - fixed;
+        nstages = 2;
+        for (int cand : {9, 6, 3})
+            if (cand * stage + 3 * raw <= avail) {
+                nstages = cand;
+                break;
+            }
         if (const char* e = getenv("PG_K2T_NSTAGES")) nstages = std::max(1, std::min(nstages, atoi(e)));
-        // one expanding group per operand stage; raw slots in multiples of that, so that every slot has ONE consumer group
-        int mult = std::min(GRAM_MAX_RAW / nstages, (budget - fixed - nstages * stage) / (raw * nstages));
+        xg = (nstages % 3 == 0) ? 3 : (nstages % 2 == 0 ? 2 : 1);
+        int mult = std::min(GRAM_MAX_RAW / xg, (avail - nstages * stage) / (raw * xg));
         if (const char* e = getenv("PG_K2T_NRAW")) mult = std::min(mult, atoi(e));
-        nraw = std::max(1, mult) * nstages;
+        nraw = std::max(1, mult) * xg;
         return (size_t)nstages * stage + (size_t)nraw * raw + fixed;
     };
     {   // persistent CTAs: one per SM, each works through a contiguous range of (window, group) items
@@ -997,7 +1027,7 @@ int pg_k2t_pairs(pg_ctx* ctx, const K2TPlanes& ps, const int64_t* d_lo, const in
         gp.ngroups = (int)gn.size();
         gp.nbmax = nbmax_n;
         gp.a_sep = asep_n;
-        const size_t smem = geometry(1, nbmax_n, asep_n, gp.nstages, gp.nraw);
+        const size_t smem = geometry(1, nbmax_n, asep_n, gp.nstages, gp.nraw, gp.xg);
         gp.plane = ps.vpair ? ps.vpair : ps.vplane;
         gp.cps = nullptr;
         gp.out = d_n;
@@ -1014,7 +1044,7 @@ int pg_k2t_pairs(pg_ctx* ctx, const K2TPlanes& ps, const int64_t* d_lo, const in
         gp.ngroups = (int)gd.size();
         gp.nbmax = nbmax_d;
         gp.a_sep = asep_d;
-        const size_t smem = geometry(2, nbmax_d, asep_d, gp.nstages, gp.nraw);
+        const size_t smem = geometry(2, nbmax_d, asep_d, gp.nstages, gp.nraw, gp.xg);
         gp.plane = ps.pq;
         gp.cps = ps.cps;
         gp.out = d_diff;
