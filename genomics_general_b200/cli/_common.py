@@ -29,6 +29,10 @@ def add_engine_args(p):
     p.add_argument("--device", help="CUDA device index", type=int, default=0)
     p.add_argument("--parseThreads", help="Host threads for the .geno tokenizer", type=int, default=None)
     p.add_argument("--hostParse", help="Tokenise the .geno text on the host instead of on the GPU", action="store_true")
+    p.add_argument("--cache", help="Keep a binary cache <genoFile>.gbin of the ingested matrix and load it on later runs "
+                                   "(same file, format, samples and ploidy)", action="store_true")
+    p.add_argument("--timing", help="Write a JSON file with the wall time of each phase and the device time of each kernel",
+                   metavar="FILE")
     p.add_argument("--devices", help="Number of GPUs: every GPU tokenises its share of the file and computes the windows that "
                                      "start there (one process per GPU, one NCCL all-gather of the rows)", type=int, default=None)
 
@@ -146,6 +150,19 @@ def load_geno(args, samples, ploidyDict, header=None, engine=None):
     """The whole file as a dense matrix.  With an engine the text is tokenised on the GPU and the matrix stays there
     (GenoData.geno is None); files too large for device memory, and --hostParse, go through the host tokenizer."""
     src = args.genoFile if args.genoFile else stdin_bytes()
+    cache = None
+    if engine is not None and getattr(args, "cache", False) and isinstance(src, str) and not src.endswith(".gz"):
+        cache = src + ".gbin"
+        gd = geno_io.load_gbin(cache, engine, src, args.genoFormat, samples=samples, ploidy=ploidyDict, header=header)
+        if gd is not None:
+            return gd
+    gd = _load_geno_uncached(args, src, samples, ploidyDict, header, engine)
+    if cache is not None:
+        geno_io.save_gbin(cache, gd, src, args.genoFormat, eng=engine)
+    return gd
+
+
+def _load_geno_uncached(args, src, samples, ploidyDict, header, engine):
     if engine is not None and not getattr(args, "hostParse", False):
         if not isinstance(src, str) or src.endswith(".gz"):
             src = geno_io.read_bytes(src)          # stdin / gzip: decompressed in host memory
@@ -157,6 +174,37 @@ def load_geno(args, samples, ploidyDict, header=None, engine=None):
                 raise
     return geno_io.parse_geno(src, geno_format=args.genoFormat, samples=samples, ploidy=ploidyDict, header=header,
                               threads=getattr(args, "parseThreads", None))
+
+
+class Timing:
+    """--timing FILE (the reference only prints progress counters): wall seconds of each phase of the
+    command line and the device milliseconds of every kernel of the statistics calls, as one JSON object."""
+
+    def __init__(self, path):
+        import time
+        self.path, self.t0, self.last = path, time.perf_counter(), time.perf_counter()
+        self.phases, self.kernels = {}, {}
+
+    def mark(self, name, eng=None):
+        import time
+        now = time.perf_counter()
+        self.phases[name] = self.phases.get(name, 0.0) + (now - self.last)
+        self.last = now
+        if eng is not None:
+            try:
+                for k, v in eng.last_timings().items():
+                    self.kernels[k] = self.kernels.get(k, 0.0) + v["ms"]
+            except Exception:
+                pass
+
+    def write(self, **extra):
+        import json
+        import time
+        if not self.path:
+            return
+        with open(self.path, "wt") as f:
+            json.dump(dict(phases_s=self.phases, kernels_ms=self.kernels, total_s=time.perf_counter() - self.t0, **extra), f,
+                      indent=1)
 
 
 def ensure_resident(eng, gd):

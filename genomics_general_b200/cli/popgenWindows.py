@@ -105,6 +105,7 @@ def main(argv=None):
     out.write(",".join(stats) + "\n")
 
     eng = Engine(args.device if rdv is None else mgpu.device_for(rdv, args.device))
+    tm = C.Timing(args.timing if (rdv is None or rdv.rank == 0) else None)
 
     # columns in the reference's haplotype order (sorted sequence names): H12's greedy clustering breaks ties by row
     col_order = C.alignment_order(sampleData.indNames, ploidyDict, args.genoFormat)
@@ -112,7 +113,9 @@ def main(argv=None):
         gd = C.load_geno(args, col_order, ploidyDict, header=args.header, engine=eng)
     else:
         gd, starts, off_all = mgpu.sharded_ingest(eng, rdv, args.genoFile, args.genoFormat, col_order, ploidyDict, args.header)
+    tm.mark("ingest", eng)
     ws = C.make_windows(args, gd, minSites, coords, C.read_scaffold_list(args.include), C.read_scaffold_list(args.exclude))
+    tm.mark("windows")
     sys.stderr.write("\n%d sites x %d haplotypes, %d windows\n" % (gd.n_sites, gd.n_haps, len(ws)))
     lo, hi = ws.ranges()
     written = 0
@@ -162,6 +165,7 @@ def main(argv=None):
         if "hapStats" in args.analysis:
             hst = eng.hapstats(args.hapDist, min_sites=masked, diag_nan=bool(masked) or "popDist" in args.analysis
                                or "popPairDist" in args.analysis or "indPairDist" in args.analysis)
+        tm.mark("statistics", eng)
         iu = np.triu_indices(len(ind_sorted)) if dmat is not None else None
         for k in range(len(ws)):
             pre = C.window_prefix(args, ws, k, gd, r["sites"][k], r["pos_sum"][k])
@@ -192,6 +196,8 @@ def main(argv=None):
                 written += 1
     if out is not sys.stdout:
         out.close()
+    tm.mark("rows")
+    tm.write(sites=int(gd.n_sites), haplotypes=int(gd.n_haps), windows=len(ws), devices=(1 if rdv is None else rdv.world))
     if rdv is not None:
         rdv.finish()
     sys.stderr.write(str(len(ws)) + " windows were tested.\n")

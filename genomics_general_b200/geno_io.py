@@ -232,3 +232,74 @@ def format_matrix_rows(m, sep=" ", prefixes=None, threads=None) -> str:
                                            None if pre is None else C.cast(pre, C.c_void_p), buf.ctypes.data_as(C.c_void_p),
                                            seg_cap, threads, seg_len.ctypes.data_as(C.c_void_p)), "pg_format_matrix_rows")
     return b"".join(buf[t * seg_cap: t * seg_cap + int(seg_len[t])].tobytes() for t in range(threads)).decode()
+
+
+# ------------------------------------------------------------------------------------------------
+# .gbin — binary cache of an ingested file: the reference re-parses the text on every run
+# (genomics.py:1884-1904); a second run on the same file loads the dense matrix instead.
+# ------------------------------------------------------------------------------------------------
+GBIN_MAGIC = b"PGWINGB1"
+
+
+def _gbin_key(source, geno_format, names, ploidy):
+    st = os.stat(source)
+    return dict(source=os.path.abspath(source), size=int(st.st_size), mtime_ns=int(st.st_mtime_ns), geno_format=geno_format,
+                names=list(names), ploidy=[int(p) for p in ploidy])
+
+
+def save_gbin(path, gd: GenoData, source, geno_format, eng=None):
+    """Write `<path>`: magic | uint64 header length | JSON header | pos int32 [S] | scaf_ids int32 [S] | geno int8 [S x H]
+    (reference codes A0 C1 G2 T3, -1 missing).  With gd.geno None the matrix is read back from the engine slab by slab."""
+    import json
+    S, H = gd.n_sites, gd.n_haps
+    head = dict(_gbin_key(source, geno_format, gd.names, gd.ploidy), n_sites=S, n_haps=H, scaf_names=list(gd.scaf_names),
+                header=gd.header)
+    blob = json.dumps(head).encode()
+    tmp = path + ".tmp%d" % os.getpid()
+    with open(tmp, "wb") as f:
+        f.write(GBIN_MAGIC)
+        f.write(np.uint64(len(blob)).tobytes())
+        f.write(blob)
+        f.write(np.ascontiguousarray(gd.pos, dtype=np.int32).tobytes())
+        f.write(np.ascontiguousarray(gd.scaf_ids, dtype=np.int32).tobytes())
+        if gd.geno is not None:
+            f.write(np.ascontiguousarray(gd.geno, dtype=np.int8).tobytes())
+        else:
+            slab = 1 << 20
+            for s in range(0, S, slab):
+                g, _ = eng.download(s, min(slab, S - s), want_pos=False)
+                f.write(g.tobytes())
+    os.replace(tmp, path)
+
+
+def load_gbin(path, eng, source, geno_format, samples=None, ploidy=None, header=None):
+    """-> GenoData with the matrix uploaded to `eng` (geno = None), or None when the cache does not match the request
+    (other file / size / mtime / format / samples / ploidy)."""
+    import json
+    if not os.path.exists(path):
+        return None
+    with open(path, "rb") as f:
+        if f.read(8) != GBIN_MAGIC:
+            return None
+        n = int(np.frombuffer(f.read(8), dtype=np.uint64)[0])
+        head = json.loads(f.read(n).decode())
+        data_off = 16 + n
+    if header is None:
+        header = head["header"]
+    file_names, want, fmt, pl, col_take = _select(header, geno_format, samples, ploidy)
+    try:
+        key = _gbin_key(source, geno_format, want, pl)
+    except OSError:
+        return None
+    if any(head.get(k) != v for k, v in key.items()):
+        return None
+    S, H = int(head["n_sites"]), int(head["n_haps"])
+    pos = np.fromfile(path, dtype=np.int32, count=S, offset=data_off)
+    scaf_ids = np.fromfile(path, dtype=np.int32, count=S, offset=data_off + 4 * S)
+    geno = np.memmap(path, dtype=np.int8, mode="r", offset=data_off + 8 * S, shape=(S, H)) if S else np.zeros((0, H), np.int8)
+    eng.upload(geno, pos)                      # slabs through the pinned staging buffers of pg_upload
+    del geno
+    pl = np.asarray(pl, dtype=np.int8)
+    hap_off = np.concatenate([[0], np.cumsum(pl.astype(np.int64))[:-1]]).astype(np.int32) if len(pl) else np.zeros(0, np.int32)
+    return GenoData(geno=None, pos=pos, scaf_ids=scaf_ids, scaf_names=list(head["scaf_names"]), names=list(want), ploidy=pl,
+                    hap_off=hap_off, header=header)

@@ -222,3 +222,33 @@ def test_sfs_genotype_command_line(key, tmp_path, capsys):
     sfs_cli.main(["-i", path, "--inputType", "genotypes", "--popsFile", pops, "--pipe", "-p", "pop0", "-p", "pop1", "-p", "pop2",
                   "-p", "pop3"] + CLI2[key + "_args"])
     assert capsys.readouterr().out == CLI2[key]
+
+
+def test_gbin_cache_and_timing_file(inputs, tmp_path):
+    """--cache writes <geno>.gbin after the first ingest and loads it on the next run (same rows, no tokenisation); a stale or
+    mismatching cache is ignored; --timing writes the phase / kernel times as JSON"""
+    import shutil
+    from genomics_general_b200.cli import popgenWindows
+    i = inputs["two_pops"] if "two_pops" in inputs else inputs[list(inputs)[0]]
+    c = i["cfg"]
+    g = str(tmp_path / "c.geno")
+    shutil.copy(i["geno"], g)
+    o2, tj = str(tmp_path / "o2.csv"), str(tmp_path / "t.json")
+    from oracle_engine import OracleEngine
+    # direct test of the cache functions (engine-independent)
+    from genomics_general_b200 import geno_io
+    gd = geno_io.parse_geno(g, geno_format="phased")
+    cache = g + ".gbin"
+    geno_io.save_gbin(cache, gd, g, "phased")
+    eng = OracleEngine()
+    back = geno_io.load_gbin(cache, eng, g, "phased")
+    assert back is not None and back.geno is None
+    assert np.array_equal(eng.g, gd.geno) and np.array_equal(back.pos, gd.pos) and np.array_equal(back.scaf_ids, gd.scaf_ids)
+    assert back.scaf_names == gd.scaf_names and back.names == gd.names
+    assert geno_io.load_gbin(cache, eng, g, "phased", samples=gd.names[:3]) is None          # other sample selection
+    os.utime(g, ns=(1, 1))
+    assert geno_io.load_gbin(cache, eng, g, "phased") is None                                # the source changed
+    popgenWindows.main(["-w", str(c["w"]), "-m", str(c["m"]), "-g", i["geno"], "-o", o2, "-f", "phased", "-T", "1", "--popsFile",
+                        i["pops"], "--timing", tj] + i["popargs"])
+    t = json.load(open(tj))
+    assert set(t["phases_s"]) == {"ingest", "windows", "statistics", "rows"} and t["windows"] > 0 and t["sites"] == c["S"]

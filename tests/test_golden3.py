@@ -183,3 +183,29 @@ def test_freq_reads_piped_genotypes(engine, tmp_path, monkeypatch):
     freq.main(["-o", o, "-f", "phased", "-t", "1", "--popsFile", pops, "-p", "pop0", "-p", "pop1", "-p", "pop2"])
     _common._STDIN.clear()
     _same_text(o, C3["freq_cli"]["stdin"])
+
+
+@pytest.mark.gpu
+def test_gbin_cache_second_run_skips_tokenisation(tmp_path):
+    """--cache: the second run of the command line loads <geno>.gbin (no text ingest) and writes the same rows"""
+    from genomics_general_b200.cli import _common, popgenWindows
+    path, pops = _write_hap_inputs(tmp_path)
+    outs = []
+    real = _common._load_geno_uncached
+    calls = []
+
+    def counting(*a, **k):
+        calls.append(1)
+        return real(*a, **k)
+    _common._load_geno_uncached = counting
+    try:
+        for k in range(2):
+            o = str(tmp_path / ("o%d.csv" % k))
+            popgenWindows.main(["-g", path, "-o", o, "-f", "phased", "-T", "1", "--popsFile", pops, "-p", "popA", "-p", "popB",
+                                "--windType", "sites", "-w", "400", "-m", "380", "--roundTo", "10", "--cache",
+                                "--analysis", "popDist", "popPairDist", "hapStats", "--hapDist", "0.01"])
+            outs.append(open(o).read())
+    finally:
+        _common._load_geno_uncached = real
+    assert os.path.exists(path + ".gbin") and len(calls) == 1          # tokenised once
+    assert outs[0] == outs[1] and outs[0].count("\n") > 2
