@@ -1,7 +1,7 @@
-"""Window sharding across the GPUs of one box: one process per GPU (torchrun), contiguous window
-shards balanced by site count, no data-path collective, and ONE all-gather of the fixed-width per-window
-records at the end.  torch.distributed is plumbing only (NCCL on GPUs, gloo in the CPU
-tests); the statistics come from libpgwin.so.
+"""Window sharding across the GPUs of one box: one process per GPU, contiguous window shards balanced by site
+count, no data-path collective, and ONE all-gather of the fixed-width per-window records at the end —
+issued by the C-ABI itself (pg_*_allgather, native NCCL).  This module is host arithmetic only (no torch): shard
+boundaries and the layouts of the gathered record tables.  The command lines' multi-GPU path is in mgpu.py.
 """
 from __future__ import annotations
 
@@ -36,64 +36,6 @@ def shard_site_range(lo, hi, w_begin: int, w_end: int):
     lo = np.asarray(lo, dtype=np.int64)[w_begin:w_end]
     hi = np.asarray(hi, dtype=np.int64)[w_begin:w_end]
     return int(lo.min()), int(hi.max())
-
-
-def all_gather_rows(local_rows: np.ndarray, counts, device=None):
-    """All-gather per-window records (float64 [W_local, C]) from every rank into [W_total, C], in rank order.
-
-    counts: number of windows per rank (known to every rank from shard_windows).  Uses one
-    torch.distributed.all_gather on a padded buffer (NCCL when `device` is a CUDA device, gloo on CPU)."""
-    import torch
-    import torch.distributed as dist
-
-    world = dist.get_world_size()
-    C = local_rows.shape[1]
-    wmax = max(int(c) for c in counts) if len(counts) else 0
-    buf = torch.zeros((max(wmax, 1), C), dtype=torch.float64, device=device)
-    if local_rows.shape[0]:
-        buf[: local_rows.shape[0]] = torch.from_numpy(np.ascontiguousarray(local_rows)).to(buf.device)
-    out = [torch.empty_like(buf) for _ in range(world)]
-    dist.all_gather(out, buf)
-    parts = [out[r][: int(counts[r])].cpu().numpy() for r in range(world)]
-    return np.concatenate(parts, axis=0) if parts else np.zeros((0, C))
-
-
-def popgen_records(res: dict) -> np.ndarray:
-    """Pack a popgen result dict into fixed-width float64 records [W, 3 + P + 2*npairs]
-    (sites, pos_sum and path are exactly representable in float64)."""
-    return np.concatenate([res["sites"][:, None].astype(np.float64), res["pos_sum"][:, None].astype(np.float64),
-                           res["path"][:, None].astype(np.float64), res["pi"], res["dxy"], res["fst"]], axis=1)
-
-
-def unpack_popgen_records(rec: np.ndarray, P: int) -> dict:
-    npairs = P * (P - 1) // 2
-    return dict(sites=rec[:, 0].astype(np.int64), pos_sum=rec[:, 1].astype(np.int64), path=rec[:, 2].astype(np.int32),
-                pi=rec[:, 3:3 + P], dxy=rec[:, 3 + P:3 + P + npairs], fst=rec[:, 3 + P + npairs:3 + P + 2 * npairs])
-
-
-class DeviceGather:
-    """Preallocated buffers for the per-step all-gather of device-resident popgen records (NCCL):
-    each rank's engine writes its records straight into `local` (pg_popgen_device), one
-    all_gather_into_tensor moves them, one D2H brings the table to the host."""
-
-    def __init__(self, counts, width, device):
-        import torch
-        self.counts = [int(c) for c in counts]
-        self.width = int(width)
-        self.wmax = max(max(self.counts), 1)
-        self.world = len(self.counts)
-        self.local = torch.zeros((self.wmax, self.width), dtype=torch.float64, device=device)
-        self.all = torch.zeros((self.world * self.wmax, self.width), dtype=torch.float64, device=device)
-        self.host = torch.zeros((self.world * self.wmax, self.width), dtype=torch.float64).pin_memory()
-
-    def gather(self) -> np.ndarray:
-        import torch
-        import torch.distributed as dist
-        dist.all_gather_into_tensor(self.all, self.local)
-        self.host.copy_(self.all, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        h = self.host.numpy()
-        return np.concatenate([h[r * self.wmax: r * self.wmax + self.counts[r]] for r in range(self.world)], axis=0)
 
 
 def unpack_device_records(rec: np.ndarray, P: int) -> dict:
