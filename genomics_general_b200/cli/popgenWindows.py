@@ -18,7 +18,7 @@ import sys
 
 import numpy as np
 
-from .. import genomics, mgpu, multigpu
+from .. import genomics, geno_io, mgpu, multigpu
 from ..engine import Engine
 from . import _common as C
 
@@ -167,7 +167,32 @@ def main(argv=None):
                                or "popPairDist" in args.analysis or "indPairDist" in args.analysis)
         tm.mark("statistics", eng)
         iu = np.triu_indices(len(ind_sorted)) if dmat is not None else None
-        for k in range(len(ws)):
+        simple = fq is None and dmat is None and het is None and hst is None
+        if simple and len(ws):
+            # popDist / popPairDist only: the statistics of ALL windows are rounded and printed at once by the native row
+            # printer (numpy's float -> str, i.e. what str(round(np.float64(v), n)) gives; popgenWindows.py:66-74); only the
+            # five prefix fields are assembled per window.  20 000 windows: 0.3 s instead of 3 s of Python.
+            sites_all = np.asarray(r["sites"])
+            goodv = sites_all >= minSites
+            cols = []
+            if "popDist" in args.analysis:
+                cols.append(r["pi"])
+            if "popPairDist" in args.analysis:
+                cols += [r["dxy"], r["fst"]]
+            M = np.concatenate(cols, axis=1) if cols else np.zeros((len(ws), 0))
+            M = np.where(goodv[:, None], np.round(M.astype(np.float64), args.roundTo), np.nan)
+            keep = np.flatnonzero(goodv | bool(args.writeFailedWindows))
+            prefixes = []
+            for k in keep:
+                pre = C.window_prefix(args, ws, int(k), gd, r["sites"][k], r["pos_sum"][k])
+                prefixes.append(",".join(str(x) for x in (([ws.ID[k]] if args.addWindowID else []) + pre))
+                                + ("," if M.shape[1] else ""))
+            if M.shape[1]:
+                out.write(geno_io.format_matrix_rows(M[keep], sep=",", prefixes=prefixes))
+            else:
+                out.write("".join(p + "\n" for p in prefixes))
+            written = len(keep)
+        for k in (range(len(ws)) if not simple else ()):
             pre = C.window_prefix(args, ws, k, gd, r["sites"][k], r["pos_sum"][k])
             good = pre[4] >= minSites
             vals = []
