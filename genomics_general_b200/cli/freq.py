@@ -7,6 +7,8 @@ from __future__ import annotations
 import argparse
 import os
 import sys
+import time
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
@@ -66,12 +68,15 @@ def main(argv=None):
         out.write("scaffold\tposition\t" + "\t".join(popNames) + "\n")
     else:
         out = open(os.path.join(rdv.dir, "rows.r%d.part" % rdv.rank), "wb")
+    tm = C.Timing(args.timing if (rdv is None or rdv.rank == 0) else None)
     eng = Engine(args.device if rdv is None else mgpu.device_for(rdv, args.device))
     if rdv is None:
         gd = C.load_geno(args, sampleData.indNames, ploidyDict, engine=eng)
     else:
         gd = mgpu.local_ingest(eng, rdv, args.genoFile, args.genoFormat, sampleData.indNames, ploidyDict)
     P = len(popNames)
+    tm.mark("ingest", eng)
+    busy = dict(fetch=0.0, format=0.0, write=0.0)
     with eng:
         C.ensure_resident(eng, gd)
         eng.set_pops(C.hap_pop_vector(gd, popNames, popInds), P)
@@ -80,32 +85,57 @@ def main(argv=None):
         if raw is not None:
             out.flush()
 
+        def fetch(s, n):
+            """one slab of per-site values off the device: (formatter mode, values, keep mask)"""
+            t0 = time.perf_counter()
+            try:
+                if not args.target:
+                    return 0, eng.site_counts(s, n), None
+                # freq.py:302-304: with a target the user's --asCounts / --keepNanLines / --minData apply
+                v, _ = eng.site_target_freqs(args.target, s, n, min_data=args.minData, as_counts=args.asCounts)
+                if args.asCounts:
+                    return 2, v, (None if args.keepNanLines else ~np.all(v == 0, axis=1))
+                v = np.around(v, 4)                                       # freq.py:91
+                if args.threshold:                                        # freq.py:96-98
+                    hi, lo = v >= args.threshold, v < args.threshold
+                    v[hi] = 1
+                    v[lo] = 0
+                return 1, v, (None if args.keepNanLines else ~np.all(np.isnan(v), axis=1))
+            finally:
+                busy["fetch"] += time.perf_counter() - t0
+
         def emit(segments):
+            t0 = time.perf_counter()
             for seg in segments:
                 if raw is not None:
                     raw.write(seg)
                 else:
                     out.write(bytes(seg).decode())
-        slab = 1 << 21
-        for s in range(0, gd.n_sites, slab):
-            n = min(slab, gd.n_sites - s)
-            ids, pos = gd.scaf_ids[s:s + n], gd.pos[s:s + n]
-            if args.target:
-                # freq.py:302-304: with a target the user's --asCounts / --keepNanLines / --minData apply
-                v, _ = eng.site_target_freqs(args.target, s, n, min_data=args.minData, as_counts=args.asCounts)
-                if args.asCounts:
-                    keep = None if args.keepNanLines else ~np.all(v == 0, axis=1)
-                    emit(geno_io.format_freq_rows(2, v, pos, ids, gd.scaf_names, keep))
-                else:
-                    v = np.around(v, 4)                                       # freq.py:91
-                    if args.threshold:                                        # freq.py:96-98
-                        hi, lo = v >= args.threshold, v < args.threshold
-                        v[hi] = 1
-                        v[lo] = 0
-                    keep = None if args.keepNanLines else ~np.all(np.isnan(v), axis=1)
-                    emit(geno_io.format_freq_rows(1, v, pos, ids, gd.scaf_names, keep))
-                continue
-            emit(geno_io.format_freq_rows(0, eng.site_counts(s, n), pos, ids, gd.scaf_names))
+            busy["write"] += time.perf_counter() - t0
+
+        # three stages in flight: the device pass + D2H of slab k+1 and the write of slab k-1 run on two helper threads
+        # under the formatting of slab k (every stage leaves the interpreter lock: ctypes calls and file writes)
+        slab = 1 << 18
+        starts = list(range(0, gd.n_sites, slab))
+        with ThreadPoolExecutor(1) as fetcher, ThreadPoolExecutor(1) as writer:
+            nxt = fetcher.submit(fetch, starts[0], min(slab, gd.n_sites - starts[0])) if starts else None
+            wrote = None
+            for k, s in enumerate(starts):
+                n = min(slab, gd.n_sites - s)
+                mode, v, keep = nxt.result()
+                if k + 1 < len(starts):
+                    nxt = fetcher.submit(fetch, starts[k + 1], min(slab, gd.n_sites - starts[k + 1]))
+                t0 = time.perf_counter()
+                segs = geno_io.format_freq_rows(mode, v, gd.pos[s:s + n], gd.scaf_ids[s:s + n], gd.scaf_names, keep)
+                busy["format"] += time.perf_counter() - t0
+                if wrote is not None:
+                    wrote.result()
+                wrote = writer.submit(emit, segs)
+            if wrote is not None:
+                wrote.result()
+    tm.mark("rows")
+    tm.write(sites=int(gd.n_sites), haplotypes=int(gd.n_haps), populations=P, stage_busy_s=busy,
+             devices=(1 if rdv is None else rdv.world))
     if rdv is not None:
         if rdv.rank != 0:
             out.close()

@@ -422,17 +422,33 @@ __global__ void __launch_bounds__(256) k2_popgen_epi_blocks(const __grid_constan
     const int nr = r1 - r0, nc = c1 - c0;
     double s = 0.0;
     long long c = 0;
-    // a warp walks one matrix row at a time, lanes along the columns (coalesced, no integer division per element)
+    // a warp walks one matrix row at a time, lanes along the columns (coalesced, no integer division per element); two
+    // columns per lane and step keep two independent fp64 divisions in flight
+    double s1 = 0.0;
+    long long cnt1 = 0;
     for (int i = r0 + (threadIdx.x >> 5); i < r1; i += 8) {
         const int mi = ep.mid[i];
         const int32_t* Drow = D + (size_t)i * ep.Hk;
-        for (int j = ((X == Y) ? i + 1 : c0) + (threadIdx.x & 31); j < c1; j += 32) {
+        for (int j = ((X == Y) ? i + 1 : c0) + (threadIdx.x & 31); j < c1; j += 64) {
+            const int j2 = j + 32;
             const int nij = N[upper_idx(mi, ep.mid[j], ep.Hm)];
-            if (nij == 0 || (ep.min_sites > 0 && nij < ep.min_sites)) continue;   // nan entries
-            s += (double)Drow[j] / (double)nij;
-            c += 1;
+            const int nij2 = (j2 < c1) ? N[upper_idx(mi, ep.mid[j2], ep.Hm)] : 0;
+            const bool ok = !(nij == 0 || (ep.min_sites > 0 && nij < ep.min_sites));          // else: a nan entry
+            const bool ok2 = !(nij2 == 0 || (ep.min_sites > 0 && nij2 < ep.min_sites));
+            const double d0 = ok ? (double)Drow[j] / (double)nij : 0.0;
+            const double d1 = ok2 ? (double)Drow[j2] / (double)nij2 : 0.0;
+            if (ok) {
+                s += d0;
+                c += 1;
+            }
+            if (ok2) {
+                s1 += d1;
+                cnt1 += 1;
+            }
         }
     }
+    s += s1;
+    c += cnt1;
     (void)nr;
     (void)nc;
     block_sum(s, c, sh_s, sh_c);
@@ -805,7 +821,10 @@ struct PlaneSet {
 int build_planes(pg_ctx* ctx, const std::vector<int32_t>& order, int64_t lo, int64_t hi, PlaneSet& ps) {
     const int Hk = (int)order.size();
     PG_CHECK(Hk >= 1, "pairwise path: no haplotypes selected");
-    if (pg_k2_use_tensor()) {
+    // the plane builders of the tensor path stage 16 bytes per column in shared memory: beyond ~4000 haplotype columns the
+    // bit-plane POPC kernels (any width) take over
+    const bool fits = (size_t)16 * ctx->pitch + (size_t)((Hk + 15) / 16 * 16) * 8 <= 96 * 1024;
+    if (pg_k2_use_tensor() && fits) {
         PG_TRY(pg_k2t_build(ctx, order, lo, hi, ps.t));
         ps.tensor = true;
         ps.Hk = Hk;

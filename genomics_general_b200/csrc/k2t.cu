@@ -84,6 +84,8 @@ __device__ __forceinline__ uint32_t valid2(uint32_t w0, uint32_t w1) {
     return (t | (t >> 2)) & 0x03030303u;
 }
 
+// ALL: every column of the row is a selected haplotype or padding (padding bytes are 0 = missing): no column mask needed
+template <bool ALL>
 __global__ void __launch_bounds__(256, 4) k2t_valid_class(const __grid_constant__ VcParams p) {
     extern __shared__ __align__(16) uint32_t vc_st[];      // [8 octets][pw]: byte (o, c) = valid bits of 8 sites of column c
     __shared__ int s_wtot[8];
@@ -97,7 +99,8 @@ __global__ void __launch_bounds__(256, 4) k2t_valid_class(const __grid_constant_
         const uint4* g4 = reinterpret_cast<const uint4*>(p.geno32);
         const int pw4 = p.pw >> 2;
         for (int q = lane; q < pw4; q += 32) {
-            const uint4 cm = reinterpret_cast<const uint4*>(p.cmask)[q];
+            uint4 cm = make_uint4(~0u, ~0u, ~0u, ~0u);
+            if (!ALL) cm = reinterpret_cast<const uint4*>(p.cmask)[q];
             uint4 w[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
@@ -105,7 +108,9 @@ __global__ void __launch_bounds__(256, 4) k2t_valid_class(const __grid_constant_
                 w[k] = (s < p.S) ? __ldg(g4 + s * pw4 + q) : make_uint4(0u, 0u, 0u, 0u);
             }
 #pragma unroll
-            for (int k = 0; k < 8; ++k) pres[k] |= (w[k].x & cm.x) | (w[k].y & cm.y) | (w[k].z & cm.z) | (w[k].w & cm.w);
+            for (int k = 0; k < 8; ++k)
+                pres[k] |= ALL ? (w[k].x | w[k].y | w[k].z | w[k].w)
+                               : ((w[k].x & cm.x) | (w[k].y & cm.y) | (w[k].z & cm.z) | (w[k].w & cm.w));
             uint4 o4;
 #define VC_WORD(C) (valid2(w[0].C, w[1].C) | (valid2(w[2].C, w[3].C) << 2) | (valid2(w[4].C, w[5].C) << 4) | (valid2(w[6].C, w[7].C) << 6))
             o4.x = VC_WORD(x);
@@ -827,7 +832,8 @@ int pg_k2t_build(pg_ctx* ctx, const std::vector<int32_t>& order, int64_t lo, int
         static bool attr_dev[64] = {};
         if (!attr_dev[ctx->device & 63]) {
             PG_CUDA(cudaFuncSetAttribute(k2t_build_pq, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-            PG_CUDA(cudaFuncSetAttribute(k2t_valid_class, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            PG_CUDA(cudaFuncSetAttribute(k2t_valid_class<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            PG_CUDA(cudaFuncSetAttribute(k2t_valid_class<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
             attr_dev[ctx->device & 63] = true;
         }
     }
@@ -882,7 +888,10 @@ int pg_k2t_build(pg_ctx* ctx, const std::vector<int32_t>& order, int64_t lo, int
     const int grid1 = (int)std::min<int64_t>(nchunk, (int64_t)ctx->sm_count * 8);
     {
         const int ti = pg_time_begin(ctx, "k2t_valid_class");
-        k2t_valid_class<<<grid1, 256, (size_t)8 * pw * 4 + (size_t)R * 8, ctx->stream>>>(vp);
+        bool all_used = true;                    // unselected real columns? (padding columns hold 0 = missing and never count)
+        for (int c = 0; c < ctx->H; ++c) all_used = all_used && c2r[c] >= 0;
+        if (all_used) k2t_valid_class<true><<<grid1, 256, (size_t)8 * pw * 4 + (size_t)R * 8, ctx->stream>>>(vp);
+        else k2t_valid_class<false><<<grid1, 256, (size_t)8 * pw * 4 + (size_t)R * 8, ctx->stream>>>(vp);
         pg_time_end(ctx, ti);
         PG_CUDA(cudaGetLastError());
     }

@@ -1,0 +1,98 @@
+"""The tensor-core pairwise path (csrc/k2t.cu: tcgen05.mma kind::i8 Gram kernels over bit-packed planes) against plain numpy
+and against the round-1 POPC kernels, through the C-ABI: integer pair matrices bit-exact on every tile geometry (one group,
+several 128-row tiles, a separate A region beyond 512 haplotypes, 1600 haplotypes), multi-allelic sites, window edges inside a
+64-site chunk, per-sample and per-haplotype missingness, many windows per persistent CTA, and the smallest ring configurations
+(PG_K2T_NRAW / PG_K2T_NSTAGES) that stress the mbarrier hand-overs."""
+import os
+
+import numpy as np
+import pytest
+
+from genomics_general_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from genomics_general_b200.engine import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def ref_counts(g):
+    """g int8 [L, H] -> diff, n int64 [H, H]  (genomics.py:903-916, 1042-1047)"""
+    v = (g >= 0).astype(np.float32)
+    n = (v.T @ v).astype(np.int64)
+    same = np.zeros_like(n)
+    for a in range(4):
+        x = (g == a).astype(np.float32)
+        same += (x.T @ x).astype(np.int64)
+    return n - same, n
+
+
+SHAPES = [  # (pops, samples per pop, sites, missing, p_third, windows)
+    (2, 10, 3000, 0.05, 0.01, [(0, 3000), (100, 164), (5, 70), (64, 128), (1000, 1001)]),
+    (2, 10, 3000, 0.0, 0.01, [(0, 3000), (17, 2100)]),
+    (3, 22, 2500, 0.10, 0.20, [(0, 2500), (63, 1999)]),
+    (4, 50, 6000, 0.02, 0.01, [(0, 5000), (5000, 6000), (123, 4567)]),
+    (1, 300, 1500, 0.03, 0.01, [(0, 1500), (200, 900)]),
+    (1, 500, 1200, 0.02, 0.05, [(0, 1200)]),
+    (8, 100, 700, 0.02, 0.01, [(0, 700), (65, 640)]),
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "H%d_miss%g" % (s[0] * s[1] * 2, s[3]))
+def test_pair_counts_bit_exact_vs_numpy_and_popc(eng, shape, monkeypatch):
+    P, spp, S, miss, p3, wins = shape
+    spec = synth.SynthSpec(P, spp, miss=miss, seed=1234 + P * 7 + spp, p_third=p3)
+    eng.synth_fill(spec, S)
+    g, _ = eng.download(0, S)
+    eng.set_windows(np.array([w[0] for w in wins], dtype=np.int64), np.array([w[1] for w in wins], dtype=np.int64))
+    for w, (lo, hi) in enumerate(wins):
+        rd, rn = ref_counts(g[lo:hi])
+        monkeypatch.delenv("PG_K2_POPC", raising=False)
+        d, n = eng.pair_counts(w)
+        assert np.array_equal(n, rn) and np.array_equal(d, rd), (w, lo, hi)
+        if P * spp * 2 <= 600:
+            monkeypatch.setenv("PG_K2_POPC", "1")
+            d2, n2 = eng.pair_counts(w)
+            assert np.array_equal(d2, d) and np.array_equal(n2, n)
+    monkeypatch.delenv("PG_K2_POPC", raising=False)
+
+
+def test_allele_level_missingness_uses_one_mask_row_per_haplotype(eng):
+    """haplotypes of a sample with different missingness: the per-sample compaction of the valid plane must be refused"""
+    rng = np.random.default_rng(3)
+    S, H = 900, 24
+    g = rng.integers(0, 4, (S, H)).astype(np.int8)
+    g[rng.random((S, H)) < 0.1] = -1                      # per allele, not per genotype
+    eng.upload(g, np.arange(1, S + 1, dtype=np.int32))
+    eng.set_windows([0, 100], [S, 777])
+    for w, (lo, hi) in enumerate(((0, S), (100, 777))):
+        rd, rn = ref_counts(g[lo:hi])
+        d, n = eng.pair_counts(w)
+        assert np.array_equal(n, rn) and np.array_equal(d, rd)
+
+
+@pytest.mark.parametrize("env", [{}, {"PG_K2T_NRAW": "1"}, {"PG_K2T_NRAW": "1", "PG_K2T_NSTAGES": "1"}, {"PG_K2T_NSTAGES": "2"},
+                                 {"PG_K2T_NO_PAIRS": "1"}], ids=lambda e: "_".join("%s%s" % (k[7:], v) for k, v in e.items()) or "default")
+def test_many_windows_per_cta_equal_the_popc_kernels(eng, env, monkeypatch):
+    """600 windows over 148 persistent CTAs, every ring geometry: statistics identical to the POPC path, run after run"""
+    S = 3_000_000
+    spec = synth.SynthSpec(4, 50, miss=0.02, seed=20260925)
+    eng.synth_fill(spec, S)
+    eng.set_pops(spec.hap_pop(), 4)
+    lo = np.arange(0, S, 5000, dtype=np.int64)
+    eng.set_windows(lo, np.minimum(lo + 5000, S))
+    monkeypatch.setenv("PG_K2_POPC", "1")
+    ref = eng.popgen(100, 0.01)
+    monkeypatch.delenv("PG_K2_POPC")
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    for rep in range(2):
+        r = eng.popgen(100, 0.01)
+        assert np.all(r["path"] == 2)
+        for key in ("pi", "dxy", "fst", "sites", "pos_sum"):
+            assert np.array_equal(r[key], ref[key], equal_nan=True), (key, rep, env)
