@@ -459,6 +459,66 @@ __global__ void __launch_bounds__(256) k2_popgen_epi_blocks(const __grid_constan
     }
 }
 
+// Stage 1 when the haplotypes of a sample share their missingness (mask id of plane row r = r >> 1) and every population
+// starts on an even row: ONE CTA per window walks all population blocks by SAMPLE pairs (a, b).  The four haplotype
+// pairs of a sample pair share n_ab, so their distances add up as (d00 + d01 + d10 + d11) / n_ab — one fp64 division per
+// four pairs, exact integer numerator (the reference's four separate quotients summed differ from this by rounding only,
+// ~1e-16 relative).  Fixed summation order: lane sums -> butterfly -> warps in order.
+__global__ void __launch_bounds__(128) k2_popgen_epi_pairs(const __grid_constant__ PopEpiParams ep) {
+    extern __shared__ __align__(16) double epi_sh[];     // [nblk][4 warps] sums, then counts
+    const int P = ep.P, nblk = P * (P + 1) / 2;
+    double* sh_s = epi_sh;
+    long long* sh_c = reinterpret_cast<long long*>(epi_sh + (size_t)nblk * 4);
+    const int wb = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int32_t* D = ep.diff + (size_t)wb * ep.Hk * ep.Hk;
+    const int32_t* N = ep.n + (size_t)wb * ep.Hm * ep.Hm;
+    int blk = 0;
+    for (int X = 0; X < P; ++X) {
+        const int a0 = ep.pop_start[X] >> 1, a1 = ep.pop_start[X + 1] >> 1;
+        for (int Y = X; Y < P; ++Y, ++blk) {
+            const int b0 = ep.pop_start[Y] >> 1, b1 = ep.pop_start[Y + 1] >> 1;
+            double s = 0.0;
+            int c = 0;
+            for (int a = a0 + warp; a < a1; a += 4) {
+                const int32_t* D0 = D + (size_t)(2 * a) * ep.Hk;
+                const int32_t* D1 = D0 + ep.Hk;
+                const int32_t* Na = N + (size_t)a * ep.Hm;      // upper_idx(a, b), a <= b
+                for (int b = ((X == Y) ? a : b0) + lane; b < b1; b += 32) {
+                    const int nab = Na[b];
+                    if (nab == 0 || (ep.min_sites > 0 && nab < ep.min_sites)) continue;       // nan entries
+                    int num, cnt;
+                    if (b == a) {          // the sample's own two haplotypes
+                        num = D0[2 * a + 1];
+                        cnt = 1;
+                    } else {
+                        const int2 u = *reinterpret_cast<const int2*>(D0 + 2 * b);
+                        const int2 v = *reinterpret_cast<const int2*>(D1 + 2 * b);
+                        num = u.x + u.y + v.x + v.y;
+                        cnt = 4;
+                    }
+                    s += (double)num / (double)nab;
+                    c += cnt;
+                }
+            }
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) {
+                s += __shfl_xor_sync(0xffffffffu, s, d);
+                c += __shfl_xor_sync(0xffffffffu, c, d);
+            }
+            if (lane == 0) {
+                sh_s[blk * 4 + warp] = s;
+                sh_c[blk * 4 + warp] = c;
+            }
+        }
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < nblk; b += 128) {
+        ep.blk_s[(size_t)wb * nblk + b] = ((sh_s[b * 4] + sh_s[b * 4 + 1]) + sh_s[b * 4 + 2]) + sh_s[b * 4 + 3];
+        ep.blk_c[(size_t)wb * nblk + b] = sh_c[b * 4] + sh_c[b * 4 + 1] + sh_c[b * 4 + 2] + sh_c[b * 4 + 3];
+    }
+}
+
 // Stage 2: block sums -> pi / dxy / Fst of one window per thread (nanmean_min fractions, genomics.py:976-993).
 __global__ void __launch_bounds__(128) k2_popgen_epi_final(const __grid_constant__ PopEpiParams ep, int nb) {
     const int wb = blockIdx.x * 128 + threadIdx.x;
@@ -1044,7 +1104,11 @@ int pg_k2_popgen_windows(pg_ctx* ctx, const std::vector<int64_t>& wins, int32_t 
         ep.blk_s = (double*)ctx->misc5.p;
         ep.blk_c = (long long*)(ep.blk_s + nb * (size_t)nblk);
         const int ti = pg_time_begin(ctx, "k2_popgen_epi");
-        k2_popgen_epi_blocks<<<dim3((unsigned)nblk, (unsigned)nb), 256, 0, ctx->stream>>>(ep);
+        // sample-pair walk: mask ids are r >> 1 (the tensor path's per-sample n rows) and populations start on even rows
+        bool by_pairs = ps.tensor && ps.Hm * 2 == ps.Hk && (size_t)nblk * 64 <= 48 * 1024;
+        for (int X = 0; X <= P; ++X) by_pairs = by_pairs && (pop_start[X] % 2 == 0);
+        if (by_pairs) k2_popgen_epi_pairs<<<(unsigned)nb, 128, (size_t)nblk * 64, ctx->stream>>>(ep);
+        else k2_popgen_epi_blocks<<<dim3((unsigned)nblk, (unsigned)nb), 256, 0, ctx->stream>>>(ep);
         k2_popgen_epi_final<<<(unsigned)((nb + 127) / 128), 128, 0, ctx->stream>>>(ep, (int)nb);
         pg_time_end(ctx, ti);
         PG_CUDA(cudaGetLastError());

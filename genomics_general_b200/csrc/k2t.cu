@@ -102,10 +102,13 @@ __global__ void __launch_bounds__(256, 4) k2t_valid_class(const __grid_constant_
             uint4 cm = make_uint4(~0u, ~0u, ~0u, ~0u);
             if (!ALL) cm = reinterpret_cast<const uint4*>(p.cmask)[q];
             uint4 w[8];
+            const uint4* rp = g4 + site0 * pw4 + q;
+            if (site0 + 8 <= p.S) {      // (warp-uniform) every chunk but the last: no per-row guards
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int64_t s = site0 + k;
-                w[k] = (s < p.S) ? __ldg(g4 + s * pw4 + q) : make_uint4(0u, 0u, 0u, 0u);
+                for (int k = 0; k < 8; ++k) w[k] = __ldg(rp + (int64_t)k * pw4);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) w[k] = (site0 + k < p.S) ? __ldg(rp + (int64_t)k * pw4) : make_uint4(0u, 0u, 0u, 0u);
             }
 #pragma unroll
             for (int k = 0; k < 8; ++k)
@@ -123,9 +126,7 @@ __global__ void __launch_bounds__(256, 4) k2t_valid_class(const __grid_constant_
         uint32_t mine = 0u;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            uint32_t v = pres[k];
-#pragma unroll
-            for (int d = 16; d >= 1; d >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, d);
+            const uint32_t v = __reduce_or_sync(0xffffffffu, pres[k]);      // REDUX.OR: one instruction per site
             if (lane == k) mine = v;
         }
         int ps = 0;
@@ -142,16 +143,38 @@ __global__ void __launch_bounds__(256, 4) k2t_valid_class(const __grid_constant_
         for (int d = 4; d >= 1; d >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, d);
         if (lane == 0) s_wtot[o] = ps;
         __syncthreads();
-        const uint8_t* st8 = reinterpret_cast<const uint8_t*>(vc_st);
         uint64_t* s_v = reinterpret_cast<uint64_t*>(vc_st + 8 * p.pw);      // [R] this chunk's words by plane row
-        for (int c = tid; c < p.pitch; c += 256) {
-            const int r = p.c2r[c];
-            if (r < 0) continue;
-            uint64_t v = 0;
+        // a thread turns four columns: 8 octet words [4 columns x 1 byte] -> 4 words of 64 sites (two 4x4 byte transposes)
+        for (int cw = tid; cw < p.pw; cw += 256) {
+            uint32_t a[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) v |= (uint64_t)st8[(size_t)q * p.pitch + c] << (8 * q);
-            p.vplane[chunk * p.R + r] = v;
-            s_v[r] = v;
+            for (int q = 0; q < 8; ++q) a[q] = vc_st[q * p.pw + cw];
+            uint32_t lo[4], hi[4];
+            {
+                const uint32_t t0 = __byte_perm(a[0], a[1], 0x5140), t1 = __byte_perm(a[2], a[3], 0x5140);
+                const uint32_t t2 = __byte_perm(a[0], a[1], 0x7362), t3 = __byte_perm(a[2], a[3], 0x7362);
+                lo[0] = __byte_perm(t0, t1, 0x5410);
+                lo[1] = __byte_perm(t0, t1, 0x7632);
+                lo[2] = __byte_perm(t2, t3, 0x5410);
+                lo[3] = __byte_perm(t2, t3, 0x7632);
+            }
+            {
+                const uint32_t t0 = __byte_perm(a[4], a[5], 0x5140), t1 = __byte_perm(a[6], a[7], 0x5140);
+                const uint32_t t2 = __byte_perm(a[4], a[5], 0x7362), t3 = __byte_perm(a[6], a[7], 0x7362);
+                hi[0] = __byte_perm(t0, t1, 0x5410);
+                hi[1] = __byte_perm(t0, t1, 0x7632);
+                hi[2] = __byte_perm(t2, t3, 0x5410);
+                hi[3] = __byte_perm(t2, t3, 0x7632);
+            }
+            const int4 r4 = *reinterpret_cast<const int4*>(p.c2r + 4 * cw);
+            const int rr[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (rr[j] < 0) continue;
+                const uint64_t v = (uint64_t)lo[j] | ((uint64_t)hi[j] << 32);
+                p.vplane[chunk * p.R + rr[j]] = v;
+                s_v[rr[j]] = v;
+            }
         }
         for (int r = p.Hk + tid; r < p.R; r += 256) p.vplane[chunk * p.R + r] = 0ull;
         if (p.vpair) {

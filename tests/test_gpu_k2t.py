@@ -94,5 +94,15 @@ def test_many_windows_per_cta_equal_the_popc_kernels(eng, env, monkeypatch):
     for rep in range(2):
         r = eng.popgen(100, 0.01)
         assert np.all(r["path"] == 2)
-        for key in ("pi", "dxy", "fst", "sites", "pos_sum"):
-            assert np.array_equal(r[key], ref[key], equal_nan=True), (key, rep, env)
+        for key in ("sites", "pos_sum"):
+            assert np.array_equal(r[key], ref[key]), (key, rep, env)
+        for key in ("pi", "dxy", "fst"):
+            # integer matrices are identical; the sample-pair epilogue divides once per four haplotype pairs, the
+            # POPC path's epilogue once per pair: the block sums differ by rounding only
+            assert np.array_equal(np.isnan(r[key]), np.isnan(ref[key])), (key, rep, env)
+            assert np.allclose(r[key], ref[key], rtol=1e-12, atol=1e-12, equal_nan=True), (key, rep, env)
+        if rep == 0:
+            first = r
+        else:
+            for key in ("pi", "dxy", "fst"):
+                assert np.array_equal(r[key], first[key], equal_nan=True), (key, env)      # run after run: bit-identical

@@ -93,7 +93,7 @@ def main():
         os.environ.pop("PG_K2_POPC", None)
         for key in ("pi", "dxy", "fst"):
             a, b = res["tensor"][key], res["popc"][key]
-            print("tensor vs popc %s: identical=%s maxabs=%g" % (key, np.array_equal(a, b, equal_nan=True), np.nanmax(np.abs(a - b))))
+            print("tensor vs popc %s: identical=%s maxabs=%g maxrel=%g" % (key, np.array_equal(a, b, equal_nan=True), np.nanmax(np.abs(a - b)), np.nanmax(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))))
     return 0 if allok else 1
 
 
