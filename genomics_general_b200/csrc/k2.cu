@@ -480,25 +480,43 @@ __global__ void __launch_bounds__(128) k2_popgen_epi_pairs(const __grid_constant
             const int b0 = ep.pop_start[Y] >> 1, b1 = ep.pop_start[Y + 1] >> 1;
             double s = 0.0;
             int c = 0;
-            for (int a = a0 + warp; a < a1; a += 4) {
-                const int32_t* D0 = D + (size_t)(2 * a) * ep.Hk;
-                const int32_t* D1 = D0 + ep.Hk;
-                const int32_t* Na = N + (size_t)a * ep.Hm;      // upper_idx(a, b), a <= b
-                for (int b = ((X == Y) ? a : b0) + lane; b < b1; b += 32) {
-                    const int nab = Na[b];
-                    if (nab == 0 || (ep.min_sites > 0 && nab < ep.min_sites)) continue;       // nan entries
-                    int num, cnt;
-                    if (b == a) {          // the sample's own two haplotypes
-                        num = D0[2 * a + 1];
-                        cnt = 1;
-                    } else {
-                        const int2 u = *reinterpret_cast<const int2*>(D0 + 2 * b);
-                        const int2 v = *reinterpret_cast<const int2*>(D1 + 2 * b);
-                        num = u.x + u.y + v.x + v.y;
-                        cnt = 4;
+            // the block's sample pairs as ONE index range over the 128 threads (full lanes, consecutive lanes on consecutive
+            // b): an off-diagonal block is the na x nb rectangle; a diagonal block of n samples folds its triangle (b >= a)
+            // into ceil(n / 2) rows of n + 1: row r = [row r of the triangle | row n - 1 - r]
+            const int n = a1 - a0;
+            const bool diag = (X == Y);
+            const uint32_t width = diag ? (uint32_t)(n + 1) : (uint32_t)(b1 - b0);
+            const uint32_t units = diag ? (uint32_t)((n + 1) / 2) * width : (uint32_t)n * width;
+            const uint32_t magic = width > 1 ? (uint32_t)(((1ull << 32) + width - 1) / width) : 0u;
+#pragma unroll 2
+            for (uint32_t idx = threadIdx.x; idx < units; idx += 128) {
+                uint32_t r = width > 1 ? __umulhi(idx, magic) : idx;
+                int k = (int)(idx - r * width);
+                if (k < 0) {                   // the rounded-up reciprocal overshoots only beyond idx * width >= 2^32
+                    r -= 1;
+                    k += (int)width;
+                }
+                int a = a0 + (int)r, b = b0 + k;
+                bool use = true;
+                if (diag) {
+                    if (k < n - (int)r) b = a + k;
+                    else {
+                        const int a2 = n - 1 - (int)r;
+                        use = (a2 != (int)r);          // odd n: the middle row is its own partner
+                        a = a0 + a2;
+                        b = a + (k - (n - (int)r));
                     }
-                    s += (double)num / (double)nab;
-                    c += cnt;
+                }
+                const int nab = N[(size_t)a * ep.Hm + b];
+                const int2 u = *reinterpret_cast<const int2*>(D + (size_t)(2 * a) * ep.Hk + 2 * b);
+                const int2 v = *reinterpret_cast<const int2*>(D + (size_t)(2 * a + 1) * ep.Hk + 2 * b);
+                const bool ok = use && nab != 0 && !(ep.min_sites > 0 && nab < ep.min_sites);      // else: nan entries
+                // a == b: only the sample's own two haplotypes (2a, 2a + 1); the other three words are not pair entries
+                const int num = (a == b) ? u.y : (u.x + u.y + v.x + v.y);
+                const double q = (double)num / (double)(ok ? nab : 1);
+                if (ok) {
+                    s += q;
+                    c += (a == b) ? 1 : 4;
                 }
             }
 #pragma unroll

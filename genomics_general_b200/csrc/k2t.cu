@@ -84,6 +84,26 @@ __device__ __forceinline__ uint32_t valid2(uint32_t w0, uint32_t w1) {
     return (t | (t >> 2)) & 0x03030303u;
 }
 
+// eight words [4 columns x 1 byte] (one per site octet) -> per column the 64-site word (lo, hi): two 4x4 byte transposes
+__device__ __forceinline__ void octets_to_words(const uint32_t (&a)[8], uint32_t (&lo)[4], uint32_t (&hi)[4]) {
+    {
+        const uint32_t t0 = __byte_perm(a[0], a[1], 0x5140), t1 = __byte_perm(a[2], a[3], 0x5140);
+        const uint32_t t2 = __byte_perm(a[0], a[1], 0x7362), t3 = __byte_perm(a[2], a[3], 0x7362);
+        lo[0] = __byte_perm(t0, t1, 0x5410);
+        lo[1] = __byte_perm(t0, t1, 0x7632);
+        lo[2] = __byte_perm(t2, t3, 0x5410);
+        lo[3] = __byte_perm(t2, t3, 0x7632);
+    }
+    {
+        const uint32_t t0 = __byte_perm(a[4], a[5], 0x5140), t1 = __byte_perm(a[6], a[7], 0x5140);
+        const uint32_t t2 = __byte_perm(a[4], a[5], 0x7362), t3 = __byte_perm(a[6], a[7], 0x7362);
+        hi[0] = __byte_perm(t0, t1, 0x5410);
+        hi[1] = __byte_perm(t0, t1, 0x7632);
+        hi[2] = __byte_perm(t2, t3, 0x5410);
+        hi[3] = __byte_perm(t2, t3, 0x7632);
+    }
+}
+
 // ALL: every column of the row is a selected haplotype or padding (padding bytes are 0 = missing): no column mask needed
 template <bool ALL>
 __global__ void __launch_bounds__(256, 4) k2t_valid_class(const __grid_constant__ VcParams p) {
@@ -150,22 +170,7 @@ __global__ void __launch_bounds__(256, 4) k2t_valid_class(const __grid_constant_
 #pragma unroll
             for (int q = 0; q < 8; ++q) a[q] = vc_st[q * p.pw + cw];
             uint32_t lo[4], hi[4];
-            {
-                const uint32_t t0 = __byte_perm(a[0], a[1], 0x5140), t1 = __byte_perm(a[2], a[3], 0x5140);
-                const uint32_t t2 = __byte_perm(a[0], a[1], 0x7362), t3 = __byte_perm(a[2], a[3], 0x7362);
-                lo[0] = __byte_perm(t0, t1, 0x5410);
-                lo[1] = __byte_perm(t0, t1, 0x7632);
-                lo[2] = __byte_perm(t2, t3, 0x5410);
-                lo[3] = __byte_perm(t2, t3, 0x7632);
-            }
-            {
-                const uint32_t t0 = __byte_perm(a[4], a[5], 0x5140), t1 = __byte_perm(a[6], a[7], 0x5140);
-                const uint32_t t2 = __byte_perm(a[4], a[5], 0x7362), t3 = __byte_perm(a[6], a[7], 0x7362);
-                hi[0] = __byte_perm(t0, t1, 0x5410);
-                hi[1] = __byte_perm(t0, t1, 0x7632);
-                hi[2] = __byte_perm(t2, t3, 0x5410);
-                hi[3] = __byte_perm(t2, t3, 0x7632);
-            }
+            octets_to_words(a, lo, hi);
             const int4 r4 = *reinterpret_cast<const int4*>(p.c2r + 4 * cw);
             const int rr[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
@@ -319,9 +324,14 @@ __global__ void __launch_bounds__(256, 4) k2t_build_pq(const __grid_constant__ P
         const int pw4 = p.pw >> 2;
         for (int q = lane; q < pw4; q += 32) {
             uint4 w[8];
+            if (j0 + 8 <= p.total) {       // (warp-uniform) all eight pseudo-sites exist
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-                w[k] = row[k] ? __ldg(reinterpret_cast<const uint4*>(row[k]) + q) : make_uint4(0u, 0u, 0u, 0u);
+                for (int k = 0; k < 8; ++k) w[k] = __ldg(reinterpret_cast<const uint4*>(row[k]) + q);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    w[k] = row[k] ? __ldg(reinterpret_cast<const uint4*>(row[k]) + q) : make_uint4(0u, 0u, 0u, 0u);
+            }
             uint4 op = make_uint4(0u, 0u, 0u, 0u), oq = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
@@ -343,18 +353,22 @@ __global__ void __launch_bounds__(256, 4) k2t_build_pq(const __grid_constant__ P
             reinterpret_cast<uint4*>(pq_st + (1 * 8 + o) * p.pw)[q] = oq;
         }
         __syncthreads();
-        const uint8_t* st8 = reinterpret_cast<const uint8_t*>(pq_st);
-        for (int c = tid; c < p.pitch; c += 256) {
-            const int r = p.c2r[c];
-            if (r < 0) continue;
-            uint64_t vp = 0, vq = 0;
+        for (int cw = tid; cw < p.pw; cw += 256) {      // a thread turns four columns of both planes
+            uint32_t a[8], plo[4], phi[4], qlo[4], qhi[4];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                vp |= (uint64_t)st8[(size_t)q * p.pitch + c] << (8 * q);
-                vq |= (uint64_t)st8[(size_t)(8 + q) * p.pitch + c] << (8 * q);
+            for (int q = 0; q < 8; ++q) a[q] = pq_st[q * p.pw + cw];
+            octets_to_words(a, plo, phi);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) a[q] = pq_st[(8 + q) * p.pw + cw];
+            octets_to_words(a, qlo, qhi);
+            const int4 r4 = *reinterpret_cast<const int4*>(p.c2r + 4 * cw);
+            const int rr[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (rr[j] < 0) continue;
+                p.pq[(chunk * 2 + 0) * p.R + rr[j]] = (uint64_t)plo[j] | ((uint64_t)phi[j] << 32);
+                p.pq[(chunk * 2 + 1) * p.R + rr[j]] = (uint64_t)qlo[j] | ((uint64_t)qhi[j] << 32);
             }
-            p.pq[(chunk * 2 + 0) * p.R + r] = vp;
-            p.pq[(chunk * 2 + 1) * p.R + r] = vq;
         }
         for (int r = p.Hk + tid; r < p.R; r += 256) {
             p.pq[(chunk * 2 + 0) * p.R + r] = 0ull;
@@ -397,14 +411,12 @@ struct GramParams {
 //   12     TMEM allocation + MMA issue (one thread)
 //   13     TMA: plane words -> raw ring (one thread)
 //   14..21 epilogue: TMEM -> registers -> global; warps w and w+4 share TMEM lane quarter w % 4
+// Geometry <GW, EW>: GW warps per expanding group (a multiple of 4: the same number on every scheduler), EW epilogue warps
+// (4 or 8).  <4, 8> = 22 warps, <8, 4> = 30 warps.
 constexpr int GRAM_XGROUPS = 3;
-constexpr int GRAM_XWARPS = 4 * GRAM_XGROUPS;
-constexpr int GRAM_WARP_MMA = GRAM_XWARPS, GRAM_WARP_TMA = GRAM_XWARPS + 1, GRAM_WARP_EPI = GRAM_XWARPS + 2;
-constexpr int GRAM_EPI_WARPS = 8;
-constexpr int GRAM_THREADS = (GRAM_WARP_EPI + GRAM_EPI_WARPS) * 32;
+constexpr int gram_threads(int GW, int EW) { return (GW * GRAM_XGROUPS + 2 + EW) * 32; }
 constexpr int GRAM_MAX_STAGES = 9;
 constexpr int GRAM_MAX_RAW = 9;            // depth of the raw plane-word ring (TMA runs this many chunks ahead)
-constexpr int GRAM_MAX_ITEMS = (128 + 512) * 2 / 128;    // plane words per expanding thread and stage
 
 // 16 bits -> 16 bytes of 0/1 (byte k = bit k): 4 bits -> 4 bytes is one IMAD + LOP3.  (A 256-entry shared-memory table,
 // 8 bits -> 8 bytes per LDS.64, was measured and dropped: the kernel is short of shared-memory bandwidth — the SS-mode MMAs
@@ -487,8 +499,13 @@ __device__ __forceinline__ GramItem gram_item(const GramParams& gp, int64_t j) {
 // Shared memory: [raw ring: nraw slots of NPL x RROWS plane words, filled by 1-D TMA bulk copies]
 //                [operand ring: nstages stages of 2 K steps x NPL planes x RROWS rows x 32 bytes] [+ slack]
 // RROWS = (128 rows of a separate A tile, only when some group needs one) + nbmax rows of the B range.
-template <int NPL>
-__global__ void __launch_bounds__(GRAM_THREADS, 1) k2t_gram(const __grid_constant__ GramParams gp) {
+template <int NPL, int GW, int EW>
+__global__ void __launch_bounds__(gram_threads(GW, EW), 1) k2t_gram(const __grid_constant__ GramParams gp) {
+    constexpr int GRAM_XWARPS = GW * GRAM_XGROUPS, GTHREADS = GW * 32;
+    constexpr int GRAM_WARP_MMA = GRAM_XWARPS, GRAM_WARP_TMA = GRAM_XWARPS + 1, GRAM_WARP_EPI = GRAM_XWARPS + 2;
+    constexpr int GRAM_EPI_WARPS = EW;
+    constexpr int GRAM_MAX_ITEMS = (128 + 512) * 2 / GTHREADS;    // plane words per expanding thread and stage
+    static_assert(GW % 4 == 0 && (EW == 4 || EW == 8) && GRAM_WARP_EPI % 4 == 2, "warp roles");
     extern __shared__ __align__(128) uint8_t gsm[];
     __shared__ __align__(8) uint64_t full[GRAM_MAX_STAGES], empty[GRAM_MAX_STAGES], raw_full[GRAM_MAX_RAW],
         raw_empty[GRAM_MAX_RAW], tmem_full, tmem_empty;
@@ -510,12 +527,12 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) k2t_gram(const __grid_constan
     if (warp == GRAM_WARP_MMA) {
         if (lane == 0) {
             for (int s = 0; s < NS; ++s) {
-                mbar_init(&full[s], 4);                 // the four warps of the expanding group that owns the slot
+                mbar_init(&full[s], GW);                // the warps of the expanding group that owns the slot
                 mbar_init(&empty[s], 1);
             }
             for (int s = 0; s < RD; ++s) {
                 mbar_init(&raw_full[s], 1);
-                mbar_init(&raw_empty[s], 4);
+                mbar_init(&raw_empty[s], GW);
             }
             mbar_init(&tmem_full, 1);
             mbar_init(&tmem_empty, GRAM_EPI_WARPS);
@@ -563,7 +580,7 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) k2t_gram(const __grid_constan
         // Several slots per group matter: a slot comes back only after the MMAs that read it have completed (the tensor
         // pipe's latency), and with one slot per group that latency sat in every group's critical path.
         const int XG = gp.xg;
-        const int xg = warp >> 2, xt = tid & 127;          // expanding group, thread inside the group
+        const int xg = warp / GW, xt = tid % GTHREADS;     // expanding group, thread inside the group
         const int SM_ = NS / XG, RM = RD / XG;             // operand / raw slots of this group
         int n_done = 0;                                    // stages this group has processed: stage n is gs = xg + n XG
         int sm = 0, rm = 0;                                // n_done % SM_, n_done % RM
@@ -579,7 +596,7 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) k2t_gram(const __grid_constan
             int r_idx[GRAM_MAX_ITEMS], d_off[GRAM_MAX_ITEMS];      // raw word index (-1 none, -2 zero row) / byte offset in a block
 #pragma unroll
             for (int q = 0; q < GRAM_MAX_ITEMS; ++q) {
-                const int item = xt + q * 128;
+                const int item = xt + q * GTHREADS;
                 r_idx[q] = -1;
                 d_off[q] = 0;
                 if (item < nitems) {
@@ -611,7 +628,7 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) k2t_gram(const __grid_constan
                 uint8_t* sb = op_base + (size_t)sslot * STAGE;
 #pragma unroll
                 for (int q = 0; q < GRAM_MAX_ITEMS; ++q) {
-                    if (q * 128 < nitems) {                 // warp-uniform: no instructions for item slots nobody uses
+                    if (q * GTHREADS < nitems) {            // warp-uniform: no instructions for item slots nobody uses
                         if (r_idx[q] != -1) {
                             const uint32_t wlo = (uint32_t)v[q], whi = (uint32_t)(v[q] >> 32);
                             uint8_t* d0 = sb + d_off[q];
@@ -719,13 +736,14 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) k2t_gram(const __grid_constan
             int32_t* orow = gp.out + (size_t)im.wb * gp.Hk * gp.Hk + (size_t)i * gp.Hk;
             const int cfirst = (ew >> 2) * 32;
             int c_last = cfirst;                            // last block this warp reads
-            while (c_last + 64 < im.g.nb_rows) c_last += 64;
+            constexpr int CSTEP = (EW / 4) * 32;          // the warps of a lane quarter take alternate 32-column blocks
+            while (c_last + CSTEP < im.g.nb_rows) c_last += CSTEP;
             if (cfirst >= im.g.nb_rows) {                   // nothing to read: release the accumulators right away
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tmem_empty);
             }
-            for (int c0 = cfirst; c0 < im.g.nb_rows; c0 += 64) {
+            for (int c0 = cfirst; c0 < im.g.nb_rows; c0 += CSTEP) {
                 uint32_t v[32];
                 if (im.nst > 0) {
                     const uint32_t taddr = tmem + ((uint32_t)(qd * 32) << 16) + (uint32_t)c0;
@@ -1009,10 +1027,20 @@ int pg_k2t_pairs(pg_ctx* ctx, const K2TPlanes& ps, const int64_t* d_lo, const in
                  int32_t* d_n) {
     static bool attr_dev[64] = {};
     if (!attr_dev[ctx->device & 63]) {
-        PG_CUDA(cudaFuncSetAttribute(k2t_gram<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-        PG_CUDA(cudaFuncSetAttribute(k2t_gram<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+        PG_CUDA(cudaFuncSetAttribute(k2t_gram<1, 4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+        PG_CUDA(cudaFuncSetAttribute(k2t_gram<2, 4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+        PG_CUDA(cudaFuncSetAttribute(k2t_gram<1, 8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+        PG_CUDA(cudaFuncSetAttribute(k2t_gram<2, 8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
         attr_dev[ctx->device & 63] = true;
     }
+    // expanding groups of 8 warps + 4 epilogue warps (30 warps) or 4 + 8 (22 warps): PG_K2T_GW = 4 | 8, per kernel
+    // PG_K2T_GW_N / PG_K2T_GW_D
+    auto gw_of = [](const char* name, int dflt) {
+        const char* e = getenv(name);
+        if (!e) e = getenv("PG_K2T_GW");
+        return e ? atoi(e) : dflt;
+    };
+    const bool wide_n = gw_of("PG_K2T_GW_N", 4) == 8, wide_d = gw_of("PG_K2T_GW_D", 4) == 8;
     // n_ij over the mask rows (one per sample when the haplotypes of a sample share their missingness), diff_ij over all rows
     const int Rn = ps.vpair ? ps.R2 : ps.R;
     std::vector<GramGroup> gn, gd;
@@ -1065,7 +1093,8 @@ int pg_k2t_pairs(pg_ctx* ctx, const K2TPlanes& ps, const int64_t* d_lo, const in
         gp.out = d_n;
         const unsigned grid = (unsigned)std::min<int64_t>((int64_t)nb * gp.ngroups, ctx->sm_count);
         const int ti = pg_time_begin(ctx, "k2t_gram_n");
-        k2t_gram<1><<<grid, GRAM_THREADS, smem, ctx->stream>>>(gp);
+        if (wide_n) k2t_gram<1, 8, 4><<<grid, gram_threads(8, 4), smem, ctx->stream>>>(gp);
+        else k2t_gram<1, 4, 8><<<grid, gram_threads(4, 8), smem, ctx->stream>>>(gp);
         pg_time_end(ctx, ti);
         PG_CUDA(cudaGetLastError());
     }
@@ -1082,7 +1111,8 @@ int pg_k2t_pairs(pg_ctx* ctx, const K2TPlanes& ps, const int64_t* d_lo, const in
         gp.out = d_diff;
         const unsigned grid = (unsigned)std::min<int64_t>((int64_t)nb * gp.ngroups, ctx->sm_count);
         const int ti = pg_time_begin(ctx, "k2t_gram_diff");
-        k2t_gram<2><<<grid, GRAM_THREADS, smem, ctx->stream>>>(gp);
+        if (wide_d) k2t_gram<2, 8, 4><<<grid, gram_threads(8, 4), smem, ctx->stream>>>(gp);
+        else k2t_gram<2, 4, 8><<<grid, gram_threads(4, 8), smem, ctx->stream>>>(gp);
         pg_time_end(ctx, ti);
         PG_CUDA(cudaGetLastError());
     }
