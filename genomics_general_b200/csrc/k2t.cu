@@ -17,10 +17,11 @@
 //                     presence nibble + pseudo-site count per chunk                       (one pass, HBM-bound)
 //   k2t_scan / k2t_inv : exclusive scan -> cps[site] (pseudo-site prefix) + inverse map pseudo-site -> (site, P bit, Q mask)
 //   k2t_build_pq    : gathers the variable sites' rows -> P / Q planes (64 pseudo-site chunks)
-//   k2t_gram<NPL>   : one CTA per (tile group, window): 4 producer warps expand plane words to 0/1 bytes in the
-//                     K-major no-swizzle core-matrix layout in shared memory, one thread issues tcgen05.mma (M=128,
-//                     N<=256, K=32 per instruction) into TMEM, tcgen05.commit releases the stage; the same 4 warps
-//                     read the accumulators back with tcgen05.ld and write the symmetric int32 matrix.
+//   k2t_gram<NPL>   : persistent CTAs (one per SM) over (window, tile group) items: TMA warps bring plane words into a raw
+//                     ring, three groups of warps expand them to 0/1 bytes in the K-major no-swizzle core-matrix layout
+//                     in shared memory, one warp issues tcgen05.mma (M=128, N<=256, K=32 per instruction) into TMEM,
+//                     tcgen05.commit releases the stage; epilogue warps read the accumulators back with tcgen05.ld and
+//                     write the upper triangle of the symmetric int32 matrix.
 #include <stdlib.h>
 
 #include <algorithm>
@@ -405,18 +406,17 @@ struct GramParams {
     int32_t* out;               // [nb][Hk][Hk], upper triangle (i <= j) only
 };
 
-// Warp roles of the persistent CTA (one per SM):
-//   0..11  expand: three groups of four warps (one warp per scheduler each); group k owns the stages k, k+3, k+6, ... so
-//          that while one group waits (shared-memory loads, the proxy fence) the other two keep the ALUs busy
-//   12     TMEM allocation + MMA issue (one thread)
-//   13     TMA: plane words -> raw ring (one thread)
-//   14..21 epilogue: TMEM -> registers -> global; warps w and w+4 share TMEM lane quarter w % 4
-// Geometry <GW, EW>: GW warps per expanding group (a multiple of 4: the same number on every scheduler), EW epilogue warps
-// (4 or 8).  <4, 8> = 22 warps, <8, 4> = 30 warps.
+// Warp roles of the persistent CTA (one per SM), geometry <GW, EW>:
+//   3 GW warps  expand: three groups of GW warps (GW / 4 per scheduler each); group k owns the stages k, k+3, k+6, ... so
+//               that while one group waits (shared-memory loads, the proxy fence) the other two keep the ALUs busy
+//   1 warp      TMEM allocation + MMA issue (warp-uniform loop, an elected lane issues)
+//   3 warps     TMA: warp t brings the plane words of group t's stages into group t's raw slots
+//   EW warps    epilogue: TMEM -> registers -> global (EW = 4 or 8; with 8, warps w and w+4 share TMEM lane quarter w % 4)
+// <8, 4> = 32 warps (the default: 64 registers), <4, 8> = 24 warps (80 registers; PG_K2T_GW=4).
 constexpr int GRAM_XGROUPS = 3;
-constexpr int gram_threads(int GW, int EW) { return (GW * GRAM_XGROUPS + 2 + EW) * 32; }
+constexpr int gram_threads(int GW, int EW) { return (GW * GRAM_XGROUPS + 1 + GRAM_XGROUPS + EW) * 32; }
 constexpr int GRAM_MAX_STAGES = 9;
-constexpr int GRAM_MAX_RAW = 9;            // depth of the raw plane-word ring (TMA runs this many chunks ahead)
+constexpr int GRAM_MAX_RAW = 48;           // depth of the raw plane-word ring (TMA runs this many chunks ahead)
 
 // 16 bits -> 16 bytes of 0/1 (byte k = bit k): 4 bits -> 4 bytes is one IMAD + LOP3.  (A 256-entry shared-memory table,
 // 8 bits -> 8 bytes per LDS.64, was measured and dropped: the kernel is short of shared-memory bandwidth — the SS-mode MMAs
@@ -502,10 +502,10 @@ __device__ __forceinline__ GramItem gram_item(const GramParams& gp, int64_t j) {
 template <int NPL, int GW, int EW>
 __global__ void __launch_bounds__(gram_threads(GW, EW), 1) k2t_gram(const __grid_constant__ GramParams gp) {
     constexpr int GRAM_XWARPS = GW * GRAM_XGROUPS, GTHREADS = GW * 32;
-    constexpr int GRAM_WARP_MMA = GRAM_XWARPS, GRAM_WARP_TMA = GRAM_XWARPS + 1, GRAM_WARP_EPI = GRAM_XWARPS + 2;
+    constexpr int GRAM_WARP_MMA = GRAM_XWARPS, GRAM_WARP_TMA = GRAM_XWARPS + 1, GRAM_WARP_EPI = GRAM_WARP_TMA + GRAM_XGROUPS;
     constexpr int GRAM_EPI_WARPS = EW;
     constexpr int GRAM_MAX_ITEMS = (128 + 512) * 2 / GTHREADS;    // plane words per expanding thread and stage
-    static_assert(GW % 4 == 0 && (EW == 4 || EW == 8) && GRAM_WARP_EPI % 4 == 2, "warp roles");
+    static_assert(GW % 4 == 0 && (EW == 4 || EW == 8) , "warp roles");
     extern __shared__ __align__(128) uint8_t gsm[];
     __shared__ __align__(8) uint64_t full[GRAM_MAX_STAGES], empty[GRAM_MAX_STAGES], raw_full[GRAM_MAX_RAW],
         raw_empty[GRAM_MAX_RAW], tmem_full, tmem_empty;
@@ -547,29 +547,47 @@ __global__ void __launch_bounds__(gram_threads(GW, EW), 1) k2t_gram(const __grid
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = s_tmem;
 
-    if (warp == GRAM_WARP_TMA) {
+    if (warp >= GRAM_WARP_TMA && warp < GRAM_WARP_EPI) {
         // ---------------- TMA: plane words of every chunk of every item -> raw ring ----------------
-        if (lane == 0) {
-            RingPos rp = {0, 0u};
-            int64_t gstage = 0;
+        // One warp per expanding group: warp t loads exactly the stages group t expands (gs % XG == t) into that group's raw
+        // slots, walking the same slot / parity sequence as the group.  (ONE thread issuing every stage's copies — ~60
+        // dependent instructions per stage — was what paced the whole kernel; the loop runs warp-uniform and an elected lane
+        // issues, so addresses stay in uniform registers.)
+        const int XG = gp.xg;
+        const int t = warp - GRAM_WARP_TMA;
+        if (t < XG) {
+            const int RM = RD / XG;
+            int n_done = 0, rm = 0;
+            uint32_t rph = 0;
+            int64_t gbase = 0;
             for (int64_t j = j0; j < j1; ++j) {
                 const GramItem im = gram_item<NPL>(gp, j);
                 const bool a_in_b = (im.g.a_row0 == im.g.b_row0);
                 const int a_rows = a_in_b ? 0 : min(128, gp.R - im.g.a_row0);
                 const uint32_t bytes_a = (uint32_t)a_rows * 8u, bytes_b = (uint32_t)im.g.nb_rows * 8u;
-                for (int it = 0; it < im.nst; ++it, ++gstage) {
-                    if (gstage >= RD) mbar_wait(&raw_empty[rp.s], rp.ph ^ 1u);
-                    mbar_expect_tx(&raw_full[rp.s], NPL * (bytes_a + bytes_b));
-                    const int64_t chunk = im.c_first + it;
+                int it = (int)(((int64_t)t - gbase % XG + XG) % XG);
+                for (; it < im.nst; it += XG) {
+                    const int rslot = t + XG * rm;
+                    if (n_done >= RM) mbar_wait(&raw_empty[rslot], rph ^ 1u);
+                    if (elect_one()) {
+                        mbar_expect_tx(&raw_full[rslot], NPL * (bytes_a + bytes_b));
+                        const int64_t chunk = im.c_first + it;
 #pragma unroll
-                    for (int pl = 0; pl < NPL; ++pl) {
-                        const uint64_t* src = gp.plane + (chunk * NPL + pl) * gp.R;
-                        uint8_t* dst = raw_base + (size_t)rp.s * RAW + (size_t)pl * RROWS * 8;
-                        if (bytes_a) bulk_g2s(dst, src + im.g.a_row0, bytes_a, &raw_full[rp.s]);
-                        bulk_g2s(dst + AOFF * 8, src + im.g.b_row0, bytes_b, &raw_full[rp.s]);
+                        for (int pl = 0; pl < NPL; ++pl) {
+                            const uint64_t* src = gp.plane + (chunk * NPL + pl) * gp.R;
+                            uint8_t* dst = raw_base + (size_t)rslot * RAW + (size_t)pl * RROWS * 8;
+                            if (bytes_a) bulk_g2s(dst, src + im.g.a_row0, bytes_a, &raw_full[rslot]);
+                            bulk_g2s(dst + AOFF * 8, src + im.g.b_row0, bytes_b, &raw_full[rslot]);
+                        }
                     }
-                    rp.advance(1, RD);
+                    __syncwarp();
+                    ++n_done;
+                    if (++rm == RM) {
+                        rm = 0;
+                        rph ^= 1u;
+                    }
                 }
+                gbase += im.nst;
             }
         }
     } else if (warp < GRAM_XWARPS) {
@@ -1040,7 +1058,7 @@ int pg_k2t_pairs(pg_ctx* ctx, const K2TPlanes& ps, const int64_t* d_lo, const in
         if (!e) e = getenv("PG_K2T_GW");
         return e ? atoi(e) : dflt;
     };
-    const bool wide_n = gw_of("PG_K2T_GW_N", 4) == 8, wide_d = gw_of("PG_K2T_GW_D", 4) == 8;
+    const bool wide_n = gw_of("PG_K2T_GW_N", 8) == 8, wide_d = gw_of("PG_K2T_GW_D", 8) == 8;
     // n_ij over the mask rows (one per sample when the haplotypes of a sample share their missingness), diff_ij over all rows
     const int Rn = ps.vpair ? ps.R2 : ps.R;
     std::vector<GramGroup> gn, gd;
