@@ -477,6 +477,7 @@ __global__ void __launch_bounds__(128) k2_popgen_epi_pairs(const __grid_constant
     for (int X = 0; X < P; ++X) {
         const int a0 = ep.pop_start[X] >> 1, a1 = ep.pop_start[X + 1] >> 1;
         for (int Y = X; Y < P; ++Y, ++blk) {
+            if (blk % (int)gridDim.y != (int)blockIdx.y) continue;      // few windows: the blocks of a window are dealt over gridDim.y CTAs
             const int b0 = ep.pop_start[Y] >> 1, b1 = ep.pop_start[Y + 1] >> 1;
             double s = 0.0;
             int c = 0;
@@ -532,6 +533,7 @@ __global__ void __launch_bounds__(128) k2_popgen_epi_pairs(const __grid_constant
     }
     __syncthreads();
     for (int b = threadIdx.x; b < nblk; b += 128) {
+        if (b % (int)gridDim.y != (int)blockIdx.y) continue;
         ep.blk_s[(size_t)wb * nblk + b] = ((sh_s[b * 4] + sh_s[b * 4 + 1]) + sh_s[b * 4 + 2]) + sh_s[b * 4 + 3];
         ep.blk_c[(size_t)wb * nblk + b] = sh_c[b * 4] + sh_c[b * 4 + 1] + sh_c[b * 4 + 2] + sh_c[b * 4 + 3];
     }
@@ -1125,7 +1127,9 @@ int pg_k2_popgen_windows(pg_ctx* ctx, const std::vector<int64_t>& wins, int32_t 
         // sample-pair walk: mask ids are r >> 1 (the tensor path's per-sample n rows) and populations start on even rows
         bool by_pairs = ps.tensor && ps.Hm * 2 == ps.Hk && (size_t)nblk * 64 <= 48 * 1024;
         for (int X = 0; X <= P; ++X) by_pairs = by_pairs && (pop_start[X] % 2 == 0);
-        if (by_pairs) k2_popgen_epi_pairs<<<(unsigned)nb, 128, (size_t)nblk * 64, ctx->stream>>>(ep);
+        // one CTA per window when there are many windows, else the blocks of a window over several CTAs (~8 CTAs per SM)
+        const unsigned nsplit = (unsigned)std::max<int64_t>(1, std::min<int64_t>(nblk, (8 * (int64_t)ctx->sm_count + (int64_t)nb - 1) / (int64_t)nb));
+        if (by_pairs) k2_popgen_epi_pairs<<<dim3((unsigned)nb, nsplit), 128, (size_t)nblk * 64, ctx->stream>>>(ep);
         else k2_popgen_epi_blocks<<<dim3((unsigned)nblk, (unsigned)nb), 256, 0, ctx->stream>>>(ep);
         k2_popgen_epi_final<<<(unsigned)((nb + 127) / 128), 128, 0, ctx->stream>>>(ep, (int)nb);
         pg_time_end(ctx, ti);

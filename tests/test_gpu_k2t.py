@@ -106,3 +106,60 @@ def test_many_windows_per_cta_equal_the_popc_kernels(eng, env, monkeypatch):
         else:
             for key in ("pi", "dxy", "fst"):
                 assert np.array_equal(r[key], first[key], equal_nan=True), (key, env)      # run after run: bit-identical
+
+
+def _direct_popgen(g, hap_pop, P, lo, hi, min_sites, min_data):
+    """pi / dxy of one window straight from the definition (genomics.py:931-993): mean over haplotype pairs of diff / n"""
+    d, n = ref_counts(g[lo:hi])
+    with np.errstate(divide="ignore", invalid="ignore"):
+        dist = np.where((n > 0) & (n >= min_sites), d / n.astype(np.float64), np.nan)
+    idx = [np.flatnonzero(hap_pop == X) for X in range(P)]
+    pi = np.full(P, np.nan)
+    for X in range(P):
+        blk = dist[np.ix_(idx[X], idx[X])].copy()
+        np.fill_diagonal(blk, np.nan)
+        if blk.size and 1.0 - np.isnan(blk).sum() / blk.size >= min_data and (~np.isnan(blk)).any():
+            pi[X] = np.nanmean(blk)
+    dxy = []
+    for X in range(P):
+        for Y in range(X + 1, P):
+            blk = dist[np.ix_(idx[X], idx[Y])]
+            ok = blk.size and 1.0 - np.isnan(blk).sum() / blk.size >= min_data and (~np.isnan(blk)).any()
+            dxy.append(np.nanmean(blk) if ok else np.nan)
+    return pi, np.array(dxy)
+
+
+@pytest.mark.parametrize("sizes,nwin", [((5, 7, 9), 3), ((1, 2, 3, 4, 5, 6, 7, 8), 2), ((50, 50, 50, 50), 7), ((101,), 1),
+                                        ((3, 3), 400)], ids=["odd3", "tiny8", "c2x7", "single101", "many_small"])
+def test_sample_pair_epilogue_every_layout(eng, sizes, nwin, monkeypatch):
+    """the sample-pair epilogue (one division per four haplotype pairs, folded diagonal blocks, blocks of a window dealt over
+    several CTAs when windows are few) against the definition and against the per-pair epilogue of the POPC path: odd and even
+    population sizes, one population, many populations with few windows, many windows"""
+    P = len(sizes)
+    rng = np.random.default_rng(11 + sum(sizes) + nwin)
+    S = 600 * nwin
+    nS = sum(sizes)
+    hap_pop = np.repeat(np.arange(P), [2 * s for s in sizes]).astype(np.int32)
+    g = rng.integers(0, 2, size=(S, 2 * nS)).astype(np.int8)
+    g[rng.random((S, 2 * nS)) < 0.02] = 2                                   # a third allele here and there
+    miss = rng.random((S, nS)) < 0.03                                        # missing GENOTYPES: both haplotypes of a sample
+    g[np.repeat(miss, 2, axis=1)] = -1
+    eng.upload(g, np.arange(1, S + 1, dtype=np.int32))
+    eng.set_pops(hap_pop, P)
+    lo = np.arange(0, S, 600, dtype=np.int64)
+    hi = lo + 600
+    eng.set_windows(lo, hi)
+    for min_sites in (0, 590):
+        r = eng.popgen(min_sites, 0.01, force_pairwise=True)
+        assert np.all(r["path"] == 2)
+        monkeypatch.setenv("PG_K2_POPC", "1")
+        ref = eng.popgen(min_sites, 0.01, force_pairwise=True)
+        monkeypatch.delenv("PG_K2_POPC")
+        for key in ("pi", "dxy", "fst"):
+            assert np.array_equal(np.isnan(r[key]), np.isnan(ref[key])), (key, min_sites)
+            assert np.allclose(r[key], ref[key], rtol=1e-12, atol=1e-12, equal_nan=True), (key, min_sites)
+        for w in range(min(nwin, 3)):
+            pi, dxy = _direct_popgen(g, hap_pop, P, int(lo[w]), int(hi[w]), min_sites, 0.01)
+            assert np.allclose(r["pi"][w], pi, rtol=1e-11, atol=1e-13, equal_nan=True), (w, min_sites)
+            if P > 1:
+                assert np.allclose(r["dxy"][w], dxy, rtol=1e-11, atol=1e-13, equal_nan=True), (w, min_sites)

@@ -8,7 +8,10 @@ KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'sm__inst_executed_pipe_fma.sum.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_lsu.sum.pct_of_peak_sustained_active',
         'sm__inst_executed_pipe_xu.sum.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_fp64.sum.pct_of_peak_sustained_active',
         'sm__cycles_elapsed.max', 'sm__cycles_elapsed.max.per_second', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
-        'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active']
+        'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 'sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed',
+        'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed',
+        'l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed']
 def main(rep, out=None):
     txt = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], stdout=subprocess.PIPE, text=True).stdout
     rows = list(csv.reader(txt.splitlines()))
