@@ -20,6 +20,6 @@ with Engine(0) as eng:
     for _ in range(3):
         r = eng.popgen(100, 0.01)
     k = {a: round(b["ms"], 3) for a, b in eng.last_timings().items()}
-    print(json.dumps(dict(env={a: b for a, b in os.environ.items() if a.startswith("PG_K2T")}, gram_n=k.get("k2t_gram_n"),
+    print(json.dumps(dict(env={a[7:]: b for a, b in os.environ.items() if a.startswith("PG_K2T")}, gram_n=k.get("k2t_gram_n"),
                           gram_diff=k.get("k2t_gram_diff"), total=round(sum(k.values()), 3),
                           check=float(np.nansum(r["pi"]) + np.nansum(r["dxy"])))))
