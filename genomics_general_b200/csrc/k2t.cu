@@ -403,6 +403,7 @@ struct GramParams {
     int nstages;                // operand ring depth (a multiple of xg)
     int nraw;                   // raw plane-word ring depth (a multiple of xg)
     int xg;                     // expanding groups at work (3, or 2 when only two operand stages fit)
+    int64_t nchunks;            // chunks of the plane (a stage of CH chunks may reach past the last one: clamped, masked to 0)
     int32_t* out;               // [nb][Hk][Hk], upper triangle (i <= j) only
 };
 
@@ -480,8 +481,9 @@ struct GramItem {
     int64_t lo, hi, c_first;
     int nst;
 };
-template <int NPL>
+template <int NPL, int CH>
 __device__ __forceinline__ GramItem gram_item(const GramParams& gp, int64_t j) {
+    constexpr int SH = 6 + (CH == 2 ? 1 : 0);           // a stage covers CH chunks of 64 (pseudo-)sites
     GramItem it;
     it.wb = (int)(j / gp.ngroups);
     it.g = gp.groups[j - (int64_t)it.wb * gp.ngroups];
@@ -491,20 +493,22 @@ __device__ __forceinline__ GramItem gram_item(const GramParams& gp, int64_t j) {
         it.lo = gp.cps[it.lo];
         it.hi = gp.cps[it.hi];
     }
-    it.c_first = it.lo >> 6;
-    it.nst = (it.hi > it.lo) ? (int)(((it.hi - 1) >> 6) - it.c_first + 1) : 0;
+    it.c_first = it.lo >> SH;                           // first STAGE of the window
+    it.nst = (it.hi > it.lo) ? (int)(((it.hi - 1) >> SH) - it.c_first + 1) : 0;
     return it;
 }
 
 // Shared memory: [raw ring: nraw slots of NPL x RROWS plane words, filled by 1-D TMA bulk copies]
 //                [operand ring: nstages stages of 2 K steps x NPL planes x RROWS rows x 32 bytes] [+ slack]
 // RROWS = (128 rows of a separate A tile, only when some group needs one) + nbmax rows of the B range.
-template <int NPL, int GW, int EW>
+// CH = chunks per stage (1 or 2): with 2, every per-stage hand-over (TMA wait, proxy fence, MMA issue, commit) serves 128 sites.
+template <int NPL, int GW, int EW, int CH = 1>
 __global__ void __launch_bounds__(gram_threads(GW, EW), 1) k2t_gram(const __grid_constant__ GramParams gp) {
+    static_assert(CH == 1 || CH == 2, "chunks per stage");
     constexpr int GRAM_XWARPS = GW * GRAM_XGROUPS, GTHREADS = GW * 32;
     constexpr int GRAM_WARP_MMA = GRAM_XWARPS, GRAM_WARP_TMA = GRAM_XWARPS + 1, GRAM_WARP_EPI = GRAM_WARP_TMA + GRAM_XGROUPS;
     constexpr int GRAM_EPI_WARPS = EW;
-    constexpr int GRAM_MAX_ITEMS = (128 + 512) * 2 / GTHREADS;    // plane words per expanding thread and stage
+    constexpr int GRAM_MAX_ITEMS = ((128 + 512) * NPL + GTHREADS - 1) / GTHREADS;    // plane rows per expanding thread and stage
     static_assert(GW % 4 == 0 && (EW == 4 || EW == 8) , "warp roles");
     extern __shared__ __align__(128) uint8_t gsm[];
     __shared__ __align__(8) uint64_t full[GRAM_MAX_STAGES], empty[GRAM_MAX_STAGES], raw_full[GRAM_MAX_RAW],
@@ -514,9 +518,10 @@ __global__ void __launch_bounds__(gram_threads(GW, EW), 1) k2t_gram(const __grid
     const int NS = gp.nstages, RD = gp.nraw;
     const int AOFF = gp.a_sep ? 128 : 0;                // rows of the separate A region in front of the B rows
     const int RROWS = AOFF + gp.nbmax;                  // rows of one plane in a raw slot / operand block
-    const int RAW = NPL * RROWS * 8;                    // bytes of one raw slot
+    const int RAW1 = NPL * RROWS * 8;                   // plane words of ONE chunk in a raw slot
+    const int RAW = CH * RAW1;                          // bytes of one raw slot
     const int BLK = RROWS * 32;                         // one (K step, plane) operand block
-    const int STAGE = 2 * NPL * BLK;
+    const int STAGE = CH * 2 * NPL * BLK;
     uint8_t* const raw_base = gsm;
     uint8_t* const op_base = gsm + (size_t)RD * RAW;
 
@@ -561,7 +566,7 @@ __global__ void __launch_bounds__(gram_threads(GW, EW), 1) k2t_gram(const __grid
             uint32_t rph = 0;
             int64_t gbase = 0;
             for (int64_t j = j0; j < j1; ++j) {
-                const GramItem im = gram_item<NPL>(gp, j);
+                const GramItem im = gram_item<NPL, CH>(gp, j);
                 const bool a_in_b = (im.g.a_row0 == im.g.b_row0);
                 const int a_rows = a_in_b ? 0 : min(128, gp.R - im.g.a_row0);
                 const uint32_t bytes_a = (uint32_t)a_rows * 8u, bytes_b = (uint32_t)im.g.nb_rows * 8u;
@@ -570,14 +575,18 @@ __global__ void __launch_bounds__(gram_threads(GW, EW), 1) k2t_gram(const __grid
                     const int rslot = t + XG * rm;
                     if (n_done >= RM) mbar_wait(&raw_empty[rslot], rph ^ 1u);
                     if (elect_one()) {
-                        mbar_expect_tx(&raw_full[rslot], NPL * (bytes_a + bytes_b));
-                        const int64_t chunk = im.c_first + it;
+                        mbar_expect_tx(&raw_full[rslot], CH * NPL * (bytes_a + bytes_b));
 #pragma unroll
-                        for (int pl = 0; pl < NPL; ++pl) {
-                            const uint64_t* src = gp.plane + (chunk * NPL + pl) * gp.R;
-                            uint8_t* dst = raw_base + (size_t)rslot * RAW + (size_t)pl * RROWS * 8;
-                            if (bytes_a) bulk_g2s(dst, src + im.g.a_row0, bytes_a, &raw_full[rslot]);
-                            bulk_g2s(dst + AOFF * 8, src + im.g.b_row0, bytes_b, &raw_full[rslot]);
+                        for (int h = 0; h < CH; ++h) {
+                            // a chunk past the end of the plane is read from the last one; its mask is 0
+                            const int64_t chunk = min((im.c_first + it) * CH + h, gp.nchunks - 1);
+#pragma unroll
+                            for (int pl = 0; pl < NPL; ++pl) {
+                                const uint64_t* src = gp.plane + (chunk * NPL + pl) * gp.R;
+                                uint8_t* dst = raw_base + (size_t)rslot * RAW + (size_t)h * RAW1 + (size_t)pl * RROWS * 8;
+                                if (bytes_a) bulk_g2s(dst, src + im.g.a_row0, bytes_a, &raw_full[rslot]);
+                                bulk_g2s(dst + AOFF * 8, src + im.g.b_row0, bytes_b, &raw_full[rslot]);
+                            }
                         }
                     }
                     __syncwarp();
@@ -605,7 +614,7 @@ __global__ void __launch_bounds__(gram_threads(GW, EW), 1) k2t_gram(const __grid
         uint32_t sph = 0, rph = 0;                         // (n_done / SM_) & 1, (n_done / RM) & 1
         int64_t gbase = 0;                                 // global stage index of the item's first stage
         for (int64_t j = j0; j < j1 && xg < XG; ++j) {
-            const GramItem im = gram_item<NPL>(gp, j);
+            const GramItem im = gram_item<NPL, CH>(gp, j);
             const bool a_in_b = (im.g.a_row0 == im.g.b_row0);
             // rows expanded per plane: [separate A tile (128 rows)] + B range
             const int skip_a = a_in_b ? 128 : 0;
@@ -630,31 +639,41 @@ __global__ void __launch_bounds__(gram_threads(GW, EW), 1) k2t_gram(const __grid
             int it = (int)(((int64_t)xg - gbase % XG + XG) % XG);
             for (; it < im.nst; it += XG) {
                 const int rslot = xg + XG * rm, sslot = xg + XG * sm;
-                const int64_t chunk = im.c_first + it;
-                uint64_t mask = ~0ull;
-                {
-                    const int64_t b0 = chunk << 6;
-                    if (im.lo > b0) mask &= ~0ull << (int)(im.lo - b0);
-                    if (im.hi < b0 + 64) mask &= ~0ull >> (int)(b0 + 64 - im.hi);
+                uint64_t mask[CH];
+#pragma unroll
+                for (int h = 0; h < CH; ++h) {
+                    const int64_t b0 = ((im.c_first + it) * CH + h) << 6;
+                    uint64_t m = 0ull;                                  // a chunk outside the window (CH > 1 only)
+                    if (b0 < im.hi && b0 + 64 > im.lo) {
+                        m = ~0ull;
+                        if (im.lo > b0) m &= ~0ull << (int)(im.lo - b0);
+                        if (im.hi < b0 + 64) m &= ~0ull >> (int)(b0 + 64 - im.hi);
+                    }
+                    mask[h] = m;
                 }
                 mbar_wait(&raw_full[rslot], rph);
                 const uint64_t* rw = reinterpret_cast<const uint64_t*>(raw_base + (size_t)rslot * RAW);
-                uint64_t v[GRAM_MAX_ITEMS];
+                uint64_t v[GRAM_MAX_ITEMS][CH];
 #pragma unroll
-                for (int q = 0; q < GRAM_MAX_ITEMS; ++q) v[q] = (r_idx[q] >= 0) ? (rw[r_idx[q]] & mask) : 0ull;
+                for (int q = 0; q < GRAM_MAX_ITEMS; ++q)
+#pragma unroll
+                    for (int h = 0; h < CH; ++h) v[q][h] = (r_idx[q] >= 0) ? (rw[h * (RAW1 / 8) + r_idx[q]] & mask[h]) : 0ull;
                 if (n_done >= SM_) mbar_wait(&empty[sslot], sph ^ 1u);
                 uint8_t* sb = op_base + (size_t)sslot * STAGE;
 #pragma unroll
                 for (int q = 0; q < GRAM_MAX_ITEMS; ++q) {
                     if (q * GTHREADS < nitems) {            // warp-uniform: no instructions for item slots nobody uses
                         if (r_idx[q] != -1) {
-                            const uint32_t wlo = (uint32_t)v[q], whi = (uint32_t)(v[q] >> 32);
-                            uint8_t* d0 = sb + d_off[q];
-                            uint8_t* d1 = d0 + NPL * BLK;
-                            *reinterpret_cast<uint4*>(d0) = expand16(wlo & 0xffffu);
-                            *reinterpret_cast<uint4*>(d0 + 128) = expand16(wlo >> 16);
-                            *reinterpret_cast<uint4*>(d1) = expand16(whi & 0xffffu);
-                            *reinterpret_cast<uint4*>(d1 + 128) = expand16(whi >> 16);
+#pragma unroll
+                            for (int h = 0; h < CH; ++h) {
+                                const uint32_t wlo = (uint32_t)v[q][h], whi = (uint32_t)(v[q][h] >> 32);
+                                uint8_t* d0 = sb + (size_t)h * 2 * NPL * BLK + d_off[q];      // K steps 2h, 2h + 1
+                                uint8_t* d1 = d0 + NPL * BLK;
+                                *reinterpret_cast<uint4*>(d0) = expand16(wlo & 0xffffu);
+                                *reinterpret_cast<uint4*>(d0 + 128) = expand16(wlo >> 16);
+                                *reinterpret_cast<uint4*>(d1) = expand16(whi & 0xffffu);
+                                *reinterpret_cast<uint4*>(d1 + 128) = expand16(whi >> 16);
+                            }
                         }
                     }
                 }
@@ -695,7 +714,7 @@ __global__ void __launch_bounds__(gram_threads(GW, EW), 1) k2t_gram(const __grid
             RingPos sp = {0, 0u};
             int64_t k = 0;                                  // items done by this CTA
             for (int64_t j = j0; j < j1; ++j, ++k) {
-                const GramItem im = gram_item<NPL>(gp, j);
+                const GramItem im = gram_item<NPL, CH>(gp, j);
                 // A tile inside the B rows for a diagonal group, else the separate A region in front of them
                 const uint32_t a16 = (im.g.a_row0 == im.g.b_row0) ? (uint32_t)AOFF * 2u : 0u;
                 const uint32_t b16 = (uint32_t)AOFF * 2u;                 // 32 bytes per row = 2 units of 16 bytes
@@ -711,7 +730,7 @@ __global__ void __launch_bounds__(gram_threads(GW, EW), 1) k2t_gram(const __grid
                     const uint32_t st16 = sbase16 + (uint32_t)sp.s * stage16;
                     if (elect_one()) {
 #pragma unroll
-                        for (int ks = 0; ks < 2; ++ks) {
+                        for (int ks = 0; ks < 2 * CH; ++ks) {
                             const uint32_t acc0 = (it > 0 || ks > 0) ? 1u : 0u;
                             if (NPL == 1) {
                                 const uint32_t blk = st16 + ks * blk16;
@@ -747,7 +766,7 @@ __global__ void __launch_bounds__(gram_threads(GW, EW), 1) k2t_gram(const __grid
         const bool vec_ok = (gp.Hk & 3) == 0;              // rows are 16-byte aligned: a lane stores its 32 columns as 8 x 16 bytes
         int64_t k = 0;
         for (int64_t j = j0; j < j1; ++j, ++k) {
-            const GramItem im = gram_item<NPL>(gp, j);
+            const GramItem im = gram_item<NPL, CH>(gp, j);
             mbar_wait(&tmem_full, (uint32_t)(k & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int i = im.g.a_row0 + qd * 32 + lane;     // this lane's matrix row
@@ -1049,6 +1068,7 @@ int pg_k2t_pairs(pg_ctx* ctx, const K2TPlanes& ps, const int64_t* d_lo, const in
         PG_CUDA(cudaFuncSetAttribute(k2t_gram<2, 4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
         PG_CUDA(cudaFuncSetAttribute(k2t_gram<1, 8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
         PG_CUDA(cudaFuncSetAttribute(k2t_gram<2, 8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+        PG_CUDA(cudaFuncSetAttribute(k2t_gram<1, 8, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
         attr_dev[ctx->device & 63] = true;
     }
     // expanding groups of 8 warps + 4 epilogue warps (30 warps) or 4 + 8 (22 warps): PG_K2T_GW = 4 | 8, per kernel
@@ -1079,9 +1099,9 @@ int pg_k2t_pairs(pg_ctx* ctx, const K2TPlanes& ps, const int64_t* d_lo, const in
     // 128-row A tile of a diagonal group may reach past a short B range)
     const int budget = 222 * 1024;            // + 2.3 KB of static shared memory (barriers, the expansion table) <= 227 KB
     const int fixed = 4096;
-    auto geometry = [&](int npl, int nbmax, int a_sep, int& nstages, int& nraw, int& xg) {
+    auto geometry = [&](int npl, int nbmax, int a_sep, int& nstages, int& nraw, int& xg, int ch = 1) {
         const int rrows = (a_sep ? 128 : 0) + nbmax;
-        const int stage = 2 * npl * rrows * 32, raw = npl * rrows * 8;
+        const int stage = ch * 2 * npl * rrows * 32, raw = ch * npl * rrows * 8;
         // operand stages: 9, 6 or 3 (three expanding groups with 3 / 2 / 1 slots each), else 2 (two groups); raw slots a
         // multiple of the group count too, so that every slot has ONE consumer group
         const int avail = budget - fixed;
@@ -1105,13 +1125,21 @@ int pg_k2t_pairs(pg_ctx* ctx, const K2TPlanes& ps, const int64_t* d_lo, const in
         gp.ngroups = (int)gn.size();
         gp.nbmax = nbmax_n;
         gp.a_sep = asep_n;
-        const size_t smem = geometry(1, nbmax_n, asep_n, gp.nstages, gp.nraw, gp.xg);
+        // 128-site stages where at least three of them fit (PG_K2T_CH=2; every site counts for n_ij, so its K is the long one)
+        int ch_n = (getenv("PG_K2T_CH") && atoi(getenv("PG_K2T_CH")) == 2 && wide_n) ? 2 : 1;
+        size_t smem = geometry(1, nbmax_n, asep_n, gp.nstages, gp.nraw, gp.xg, ch_n);
+        if (ch_n == 2 && gp.nstages < 3) {
+            ch_n = 1;
+            smem = geometry(1, nbmax_n, asep_n, gp.nstages, gp.nraw, gp.xg, 1);
+        }
         gp.plane = ps.vpair ? ps.vpair : ps.vplane;
+        gp.nchunks = ps.nchunk_v;
         gp.cps = nullptr;
         gp.out = d_n;
         const unsigned grid = (unsigned)std::min<int64_t>((int64_t)nb * gp.ngroups, ctx->sm_count);
         const int ti = pg_time_begin(ctx, "k2t_gram_n");
-        if (wide_n) k2t_gram<1, 8, 4><<<grid, gram_threads(8, 4), smem, ctx->stream>>>(gp);
+        if (ch_n == 2) k2t_gram<1, 8, 4, 2><<<grid, gram_threads(8, 4), smem, ctx->stream>>>(gp);
+        else if (wide_n) k2t_gram<1, 8, 4><<<grid, gram_threads(8, 4), smem, ctx->stream>>>(gp);
         else k2t_gram<1, 4, 8><<<grid, gram_threads(4, 8), smem, ctx->stream>>>(gp);
         pg_time_end(ctx, ti);
         PG_CUDA(cudaGetLastError());
@@ -1125,6 +1153,7 @@ int pg_k2t_pairs(pg_ctx* ctx, const K2TPlanes& ps, const int64_t* d_lo, const in
         gp.a_sep = asep_d;
         const size_t smem = geometry(2, nbmax_d, asep_d, gp.nstages, gp.nraw, gp.xg);
         gp.plane = ps.pq;
+        gp.nchunks = (ps.npseudo + 63) / 64;
         gp.cps = ps.cps;
         gp.out = d_diff;
         const unsigned grid = (unsigned)std::min<int64_t>((int64_t)nb * gp.ngroups, ctx->sm_count);

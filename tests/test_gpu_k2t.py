@@ -53,8 +53,11 @@ def test_pair_counts_bit_exact_vs_numpy_and_popc(eng, shape, monkeypatch):
     for w, (lo, hi) in enumerate(wins):
         rd, rn = ref_counts(g[lo:hi])
         monkeypatch.delenv("PG_K2_POPC", raising=False)
-        d, n = eng.pair_counts(w)
-        assert np.array_equal(n, rn) and np.array_equal(d, rd), (w, lo, hi)
+        for ch in ("2", "1"):                      # 128-site and 64-site stages of the co-valid Gram kernel
+            monkeypatch.setenv("PG_K2T_CH", ch)
+            d, n = eng.pair_counts(w)
+            assert np.array_equal(n, rn) and np.array_equal(d, rd), (w, lo, hi, ch)
+        monkeypatch.delenv("PG_K2T_CH")
         if P * spp * 2 <= 600:
             monkeypatch.setenv("PG_K2_POPC", "1")
             d2, n2 = eng.pair_counts(w)
@@ -77,7 +80,8 @@ def test_allele_level_missingness_uses_one_mask_row_per_haplotype(eng):
 
 
 @pytest.mark.parametrize("env", [{}, {"PG_K2T_NRAW": "1"}, {"PG_K2T_NRAW": "1", "PG_K2T_NSTAGES": "1"}, {"PG_K2T_NSTAGES": "2"},
-                                 {"PG_K2T_NO_PAIRS": "1"}], ids=lambda e: "_".join("%s%s" % (k[7:], v) for k, v in e.items()) or "default")
+                                 {"PG_K2T_NO_PAIRS": "1"}, {"PG_K2T_CH": "2"}, {"PG_K2T_CH": "2", "PG_K2T_NRAW": "1"},
+                                 {"PG_K2T_CH": "1"}], ids=lambda e: "_".join("%s%s" % (k[7:], v) for k, v in e.items()) or "default")
 def test_many_windows_per_cta_equal_the_popc_kernels(eng, env, monkeypatch):
     """600 windows over 148 persistent CTAs, every ring geometry: statistics identical to the POPC path, run after run"""
     S = 3_000_000
