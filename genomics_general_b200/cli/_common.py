@@ -104,13 +104,50 @@ def ploidy_dict(args, allInds, haploid_list):
         with open(args.ploidyFile, "rt") as pf:
             return dict([[s[0], int(s[1])] for s in [l.split() for l in pf if l.strip()]])
     if getattr(args, "inferPloidy", False):
-        raise NotImplementedError("--inferPloidy (per-window ploidy inference, 'NOT RECOMMENDED' in the reference) "
-                                  "is not supported by the dense engine")
+        return infer_ploidy(args, allInds)
     base = 1 if args.genoFormat == "haplo" else 2
     d = dict(zip(allInds, [base] * len(allInds)))
     for s in haploid_list or []:
         d[s] = 1
     return d
+
+
+def first_data_line(args):
+    """First genotype line of the input (the line after the header; '#' and blank lines skipped)."""
+    path = getattr(args, "genoFile", None)
+    has_header = not getattr(args, "header", None)
+    if path is None:
+        lines = iter(stdin_bytes().split(b"\n", 64))
+    else:
+        lines = gzip.open(path, "rb") if path.endswith(".gz") else open(path, "rb")
+    try:
+        for ln in lines:
+            if has_header:
+                has_header = False
+                continue
+            if ln.strip() and not ln.startswith(b"#"):
+                return ln.decode()
+    finally:
+        if path is not None:
+            lines.close()
+    return ""
+
+
+def infer_ploidy(args, allInds):
+    """--inferPloidy (popgenWindows.py:299-300): the reference leaves every ploidy None and genoToAlignment takes the number
+    of sequences splitSeq makes of the window's genotype tokens (genomics.py:1109-1110, 390-396: characters 0,2,.. of a
+    phased token, every character of a pairs / alleles / haplo token, two for a diplo letter).  The dense engine holds one
+    matrix for the whole file, so the token widths of the first genotype line fix the ploidies; a later line whose tokens
+    have another width is reported by the tokenizer with its line number (the reference would give that window a
+    different number of haplotypes)."""
+    names = header_names(getattr(args, "genoFile", None)) if not getattr(args, "header", None) else args.header.split()[2:]
+    toks = first_data_line(args).split()[2:]
+    fmt = args.genoFormat
+    width = {}
+    for n, t in zip(names, toks):
+        width.setdefault(n, 2 if fmt == "diplo" else (len(t) + 1) // 2 if fmt == "phased" else len(t))
+    base = 1 if fmt == "haplo" else 2
+    return dict((s, width.get(s, base)) for s in allInds)
 
 
 _STDIN = {}        # the piped input is read once: the header comes from its first line, load_geno gets the same bytes

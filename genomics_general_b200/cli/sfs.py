@@ -5,8 +5,18 @@ counts -> target allele -> dense histograms, `pg_sfs`) or from tables of counts 
 `targetCounts`, the script's default: e.g. freq.py --target derived --asCounts; `pg_sfs_tables`) — and written in the
 reference's sparse format and order.
 
-Not covered: `--subsample` (the reference draws with numpy's global RNG per site), `--regions`.  Where the reference's choice of the minor allele depends on numpy's unstable
-sort (two alleles with exactly equal counts, sfs.py:90) the lower allele is used.
+`--regions` / `--regionsFile` (sfs.py:266-276, 430-435): one count column per interval — the spectra of the intervals
+are computed one after the other on the device (the interval is a site mask) and merged into the reference's rows.
+`--subsample N` (sfs.py:23-24, 42-53, 380-403, 468-471): the reference down-samples the base counts of every population
+at every site with numpy's GLOBAL Mersenne-Twister stream (`np.random.seed(--seed)`, one `np.random.choice` per
+population and site, in file order).  The draw is defined by that stream, so it is made here with the same generator
+(`np.random.RandomState(seed)`) on the per-site counts the device wrote, in the same order; the target allele and the
+histograms of the down-sampled counts are then computed on the device (`pg_sfs_tables`).
+Not covered: `--subsampleIndividuals` (the reference draws individuals with Python's *unseeded* `random.sample`, and on
+Python >= 3.11 that call rejects the numpy array it is given, so every site is dropped, sfs.py:44-49).  Where the
+reference's choice of the minor allele depends on numpy's unstable sort (two alleles with exactly equal counts,
+sfs.py:90) the lower allele is used.  A region without coordinates ("chr1") means the whole scaffold; the reference
+builds its upper limit as `np.array([np.inf], dtype=int)` (genomics.py:2367), which numpy >= 2 refuses.
 """
 from __future__ import annotations
 
@@ -60,21 +70,31 @@ def build_parser():
 
 def ordered_chains(hist, first):
     """Dense spectrum + first-site array -> rows [k1, .., kd, count] in the order the reference writes its nested
-    SparseFS dictionaries (sfs.py:117-125): at every nesting level, keys in order of first appearance."""
-    nz = np.argwhere(hist > 0)
+    SparseFS dictionaries (sfs.py:117-125): at every nesting level, keys in order of first appearance.  `hist` / `first`
+    may be lists (one spectrum per --regions interval): a row then carries one count per interval, and a key appears
+    when its first site in ANY interval does (sfs.py:492-494 adds the whole boolean vector at once)."""
+    hs = list(hist) if isinstance(hist, (list, tuple)) else [hist]
+    fs = list(first) if isinstance(first, (list, tuple)) else [first]
+    big = np.iinfo(np.int64).max
+    tot = hs[0].copy()
+    fmin = np.where(hs[0] > 0, fs[0], big)
+    for h, f1 in zip(hs[1:], fs[1:]):
+        tot = tot + h
+        fmin = np.minimum(fmin, np.where(h > 0, f1, big))
+    nz = np.argwhere(tot > 0)
     if len(nz) == 0:
         return []
-    f = first[tuple(nz.T)]
+    f = fmin[tuple(nz.T)]
     keys = []
     for lev in range(nz.shape[1]):
         _, inv = np.unique(nz[:, :lev + 1], axis=0, return_inverse=True)
         inv = np.asarray(inv).reshape(-1)
-        m = np.full(inv.max() + 1, np.iinfo(np.int64).max, dtype=np.int64)
+        m = np.full(inv.max() + 1, big, dtype=np.int64)
         np.minimum.at(m, inv, f)
         keys.append(m[inv])
     order = np.lexsort(tuple(reversed(keys)))
-    cnt = hist[tuple(nz.T)]
-    return [list(map(int, nz[i])) + [int(cnt[i])] for i in order]
+    cnts = [h[tuple(nz.T)] for h in hs]
+    return [list(map(int, nz[i])) + [int(c[i]) for c in cnts] for i in order]
 
 
 def write_spectra(args, FSpops, hists, firsts):
@@ -86,6 +106,112 @@ def write_spectra(args, FSpops, hists, firsts):
         else:
             with open(args.pref + "_".join(grp) + args.suff, "w") as out:
                 out.write(text)
+
+
+def parse_region_text(text):
+    """genomics.parseRegionText (genomics.py:2323-2336): chrom | chrom:pos | chrom:from-to (a reversed pair is swapped)."""
+    parts = text.split(":")
+    if len(parts) >= 3 and parts[2] != "" and parts[2] not in "+-":
+        raise ValueError("Incorrect region specification")
+    try:
+        ft = [int(x) for x in parts[1].split("-")]
+        if len(ft) == 1:
+            ft.append(None)
+        if ft[1] is not None and ft[0] > ft[1]:
+            ft = ft[::-1]
+        return (parts[0], ft[0], ft[1])
+    except Exception:
+        return (parts[0], None, None)
+
+
+def read_intervals(args):
+    """--regions / --regionsFile -> [(chrom, start, end)], both ends inclusive, end None = open (genomics.Intervals,
+    genomics.py:2361-2367: no start = 0; no end = the start, i.e. one position; neither = the whole scaffold)."""
+    if args.regions:
+        tuples = [parse_region_text(r) for r in args.regions]
+    elif args.regionsFile:
+        with open(args.regionsFile, "rt") as f:
+            tuples = [tuple(line.split()) for line in f if line.strip()]
+    else:
+        return None
+    out = []
+    for t in tuples:
+        has_start = len(t) > 1 and t[1] is not None
+        start = int(t[1]) if has_start else 0
+        end = int(t[2]) if len(t) > 2 and t[2] is not None else (start if has_start else None)
+        out.append((str(t[0]), start, end))
+    sys.stderr.write("Recording SFS for {} intervals\n".format(len(out)))
+    return out
+
+
+def interval_masks(intervals, scaffold_of_site, pos, base_mask):
+    """Intervals.containsPoint (genomics.py:2377-2378) for every site: one uint8 mask per interval, ANDed with the
+    --include / --exclude mask.  Without intervals: [base_mask]."""
+    if intervals is None:
+        return [base_mask]
+    pos = np.asarray(pos, dtype=np.int64)
+    out = []
+    for chrom, start, end in intervals:
+        m = (scaffold_of_site == chrom) & (pos >= start)
+        if end is not None:
+            m &= pos <= end
+        if base_mask is not None:
+            m &= base_mask.astype(bool)
+        out.append(m.astype(np.uint8))
+    return out
+
+
+def considered_sites(masks, n):
+    """sites that get as far as the draw: inside --include / --exclude and inside at least one interval (sfs.py:427-435)"""
+    if masks[0] is None:
+        return np.ones(n, dtype=bool)
+    return np.logical_or.reduce([np.asarray(m, dtype=bool) for m in masks])
+
+
+def subsample_sizes(args, inPopNames):
+    """sfs.py:380-385"""
+    if args.subsampleIndividuals:
+        raise NotImplementedError("--subsampleIndividuals: the reference draws with Python's unseeded random.sample (and drops "
+                                  "every site on Python >= 3.11, sfs.py:44-49); not supported")
+    if args.subsample is None:
+        return None
+    sub = list(args.subsample)
+    if len(sub) == 1:
+        sub = sub * len(inPopNames)
+    assert len(sub) == len(inPopNames), \
+        "subsample list ({}) must match number of ingroup populations ({}).".format(len(sub), len(inPopNames))
+    return sub
+
+
+def downsample_counts(counts, sizes, seed, considered):
+    """downSampleBaseCounts at every considered site (sfs.py:23-24, 51, 470): for site after site and in-group population
+    after population, N alleles are drawn without replacement from the population's base counts with the legacy global
+    stream numpy seeds with --seed; a population with fewer than N alleles raises inside the reference's list
+    comprehension, the site is dropped and the populations after it draw nothing.  counts: [n, >= len(sizes), 4];
+    returns (down-sampled copy, uint8 mask of the sites that went through)."""
+    rs = np.random.RandomState(seed)
+    out = np.array(counts, dtype=np.int64, copy=True)
+    ok = np.zeros(len(out), dtype=np.uint8)
+    bases = np.arange(4)
+    for s in np.flatnonzero(considered):
+        row = out[s]
+        good = True
+        for i, N in enumerate(sizes):
+            pool = np.repeat(bases, row[i])
+            if N > len(pool) or (len(pool) == 0 and N != 0):
+                good = False
+                break
+            row[i] = np.bincount(rs.choice(pool, N, replace=False), minlength=4)
+        ok[s] = good
+    return out, ok
+
+
+def merge_intervals(per, n_spectra):
+    """[(hists, firsts, n) per interval] -> (per spectrum: list of the intervals' hists, list of their firsts).  Tables
+    size their histograms by the largest count they hold, so the shapes are the same for every interval."""
+    if len(per) == 1:
+        return per[0][0], per[0][1]
+    return ([[p[0][k] for p in per] for k in range(n_spectra)], [[p[1][k] for p in per] for k in range(n_spectra)])
 
 
 def main_tables(args, include, exclude):
@@ -127,9 +253,12 @@ def main_tables(args, include, exclude):
     df = pd.read_csv(io.StringIO(body), sep=r"\s+", header=None, names=["scaffold", "position"] + names, dtype=str)
     order = inPopNames + ([outgroup] if outgroup else [])
     mask = None
+    sc = df["scaffold"].to_numpy().astype(str) if len(df) else np.zeros(0, dtype=str)
     if include or exclude:
-        sc = df["scaffold"].to_numpy()
         mask = np.array([(not include or x in include) and (x not in exclude) for x in sc], dtype=np.uint8)
+    intervals = read_intervals(args)
+    masks = interval_masks(intervals, sc, df["position"].to_numpy(dtype=np.int64) if intervals else None, mask)
+    sub = subsample_sizes(args, inPopNames)
     if args.inputType == "baseCounts":
         cols = []
         for pn in order:
@@ -138,22 +267,21 @@ def main_tables(args, include, exclude):
         table = np.stack(cols, axis=1) if len(df) else np.zeros((0, len(order), 4), dtype=np.int64)
         assert table.max(initial=0) <= 65535, "counts above 65535 are not supported"
         kind = "base"
+        if sub is not None:                                              # sfs.py:468-471
+            table, went = downsample_counts(table, sub, args.seed, considered_sites(masks, len(table)))
+            masks = [went if m is None else (m & went) for m in masks]
     else:
         table = df[order].to_numpy(dtype=np.int64) if len(df) else np.zeros((0, len(order)), dtype=np.int64)
         kind = "target"
     groups = [tuple(inPopNames.index(pn) for pn in grp) for grp in FSpops]
     with Engine(args.device) as eng:
-        hists, firsts, _ = eng.sfs_tables(kind, table, len(inPopNames), groups, outgroup=len(inPopNames) if outgroup else -1,
-                                          site_mask=mask)
-    write_spectra(args, FSpops, hists, firsts)
+        per = [eng.sfs_tables(kind, table, len(inPopNames), groups, outgroup=len(inPopNames) if outgroup else -1, site_mask=m)
+               for m in masks]
+    write_spectra(args, FSpops, *merge_intervals(per, len(FSpops)))
 
 
 def main(argv=None):
     args = build_parser().parse_args(argv)
-    if args.subsample or args.subsampleIndividuals:
-        raise NotImplementedError("--subsample draws with numpy's global RNG per site in the reference; not supported")
-    if args.regions or args.regionsFile:
-        raise NotImplementedError("--regions is not supported")
     assert (args.scafCol, args.posCol, args.firstSampleCol) == (0, 1, 2), "non-default column layout is not supported"
     if not args.polarized and args.outgroup is None and args.inputType != "targetCounts":
         sys.stderr.write("\nNo outgroup provided. Minor allele frequency will be used.\n")
@@ -227,14 +355,30 @@ def main(argv=None):
     if include or exclude:
         ok = np.array([(not include or n in include) and (n not in exclude) for n in gd.scaf_names], dtype=np.uint8)
         mask = ok[gd.scaf_ids]
+    intervals = read_intervals(args)
+    masks = interval_masks(intervals, np.asarray(gd.scaf_names, dtype=str)[gd.scaf_ids] if intervals else None, gd.pos, mask)
     with eng:
         C.ensure_resident(eng, gd)
         hp = C.hap_pop_vector(gd, enginePops, [popDict[pn] for pn in enginePops])
         eng.set_pops(hp, len(enginePops))
         sizes = [int((hp == x).sum()) for x in range(len(enginePops))]
         groups = [tuple(inPopNames.index(pn) for pn in grp) for grp in FSpops]
-        hists, firsts, _ = eng.sfs(len(inPopNames), groups, sizes, outgroup=len(inPopNames) if outgroup else -1, site_mask=mask)
-    write_spectra(args, FSpops, hists, firsts)
+        og = len(inPopNames) if outgroup else -1
+        sub = subsample_sizes(args, inPopNames)
+        if sub is None:
+            per = [eng.sfs(len(inPopNames), groups, sizes, outgroup=og, site_mask=m) for m in masks]
+        else:
+            for pn, n in zip(inPopNames, sub):                            # sfs.py:391-392
+                have = sizes[enginePops.index(pn)]
+                assert have >= n, "Population {} has fewer than {} haplotypes ({}).".format(pn, n, have)
+            # per-site counts from the device, the reference's random draw on them, target allele + histograms on the device;
+            # after a draw every in-group population holds exactly N alleles, which is the completeness test of sfs.py:453
+            counts = eng.site_counts()
+            table, went = downsample_counts(counts, sub, args.seed, considered_sites(masks, len(counts)))
+            assert table.max(initial=0) <= 65535
+            per = [eng.sfs_tables("base", table, len(inPopNames), groups, outgroup=og,
+                                  site_mask=went if m is None else (m & went)) for m in masks]
+    write_spectra(args, FSpops, *merge_intervals(per, len(FSpops)))
 
 
 if __name__ == "__main__":

@@ -173,3 +173,29 @@ class OracleEngine:
             hists.append(h)
             firsts.append(f)
         return hists, firsts, int(used.sum())
+
+    def sfs_tables(self, kind, table, n_in, groups, outgroup=-1, site_mask=None):
+        """same contract as Engine.sfs_tables: target allele of every row with the oracle, dense histograms + first rows"""
+        table = np.asarray(table)
+        n = table.shape[0]
+        if kind == "base":
+            tc, used = do.sfs_target_counts_from_counts(table, n_in, outgroup)
+            dims = table.sum(axis=2).max(axis=0) + 1 if n else np.ones(table.shape[1], dtype=np.int64)
+        else:
+            tc, used = table, np.ones(n, dtype=bool)
+            dims = table.max(axis=0) + 1 if n else np.ones(table.shape[1], dtype=np.int64)
+        if site_mask is not None:
+            used = used & np.asarray(site_mask, dtype=bool)
+        hists, firsts = [], []
+        for grp in groups:
+            shape = tuple(int(dims[x]) for x in grp)
+            h = np.zeros(shape, dtype=np.int64)
+            f = np.full(shape, -1, dtype=np.int64)
+            for s in np.where(used)[0]:
+                cell = tuple(int(tc[s, x]) for x in grp)
+                h[cell] += 1
+                if f[cell] < 0:
+                    f[cell] = s
+            hists.append(h)
+            firsts.append(f)
+        return hists, firsts, int(used.sum())
