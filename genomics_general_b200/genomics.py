@@ -99,6 +99,59 @@ class GenoWindow:
             self._sites = _decode_sites(self.geno, self.ploidy, self.genoFormat) if self.geno is not None else []
         return self._sites
 
+    def _cut(self, sl):
+        """keep the sites of a Python slice (positions, dense rows and the token cache stay aligned)"""
+        self.positions = self.positions[sl]
+        if self.geno is not None:
+            self.geno = self.geno[sl]
+        if self._sites is not None:
+            self._sites = self._sites[sl]
+
+    def addBlock(self, sites, positions):
+        """genomics.py:1745-1751"""
+        assert len(set([len(site) for site in sites])) == 1, "Number of genotypes per site must be equal."
+        assert len(sites[0]) == self.n, "Number of genotypes per site must match number of names."
+        assert len(positions) == len(sites), "Positions must match number of sites"
+        assert all(self.limits[0] <= p <= self.limits[1] for p in positions), "Position outside of window limit"
+        rows = _encode_sites(sites, self.ploidy, self.genoFormat)
+        self.geno = rows if self.geno is None or len(self.positions) == 0 else np.concatenate([self.geno, rows], axis=0)
+        if self._sites is not None:
+            self._sites = list(self._sites) + list(sites)
+        self.positions = list(self.positions) + list(positions)
+
+    def addSite(self, GTs, position=np.nan, ignorePosition=False):
+        """genomics.py:1753-1759"""
+        assert len(GTs) == self.n, "Number of genotypes per site must match number of names."
+        if not ignorePosition:
+            assert self.limits[0] <= position <= self.limits[1], "Position: " + str(position) + " outside of window limits: " + \
+                "-".join([str(l) for l in self.limits])
+        else:
+            position = np.nan
+        row = _encode_sites([GTs], self.ploidy, self.genoFormat)
+        self.geno = row if self.geno is None or len(self.positions) == 0 else np.concatenate([self.geno, row], axis=0)
+        if self._sites is not None:
+            self._sites = list(self._sites) + [GTs]
+        self.positions = list(self.positions) + [position]
+
+    def slide(self, step=None, newLimits=None):
+        """genomics.py:1767-1777: move the limits, drop the sites that now lie before the window"""
+        assert step is not None or newLimits is not None
+        if step:
+            self.limits = [l + step for l in self.limits]
+        else:
+            self.limits = newLimits
+        i, end = 0, len(self.positions)
+        while i < end and self.positions[i] < self.limits[0]:
+            i += 1
+        self._cut(slice(i, None))
+
+    def trim(self, right=False, remove=None, leave=None):
+        """genomics.py:1779-1788 (with its slices: `right=True, remove=0` empties the window, [:-0])"""
+        assert remove is not None or leave is not None
+        if not remove:
+            remove = self.seqLen() - leave
+        self._cut(slice(remove, None) if not right else slice(None, -remove))
+
     def seqLen(self):
         return len(self.positions)
 

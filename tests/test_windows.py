@@ -127,3 +127,38 @@ def test_mid_pos_matches_python_round():
     assert W.mid_pos(5, 2) == 2          # 2.5 -> 2 (banker's)
     assert W.mid_pos(7, 2) == 4          # 3.5 -> 4
     assert math.isnan(W.mid_pos(0, 0))
+
+
+def test_geno_window_mutators_follow_the_reference_container():
+    """GenoWindow.addSite / addBlock / slide / trim (genomics.py:1745-1788) on the dense-backed mirror: positions, token
+    rows and the int8 matrix stay aligned; the expected states are the reference container's (the same calls on
+    /root/reference/genomics.GenoWindow give these lists — the `[:-0]` slice of trim included; the reference's own
+    addBlock cannot run: its chained comparison of a list / array of positions raises, genomics.py:1749)."""
+    from genomics_general_b200 import genomics as G
+    w = G.GenoWindow(scaffold="chr1", limits=[1, 100], names=["a", "b"], ploidy=[2, 2])
+    w.addSite(["A/T", "N/N"], 5)
+    w.addSite(["C/C", "G/T"], 17)
+    w.addBlock([["A/A", "A/A"], ["T/T", "N/G"], ["G/G", "C/C"]], [30, 42, 88])
+    assert w.seqLen() == 5 and w.firstPos() == 5 and w.lastPos() == 88 and w.midPos() == 36
+    assert w.geno.tolist() == [[0, 3, -1, -1], [1, 1, 2, 3], [0, 0, 0, 0], [3, 3, -1, 2], [2, 2, 1, 1]]
+    assert w.seqDict()["b"] == ["N/N", "G/T", "A/A", "N/G", "C/C"]
+    with pytest.raises(AssertionError):
+        w.addSite(["A/A", "A/A"], 101)
+    with pytest.raises(AssertionError):
+        w.addSite(["A/A"], 50)
+    w.addSite(["T/T", "T/T"], ignorePosition=True)
+    assert np.isnan(w.positions[-1]) and w.seqLen() == 6
+    w.trim(right=True, remove=1)
+    w.slide(step=15)                                    # limits 16..115: the site at 5 leaves
+    assert w.limits == [16, 115] and w.positions == [17, 30, 42, 88]
+    assert w.geno.tolist() == [[1, 1, 2, 3], [0, 0, 0, 0], [3, 3, -1, 2], [2, 2, 1, 1]]
+    w.slide(newLimits=[31, 60])
+    assert w.positions == [42, 88]                      # only the left edge drops sites (1773-1777)
+    w.trim(leave=1)
+    assert w.positions == [88] and w.sites == [["G/G", "C/C"]] and w.geno.tolist() == [[2, 2, 1, 1]]
+    c = w.copy()
+    c.trim(right=True, leave=1)                         # nothing to remove -> the reference's slice [:-0] empties the window
+    assert c.positions == [] and c.seqLen() == 0 and c.geno.shape == (0, 4)
+    assert w.positions == [88]
+    with pytest.raises(TypeError):
+        w.trim(right=True, remove=0)                    # seqLen() - None, as in the reference
