@@ -483,7 +483,7 @@ struct GramItem {
 };
 template <int NPL, int CH>
 __device__ __forceinline__ GramItem gram_item(const GramParams& gp, int64_t j) {
-    constexpr int SH = 6 + (CH == 2 ? 1 : 0);           // a stage covers CH chunks of 64 (pseudo-)sites
+    constexpr int SH = 6 + (CH == 4 ? 2 : (CH == 2 ? 1 : 0));   // a stage covers CH chunks of 64 (pseudo-)sites
     GramItem it;
     it.wb = (int)(j / gp.ngroups);
     it.g = gp.groups[j - (int64_t)it.wb * gp.ngroups];
@@ -501,10 +501,10 @@ __device__ __forceinline__ GramItem gram_item(const GramParams& gp, int64_t j) {
 // Shared memory: [raw ring: nraw slots of NPL x RROWS plane words, filled by 1-D TMA bulk copies]
 //                [operand ring: nstages stages of 2 K steps x NPL planes x RROWS rows x 32 bytes] [+ slack]
 // RROWS = (128 rows of a separate A tile, only when some group needs one) + nbmax rows of the B range.
-// CH = chunks per stage (1 or 2): with 2, every per-stage hand-over (TMA wait, proxy fence, MMA issue, commit) serves 128 sites.
+// CH = chunks per stage (1, 2 or 4): every per-stage hand-over (TMA wait, proxy fence, MMA issue, commit) serves CH x 64 sites.
 template <int NPL, int GW, int EW, int CH = 1>
 __global__ void __launch_bounds__(gram_threads(GW, EW), 1) k2t_gram(const __grid_constant__ GramParams gp) {
-    static_assert(CH == 1 || CH == 2, "chunks per stage");
+    static_assert(CH == 1 || CH == 2 || CH == 4, "chunks per stage");
     constexpr int GRAM_XWARPS = GW * GRAM_XGROUPS, GTHREADS = GW * 32;
     constexpr int GRAM_WARP_MMA = GRAM_XWARPS, GRAM_WARP_TMA = GRAM_XWARPS + 1, GRAM_WARP_EPI = GRAM_WARP_TMA + GRAM_XGROUPS;
     constexpr int GRAM_EPI_WARPS = EW;
@@ -1069,6 +1069,7 @@ int pg_k2t_pairs(pg_ctx* ctx, const K2TPlanes& ps, const int64_t* d_lo, const in
         PG_CUDA(cudaFuncSetAttribute(k2t_gram<1, 8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
         PG_CUDA(cudaFuncSetAttribute(k2t_gram<2, 8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
         PG_CUDA(cudaFuncSetAttribute(k2t_gram<1, 8, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+        PG_CUDA(cudaFuncSetAttribute(k2t_gram<1, 8, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
         attr_dev[ctx->device & 63] = true;
     }
     // expanding groups of 8 warps + 4 epilogue warps (30 warps) or 4 + 8 (22 warps): PG_K2T_GW = 4 | 8, per kernel
@@ -1125,12 +1126,18 @@ int pg_k2t_pairs(pg_ctx* ctx, const K2TPlanes& ps, const int64_t* d_lo, const in
         gp.ngroups = (int)gn.size();
         gp.nbmax = nbmax_n;
         gp.a_sep = asep_n;
-        // 128-site stages where at least three of them fit (PG_K2T_CH=2; every site counts for n_ij, so its K is the long one)
-        int ch_n = (getenv("PG_K2T_CH") && atoi(getenv("PG_K2T_CH")) == 2 && wide_n) ? 2 : 1;
+        // 128-site stages where at least three of them fit (every site counts for n_ij, so its K is the long one and the
+        // per-stage hand-overs — TMA wait, proxy fence, MMA issue, commit — are what paces the kernel: 0.70 -> 0.56 ms on the
+        // C2 shape, bit-identical sums).  PG_K2T_CH = 1 | 2 | 4 overrides (4: 256-site stages, experimental).
+        int ch_n = wide_n ? 2 : 1;
+        if (const char* e = getenv("PG_K2T_CH")) {
+            const int v = atoi(e);
+            ch_n = (v == 4 && wide_n) ? 4 : ((v == 2 && wide_n) ? 2 : 1);
+        }
         size_t smem = geometry(1, nbmax_n, asep_n, gp.nstages, gp.nraw, gp.xg, ch_n);
-        if (ch_n == 2 && gp.nstages < 3) {
-            ch_n = 1;
-            smem = geometry(1, nbmax_n, asep_n, gp.nstages, gp.nraw, gp.xg, 1);
+        while (ch_n > 1 && gp.nstages < 3) {
+            ch_n /= 2;
+            smem = geometry(1, nbmax_n, asep_n, gp.nstages, gp.nraw, gp.xg, ch_n);
         }
         gp.plane = ps.vpair ? ps.vpair : ps.vplane;
         gp.nchunks = ps.nchunk_v;
@@ -1138,7 +1145,8 @@ int pg_k2t_pairs(pg_ctx* ctx, const K2TPlanes& ps, const int64_t* d_lo, const in
         gp.out = d_n;
         const unsigned grid = (unsigned)std::min<int64_t>((int64_t)nb * gp.ngroups, ctx->sm_count);
         const int ti = pg_time_begin(ctx, "k2t_gram_n");
-        if (ch_n == 2) k2t_gram<1, 8, 4, 2><<<grid, gram_threads(8, 4), smem, ctx->stream>>>(gp);
+        if (ch_n == 4) k2t_gram<1, 8, 4, 4><<<grid, gram_threads(8, 4), smem, ctx->stream>>>(gp);
+        else if (ch_n == 2) k2t_gram<1, 8, 4, 2><<<grid, gram_threads(8, 4), smem, ctx->stream>>>(gp);
         else if (wide_n) k2t_gram<1, 8, 4><<<grid, gram_threads(8, 4), smem, ctx->stream>>>(gp);
         else k2t_gram<1, 4, 8><<<grid, gram_threads(4, 8), smem, ctx->stream>>>(gp);
         pg_time_end(ctx, ti);
@@ -1151,6 +1159,7 @@ int pg_k2t_pairs(pg_ctx* ctx, const K2TPlanes& ps, const int64_t* d_lo, const in
         gp.ngroups = (int)gd.size();
         gp.nbmax = nbmax_d;
         gp.a_sep = asep_d;
+        // (128-pseudo-site stages do not fit here: two planes per stage, 3 x 102 KB for 400 rows)
         const size_t smem = geometry(2, nbmax_d, asep_d, gp.nstages, gp.nraw, gp.xg);
         gp.plane = ps.pq;
         gp.nchunks = (ps.npseudo + 63) / 64;
