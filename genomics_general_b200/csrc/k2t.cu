@@ -1126,10 +1126,10 @@ int pg_k2t_pairs(pg_ctx* ctx, const K2TPlanes& ps, const int64_t* d_lo, const in
         gp.ngroups = (int)gn.size();
         gp.nbmax = nbmax_n;
         gp.a_sep = asep_n;
-        // 128-site stages where at least three of them fit (every site counts for n_ij, so its K is the long one and the
-        // per-stage hand-overs — TMA wait, proxy fence, MMA issue, commit — are what paces the kernel: 0.70 -> 0.56 ms on the
-        // C2 shape, bit-identical sums).  PG_K2T_CH = 1 | 2 | 4 overrides (4: 256-site stages, experimental).
-        int ch_n = wide_n ? 2 : 1;
+        // 256-site stages (128 / 64 where three of the larger ones do not fit): every site counts for n_ij, so its K is the
+        // long one and the per-stage hand-overs — TMA wait, proxy fence, MMA issue, commit — are what paces the kernel:
+        // 0.70 (64) -> 0.55 (128) -> 0.50 ms (256 sites per stage) on the C2 shape, bit-identical sums.  PG_K2T_CH = 1 | 2 | 4.
+        int ch_n = wide_n ? 4 : 1;
         if (const char* e = getenv("PG_K2T_CH")) {
             const int v = atoi(e);
             ch_n = (v == 4 && wide_n) ? 4 : ((v == 2 && wide_n) ? 2 : 1);
