@@ -24,7 +24,8 @@ namespace {
 // consumer warps per CTA (+ one TMA producer warp): 8, or 12 where the register budget allows (65536 / 13 / 32 = 157)
 constexpr int K1_MAX_WARPS = 12;
 
-enum { MODE_POPGEN = 0, MODE_ABBA = 1, MODE_COUNTS = 2, MODE_POPGEN_FREQ = 3, MODE_FOURPOP = 4 };   // FREQ = POPGEN + popFreq counters
+enum { MODE_POPGEN = 0, MODE_ABBA = 1, MODE_COUNTS = 2, MODE_POPGEN_FREQ = 3, MODE_FOURPOP = 4,   // FREQ = POPGEN + popFreq counters
+       MODE_FOURPOP_Q = 5 };   // FOURPOP with the informative sites of a warp queued and evaluated 32 at a time (site pass only)
 
 struct K1Params {
     const uint8_t* geno;
@@ -232,6 +233,10 @@ template <int P>
 struct ModeTraits<MODE_FOURPOP, P> {
     static constexpr int QI = 3, QU = 0, QD = 16;
 };
+template <int P>
+struct ModeTraits<MODE_FOURPOP_Q, P> {
+    static constexpr int QI = 3, QU = 0, QD = 16;
+};
 
 // genomics.py:1409-1418, operation order of the reference's numpy expressions
 __device__ __forceinline__ double f4_dev(double p1, double p2, double p3, double p4) {
@@ -242,6 +247,49 @@ __device__ __forceinline__ double f4c_dev(double p1, double p2, double p3, doubl
 }
 // np.amax propagates nan
 __device__ __forceinline__ double nmax(double a, double b) { return (a != a) ? a : ((b != b) ? b : (a > b ? a : b)); }
+
+// The 16 running sums of genomics.fourPop (genomics.py:1617-1643) for one informative site: counts of the chosen allele
+// k_X and non-missing haplotypes n_X of P1..P4, packed as k | n << 16.
+template <class ACC>
+__device__ __forceinline__ void fourpop_add(ACC& acc, uint32_t e1, uint32_t e2, uint32_t e3, uint32_t e4) {
+    const double p1 = (double)(e1 & 0xffffu) / (double)(e1 >> 16);      // 0/0 = nan, as in the reference (genomics.py:597)
+    const double p2 = (double)(e2 & 0xffffu) / (double)(e2 >> 16);
+    const double p3 = (double)(e3 & 0xffffu) / (double)(e3 >> 16);
+    const double p4 = (double)(e4 & 0xffffu) / (double)(e4 >> 16);
+    const double abba = (1 - p1) * p2 * p3 * (1 - p4);
+    const double baba = p1 * (1 - p2) * p3 * (1 - p4);
+    const double pd = p2 * (p2 > p3 ? 1.0 : 0.0) + p3 * (p3 >= p2 ? 1.0 : 0.0);
+    const bool A = p3 > p1, Bq = p3 > p2, Xq = p1 > p2, Yq = !Xq;
+    const double xa = (Xq && A) ? 1.0 : 0.0, yb = (Yq && Bq) ? 1.0 : 0.0;
+    const double xna = (Xq && !A) ? 1.0 : 0.0, ynb = (Yq && !Bq) ? 1.0 : 0.0;
+    const double pdm1 = p3 * xa + p1 * (1.0 - xa);
+    const double pdm2 = p3 * yb + p2 * (1.0 - yb);
+    const double pdm3 = -p3 * xa + p3 * yb - p1 * xna + p2 * ynb;
+    const double t11 = f4c_dev(p1, p3, p3, p4), t12 = f4c_dev(p4, p2, p3, p4);
+    const double t21 = f4c_dev(p3, p2, p3, p4), t22 = f4c_dev(p1, p4, p3, p4);
+    const double t31 = f4c_dev(p1, p2, p2, p4), t32 = f4c_dev(p1, p2, p3, p1);
+    const double t41 = f4c_dev(p1, p2, p1, p4), t42 = f4c_dev(p1, p2, p3, p2);
+    const double m4 = nmax(nmax(t11, t12), nmax(t21, t22));
+    const double m8 = nmax(nmax(m4, nmax(t31, t32)), nmax(t41, t42));
+    const double u1 = fabs(p1 - p2), u2 = fabs(p3 - p4);
+    const double um = u1 * (u1 > u2 ? 1.0 : 0.0) + u2 * (u2 >= u1 ? 1.0 : 0.0);
+    acc.d[0] += f4_dev(p1, p2, p3, p4);
+    acc.d[1] += f4_dev(p1, p3, p3, p4);
+    acc.d[2] += f4c_dev(p1, p2, p3, p4);
+    acc.d[3] += t11;
+    acc.d[4] += abba + baba;
+    acc.d[5] += f4_dev(p1, pd, pd, p4);
+    acc.d[6] += f4c_dev(p1, pd, pd, p4);
+    acc.d[7] += f4_dev(pdm1, pdm2, pdm3, p4);
+    acc.d[8] += f4c_dev(pdm1, pdm2, pdm3, p4);
+    acc.d[9] += m4;
+    acc.d[10] += m8;
+    acc.d[11] += um * um;
+    acc.d[12] += abba;
+    acc.d[13] += baba;
+    acc.d[14] += (1 - p1) * p2 * (1 - p3) * (1 - p4);
+    acc.d[15] += p1 * (1 - p2) * (1 - p3) * (1 - p4);
+}
 
 // TMA producer (one elected lane of the producer warp): keeps the ring of tiles full.
 template <int MODE>
@@ -331,6 +379,11 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k1_site_pass(const __grid_co
     int64_t seg_end = -1;
     const int seg_first = (MODE == MODE_COUNTS) ? 0 : prm.cta_seg_first[b];
     const int64_t slot_base = (MODE == MODE_COUNTS) ? 0 : prm.cta_slot_off[b];
+    // MODE_FOURPOP_Q: one queued informative site per lane (k | n << 16 of P1..P4).  Sites are queued only while every lane
+    // of the warp is in the same segment, and the queue is emptied before any lane changes segment, so whichever lane
+    // evaluates a queued site adds it to the sums of the right segment.
+    uint32_t q1 = 0u, q2 = 0u, q3 = 0u, q4 = 0u;
+    bool qpend = false;
 
     for (int it = team; it < ntiles; it += nteams) {
         const int stage = it % prm.stages;
@@ -411,6 +464,10 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k1_site_pass(const __grid_co
             int sg = cur_seg;
             if (owner && site >= seg_end) sg = find_seg(prm.brk, prm.nseg, cur_seg + 1, site);
             if (__any_sync(0xffffffffu, sg != cur_seg)) {
+                if (MODE == MODE_FOURPOP_Q) {
+                    if (qpend) fourpop_add(acc, q1, q2, q3, q4);
+                    qpend = false;
+                }
                 warp_flush<QI, QU, QD>(acc, cur_seg, prm.part, slot_base, seg_first, warp, lane, NW);
                 since_flush = 0;
                 if (sg != cur_seg) {
@@ -530,7 +587,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k1_site_pass(const __grid_co
                 }
             }
 
-            if (MODE == MODE_FOURPOP) {
+            if (MODE == MODE_FOURPOP || MODE == MODE_FOURPOP_Q) {
                 // genomics.py:1595-1603: biallelic over P1+P2+P3+P4 and enough data in each population
                 uint32_t tot[4];
                 int nall = 0;
@@ -570,45 +627,46 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k1_site_pass(const __grid_co
                 if (prm.variant == 2)       // fixed (1611-1614): frequency exactly 0 or 1 in P1, P2, P3 (nan fails both)
                     hit = hit && n[0] > 0 && n[1] > 0 && n[2] > 0 && (k1 == 0 || k1 == n[0]) && (k2 == 0 || k2 == n[1]) &&
                           (k3 == 0 || k3 == n[2]);
-                if (hit) {
-                    const double p1 = (double)k1 / (double)n[0];      // 0/0 = nan, as in the reference (genomics.py:597)
-                    const double p2 = (double)k2 / (double)n[1];
-                    const double p3 = (double)k3 / (double)n[2];
-                    const double p4 = (double)k4 / (double)n[3];
-                    const double abba = (1 - p1) * p2 * p3 * (1 - p4);
-                    const double baba = p1 * (1 - p2) * p3 * (1 - p4);
-                    const double pd = p2 * (p2 > p3 ? 1.0 : 0.0) + p3 * (p3 >= p2 ? 1.0 : 0.0);
-                    const bool A = p3 > p1, Bq = p3 > p2, Xq = p1 > p2, Yq = !Xq;
-                    const double xa = (Xq && A) ? 1.0 : 0.0, yb = (Yq && Bq) ? 1.0 : 0.0;
-                    const double xna = (Xq && !A) ? 1.0 : 0.0, ynb = (Yq && !Bq) ? 1.0 : 0.0;
-                    const double pdm1 = p3 * xa + p1 * (1.0 - xa);
-                    const double pdm2 = p3 * yb + p2 * (1.0 - yb);
-                    const double pdm3 = -p3 * xa + p3 * yb - p1 * xna + p2 * ynb;
-                    const double t11 = f4c_dev(p1, p3, p3, p4), t12 = f4c_dev(p4, p2, p3, p4);
-                    const double t21 = f4c_dev(p3, p2, p3, p4), t22 = f4c_dev(p1, p4, p3, p4);
-                    const double t31 = f4c_dev(p1, p2, p2, p4), t32 = f4c_dev(p1, p2, p3, p1);
-                    const double t41 = f4c_dev(p1, p2, p1, p4), t42 = f4c_dev(p1, p2, p3, p2);
-                    const double m4 = nmax(nmax(t11, t12), nmax(t21, t22));
-                    const double m8 = nmax(nmax(m4, nmax(t31, t32)), nmax(t41, t42));
-                    const double u1 = fabs(p1 - p2), u2 = fabs(p3 - p4);
-                    const double um = u1 * (u1 > u2 ? 1.0 : 0.0) + u2 * (u2 >= u1 ? 1.0 : 0.0);
-                    acc.i[0] += 1;
-                    acc.d[0] += f4_dev(p1, p2, p3, p4);
-                    acc.d[1] += f4_dev(p1, p3, p3, p4);
-                    acc.d[2] += f4c_dev(p1, p2, p3, p4);
-                    acc.d[3] += t11;
-                    acc.d[4] += abba + baba;
-                    acc.d[5] += f4_dev(p1, pd, pd, p4);
-                    acc.d[6] += f4c_dev(p1, pd, pd, p4);
-                    acc.d[7] += f4_dev(pdm1, pdm2, pdm3, p4);
-                    acc.d[8] += f4c_dev(pdm1, pdm2, pdm3, p4);
-                    acc.d[9] += m4;
-                    acc.d[10] += m8;
-                    acc.d[11] += um * um;
-                    acc.d[12] += abba;
-                    acc.d[13] += baba;
-                    acc.d[14] += (1 - p1) * p2 * (1 - p3) * (1 - p4);
-                    acc.d[15] += p1 * (1 - p2) * (1 - p3) * (1 - p4);
+                const uint32_t e1 = k1 | (n[0] << 16), e2 = k2 | (n[1] << 16), e3 = k3 | (n[2] << 16), e4 = k4 | (n[3] << 16);
+                acc.i[0] += hit ? 1 : 0;
+                if (MODE == MODE_FOURPOP) {
+                    if (hit) fourpop_add(acc, e1, e2, e3, e4);
+                } else {
+                    // About a third of the lanes hold an informative site, and the ~1000 instructions of the evaluation
+                    // ran for the whole warp whenever one did.  Here the informative sites move into free queue slots of
+                    // the warp (one per lane) and are evaluated when the next ones no longer fit, i.e. with (nearly) all
+                    // 32 lanes at work.
+                    const unsigned full_m = 0xffffffffu;
+                    const int seg0 = __shfl_sync(full_m, cur_seg, 0);
+                    if (!__all_sync(full_m, cur_seg == seg0)) {
+                        // lanes in two segments (the iteration that crosses a window boundary, the tail of the data): the
+                        // queue is empty — a segment change empties it — and every lane evaluates its own site
+                        if (hit) fourpop_add(acc, e1, e2, e3, e4);
+                    } else {
+                        const unsigned hits = __ballot_sync(full_m, hit);
+                        if (hits) {
+                            unsigned pm = __ballot_sync(full_m, qpend);
+                            const int nh = __popc(hits);
+                            if (nh > 32 - __popc(pm)) {         // no room for the new sites: evaluate the queued ones
+                                if (qpend) fourpop_add(acc, q1, q2, q3, q4);
+                                qpend = false;
+                                pm = 0u;
+                            }
+                            const unsigned fr = ~pm;
+                            const int r = __popc(fr & ((1u << lane) - 1u));          // rank of this lane among the free ones
+                            const bool take = ((fr >> lane) & 1u) && r < nh;
+                            const int src = take ? (int)__fns(hits, 0, r + 1) : lane;  // lane of the (r+1)-th new site
+                            const uint32_t t1 = __shfl_sync(full_m, e1, src), t2 = __shfl_sync(full_m, e2, src);
+                            const uint32_t t3 = __shfl_sync(full_m, e3, src), t4 = __shfl_sync(full_m, e4, src);
+                            if (take) {
+                                q1 = t1;
+                                q2 = t2;
+                                q3 = t3;
+                                q4 = t4;
+                                qpend = true;
+                            }
+                        }
+                    }
                 }
             }
         }
@@ -616,6 +674,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k1_site_pass(const __grid_co
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[stage]);   // this warp is done with the stage's bytes
     }
+    if (MODE == MODE_FOURPOP_Q && qpend) fourpop_add(acc, q1, q2, q3, q4);
     if (MODE != MODE_COUNTS) warp_flush<QI, QU, QD>(acc, cur_seg, prm.part, slot_base, seg_first, warp, lane, NW);
 }
 
@@ -1745,7 +1804,8 @@ int pg_fourpop_enqueue(pg_ctx* ctx, const int* sel, double min_data, int mode, v
     }
     c.L.prm.variant = mode;
     PG_TRY(arm_slots(ctx, c));
-    PG_TRY((launch_site_pass<MODE_FOURPOP, 4>(ctx, c.L, "k1_fourpop")));
+    if (getenv("PG_K1_FOURPOP_QUEUE")) PG_TRY((launch_site_pass<MODE_FOURPOP_Q, 4>(ctx, c.L, "k1_fourpop")));
+    else PG_TRY((launch_site_pass<MODE_FOURPOP, 4>(ctx, c.L, "k1_fourpop")));
     FinParams fp;
     fill_fin(fp, ctx, c, Q, 3);
     fp.P = 4;
