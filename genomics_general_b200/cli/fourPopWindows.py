@@ -4,11 +4,12 @@
 from __future__ import annotations
 
 import argparse
+import os
 import sys
 
 import numpy as np
 
-from .. import genomics
+from .. import genomics, mgpu, multigpu
 from ..engine import Engine
 from . import _common as C
 
@@ -52,19 +53,42 @@ def main(argv=None):
     allInds = sorted(set(i for p in popInds for i in p))
     ploidyDict = C.ploidy_dict(args, allInds, args.haploid.split(",") if args.haploid else None)
     sampleData = genomics.SampleData(indNames=allInds, popNames=popNames, popInds=popInds, ploidyDict=ploidyDict)
-    out = C.open_out(args.outFile)
+    # --devices N: this process becomes rank 0 of N (fourPopWindows.py:253-330's worker pool, one process per GPU here)
+    rdv = mgpu.init("genomics_general_b200.cli.fourPopWindows", argv, args.devices)
+    out = C.open_out(args.outFile) if (rdv is None or rdv.rank == 0) else open(os.devnull, "wt")
     out.write(",".join((["windowID"] if args.addWindowID else []) + ["scaffold", "start", "end", "mid", "sites", "sitesUsed"]
                        + STATS) + "\n")
-    eng = Engine(args.device)
-    gd = C.load_geno(args, sampleData.indNames, ploidyDict, header=args.header, engine=eng)
+    eng = Engine(args.device if rdv is None else mgpu.device_for(rdv, args.device))
+    if rdv is None:
+        gd = C.load_geno(args, sampleData.indNames, ploidyDict, header=args.header, engine=eng)
+    else:
+        gd, starts, off_all = mgpu.sharded_ingest(eng, rdv, args.genoFile, args.genoFormat, sampleData.indNames, ploidyDict,
+                                                  args.header)
     ws = C.make_windows(args, gd, minSites, coords, C.read_scaffold_list(args.include), C.read_scaffold_list(args.exclude))
     lo, hi = ws.ranges()
     written = 0
     with eng:
-        C.ensure_resident(eng, gd)
-        eng.set_windows(lo, hi)
-        eng.set_pops(C.hap_pop_vector(gd, popNames, popInds), 4)
-        r = eng.fourpop(0, 1, 2, 3, args.minData, polarize=args.polarize, fixed=args.fixed)
+        if rdv is None:
+            C.ensure_resident(eng, gd)
+            eng.set_windows(lo, hi)
+            eng.set_pops(C.hap_pop_vector(gd, popNames, popInds), 4)
+            r = eng.fourpop(0, 1, 2, 3, args.minData, polarize=args.polarize, fixed=args.fixed)
+        else:
+            idx, llo, lhi, halo = mgpu.assign_windows(lo, hi, starts, rdv.rank)
+            mgpu.fetch_halo(eng, args.genoFile, gd, starts, off_all, rdv.rank, halo, args.genoFormat, ploidyDict)
+            eng.set_windows(llo, lhi)
+            eng.set_pops(C.hap_pop_vector(gd, popNames, popInds), 4)
+            w_max, row_of = mgpu.gathered_order([mgpu.assign_windows(lo, hi, starts, q)[0] for q in range(rdv.world)])
+            mgpu.nccl_connect(eng, rdv)
+            table = np.zeros((rdv.world * w_max, 17), dtype=np.float64)
+            eng.fourpop_allgather(0, 1, 2, 3, args.minData, w_max, table, polarize=args.polarize,
+                                  fixed=args.fixed)                             # ONE ncclAllGather of the records
+            eng.nccl_finalize()
+            rows = np.array([row_of[w] for w in range(len(ws))], dtype=np.int64)
+            r = multigpu.unpack_fourpop_records(table[rows] if len(rows) else table[:0])
+            if rdv.rank != 0:
+                rdv.finish()
+                return
     for k in range(len(ws)):
         pre = C.window_prefix(args, ws, k, gd, r["sites"][k], r["pos_sum"][k])
         sitesUsed = np.nan
@@ -81,6 +105,8 @@ def main(argv=None):
             written += 1
     if out is not sys.stdout:
         out.close()
+    if rdv is not None:
+        rdv.finish()
     sys.stderr.write("%d windows were tested.\n%d results were written.\n" % (len(ws), written))
 
 

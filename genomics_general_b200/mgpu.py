@@ -81,9 +81,16 @@ class Rendezvous:
             self.get_bytes("bar_" + name, r)
 
     def finish(self):
-        """rank 0: wait for the children, remove the directory"""
+        """rank 0: wait for the other ranks, remove the directory.  A rank writes a last file once it has passed the
+        barrier, i.e. needs nothing more from the directory; rank 0 removes the files only after it has seen all of them —
+        under torchrun the other ranks are not its children, and deleting right after its own barrier would leave a rank
+        that is still polling for the barrier files waiting forever."""
         self.barrier("done")
+        self.put_bytes("bye", b"1")
         rc = 0
+        if self.rank == 0:
+            for r in range(self.world):
+                self.get_bytes("bye", r)
         for c in self.children:
             rc = rc or c.wait()
         if self.rank == 0:

@@ -56,7 +56,7 @@ def _write_inputs(tmp_path, miss, scaffolds=3):
 
 @pytest.mark.parametrize("miss", [0.0, 0.03])
 def test_command_lines_on_two_devices_equal_one_device(tmp_path, miss):
-    """popgenWindows / ABBABABAwindows / freq with --devices 2 (each rank tokenises its byte range of the file, windows that
+    """popgenWindows / ABBABABAwindows / fourPopWindows / freq with --devices 2 (each rank tokenises its byte range of the file, windows that
     straddle the cut fetch their halo sites, one NCCL all-gather, rank 0 writes) == the single-device output, byte for byte"""
     if not _two_gpus():
         pytest.skip("needs 2 GPUs")
@@ -67,6 +67,8 @@ def test_command_lines_on_two_devices_equal_one_device(tmp_path, miss):
             ("popgenWindows", ["--windType", "sites", "-w", "900", "-O", "300", "-m", "100", "-f", "phased", "--roundTo", "10"] + pp),
             ("ABBABABAwindows", ["-w", "7000", "-m", "50", "-f", "phased", "--minData", "0.5", "--popsFile", pops, "-P1", "pop0",
                                  "-P2", "pop1", "-P3", "pop2", "-O", "pop3", "--writeFailedWindows"]),
+            ("fourPopWindows", ["-w", "7000", "-m", "50", "-f", "phased", "--minData", "0.5", "--popsFile", pops, "-P1", "pop0",
+                                "-P2", "pop1", "-P3", "pop2", "-O", "pop3", "--polarize", "--writeFailedWindows"]),
             ("freq", ["-f", "phased"] + pp)]
     for mod, argv in runs:
         outs = []
@@ -77,7 +79,7 @@ def test_command_lines_on_two_devices_equal_one_device(tmp_path, miss):
             assert r.returncode == 0, r.stdout[-3000:]
             outs.append(open(o).read())
         assert outs[0].count("\n") > 3
-        if mod == "ABBABABAwindows":        # fp64 sums of a window differ in the last bits when a rank tiles its sites differently
+        if mod in ("ABBABABAwindows", "fourPopWindows"):        # fp64 sums of a window differ in the last bits when a rank tiles its sites differently
             a, b = outs[0].strip().split("\n"), outs[1].strip().split("\n")
             assert len(a) == len(b) and a[0] == b[0]
             for x, y in zip(a[1:], b[1:]):

@@ -49,3 +49,83 @@ def test_rendezvous_between_processes(tmp_path):
     for p in procs:
         out, _ = p.communicate(timeout=120)
         assert p.returncode == 0 and "ok" in out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The complete `--devices N` command lines on the CPU: N rank processes (tests/_mgpu_cpu_worker.py) whose engine is the
+# oracle-backed stand-in (tests/oracle_engine_mg.py: host tokenizer for the rank's byte range, the all-gather through
+# files), everything else — byte ranges, the global picture, window ownership, halo sites, the gathered table's order,
+# rank 0 writing — the product's own multi-GPU path.  The output must equal the single-device command line's.
+# ------------------------------------------------------------------------------------------------------------------
+import pytest  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def mg_input(tmp_path_factory):
+    from genomics_general_b200 import synth
+    d = tmp_path_factory.mktemp("mg_cpu")
+    spec = synth.SynthSpec(4, 3, seed=77, miss=0.03)
+    S = 3600
+    g = synth.synth_genotypes(spec, 0, S)
+    scafs = ["chr1"] * 1500 + ["chr2"] * 900 + ["chr3"] * 1200
+    pos = np.concatenate([synth.synth_positions(n, seed=77 + k) for k, n in enumerate((1500, 900, 1200))])
+    geno = str(d / "mg.geno")
+    synth.write_geno(geno, g, pos, scafs, spec.sample_names())
+    pops = str(d / "mg.pops")
+    with open(pops, "wt") as f:
+        for i, n in enumerate(spec.sample_names()):
+            f.write("%s pop%d\n" % (n, i // 3))
+    return dict(geno=geno, pops=pops, dir=str(d))
+
+
+def _single_device(module, argv, monkeypatch):
+    import importlib
+    from oracle_engine import OracleEngine
+    from genomics_general_b200.cli import _common
+    mod = importlib.import_module("genomics_general_b200.cli." + module)
+    monkeypatch.setattr(mod, "Engine", OracleEngine)
+    real = _common.load_geno
+    monkeypatch.setattr(_common, "load_geno", lambda args, samples, pl, header=None, engine=None: real(args, samples, pl, header, None))
+    mod.main(argv)
+
+
+def _ranks(module, argv, world, rdv_dir):
+    os.makedirs(rdv_dir, exist_ok=True)
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, PG_MG_RANK=str(r), PG_MG_WORLD=str(world), PG_MG_DIR=rdv_dir, OMP_NUM_THREADS="1")
+        procs.append(subprocess.Popen([sys.executable, os.path.join(HERE, "_mgpu_cpu_worker.py"), module] + argv, env=env,
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        out, _ = p.communicate(timeout=240)
+        assert p.returncode == 0, out[-3000:]
+
+
+POPS4 = ["-p", "pop0", "-p", "pop1", "-p", "pop2", "-p", "pop3"]
+P4 = ["-P1", "pop0", "-P2", "pop1", "-P3", "pop2", "-O", "pop3"]
+MG_CASES = {
+    "popgen_coordinate": ("popgenWindows", ["-w", "9000", "-m", "50", "-f", "phased", "--roundTo", "9"] + POPS4),
+    "popgen_sites_overlap": ("popgenWindows", ["--windType", "sites", "-w", "400", "-O", "150", "-m", "100", "-f", "phased",
+                                               "--writeFailedWindows", "--addWindowID"] + POPS4),
+    "abba_coordinate": ("ABBABABAwindows", ["-w", "12000", "-m", "30", "-f", "phased", "--minData", "0.5"] + P4),
+    "fourpop_sites": ("fourPopWindows", ["--windType", "sites", "-w", "500", "--overlap", "100", "-m", "30", "-f", "phased",
+                                         "--minData", "0.5", "--polarize"] + P4),
+    "freq_counts": ("freq", ["-f", "phased"] + POPS4),
+    "freq_target": ("freq", ["-f", "phased", "--target", "derived", "--minData", "0.5"] + POPS4),
+}
+
+
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("case", list(MG_CASES))
+def test_command_lines_on_n_ranks_equal_one_device_cpu(mg_input, case, world, monkeypatch, tmp_path):
+    module, argv = MG_CASES[case]
+    base = argv + ["-g", mg_input["geno"], "--popsFile", mg_input["pops"]]
+    one = str(tmp_path / "one.txt")
+    _single_device(module, base + ["-o", one], monkeypatch)
+    many = str(tmp_path / "many.txt")
+    _ranks(module, base + ["-o", many], world, str(tmp_path / "rdv"))
+    a, b = open(one).read(), open(many).read()
+    assert len(a.splitlines()) > 3
+    assert a == b
