@@ -45,6 +45,16 @@ class PinnedArray:
             pass
 
 
+SFS_MAX_CELLS = 1 << 28      # dense histograms of pg_sfs / pg_sfs_tables (k1.cu); the reference's sparse dicts have no such limit
+
+
+def _check_sfs_cells(cells):
+    """refuse before 16 bytes per cell are allocated on the host: e.g. a 4-D spectrum of > 127 haplotypes per population"""
+    if sum(cells) > SFS_MAX_CELLS:
+        raise PgError("sfs: %d histogram cells requested, the dense spectra are limited to %d in total (fewer dimensions, "
+                      "fewer joint spectra per run, or --subsample smaller populations)" % (sum(cells), SFS_MAX_CELLS))
+
+
 class Engine:
     def __init__(self, device: int = 0):
         self._lib = _lib.lib()
@@ -334,7 +344,8 @@ class Engine:
             goff[k + 1] = goff[k] + len(grp)
         gp = np.array([x for grp in groups for x in grp], dtype=np.int32)
         shapes = [tuple(int(pop_sizes[x]) + 1 for x in grp) for grp in groups]
-        cells = [int(np.prod(sh)) for sh in shapes]
+        cells = [int(np.prod([int(d) for d in sh], dtype=object)) for sh in shapes]
+        _check_sfs_cells(cells)
         hist = np.zeros(sum(cells), dtype=np.int64)
         first = np.zeros(sum(cells), dtype=np.int64)
         mask = None if site_mask is None else np.ascontiguousarray(site_mask, dtype=np.uint8)
@@ -364,7 +375,8 @@ class Engine:
             goff[k + 1] = goff[k] + len(grp)
         gp = np.array([x for grp in groups for x in grp], dtype=np.int32)
         shapes = [tuple(int(dims[x]) for x in grp) for grp in groups]
-        cells = [int(np.prod(sh)) for sh in shapes]
+        cells = [int(np.prod([int(d) for d in sh], dtype=object)) for sh in shapes]
+        _check_sfs_cells(cells)
         hist = np.zeros(sum(cells), dtype=np.int64)
         first = np.zeros(sum(cells), dtype=np.int64)
         mask = None if site_mask is None else np.ascontiguousarray(site_mask, dtype=np.uint8)

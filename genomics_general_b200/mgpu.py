@@ -113,8 +113,10 @@ def init(module: str, argv, devices: int):
     if "PG_MG_RANK" in env:                               # a rank started by the parent command line
         return Rendezvous(int(env["PG_MG_RANK"]), int(env["PG_MG_WORLD"]), env["PG_MG_DIR"])
     if devices is None and "RANK" in env and int(env.get("WORLD_SIZE", "1")) > 1:       # torchrun
+        # the ranks of one launch share their parent (the torchrun agent): its pid keeps the files of an earlier launch that
+        # died before cleaning up (same port, same run id) out of this one's exchange
         d = os.path.join("/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir(),
-                         "pgwin_%s_%s" % (env.get("MASTER_PORT", "0"), env.get("TORCHELASTIC_RUN_ID", "run")))
+                         "pgwin_%s_%s_%d" % (env.get("MASTER_PORT", "0"), env.get("TORCHELASTIC_RUN_ID", "run"), os.getppid()))
         return Rendezvous(int(env["RANK"]), int(env["WORLD_SIZE"]), d)
     if not devices or devices <= 1:
         return None
