@@ -80,9 +80,10 @@ def main(argv=None):
     # --devices N: this process becomes rank 0 of N (ranks 1.. are re-launched copies of this command line)
     rdv = mgpu.init("genomics_general_b200.cli.popgenWindows", argv, args.devices)
     if rdv is not None:
-        unsupported = [a for a in args.analysis if a not in ("popDist", "popPairDist")]
+        unsupported = [a for a in args.analysis if a not in ("popDist", "popPairDist", "popFreq")]
         if unsupported:
-            raise NotImplementedError("--devices > 1 supports --analysis popDist popPairDist (got %s)" % " ".join(unsupported))
+            raise NotImplementedError("--devices > 1 supports --analysis popDist popPairDist popFreq (got %s)"
+                                      % " ".join(unsupported))
     out = C.open_out(args.outFile) if (rdv is None or rdv.rank == 0) else open(os.devnull, "wt")
     out.write("scaffold,start,end,mid,sites," if not args.addWindowID else "windowID,scaffold,start,end,mid,sites,")
     stats = []
@@ -133,6 +134,7 @@ def main(argv=None):
             mgpu.fetch_halo(eng, args.genoFile, gd, starts, off_all, rdv.rank, halo, args.genoFormat, ploidyDict)
             eng.set_windows(llo, lhi)
             eng.set_pops(C.hap_pop_vector(gd, popNames, popInds), max(P, 1))
+            eng.set_freqstats("popFreq" in args.analysis)          # the popFreq counters travel in the same records
             all_idx = [mgpu.assign_windows(lo, hi, starts, q)[0] for q in range(rdv.world)]
             w_max, row_of = mgpu.gathered_order(all_idx)
             mgpu.nccl_connect(eng, rdv)
@@ -149,7 +151,12 @@ def main(argv=None):
             hp_all = C.hap_pop_vector(gd, popNames, popInds)
             if np.any(hp_all < 0):
                 raise NotImplementedError("popFreq with samples outside every population (--samples) is not supported")
-            fq = eng.popgen_freqstats()
+            if rdv is None:
+                fq = eng.popgen_freqstats()
+            else:                          # [l, S[P], thetaPi[P], thetaW[P], TajD[P]] behind the distance statistics of a record
+                pf = r["popfreq"]
+                fq = dict(l=pf[:, 0], S=pf[:, 1:1 + P], thetaPi=pf[:, 1 + P:1 + 2 * P], thetaW=pf[:, 1 + 2 * P:1 + 3 * P],
+                          TajD=pf[:, 1 + 3 * P:1 + 4 * P])
         npairs = P * (P - 1) // 2
         # state of the reference's cached distance matrix when the later analyses run (popgenWindows.py:50-64)
         masked = minSites if ("popDist" in args.analysis or "popPairDist" in args.analysis) else 0

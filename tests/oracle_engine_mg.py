@@ -62,6 +62,9 @@ class OracleEngineMG(OracleEngine):
     def last_timings(self):
         return {}
 
+    def set_freqstats(self, enable=True):
+        self._want_freq = bool(enable)
+
     # ---- the exchange: the "NCCL id" is the path of a directory ----
     def nccl_unique_id(self):
         d = tempfile.mkdtemp(prefix="pg_fake_nccl_").encode()
@@ -107,6 +110,12 @@ class OracleEngineMG(OracleEngine):
         rec[:, 3:3 + P] = r["pi"]
         rec[:, 3 + P:3 + P + npairs] = r["dxy"]
         rec[:, 3 + P + npairs:3 + P + 2 * npairs] = r["fst"]
+        if getattr(self, "_want_freq", False):       # [l, S[P], thetaPi[P], thetaW[P], TajD[P]] (pg_popgen_freqstats decodes the same)
+            f = self.popgen_freqstats()
+            b = 3 + P + 2 * npairs
+            rec[:, b] = f["l"]
+            for k, key in enumerate(("S", "thetaPi", "thetaW", "TajD")):
+                rec[:, b + 1 + k * P:b + 1 + (k + 1) * P] = f[key]
         self._allgather(rec, int(w_max), table)
         return int((r["path"] == 2).sum())
 

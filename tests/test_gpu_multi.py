@@ -65,6 +65,8 @@ def test_command_lines_on_two_devices_equal_one_device(tmp_path, miss):
     pp = ["-p", "pop0", "-p", "pop1", "-p", "pop2", "-p", "pop3", "--popsFile", pops]
     runs = [("popgenWindows", ["-w", "7000", "-m", "50", "-f", "phased", "--roundTo", "10", "--writeFailedWindows"] + pp),
             ("popgenWindows", ["--windType", "sites", "-w", "900", "-O", "300", "-m", "100", "-f", "phased", "--roundTo", "10"] + pp),
+            ("popgenWindows", ["-w", "7000", "-m", "50", "-f", "phased", "--roundTo", "10", "--analysis", "popFreq", "popDist",
+                               "popPairDist"] + pp),
             ("ABBABABAwindows", ["-w", "7000", "-m", "50", "-f", "phased", "--minData", "0.5", "--popsFile", pops, "-P1", "pop0",
                                  "-P2", "pop1", "-P3", "pop2", "-O", "pop3", "--writeFailedWindows"]),
             ("fourPopWindows", ["-w", "7000", "-m", "50", "-f", "phased", "--minData", "0.5", "--popsFile", pops, "-P1", "pop0",

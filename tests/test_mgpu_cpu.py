@@ -109,6 +109,8 @@ MG_CASES = {
     "popgen_coordinate": ("popgenWindows", ["-w", "9000", "-m", "50", "-f", "phased", "--roundTo", "9"] + POPS4),
     "popgen_sites_overlap": ("popgenWindows", ["--windType", "sites", "-w", "400", "-O", "150", "-m", "100", "-f", "phased",
                                                "--writeFailedWindows", "--addWindowID"] + POPS4),
+    "popgen_popfreq": ("popgenWindows", ["-w", "9000", "-m", "50", "-f", "phased", "--analysis", "popFreq", "popDist", "popPairDist",
+                                         "--writeFailedWindows"] + POPS4),
     "abba_coordinate": ("ABBABABAwindows", ["-w", "12000", "-m", "30", "-f", "phased", "--minData", "0.5"] + P4),
     "fourpop_sites": ("fourPopWindows", ["--windType", "sites", "-w", "500", "--overlap", "100", "-m", "30", "-f", "phased",
                                          "--minData", "0.5", "--polarize"] + P4),
