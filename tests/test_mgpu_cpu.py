@@ -77,7 +77,10 @@ def mg_input(tmp_path_factory):
     with open(pops, "wt") as f:
         for i, n in enumerate(spec.sample_names()):
             f.write("%s pop%d\n" % (n, i // 3))
-    return dict(geno=geno, pops=pops, dir=str(d))
+    coords = str(d / "mg.windows")
+    with open(coords, "wt") as f:            # predefined windows: file order, one empty, one spanning most of a scaffold
+        f.write("chr1 1 4000 a\nchr1 3000 9000 b\nchr1 9001 9002 c\nchr2 100 8000 d\nchr3 1 3000 e\nchr3 2500 12000 f\n")
+    return dict(geno=geno, pops=pops, dir=str(d), coords=coords)
 
 
 def _single_device(module, argv, monkeypatch):
@@ -109,6 +112,8 @@ MG_CASES = {
     "popgen_coordinate": ("popgenWindows", ["-w", "9000", "-m", "50", "-f", "phased", "--roundTo", "9"] + POPS4),
     "popgen_sites_overlap": ("popgenWindows", ["--windType", "sites", "-w", "400", "-O", "150", "-m", "100", "-f", "phased",
                                                "--writeFailedWindows", "--addWindowID"] + POPS4),
+    "popgen_predefined": ("popgenWindows", ["--windType", "predefined", "--windCoords", "@COORDS@", "-m", "20", "-f", "phased",
+                                            "--writeFailedWindows", "--addWindowID"] + POPS4),
     "popgen_popfreq": ("popgenWindows", ["-w", "9000", "-m", "50", "-f", "phased", "--analysis", "popFreq", "popDist", "popPairDist",
                                          "--writeFailedWindows"] + POPS4),
     "abba_coordinate": ("ABBABABAwindows", ["-w", "12000", "-m", "30", "-f", "phased", "--minData", "0.5"] + P4),
@@ -119,11 +124,11 @@ MG_CASES = {
 }
 
 
-@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("world", [2, 3, 5])
 @pytest.mark.parametrize("case", list(MG_CASES))
 def test_command_lines_on_n_ranks_equal_one_device_cpu(mg_input, case, world, monkeypatch, tmp_path):
     module, argv = MG_CASES[case]
-    base = argv + ["-g", mg_input["geno"], "--popsFile", mg_input["pops"]]
+    base = [mg_input["coords"] if x == "@COORDS@" else x for x in argv] + ["-g", mg_input["geno"], "--popsFile", mg_input["pops"]]
     one = str(tmp_path / "one.txt")
     _single_device(module, base + ["-o", one], monkeypatch)
     many = str(tmp_path / "many.txt")
