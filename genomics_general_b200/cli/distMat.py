@@ -7,7 +7,7 @@ import sys
 
 import numpy as np
 
-from .. import genomics, windows as W
+from .. import genomics, mgpu, windows as W
 from ..engine import Engine
 from . import _common as C
 
@@ -57,36 +57,58 @@ def main(argv=None):
     ploidyDict = C.ploidy_dict(args, samples, args.haploid)
     sampleData = genomics.SampleData(indNames=list(samples), ploidyDict=ploidyDict)
     header = "\t".join(args.headers) if args.headers else None
-    eng = Engine(args.device)
-    gd = C.load_geno(args, sampleData.indNames, ploidyDict, header=header, engine=eng)
+    # --devices N (window modes): every rank tokenises its share of the file and computes + formats the windows that start
+    # there; there is no collective — the formatted windows travel through the exchange directory and rank 0 writes them in
+    # window order (distMat.py:317-353's worker pool and sorter).  `cat` is one window over every site: one device.
+    rdv = None
+    if args.windType != "cat":
+        rdv = mgpu.init("genomics_general_b200.cli.distMat", argv, args.devices)
+    eng = Engine(args.device if rdv is None else mgpu.device_for(rdv, args.device))
+    if rdv is None:
+        gd = C.load_geno(args, sampleData.indNames, ploidyDict, header=header, engine=eng)
+    else:
+        gd, starts, off_all = mgpu.sharded_ingest(eng, rdv, args.genoFile, args.genoFormat, sampleData.indNames, ploidyDict, header)
     if args.windType == "cat":
         ws = W.WindowSet()
         ws.add(None, -np.inf, np.inf, 0, gd.n_sites, None)               # parseGenoFile: one window, positions ignored
     else:
         ws = C.make_windows(args, gd, minSites, coords, C.read_scaffold_list(args.include), C.read_scaffold_list(args.exclude))
-    out = C.open_out(args.outFile)
+    writer = rdv is None or rdv.rank == 0
+    out = C.open_out(args.outFile) if writer else None
     wout = None
-    if args.windowDataOutFile:
+    if args.windowDataOutFile and writer:
         wout = C.open_out(args.windowDataOutFile)
         wout.write("scaffold,start,end,mid,sites," if not args.addWindowID else "windowID,scaffold,start,end,mid,sites,")
     lo, hi = ws.ranges()
     nInd = len(sampleData.indNames)
-    hap_ind = gd.hap_sample()
+    hap_ind = np.repeat(np.arange(len(gd.names), dtype=np.int32), np.asarray(gd.ploidy, dtype=np.int64))
+    mine = np.arange(len(ws))                     # windows this process computes (all of them on one device)
     with eng:
-        C.ensure_resident(eng, gd)
-        eng.set_windows(lo, hi)
-        if args.windType == "cat":
+        if rdv is None:
+            C.ensure_resident(eng, gd)
+            eng.set_windows(lo, hi)
+        else:
+            mine, llo, lhi, halo = mgpu.assign_windows(lo, hi, starts, rdv.rank)
+            mgpu.fetch_halo(eng, args.genoFile, gd, starts, off_all, rdv.rank, halo, args.genoFormat, ploidyDict)
+            eng.set_windows(llo, lhi)
+        if len(mine) == 0:
+            r = dict(dist=np.zeros((0, nInd, nInd)), sites=np.zeros(0, np.int64), pos_sum=np.zeros(0, np.int64))
+            per_ind_ok = np.ones(0, dtype=bool)
+        elif args.windType == "cat":
             dcat, ntot = eng.pairdist_cat(hap_ind, nInd, args.includeSameWithSame)      # chunked over the site axis
             r = dict(dist=dcat[None], sites=np.array([ntot], dtype=np.int64), pos_sum=np.zeros(1, dtype=np.int64))
         else:
             r = eng.pairdist(hap_ind, nInd, args.includeSameWithSame)
-        per_ind_ok = np.ones(len(ws), dtype=bool)
-        if args.minPerInd:
-            per_ind_ok = eng.seq_nonnan().min(axis=1) >= args.minPerInd             # min(aln.seqNonNan()) (distMat.py:40)
-    for k in range(len(ws)):
-        sites = int(r["sites"][k])
-        good = sites >= minSites and bool(per_ind_ok[k])
-        m = r["dist"][k] if good else np.full((nInd, nInd), np.nan)
+        if len(mine):
+            per_ind_ok = np.ones(len(mine), dtype=bool)
+            if args.minPerInd:
+                per_ind_ok = eng.seq_nonnan().min(axis=1) >= args.minPerInd         # min(aln.seqNonNan()) (distMat.py:40)
+    texts, wrows = {}, {}                         # window index -> matrix text / window-data row of the windows that are written
+    for j, k in enumerate(mine):
+        k = int(k)
+        sites = int(r["sites"][j])
+        good = sites >= minSites and bool(per_ind_ok[j])
+        m = r["dist"][j] if good else np.full((nInd, nInd), np.nan)
         if args.outFormat == "nexus":
             s = genomics.makeDistMatNexusString(m, names=sampleData.indNames, roundTo=args.roundTo)
         elif args.outFormat == "phylip":
@@ -94,17 +116,52 @@ def main(argv=None):
         else:
             s = genomics.makeDistMatString(m, roundTo=args.roundTo) + "\n"
         if good or args.writeFailedWindows:
-            out.write(s)
-            if wout is not None:
+            wrow = None
+            if args.windowDataOutFile:
                 if args.windType == "cat":
                     pre = [None, -np.inf, np.inf, np.nan, sites]
                 else:
-                    pre = C.window_prefix(args, ws, k, gd, sites, r["pos_sum"][k])
-                wout.write("\t".join(str(x) for x in (([] if not args.addWindowID else [ws.ID[k]]) + pre)) + "\n")
+                    pre = C.window_prefix(args, ws, k, gd, sites, r["pos_sum"][j])
+                wrow = "\t".join(str(x) for x in (([] if not args.addWindowID else [ws.ID[k]]) + pre)) + "\n"
+            if rdv is None:                       # one device: written as they come
+                out.write(s)
+                if wout is not None:
+                    wout.write(wrow)
+            else:
+                texts[k] = s
+                if wrow is not None:
+                    wrows[k] = wrow
+    if rdv is not None:
+        # a rank's windows as one blob: window indices, text lengths, the texts back to back (same for the window-data rows)
+        keys = sorted(texts)
+        rdv.put("dm_idx", np.array(keys, dtype=np.int64))
+        rdv.put("dm_len", np.array([len(texts[k].encode()) for k in keys], dtype=np.int64))
+        rdv.put_bytes("dm_txt", "".join(texts[k] for k in keys).encode())
+        rdv.put("dm_wlen", np.array([len(wrows[k].encode()) if k in wrows else 0 for k in keys], dtype=np.int64))
+        rdv.put_bytes("dm_wtxt", "".join(wrows.get(k, "") for k in keys).encode())
+        if rdv.rank != 0:
+            rdv.finish()
+            return
+        texts, wrows = {}, {}
+        for q in range(rdv.world):
+            keys, blob, wblob = rdv.get("dm_idx", q), rdv.get_bytes("dm_txt", q), rdv.get_bytes("dm_wtxt", q)
+            o = wo = 0
+            for k, n, wn in zip(keys, rdv.get("dm_len", q), rdv.get("dm_wlen", q)):
+                texts[int(k)] = blob[o:o + int(n)].decode()
+                o += int(n)
+                if wn:
+                    wrows[int(k)] = wblob[wo:wo + int(wn)].decode()
+                    wo += int(wn)
+    for k in sorted(texts):
+        out.write(texts[k])
+        if wout is not None and k in wrows:
+            wout.write(wrows[k])
     if out is not sys.stdout:
         out.close()
     if wout is not None and wout is not sys.stdout:
         wout.close()
+    if rdv is not None:
+        rdv.finish()
 
 
 if __name__ == "__main__":

@@ -79,11 +79,6 @@ def main(argv=None):
 
     # --devices N: this process becomes rank 0 of N (ranks 1.. are re-launched copies of this command line)
     rdv = mgpu.init("genomics_general_b200.cli.popgenWindows", argv, args.devices)
-    if rdv is not None:
-        unsupported = [a for a in args.analysis if a not in ("popDist", "popPairDist", "popFreq")]
-        if unsupported:
-            raise NotImplementedError("--devices > 1 supports --analysis popDist popPairDist popFreq (got %s)"
-                                      % " ".join(unsupported))
     out = C.open_out(args.outFile) if (rdv is None or rdv.rank == 0) else open(os.devnull, "wt")
     out.write("scaffold,start,end,mid,sites," if not args.addWindowID else "windowID,scaffold,start,end,mid,sites,")
     stats = []
@@ -143,9 +138,6 @@ def main(argv=None):
             eng.nccl_finalize()
             rows = np.array([row_of[w] for w in range(len(ws))], dtype=np.int64)
             r = multigpu.unpack_device_records(table[rows] if len(rows) else table[:0], P)
-            if rdv.rank != 0:
-                rdv.finish()
-                return
         fq = None
         if "popFreq" in args.analysis:
             hp_all = C.hap_pop_vector(gd, popNames, popInds)
@@ -161,17 +153,39 @@ def main(argv=None):
         # state of the reference's cached distance matrix when the later analyses run (popgenWindows.py:50-64)
         masked = minSites if ("popDist" in args.analysis or "popPairDist" in args.analysis) else 0
         dmat = het = hst = None
+        # (on several devices these run on the rank's own windows; a rank without windows has nothing to compute)
+        idle = rdv is not None and len(idx) == 0
         if "indPairDist" in args.analysis:
             inv = {gd.names.index(n): k for k, n in enumerate(ind_sorted)}
             hap_ind = np.repeat(np.array([inv[i] for i in range(len(gd.names))], dtype=np.int32), gd.ploidy.astype(np.int64))
-            dmat = eng.pairdist(hap_ind, len(ind_sorted), False, min_sites=masked)["dist"]
+            dmat = np.zeros((0, len(ind_sorted), len(ind_sorted))) if idle else \
+                eng.pairdist(hap_ind, len(ind_sorted), False, min_sites=masked)["dist"]
         if "indHet" in args.analysis:
             inv = {gd.names.index(n): k for k, n in enumerate(allInds)}
             hap_ind = np.repeat(np.array([inv[i] for i in range(len(gd.names))], dtype=np.int32), gd.ploidy.astype(np.int64))
-            het = eng.ind_het(hap_ind, len(allInds), min_sites=masked)
+            het = np.zeros((0, len(allInds))) if idle else eng.ind_het(hap_ind, len(allInds), min_sites=masked)
         if "hapStats" in args.analysis:
-            hst = eng.hapstats(args.hapDist, min_sites=masked, diag_nan=bool(masked) or "popDist" in args.analysis
-                               or "popPairDist" in args.analysis or "indPairDist" in args.analysis)
+            hst = np.zeros((0, max(P, 1), 3)) if idle else \
+                eng.hapstats(args.hapDist, min_sites=masked, diag_nan=bool(masked) or "popDist" in args.analysis
+                             or "popPairDist" in args.analysis or "indPairDist" in args.analysis)
+        if rdv is not None:
+            # The pairwise analyses have no collective: a rank publishes the arrays of its windows through the exchange
+            # directory (they are on the host already), rank 0 puts them in window order.
+            extras = dict(dmat=dmat, het=het, hst=hst)
+            for name, arr in extras.items():
+                if arr is not None:
+                    rdv.put("x_" + name, np.asarray(arr, dtype=np.float64))
+            if rdv.rank != 0:
+                rdv.finish()
+                return
+            for name, arr in extras.items():
+                if arr is not None:
+                    full = np.full((len(ws),) + tuple(np.shape(arr)[1:]), np.nan)
+                    for q in range(rdv.world):
+                        if len(all_idx[q]):
+                            full[all_idx[q]] = rdv.get("x_" + name, q)
+                    extras[name] = full
+            dmat, het, hst = extras["dmat"], extras["het"], extras["hst"]
         tm.mark("statistics", eng)
         iu = np.triu_indices(len(ind_sorted)) if dmat is not None else None
         simple = fq is None and dmat is None and het is None and hst is None

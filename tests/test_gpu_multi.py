@@ -56,7 +56,7 @@ def _write_inputs(tmp_path, miss, scaffolds=3):
 
 @pytest.mark.parametrize("miss", [0.0, 0.03])
 def test_command_lines_on_two_devices_equal_one_device(tmp_path, miss):
-    """popgenWindows / ABBABABAwindows / fourPopWindows / freq with --devices 2 (each rank tokenises its byte range of the file, windows that
+    """popgenWindows (all analyses) / ABBABABAwindows / fourPopWindows / distMat / freq with --devices 2 (each rank tokenises its byte range of the file, windows that
     straddle the cut fetch their halo sites, one NCCL all-gather, rank 0 writes) == the single-device output, byte for byte"""
     if not _two_gpus():
         pytest.skip("needs 2 GPUs")
@@ -71,6 +71,9 @@ def test_command_lines_on_two_devices_equal_one_device(tmp_path, miss):
                                  "-P2", "pop1", "-P3", "pop2", "-O", "pop3", "--writeFailedWindows"]),
             ("fourPopWindows", ["-w", "7000", "-m", "50", "-f", "phased", "--minData", "0.5", "--popsFile", pops, "-P1", "pop0",
                                 "-P2", "pop1", "-P3", "pop2", "-O", "pop3", "--polarize", "--writeFailedWindows"]),
+            ("popgenWindows", ["-w", "7000", "-m", "50", "-f", "phased", "--roundTo", "10", "--analysis", "popDist", "popPairDist",
+                               "indPairDist", "indHet", "hapStats", "--hapDist", "0.02"] + pp),
+            ("distMat", ["-w", "7000", "-m", "50", "-f", "phased", "--outFormat", "raw", "--roundTo", "10"]),
             ("freq", ["-f", "phased"] + pp)]
     for mod, argv in runs:
         outs = []

@@ -116,9 +116,17 @@ MG_CASES = {
                                             "--writeFailedWindows", "--addWindowID"] + POPS4),
     "popgen_popfreq": ("popgenWindows", ["-w", "9000", "-m", "50", "-f", "phased", "--analysis", "popFreq", "popDist", "popPairDist",
                                          "--writeFailedWindows"] + POPS4),
+    "popgen_all_analyses": ("popgenWindows", ["-w", "9000", "-m", "50", "-f", "phased", "--analysis", "popDist", "popPairDist",
+                                              "indPairDist", "indHet", "hapStats", "--hapDist", "0.02"] + POPS4),
+    "popgen_pairwise_only": ("popgenWindows", ["--windType", "sites", "-w", "700", "-m", "100", "-f", "phased", "--analysis",
+                                               "indPairDist", "hapStats", "--writeFailedWindows"] + POPS4),
     "abba_coordinate": ("ABBABABAwindows", ["-w", "12000", "-m", "30", "-f", "phased", "--minData", "0.5"] + P4),
     "fourpop_sites": ("fourPopWindows", ["--windType", "sites", "-w", "500", "--overlap", "100", "-m", "30", "-f", "phased",
                                          "--minData", "0.5", "--polarize"] + P4),
+    "distmat_raw_windowdata": ("distMat", ["-w", "9000", "-m", "50", "-f", "phased", "--outFormat", "raw", "--roundTo", "8",
+                                           "--windowDataOutFile", "@WDATA@", "--addWindowID"]),
+    "distmat_phylip_sites": ("distMat", ["--windType", "sites", "-w", "600", "-O", "200", "-m", "100", "-f", "phased", "--outFormat",
+                                         "phylip", "--includeSameWithSame", "--minPerInd", "560", "--writeFailedWindows"]),
     "freq_counts": ("freq", ["-f", "phased"] + POPS4),
     "freq_target": ("freq", ["-f", "phased", "--target", "derived", "--minData", "0.5"] + POPS4),
 }
@@ -129,10 +137,14 @@ MG_CASES = {
 def test_command_lines_on_n_ranks_equal_one_device_cpu(mg_input, case, world, monkeypatch, tmp_path):
     module, argv = MG_CASES[case]
     base = [mg_input["coords"] if x == "@COORDS@" else x for x in argv] + ["-g", mg_input["geno"], "--popsFile", mg_input["pops"]]
+    if module == "distMat":
+        base = [x for x in base if x != "--popsFile" and x != mg_input["pops"]]
     one = str(tmp_path / "one.txt")
-    _single_device(module, base + ["-o", one], monkeypatch)
+    _single_device(module, [x if x != "@WDATA@" else one + ".w" for x in base] + ["-o", one], monkeypatch)
     many = str(tmp_path / "many.txt")
-    _ranks(module, base + ["-o", many], world, str(tmp_path / "rdv"))
+    _ranks(module, [x if x != "@WDATA@" else many + ".w" for x in base] + ["-o", many], world, str(tmp_path / "rdv"))
     a, b = open(one).read(), open(many).read()
     assert len(a.splitlines()) > 3
     assert a == b
+    if "@WDATA@" in base:
+        assert open(one + ".w").read() == open(many + ".w").read() and open(one + ".w").read().count("\n") > 2
