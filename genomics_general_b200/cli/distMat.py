@@ -57,15 +57,16 @@ def main(argv=None):
     ploidyDict = C.ploidy_dict(args, samples, args.haploid)
     sampleData = genomics.SampleData(indNames=list(samples), ploidyDict=ploidyDict)
     header = "\t".join(args.headers) if args.headers else None
-    # --devices N (window modes): every rank tokenises its share of the file and computes + formats the windows that start
-    # there; there is no collective — the formatted windows travel through the exchange directory and rank 0 writes them in
-    # window order (distMat.py:317-353's worker pool and sorter).  `cat` is one window over every site: one device.
-    rdv = None
-    if args.windType != "cat":
-        rdv = mgpu.init("genomics_general_b200.cli.distMat", argv, args.devices)
+    # --devices N: every rank tokenises its share of the file.  Window modes: a rank computes + formats the windows that start
+    # in its share; there is no collective — the formatted windows travel through the exchange directory and rank 0 writes
+    # them in window order (distMat.py:317-353's worker pool and sorter).  `cat` (one window over every site): the ranks hold
+    # shards of the SITES and pg_pairdist_cat adds the integer pair matrices with ONE ncclAllReduce before the division.
+    rdv = mgpu.init("genomics_general_b200.cli.distMat", argv, args.devices)
     eng = Engine(args.device if rdv is None else mgpu.device_for(rdv, args.device))
     if rdv is None:
         gd = C.load_geno(args, sampleData.indNames, ploidyDict, header=header, engine=eng)
+    elif args.windType == "cat":
+        gd = mgpu.local_ingest(eng, rdv, args.genoFile, args.genoFormat, sampleData.indNames, ploidyDict, header)
     else:
         gd, starts, off_all = mgpu.sharded_ingest(eng, rdv, args.genoFile, args.genoFormat, sampleData.indNames, ploidyDict, header)
     if args.windType == "cat":
@@ -87,6 +88,9 @@ def main(argv=None):
         if rdv is None:
             C.ensure_resident(eng, gd)
             eng.set_windows(lo, hi)
+        elif args.windType == "cat":
+            eng.set_windows(lo, hi)               # the rank's shard of the one window
+            mgpu.nccl_connect(eng, rdv)
         else:
             mine, llo, lhi, halo = mgpu.assign_windows(lo, hi, starts, rdv.rank)
             mgpu.fetch_halo(eng, args.genoFile, gd, starts, off_all, rdv.rank, halo, args.genoFormat, ploidyDict)
@@ -102,7 +106,17 @@ def main(argv=None):
         if len(mine):
             per_ind_ok = np.ones(len(mine), dtype=bool)
             if args.minPerInd:
-                per_ind_ok = eng.seq_nonnan().min(axis=1) >= args.minPerInd         # min(aln.seqNonNan()) (distMat.py:40)
+                nn = eng.seq_nonnan()
+                if rdv is not None and args.windType == "cat":                      # the counts of the shards add up
+                    nn = np.sum(rdv.allgather("cat_nonnan", nn), axis=0)
+                per_ind_ok = nn.min(axis=1) >= args.minPerInd                        # min(aln.seqNonNan()) (distMat.py:40)
+        if rdv is not None and args.windType == "cat":
+            eng.nccl_finalize()
+            if rdv.rank != 0:                     # every rank holds the same matrix; rank 0 writes it
+                rdv.finish()
+                return
+            rdv.finish()
+            rdv = None
     texts, wrows = {}, {}                         # window index -> matrix text / window-data row of the windows that are written
     for j, k in enumerate(mine):
         k = int(k)

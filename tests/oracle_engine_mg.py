@@ -137,3 +137,25 @@ class OracleEngineMG(OracleEngine):
             rec[:, 2 + k] = r[key]
         rec[:, 16] = r["sitesUsed"]
         self._allgather(rec, int(w_max), table)
+
+    def pairdist_cat(self, hap_ind, n_ind, include_same_with_same=False):
+        """with a communicator: the integer pair matrices of the ranks' site shards are added before the division — the
+        same numbers as one pass over the concatenated shards, which is what this computes"""
+        if self._world <= 1:
+            return super().pairdist_cat(hap_ind, n_ind, include_same_with_same)
+        self._round += 1
+        p = os.path.join(self._xdir, "cat%d.r%d.npy" % (self._round, self._rank))
+        with open(p + ".tmp", "wb") as f:
+            np.save(f, self.g)
+        os.rename(p + ".tmp", p)
+        parts = []
+        for r in range(self._world):
+            q = os.path.join(self._xdir, "cat%d.r%d.npy" % (self._round, r))
+            t0 = time.time()
+            while not os.path.exists(q):
+                assert time.time() - t0 < 300
+                time.sleep(0.005)
+            parts.append(np.load(q))
+        whole = OracleEngine()
+        whole.upload(np.concatenate(parts, axis=0))
+        return whole.pairdist_cat(hap_ind, n_ind, include_same_with_same)

@@ -127,6 +127,8 @@ MG_CASES = {
                                            "--windowDataOutFile", "@WDATA@", "--addWindowID"]),
     "distmat_phylip_sites": ("distMat", ["--windType", "sites", "-w", "600", "-O", "200", "-m", "100", "-f", "phased", "--outFormat",
                                          "phylip", "--includeSameWithSame", "--minPerInd", "560", "--writeFailedWindows"]),
+    "distmat_cat_nexus": ("distMat", ["--windType", "cat", "-f", "phased", "--outFormat", "nexus", "--roundTo", "9", "--minPerInd",
+                                      "3000"]),
     "freq_counts": ("freq", ["-f", "phased"] + POPS4),
     "freq_target": ("freq", ["-f", "phased", "--target", "derived", "--minData", "0.5"] + POPS4),
 }
