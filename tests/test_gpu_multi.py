@@ -74,6 +74,7 @@ def test_command_lines_on_two_devices_equal_one_device(tmp_path, miss):
             ("popgenWindows", ["-w", "7000", "-m", "50", "-f", "phased", "--roundTo", "10", "--analysis", "popDist", "popPairDist",
                                "indPairDist", "indHet", "hapStats", "--hapDist", "0.02"] + pp),
             ("distMat", ["-w", "7000", "-m", "50", "-f", "phased", "--outFormat", "raw", "--roundTo", "10"]),
+            ("distMat", ["--windType", "cat", "-f", "phased", "--outFormat", "phylip", "--roundTo", "10"]),
             ("freq", ["-f", "phased"] + pp)]
     for mod, argv in runs:
         outs = []
