@@ -26,7 +26,7 @@ import sys
 
 import numpy as np
 
-from .. import genomics
+from .. import genomics, mgpu
 from ..engine import Engine
 from . import _common as C
 
@@ -349,8 +349,17 @@ def main(argv=None):
     sampleData = genomics.SampleData(indNames=list(allSamples), popNames=enginePops,
                                      popInds=[popDict[pn] for pn in enginePops], ploidyDict=ploidyDict)
     args.genoFile, args.hostParse = args.inputFile, getattr(args, "hostParse", False)
-    eng = Engine(args.device)
-    gd = C.load_geno(args, sampleData.indNames, ploidyDict, header=args.header, engine=eng)
+    # --devices N (genotype input): spectra add up over the sites, so every rank tokenises its share of the file and counts it;
+    # the dense histograms and the first site of every cell (its index in the whole file: local index + the sites of the
+    # ranks before) go to rank 0 through the exchange directory — no collective.
+    rdv = mgpu.init("genomics_general_b200.cli.sfs", argv, args.devices)
+    if rdv is not None and (args.subsample or args.subsampleIndividuals):
+        raise NotImplementedError("--subsample draws from ONE random stream over the sites in file order; use one device")
+    eng = Engine(args.device if rdv is None else mgpu.device_for(rdv, args.device))
+    if rdv is None:
+        gd = C.load_geno(args, sampleData.indNames, ploidyDict, header=args.header, engine=eng)
+    else:
+        gd = mgpu.local_ingest(eng, rdv, args.inputFile, args.genoFormat, sampleData.indNames, ploidyDict, args.header)
     mask = None
     if include or exclude:
         ok = np.array([(not include or n in include) and (n not in exclude) for n in gd.scaf_names], dtype=np.uint8)
@@ -378,6 +387,27 @@ def main(argv=None):
             assert table.max(initial=0) <= 65535
             per = [eng.sfs_tables("base", table, len(inPopNames), groups, outgroup=og,
                                   site_mask=went if m is None else (m & went)) for m in masks]
+    if rdv is not None:
+        n_before = int(sum(int(x) for x in rdv.allgather("sfs_sites", np.array(gd.n_sites, dtype=np.int64))[:rdv.rank]))
+        for i, (hists, firsts, _) in enumerate(per):
+            for k in range(len(FSpops)):
+                rdv.put("sfs_h_%d_%d" % (i, k), hists[k])
+                rdv.put("sfs_f_%d_%d" % (i, k), np.where(hists[k] > 0, firsts[k] + n_before, 0))
+        if rdv.rank != 0:
+            rdv.finish()
+            return
+        big = np.iinfo(np.int64).max
+        merged = []
+        for i in range(len(per)):
+            H, F = [], []
+            for k in range(len(FSpops)):
+                hs = [rdv.get("sfs_h_%d_%d" % (i, k), q) for q in range(rdv.world)]
+                fs = [rdv.get("sfs_f_%d_%d" % (i, k), q) for q in range(rdv.world)]
+                H.append(np.sum(hs, axis=0))
+                F.append(np.min([np.where(h > 0, f, big) for h, f in zip(hs, fs)], axis=0))
+            merged.append((H, F, 0))
+        per = merged
+        rdv.finish()
     write_spectra(args, FSpops, *merge_intervals(per, len(FSpops)))
 
 

@@ -129,6 +129,8 @@ MG_CASES = {
                                          "phylip", "--includeSameWithSame", "--minPerInd", "560", "--writeFailedWindows"]),
     "distmat_cat_nexus": ("distMat", ["--windType", "cat", "-f", "phased", "--outFormat", "nexus", "--roundTo", "9", "--minPerInd",
                                       "3000"]),
+    "sfs_polarized_pairs_regions": ("sfs", ["--inputType", "genotypes", "--polarized", "--doPairs", "--exclude", "chr2", "--regions",
+                                            "chr1:1-9000", "chr3:2000-11000", "chr1:5000-15000"] + POPS4),
     "freq_counts": ("freq", ["-f", "phased"] + POPS4),
     "freq_target": ("freq", ["-f", "phased", "--target", "derived", "--minData", "0.5"] + POPS4),
 }
@@ -141,12 +143,26 @@ def test_command_lines_on_n_ranks_equal_one_device_cpu(mg_input, case, world, mo
     base = [mg_input["coords"] if x == "@COORDS@" else x for x in argv] + ["-g", mg_input["geno"], "--popsFile", mg_input["pops"]]
     if module == "distMat":
         base = [x for x in base if x != "--popsFile" and x != mg_input["pops"]]
+    if module == "sfs":                            # -i / -p / --pref instead of -g / -p / -o
+        base = ["-i" if x == "-g" else x for x in base]
     one = str(tmp_path / "one.txt")
-    _single_device(module, [x if x != "@WDATA@" else one + ".w" for x in base] + ["-o", one], monkeypatch)
     many = str(tmp_path / "many.txt")
-    _ranks(module, [x if x != "@WDATA@" else many + ".w" for x in base] + ["-o", many], world, str(tmp_path / "rdv"))
+    if module == "sfs":                            # one file per spectrum: concatenate them for the comparison
+        import glob
+        for pref, run in ((one, lambda a: _single_device(module, a, monkeypatch)),
+                          (many, lambda a: _ranks(module, a, world, str(tmp_path / "rdv")))):
+            run(base + ["--pref", pref + ".", "--suff", ".sfs"])
+            files = sorted(glob.glob(pref + ".*.sfs"))
+            assert len(files) == 3 + 3          # polarized: three in-group populations, their three pairs
+            with open(pref, "wt") as f:
+                for x in files:
+                    f.write(os.path.basename(x)[len(os.path.basename(pref)):] + "\n" + open(x).read())
+        base = None
+    else:
+        _single_device(module, [x if x != "@WDATA@" else one + ".w" for x in base] + ["-o", one], monkeypatch)
+        _ranks(module, [x if x != "@WDATA@" else many + ".w" for x in base] + ["-o", many], world, str(tmp_path / "rdv"))
     a, b = open(one).read(), open(many).read()
     assert len(a.splitlines()) > 3
     assert a == b
-    if "@WDATA@" in base:
+    if base and "@WDATA@" in base:
         assert open(one + ".w").read() == open(many + ".w").read() and open(one + ".w").read().count("\n") > 2
