@@ -166,3 +166,20 @@ def test_command_lines_on_n_ranks_equal_one_device_cpu(mg_input, case, world, mo
     assert a == b
     if base and "@WDATA@" in base:
         assert open(one + ".w").read() == open(many + ".w").read() and open(one + ".w").read().count("\n") > 2
+
+
+def test_devices_launch_path_relaunches_the_command_line(tmp_path):
+    """mgpu.init(module, argv, N): rank 0 starts N-1 copies of the command line with PG_MG_RANK / PG_MG_WORLD / PG_MG_DIR,
+    they meet in the exchange directory, finish() waits for them and removes it"""
+    import json
+    out = str(tmp_path / "seen.json")
+    env = dict(os.environ, PYTHONPATH=HERE + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    for k in ("PG_MG_RANK", "PG_MG_WORLD", "PG_MG_DIR", "RANK", "WORLD_SIZE"):
+        env.pop(k, None)
+    r = subprocess.run([sys.executable, "-m", "_mgpu_dummy_cli", "3", out, "--flag", "x y"], env=env, cwd=HERE,
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout[-2000:]
+    seen = json.load(open(out))
+    assert seen["ranks"] == [0, 1, 2]
+    assert seen["argv"] == [["3", out, "--flag", "x y"]] * 3
+    assert not os.path.exists(seen["dir"])
