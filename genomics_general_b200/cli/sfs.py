@@ -192,16 +192,19 @@ def downsample_counts(counts, sizes, seed, considered):
     rs = np.random.RandomState(seed)
     out = np.array(counts, dtype=np.int64, copy=True)
     ok = np.zeros(len(out), dtype=np.uint8)
-    bases = np.arange(4)
+    npop = len(sizes)
+    tot = out[:, :npop].sum(axis=2)
+    cum = np.cumsum(out[:, :npop], axis=2)
+    # np.random.choice(pool, N, replace=False) is `permutation(len(pool))[:N]` applied to the pool (numpy's legacy generator):
+    # the same permutation is drawn here and mapped to alleles through the cumulative counts, without building the pool
     for s in np.flatnonzero(considered):
-        row = out[s]
         good = True
         for i, N in enumerate(sizes):
-            pool = np.repeat(bases, row[i])
-            if N > len(pool) or (len(pool) == 0 and N != 0):
+            n = tot[s, i]
+            if N > n or (n == 0 and N != 0):
                 good = False
                 break
-            row[i] = np.bincount(rs.choice(pool, N, replace=False), minlength=4)
+            out[s, i] = np.bincount(np.searchsorted(cum[s, i], rs.permutation(n)[:N], side="right"), minlength=4)
         ok[s] = good
     return out, ok
 
