@@ -364,6 +364,31 @@ class Alignment:
             out["Fst_%s_%s" % (a, b)] = out["Fst_%s_%s" % (b, a)] = float(r["fst"][0, k])
         return out
 
+    def groupFreqStats(self):
+        """genomics.py:1002-1028 -> dict l_X, S_X, thetaPi_X, thetaW_X, TajD_X per group (the popFreq columns): only sites
+        without missing data in ANY sequence count (1010); l is an int, S an int or nan (no such site), like the
+        reference's Python values."""
+        pops, hp = self._pop_index()
+        if np.any(hp < 0):
+            raise NotImplementedError("groupFreqStats with sequences outside every group is not supported (the reference "
+                                      "itself fails on mixed None / str groups, genomics.py:1007)")
+        eng = self._engine()
+        eng.set_pops(hp, len(pops))
+        eng.set_freqstats(True)
+        try:
+            eng.popgen(0, 0.01)
+            f = eng.popgen_freqstats()
+        finally:
+            eng.set_freqstats(False)
+        out = {}
+        for x, p in enumerate(pops):
+            S = f["S"][0, x]
+            out["l_" + str(p)] = int(f["l"][0])
+            out["S_" + str(p)] = np.nan if np.isnan(S) else int(S)
+            for k in ("thetaPi", "thetaW", "TajD"):
+                out["%s_%s" % (k, p)] = float(f[k][0, x])
+        return out
+
     def indPairDists(self, asDict=True, includeSameWithSame=False, minSites=None):
         """genomics.py:934-954 (order of first appearance of sample names)."""
         samples = list(dict.fromkeys(self.sampleNames.tolist()))

@@ -161,3 +161,23 @@ def test_window_generators(idx):
         assert [pos[k] for k in w["sites"]] == r["positions"]
         if case["kind"] != "sites":
             assert [w["start"], w["end"]] == r["limits"]
+
+
+@pytest.mark.parametrize("case", [m for m in META if m.get("groupFreqStats")], ids=[m["name"] for m in META if m.get("groupFreqStats")])
+def test_alignment_mirror_group_freq_stats(case):
+    """Alignment.groupFreqStats of the drop-in API (host logic on the oracle-backed engine) against the reference's dict"""
+    import sys
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from oracle_engine import OracleEngine
+    from genomics_general_b200 import genomics as G
+    hp = ARR[case["name"] + "__hap_pop"]
+    if np.any(hp < 0):
+        pytest.skip("sequences outside every group")
+    groups = [case["pop_names"][x] for x in hp]
+    a = G.Alignment(ARR[case["name"] + "__g_aln"], groups=groups, engine=OracleEngine())
+    got = a.groupFreqStats()
+    assert set(got) == set(case["groupFreqStats"])
+    for k, want in case["groupFreqStats"].items():
+        assert_close(got[k], want, k, rtol=1e-12)
+    assert all(isinstance(got["l_" + p], int) for p in case["pop_names"])
