@@ -493,6 +493,84 @@ def fourPop(aln, P1, P2, P3, P4, minData, polarize=False, fixed=False):
 # ------------------------------------------------------------------------------------------------
 # window generators over a parsed file
 # ------------------------------------------------------------------------------------------------
+# ------------------------------------------------------------------------------------------------
+# line-by-line readers (genomics.py:1884-1945): host Python, kept for scripts that walk a genotype file site by site —
+# the command lines of this package tokenise whole files on the device instead (geno_io.ingest_geno)
+# ------------------------------------------------------------------------------------------------
+def makeHaploidNames(names, ploidy=2):
+    """genomics.py:448-453: `ind_A`, `ind_B`, ... per individual (the plain names when every ploidy is 1)"""
+    pl = list(ploidy) if isinstance(ploidy, (list, tuple, np.ndarray)) else [ploidy]
+    if len(pl) == 1:
+        pl = pl * len(names)
+    if all(int(x) == 1 for x in pl):
+        return names
+    per = dict(zip(names, pl))              # (a repeated name keeps its LAST ploidy, as the reference's dict does)
+    return [n + "_" + string.ascii_uppercase[k] for n in names for k in range(int(per[n]))]
+
+
+def parseGenoLine(line, names, scafCol=0, posCol=1, firstSampleCol=2, type=str, splitPhased=False, asDict=True,
+                  precompDict=None, addToPrecomp=True):
+    """One line of a .geno / counts table -> {"scaffold", "position", "GTs"} (genomics.py:1884-1904).  GTs: the genotype
+    fields as `type`, as a name -> value dict (asDict) or a list; splitPhased turns "A|T" into its alleles.  precompDict
+    caches the parsed fields by their text (identical lines are common), counting insertions in "__counter__"."""
+    if not line:
+        return {"scaffold": None, "position": None, "GTs": None}
+    fields = line.split(None, firstSampleCol)
+    text = fields[-1]
+    if precompDict and text in precompDict:
+        gts = precompDict[text]
+    else:
+        gts = text.split()
+        if splitPhased:
+            gts = [a for tok in gts for a in tok[::2]]
+        if type is float:
+            gts = [float(t) for t in gts]
+        elif type is not str:
+            gts = [int(t) for t in gts]
+        if asDict:
+            gts = dict(zip(names, gts))
+        if precompDict is not None and addToPrecomp:
+            precompDict[text] = gts
+            precompDict["__counter__"] += 1
+    return {"scaffold": fields[scafCol] if scafCol >= 0 else None,
+            "position": int(fields[posCol]) if posCol >= 0 else None, "GTs": gts}
+
+
+class GenoFileReader:
+    """genomics.py:1913-1945: iterates the data lines of an open genotype file ('#' lines skipped); `names` come from the
+    header line (read from the file unless given)."""
+
+    def __init__(self, genoFile, headerLine=None, scafCol=0, posCol=1, firstSampleCol=2, type=str, splitPhased=False,
+                 ploidy=None, precomp=True, precompMaxSize=10000):
+        self.genoFile = genoFile
+        if not headerLine:
+            headerLine = next(genoFile)
+        self.names = headerLine.split()[firstSampleCol:]
+        self.scafCol, self.posCol, self.firstSampleCol = scafCol, posCol, firstSampleCol
+        self.type, self.splitPhased = type, splitPhased
+        if splitPhased:
+            assert ploidy is not None, "Ploidy must be defined for splitting phased sequences"
+            if self.names:
+                self.names = makeHaploidNames(self.names, ploidy)
+        self.precompDict = {"__maxSize__": precompMaxSize, "__counter__": 0}
+
+    def _parse(self, line, asDict):
+        d = self.precompDict
+        return parseGenoLine(line, self.names, self.scafCol, self.posCol, self.firstSampleCol, self.type, self.splitPhased,
+                             asDict, d, addToPrecomp=d["__counter__"] < d["__maxSize__"])
+
+    def siteBySite(self, asDict=True):
+        for line in self.genoFile:
+            if line[0] != "#":
+                yield self._parse(line, asDict)
+
+    def nextSite(self, asDict=True):
+        while True:
+            line = next(self.genoFile, None)
+            if not (line and line[0] == "#"):
+                return self._parse(line, asDict)
+
+
 def _windows_from(gd: geno_io.GenoData, ws: _win.WindowSet, genoFormat):
     for k in range(len(ws)):
         lo, hi = ws.lo[k], ws.hi[k]

@@ -162,3 +162,26 @@ def test_geno_window_mutators_follow_the_reference_container():
     assert w.positions == [88]
     with pytest.raises(TypeError):
         w.trim(right=True, remove=0)                    # seqLen() - None, as in the reference
+
+
+def test_line_readers_follow_the_reference():
+    """parseGenoLine / GenoFileReader / makeHaploidNames of the drop-in API (genomics.py:1884-1945, 448-453) against what
+    the reference returns for the same text (tests/golden/reader_cases.json, written by running the reference's own
+    classes): dict and list rows, '#' lines skipped, phased genotypes split into alleles, the parsed-line cache counter,
+    the end-of-file record, integer / float tables."""
+    import io
+    from genomics_general_b200 import genomics as G
+    c = json.load(open(os.path.join(GOLDEN, "reader_cases.json")))
+    for name in ("plain", "split2", "split212"):
+        e = c[name]
+        kw = e["kw"]
+        assert G.GenoFileReader(io.StringIO(c["text"]), **kw).names == e["names"]
+        assert list(G.GenoFileReader(io.StringIO(c["text"]), **kw).siteBySite(asDict=True)) == e["dict_rows"]
+        assert list(G.GenoFileReader(io.StringIO(c["text"]), **kw).siteBySite(asDict=False)) == e["list_rows"]
+        r = G.GenoFileReader(io.StringIO(c["text"]), **kw)
+        assert [r.nextSite() for _ in range(5)] == e["next5"]
+        assert r.precompDict["__counter__"] == e["counter"]
+    assert list(G.GenoFileReader(io.StringIO(c["counts_text"]), type=int).siteBySite()) == c["counts_rows"]
+    assert G.parseGenoLine("x 1.5 2", ["u"], posCol=-1, firstSampleCol=1, type=float, asDict=False) == c["float_line"]
+    assert G.parseGenoLine("", ["u"]) == c["empty_line"]
+    assert [G.makeHaploidNames(["a", "b"], 1), G.makeHaploidNames(["a", "b"], [3, 1])] == c["haploid_names"]
