@@ -7,8 +7,9 @@ type, gates, prefixes, rounding, number formatting, the sfs interval / subsample
     python oracle/fuzz_vs_reference.py popgen 0 24      # popgenWindows: window types x analyses x flags (rows to 1e-6)
     python oracle/fuzz_vs_reference.py abba 0 12        # ABBABABAwindows: population orders, minData, window types
     python oracle/fuzz_vs_reference.py sfs 0 25         # sfs.py: --regions / --subsample / --exclude (byte for byte)
+    python oracle/fuzz_vs_reference.py freq_distmat 0 10   # freq.py modes (byte for byte) + distMat formats / cat / windows
 
-Round 2: 24 + 12 + 37 cases, no mismatch.  A reference worker that dies leaves its parent waiting: every run has a timeout."""
+Round 2: 24 + 12 + 37 + 20 cases, no mismatch (distMat windows use -m 1: the reference hangs on a failed window under numpy 2).  A reference worker that dies leaves its parent waiting: every run has a timeout."""
 import contextlib
 import io
 import os
@@ -22,10 +23,10 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 sys.path.insert(0, os.path.join(REPO, "tests"))
 from genomics_general_b200 import synth  # noqa: E402
-from genomics_general_b200.cli import ABBABABAwindows as ab, _common, popgenWindows as pg, sfs as sfs_cli  # noqa: E402
+from genomics_general_b200.cli import ABBABABAwindows as ab, _common, distMat as dm, freq as fq, popgenWindows as pg, sfs as sfs_cli  # noqa: E402
 from oracle_engine import OracleEngine  # noqa: E402
 
-for _m in (ab, pg, sfs_cli):
+for _m in (ab, dm, fq, pg, sfs_cli):
     _m.Engine = OracleEngine
 _real = _common.load_geno
 _common.load_geno = lambda args, samples, pl, header=None, engine=None: _real(args, samples, pl, header, None)
@@ -205,6 +206,66 @@ def fuzz_sfs(lo, hi):
     return bad
 
 
+def fuzz_freq_distmat(lo, hi):
+    bad = 0
+    d = TMP
+    for seed in range(lo, hi):
+        rng = np.random.default_rng(9000 + seed)
+        npops = int(rng.integers(2, 5)); spp = int(rng.integers(2, 4)); S = int(rng.integers(400, 1500)); miss = float(rng.choice([0.0, 0.05, 0.3]))
+        spec = synth.SynthSpec(npops, spp, seed=seed, miss=miss)
+        g = synth.synth_genotypes(spec, 0, S); pos = synth.synth_positions(S, seed=seed)
+        nsc = int(rng.integers(1, 3)); cut = int(rng.integers(1, S)) if nsc == 2 else S
+        scaf = ["c1"] * cut + ["c2"] * (S - cut)
+        gp = os.path.join(d, "fd.geno"); synth.write_geno(gp, g, pos, scaf, spec.sample_names())
+        pp = os.path.join(d, "fd.pops")
+        with open(pp, "wt") as f:
+            for i, n in enumerate(spec.sample_names()): f.write("%s pop%d\n" % (n, i // spp))
+        # ---- freq ----
+        argv = ["-g", gp, "-f", "phased", "--popsFile", pp, "-t", "1"]
+        for k in rng.permutation(npops): argv += ["-p", "pop%d" % k]
+        mode = rng.choice(["counts", "derived", "derived_counts", "derived_thr", "keepnan"])
+        if mode == "derived": argv += ["--target", "derived"]
+        elif mode == "derived_counts": argv += ["--target", "derived", "--asCounts"]
+        elif mode == "derived_thr": argv += ["--target", "derived", "--threshold", "0.5", "--minData", "0.5"]
+        elif mode == "keepnan": argv += ["--target", "derived", "--keepNanLines", "--minData", "0.8"]
+        oref, oours = os.path.join(d, "fref.tsv"), os.path.join(d, "fours.tsv")
+        r = subprocess.run([sys.executable, os.path.join(REF, "freq.py")] + argv + ["-o", oref], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
+        with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+            fq.main(argv + ["-o", oours])
+        same = r.returncode == 0 and open(oref).read() == open(oours).read()
+        bad += not same
+        print(seed, "freq", mode, "ok" if same else "MISMATCH rc=%d" % r.returncode, os.path.getsize(oours))
+        # ---- distMat (windows with -m 1 so that no window fails: the reference hangs on failed windows under numpy 2) ----
+        fmt = str(rng.choice(["raw", "phylip", "nexus"]))
+        argv = ["-g", gp, "-f", "phased", "-T", "1", "--outFormat", fmt, "--roundTo", str(int(rng.choice([4, 8])))]
+        if rng.random() < 0.5: argv += ["-w", str(int(rng.integers(3000, 8000))), "-m", "1"]
+        else: argv += ["--windType", "cat"]
+        if rng.random() < 0.5: argv += ["--includeSameWithSame"]
+        oref, oours = os.path.join(d, "dref.txt"), os.path.join(d, "dours.txt")
+        try:
+            r = subprocess.run([sys.executable, os.path.join(REF, "distMat.py")] + argv + ["-o", oref], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=90)
+        except subprocess.TimeoutExpired:
+            print(seed, "distMat REF TIMEOUT", argv[5:]); continue
+        with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+            dm.main(argv + ["-o", oours])
+        A, B = open(oours).read(), open(oref).read()
+        same = A == B
+        if not same:      # allow last-digit differences of the rounding
+            ta, tb = A.split(), B.split()
+            same = len(ta) == len(tb)
+            for x, y in zip(ta, tb):
+                if x == y: continue
+                try:
+                    if abs(float(x) - float(y)) > 2e-4: same = False; break
+                except ValueError:
+                    same = False; break
+        bad += not same
+        print(seed, "distMat", fmt, "ok" if same else "MISMATCH", len(A), argv[5:])
+    print("bad", bad)
+
+    return bad
+
+
 if __name__ == "__main__":
     which, lo, hi = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
-    sys.exit(1 if {"popgen": fuzz_popgen, "abba": fuzz_abba, "sfs": fuzz_sfs}[which](lo, hi) else 0)
+    sys.exit(1 if {"popgen": fuzz_popgen, "abba": fuzz_abba, "sfs": fuzz_sfs, "freq_distmat": fuzz_freq_distmat}[which](lo, hi) else 0)
