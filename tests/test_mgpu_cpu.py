@@ -80,7 +80,14 @@ def mg_input(tmp_path_factory):
     coords = str(d / "mg.windows")
     with open(coords, "wt") as f:            # predefined windows: file order, one empty, one spanning most of a scaffold
         f.write("chr1 1 4000 a\nchr1 3000 9000 b\nchr1 9001 9002 c\nchr2 100 8000 d\nchr3 1 3000 e\nchr3 2500 12000 f\n")
-    return dict(geno=geno, pops=pops, dir=str(d), coords=coords)
+    excl = str(d / "mg.exclude")
+    with open(excl, "wt") as f:
+        f.write("chr2\n")
+    nohdr = str(d / "mg_nohdr.geno")                  # the same genotypes without the header line (--header supplies it)
+    with open(geno) as f, open(nohdr, "wt") as o:
+        header = f.readline().rstrip("\n")
+        o.write(f.read())
+    return dict(geno=geno, pops=pops, dir=str(d), coords=coords, exclude=excl, nohdr=nohdr, header=header)
 
 
 def _single_device(module, argv, monkeypatch):
@@ -114,6 +121,10 @@ MG_CASES = {
                                                "--writeFailedWindows", "--addWindowID"] + POPS4),
     "popgen_predefined": ("popgenWindows", ["--windType", "predefined", "--windCoords", "@COORDS@", "-m", "20", "-f", "phased",
                                             "--writeFailedWindows", "--addWindowID"] + POPS4),
+    "popgen_exclude_file": ("popgenWindows", ["-w", "5000", "-m", "50", "-f", "phased", "--exclude", "@EXCLUDE@", "--addWindowID"]
+                            + POPS4),
+    "abba_headerless_file": ("ABBABABAwindows", ["-w", "8000", "-m", "30", "-f", "phased", "--minData", "0.5", "--header", "@HEADER@",
+                                                 "@NOHDR@"] + P4),
     "popgen_popfreq": ("popgenWindows", ["-w", "9000", "-m", "50", "-f", "phased", "--analysis", "popFreq", "popDist", "popPairDist",
                                          "--writeFailedWindows"] + POPS4),
     "popgen_all_analyses": ("popgenWindows", ["-w", "9000", "-m", "50", "-f", "phased", "--analysis", "popDist", "popPairDist",
@@ -140,7 +151,9 @@ MG_CASES = {
 @pytest.mark.parametrize("case", list(MG_CASES))
 def test_command_lines_on_n_ranks_equal_one_device_cpu(mg_input, case, world, monkeypatch, tmp_path):
     module, argv = MG_CASES[case]
-    base = [mg_input["coords"] if x == "@COORDS@" else x for x in argv] + ["-g", mg_input["geno"], "--popsFile", mg_input["pops"]]
+    sub = {"@COORDS@": mg_input["coords"], "@EXCLUDE@": mg_input["exclude"], "@HEADER@": mg_input["header"]}
+    base = [sub.get(x, x) for x in argv if x != "@NOHDR@"]
+    base += ["-g", mg_input["nohdr"] if "@NOHDR@" in argv else mg_input["geno"], "--popsFile", mg_input["pops"]]
     if module == "distMat":
         base = [x for x in base if x != "--popsFile" and x != mg_input["pops"]]
     if module == "sfs":                            # -i / -p / --pref instead of -g / -p / -o
